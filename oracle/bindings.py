@@ -1,0 +1,159 @@
+"""ctypes bindings for the CPU checkers.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module; the product package (hvqm4_b200/) never does.
+
+  RefDecoder    -> oracle/_ref/libhvqm4_ref.so, the unmodified reference compiled
+                   from /root/reference by oracle/Makefile (kind "reference")
+  PortDecoder   -> oracle/liboracle_port.so, our own C restatement (kind "port")
+"""
+from __future__ import annotations
+
+import ctypes
+import hashlib
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_LIB = os.path.join(_HERE, "_ref", "libhvqm4_ref.so")
+PORT_LIB = os.path.join(_HERE, "liboracle_port.so")
+
+I_FRAME, P_FRAME, B_FRAME = 0x10, 0x20, 0x30
+
+
+def build(ref: bool = True, port: bool = True) -> None:
+    targets = []
+    if port and os.path.exists(os.path.join(_HERE, "hvqm4_oracle.c")):
+        targets.append("port")
+    if ref:
+        targets.append("ref")
+    if targets:
+        subprocess.check_call(["make", "-s", "-C", _HERE] + targets)
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_LIB)
+
+
+def have_port() -> bool:
+    return os.path.exists(PORT_LIB)
+
+
+class _Decoder:
+    """Common walker API: open(data) -> iterate frames -> planar YUV bytes."""
+
+    _prefix = ""
+    _path = ""
+    _libs: dict = {}
+
+    def __init__(self, data: bytes):
+        lib = self._lib()
+        self._buf = ctypes.create_string_buffer(data, len(data))   # keep alive
+        self._h = getattr(lib, self._prefix + "open")(self._buf, len(data))
+        if not self._h:
+            raise ValueError("not a HVQM4 stream")
+        info = (ctypes.c_int32 * 6)()
+        getattr(lib, self._prefix + "info")(self._h, info)
+        self.width, self.height, self.n_frames, self.version, self.picsize, self.n_gops = list(info)
+        self._out = (ctypes.c_uint8 * self.picsize)()
+
+    @classmethod
+    def _lib(cls):
+        lib = cls._libs.get(cls._path)
+        if lib is None:
+            lib = ctypes.CDLL(cls._path)
+            p = cls._prefix
+            getattr(lib, p + "open").restype = ctypes.c_void_p
+            getattr(lib, p + "open").argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+            getattr(lib, p + "close").argtypes = [ctypes.c_void_p]
+            getattr(lib, p + "info").argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)]
+            getattr(lib, p + "decode_next").argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)]
+            getattr(lib, p + "decode_next").restype = ctypes.c_int
+            getattr(lib, p + "section_usage").argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
+            getattr(lib, p + "get_map").argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)]
+            getattr(lib, p + "get_nest").argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+            getattr(lib, p + "bench").restype = ctypes.c_double
+            getattr(lib, p + "bench").argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
+            getattr(lib, p + "bench_mp").argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+            getattr(lib, p + "bench_mp").restype = ctypes.c_int
+            cls._libs[cls._path] = lib
+        return lib
+
+    def close(self):
+        if self._h:
+            getattr(self._lib(), self._prefix + "close")(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def decode_next(self):
+        """-> (frame_type, disp_id, display_index, yuv bytes) or None at end of stream."""
+        meta = (ctypes.c_int32 * 4)()
+        rc = getattr(self._lib(), self._prefix + "decode_next")(self._h, self._out, meta)
+        if rc == 0:
+            return None
+        if rc < 0:
+            raise ValueError(f"container error {rc}")
+        return meta[0], meta[1], meta[2], bytes(self._out)
+
+    def frames(self):
+        while True:
+            f = self.decode_next()
+            if f is None:
+                return
+            yield f
+
+    def section_usage(self):
+        c = (ctypes.c_int32 * 17)()
+        s = (ctypes.c_int32 * 17)()
+        getattr(self._lib(), self._prefix + "section_usage")(self._h, c, s)
+        return list(c), list(s)
+
+    def get_map(self, plane: int):
+        dims = (ctypes.c_int32 * 2)()
+        getattr(self._lib(), self._prefix + "get_map")(self._h, plane, None, dims)
+        buf = (ctypes.c_uint8 * (dims[0] * dims[1] * 2))()
+        getattr(self._lib(), self._prefix + "get_map")(self._h, plane, buf, dims)
+        return dims[0], dims[1], bytes(buf)
+
+    def get_nest(self) -> bytes:
+        buf = (ctypes.c_uint8 * (70 * 38))()
+        getattr(self._lib(), self._prefix + "get_nest")(self._h, buf)
+        return bytes(buf)
+
+    @classmethod
+    def md5s(cls, data: bytes):
+        d = cls(data)
+        out = [(t, disp, hashlib.md5(yuv).hexdigest()) for t, disp, _, yuv in d.frames()]
+        d.close()
+        return out
+
+    @classmethod
+    def bench(cls, data: bytes, reps: int = 1):
+        """Single process: (seconds inside Decode?pic calls, frames)."""
+        n = ctypes.c_int64()
+        t = getattr(cls._lib(), cls._prefix + "bench")(data, len(data), reps, ctypes.byref(n))
+        return t, n.value
+
+    @classmethod
+    def bench_mp(cls, data: bytes, nproc: int, reps: int = 1):
+        """nproc forked workers: (wall seconds, sum of in-decode seconds, total frames)."""
+        out = (ctypes.c_double * 3)()
+        rc = getattr(cls._lib(), cls._prefix + "bench_mp")(data, len(data), nproc, reps, out)
+        if rc:
+            raise RuntimeError(f"bench_mp failed {rc}")
+        return out[0], out[1], int(out[2])
+
+
+class RefDecoder(_Decoder):
+    _prefix = "ref_"
+    _path = REF_LIB
+
+
+class PortDecoder(_Decoder):
+    _prefix = "port_"
+    _path = PORT_LIB
