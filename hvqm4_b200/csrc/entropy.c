@@ -1,0 +1,961 @@
+/*
+ * entropy.c -- host serial stage: HVQM4 picture bitstream -> symbol buffer (symbuf.h).
+ *
+ * Written from scratch; the reference lines each routine corresponds to are cited as
+ * "h4m:N" (= /root/reference/h4m_audio_decode.c line N).  Differences from the
+ * reference by design:
+ *   - the bit reader is a 64-bit left-aligned window refilled 8 bytes at a time, and
+ *     is bounded by the declared section size (the reference reads BE32 words with no
+ *     bounds, h4m:552-602); both consume the same MSB-first bit sequence;
+ *   - Huffman codes are decoded through a 2^10-entry prefix table rebuilt per tree,
+ *     falling back to a node walk for longer codes (the reference walks the tree bit
+ *     by bit, h4m:644-651);
+ *   - all parsing runs to completion before any pixel work: pass 2 of a P/B picture
+ *     (h4m:1922-1967) only resolves motion vectors and copies each block's side data
+ *     into its slot of the work-ordered symbol buffer;
+ *   - malformed input raises SYM_ERR_* bits instead of reading out of bounds.
+ */
+#include "entropy.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ bit reader */
+
+typedef struct
+{
+    const uint8_t *base, *p, *end;
+    uint64_t buf;   /* unread bits, left aligned */
+    int n;          /* number of valid bits in buf */
+} BR;
+
+static inline uint32_t rd_be32(const uint8_t *p)
+{
+    return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
+}
+
+static inline void br_open(BR *b, const uint8_t *base, uint32_t size)
+{
+    b->base = b->p = base;
+    b->end = base ? base + size : base;
+    b->buf = 0;
+    b->n = 0;
+}
+
+static inline void br_refill(BR *b)
+{
+    if (b->end - b->p >= 8)
+    {
+        uint64_t w;
+        memcpy(&w, b->p, 8);
+        w = __builtin_bswap64(w);
+        b->buf |= w >> b->n;
+        int adv = (63 - b->n) >> 3;
+        b->p += adv;
+        b->n += adv * 8;
+    }
+    else
+    {
+        while (b->n <= 56)
+        {
+            uint64_t byte = b->p < b->end ? *b->p : 0;   /* zeros past the end; checked by br_overrun() */
+            b->p++;
+            b->buf |= byte << (56 - b->n);
+            b->n += 8;
+        }
+    }
+}
+
+static inline uint32_t br_bit(BR *b)
+{
+    if (b->n < 1) br_refill(b);
+    uint32_t v = (uint32_t)(b->buf >> 63);
+    b->buf <<= 1;
+    b->n -= 1;
+    return v;
+}
+
+static inline uint32_t br_bits(BR *b, int k)   /* 0 <= k <= 16 */
+{
+    if (k == 0) return 0;
+    if (b->n < k) br_refill(b);
+    uint32_t v = (uint32_t)(b->buf >> (64 - k));
+    b->buf <<= k;
+    b->n -= k;
+    return v;
+}
+
+/* bits consumed so far, and whether the reader went past the section */
+static inline int64_t br_pos(const BR *b) { return (int64_t)(b->p - b->base) * 8 - b->n; }
+static inline int br_overrun(const BR *b) { return br_pos(b) > (int64_t)(b->end - b->base) * 8; }
+
+/* ------------------------------------------------------------------ Huffman (h4m:385-394, 607-651) */
+
+#define HT_BITS 10
+
+typedef struct { int16_t val; uint8_t len; uint8_t walk; } HEnt;
+
+typedef struct
+{
+    int32_t leaf[256];       /* value per leaf byte; persists across pictures like Tree.array[0][0..255] */
+    int16_t kid[2][256];     /* children of internal node i (node id 256+i) */
+    int root;
+    int used;
+    int bad;
+    HEnt tab[1 << HT_BITS];
+} HTab;
+
+static int ht_parse(HTab *t, BR *b, int is_signed, int scale, int depth)
+{
+    if (br_bit(b) == 0)
+    {
+        uint32_t byte = br_bits(b, 8);
+        int32_t v = (is_signed && byte > 0x7F) ? (int32_t)byte - 256 : (int32_t)byte;
+        t->leaf[byte] = (int32_t)(int16_t)((uint32_t)v << scale);   /* int16_t symbol <<= scale, h4m:613-617 */
+        return (int)byte;
+    }
+    if (t->used >= 256 || depth > 300 || br_overrun(b))
+    {
+        t->bad = 1;
+        return 0;
+    }
+    int node = t->used++;
+    int a = ht_parse(t, b, is_signed, scale, depth + 1);
+    int c = ht_parse(t, b, is_signed, scale, depth + 1);
+    t->kid[0][node] = (int16_t)a;
+    t->kid[1][node] = (int16_t)c;
+    return node + 256;
+}
+
+static void ht_fill(HTab *t, int node, int depth, uint32_t code)
+{
+    if (node < 256)
+    {
+        HEnt e = {(int16_t)t->leaf[node], (uint8_t)depth, 0};
+        uint32_t lo = code << (HT_BITS - depth), hi = (code + 1) << (HT_BITS - depth);
+        for (uint32_t i = lo; i < hi; ++i) t->tab[i] = e;
+        return;
+    }
+    if (depth == HT_BITS)
+    {
+        HEnt e = {(int16_t)node, HT_BITS, 1};
+        t->tab[code] = e;
+        return;
+    }
+    ht_fill(t, t->kid[0][node - 256], depth + 1, code << 1);
+    ht_fill(t, t->kid[1][node - 256], depth + 1, code << 1 | 1);
+}
+
+/* readTree, h4m:632-642: an empty leader section leaves root = 0, i.e. every symbol
+   decodes to the stale leaf[0] without consuming bits. */
+static void ht_read(HTab *t, BR *leader, uint32_t leader_size, int is_signed, int scale)
+{
+    t->used = 0;
+    t->bad = 0;
+    t->root = leader_size ? ht_parse(t, leader, is_signed, scale, 0) : 0;
+    if (t->bad) t->root = 0;
+    ht_fill(t, t->root, 0, 0);
+}
+
+static inline int32_t ht_get(const HTab *t, BR *b)
+{
+    if (b->n < 32) br_refill(b);
+    HEnt e = t->tab[b->buf >> (64 - HT_BITS)];
+    b->buf <<= e.len;
+    b->n -= e.len;
+    if (!e.walk) return e.val;
+    int node = e.val;
+    while (node >= 256) node = t->kid[br_bit(b)][node - 256];
+    return t->leaf[node];
+}
+
+/* decodeSOvfSym, h4m:654-664 */
+static inline int32_t ht_get_sovf(const HTab *t, BR *b, int32_t lo, int32_t hi)
+{
+    int32_t sum = 0, v;
+    do
+    {
+        v = ht_get(t, b);
+        sum += v;
+    } while ((v <= lo || v >= hi) && !br_overrun(b));
+    return sum;
+}
+
+/* decodeUOvfSym, h4m:667-677 */
+static inline int32_t ht_get_uovf(const HTab *t, BR *b)
+{
+    int32_t sum = 0, v;
+    do
+    {
+        v = ht_get(t, b);
+        sum += v;
+    } while (v >= 255 && !br_overrun(b));
+    return sum;
+}
+
+/* ------------------------------------------------------------------ stream state */
+
+enum { T_DC = 0, T_RUN = 1, T_SCALE = 2, T_BNUM = 3, T_MV = 4, T_MCB = 5 };   /* tree sharing, h4m:977-999 */
+
+typedef struct { const uint8_t *base; uint32_t size, pos; } ByteSec;   /* fixvl: plain byte stream */
+
+struct H4Seq
+{
+    int width, height, version15;
+    int bw[3], bh[3], stride[3];
+    int mbw, mbh, nseg;
+    size_t map_cells[3];
+    uint8_t *type[3], *dc[3];            /* bordered, persistent (h4m:1001-1040) */
+    uint8_t nest[SYM_NEST_BYTES];        /* packed nibbles of the last I picture's nest */
+    HTab tree[6];
+    uint32_t *blk_off[3];                /* side-word offset of every block (work order) */
+    uint32_t *seg;                       /* nseg*mbh + 1 */
+    uint32_t errors_total;
+
+    /* per picture, between parse_begin and parse_finish */
+    int pic_type;
+    uint32_t err;
+    uint32_t n_side;
+    int need_nest;
+    int dc_shift, unk_shift, rb[2][2];
+    int32_t dc_lo, dc_hi;
+    BR bn[2], bnr[2], dcv[3], sc[3], rle[3], mvh, mvv, mcbt, mcbp;
+    ByteSec fix[3];
+    size_t blob_bytes;
+    SymHeader hdr;
+};
+
+static inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+H4Seq *h4e_seq_create(int width, int height, int h_samp, int v_samp, int version15)
+{
+    /* 4:2:0 landscape only: the only layout HVQM4 content uses (h4m:872,896; README:23) */
+    if (width <= 0 || height <= 0 || (width & 7) || (height & 7) || h_samp != 2 || v_samp != 2 || width < height)
+        return NULL;
+    if (width > 8192 || height > 8192)
+        return NULL;
+    H4Seq *s = calloc(1, sizeof *s);
+    if (!s) return NULL;
+    s->width = width;
+    s->height = height;
+    s->version15 = version15 ? 1 : 0;
+    s->mbw = width / 8;
+    s->mbh = height / 8;
+    s->nseg = (s->mbw + SYM_SEG_MCBS - 1) / SYM_SEG_MCBS;
+    for (int p = 0; p < 3; ++p)
+    {
+        int sh = p ? 1 : 0;
+        s->bw[p] = (width >> sh) / 4;
+        s->bh[p] = (height >> sh) / 4;
+        s->stride[p] = s->bw[p] + 2;
+        s->map_cells[p] = (size_t)s->stride[p] * (s->bh[p] + 2);
+        s->type[p] = malloc(s->map_cells[p]);
+        s->dc[p] = malloc(s->map_cells[p]);
+        s->blk_off[p] = calloc((size_t)s->bw[p] * s->bh[p], sizeof(uint32_t));
+        /* border cells {0x7F, 0xFF} (h4m:951-955); payload starts zeroed */
+        memset(s->type[p], 0, s->map_cells[p]);
+        memset(s->dc[p], 0, s->map_cells[p]);
+        for (int y = 0; y < s->bh[p] + 2; ++y)
+            for (int x = 0; x < s->stride[p]; ++x)
+                if (y == 0 || y == s->bh[p] + 1 || x == 0 || x == s->stride[p] - 1)
+                {
+                    s->type[p][y * s->stride[p] + x] = 0xFF;
+                    s->dc[p][y * s->stride[p] + x] = 0x7F;
+                }
+    }
+    s->seg = calloc((size_t)s->nseg * s->mbh + 1, sizeof(uint32_t));
+    return s;
+}
+
+void h4e_seq_destroy(H4Seq *s)
+{
+    if (!s) return;
+    for (int p = 0; p < 3; ++p)
+    {
+        free(s->type[p]);
+        free(s->dc[p]);
+        free(s->blk_off[p]);
+    }
+    free(s->seg);
+    free(s);
+}
+
+void h4e_seq_set_version(H4Seq *s, int version15) { s->version15 = version15 ? 1 : 0; }
+uint32_t h4e_seq_errors(const H4Seq *s) { return s->errors_total; }
+size_t h4e_frame_bytes(const H4Seq *s) { return (size_t)s->width * s->height * 3 / 2; }
+
+void h4e_seq_dims(const H4Seq *s, int out[6])
+{
+    out[0] = s->width; out[1] = s->height; out[2] = s->mbw; out[3] = s->mbh; out[4] = s->nseg; out[5] = s->version15;
+}
+
+static inline size_t cell_at(const H4Seq *s, int p, int bx, int by) { return (size_t)(by + 1) * s->stride[p] + bx + 1; }
+
+/* setCode, h4m:1061-1071, with bounds */
+static void open_section(H4Seq *s, const uint8_t *data, size_t data_len, uint32_t off, const uint8_t **base, uint32_t *size)
+{
+    *base = NULL;
+    *size = 0;
+    if ((size_t)off + 4 > data_len)
+    {
+        s->err |= SYM_ERR_TRUNCATED;
+        return;
+    }
+    uint32_t sz = rd_be32(data + off);
+    if (sz == 0) return;
+    if ((size_t)off + 4 + sz > data_len)
+    {
+        s->err |= SYM_ERR_TRUNCATED;
+        sz = (uint32_t)(data_len - off - 4);
+        if (sz == 0) return;
+    }
+    *base = data + off + 4;
+    *size = sz;
+}
+
+static void open_bits(H4Seq *s, BR *b, const uint8_t *data, size_t len, uint32_t off)
+{
+    const uint8_t *base;
+    uint32_t size;
+    open_section(s, data, len, off, &base, &size);
+    br_open(b, base, size);
+}
+
+static void open_bytes(H4Seq *s, ByteSec *b, const uint8_t *data, size_t len, uint32_t off)
+{
+    open_section(s, data, len, off, &b->base, &b->size);
+    b->pos = 0;
+}
+
+/* ------------------------------------------------------------------ work-order offsets */
+
+/* Assigns every block its slot in the side-word array, in the order the warps of
+   recon.cu walk the picture (see symbuf.h), and fills the segment table. */
+static void assign_offsets(H4Seq *s, int is_ipic)
+{
+    uint32_t word = 0;
+    int need_nest = 0;
+    for (int row = 0; row < s->mbh; ++row)
+        for (int sg = 0; sg < s->nseg; ++sg)
+        {
+            s->seg[row * s->nseg + sg] = word;
+            int mx0 = sg * SYM_SEG_MCBS, mx1 = mx0 + SYM_SEG_MCBS;
+            if (mx1 > s->mbw) mx1 = s->mbw;
+            for (int half = 0; half < 2; ++half)
+            {
+                int by = row * 2 + half;
+                const uint8_t *ty = s->type[0] + cell_at(s, 0, 0, by);
+                uint32_t *off = s->blk_off[0] + (size_t)by * s->bw[0];
+                for (int bx = mx0 * 2; bx < mx1 * 2; ++bx)
+                {
+                    uint32_t t = ty[bx], n = sym_side_words(t, is_ipic);
+                    off[bx] = word;
+                    word += n;
+                    if (n && !(t & 0x60 & (is_ipic ? 0 : 0xFF)) && (is_ipic ? t : (t & 0xF)) != 6) need_nest = 1;
+                }
+            }
+            for (int p = 1; p < 3; ++p)
+            {
+                const uint8_t *ty = s->type[p] + cell_at(s, p, 0, row);
+                uint32_t *off = s->blk_off[p] + (size_t)row * s->bw[p];
+                for (int bx = mx0; bx < mx1; ++bx)
+                {
+                    uint32_t t = ty[bx], n = sym_side_words(t, is_ipic);
+                    off[bx] = word;
+                    word += n;
+                    if (n && !(t & 0x60 & (is_ipic ? 0 : 0xFF)) && (is_ipic ? t : (t & 0xF)) != 6) need_nest = 1;
+                }
+            }
+        }
+    s->seg[s->nseg * s->mbh] = word;
+    s->n_side = word;
+    s->need_nest = is_ipic ? 1 : need_nest;
+}
+
+static void plan_blob(H4Seq *s)
+{
+    SymHeader *h = &s->hdr;
+    memset(h, 0, sizeof *h);
+    h->magic = SYM_MAGIC;
+    h->width = (uint16_t)s->width;
+    h->height = (uint16_t)s->height;
+    h->pic_type = (uint8_t)s->pic_type;
+    h->version15 = (uint8_t)s->version15;
+    h->dc_shift = (uint8_t)s->dc_shift;
+    h->unk_shift = (uint8_t)s->unk_shift;
+    h->has_nest = (uint8_t)s->need_nest;
+    h->mcb_w = (uint16_t)s->mbw;
+    h->mcb_h = (uint16_t)s->mbh;
+    h->nseg = (uint16_t)s->nseg;
+    size_t at = sizeof(SymHeader);
+    h->off_seg = (uint32_t)at;
+    at = align16(at + ((size_t)s->nseg * s->mbh + 1) * 4);
+    if (s->pic_type != SYM_PIC_I)
+    {
+        h->off_mv = (uint32_t)at;
+        at = align16(at + (size_t)s->mbw * s->mbh * 4);
+    }
+    for (int p = 0; p < 3; ++p)
+    {
+        h->off_type[p] = (uint32_t)at;
+        at = align16(at + s->map_cells[p]);
+    }
+    for (int p = 0; p < 3; ++p)
+    {
+        h->off_dc[p] = (uint32_t)at;
+        at = align16(at + s->map_cells[p]);
+    }
+    if (s->need_nest)
+    {
+        h->off_nest = (uint32_t)at;
+        at = align16(at + SYM_NEST_BYTES);
+    }
+    h->off_side = (uint32_t)at;
+    h->n_side_words = s->n_side;
+    at = align16(at + (size_t)s->n_side * 4);
+    h->total_bytes = (uint32_t)at;
+    s->blob_bytes = at;
+}
+
+/* ------------------------------------------------------------------ I picture, symbol part */
+
+/* Ipic_BasisNumDec, h4m:1073-1130 */
+static void ipic_types(H4Seq *s)
+{
+    const HTab *tn = &s->tree[T_BNUM], *tr = &s->tree[T_RUN];
+    uint32_t run = 0;
+    for (int by = 0; by < s->bh[0]; ++by)
+    {
+        uint8_t *row = s->type[0] + cell_at(s, 0, 0, by);
+        for (int bx = 0; bx < s->bw[0]; ++bx)
+        {
+            if (run)
+            {
+                row[bx] = 0;
+                --run;
+                continue;
+            }
+            int32_t n = ht_get(tn, &s->bn[0]);
+            if ((int16_t)n == 0) run = (uint32_t)ht_get(tr, &s->bnr[0]);
+            row[bx] = (uint8_t)n;
+        }
+    }
+    run = 0;
+    for (int by = 0; by < s->bh[1]; ++by)
+    {
+        uint8_t *ru = s->type[1] + cell_at(s, 1, 0, by), *rv = s->type[2] + cell_at(s, 2, 0, by);
+        for (int bx = 0; bx < s->bw[1]; ++bx)
+        {
+            if (run)
+            {
+                ru[bx] = rv[bx] = 0;
+                --run;
+                continue;
+            }
+            int32_t n = ht_get(tn, &s->bn[1]);
+            if ((int16_t)n == 0) run = (uint32_t)ht_get(tr, &s->bnr[1]);
+            ru[bx] = n & 0xF;
+            rv[bx] = (n >> 4) & 0xF;
+        }
+    }
+}
+
+/* IpicDcvDec + getDeltaDC, h4m:1043-1058, 1132-1164 */
+static void ipic_dcs(H4Seq *s)
+{
+    const HTab *td = &s->tree[T_DC], *tr = &s->tree[T_RUN];
+    for (int p = 0; p < 3; ++p)
+    {
+        uint32_t run = 0;
+        for (int by = 0; by < s->bh[p]; ++by)
+        {
+            uint8_t *cur = s->dc[p] + cell_at(s, p, 0, by);
+            const uint8_t *up = cur - s->stride[p];
+            uint8_t v = up[0];
+            for (int bx = 0; bx < s->bw[p]; ++bx)
+            {
+                if (run) --run;
+                else
+                {
+                    uint32_t delta = (uint32_t)ht_get_sovf(td, &s->dcv[p], s->dc_lo, s->dc_hi);
+                    if (delta == 0) run = (uint32_t)ht_get(tr, &s->rle[p]);
+                    v = (uint8_t)(v + delta);
+                }
+                cur[bx] = v;
+                v = (uint8_t)((v + up[bx + 1] + 1) >> 1);
+            }
+        }
+    }
+}
+
+/* MakeNest, h4m:1166-1239 (including the mirror / zero-fill path), packed to nibbles */
+static void make_nest(H4Seq *s, int nx, int ny)
+{
+    uint8_t full[SYM_NEST_H][SYM_NEST_W];
+    int bw = s->bw[0], bh = s->bh[0];
+    int cols = bw < SYM_NEST_W ? bw : SYM_NEST_W, rows = bh < SYM_NEST_H ? bh : SYM_NEST_H;
+    int mcols = bw < SYM_NEST_W ? (SYM_NEST_W - bw < bw ? SYM_NEST_W - bw : bw) : 0;
+    int mrows = bh < SYM_NEST_H ? (SYM_NEST_H - bh < bh ? SYM_NEST_H - bh : bh) : 0;
+    /* keep the window inside the map even for a hostile header */
+    if (nx < 0 || nx + cols > bw) { nx = 0; s->err |= SYM_ERR_MV_RANGE; }
+    if (ny < 0 || ny + rows > bh) { ny = 0; s->err |= SYM_ERR_MV_RANGE; }
+    memset(full, 0, sizeof full);
+    for (int i = 0; i < rows; ++i)
+    {
+        const uint8_t *src = s->dc[0] + cell_at(s, 0, nx, ny + i);
+        for (int j = 0; j < cols; ++j) full[i][j] = (src[j] >> 4) & 0xF;
+        for (int j = 0; j < mcols; ++j) full[i][cols + j] = (src[cols - 1 - j] >> 4) & 0xF;
+    }
+    for (int i = 0; i < mrows; ++i) memcpy(full[rows + i], full[rows - 1 - i], SYM_NEST_W);
+    for (int i = 0; i < SYM_NEST_H; ++i)
+        for (int j = 0; j < SYM_NEST_ROW_BYTES; ++j)
+            s->nest[i * SYM_NEST_ROW_BYTES + j] = (uint8_t)(full[i][2 * j] | full[i][2 * j + 1] << 4);
+}
+
+/* ------------------------------------------------------------------ side-word emitters */
+
+static inline int fix_has(H4Seq *s, int p, uint32_t n)
+{
+    if (s->fix[p].base && s->fix[p].pos + n <= s->fix[p].size) return 1;
+    s->err |= SYM_ERR_TRUNCATED;
+    return 0;
+}
+
+/* n x (descriptor, scale symbol): read16(fixvl) + decodeHuff(bufTree0), h4m:691,726 / 738,767 */
+static inline void emit_bases(H4Seq *s, int p, uint32_t n, uint32_t *dst)
+{
+    const HTab *ts = &s->tree[T_SCALE];
+    for (uint32_t k = 0; k < n; ++k)
+    {
+        uint32_t desc = 0;
+        if (fix_has(s, p, 2))
+        {
+            const uint8_t *f = s->fix[p].base + s->fix[p].pos;
+            desc = (uint32_t)f[0] << 8 | f[1];
+            s->fix[p].pos += 2;
+        }
+        uint32_t sym = (uint32_t)ht_get(ts, &s->sc[p]);
+        dst[k] = desc | ((sym >> 2) & 0xFF) << 16;
+    }
+}
+
+/* OrgBlock, h4m:543-549 */
+static inline void emit_raw(H4Seq *s, int p, uint32_t *dst)
+{
+    if (fix_has(s, p, 16))
+    {
+        memcpy(dst, s->fix[p].base + s->fix[p].pos, 16);
+        s->fix[p].pos += 16;
+    }
+    else
+        memset(dst, 0x80, 16);
+}
+
+/* the two decodeSOvfSym reads of PrediAotBlock, h4m:1405-1406, pre-shifted by dc_shift */
+static inline void emit_pair(H4Seq *s, int p, uint32_t *dst)
+{
+    const HTab *td = &s->tree[T_DC];
+    int32_t a = ht_get_sovf(td, &s->dcv[p], s->dc_lo, s->dc_hi) >> s->dc_shift;
+    int32_t f = ht_get_sovf(td, &s->dcv[p], s->dc_lo, s->dc_hi) >> s->dc_shift;
+    if (a < -32768 || a > 32767 || f < -32768 || f > 32767)
+    {
+        s->err |= SYM_ERR_PAIR_RANGE;
+        a = a < -32768 ? -32768 : a > 32767 ? 32767 : a;
+        f = f < -32768 ? -32768 : f > 32767 ? 32767 : f;
+    }
+    *dst = ((uint32_t)a & 0xFFFF) | (uint32_t)f << 16;
+}
+
+static inline void emit_intra_block(H4Seq *s, int p, uint32_t t, uint32_t *dst)
+{
+    if (t == 6) emit_raw(s, p, dst);
+    else if (t != 0 && t != 8) emit_bases(s, p, t, dst);
+}
+
+/* ------------------------------------------------------------------ P/B picture, pass 1 */
+
+typedef struct { uint32_t value, count; } RunLen;
+
+static const int SUBX[4] = {0, 0, 1, 1}, SUBY[4] = {0, 1, 1, 0};   /* TL, BL, BR, TR: mcb_offset, h4m:862-865 */
+
+/* spread_PB_descMap, h4m:1742-1776, with decode_PB_dc (1649), decode_PB_cc (1670),
+   getMCBtype (1596), getMCBproc (1613), initMCBtype/proc (1551-1569) */
+static void pb_pass1(H4Seq *s)
+{
+    static const uint8_t next_type[2][4] = {{1, 2, 0, 0}, {2, 0, 1, 0}};   /* mcbtypetrans, h4m:1591-1594 */
+    const HTab *tm = &s->tree[T_MCB], *td = &s->tree[T_DC], *tn = &s->tree[T_BNUM], *tr = &s->tree[T_RUN];
+    RunLen proc = {0, 0}, type = {0, 0};
+    if (s->mcbp.base)
+    {
+        proc.value = br_bit(&s->mcbp);
+        proc.count = (uint32_t)ht_get_uovf(tm, &s->mcbp);
+    }
+    if (s->mcbt.base)
+    {
+        type.value = br_bits(&s->mcbt, 2);
+        type.count = (uint32_t)ht_get_uovf(tm, &s->mcbt);
+    }
+    else
+        s->err |= SYM_ERR_TRUNCATED;   /* the reference would use an uninitialised type here */
+    uint32_t run_y = 0, run_c = 0;
+    uint32_t acc[3] = {0x7F, 0x7F, 0x7F};
+    const int st0 = s->stride[0];
+    for (int my = 0; my < s->mbh; ++my)
+    {
+        uint8_t *ty0 = s->type[0] + cell_at(s, 0, 0, my * 2), *dc0 = s->dc[0] + cell_at(s, 0, 0, my * 2);
+        uint8_t *ty1 = s->type[1] + cell_at(s, 1, 0, my), *dc1 = s->dc[1] + cell_at(s, 1, 0, my);
+        uint8_t *ty2 = s->type[2] + cell_at(s, 2, 0, my), *dc2 = s->dc[2] + cell_at(s, 2, 0, my);
+        for (int mx = 0; mx < s->mbw; ++mx)
+        {
+            if (type.count == 0 && s->mcbt.base)
+            {
+                type.value = next_type[br_bit(&s->mcbt)][type.value & 3];
+                type.count = (uint32_t)ht_get_uovf(tm, &s->mcbt);
+            }
+            --type.count;
+            uint32_t mt = type.value;
+            if (mt == 3 || (mt == 2 && s->pic_type == SYM_PIC_P))
+            {
+                /* type 3 indexes outside mcbtypetrans in the reference; type 2 in a P picture
+                   would predict from the picture being written (h4m:2060) */
+                s->err |= SYM_ERR_MCB_TYPE;
+                mt = 1;
+            }
+            uint32_t pr = 0;
+            const int lx = mx * 2;
+            if (mt == 0)
+            {
+                for (int k = 0; k < 4; ++k)
+                {
+                    acc[0] += (uint32_t)ht_get_sovf(td, &s->dcv[0], s->dc_lo, s->dc_hi);
+                    dc0[SUBY[k] * st0 + lx + SUBX[k]] = (uint8_t)acc[0];
+                }
+                acc[1] += (uint32_t)ht_get_sovf(td, &s->dcv[1], s->dc_lo, s->dc_hi);
+                dc1[mx] = (uint8_t)acc[1];
+                acc[2] += (uint32_t)ht_get_sovf(td, &s->dcv[2], s->dc_lo, s->dc_hi);
+                dc2[mx] = (uint8_t)acc[2];
+            }
+            else
+            {
+                acc[0] = acc[1] = acc[2] = 0x7F;
+                if (proc.count == 0 && s->mcbp.base)
+                {
+                    proc.value ^= 1;
+                    proc.count = (uint32_t)ht_get_uovf(tm, &s->mcbp);
+                }
+                --proc.count;
+                pr = proc.value & 1;
+            }
+            const uint8_t tag = (uint8_t)(mt << 5 | pr << 4);
+            if (pr)
+            {
+                for (int k = 0; k < 4; ++k) ty0[SUBY[k] * st0 + lx + SUBX[k]] = tag;
+                ty1[mx] = ty2[mx] = tag;
+                continue;
+            }
+            for (int k = 0; k < 4; ++k)
+            {
+                uint8_t *c = &ty0[SUBY[k] * st0 + lx + SUBX[k]];
+                if (run_y)
+                {
+                    *c = tag;
+                    --run_y;
+                    continue;
+                }
+                int32_t n = (int16_t)ht_get(tn, &s->bn[0]);
+                if (n)
+                {
+                    if (n & ~0xF)
+                    {
+                        s->err |= SYM_ERR_MCB_TYPE;   /* would corrupt the macroblock bits, h4m:1701 */
+                        n &= 0xF;
+                    }
+                    *c = (uint8_t)(tag | n);
+                }
+                else
+                {
+                    *c = tag;
+                    run_y = (uint32_t)ht_get(tr, &s->bnr[0]);
+                }
+            }
+            if (run_c)
+            {
+                ty1[mx] = ty2[mx] = tag;
+                --run_c;
+            }
+            else
+            {
+                int32_t n = (int16_t)ht_get(tn, &s->bn[1]);
+                if (n)
+                {
+                    ty1[mx] = (uint8_t)(tag | (n & 0xF));
+                    ty2[mx] = (uint8_t)(tag | ((n >> 4) & 0xF));
+                }
+                else
+                {
+                    ty1[mx] = ty2[mx] = tag;
+                    run_c = (uint32_t)ht_get(tr, &s->bnr[1]);
+                }
+            }
+        }
+    }
+}
+
+/* getMVector, h4m:1846-1860 */
+static inline void read_mv(H4Seq *s, BR *b, int32_t *mv, int rbits)
+{
+    if (rbits > 16) rbits = 16;
+    int32_t lim = 1 << (rbits + 5);
+    int32_t v = ht_get(&s->tree[T_MV], b) * (1 << rbits);
+    v += (int32_t)br_bits(b, rbits);
+    *mv += v;
+    if (*mv >= lim) *mv -= lim << 1;
+    else if (*mv < -lim) *mv += lim << 1;
+}
+
+/*
+ * Checks that every address the reconstruction of this macroblock will read lies inside
+ * the reference surface.  The reference addresses frames linearly with no clamping
+ * (h4m:1344, 1866, 1897), so "inside" means inside the contiguous Y|U|V buffer, not inside
+ * the plane; recon.cu addresses the same way, which keeps even row-wrapping vectors exact.
+ */
+static int mcb_refs_in_surface(const H4Seq *s, int32_t rx, int32_t ry, int needs_window)
+{
+    const int64_t total = (int64_t)s->width * s->height * 3 / 2;
+    int64_t plane_base = 0;
+    int hx = rx & 1, hy = ry & 1;
+    for (int p = 0; p < 3; ++p)
+    {
+        int sh = p ? 1 : 0;
+        int64_t w = s->width >> sh;
+        int32_t px = rx >> sh, py = ry >> sh;
+        if (s->version15) { hx = px & 1; hy = py & 1; }
+        int64_t first = plane_base + (int64_t)(py >> 1) * w + (px >> 1);
+        int span = p ? 4 : 8;
+        int64_t last = first + (int64_t)(span - 1 + hy) * w + span - 1 + hx;
+        if (first < 0 || last >= total) return 0;
+        plane_base += w * (s->height >> sh);
+    }
+    if (needs_window)
+    {
+        int64_t org = (int64_t)(rx / 2) + (int64_t)(ry / 2 - 16) * s->width - 32;
+        if (org < 0 || org + (int64_t)(SYM_NEST_H - 1) * s->width + SYM_NEST_W - 1 >= total) return 0;
+    }
+    return 1;
+}
+
+/* BpicPlaneDec pass 2, h4m:1922-1967, symbol part only */
+static void pb_pass2(H4Seq *s, int16_t *mv_out, uint32_t *side)
+{
+    int32_t mvx = 0, mvy = 0;
+    int cur_ref = -1;
+    const int st0 = s->stride[0];
+    for (int my = 0; my < s->mbh; ++my)
+    {
+        const uint8_t *ty0 = s->type[0] + cell_at(s, 0, 0, my * 2);
+        const uint8_t *ty1 = s->type[1] + cell_at(s, 1, 0, my), *ty2 = s->type[2] + cell_at(s, 2, 0, my);
+        const uint32_t *of0 = s->blk_off[0] + (size_t)(my * 2) * s->bw[0];
+        const uint32_t *of1 = s->blk_off[1] + (size_t)my * s->bw[1], *of2 = s->blk_off[2] + (size_t)my * s->bw[2];
+        for (int mx = 0; mx < s->mbw; ++mx)
+        {
+            const int lx = mx * 2;
+            const uint8_t tag = ty0[lx];
+            int16_t *mvp = mv_out + 2 * ((size_t)my * s->mbw + mx);
+            const int mt = (tag >> 5) & 3;
+            if (mt == 0)
+            {   /* MCBlockDecDCNest, h4m:1789-1827 */
+                mvp[0] = mvp[1] = 0;
+                for (int k = 0; k < 4; ++k)
+                    emit_intra_block(s, 0, ty0[SUBY[k] * st0 + lx + SUBX[k]] & 0xF, side + of0[SUBY[k] * s->bw[0] + lx + SUBX[k]]);
+                emit_intra_block(s, 1, ty1[mx] & 0xF, side + of1[mx]);
+                emit_intra_block(s, 2, ty2[mx] & 0xF, side + of2[mx]);
+                continue;
+            }
+            const int ref = mt - 1;
+            if (ref != cur_ref)
+            {   /* h4m:1943-1949 */
+                cur_ref = ref;
+                mvx = mvy = 0;
+            }
+            read_mv(s, &s->mvh, &mvx, s->rb[ref][0]);
+            read_mv(s, &s->mvv, &mvy, s->rb[ref][1]);
+            const int32_t rx = mx * 16 + mvx, ry = my * 16 + mvy;   /* h4m:1954-1955 */
+            int needs_window = 0;
+            if (!(tag & 0x10))
+            {   /* MCBlockDecMCNest, h4m:1871-1909 */
+                for (int k = 0; k < 6; ++k)
+                {
+                    int p = k < 4 ? 0 : k - 3;
+                    uint32_t nib, *dst;
+                    if (k < 4)
+                    {
+                        nib = ty0[SUBY[k] * st0 + lx + SUBX[k]] & 0xF;
+                        dst = side + of0[SUBY[k] * s->bw[0] + lx + SUBX[k]];
+                    }
+                    else
+                    {
+                        nib = (k == 4 ? ty1[mx] : ty2[mx]) & 0xF;
+                        dst = side + (k == 4 ? of1[mx] : of2[mx]);
+                    }
+                    if (nib == 6) emit_raw(s, p, dst);
+                    else if (nib)
+                    {
+                        emit_bases(s, p, nib - 1, dst);
+                        emit_pair(s, p, dst + nib - 1);
+                        if (nib > 1) needs_window = 1;
+                    }
+                }
+            }
+            if (rx < -32000 || rx > 32000 || ry < -32000 || ry > 32000 || !mcb_refs_in_surface(s, rx, ry, needs_window))
+            {
+                s->err |= SYM_ERR_MV_RANGE;
+                mvp[0] = mvp[1] = -32768;   /* poison: recon.cu paints the macroblock grey */
+            }
+            else
+            {
+                mvp[0] = (int16_t)rx;
+                mvp[1] = (int16_t)ry;
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ entry points */
+
+size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_t pic_len)
+{
+    s->pic_type = pic_type;
+    s->err = 0;
+    s->blob_bytes = 0;
+    const int is_i = pic_type == SYM_PIC_I;
+    const int nsec = is_i ? 16 : 17;
+    if (pic_type != SYM_PIC_I && pic_type != SYM_PIC_P && pic_type != SYM_PIC_B)
+    {
+        s->err |= SYM_ERR_GEOMETRY;
+        s->errors_total |= s->err;
+        return 0;
+    }
+    uint8_t zero_hdr[8 + 17 * 4] = {0};
+    if (pic_len < (size_t)(8 + nsec * 4))
+    {
+        s->err |= SYM_ERR_TRUNCATED;
+        pic = zero_hdr;
+        pic_len = sizeof zero_hdr;
+    }
+    const uint8_t *tab = pic + 8, *data = tab + nsec * 4;
+    const size_t dlen = pic_len - 8 - (size_t)nsec * 4;
+    int nest_x = 0, nest_y = 0;
+    if (is_i)
+    {   /* h4m:1973-1977: the I picture keeps dc_shift local; state->dc_shift is P/B only */
+        s->dc_shift = pic[0];
+        s->unk_shift = pic[1];
+        nest_x = pic[4] << 8 | pic[5];
+        nest_y = pic[6] << 8 | pic[7];
+    }
+    else
+    {   /* h4m:2021-2026 */
+        s->dc_shift = pic[0];
+        s->unk_shift = pic[1];
+        s->rb[0][0] = pic[2]; s->rb[0][1] = pic[3];
+        s->rb[1][0] = pic[4]; s->rb[1][1] = pic[5];
+    }
+    if (s->dc_shift > 7 || s->unk_shift > 24)
+    {   /* int16 leaf << dc_shift overflows beyond 7 (h4m:616); shifts >= 32 are undefined */
+        s->err |= SYM_ERR_GEOMETRY;
+        if (s->dc_shift > 7) s->dc_shift = 7;
+        if (s->unk_shift > 24) s->unk_shift = 24;
+    }
+    open_bits(s, &s->bn[0], data, dlen, rd_be32(tab + 0));
+    open_bits(s, &s->bnr[0], data, dlen, rd_be32(tab + 4));
+    open_bits(s, &s->bn[1], data, dlen, rd_be32(tab + 8));
+    open_bits(s, &s->bnr[1], data, dlen, rd_be32(tab + 12));
+    for (int p = 0; p < 3; ++p)
+    {
+        open_bits(s, &s->dcv[p], data, dlen, rd_be32(tab + 16 + 12 * p));
+        open_bits(s, &s->sc[p], data, dlen, rd_be32(tab + 20 + 12 * p));
+        open_bytes(s, &s->fix[p], data, dlen, rd_be32(tab + 24 + 12 * p));
+    }
+    if (is_i)
+        for (int p = 0; p < 3; ++p) open_bits(s, &s->rle[p], data, dlen, rd_be32(tab + 52 + 4 * p));
+    else
+    {
+        open_bits(s, &s->mvh, data, dlen, rd_be32(tab + 52));
+        open_bits(s, &s->mvv, data, dlen, rd_be32(tab + 56));
+        open_bits(s, &s->mcbt, data, dlen, rd_be32(tab + 60));
+        open_bits(s, &s->mcbp, data, dlen, rd_be32(tab + 64));
+    }
+    /* tree order as h4m:1996-1999 / 2045-2050 */
+    ht_read(&s->tree[T_BNUM], &s->bn[0], (uint32_t)(s->bn[0].end - s->bn[0].base), 0, 0);
+    ht_read(&s->tree[T_RUN], &s->bnr[0], (uint32_t)(s->bnr[0].end - s->bnr[0].base), 0, 0);
+    ht_read(&s->tree[T_DC], &s->dcv[0], (uint32_t)(s->dcv[0].end - s->dcv[0].base), 1, s->dc_shift);
+    ht_read(&s->tree[T_SCALE], &s->sc[0], (uint32_t)(s->sc[0].end - s->sc[0].base), 0, 2);
+    if (!is_i)
+    {
+        ht_read(&s->tree[T_MV], &s->mvh, (uint32_t)(s->mvh.end - s->mvh.base), 1, 0);
+        ht_read(&s->tree[T_MCB], &s->mcbt, (uint32_t)(s->mcbt.end - s->mcbt.base), 0, 0);
+    }
+    for (int t = 0; t < 6; ++t)
+        if (s->tree[t].bad) s->err |= SYM_ERR_BAD_TREE;
+    s->dc_hi = 0x7F * (1 << s->dc_shift);   /* h4m:2001-2002, 2052-2053 */
+    s->dc_lo = -0x80 * (1 << s->dc_shift);
+
+    if (is_i)
+    {
+        ipic_types(s);
+        ipic_dcs(s);
+        make_nest(s, nest_x, nest_y);
+    }
+    else
+        pb_pass1(s);
+    assign_offsets(s, is_i);
+    plan_blob(s);
+    return s->blob_bytes;
+}
+
+uint32_t h4e_parse_finish(H4Seq *s, uint8_t *blob)
+{
+    const SymHeader *h = &s->hdr;
+    const int is_i = s->pic_type == SYM_PIC_I;
+    if (s->blob_bytes == 0) return s->err;
+    uint32_t *side = (uint32_t *)(blob + h->off_side);
+    if (is_i)
+    {   /* IpicPlaneDec order: plane by plane, raster (h4m:2011-2015, 1487-1518) */
+        for (int p = 0; p < 3; ++p)
+            for (int by = 0; by < s->bh[p]; ++by)
+            {
+                const uint8_t *ty = s->type[p] + cell_at(s, p, 0, by);
+                const uint32_t *off = s->blk_off[p] + (size_t)by * s->bw[p];
+                for (int bx = 0; bx < s->bw[p]; ++bx)
+                    if (ty[bx] != 0 && ty[bx] != 8) emit_intra_block(s, p, ty[bx], side + off[bx]);
+            }
+    }
+    else
+        pb_pass2(s, (int16_t *)(blob + h->off_mv), side);
+
+    /* every reader must have stayed inside its section */
+    {
+        BR *all[] = {&s->bn[0], &s->bnr[0], &s->bn[1], &s->bnr[1], &s->dcv[0], &s->dcv[1], &s->dcv[2],
+                     &s->sc[0], &s->sc[1], &s->sc[2]};
+        for (size_t i = 0; i < sizeof all / sizeof *all; ++i)
+            if (br_overrun(all[i])) s->err |= SYM_ERR_TRUNCATED;
+        if (is_i)
+        {
+            for (int p = 0; p < 3; ++p)
+                if (br_overrun(&s->rle[p])) s->err |= SYM_ERR_TRUNCATED;
+        }
+        else if (br_overrun(&s->mvh) || br_overrun(&s->mvv) || br_overrun(&s->mcbt) || br_overrun(&s->mcbp))
+            s->err |= SYM_ERR_TRUNCATED;
+    }
+    memcpy(blob + h->off_seg, s->seg, ((size_t)s->nseg * s->mbh + 1) * 4);
+    for (int p = 0; p < 3; ++p)
+    {
+        memcpy(blob + h->off_type[p], s->type[p], s->map_cells[p]);
+        memcpy(blob + h->off_dc[p], s->dc[p], s->map_cells[p]);
+    }
+    if (h->has_nest) memcpy(blob + h->off_nest, s->nest, SYM_NEST_BYTES);
+    SymHeader out = *h;
+    out.errors = s->err;
+    memcpy(blob, &out, sizeof out);
+    s->errors_total |= s->err;
+    return s->err;
+}

@@ -1,0 +1,119 @@
+/*
+ * symbuf.h -- layout of the per-picture SYMBOL BUFFER, the only thing that crosses
+ * from the host serial stage (entropy.c) to the CUDA reconstruction kernels
+ * (recon.cu).  One picture = one contiguous, self-contained blob, so a batch of
+ * pictures is uploaded with a single cudaMemcpyAsync.
+ *
+ * The blob carries exactly what pixel reconstruction consumes in the reference
+ * (/root/reference/h4m_audio_decode.c, "h4m:N" below) and nothing that needs a bit
+ * reader:
+ *
+ *   type/dc maps   the reference's BlockData{value,type} maps (h4m:432-436) split into
+ *                  two byte planes per picture plane, each with the 1-cell border
+ *                  {dc 0x7F, type 0xFF} of h4m:951-955.  type byte layout as h4m:1296-1304:
+ *                  bits 6:5 macroblock type (0 intra, 1 past, 2 future), bit 4 proc,
+ *                  bits 3:0 block nibble (I pictures: the whole byte is the basis count).
+ *   mv table       per macroblock, absolute half-sample luma position of the prediction
+ *                  (ref_x, ref_y of h4m:1954-1955) as int16 x 2; predictor chain,
+ *                  wrap-around and reference switches (h4m:1846-1860,1943-1949) are
+ *                  already resolved by the host.
+ *   nest           the 70x38 4-bit nest of the last I picture (h4m:1166-1239), packed two
+ *                  samples per byte (even x in the low nibble); present in every I picture
+ *                  and in P/B pictures that contain intra AOT blocks.
+ *   side words     variable-length per-block data, one 32-bit word per item:
+ *                    basis word   bits 15:0  descriptor exactly as read from fixvl (h4m:691),
+ *                                 bits 23:16 scale symbol = decodeHuff(bufTree0) >> 2 (h4m:726)
+ *                    raw block    4 words = the 16 fixvl bytes of h4m:543-549, row by row
+ *                    pair word    predicted-AOT block: low 16 = S1 >> dc_shift, high 16 =
+ *                                 S2 >> dc_shift (both int16; h4m:1405-1406)
+ *                  A block owns  n  words (intra AOT with n bases),  4  words (raw),
+ *                  k  words (inter nibble k: k-1 bases + 1 pair word) or none.
+ *   segment table  side words are stored in GPU WORK ORDER, not bitstream order: the
+ *                  picture is cut into segments of 16 macroblocks of one macroblock row;
+ *                  inside a segment the order is: upper luma block row (32 blocks left to
+ *                  right), lower luma block row, 16 U blocks, 16 V blocks.  seg[i] is the
+ *                  word offset of segment i; a warp finds each block's words with a
+ *                  prefix sum over the per-block word counts, which are a pure function
+ *                  of the type byte (sym_side_words()).
+ */
+#ifndef HVQM4_SYMBUF_H
+#define HVQM4_SYMBUF_H
+
+#include <stdint.h>
+
+#define SYM_MAGIC 0x42533448u /* "H4SB" */
+#define SYM_SEG_MCBS 16       /* macroblocks per segment (= 32 luma blocks = one warp) */
+#define SYM_NEST_W 70
+#define SYM_NEST_H 38
+#define SYM_NEST_ROW_BYTES 35 /* packed nibbles */
+#define SYM_NEST_BYTES (SYM_NEST_ROW_BYTES * SYM_NEST_H)
+
+enum { SYM_PIC_I = 0x10, SYM_PIC_P = 0x20, SYM_PIC_B = 0x30 };
+
+/* error bits raised by the host stage (the SDK entry points return void) */
+enum
+{
+    SYM_ERR_TRUNCATED   = 1 << 0,  /* a section or tree ran past its declared size */
+    SYM_ERR_BAD_TREE    = 1 << 1,  /* tree with more than 256 internal nodes */
+    SYM_ERR_MCB_TYPE    = 1 << 2,  /* macroblock type 3, or type 2 inside a P picture */
+    SYM_ERR_MV_RANGE    = 1 << 3,  /* prediction or nest window leaves the frame surface */
+    SYM_ERR_PAIR_RANGE  = 1 << 4,  /* S1/S2 of a predicted-AOT block do not fit int16 */
+    SYM_ERR_GEOMETRY    = 1 << 5,  /* unsupported size / sampling */
+    SYM_ERR_OVERFLOW    = 1 << 6,  /* symbol buffer capacity exceeded */
+};
+
+typedef struct SymHeader
+{
+    uint32_t magic;
+    uint32_t total_bytes;      /* whole blob, multiple of 16 */
+    uint16_t width, height;    /* luma samples */
+    uint8_t  pic_type;         /* SYM_PIC_* */
+    uint8_t  version15;        /* 1: per-plane half-sample phase (h4m:1337-1343) */
+    uint8_t  dc_shift;         /* P/B only (h4m:2021) */
+    uint8_t  unk_shift;        /* h4m:1974, 2022 */
+    uint8_t  has_nest;
+    uint8_t  pad0[3];
+    uint32_t errors;           /* SYM_ERR_* */
+    uint16_t mcb_w, mcb_h;     /* macroblocks */
+    uint16_t nseg;             /* segments per macroblock row = ceil(mcb_w / 16) */
+    uint16_t pad1;
+    uint32_t off_type[3];      /* byte offsets from the blob start; bordered (bw+2)x(bh+2) */
+    uint32_t off_dc[3];
+    uint32_t off_mv;           /* int16[2] per macroblock; 0 for I pictures */
+    uint32_t off_seg;          /* uint32 per segment (+1 terminator) */
+    uint32_t off_nest;         /* SYM_NEST_BYTES; 0 if !has_nest */
+    uint32_t off_side;         /* uint32 words */
+    uint32_t n_side_words;
+    uint32_t pad2[13];
+} SymHeader;                   /* 128 bytes */
+
+#ifdef __cplusplus
+static_assert(sizeof(SymHeader) == 128, "SymHeader must be 128 bytes");
+#else
+_Static_assert(sizeof(SymHeader) == 128, "SymHeader must be 128 bytes");
+#endif
+
+#if defined(__CUDACC__)
+#define SYM_HD __host__ __device__ __forceinline__
+#else
+#define SYM_HD static inline
+#endif
+
+/*
+ * Number of side words owned by a block, from its type byte alone.
+ *   I picture:           type is the full byte: 0/8 -> 0, 6 -> 4 (raw), n -> n bases
+ *   P/B intra MCB:       nibble as above
+ *   P/B inter, proc 1:   0 (whole-macroblock motion compensation, h4m:1673-1683)
+ *   P/B inter, proc 0:   nibble 0 -> 0, 6 -> 4, k -> (k-1) bases + 1 pair = k
+ */
+SYM_HD uint32_t sym_side_words(uint32_t type, int is_ipic)
+{
+    if (is_ipic)
+        return type == 6 ? 4u : (type == 0 || type == 8) ? 0u : type;
+    uint32_t nib = type & 0xF;
+    if (type & 0x60)
+        return (type & 0x10) ? 0u : nib == 6 ? 4u : nib;
+    return nib == 6 ? 4u : (nib == 0 || nib == 8) ? 0u : nib;
+}
+
+#endif
