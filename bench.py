@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- HVQM4 picture-decode throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json config 5 -- independent synthetic 640x480 HVQM4
+1.5 I/P/B streams (GOP = I + 5 x PBB, dense profile, distinct seeds), batched per launch
+and sharded across GPUs with no collective (streams are independent; weak scaling:
+--streams-per-gpu is fixed as N grows).  One STEP = one GOP (16 pictures) of every
+stream of the rank = 16 reconstruction launches.
+
+Printed JSON (one line, rank 0):
+  value      reconstruction-only frames/s: symbol buffers already resident in HBM, the 16
+             kernels of a GOP replayed K times, timed with CUDA events on the launching
+             stream inside the library (HVQM4BatchReplay), max over ranks.
+  e2e        same metric through the C ABI with HOST buffers: bitstreams in host memory ->
+             host entropy threads -> pinned symbol arena -> H2D -> kernels -> D2H of every
+             decoded frame into pinned host memory, all inside the timed region.
+  roofline   recon kernel: algorithmic bytes per launch (frame bytes written + reference
+             bytes of inter macroblocks + symbol bytes read) / measured launch time,
+             against the measured HBM copy peak of MEASURED_PEAKS.json.
+  cpu_baseline  the reference decoder (oracle/_ref; else the oracle port) on the host cores,
+             bounded sample, N=1 only.
+`--impl reference` times that CPU decoder as its own line instead.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "640x480 decoded frames/sec (HVQM4 1.5 I/P/B, multi-stream)"
+UNIT = "frames/s"
+W, H = 640, 480
+GOP = "I" + "PBB" * 5
+BASE_SEED = 5000            # stream s uses seed BASE_SEED + s (tests/golden pins s = 0, 1, 511, 1023)
+DISTINCT_STREAMS = 128      # distinct bitstreams generated per rank; larger batches reuse them cyclically
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def gen_streams(rank: int, count: int, profile: int):
+    from hvqm4_b200 import synth
+    return [synth.generate(W, H, 15, GOP, 1, seed=BASE_SEED + rank * DISTINCT_STREAMS + i, profile=profile) for i in range(count)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions (B200_PROFILING.md)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self, windows):
+        rows = [r for t, r in self.rows if any(a <= t <= b for a, b in windows)] or [r for _, r in self.rows]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_run(streams, seconds_target: float, nproc: int):
+    """Times the reference CPU decoder (all host cores, one process per core -- it keeps state in
+    globals, h4m:604-605) on a bounded sample: every process decodes one stream's GOP `reps` times."""
+    from oracle import bindings
+    bindings.build(ref=os.path.exists("/root/reference/h4m_audio_decode.c"), port=True)
+    if bindings.have_ref():
+        dec, kind = bindings.RefDecoder, "reference"
+    else:
+        dec, kind = bindings.PortDecoder, "port"
+    t1, n1 = dec.bench(streams[0], 1)                      # calibration: one GOP on one core
+    per_gop = max(t1, 1e-3)
+    reps = max(1, int(seconds_target / per_gop))
+    wall, cpu_s, frames = dec.bench_mp(streams[0], nproc, reps)
+    return {
+        "value": frames / wall, "unit": UNIT, "cores": nproc, "kind": kind,
+        "sample": f"{nproc} processes x {reps} x one 16-picture 640x480 I/P/B GOP (stream seed {BASE_SEED}), decode calls only",
+        "single_core_fps": n1 / t1, "wall_s": wall,
+    }, reps
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    streams = gen_streams(0, 1, args.profile)
+    nproc = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    total_frames, total_wall, base = 0, 0.0, None
+    for i in range(args.warmup + args.steps):
+        base, _ = cpu_reference_run(streams, args.ref_seconds, nproc)
+        if i >= args.warmup:
+            total_frames += base["value"] * base["wall_s"]
+            total_wall += base["wall_s"]
+    value = total_frames / total_wall
+    base["value"] = value
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "gop": GOP, "profile": "dense" if args.profile == 0 else "realistic"},
+        "cpu_baseline": base,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return (f"BASELINE config 5 shard: {args.streams_per_gpu} independent synthetic 640x480 HVQM4 1.5 I/P/B streams per GPU "
+            f"(GOP {GOP}, seeds {BASE_SEED}+), one picture per stream per launch")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams-per-gpu", type=int, default=128)
+    ap.add_argument("--profile", type=int, default=0, help="0 dense (headline), 1 realistic")
+    ap.add_argument("--host-threads", type=int, default=0)
+    ap.add_argument("--ref-seconds", type=float, default=12.0, help="CPU seconds per process for the reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; hvqm4_b200 has no CPU path (use --impl reference for the CPU decoder)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if dist:
+        dist.barrier()
+    from hvqm4_b200 import api
+
+    S = args.streams_per_gpu
+    distinct = min(S, DISTINCT_STREAMS)
+    files = gen_streams(rank, distinct, args.profile)
+    parsed = [api.parse_file(f) for f in files]
+    bufs = [ctypes.create_string_buffer(f, len(f) + 8) for f in files]
+    bases = [ctypes.addressof(b) for b in bufs]
+    n_pics = len(parsed[0][1])
+    threads = args.host_threads or max(1, (os.cpu_count() or 1) // world)
+    batch = api.Batch(S, W, H, 15, device=local, host_threads=threads)
+    ids = list(range(S))
+    steps = []
+    for k in range(n_pics):
+        frs = [parsed[i % distinct][1][k] for i in range(S)]
+        steps.append(api.Batch.prepare_step(ids, [f.frame_type for f in frs],
+                                            [bases[i % distinct] + frs[i].offset for i in range(S)], [f.bytes for f in frs]))
+    ids_arr = (ctypes.c_int32 * S)(*ids)
+    frame_bytes = batch.frame_bytes
+    pinned = api.lib().HVQM4HostAlloc(S * frame_bytes)
+    if not pinned:
+        raise SystemExit("HVQM4HostAlloc failed")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    windows = []
+
+    # ---- record one GOP: symbol buffers of all 16 steps stay resident in HBM
+    batch.record(True)
+    for st in steps:
+        batch.decode_prepared(st)
+    batch.sync()
+    batch.record(False)
+    stats0 = batch.stats()
+    alg_bytes_per_gop = stats0["algorithmic_bytes"]
+    sym_bytes_per_gop = stats0["symbol_bytes"]
+    inter_frac = stats0["inter_mcbs"] / max(1, stats0["total_mcbs"])
+
+    # ---- reconstruction only (value)
+    batch.replay(args.warmup)
+    barrier()
+    launches0 = api.kernel_launches()
+    t_a = time.perf_counter()
+    ms = batch.replay(args.steps)
+    t_b = time.perf_counter()
+    windows.append((t_a, t_b))
+    barrier()
+    ms = max_over_ranks(ms)
+    recon_launches = api.kernel_launches() - launches0
+    frames_per_step = S * n_pics
+    value = world * frames_per_step * args.steps / (ms * 1e-3)
+    launch_ms = ms / (args.steps * n_pics)
+    achieved_gbs = alg_bytes_per_gop / n_pics / (launch_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak_gbs()
+
+    # ---- end to end through the C ABI with host buffers
+    e2e = None
+    e2e_launches = 0
+    if not args.no_e2e:
+        def one_gop():
+            for st in steps:
+                batch.decode_prepared(st)
+                batch.read_frames_async(ids_arr, S, pinned, frame_bytes)
+        for _ in range(args.warmup):
+            one_gop()
+        batch.sync()
+        barrier()
+        launches1 = api.kernel_launches()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            one_gop()
+        batch.sync()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        windows.append((t0, t1))
+        e2e_s = max_over_ranks(t1 - t0)
+        barrier()
+        e2e_launches = api.kernel_launches() - launches1
+        e2e = {"value": world * frames_per_step * args.steps / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": sym_bytes_per_gop, "d2h_bytes_per_step": frames_per_step * frame_bytes,
+               "host_threads_per_gpu": threads, "ms_per_step": 1e3 * e2e_s / args.steps,
+               "note": "wall clock around K GOPs: host entropy + H2D + kernels + D2H of every frame to pinned host memory"}
+    sampler.stop()
+    clocks = sampler.summary(windows)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base, _ = cpu_reference_run(files, args.ref_seconds, os.cpu_count() or 1)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/int32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "gop": GOP, "profile": "dense" if args.profile == 0 else "realistic",
+                       "streams_per_gpu": S, "pictures_per_step": frames_per_step, "launches_per_step": n_pics,
+                       "inter_mcb_fraction": round(inter_frac, 4),
+                       "l2": "inputs larger than L2: one step touches %.0f MB of symbols + %.0f MB of surfaces per GPU"
+                             % (sym_bytes_per_gop / 1e6, 3 * S * frame_bytes / 1e6)},
+            "mpixel_per_s": value * W * H / 1e6,
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peak, "unit": "GB/s", "frac": achieved_gbs / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "recon_pictures_kernel",
+                         "algorithmic_bytes_per_launch": alg_bytes_per_gop / n_pics, "launch_ms": launch_ms,
+                         "frac_of_nominal_8TBs": achieved_gbs / 8000.0},
+            "e2e": e2e, "gpu_launches": int(recon_launches + e2e_launches), "clocks": clocks,
+        }
+        if cpu_base:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+
+    api.lib().HVQM4HostFree(pinned)
+    batch.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,847 @@
+/*
+ * api.cpp -- C ABI of libhvqm4_b200.so (include/hvqm4.h): the SDK-compatible seven entry
+ * points, the batched multi-stream runtime, and the .h4m container walker.
+ *
+ * Runtime design (B200-first):
+ *   - one HVQM4Batch per GPU; streams are independent, so multi-GPU = one batch per
+ *     device/process with no communication;
+ *   - a step decodes one picture for each of n streams:  host threads run the serial
+ *     stage (entropy.c) in two parallel phases (sizes, then emission straight into a
+ *     pinned arena), ONE cudaMemcpyAsync uploads the whole arena on the copy stream, ONE
+ *     kernel launch reconstructs all n pictures on the compute stream;
+ *   - arenas are double buffered, so the host stage of step k+1 overlaps upload and
+ *     reconstruction of step k; frame surfaces never leave HBM unless asked for.
+ *
+ * The reference equivalents: the call protocol of main()/decode_video()
+ * (/root/reference/h4m_audio_decode.c:2409-2419, 2078-2138) and the buffer rotation
+ * rule (2087-2093, 2131-2137), which HVQM4Batch applies per stream.
+ */
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/hvqm4.h"
+#include "entropy.h"
+#include "recon.h"
+
+#define H4_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+std::atomic<int> g_last_cuda_error{0};
+std::atomic<long long> g_launches{0};
+
+bool cuda_ok(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return true;
+    g_last_cuda_error = (int)e;
+    fprintf(stderr, "hvqm4_b200: %s failed: %s\n", what, cudaGetErrorString(e));
+    return false;
+}
+
+bool have_device()
+{
+    static int state = -1;
+    if (state < 0)
+    {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        state = (e == cudaSuccess && n > 0) ? 1 : 0;
+        if (!state)
+        {
+            cudaGetLastError();
+            fprintf(stderr, "hvqm4_b200: no CUDA device available -- this decoder has no CPU reconstruction path\n");
+        }
+    }
+    return state == 1;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+/* ------------------------------------------------------------------ host thread pool */
+
+class Pool
+{
+    /* one Job object per parallel_for: a worker that is late leaving the previous job can
+       only ever touch that job's own counters */
+    struct Job
+    {
+        const std::function<void(int)> *fn;
+        int n;
+        std::atomic<int> next{0};
+        std::atomic<int> pending;
+        Job(const std::function<void(int)> *f, int count) : fn(f), n(count), pending(count) {}
+    };
+
+public:
+    explicit Pool(int n_threads)
+    {
+        for (int i = 0; i < n_threads; ++i) workers_.emplace_back([this] { loop(); });
+    }
+    ~Pool()
+    {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    /* runs f(i) for i in [0,n); the calling thread takes part */
+    void parallel_for(int n, const std::function<void(int)> &f)
+    {
+        if (n <= 0) return;
+        if (workers_.empty() || n == 1)
+        {
+            for (int i = 0; i < n; ++i) f(i);
+            return;
+        }
+        auto job = std::make_shared<Job>(&f, n);
+        {
+            std::lock_guard<std::mutex> l(m_);
+            job_ = job;
+            ++epoch_;
+        }
+        cv_.notify_all();
+        run(*job);
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [&] { return job->pending.load() == 0; });
+        job_.reset();
+    }
+    int size() const { return (int)workers_.size() + 1; }
+
+private:
+    void run(Job &j)
+    {
+        for (;;)
+        {
+            const int i = j.next.fetch_add(1);
+            if (i >= j.n) break;
+            (*j.fn)(i);
+            if (j.pending.fetch_sub(1) == 1)
+            {
+                std::lock_guard<std::mutex> l(m_);
+                done_.notify_all();
+            }
+        }
+    }
+    void loop()
+    {
+        unsigned long seen = 0;
+        for (;;)
+        {
+            std::shared_ptr<Job> j;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return stop_ || epoch_ != seen; });
+                if (stop_) return;
+                seen = epoch_;
+                j = job_;
+            }
+            if (j) run(*j);
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    std::shared_ptr<Job> job_;
+    unsigned long epoch_ = 0;
+    bool stop_ = false;
+};
+
+}  // namespace
+
+/* ====================================================================== batch runtime */
+
+struct StreamState
+{
+    H4Seq *seq = nullptr;
+    int past = 0, present = 1, future = 2;   /* surface indices, rotated like the reference's Player */
+    int last = -1;                           /* surface holding the most recently decoded picture */
+};
+
+struct Arena
+{
+    uint8_t *h = nullptr;   /* pinned */
+    uint8_t *d = nullptr;
+    size_t cap = 0;
+    cudaEvent_t consumed = nullptr;   /* recorded after the kernel that reads this arena */
+    bool in_flight = false;
+};
+
+struct RecordedStep
+{
+    uint8_t *d = nullptr;   /* jobs + blobs */
+    int n = 0;
+};
+
+struct HVQM4Batch
+{
+    int device = 0, n_streams = 0, width = 0, height = 0, version15 = 1;
+    int mcb_w = 0, mcb_h = 0;
+    size_t frame_bytes = 0, surf_stride = 0;
+    uint8_t *d_surfaces = nullptr;
+    std::vector<StreamState> st;
+    Arena arena[2];
+    int cur = 0;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_d2h = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    bool d2h_pending = false;
+    Pool *pool = nullptr;
+    uint32_t errors = 0;
+    bool recording = false;
+    std::vector<RecordedStep> recorded;
+    uint64_t stats[8] = {0};
+    std::vector<size_t> sizes, offs;
+    std::vector<uint8_t> seen;
+
+    uint8_t *surface(int stream, int idx) const { return d_surfaces + ((size_t)stream * 3 + idx) * surf_stride; }
+};
+
+static bool arena_reserve(HVQM4Batch *b, Arena &a, size_t need)
+{
+    if (need <= a.cap) return true;
+    size_t cap = align_up(need + need / 4 + (1 << 20), 1 << 20);
+    if (a.h) cudaFreeHost(a.h);
+    if (a.d) cudaFree(a.d);
+    a.h = a.d = nullptr;
+    a.cap = 0;
+    if (!cuda_ok(cudaHostAlloc((void **)&a.h, cap, cudaHostAllocDefault), "cudaHostAlloc(arena)")) return false;
+    if (!cuda_ok(cudaMalloc((void **)&a.d, cap), "cudaMalloc(arena)")) return false;
+    a.cap = cap;
+    (void)b;
+    return true;
+}
+
+H4_API HVQM4Batch *HVQM4BatchCreate(int device, int n_streams, int width, int height, int version, int host_threads)
+{
+    if (n_streams <= 0 || (version != 13 && version != 15)) return nullptr;
+    if (!have_device()) return nullptr;
+    if (device >= 0 && !cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return nullptr;
+    if (device < 0) cudaGetDevice(&device);
+    HVQM4Batch *b = new HVQM4Batch;
+    b->device = device;
+    b->n_streams = n_streams;
+    b->width = width;
+    b->height = height;
+    b->version15 = version == 15;
+    b->st.resize(n_streams);
+    for (int i = 0; i < n_streams; ++i)
+    {
+        b->st[i].seq = h4e_seq_create(width, height, 2, 2, b->version15);
+        if (!b->st[i].seq)
+        {
+            HVQM4BatchDestroy(b);
+            return nullptr;
+        }
+    }
+    int dims[6];
+    h4e_seq_dims(b->st[0].seq, dims);
+    b->mcb_w = dims[2];
+    b->mcb_h = dims[3];
+    b->frame_bytes = h4e_frame_bytes(b->st[0].seq);
+    /* 256-byte aligned surfaces with a tail so that the aligned 8-byte row reads of the
+       half-sample filter never leave the allocation */
+    b->surf_stride = align_up(b->frame_bytes + 64, 256);
+    size_t total = b->surf_stride * 3 * (size_t)n_streams + 256;
+    if (!cuda_ok(cudaMalloc((void **)&b->d_surfaces, total), "cudaMalloc(surfaces)") ||
+        !cuda_ok(cudaMemset(b->d_surfaces, 0, total), "cudaMemset(surfaces)") ||
+        !cuda_ok(cudaStreamCreateWithFlags(&b->s_copy, cudaStreamNonBlocking), "cudaStreamCreate") ||
+        !cuda_ok(cudaStreamCreateWithFlags(&b->s_comp, cudaStreamNonBlocking), "cudaStreamCreate") ||
+        !cuda_ok(cudaStreamCreateWithFlags(&b->s_d2h, cudaStreamNonBlocking), "cudaStreamCreate") ||
+        !cuda_ok(cudaEventCreateWithFlags(&b->ev_h2d, cudaEventDisableTiming), "cudaEventCreate") ||
+        !cuda_ok(cudaEventCreateWithFlags(&b->ev_kernel, cudaEventDisableTiming), "cudaEventCreate") ||
+        !cuda_ok(cudaEventCreateWithFlags(&b->ev_d2h, cudaEventDisableTiming), "cudaEventCreate") ||
+        !cuda_ok(cudaEventCreate(&b->ev_t0), "cudaEventCreate") || !cuda_ok(cudaEventCreate(&b->ev_t1), "cudaEventCreate"))
+    {
+        HVQM4BatchDestroy(b);
+        return nullptr;
+    }
+    for (auto &a : b->arena)
+        if (!cuda_ok(cudaEventCreateWithFlags(&a.consumed, cudaEventDisableTiming), "cudaEventCreate"))
+        {
+            HVQM4BatchDestroy(b);
+            return nullptr;
+        }
+    if (host_threads <= 0)
+    {
+        host_threads = (int)std::thread::hardware_concurrency();
+        if (host_threads > 64) host_threads = 64;
+        if (host_threads < 1) host_threads = 1;
+    }
+    if (host_threads > n_streams) host_threads = n_streams;
+    b->pool = new Pool(host_threads - 1);
+    b->sizes.resize(n_streams);
+    b->offs.resize(n_streams);
+    b->seen.assign(n_streams, 0);
+    return b;
+}
+
+H4_API void HVQM4BatchDestroy(HVQM4Batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    cudaDeviceSynchronize();
+    delete b->pool;
+    for (auto &s : b->st) h4e_seq_destroy(s.seq);
+    for (auto &r : b->recorded) cudaFree(r.d);
+    for (auto &a : b->arena)
+    {
+        if (a.h) cudaFreeHost(a.h);
+        if (a.d) cudaFree(a.d);
+        if (a.consumed) cudaEventDestroy(a.consumed);
+    }
+    if (b->d_surfaces) cudaFree(b->d_surfaces);
+    if (b->s_copy) cudaStreamDestroy(b->s_copy);
+    if (b->s_comp) cudaStreamDestroy(b->s_comp);
+    if (b->s_d2h) cudaStreamDestroy(b->s_d2h);
+    for (cudaEvent_t e : {b->ev_h2d, b->ev_kernel, b->ev_d2h, b->ev_t0, b->ev_t1})
+        if (e) cudaEventDestroy(e);
+    delete b;
+}
+
+H4_API int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, const int32_t *frame_types,
+                            const uint8_t *const *frames, const uint32_t *frame_bytes)
+{
+    if (!b || n <= 0 || n > b->n_streams || !stream_ids || !frame_types || !frames || !frame_bytes) return HVQM4_ERR_ARGUMENT;
+    cudaSetDevice(b->device);
+    std::fill(b->seen.begin(), b->seen.end(), 0);
+    for (int i = 0; i < n; ++i)
+    {
+        int s = stream_ids[i], t = frame_types[i];
+        if (s < 0 || s >= b->n_streams || b->seen[s] || (t != SYM_PIC_I && t != SYM_PIC_P && t != SYM_PIC_B)) return HVQM4_ERR_ARGUMENT;
+        b->seen[s] = 1;
+    }
+    auto t_host0 = std::chrono::steady_clock::now();
+    /* phase A: headers, trees, maps, work-order offsets -> exact blob sizes */
+    b->pool->parallel_for(n, [&](int i) {
+        b->sizes[i] = h4e_parse_begin(b->st[stream_ids[i]].seq, frame_types[i], frames[i], frame_bytes[i]);
+    });
+    const size_t jobs_bytes = align_up((size_t)n * sizeof(ReconJob), 256);
+    size_t total = jobs_bytes;
+    for (int i = 0; i < n; ++i)
+    {
+        if (b->sizes[i] == 0) return HVQM4_ERR_GEOMETRY;
+        b->offs[i] = total;
+        total += align_up(b->sizes[i], 128);
+    }
+    Arena &a = b->arena[b->cur];
+    if (a.in_flight)
+    {
+        if (!cuda_ok(cudaEventSynchronize(a.consumed), "cudaEventSynchronize")) return HVQM4_ERR_CUDA;
+        a.in_flight = false;
+    }
+    if (!arena_reserve(b, a, total)) return HVQM4_ERR_NOMEM;
+    uint8_t *d_base = a.d;
+    if (b->recording)
+    {
+        RecordedStep r;
+        if (!cuda_ok(cudaMalloc((void **)&r.d, total), "cudaMalloc(recorded step)")) return HVQM4_ERR_NOMEM;
+        r.n = n;
+        b->recorded.push_back(r);
+        d_base = r.d;
+    }
+    /* phase B: side words, motion vectors, maps -> pinned arena */
+    std::atomic<uint32_t> err{0};
+    std::atomic<uint64_t> inter{0};
+    b->pool->parallel_for(n, [&](int i) {
+        H4Seq *seq = b->st[stream_ids[i]].seq;
+        err |= h4e_parse_finish(seq, a.h + b->offs[i]);
+        inter += h4e_last_inter_mcbs(seq);
+    });
+    /* rotation (h4m:2087-2093, 2131-2137) and job descriptors */
+    ReconJob *jobs = reinterpret_cast<ReconJob *>(a.h);
+    for (int i = 0; i < n; ++i)
+    {
+        StreamState &s = b->st[stream_ids[i]];
+        const int t = frame_types[i];
+        if (t != SYM_PIC_B) std::swap(s.past, s.future);
+        jobs[i].blob = d_base + b->offs[i];
+        jobs[i].present = b->surface(stream_ids[i], s.present);
+        jobs[i].past = b->surface(stream_ids[i], s.past);
+        /* HVQM4DecodePpic passes `present` as the future frame (h4m:2060); the host stage
+           has already rejected type-2 macroblocks in P pictures, so it is never read */
+        jobs[i].future = b->surface(stream_ids[i], t == SYM_PIC_P ? s.present : s.future);
+        s.last = s.present;
+        if (t != SYM_PIC_B) std::swap(s.present, s.future);
+    }
+    auto t_host1 = std::chrono::steady_clock::now();
+    b->stats[4] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_host1 - t_host0).count();
+
+    if (!cuda_ok(cudaMemcpyAsync(d_base, a.h, total, cudaMemcpyHostToDevice, b->s_copy), "cudaMemcpyAsync(H2D)")) return HVQM4_ERR_CUDA;
+    cudaEventRecord(b->ev_h2d, b->s_copy);
+    cudaStreamWaitEvent(b->s_comp, b->ev_h2d, 0);
+    if (b->d2h_pending)
+    {   /* the previous step's read-backs must finish before surfaces are overwritten */
+        cudaStreamWaitEvent(b->s_comp, b->ev_d2h, 0);
+        b->d2h_pending = false;
+    }
+    int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(d_base), n, b->mcb_w, b->mcb_h, b->s_comp);
+    if (rc != 0)
+    {
+        cuda_ok((cudaError_t)rc, "recon kernel launch");
+        return HVQM4_ERR_CUDA;
+    }
+    ++g_launches;
+    cudaEventRecord(a.consumed, b->s_comp);
+    cudaEventRecord(b->ev_kernel, b->s_comp);
+    a.in_flight = true;
+    b->cur ^= 1;
+
+    const uint64_t mcbs = (uint64_t)b->mcb_w * b->mcb_h * n;
+    b->stats[0] += n;
+    b->stats[1] += 1;
+    b->stats[2] += total;
+    b->stats[3] += (uint64_t)n * b->frame_bytes + inter.load() * 96 + (total - jobs_bytes);
+    b->stats[5] += inter.load();
+    b->stats[6] += mcbs;
+    b->errors |= err.load();
+    return (int)err.load();
+}
+
+H4_API int HVQM4BatchSync(HVQM4Batch *b)
+{
+    if (!b) return HVQM4_ERR_ARGUMENT;
+    cudaSetDevice(b->device);
+    uint32_t e = b->errors;
+    b->errors = 0;
+    bool ok = cuda_ok(cudaStreamSynchronize(b->s_copy), "sync copy") & cuda_ok(cudaStreamSynchronize(b->s_comp), "sync compute") &
+              cuda_ok(cudaStreamSynchronize(b->s_d2h), "sync d2h");
+    for (auto &a : b->arena) a.in_flight = false;
+    b->d2h_pending = false;
+    if (!ok) e |= HVQM4_ERR_CUDA;
+    return (int)e;
+}
+
+H4_API void *HVQM4BatchFramePtr(HVQM4Batch *b, int stream_id)
+{
+    if (!b || stream_id < 0 || stream_id >= b->n_streams || b->st[stream_id].last < 0) return nullptr;
+    return b->surface(stream_id, b->st[stream_id].last);
+}
+
+H4_API int HVQM4BatchReadFrameAsync(HVQM4Batch *b, int stream_id, void *host_dst)
+{
+    void *src = HVQM4BatchFramePtr(b, stream_id);
+    if (!src || !host_dst) return HVQM4_ERR_ARGUMENT;
+    cudaSetDevice(b->device);
+    if (!b->d2h_pending) cudaStreamWaitEvent(b->s_d2h, b->ev_kernel, 0);
+    if (!cuda_ok(cudaMemcpyAsync(host_dst, src, b->frame_bytes, cudaMemcpyDeviceToHost, b->s_d2h), "cudaMemcpyAsync(D2H)")) return HVQM4_ERR_CUDA;
+    cudaEventRecord(b->ev_d2h, b->s_d2h);
+    b->d2h_pending = true;
+    return HVQM4_OK;
+}
+
+H4_API int HVQM4BatchReadFramesAsync(HVQM4Batch *b, int n, const int32_t *stream_ids, void *host_base, size_t host_stride)
+{
+    if (!b || n <= 0 || !stream_ids || !host_base || host_stride < b->frame_bytes) return HVQM4_ERR_ARGUMENT;
+    for (int i = 0; i < n; ++i)
+    {
+        int rc = HVQM4BatchReadFrameAsync(b, stream_ids[i], static_cast<uint8_t *>(host_base) + (size_t)i * host_stride);
+        if (rc) return rc;
+    }
+    return HVQM4_OK;
+}
+
+H4_API int HVQM4BatchReadFrame(HVQM4Batch *b, int stream_id, void *host_dst)
+{
+    int rc = HVQM4BatchReadFrameAsync(b, stream_id, host_dst);
+    if (rc) return rc;
+    return cuda_ok(cudaStreamSynchronize(b->s_d2h), "sync d2h") ? HVQM4_OK : HVQM4_ERR_CUDA;
+}
+
+H4_API int HVQM4BatchRecord(HVQM4Batch *b, int enable)
+{
+    if (!b) return HVQM4_ERR_ARGUMENT;
+    cudaSetDevice(b->device);
+    cudaDeviceSynchronize();
+    if (enable)
+    {
+        for (auto &r : b->recorded) cudaFree(r.d);
+        b->recorded.clear();
+    }
+    b->recording = enable != 0;
+    return HVQM4_OK;
+}
+
+H4_API float HVQM4BatchReplay(HVQM4Batch *b, int repeats)
+{
+    if (!b || b->recorded.empty() || repeats <= 0) return -1.f;
+    cudaSetDevice(b->device);
+    if (!cuda_ok(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return -1.f;
+    cudaEventRecord(b->ev_t0, b->s_comp);
+    for (int r = 0; r < repeats; ++r)
+        for (auto &st : b->recorded)
+        {
+            int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(st.d), st.n, b->mcb_w, b->mcb_h, b->s_comp);
+            if (rc != 0)
+            {
+                cuda_ok((cudaError_t)rc, "recon kernel launch");
+                return -1.f;
+            }
+            ++g_launches;
+            b->stats[1] += 1;
+        }
+    cudaEventRecord(b->ev_t1, b->s_comp);
+    if (!cuda_ok(cudaEventSynchronize(b->ev_t1), "cudaEventSynchronize")) return -1.f;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, b->ev_t0, b->ev_t1);
+    return ms;
+}
+
+H4_API void HVQM4BatchStats(HVQM4Batch *b, uint64_t out[8])
+{
+    for (int i = 0; i < 8; ++i) out[i] = b ? b->stats[i] : 0;
+}
+
+H4_API void *HVQM4HostAlloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (!have_device()) return nullptr;
+    if (!cuda_ok(cudaHostAlloc(&p, bytes, cudaHostAllocDefault), "cudaHostAlloc")) return nullptr;
+    return p;
+}
+
+H4_API void HVQM4HostFree(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+H4_API int HVQM4GetLastCudaError(void) { return g_last_cuda_error.load(); }
+
+/* ====================================================================== SDK-compatible layer */
+
+namespace {
+
+constexpr uint32_t kCompatMagic = 0x48344232u;   /* "H4B2" */
+constexpr int kTwins = 4;
+
+struct Twin
+{
+    const void *host = nullptr;
+    uint8_t *dev = nullptr;
+    uint64_t stamp = 0;
+};
+
+struct Compat
+{
+    H4Seq *seq = nullptr;
+    int width = 0, height = 0;
+    size_t frame_bytes = 0, surf_bytes = 0;
+    int mcb_w = 0, mcb_h = 0;
+    uint8_t *h_blob = nullptr, *d_blob = nullptr;   /* job descriptor (256 B) + blob */
+    size_t blob_cap = 0;
+    Twin twin[kTwins];
+    uint64_t clock = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t errors = 0;
+    uint32_t next_frame_bytes = 0;
+};
+
+/* what lives in the caller's work buffer */
+struct WorkHeader
+{
+    uint32_t magic;
+    uint32_t version15;
+    Compat *impl;
+};
+
+Compat *compat_of(SeqObj *so)
+{
+    if (!so || !so->state) return nullptr;
+    WorkHeader *w = static_cast<WorkHeader *>(so->state);
+    return w->magic == kCompatMagic ? w->impl : nullptr;
+}
+
+bool is_device_ptr(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+/* device copy of a caller frame: the pointer itself if it is device memory, otherwise a
+   cached twin keyed by the host address (uploaded on first sight when it is a reference) */
+uint8_t *resolve(Compat *c, void *p, bool is_reference)
+{
+    if (is_device_ptr(p)) return static_cast<uint8_t *>(p);
+    Twin *slot = nullptr;
+    for (auto &t : c->twin)
+        if (t.host == p) slot = &t;
+    bool fresh = false;
+    if (!slot)
+    {
+        slot = &c->twin[0];
+        for (auto &t : c->twin)
+            if (t.stamp < slot->stamp) slot = &t;
+        if (!slot->dev && !cuda_ok(cudaMalloc((void **)&slot->dev, c->surf_bytes), "cudaMalloc(frame twin)")) return nullptr;
+        slot->host = p;
+        fresh = true;
+    }
+    slot->stamp = ++c->clock;
+    if (fresh && is_reference &&
+        !cuda_ok(cudaMemcpyAsync(slot->dev, p, c->frame_bytes, cudaMemcpyHostToDevice, c->stream), "upload reference frame"))
+        return nullptr;
+    return slot->dev;
+}
+
+void compat_decode(SeqObj *so, int type, const uint8_t *frame, void *present, void *past, void *future)
+{
+    Compat *c = compat_of(so);
+    if (!c)
+    {
+        fprintf(stderr, "hvqm4_b200: decode called on a SeqObj without HVQM4SetBuffer\n");
+        return;
+    }
+    if (!have_device() || !c->stream)
+    {
+        c->errors |= HVQM4_ERR_NO_DEVICE;
+        return;
+    }
+    const size_t len = c->next_frame_bytes ? c->next_frame_bytes : (size_t)1 << 30;
+    c->next_frame_bytes = 0;
+    const size_t need = h4e_parse_begin(c->seq, type, frame, len);
+    if (!need)
+    {
+        c->errors |= HVQM4_ERR_GEOMETRY;
+        return;
+    }
+    const size_t total = 256 + need;
+    if (total > c->blob_cap)
+    {
+        cudaStreamSynchronize(c->stream);
+        if (c->h_blob) cudaFreeHost(c->h_blob);
+        if (c->d_blob) cudaFree(c->d_blob);
+        c->h_blob = c->d_blob = nullptr;
+        c->blob_cap = 0;
+        const size_t cap = align_up(total + total / 2, 1 << 16);
+        if (!cuda_ok(cudaHostAlloc((void **)&c->h_blob, cap, cudaHostAllocDefault), "cudaHostAlloc(blob)") ||
+            !cuda_ok(cudaMalloc((void **)&c->d_blob, cap), "cudaMalloc(blob)"))
+        {
+            c->errors |= HVQM4_ERR_NOMEM;
+            return;
+        }
+        c->blob_cap = cap;
+    }
+    c->errors |= h4e_parse_finish(c->seq, c->h_blob + 256);
+    ReconJob *job = reinterpret_cast<ReconJob *>(c->h_blob);
+    uint8_t *d_present = resolve(c, present, false);
+    uint8_t *d_past = past ? resolve(c, past, true) : d_present;
+    uint8_t *d_future = (future && future != present) ? resolve(c, future, true) : d_present;
+    if (!d_present || !d_past || !d_future)
+    {
+        c->errors |= HVQM4_ERR_CUDA;
+        return;
+    }
+    job->blob = c->d_blob + 256;
+    job->present = d_present;
+    job->past = d_past;
+    job->future = d_future;
+    bool ok = cuda_ok(cudaMemcpyAsync(c->d_blob, c->h_blob, total, cudaMemcpyHostToDevice, c->stream), "upload symbols");
+    if (ok)
+    {
+        int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(c->d_blob), 1, c->mcb_w, c->mcb_h, c->stream);
+        ok = rc == 0 || cuda_ok((cudaError_t)rc, "recon kernel launch");
+        if (rc == 0) ++g_launches;
+    }
+    if (ok && !is_device_ptr(present))
+        ok = cuda_ok(cudaMemcpyAsync(present, d_present, c->frame_bytes, cudaMemcpyDeviceToHost, c->stream), "download frame");
+    ok = ok && cuda_ok(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
+    if (!ok) c->errors |= HVQM4_ERR_CUDA;
+}
+
+}  // namespace
+
+H4_API void HVQM4InitDecoder(void)
+{
+    /* The reference fills divTable/mcdivTable here (h4m:265-278); the kernels build them in
+       shared memory per CTA, so only the device probe remains. */
+    have_device();
+}
+
+H4_API void HVQM4InitSeqObj(SeqObj *seqobj, VideoInfo *videoinfo)
+{
+    seqobj->width = videoinfo->hres;
+    seqobj->height = videoinfo->vres;
+    seqobj->h_samp = videoinfo->h_samp;
+    seqobj->v_samp = videoinfo->v_samp;
+}
+
+H4_API uint32_t HVQM4BuffSize(SeqObj *) { return 256; }
+
+H4_API void HVQM4SetBuffer(SeqObj *seqobj, void *workbuff)
+{
+    WorkHeader *w = static_cast<WorkHeader *>(workbuff);
+    seqobj->state = workbuff;
+    w->magic = 0;
+    w->impl = nullptr;
+    w->version15 = 1;
+    Compat *c = new Compat;
+    c->seq = h4e_seq_create(seqobj->width, seqobj->height, seqobj->h_samp, seqobj->v_samp, 1);
+    if (!c->seq)
+    {
+        fprintf(stderr, "hvqm4_b200: unsupported geometry %ux%u (sampling %u x %u)\n", seqobj->width, seqobj->height,
+                seqobj->h_samp, seqobj->v_samp);
+        delete c;
+        return;
+    }
+    c->width = seqobj->width;
+    c->height = seqobj->height;
+    int dims[6];
+    h4e_seq_dims(c->seq, dims);
+    c->mcb_w = dims[2];
+    c->mcb_h = dims[3];
+    c->frame_bytes = h4e_frame_bytes(c->seq);
+    c->surf_bytes = align_up(c->frame_bytes + 64, 256);
+    if (have_device() && !cuda_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate"))
+        c->stream = nullptr;
+    w->impl = c;
+    w->magic = kCompatMagic;
+}
+
+H4_API void HVQM4ReleaseBuffer(SeqObj *seqobj)
+{
+    Compat *c = compat_of(seqobj);
+    if (!c) return;
+    if (c->stream)
+    {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamDestroy(c->stream);
+    }
+    for (auto &t : c->twin)
+        if (t.dev) cudaFree(t.dev);
+    if (c->h_blob) cudaFreeHost(c->h_blob);
+    if (c->d_blob) cudaFree(c->d_blob);
+    h4e_seq_destroy(c->seq);
+    delete c;
+    static_cast<WorkHeader *>(seqobj->state)->magic = 0;
+    static_cast<WorkHeader *>(seqobj->state)->impl = nullptr;
+}
+
+H4_API int HVQM4SetVersion(SeqObj *seqobj, int version)
+{
+    Compat *c = compat_of(seqobj);
+    if (!c || (version != 13 && version != 15)) return HVQM4_ERR_ARGUMENT;
+    h4e_seq_set_version(c->seq, version == 15);
+    static_cast<WorkHeader *>(seqobj->state)->version15 = version == 15;
+    return HVQM4_OK;
+}
+
+H4_API void HVQM4SetFrameBytes(SeqObj *seqobj, uint32_t bytes)
+{
+    Compat *c = compat_of(seqobj);
+    if (c) c->next_frame_bytes = bytes;
+}
+
+H4_API uint32_t HVQM4GetLastError(SeqObj *seqobj)
+{
+    Compat *c = compat_of(seqobj);
+    if (!c) return HVQM4_ERR_ARGUMENT;
+    uint32_t e = c->errors;
+    c->errors = 0;
+    return e;
+}
+
+H4_API void HVQM4InvalidateFrame(SeqObj *seqobj, void *host_frame)
+{
+    Compat *c = compat_of(seqobj);
+    if (!c) return;
+    for (auto &t : c->twin)
+        if (t.host == host_frame)
+        {
+            t.host = nullptr;
+            t.stamp = 0;
+        }
+}
+
+H4_API void HVQM4DecodeIpic(SeqObj *seqobj, uint8_t const *frame, void *present)
+{
+    compat_decode(seqobj, SYM_PIC_I, frame, present, nullptr, nullptr);
+}
+
+H4_API void HVQM4DecodePpic(SeqObj *seqobj, uint8_t const *frame, void *present, void *past)
+{
+    compat_decode(seqobj, SYM_PIC_P, frame, present, past, present);
+}
+
+H4_API void HVQM4DecodeBpic(SeqObj *seqobj, uint8_t const *frame, void *present, void *past, void *future)
+{
+    compat_decode(seqobj, SYM_PIC_B, frame, present, past, future);
+}
+
+H4_API long long HVQM4KernelLaunches(void) { return g_launches.load(); }
+
+/* ====================================================================== container walker */
+
+static inline uint32_t be32(const uint8_t *p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
+static inline uint32_t be16(const uint8_t *p) { return (uint32_t)p[0] << 8 | p[1]; }
+
+H4_API int HVQM4ParseFile(const uint8_t *data, size_t len, HVQM4FileInfo *info, HVQM4FrameRef *frames, int max_frames)
+{
+    if (!data || len < 0x44 || !info) return -1;
+    if (!memcmp(data, "HVQM4 1.3\0\0\0\0\0\0\0", 16)) info->version = 13;
+    else if (!memcmp(data, "HVQM4 1.5\0\0\0\0\0\0\0", 16)) info->version = 15;
+    else return -2;
+    if (be32(data + 0x10) != 0x44) return -3;                       /* h4m:2213 */
+    info->n_gops = (int32_t)be32(data + 0x18);
+    info->n_video_frames = (int32_t)be32(data + 0x1C);
+    info->usec_per_frame = (int32_t)be32(data + 0x24);
+    info->width = (int32_t)be16(data + 0x34);
+    info->height = (int32_t)be16(data + 0x36);
+    info->h_samp = data[0x38];
+    info->v_samp = data[0x39];
+    if (info->n_gops == 0) return -4;                               /* h4m:2215-2219 */
+    size_t pos = 0x44;
+    int count = 0;
+    for (int g = 0; g < info->n_gops; ++g)
+    {
+        if (pos + 20 > len) return -5;
+        uint32_t nv = be32(data + pos + 8), na = be32(data + pos + 12);
+        if (be32(data + pos + 16) != 0x01000000) return -6;         /* h4m:2436 */
+        pos += 20;
+        while (nv || na)
+        {
+            if (pos + 8 > len) return -5;
+            uint32_t id1 = be16(data + pos), id2 = be16(data + pos + 2), size = be32(data + pos + 4);
+            pos += 8;
+            if (pos + size > len) return -5;
+            if (id1 == 1)
+            {
+                if (!nv || size < 4) return -7;
+                if (id2 != 0x10 && id2 != 0x20 && id2 != 0x30) return -8;   /* h4m:2113-2115 */
+                if (frames && count < max_frames)
+                {
+                    frames[count].offset = (uint32_t)(pos + 4);
+                    frames[count].bytes = size - 4;
+                    frames[count].frame_type = (uint16_t)id2;
+                    frames[count].gop = (uint16_t)g;
+                    frames[count].disp_id = be32(data + pos);
+                }
+                ++count;
+                --nv;
+            }
+            else if (id1 == 0)
+            {
+                if (!na) return -7;
+                --na;
+            }
+            else
+                return -9;                                          /* h4m:2509-2512 */
+            pos += size;
+        }
+    }
+    return count;
+}

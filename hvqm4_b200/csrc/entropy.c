@@ -216,6 +216,7 @@ struct H4Seq
     int pic_type;
     uint32_t err;
     uint32_t n_side;
+    uint32_t n_inter_mcb;
     int need_nest;
     int dc_shift, unk_shift, rb[2][2];
     int32_t dc_lo, dc_hi;
@@ -284,6 +285,8 @@ void h4e_seq_set_version(H4Seq *s, int version15) { s->version15 = version15 ? 1
 uint32_t h4e_seq_errors(const H4Seq *s) { return s->errors_total; }
 size_t h4e_frame_bytes(const H4Seq *s) { return (size_t)s->width * s->height * 3 / 2; }
 
+uint32_t h4e_last_inter_mcbs(const H4Seq *s) { return s->n_inter_mcb; }
+
 void h4e_seq_dims(const H4Seq *s, int out[6])
 {
     out[0] = s->width; out[1] = s->height; out[2] = s->mbw; out[3] = s->mbh; out[4] = s->nseg; out[5] = s->version15;
@@ -329,6 +332,14 @@ static void open_bytes(H4Seq *s, ByteSec *b, const uint8_t *data, size_t len, ui
 
 /* ------------------------------------------------------------------ work-order offsets */
 
+/* intra AOT blocks (not raw, not inter) gather from the I-picture nest */
+static inline int block_needs_nest(uint32_t t, uint32_t n_words, int is_ipic)
+{
+    if (!n_words) return 0;
+    if (is_ipic) return t != 6;
+    return !(t & 0x60) && (t & 0xF) != 6;
+}
+
 /* Assigns every block its slot in the side-word array, in the order the warps of
    recon.cu walk the picture (see symbuf.h), and fills the segment table. */
 static void assign_offsets(H4Seq *s, int is_ipic)
@@ -351,7 +362,7 @@ static void assign_offsets(H4Seq *s, int is_ipic)
                     uint32_t t = ty[bx], n = sym_side_words(t, is_ipic);
                     off[bx] = word;
                     word += n;
-                    if (n && !(t & 0x60 & (is_ipic ? 0 : 0xFF)) && (is_ipic ? t : (t & 0xF)) != 6) need_nest = 1;
+                    need_nest |= block_needs_nest(t, n, is_ipic);
                 }
             }
             for (int p = 1; p < 3; ++p)
@@ -363,7 +374,7 @@ static void assign_offsets(H4Seq *s, int is_ipic)
                     uint32_t t = ty[bx], n = sym_side_words(t, is_ipic);
                     off[bx] = word;
                     word += n;
-                    if (n && !(t & 0x60 & (is_ipic ? 0 : 0xFF)) && (is_ipic ? t : (t & 0xF)) != 6) need_nest = 1;
+                    need_nest |= block_needs_nest(t, n, is_ipic);
                 }
             }
         }
@@ -750,6 +761,7 @@ static void pb_pass2(H4Seq *s, int16_t *mv_out, uint32_t *side)
     int32_t mvx = 0, mvy = 0;
     int cur_ref = -1;
     const int st0 = s->stride[0];
+    s->n_inter_mcb = 0;
     for (int my = 0; my < s->mbh; ++my)
     {
         const uint8_t *ty0 = s->type[0] + cell_at(s, 0, 0, my * 2);
@@ -772,6 +784,7 @@ static void pb_pass2(H4Seq *s, int16_t *mv_out, uint32_t *side)
                 continue;
             }
             const int ref = mt - 1;
+            s->n_inter_mcb++;
             if (ref != cur_ref)
             {   /* h4m:1943-1949 */
                 cur_ref = ref;
@@ -826,6 +839,7 @@ size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_t pic_le
 {
     s->pic_type = pic_type;
     s->err = 0;
+    s->n_inter_mcb = 0;
     s->blob_bytes = 0;
     const int is_i = pic_type == SYM_PIC_I;
     const int nsec = is_i ? 16 : 17;

@@ -42,6 +42,9 @@ uint32_t h4e_seq_errors(const H4Seq *s);   /* OR of SYM_ERR_* since creation */
 size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_t pic_len);
 uint32_t h4e_parse_finish(H4Seq *s, uint8_t *blob);
 
+/* inter-coded macroblocks of the last parsed picture (for bandwidth accounting) */
+uint32_t h4e_last_inter_mcbs(const H4Seq *s);
+
 /* geometry helpers */
 size_t h4e_frame_bytes(const H4Seq *s);    /* planar Y|U|V bytes = W*H*3/2 */
 void h4e_seq_dims(const H4Seq *s, int out[6]); /* width,height,mcb_w,mcb_h,nseg,version15 */

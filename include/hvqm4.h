@@ -1,0 +1,212 @@
+/*
+ * hvqm4.h -- C ABI of libhvqm4_b200.so, a B200-native HVQM4 1.3/1.5 picture decoder.
+ *
+ * PART 1 is the HVQM4 SDK picture-decode interface exactly as the reference exposes it
+ * (the reference keeps these seven functions `static` in one translation unit and lists
+ * them first in symbols.inc:2-8 as the SDK's public entry points); a program written
+ * against the reference's API links against this library unchanged.  "h4m:N" below is
+ * /root/reference/h4m_audio_decode.c line N.
+ *
+ * PART 2 holds the extensions the SDK lacks and a GPU decoder needs: version select,
+ * error reporting, resource release, and a batched multi-stream interface that keeps
+ * frame surfaces resident in device memory.
+ *
+ * Division of labour: the serial bitstream stage runs in C on host
+ * threads and emits a per-picture symbol buffer into pinned memory; all pixel
+ * reconstruction runs in CUDA kernels for sm_100a.  There is no CPU reconstruction
+ * path: without a CUDA device every decode call fails (HVQM4_ERR_NO_DEVICE).
+ */
+#ifndef HVQM4_H
+#define HVQM4_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ====================================================================== PART 1: SDK */
+
+/* h4m:516-523.  `state` points into the caller's work buffer after HVQM4SetBuffer. */
+typedef struct SeqObj
+{
+    void *state;
+    uint16_t width;
+    uint16_t height;
+    uint8_t h_samp;   /* 2 = chroma halved horizontally */
+    uint8_t v_samp;   /* 2 = chroma halved vertically */
+} SeqObj;
+
+/* h4m:533-540.  The reference passes a pointer into the parsed file header (h4m:2412). */
+typedef struct VideoInfo
+{
+    uint16_t hres;
+    uint16_t vres;
+    uint8_t h_samp;
+    uint8_t v_samp;
+    uint8_t video_mode;
+} VideoInfo;
+
+/* replaces h4m:275 -- one-time global initialisation (constant tables; here also the
+   CUDA context is created lazily on first decode). */
+void HVQM4InitDecoder(void);
+
+/* replaces h4m:819 -- copies geometry from the stream header into the sequence object. */
+void HVQM4InitSeqObj(SeqObj *seqobj, VideoInfo *videoinfo);
+
+/* replaces h4m:828 -- bytes of caller-owned work memory HVQM4SetBuffer needs.  (The
+   value differs from the reference's: it is an ABI detail there as well, 32- vs 64-bit.) */
+uint32_t HVQM4BuffSize(SeqObj *seqobj);
+
+/* replaces h4m:957 -- binds the work buffer and builds per-stream decoder state.  The
+   stream version defaults to 1.5; call HVQM4SetVersion for 1.3 streams (the reference
+   pokes state->padding[0] before this call instead, h4m:2414-2417). */
+void HVQM4SetBuffer(SeqObj *seqobj, void *workbuff);
+
+/*
+ * replace h4m:1970 / 2058 / 2018.  `frame` points 4 bytes into the video frame record,
+ * just past the display id (h4m:2085,2100).  present/past/future are planar Y|U|V
+ * buffers of width*height*3/2 bytes, stride = plane width (h4m:2343-2349); rotation of
+ * the three buffers between calls is the caller's job (h4m:2087-2093, 2131-2137).
+ *
+ * Each pointer may be a host pointer (drop-in mode: references are uploaded when the
+ * library has no device copy of them, the result is copied back before the call
+ * returns) or a CUDA device pointer on the current device (zero-copy mode).
+ */
+void HVQM4DecodeIpic(SeqObj *seqobj, uint8_t const *frame, void *present);
+void HVQM4DecodePpic(SeqObj *seqobj, uint8_t const *frame, void *present, void *past);
+void HVQM4DecodeBpic(SeqObj *seqobj, uint8_t const *frame, void *present, void *past, void *future);
+
+/* =============================================================== PART 2: extensions */
+
+enum
+{
+    HVQM4_OK = 0,
+    /* bits 0..7: stream errors found by the host stage (hvqm4_b200/csrc/symbuf.h SYM_ERR_*) */
+    HVQM4_ERR_TRUNCATED  = 1 << 0,
+    HVQM4_ERR_BAD_TREE   = 1 << 1,
+    HVQM4_ERR_MCB_TYPE   = 1 << 2,
+    HVQM4_ERR_MV_RANGE   = 1 << 3,
+    HVQM4_ERR_PAIR_RANGE = 1 << 4,
+    HVQM4_ERR_GEOMETRY   = 1 << 5,
+    HVQM4_ERR_OVERFLOW   = 1 << 6,
+    /* bits 16..: runtime errors */
+    HVQM4_ERR_NO_DEVICE  = 1 << 16,  /* no CUDA device / driver: decoding is impossible */
+    HVQM4_ERR_CUDA       = 1 << 17,  /* a CUDA call failed (see HVQM4GetLastCudaError) */
+    HVQM4_ERR_ARGUMENT   = 1 << 18,
+    HVQM4_ERR_NOMEM      = 1 << 19
+};
+
+/* version = 13 or 15.  Returns HVQM4_OK or HVQM4_ERR_ARGUMENT.  Call after HVQM4SetBuffer. */
+int HVQM4SetVersion(SeqObj *seqobj, int version);
+
+/* Optional: readable bytes behind the `frame` pointer of the NEXT decode call (record size
+   minus 4).  Without it sections are bounded by their own declared sizes only. */
+void HVQM4SetFrameBytes(SeqObj *seqobj, uint32_t bytes);
+
+/* OR of all error bits since the last call; clears them.  The SDK entry points return void. */
+uint32_t HVQM4GetLastError(SeqObj *seqobj);
+int HVQM4GetLastCudaError(void);
+
+/* Frees everything HVQM4SetBuffer allocated behind the work buffer (the SDK has no such call). */
+void HVQM4ReleaseBuffer(SeqObj *seqobj);
+
+/* Drop-in mode caches a device copy of every host frame buffer it has written, keyed by
+   the host address.  Call this if the application modified such a buffer itself. */
+void HVQM4InvalidateFrame(SeqObj *seqobj, void *host_frame);
+
+/* ---------------------------------------------------------------- batched decoding
+ * A batch is a pool of `n_streams` independent streams of identical geometry living on
+ * one GPU: three device-resident frame surfaces per stream (past/present/future, rotated
+ * by the library with the reference's rule), per-stream host entropy state, a pool of
+ * host threads, and double-buffered pinned/device symbol arenas so that the entropy
+ * decode of step k+1 overlaps the upload and reconstruction of step k.
+ */
+typedef struct HVQM4Batch HVQM4Batch;
+
+/* device < 0: current device.  host_threads <= 0: one per online CPU (capped at 64). */
+HVQM4Batch *HVQM4BatchCreate(int device, int n_streams, int width, int height, int version, int host_threads);
+void HVQM4BatchDestroy(HVQM4Batch *b);
+
+/*
+ * One step: decodes one picture for each listed stream (each stream at most once per
+ * step).  frame_types[i] is 0x10 (I), 0x20 (P) or 0x30 (B) (h4m:2065-2070); frames[i]
+ * points 4 bytes into the record like the SDK calls; frame_bytes[i] is the number of
+ * readable bytes there.  Returns after the kernels are enqueued (asynchronous); returns
+ * an OR of error bits.
+ */
+int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, const int32_t *frame_types,
+                     const uint8_t *const *frames, const uint32_t *frame_bytes);
+
+/* Waits for all enqueued work; returns accumulated error bits and clears them. */
+int HVQM4BatchSync(HVQM4Batch *b);
+
+/* Copies the most recently decoded picture of a stream (width*height*3/2 bytes) to host
+   memory.  Synchronous. */
+int HVQM4BatchReadFrame(HVQM4Batch *b, int stream_id, void *host_dst);
+
+/* Asynchronous variant for pipelines: enqueues the device->host copy (host_dst should be
+   pinned, see HVQM4HostAlloc) behind the step's kernel; complete after HVQM4BatchSync. */
+int HVQM4BatchReadFrameAsync(HVQM4Batch *b, int stream_id, void *host_dst);
+
+/* Same for n streams: frame of stream_ids[i] goes to host_base + i * host_stride. */
+int HVQM4BatchReadFramesAsync(HVQM4Batch *b, int n, const int32_t *stream_ids, void *host_base, size_t host_stride);
+
+/* Device pointer of the most recently decoded picture of a stream (zero-copy consumers). */
+void *HVQM4BatchFramePtr(HVQM4Batch *b, int stream_id);
+
+/*
+ * Reconstruction-only replay, used for kernel measurements: HVQM4BatchDecode with
+ * `keep` steps recorded leaves each step's symbol buffers resident in device memory;
+ * HVQM4BatchReplay re-launches the reconstruction kernels of the recorded steps in
+ * order (no host stage, no upload) and returns the time the kernels took on the GPU,
+ * measured with CUDA events on the launching stream, in milliseconds (< 0 on error).
+ */
+int HVQM4BatchRecord(HVQM4Batch *b, int enable);
+float HVQM4BatchReplay(HVQM4Batch *b, int repeats);
+
+/* Counters since creation: out[0] pictures, out[1] kernel launches, out[2] symbol bytes
+   uploaded, out[3] algorithmic bytes (frame bytes written + reference bytes predicted from
+   + symbol bytes), out[4] host-stage nanoseconds summed over threads, out[5] inter-coded
+   macroblocks, out[6] total macroblocks, out[7] reserved. */
+void HVQM4BatchStats(HVQM4Batch *b, uint64_t out[8]);
+
+/* Number of reconstruction kernel launches issued by this process so far (all batches and
+   SDK-mode decodes); used by benchmarks to report how much work really ran on the GPU. */
+long long HVQM4KernelLaunches(void);
+
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA toolchain. */
+void *HVQM4HostAlloc(size_t bytes);
+void HVQM4HostFree(void *p);
+
+/* ---------------------------------------------------------------- container helper
+ * Minimal .h4m walker (header h4m:2175-2247, GOP blocks h4m:2429-2438, frame records
+ * h4m:2456-2458) so that harnesses need not re-implement it.  Not needed by the decoder.
+ */
+typedef struct HVQM4FileInfo
+{
+    int32_t version;       /* 13 or 15 */
+    int32_t width, height;
+    int32_t h_samp, v_samp;
+    int32_t n_gops, n_video_frames;
+    int32_t usec_per_frame;
+} HVQM4FileInfo;
+
+typedef struct HVQM4FrameRef
+{
+    uint32_t offset;       /* of the picture header inside the file image (record + 4) */
+    uint32_t bytes;        /* record size - 4 */
+    uint16_t frame_type;   /* 0x10 / 0x20 / 0x30 */
+    uint16_t gop;
+    uint32_t disp_id;      /* display index inside the GOP (h4m:2085) */
+} HVQM4FrameRef;
+
+/* Returns the number of video frames (<0 on a malformed container); fills at most
+   max_frames entries. */
+int HVQM4ParseFile(const uint8_t *data, size_t len, HVQM4FileInfo *info, HVQM4FrameRef *frames, int max_frames);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,62 @@
+"""Shared helpers for the tests (pure Python container walk, emulation driver)."""
+import ctypes
+import hashlib
+import struct
+
+import numpy as np
+
+I_FRAME, P_FRAME, B_FRAME = 0x10, 0x20, 0x30
+
+
+def demux(data: bytes):
+    """-> (version, width, height, [(frame_type, disp_id, picture bytes)]) following
+    /root/reference/h4m_audio_decode.c:2192-2211 (header), 2429-2438 (GOP), 2456-2458 (record)."""
+    version = 15 if data[:9] == b"HVQM4 1.5" else 13
+    n_gops = struct.unpack(">I", data[0x18:0x1C])[0]
+    w, h = struct.unpack(">HH", data[0x34:0x38])
+    pos = 0x44
+    recs = []
+    for _ in range(n_gops):
+        nv, na = struct.unpack(">II", data[pos + 8:pos + 16])
+        pos += 20
+        while nv or na:
+            id1, id2, size = struct.unpack(">HHI", data[pos:pos + 8])
+            pos += 8
+            if id1 == 1:
+                recs.append((id2, struct.unpack(">I", data[pos:pos + 4])[0], data[pos + 4:pos + size]))
+                nv -= 1
+            else:
+                na -= 1
+            pos += size
+    return version, w, h, recs
+
+
+def emul_decode(lib, data: bytes):
+    """Host stage (entropy.c) + CPU emulation of the kernel work order; yields (type, yuv bytes, err)."""
+    version, w, h, recs = demux(data)
+    seq = lib.h4e_seq_create(w, h, 2, 2, int(version == 15))
+    assert seq
+    fb = w * h * 3 // 2
+    bufs = [np.zeros(fb + 64, np.uint8) for _ in range(3)]
+    past, present, future = 0, 1, 2
+    try:
+        for ty, _, pic in recs:
+            if ty != B_FRAME:
+                past, future = future, past
+            padded = pic + b"\0" * 8
+            n = lib.h4e_parse_begin(seq, ty, padded, len(pic))
+            assert n > 0
+            blob = np.zeros(n, np.uint8)
+            err = lib.h4e_parse_finish(seq, blob.ctypes.data)
+            fut = bufs[present] if ty == P_FRAME else bufs[future]
+            rc = lib.emul_recon_picture(blob.ctypes.data, bufs[present].ctypes.data, bufs[past].ctypes.data, fut.ctypes.data)
+            assert rc == 0, f"segment table / prefix sum disagree ({rc})"
+            yield ty, bufs[present][:fb].tobytes(), err
+            if ty != B_FRAME:
+                present, future = future, present
+    finally:
+        lib.h4e_seq_destroy(seq)
+
+
+def md5(b: bytes) -> str:
+    return hashlib.md5(b).hexdigest()
