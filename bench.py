@@ -54,9 +54,11 @@ def env_int(name, default):
         return default
 
 
-def gen_streams(rank: int, count: int, profile: int):
-    from hvqm4_b200 import synth
-    return [synth.generate(W, H, 15, GOP, 1, seed=BASE_SEED + rank * DISTINCT_STREAMS + i, profile=profile) for i in range(count)]
+def gen_streams(rank: int, world: int, per_gpu: int, count: int, profile: int):
+    """The first `count` distinct bitstreams of this rank's slab of streams (hvqm4_b200/shard.py)."""
+    from hvqm4_b200 import shard, synth
+    ids = shard.rank_streams(rank, world, per_gpu)[:count]
+    return [synth.generate(W, H, 15, GOP, 1, seed=shard.stream_seed(BASE_SEED, s), profile=profile) for s in ids]
 
 
 class ClockSampler:
@@ -141,7 +143,7 @@ def cpu_reference_run(streams, seconds_target: float, nproc: int):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    streams = gen_streams(0, 1, args.profile)
+    streams = gen_streams(0, 1, args.streams_per_gpu, 1, args.profile)
     nproc = os.cpu_count() or 1
     t0 = time.perf_counter()
     total_frames, total_wall, base = 0, 0.0, None
@@ -207,7 +209,7 @@ def main():
 
     S = args.streams_per_gpu
     distinct = min(S, DISTINCT_STREAMS)
-    files = gen_streams(rank, distinct, args.profile)
+    files = gen_streams(rank, world, S, distinct, args.profile)
     parsed = [api.parse_file(f) for f in files]
     bufs = [ctypes.create_string_buffer(f, len(f) + 8) for f in files]
     bases = [ctypes.addressof(b) for b in bufs]

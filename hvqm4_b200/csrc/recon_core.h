@@ -12,7 +12,15 @@
  * The functions are __host__ __device__ so that tests/emul/ can run the very same code
  * serially on the CPU before a GPU is available (test infrastructure; the product only
  * ever calls them from the CUDA kernels).  A block's result is returned as four 32-bit
- * words, one per row, leftmost pixel in the low byte, ready for a 4-byte store.
+ * words, one per row, leftmost pixel in the low byte.
+ *
+ * Data-parallel formulation (what makes the kernel cheap per block):
+ *   - a basis row (4 samples, step 1 or 2) is ONE 32-bit load from a table that holds, for
+ *     every nest row y and start x, the 8 nibbles x..x+7 (rc_build_nest_table), or two
+ *     64-bit loads from the reference frame for the inter "window" nest;
+ *   - the four half-sample filters are one branch-free formula (rc_predict):
+ *     (p00 + p01 + p10 + p11 + 2) >> 2 with p01/p10/p11 aliased to p00 when the phase bit
+ *     is 0 -- (4a+2)>>2 = a, (2a+2b+2)>>2 = (a+b+1)>>1 -- evaluated on packed bytes.
  */
 #ifndef HVQM4_RECON_CORE_H
 #define HVQM4_RECON_CORE_H
@@ -29,18 +37,50 @@
 #if defined(__CUDA_ARCH__)
 #define RC_LD8(p) __ldg((const uint8_t *)(p))
 #define RC_LD32(p) __ldg((const uint32_t *)(p))
+#define RC_LD64(p) __ldg((const unsigned long long *)(p))
+#define RC_PRMT(a, b, s) __byte_perm((a), (b), (s))
 #else
 #define RC_LD8(p) (*(const uint8_t *)(p))
 #define RC_LD32(p) (*(const uint32_t *)(p))
+#define RC_LD64(p) (*(const unsigned long long *)(p))
+static inline uint32_t rc_prmt_host(uint32_t a, uint32_t b, uint32_t s)
+{
+    const uint64_t v = (uint64_t)b << 32 | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+}
+#define RC_PRMT(a, b, s) rc_prmt_host((a), (b), (s))
+#endif
+
+#define RC_NEST_TABLE_WORDS (SYM_NEST_H * 64)
+
+/* The three lookup tables live at fixed offsets at the start of dynamic shared memory on the
+   GPU (no pointer registers); on the CPU they are reached through the view. */
+#define RC_SMEM_NEST_OFF 0
+#define RC_SMEM_MCDIV_OFF (RC_NEST_TABLE_WORDS * 4)
+#define RC_SMEM_DIV_OFF (RC_SMEM_MCDIV_OFF + 256 * 4)
+#define RC_SMEM_TABLE_BYTES (RC_SMEM_DIV_OFF + 16 * 4)
+#if defined(__CUDACC__)
+extern __shared__ __align__(16) uint8_t rc_smem[];
+#endif
+#if defined(__CUDA_ARCH__)
+#define RC_NEST_TAB(v) (reinterpret_cast<const uint32_t *>(rc_smem + RC_SMEM_NEST_OFF))
+#define RC_MCDIV(v, i) (reinterpret_cast<const int32_t *>(rc_smem + RC_SMEM_MCDIV_OFF)[i])
+#define RC_DIV(v, i) (reinterpret_cast<const int32_t *>(rc_smem + RC_SMEM_DIV_OFF)[i])
+#else
+#define RC_NEST_TAB(v) ((v).nest_tab)
+#define RC_MCDIV(v, i) ((v).mcdiv_tab[i])
+#define RC_DIV(v, i) ((v).div_tab[i])
 #endif
 
 /* Read-only view of one picture job. */
 struct ReconView
 {
     const uint8_t *blob;       /* symbol buffer (symbuf.h) */
-    const uint8_t *nest;       /* packed nest: shared memory on the GPU, blob memory on the CPU */
+    const uint32_t *nest_tab;  /* rc_build_nest_table() output: shared memory on the GPU */
     const int32_t *div_tab;    /* 16 entries,  h4m:262,270 */
-    const int32_t *mcdiv_tab;  /* 512 entries, h4m:263,272 */
+    const int32_t *mcdiv_tab;  /* 256 entries used of h4m:263,272 */
     const uint8_t *ref[2];     /* past, future frame surfaces (Y|U|V contiguous) */
     int width, height;
     int is_ipic, version15;
@@ -49,10 +89,10 @@ struct ReconView
     int mcb_w;
 };
 
-RC_HD void rc_make_view(ReconView &v, const uint8_t *blob, const SymHeader &h, const uint8_t *nest,
+RC_HD void rc_make_view(ReconView &v, const uint8_t *blob, const SymHeader &h, const uint32_t *nest_tab,
                         const int32_t *div_tab, const int32_t *mcdiv_tab, const uint8_t *past, const uint8_t *future)
 {
-    v.blob = blob; v.nest = nest; v.div_tab = div_tab; v.mcdiv_tab = mcdiv_tab;
+    v.blob = blob; v.nest_tab = nest_tab; v.div_tab = div_tab; v.mcdiv_tab = mcdiv_tab;
     v.ref[0] = past; v.ref[1] = future;
     v.width = h.width; v.height = h.height;
     v.is_ipic = h.pic_type == SYM_PIC_I; v.version15 = h.version15;
@@ -62,17 +102,29 @@ RC_HD void rc_make_view(ReconView &v, const uint8_t *blob, const SymHeader &h, c
     v.mcb_w = h.mcb_w;
 }
 
-RC_HD uint32_t rc_clamp255(int32_t x) { return x < 0 ? 0u : x > 255 ? 255u : (uint32_t)x; }
+/* Entry (y, x), x in 0..63: the nibbles x..x+7 of packed nest row y (zero past column 69). */
+RC_HD uint32_t rc_nest_table_entry(const uint8_t *packed, int y, int x)
+{
+    const uint8_t *row = packed + y * SYM_NEST_ROW_BYTES;
+    uint64_t bits = 0;
+    const int b0 = x >> 1;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+        if (b0 + i < SYM_NEST_ROW_BYTES) bits |= (uint64_t)row[b0 + i] << (8 * i);
+    return (uint32_t)(bits >> ((x & 1) * 4));
+}
 
-/* byte-wise (a + b + 1) >> 1 on four packed bytes: (a|b) - (((a^b) & 0xFE..) >> 1) */
-RC_HD uint32_t rc_avg4(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) & 0xFEFEFEFEu) >> 1); }
+/* runtime-indexed picks without a local-memory array */
+RC_HD uint32_t rc_pick3(const uint32_t a[3], int i) { return i == 0 ? a[0] : i == 1 ? a[1] : a[2]; }
+
+RC_HD uint32_t rc_clamp255(int32_t x) { return x < 0 ? 0u : x > 255 ? 255u : (uint32_t)x; }
 
 /* byte-wise (a + b + c + d + 2) >> 2 on four packed bytes, via two 16-bit lanes */
 RC_HD uint32_t rc_avg4x4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
     const uint32_t M = 0x00FF00FFu;
-    uint32_t lo = (a & M) + (b & M) + (c & M) + (d & M) + 0x00020002u;
-    uint32_t hi = ((a >> 8) & M) + ((b >> 8) & M) + ((c >> 8) & M) + ((d >> 8) & M) + 0x00020002u;
+    const uint32_t lo = (a & M) + (b & M) + (c & M) + (d & M) + 0x00020002u;
+    const uint32_t hi = ((a >> 8) & M) + ((b >> 8) & M) + ((c >> 8) & M) + ((d >> 8) & M) + 0x00020002u;
     return ((lo >> 2) & M) | (((hi >> 2) & M) << 8);
 }
 
@@ -83,133 +135,186 @@ RC_HD uint32_t rc_avg4x4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
  * (sum + 4) by 8 as an UNSIGNED number and then clamps: sums <= -5 -> 255, -4..-1 -> 0. */
 RC_HD uint32_t rc_sat_mean8(int32_t sum)
 {
-    uint32_t q = ((uint32_t)sum + 4u) >> 3;
+    const uint32_t q = ((uint32_t)sum + 4u) >> 3;
     return q > 255u ? 255u : q;
 }
 
 RC_HD void rc_weighted(uint32_t rows[4], int V, int T, int B, int L, int R)
 {
-    const int rt[4] = {2 * T - B - V, V - B, V - T, 2 * B - T - V};
-    const int ct[4] = {2 * L - R - V, V - R, V - L, 2 * R - L - V};
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-    {
-        const int base = 8 * V + rt[r];
-        rows[r] = rc_sat_mean8(base + ct[0]) | rc_sat_mean8(base + ct[1]) << 8 |
-                  rc_sat_mean8(base + ct[2]) << 16 | rc_sat_mean8(base + ct[3]) << 24;
-    }
+    const int c0 = 2 * L - R - V, c1 = V - R, c2 = V - L, c3 = 2 * R - L - V;
+    const int r0 = 7 * V + 2 * T - B, r1 = 9 * V - B, r2 = 9 * V - T, r3 = 7 * V + 2 * B - T;
+    /* r_k = 8V + rowterm[k] */
+#define RC_WROW(b) (rc_sat_mean8((b) + c0) | rc_sat_mean8((b) + c1) << 8 | rc_sat_mean8((b) + c2) << 16 | rc_sat_mean8((b) + c3) << 24)
+    rows[0] = RC_WROW(r0);
+    rows[1] = RC_WROW(r1);
+    rows[2] = RC_WROW(r2);
+    rows[3] = RC_WROW(r3);
+#undef RC_WROW
 }
 
 /* ---- AOT bases (h4m:679-817) --------------------------------------------------------
- * word: bits 15:0 descriptor ([5:0] x, [10:6] y, [11] x step 2, [12] y step 2,
+ * side word: bits 15:0 descriptor ([5:0] x, [10:6] y, [11] x step 2, [12] y step 2,
  * [14:13] scale offset, [15] negate), bits 23:16 scale symbol (>> 2). */
 
-/* sample of the packed I-picture nest */
-RC_HD int rc_nest_at(const uint8_t *nest, int x, int y)
+/* four samples of one basis row as packed bytes, from the I-picture nest table */
+RC_HD uint32_t rc_row_nest(const uint32_t *tab, int y, int ox, uint32_t step2)
 {
-    return (nest[y * SYM_NEST_ROW_BYTES + (x >> 1)] >> ((x & 1) * 4)) & 0xF;
+    const uint32_t w = tab[y * 64 + ox];
+    if (step2) return w & 0x0F0F0F0Fu;                 /* nibbles 0,2,4,6 */
+    uint32_t x = w & 0xFFFFu;                          /* nibbles 0,1,2,3 -> one per byte */
+    x = (x | x << 8) & 0x00FF00FFu;
+    return (x | x << 4) & 0x0F0F0F0Fu;
 }
 
-template <bool kWindow>
-RC_HD void rc_add_basis(const ReconView &v, uint32_t word, const uint8_t *src, int src_stride,
-                        int32_t &scale_sum, int32_t acc[16])
+/* same from the reference-frame window: sample = (pixel >> 4) & 0xF (h4m:756-761) */
+RC_HD uint32_t rc_row_window(const uint8_t *p, uint32_t step2)
 {
-    const int ox = word & 0x3F, oy = (word >> 6) & 0x1F;
-    const int xs = 1 + ((word >> 11) & 1), ys = 1 + ((word >> 12) & 1);
+    const uint32_t a = (uint32_t)((uintptr_t)p & 7);
+    const uint8_t *base = p - a;
+    const uint64_t lo = RC_LD64(base), hi = RC_LD64(base + 8);
+    const uint64_t bytes = a ? (lo >> (8 * a)) | (hi << (64 - 8 * a)) : lo;   /* the 8 bytes at p */
+    const uint32_t b03 = (uint32_t)bytes, b47 = (uint32_t)(bytes >> 32);
+    const uint32_t v = step2 ? RC_PRMT(b03, b47, 0x6420) : b03;
+    return (v >> 4) & 0x0F0F0F0Fu;
+}
+
+/* accumulates one basis given its four packed rows */
+RC_HD void rc_accumulate(const ReconView &v, uint32_t word, const uint32_t R[4], int32_t &scale_sum, int32_t acc[16])
+{
     int b[16];
-    int lo = 15, hi = 0;
 #pragma unroll
     for (int y = 0; y < 4; ++y)
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
-        {
-            int s;
-            if (kWindow) s = (RC_LD8(src + (oy + y * ys) * src_stride + ox + x * xs) >> 4) & 0xF;   /* h4m:756-761 */
-            else s = rc_nest_at(src, ox + x * xs, oy + y * ys);
-            b[y * 4 + x] = s;
-            lo = s < lo ? s : lo;
-            hi = s > hi ? s : hi;
-        }
+        for (int x = 0; x < 4; ++x) b[y * 4 + x] = (int)((R[y] >> (8 * x)) & 0xFF);
+    int lo = b[0], hi = b[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i)
+    {
+        lo = b[i] < lo ? b[i] : lo;
+        hi = b[i] > hi ? b[i] : hi;
+    }
     scale_sum += (int32_t)((word >> 16) & 0xFF) << 2;            /* cumulative within the block, h4m:726,781 */
-    int32_t inv = v.div_tab[hi - lo];
+    int32_t inv = RC_DIV(v, hi - lo);
     if (word & 0x8000) inv = -inv;
     const uint32_t factor = (uint32_t)(scale_sum + (int32_t)((word >> 13) & 3)) * (uint32_t)inv;
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = (int32_t)((uint32_t)acc[i] + factor * (uint32_t)b[i]);   /* mod 2^32 */
 }
 
-template <bool kWindow>
-RC_HD int32_t rc_aot_sum(const ReconView &v, const uint32_t *side, int n, const uint8_t *src, int src_stride, int32_t acc[16])
+/* window == nullptr: intra (nest table); else inter (reference luma window, stride = luma width) */
+RC_HD void rc_add_basis(const ReconView &v, uint32_t word, const uint8_t *window, int32_t &scale_sum, int32_t acc[16])
+{
+    const int ox = word & 0x3F, oy = (word >> 6) & 0x1F;
+    const uint32_t xs2 = (word >> 11) & 1;
+    const int ys = 1 + ((word >> 12) & 1);
+    uint32_t R[4];
+    if (window)
+    {
+        const uint8_t *p = window + oy * v.width + ox;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) R[y] = rc_row_window(p + y * ys * v.width, xs2);
+    }
+    else
+    {
+#pragma unroll
+        for (int y = 0; y < 4; ++y) R[y] = rc_row_nest(RC_NEST_TAB(v), oy + y * ys, ox, xs2);
+    }
+    rc_accumulate(v, word, R, scale_sum, acc);
+}
+
+RC_HD int32_t rc_aot_sum(const ReconView &v, const uint32_t *side, int n, const uint8_t *window, int32_t acc[16])
 {
     int32_t scale_sum = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0;
-    for (int k = 0; k < n; ++k) rc_add_basis<kWindow>(v, RC_LD32(side + k), src, src_stride, scale_sum, acc);
+    for (int k = 0; k < n; ++k) rc_add_basis(v, RC_LD32(side + k), window, scale_sum, acc);
     uint32_t total = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) total += (uint32_t)acc[i];
     return (int32_t)total >> 4;                                   /* arithmetic, h4m:793,815 */
 }
 
-/* ---- half-sample prediction (h4m:1242-1294) -------------------------------------------
- * Fetches the 4x4 prediction whose top-left integer sample is `src` with phase (hx,hy).
+/* IntraAotBlock, h4m:1358-1377 */
+RC_HD void rc_intra_aot(const ReconView &v, uint32_t rows[4], const uint32_t *side, int n, int V)
+{
+    int32_t acc[16];
+    const int32_t mean = rc_aot_sum(v, side, n, nullptr, acc);
+    const int32_t delta = (int32_t)((uint32_t)V << v.unk_shift) - mean;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+    {
+        uint32_t out = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) out |= rc_clamp255((acc[r * 4 + c] + delta) >> v.unk_shift) << (8 * c);
+        rows[r] = out;
+    }
+}
+
+/* ---- half-sample prediction (h4m:1242-1294), branch-free on the phase ------------------
  * Rows are read as two aligned 32-bit words (covers the 5 bytes a row can need). */
 RC_HD void rc_predict(uint32_t rows[4], const uint8_t *src, int stride, int hx, int hy)
 {
     const uint32_t a = (uint32_t)((uintptr_t)src & 3);
     const uint8_t *base = src - a;
     uint32_t A[5], Bx[5];
-    const int nrow = 4 + hy;
 #pragma unroll
     for (int r = 0; r < 5; ++r)
     {
-        if (r < nrow)
+        if (r < 4 || hy)
         {
             const uint32_t w0 = RC_LD32(base + r * stride), w1 = RC_LD32(base + r * stride + 4);
             const uint64_t w = ((uint64_t)w1 << 32 | w0) >> (8 * a);
             A[r] = (uint32_t)w;
-            Bx[r] = (uint32_t)(w >> 8);
+            Bx[r] = hx ? (uint32_t)(w >> 8) : A[r];
         }
         else
             A[r] = Bx[r] = 0;
     }
+    if (!hx && !hy)
+    {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) rows[r] = A[r];
+        return;
+    }
 #pragma unroll
     for (int r = 0; r < 4; ++r)
     {
-        if (!hx && !hy) rows[r] = A[r];
-        else if (hx && !hy) rows[r] = rc_avg4(A[r], Bx[r]);
-        else if (!hx && hy) rows[r] = rc_avg4(A[r], A[r + 1]);
-        else rows[r] = rc_avg4x4(A[r], Bx[r], A[r + 1], Bx[r + 1]);
+        const uint32_t C = hy ? A[r + 1] : A[r], D = hy ? Bx[r + 1] : Bx[r];
+        rows[r] = rc_avg4x4(A[r], Bx[r], C, D);
     }
 }
 
-/* ---- predicted AOT block (h4m:1379-1420) ---------------------------------------------- */
-RC_HD void rc_predicted_aot(const ReconView &v, uint32_t rows[4], const uint32_t *side, int nibble,
-                            const uint8_t *window, int window_stride)
+/* ---- predicted AOT block (h4m:1379-1420); rows[] holds the MC prediction on entry ------
+ * The prediction stays packed in rows[]: its sum is four byte-wise dot products with 1, its
+ * range a min/max over transient byte extracts; samples are re-extracted in the output loop,
+ * so only the 16 accumulators stay live across the basis loop. */
+RC_HD uint32_t rc_sum4(uint32_t packed, uint32_t acc)
+{
+#if defined(__CUDA_ARCH__)
+    return __dp4a(packed, 0x01010101u, acc);
+#else
+    return acc + (packed & 0xFF) + ((packed >> 8) & 0xFF) + ((packed >> 16) & 0xFF) + (packed >> 24);
+#endif
+}
+
+RC_HD void rc_predicted_aot(const ReconView &v, uint32_t rows[4], const uint32_t *side, int nibble, const uint8_t *window)
 {
     int32_t acc[16];
-    const uint32_t aot_mean = (uint32_t)rc_aot_sum<true>(v, side, nibble - 1, window, window_stride, acc);
+    const uint32_t aot_mean = (uint32_t)rc_aot_sum(v, side, nibble - 1, window, acc);
     const uint32_t pair = RC_LD32(side + nibble - 1);
-    int m[16];
-    int32_t mean = 8;
+    const int32_t mean = (int32_t)(rc_sum4(rows[3], rc_sum4(rows[2], rc_sum4(rows[1], rc_sum4(rows[0], 8u)))) >> 4);
+    int32_t lo = 255, hi = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i)
     {
-        m[i] = (rows[i >> 2] >> ((i & 3) * 8)) & 0xFF;
-        mean += m[i];
-    }
-    mean >>= 4;                                                   /* non-negative: same as /16 */
-    int32_t lo = m[0] - mean, hi = lo;
-#pragma unroll
-    for (int i = 1; i < 16; ++i)
-    {
-        const int32_t d = m[i] - mean;
-        lo = d < lo ? d : lo;
-        hi = d > hi ? d : hi;
+        const int32_t m = (int32_t)((rows[i >> 2] >> ((i & 3) * 8)) & 0xFF);
+        lo = m < lo ? m : lo;
+        hi = m > hi ? m : hi;
     }
     const int32_t s1 = (int32_t)(int16_t)(pair & 0xFFFF), s2 = (int32_t)(int16_t)(pair >> 16);
-    const uint32_t addend = ((uint32_t)s1 << v.unk_shift) - aot_mean;
-    const uint32_t factor = (uint32_t)s2 * (uint32_t)v.mcdiv_tab[hi - lo];
+    const uint32_t factor = (uint32_t)s2 * (uint32_t)RC_MCDIV(v, hi - lo);   /* range of (m - mean) = range of m */
+    /* acc + addend + (m - mean) * factor  =  acc + (addend - mean * factor) + m * factor */
+    const uint32_t addend = ((uint32_t)s1 << v.unk_shift) - aot_mean - (uint32_t)mean * factor;
 #pragma unroll
     for (int r = 0; r < 4; ++r)
     {
@@ -217,95 +322,128 @@ RC_HD void rc_predicted_aot(const ReconView &v, uint32_t rows[4], const uint32_t
 #pragma unroll
         for (int c = 0; c < 4; ++c)
         {
-            const int i = r * 4 + c;
-            const int32_t res = (int32_t)((uint32_t)acc[i] + addend + (uint32_t)(m[i] - mean) * factor);
-            out |= rc_clamp255((res >> v.unk_shift) + m[i]) << (8 * c);
+            const uint32_t m = (rows[r] >> (8 * c)) & 0xFF;
+            const int32_t res = (int32_t)((uint32_t)acc[r * 4 + c] + addend + m * factor);
+            out |= rc_clamp255((res >> v.unk_shift) + (int32_t)m) << (8 * c);
         }
         rows[r] = out;
     }
 }
 
-/* ---- one block, all cases --------------------------------------------------------------
- * plane/bx/by: block position; t: its type byte; side: its words in the side array. */
-RC_HD void rc_block(const ReconView &v, int plane, int bx, int by, uint32_t t, const uint32_t *side, uint32_t rows[4])
+/* ---- block classes -----------------------------------------------------------------------
+ * RC_DIRECT  flat DC or raw: a handful of instructions, done while classifying
+ * RC_WEIGHTED weighted DC fill (needs the four neighbour cells)
+ * RC_MC      motion compensation only (proc-1 macroblock, or nibble 0 of a proc-0 one)
+ * RC_AOT_INTRA / RC_AOT_INTER  blocks with a basis loop */
+enum { RC_DIRECT = 0, RC_WEIGHTED = 1, RC_MC = 2, RC_AOT_INTRA = 3, RC_AOT_INTER = 4, RC_NCLASS = 5 };
+
+RC_HD int rc_classify(uint32_t t, int is_ipic)
+{
+    const uint32_t nib = is_ipic ? t : (t & 0xF);
+    if (!is_ipic && (t & 0x60))
+    {
+        if (t & 0x10) return RC_MC;
+        return nib == 0 ? RC_MC : nib == 6 ? RC_DIRECT : RC_AOT_INTER;
+    }
+    return nib == 0 ? RC_WEIGHTED : (nib == 8 || nib == 6) ? RC_DIRECT : RC_AOT_INTRA;
+}
+
+struct RcMotion
+{
+    const uint8_t *src;      /* integer-sample position of this 4x4 block in the reference plane */
+    const uint8_t *window;   /* origin of the 70x38 luma window (h4m:1864-1868) */
+    int stride, hx, hy;
+    bool poisoned;
+};
+
+/* per-plane MC address and phase of the block at (plane,bx,by) of an inter macroblock */
+RC_HD void rc_motion(const ReconView &v, int plane, int bx, int by, uint32_t t, RcMotion &m)
 {
     const int sh = plane ? 1 : 0;
     const int pw = v.width >> sh;
-    const int bstride = (pw >> 2) + 2;
-    const bool inter = !v.is_ipic && (t & 0x60);
+    const int mx = bx >> (1 - sh), my = by >> (1 - sh);
+    const uint32_t mvw = RC_LD32(v.blob + v.off_mv + 4 * (my * v.mcb_w + mx));
+    const int rx = (int16_t)(mvw & 0xFFFF), ry = (int16_t)(mvw >> 16);
+    m.poisoned = rx == -32768;                        /* SYM_ERR_MV_RANGE: never dereference */
+    const uint8_t *ref = ((t >> 5) & 3) == 2 ? v.ref[1] : v.ref[0];
+    const int px = rx >> sh, py = ry >> sh;
+    m.hx = rx & 1; m.hy = ry & 1;                     /* 1.3: luma phase for every plane (h4m:1329-1330,1869-1870) */
+    if (v.version15) { m.hx = px & 1; m.hy = py & 1; }/* 1.5: per-plane phase (h4m:1337-1343,1890-1896) */
+    const int plane_off = plane == 0 ? 0 : plane == 1 ? v.width * v.height : v.width * v.height + (v.width >> 1) * (v.height >> 1);
+    /* linear addressing, no clamping (h4m:1344,1897); sub-block offset = pb_offset (h4m:866-869) */
+    const int subx = plane == 0 ? (bx & 1) * 4 : 0, suby = plane == 0 ? (by & 1) * 4 : 0;
+    m.src = ref + plane_off + ((py >> 1) + suby) * pw + (px >> 1) + subx;
+    m.window = ref + rx / 2 + (ry / 2 - 16) * v.width - 32;
+    m.stride = pw;
+}
+
+/* flat DC (nibble 8) or raw (nibble 6) */
+RC_HD void rc_direct_block(const ReconView &v, int plane, int bx, int by, uint32_t t, const uint32_t *side, uint32_t rows[4])
+{
     const uint32_t nib = v.is_ipic ? t : (t & 0xF);
-
-    if (!inter)
-    {
-        const uint8_t *tmap = v.blob + v.off_type[plane] + (by + 1) * bstride + bx + 1;
-        const uint8_t *dmap = v.blob + v.off_dc[plane] + (by + 1) * bstride + bx + 1;
-        const int V = RC_LD8(dmap);
-        if (nib == 0)
-        {
-            /* neighbour DC only if (type & 0x77) == 0, else own DC; borders carry type 0xFF.
-               In I pictures the left neighbour is tracked as "type 0 or 8" (h4m:1441-1454). */
-            const uint32_t tT = RC_LD8(tmap - bstride), tB = RC_LD8(tmap + bstride), tL = RC_LD8(tmap - 1), tR = RC_LD8(tmap + 1);
-            const int T = (tT & 0x77) ? V : RC_LD8(dmap - bstride);
-            const int B = (tB & 0x77) ? V : RC_LD8(dmap + bstride);
-            const int R = (tR & 0x77) ? V : RC_LD8(dmap + 1);
-            const bool left_ok = v.is_ipic ? (tL == 0 || tL == 8) : !(tL & 0x77);
-            const int L = left_ok ? RC_LD8(dmap - 1) : V;
-            rc_weighted(rows, V, T, B, L, R);
-        }
-        else if (nib == 8)
-        {
-            rows[0] = rows[1] = rows[2] = rows[3] = (uint32_t)V * 0x01010101u;
-        }
-        else if (nib == 6)
-        {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) rows[r] = RC_LD32(side + r);
-        }
-        else
-        {   /* IntraAotBlock, h4m:1358-1377 */
-            int32_t acc[16];
-            const int32_t mean = rc_aot_sum<false>(v, side, (int)nib, v.nest, 0, acc);
-            const int32_t delta = (int32_t)((uint32_t)V << v.unk_shift) - mean;
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-            {
-                uint32_t out = 0;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) out |= rc_clamp255((acc[r * 4 + c] + delta) >> v.unk_shift) << (8 * c);
-                rows[r] = out;
-            }
-        }
-        return;
-    }
-
-    /* inter macroblock */
-    if (nib == 6 && !(t & 0x10))
+    if (nib == 6)
     {
 #pragma unroll
         for (int r = 0; r < 4; ++r) rows[r] = RC_LD32(side + r);
         return;
     }
-    const int mx = bx >> (1 - sh), my = by >> (1 - sh);
-    const uint32_t mvw = RC_LD32(v.blob + v.off_mv + 4 * (my * v.mcb_w + mx));
-    const int rx = (int16_t)(mvw & 0xFFFF), ry = (int16_t)(mvw >> 16);
-    if (rx == -32768)
-    {   /* poisoned by the host stage (SYM_ERR_MV_RANGE): never dereference */
-        rows[0] = rows[1] = rows[2] = rows[3] = 0x80808080u;
-        return;
+    const int bstride = ((v.width >> (plane ? 1 : 0)) >> 2) + 2;
+    const uint32_t V = RC_LD8(v.blob + rc_pick3(v.off_dc, plane) + (by + 1) * bstride + bx + 1);
+    rows[0] = rows[1] = rows[2] = rows[3] = V * 0x01010101u;
+}
+
+RC_HD void rc_weighted_block(const ReconView &v, int plane, int bx, int by, uint32_t rows[4])
+{
+    const int bstride = ((v.width >> (plane ? 1 : 0)) >> 2) + 2;
+    const uint8_t *tmap = v.blob + rc_pick3(v.off_type, plane) + (by + 1) * bstride + bx + 1;
+    const uint8_t *dmap = v.blob + rc_pick3(v.off_dc, plane) + (by + 1) * bstride + bx + 1;
+    const int V = RC_LD8(dmap);
+    /* neighbour DC only if (type & 0x77) == 0, else own DC; borders carry type 0xFF.
+       In I pictures the left neighbour is tracked as "type 0 or 8" (h4m:1441-1454). */
+    const uint32_t tT = RC_LD8(tmap - bstride), tB = RC_LD8(tmap + bstride), tL = RC_LD8(tmap - 1), tR = RC_LD8(tmap + 1);
+    const int T = (tT & 0x77) ? V : RC_LD8(dmap - bstride);
+    const int B = (tB & 0x77) ? V : RC_LD8(dmap + bstride);
+    const int R = (tR & 0x77) ? V : RC_LD8(dmap + 1);
+    const bool left_ok = v.is_ipic ? (tL == 0 || tL == 8) : !(tL & 0x77);
+    const int L = left_ok ? RC_LD8(dmap - 1) : V;
+    rc_weighted(rows, V, T, B, L, R);
+}
+
+RC_HD void rc_mc_block(const ReconView &v, int plane, int bx, int by, uint32_t t, uint32_t rows[4])
+{
+    RcMotion m;
+    rc_motion(v, plane, bx, by, t, m);
+    if (m.poisoned) { rows[0] = rows[1] = rows[2] = rows[3] = 0x80808080u; return; }
+    rc_predict(rows, m.src, m.stride, m.hx, m.hy);
+}
+
+RC_HD void rc_aot_intra_block(const ReconView &v, int plane, int bx, int by, uint32_t t, const uint32_t *side, uint32_t rows[4])
+{
+    const int bstride = ((v.width >> (plane ? 1 : 0)) >> 2) + 2;
+    const int V = RC_LD8(v.blob + rc_pick3(v.off_dc, plane) + (by + 1) * bstride + bx + 1);
+    rc_intra_aot(v, rows, side, (int)(v.is_ipic ? t : (t & 0xF)), V);
+}
+
+RC_HD void rc_aot_inter_block(const ReconView &v, int plane, int bx, int by, uint32_t t, const uint32_t *side, uint32_t rows[4])
+{
+    RcMotion m;
+    rc_motion(v, plane, bx, by, t, m);
+    if (m.poisoned) { rows[0] = rows[1] = rows[2] = rows[3] = 0x80808080u; return; }
+    rc_predict(rows, m.src, m.stride, m.hx, m.hy);
+    rc_predicted_aot(v, rows, side, (int)(t & 0xF), m.window);
+}
+
+/* one block, all cases (used by the CPU emulation; the kernel drains one class at a time) */
+RC_HD void rc_block(const ReconView &v, int plane, int bx, int by, uint32_t t, const uint32_t *side, uint32_t rows[4])
+{
+    switch (rc_classify(t, v.is_ipic))
+    {
+    case RC_AOT_INTRA: rc_aot_intra_block(v, plane, bx, by, t, side, rows); break;
+    case RC_AOT_INTER: rc_aot_inter_block(v, plane, bx, by, t, side, rows); break;
+    case RC_WEIGHTED: rc_weighted_block(v, plane, bx, by, rows); break;
+    case RC_MC: rc_mc_block(v, plane, bx, by, t, rows); break;
+    default: rc_direct_block(v, plane, bx, by, t, side, rows); break;
     }
-    const uint8_t *ref = v.ref[((t >> 5) & 3) - 1];
-    const int px = rx >> sh, py = ry >> sh;
-    int hx = rx & 1, hy = ry & 1;                    /* 1.3: luma phase for every plane (h4m:1329-1330,1869-1870) */
-    if (v.version15) { hx = px & 1; hy = py & 1; }   /* 1.5: per-plane phase (h4m:1337-1343,1890-1896) */
-    const int plane_off = plane == 0 ? 0 : plane == 1 ? v.width * v.height : v.width * v.height + (v.width >> 1) * (v.height >> 1);
-    /* linear addressing, no clamping (h4m:1344,1897); sub-block offset = pb_offset (h4m:866-869) */
-    const int subx = plane == 0 ? (bx & 1) * 4 : 0, suby = plane == 0 ? (by & 1) * 4 : 0;
-    const uint8_t *src = ref + plane_off + ((py >> 1) + suby) * pw + (px >> 1) + subx;
-    rc_predict(rows, src, pw, hx, hy);
-    if ((t & 0x10) || nib == 0) return;
-    /* 70x38 window of the reference luma, origin (rx/2 - 32, ry/2 - 16) (h4m:1864-1868) */
-    const uint8_t *window = ref + rx / 2 + (ry / 2 - 16) * v.width - 32;
-    rc_predicted_aot(v, rows, side, (int)nib, window, v.width);
 }
 
 #endif

@@ -32,8 +32,12 @@ int emul_recon_picture(const uint8_t *blob, uint8_t *present, const uint8_t *pas
     SymHeader h;
     memcpy(&h, blob, sizeof h);
     if (h.magic != SYM_MAGIC) return -1;
+    static uint32_t nest_tab[RC_NEST_TABLE_WORDS];
+    if (h.has_nest)
+        for (int y = 0; y < SYM_NEST_H; ++y)
+            for (int x = 0; x < 64; ++x) nest_tab[y * 64 + x] = rc_nest_table_entry(blob + h.off_nest, y, x);
     ReconView v;
-    rc_make_view(v, blob, h, h.has_nest ? blob + h.off_nest : nullptr, g_div, g_mcdiv, past, future);
+    rc_make_view(v, blob, h, nest_tab, g_div, g_mcdiv, past, future);
     const uint32_t *seg = (const uint32_t *)(blob + h.off_seg);
     const uint32_t *side = (const uint32_t *)(blob + h.off_side);
     uint8_t *planes[3] = {present, present + h.width * h.height, present + h.width * h.height * 5 / 4};
