@@ -147,8 +147,10 @@ def run_reference_arm(args, rank, world):
     nproc = os.cpu_count() or 1
     t0 = time.perf_counter()
     total_frames, total_wall, base = 0, 0.0, None
+    # every step is a bounded sample; the whole arm is kept near 75 s whatever K and W are
+    per_step = min(args.ref_seconds, 75.0 / max(1, args.warmup + args.steps))
     for i in range(args.warmup + args.steps):
-        base, _ = cpu_reference_run(streams, args.ref_seconds, nproc)
+        base, _ = cpu_reference_run(streams, per_step, nproc)
         if i >= args.warmup:
             total_frames += base["value"] * base["wall_s"]
             total_wall += base["wall_s"]

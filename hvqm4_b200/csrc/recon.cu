@@ -43,16 +43,16 @@ namespace {
 
 constexpr int kTileLumaBytes = 8 * 128;
 constexpr int kTileBytes = kTileLumaBytes + 2 * 4 * 64;   /* 1536 per segment */
-constexpr int kSegsPerIter = 2;                           /* segments a warp classifies and drains together */
-constexpr int kSlots = kSegsPerIter * 96;
 constexpr int kQueues = 4;                                /* weighted, MC, intra AOT, predicted AOT */
 
-struct __align__(16) WarpScratch
+/* kSegs = segments a warp classifies and drains together (1 or 2) */
+template <int kSegs>
+struct __align__(16) WarpScratchT
 {
-    uint32_t tile[kSegsPerIter][kTileBytes / 4];
-    uint16_t queue[kQueues][kSlots];                      /* entry: [7:0] slot, [15:8] type byte */
-    uint16_t side_off[kSlots];                            /* side-word offset of the slot relative to its pass base */
-    uint32_t pass_base[kSegsPerIter * 3 + 2];
+    uint32_t tile[kSegs][kTileBytes / 4];
+    uint16_t queue[kQueues][kSegs * 96];                  /* entry: [7:0] slot, [15:8] type byte */
+    uint16_t side_off[kSegs * 96];                        /* side-word offset of the slot relative to its pass base */
+    uint32_t pass_base[kSegs * 3 + 2];
 };
 
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t &total)
@@ -78,7 +78,7 @@ struct Slot
 /* (row, first macroblock) of the segments of the current iteration, warp-uniform */
 struct IterGeom
 {
-    int row[kSegsPerIter], mx0[kSegsPerIter];
+    int row[2], mx0[2];
 };
 
 __device__ __forceinline__ Slot decode_slot(int slot, const IterGeom &g)
@@ -105,7 +105,8 @@ __device__ __forceinline__ Slot decode_slot(int slot, const IterGeom &g)
     return s;
 }
 
-__device__ __forceinline__ void tile_put(WarpScratch &ws, const Slot &s, const uint32_t rows[4])
+template <typename WS>
+__device__ __forceinline__ void tile_put(WS &ws, const Slot &s, const uint32_t rows[4])
 {
     const int stride = s.plane ? 16 : 32;
     uint32_t *t = ws.tile[s.seg] + s.tile_word;
@@ -113,10 +114,11 @@ __device__ __forceinline__ void tile_put(WarpScratch &ws, const Slot &s, const u
     for (int r = 0; r < 4; ++r) t[r * stride] = rows[r];
 }
 
-template <int kWarps, int kItersPerWarp, int kMinBlocks>
+template <int kWarps, int kItersPerWarp, int kMinBlocks, int kSegsPerIter>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 recon_pictures_kernel(const ReconJob *__restrict__ jobs, int units_per_pic, int ctas_per_pic)
 {
+    using WarpScratch = WarpScratchT<kSegsPerIter>;
     /* dynamic shared memory: [nest table | mcdiv | div] (fixed offsets, recon_core.h) then one scratch per warp */
     WarpScratch *s_warp = reinterpret_cast<WarpScratch *>(rc_smem + RC_SMEM_TABLE_BYTES);
     uint32_t *s_nest_tab = reinterpret_cast<uint32_t *>(rc_smem + RC_SMEM_NEST_OFF);
@@ -125,38 +127,32 @@ recon_pictures_kernel(const ReconJob *__restrict__ jobs, int units_per_pic, int 
 
     const int job = blockIdx.x / ctas_per_pic;
     const int cta = blockIdx.x - job * ctas_per_pic;
-    const ReconJob J = jobs[job];
 
-    /* the scalar header fields this kernel needs (uniform loads, read-only path) */
-    const uint32_t *__restrict__ hw = reinterpret_cast<const uint32_t *>(J.blob);
-    const uint32_t w2 = __ldg(hw + 2), w3 = __ldg(hw + 3), w4 = __ldg(hw + 4), w6 = __ldg(hw + 6), w7 = __ldg(hw + 7);
-    SymHeader h;
-    h.width = (uint16_t)(w2 & 0xFFFF);
-    h.height = (uint16_t)(w2 >> 16);
-    h.pic_type = (uint8_t)(w3 & 0xFF);
-    h.version15 = (uint8_t)((w3 >> 8) & 0xFF);
-    h.unk_shift = (uint8_t)(w3 >> 24);
-    h.has_nest = (uint8_t)(w4 & 0xFF);
-    h.mcb_w = (uint16_t)(w6 & 0xFFFF);
-    h.mcb_h = (uint16_t)(w6 >> 16);
-    h.nseg = (uint16_t)(w7 & 0xFFFF);
-#pragma unroll
-    for (int p = 0; p < 3; ++p)
+    /* Picture parameters live in shared memory (one ReconView per CTA) instead of ~50 registers per
+       thread: every field is a constant-offset LDS away and nothing stays live across the drains. */
+    static_assert(sizeof(ReconView) <= 256, "ReconView must fit its shared-memory slot");
+    ReconView &vw = *reinterpret_cast<ReconView *>(rc_smem + RC_SMEM_VIEW_OFF);
+    if (threadIdx.x == 0)
     {
-        h.off_type[p] = __ldg(hw + 8 + p);
-        h.off_dc[p] = __ldg(hw + 11 + p);
+        const ReconJob J = jobs[job];
+        SymHeader h;
+        const uint4 *src = reinterpret_cast<const uint4 *>(J.blob);
+        uint4 *dst = reinterpret_cast<uint4 *>(&h);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) dst[i] = __ldg(src + i);     /* header fields end at byte 76 */
+        rc_make_view(vw, J.blob, h, nullptr, nullptr, nullptr, J.past, J.future);
+        vw.present = J.present;
     }
-    h.off_mv = __ldg(hw + 14);
-    const uint32_t off_seg = __ldg(hw + 15), off_nest = __ldg(hw + 16), off_side = __ldg(hw + 17);
-
-    /* constants of h4m:262-273 and the nest table */
+    /* constants of h4m:262-273 */
     for (int i = threadIdx.x; i < 256; i += kWarps * 32) s_mcdiv[i] = i ? 0x1000 / i : 0;
     if (threadIdx.x < 16) s_div[threadIdx.x] = threadIdx.x ? 0x1000 / (threadIdx.x * 16) * 16 : 0;
-    if (h.has_nest)
+    __syncthreads();
+    const ReconView &v = vw;
+    if (v.has_nest)
     {
         /* stage the packed rows (35 B) at a 40-byte pitch, zero padded, in scratch that is free until the barrier */
         uint8_t *packed = reinterpret_cast<uint8_t *>(s_warp);
-        const uint8_t *src = J.blob + off_nest;
+        const uint8_t *src = v.blob + v.off_nest;
         for (int i = threadIdx.x; i < SYM_NEST_H * 40; i += kWarps * 32)
         {
             const int y = i / 40, x = i - y * 40;
@@ -174,17 +170,18 @@ recon_pictures_kernel(const ReconJob *__restrict__ jobs, int units_per_pic, int 
             s_nest_tab[y * 64 + 2 * j] = lo;
             s_nest_tab[y * 64 + 2 * j + 1] = (lo >> 4) | (hi << 28);
         }
+        __syncthreads();
     }
-    __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    ReconView v;
-    rc_make_view(v, J.blob, h, nullptr, nullptr, nullptr, J.past, J.future);
-    const uint32_t *__restrict__ side = reinterpret_cast<const uint32_t *>(J.blob + off_side);
-    const uint32_t *__restrict__ segtab = reinterpret_cast<const uint32_t *>(J.blob + off_seg);
     WarpScratch &ws = s_warp[warp];
-    const int W = h.width, H = h.height, nseg = h.nseg, mcb_w = h.mcb_w;
     const uint32_t lt_mask = (1u << lane) - 1u;
+#define W (v.width)
+#define H (v.height)
+#define nseg (v.nseg)
+#define mcb_w (v.mcb_w)
+#define side (v.side)
+#define segtab (v.segtab)
 
 #pragma unroll 1
     for (int it = 0; it < kItersPerWarp; ++it)
@@ -194,9 +191,9 @@ recon_pictures_kernel(const ReconJob *__restrict__ jobs, int units_per_pic, int 
         const int n_units = min(kSegsPerIter, units_per_pic - unit0);
         IterGeom geom;
 #pragma unroll
-        for (int u = 0; u < kSegsPerIter; ++u)
+        for (int u = 0; u < 2; ++u)
         {
-            const int unit = min(unit0 + u, units_per_pic - 1);
+            const int unit = min(unit0 + (u < kSegsPerIter ? u : 0), units_per_pic - 1);
             geom.row[u] = unit / nseg;
             geom.mx0[u] = (unit - geom.row[u] * nseg) * SYM_SEG_MCBS;
         }
@@ -211,7 +208,7 @@ recon_pictures_kernel(const ReconJob *__restrict__ jobs, int units_per_pic, int 
             const bool valid = s.plane ? s.bx < mcb_w : s.bx < mcb_w * 2;
             const int bstride = ((s.plane ? W >> 1 : W) >> 2) + 2;
             uint32_t t = 0;
-            if (valid) t = __ldg(J.blob + rc_pick3(h.off_type, s.plane) + (s.by + 1) * bstride + s.bx + 1);
+            if (valid) t = __ldg(v.blob + rc_pick3(v.off_type, s.plane) + (s.by + 1) * bstride + s.bx + 1);
             const uint32_t nwords = valid ? sym_side_words(t, v.is_ipic) : 0u;
             uint32_t total;
             const uint32_t rel = warp_excl_scan(nwords, total);
@@ -290,8 +287,8 @@ recon_pictures_kernel(const ReconJob *__restrict__ jobs, int units_per_pic, int 
         {
             const int row = u ? geom.row[1] : geom.row[0], mx0 = u ? geom.mx0[1] : geom.mx0[0];
             const int valid_mcbs = min(SYM_SEG_MCBS, mcb_w - mx0);
-            uint8_t *const y_dst = J.present + (size_t)(row * 8) * W + mx0 * 8;
-            uint8_t *const u_dst = J.present + (size_t)W * H + (size_t)(row * 4) * (W >> 1) + mx0 * 4;
+            uint8_t *const y_dst = v.present + (size_t)(row * 8) * W + mx0 * 8;
+            uint8_t *const u_dst = v.present + (size_t)W * H + (size_t)(row * 4) * (W >> 1) + mx0 * 4;
             uint8_t *const v_dst = u_dst + (size_t)(W >> 1) * (H >> 1);
             const uint32_t *tile = ws.tile[u];
             if ((W & 31) == 0)
@@ -323,20 +320,27 @@ recon_pictures_kernel(const ReconJob *__restrict__ jobs, int units_per_pic, int 
         }
         __syncwarp();
     }
+#undef W
+#undef H
+#undef nseg
+#undef mcb_w
+#undef side
+#undef segtab
 }
 
-template <int kWarps, int kItersPerWarp, int kMinBlocks>
+template <int kWarps, int kItersPerWarp, int kMinBlocks, int kSegsPerIter = 2>
 int launch(const ReconJob *d_jobs, int n_jobs, int units, cudaStream_t stream)
 {
+    using WarpScratch = WarpScratchT<kSegsPerIter>;
     const int per_cta = kWarps * kItersPerWarp * kSegsPerIter;
     const int ctas_per_pic = (units + per_cta - 1) / per_cta;
     const long long grid = (long long)ctas_per_pic * n_jobs;
     if (grid > 0x7FFFFFFFll) return (int)cudaErrorInvalidConfiguration;
     constexpr size_t smem = sizeof(WarpScratch) * kWarps + RC_SMEM_TABLE_BYTES;
-    static const cudaError_t attr = cudaFuncSetAttribute(recon_pictures_kernel<kWarps, kItersPerWarp, kMinBlocks>,
+    static const cudaError_t attr = cudaFuncSetAttribute(recon_pictures_kernel<kWarps, kItersPerWarp, kMinBlocks, kSegsPerIter>,
                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (attr != cudaSuccess) return (int)attr;
-    recon_pictures_kernel<kWarps, kItersPerWarp, kMinBlocks><<<(unsigned)grid, kWarps * 32, smem, stream>>>(d_jobs, units, ctas_per_pic);
+    recon_pictures_kernel<kWarps, kItersPerWarp, kMinBlocks, kSegsPerIter><<<(unsigned)grid, kWarps * 32, smem, stream>>>(d_jobs, units, ctas_per_pic);
     return (int)cudaGetLastError();
 }
 
@@ -356,10 +360,15 @@ extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w,
     {
     case 1: return launch<4, 1, 1>(d_jobs, n_jobs, units, stream);
     case 2: return launch<4, 2, 6>(d_jobs, n_jobs, units, stream);
-    case 3: return launch<4, 2, 8>(d_jobs, n_jobs, units, stream);
+    case 3: return launch<4, 2, 7>(d_jobs, n_jobs, units, stream);
     case 4: return launch<8, 2, 3>(d_jobs, n_jobs, units, stream);
     case 5: return launch<8, 2, 4>(d_jobs, n_jobs, units, stream);
-    case 6: return launch<4, 4, 6>(d_jobs, n_jobs, units, stream);
+    case 6: return launch<4, 4, 7>(d_jobs, n_jobs, units, stream);
+    case 7: return launch<8, 4, 3, 1>(d_jobs, n_jobs, units, stream);
+    case 8: return launch<8, 2, 3, 1>(d_jobs, n_jobs, units, stream);
+    case 9: return launch<4, 4, 6, 1>(d_jobs, n_jobs, units, stream);
+    case 10: return launch<16, 2, 1, 1>(d_jobs, n_jobs, units, stream);
+    case 11: return launch<12, 2, 2, 1>(d_jobs, n_jobs, units, stream);
     default: break;
     }
     /* few pictures: many small CTAs (latency); large batches: amortise the per-CTA nest table */

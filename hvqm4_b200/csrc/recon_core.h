@@ -60,7 +60,8 @@ static inline uint32_t rc_prmt_host(uint32_t a, uint32_t b, uint32_t s)
 #define RC_SMEM_NEST_OFF 0
 #define RC_SMEM_MCDIV_OFF (RC_NEST_TABLE_WORDS * 4)
 #define RC_SMEM_DIV_OFF (RC_SMEM_MCDIV_OFF + 256 * 4)
-#define RC_SMEM_TABLE_BYTES (RC_SMEM_DIV_OFF + 16 * 4)
+#define RC_SMEM_VIEW_OFF (RC_SMEM_DIV_OFF + 16 * 4)
+#define RC_SMEM_TABLE_BYTES (RC_SMEM_VIEW_OFF + 256)   /* ReconView of the CTA's picture lives in shared memory too */
 #if defined(__CUDACC__)
 extern __shared__ __align__(16) uint8_t rc_smem[];
 #endif
@@ -87,6 +88,11 @@ struct ReconView
     int unk_shift;
     uint32_t off_type[3], off_dc[3], off_mv;
     int mcb_w;
+    /* used by the kernel only */
+    uint8_t *present;
+    const uint32_t *side, *segtab;
+    int nseg, mcb_h, has_nest;
+    uint32_t off_nest;
 };
 
 RC_HD void rc_make_view(ReconView &v, const uint8_t *blob, const SymHeader &h, const uint32_t *nest_tab,
@@ -100,6 +106,11 @@ RC_HD void rc_make_view(ReconView &v, const uint8_t *blob, const SymHeader &h, c
     for (int p = 0; p < 3; ++p) { v.off_type[p] = h.off_type[p]; v.off_dc[p] = h.off_dc[p]; }
     v.off_mv = h.off_mv;
     v.mcb_w = h.mcb_w;
+    v.present = nullptr;
+    v.side = reinterpret_cast<const uint32_t *>(blob + h.off_side);
+    v.segtab = reinterpret_cast<const uint32_t *>(blob + h.off_seg);
+    v.nseg = h.nseg; v.mcb_h = h.mcb_h; v.has_nest = h.has_nest;
+    v.off_nest = h.off_nest;
 }
 
 /* Entry (y, x), x in 0..63: the nibbles x..x+7 of packed nest row y (zero past column 69). */
