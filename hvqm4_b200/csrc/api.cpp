@@ -183,6 +183,7 @@ struct RecordedStep
 {
     uint8_t *d = nullptr;   /* jobs + blobs */
     int n = 0;
+    uint32_t rec_ctas = 0;
 };
 
 struct HVQM4Batch
@@ -351,6 +352,18 @@ H4_API int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, con
         b->recorded.push_back(r);
         d_base = r.d;
     }
+    /* record-kernel CTA ranges (chunk counts are known since phase A) */
+    ReconJob *jobs = reinterpret_cast<ReconJob *>(a.h);
+    uint32_t rec_ctas = 0;
+    for (int i = 0; i < n; ++i)
+    {
+        const uint32_t chunks = h4e_last_chunks(b->st[stream_ids[i]].seq);
+        jobs[i].rec_cta_begin = rec_ctas;
+        jobs[i].n_chunks = chunks;
+        jobs[i].pad[0] = jobs[i].pad[1] = 0;
+        rec_ctas += hvqm4_rec_ctas(chunks);
+    }
+    if (b->recording) b->recorded.back().rec_ctas = rec_ctas;
     /* phase B: side words, motion vectors, maps -> pinned arena */
     std::atomic<uint32_t> err{0};
     std::atomic<uint64_t> inter{0};
@@ -360,7 +373,6 @@ H4_API int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, con
         inter += h4e_last_inter_mcbs(seq);
     });
     /* rotation (h4m:2087-2093, 2131-2137) and job descriptors */
-    ReconJob *jobs = reinterpret_cast<ReconJob *>(a.h);
     for (int i = 0; i < n; ++i)
     {
         StreamState &s = b->st[stream_ids[i]];
@@ -386,13 +398,15 @@ H4_API int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, con
         cudaStreamWaitEvent(b->s_comp, b->ev_d2h, 0);
         b->d2h_pending = false;
     }
-    int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(d_base), n, b->mcb_w, b->mcb_h, b->s_comp);
+    int launched = 0;
+    int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(d_base), n, b->mcb_w, b->mcb_h, rec_ctas, b->s_comp, &launched);
+    g_launches += launched;
+    b->stats[1] += (uint64_t)launched;
     if (rc != 0)
     {
         cuda_ok((cudaError_t)rc, "recon kernel launch");
         return HVQM4_ERR_CUDA;
     }
-    ++g_launches;
     cudaEventRecord(a.consumed, b->s_comp);
     cudaEventRecord(b->ev_kernel, b->s_comp);
     a.in_flight = true;
@@ -400,7 +414,6 @@ H4_API int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, con
 
     const uint64_t mcbs = (uint64_t)b->mcb_w * b->mcb_h * n;
     b->stats[0] += n;
-    b->stats[1] += 1;
     b->stats[2] += total;
     b->stats[3] += (uint64_t)n * b->frame_bytes + inter.load() * 96 + (total - jobs_bytes);
     b->stats[5] += inter.load();
@@ -482,14 +495,15 @@ H4_API float HVQM4BatchReplay(HVQM4Batch *b, int repeats)
     for (int r = 0; r < repeats; ++r)
         for (auto &st : b->recorded)
         {
-            int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(st.d), st.n, b->mcb_w, b->mcb_h, b->s_comp);
+            int launched = 0;
+            int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(st.d), st.n, b->mcb_w, b->mcb_h, st.rec_ctas, b->s_comp, &launched);
+            g_launches += launched;
+            b->stats[1] += (uint64_t)launched;
             if (rc != 0)
             {
                 cuda_ok((cudaError_t)rc, "recon kernel launch");
                 return -1.f;
             }
-            ++g_launches;
-            b->stats[1] += 1;
         }
     cudaEventRecord(b->ev_t1, b->s_comp);
     if (!cuda_ok(cudaEventSynchronize(b->ev_t1), "cudaEventSynchronize")) return -1.f;
@@ -650,12 +664,17 @@ void compat_decode(SeqObj *so, int type, const uint8_t *frame, void *present, vo
     job->present = d_present;
     job->past = d_past;
     job->future = d_future;
+    job->rec_cta_begin = 0;
+    job->n_chunks = h4e_last_chunks(c->seq);
+    job->pad[0] = job->pad[1] = 0;
     bool ok = cuda_ok(cudaMemcpyAsync(c->d_blob, c->h_blob, total, cudaMemcpyHostToDevice, c->stream), "upload symbols");
     if (ok)
     {
-        int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(c->d_blob), 1, c->mcb_w, c->mcb_h, c->stream);
+        int launched = 0;
+        int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(c->d_blob), 1, c->mcb_w, c->mcb_h,
+                                    hvqm4_rec_ctas(job->n_chunks), c->stream, &launched);
+        g_launches += launched;
         ok = rc == 0 || cuda_ok((cudaError_t)rc, "recon kernel launch");
-        if (rc == 0) ++g_launches;
     }
     if (ok && !is_device_ptr(present))
         ok = cuda_ok(cudaMemcpyAsync(present, d_present, c->frame_bytes, cudaMemcpyDeviceToHost, c->stream), "download frame");

@@ -208,14 +208,17 @@ struct H4Seq
     uint8_t *type[3], *dc[3];            /* bordered, persistent (h4m:1001-1040) */
     uint8_t nest[SYM_NEST_BYTES];        /* packed nibbles of the last I picture's nest */
     HTab tree[6];
-    uint32_t *blk_off[3];                /* side-word offset of every block (work order) */
-    uint32_t *seg;                       /* nseg*mbh + 1 */
+    int nbands, ngroups;                 /* record groups: [class][band][length bucket] */
+    uint32_t *grp_count, *grp_base, *grp_next, *grp_chunk;
+    uint32_t *chunks;                    /* chunk table under construction (2 words per chunk) */
+    uint32_t chunks_cap;
     uint32_t errors_total;
 
     /* per picture, between parse_begin and parse_finish */
     int pic_type;
     uint32_t err;
-    uint32_t n_side;
+    uint32_t n_rec_words, n_chunks, n_chunks_nest, n_records;
+    uint32_t *rec_base;                  /* records region inside the blob being written */
     uint32_t n_inter_mcb;
     int need_nest;
     int dc_shift, unk_shift, rb[2][2];
@@ -252,7 +255,6 @@ H4Seq *h4e_seq_create(int width, int height, int h_samp, int v_samp, int version
         s->map_cells[p] = (size_t)s->stride[p] * (s->bh[p] + 2);
         s->type[p] = malloc(s->map_cells[p]);
         s->dc[p] = malloc(s->map_cells[p]);
-        s->blk_off[p] = calloc((size_t)s->bw[p] * s->bh[p], sizeof(uint32_t));
         /* border cells {0x7F, 0xFF} (h4m:951-955); payload starts zeroed */
         memset(s->type[p], 0, s->map_cells[p]);
         memset(s->dc[p], 0, s->map_cells[p]);
@@ -264,7 +266,15 @@ H4Seq *h4e_seq_create(int width, int height, int h_samp, int v_samp, int version
                     s->dc[p][y * s->stride[p] + x] = 0x7F;
                 }
     }
-    s->seg = calloc((size_t)s->nseg * s->mbh + 1, sizeof(uint32_t));
+    s->nbands = (s->mbh + SYM_BAND_MCB_ROWS - 1) / SYM_BAND_MCB_ROWS;
+    s->ngroups = SYM_REC_CLASSES * s->nbands * SYM_LEN_BUCKETS;
+    s->grp_count = calloc((size_t)s->ngroups, sizeof(uint32_t));
+    s->grp_base = calloc((size_t)s->ngroups, sizeof(uint32_t));
+    s->grp_next = calloc((size_t)s->ngroups, sizeof(uint32_t));
+    s->grp_chunk = calloc((size_t)s->ngroups, sizeof(uint32_t));
+    /* upper bound on chunks: one per group plus one per 32 blocks, or one per block in the long bucket */
+    s->chunks_cap = (uint32_t)s->ngroups + (uint32_t)(s->bw[0] * s->bh[0] + 2 * s->bw[1] * s->bh[1]);
+    s->chunks = calloc((size_t)s->chunks_cap * 2, sizeof(uint32_t));
     return s;
 }
 
@@ -275,9 +285,12 @@ void h4e_seq_destroy(H4Seq *s)
     {
         free(s->type[p]);
         free(s->dc[p]);
-        free(s->blk_off[p]);
     }
-    free(s->seg);
+    free(s->grp_count);
+    free(s->grp_base);
+    free(s->grp_next);
+    free(s->grp_chunk);
+    free(s->chunks);
     free(s);
 }
 
@@ -286,6 +299,7 @@ uint32_t h4e_seq_errors(const H4Seq *s) { return s->errors_total; }
 size_t h4e_frame_bytes(const H4Seq *s) { return (size_t)s->width * s->height * 3 / 2; }
 
 uint32_t h4e_last_inter_mcbs(const H4Seq *s) { return s->n_inter_mcb; }
+uint32_t h4e_last_chunks(const H4Seq *s) { return s->n_chunks; }
 
 void h4e_seq_dims(const H4Seq *s, int out[6])
 {
@@ -330,57 +344,106 @@ static void open_bytes(H4Seq *s, ByteSec *b, const uint8_t *data, size_t len, ui
     b->pos = 0;
 }
 
-/* ------------------------------------------------------------------ work-order offsets */
+/* ------------------------------------------------------------------ record groups */
 
-/* intra AOT blocks (not raw, not inter) gather from the I-picture nest */
-static inline int block_needs_nest(uint32_t t, uint32_t n_words, int is_ipic)
+static inline int len_bucket(uint32_t len) { return len < SYM_LEN_BUCKETS ? (int)len - 1 : SYM_LEN_BUCKETS - 1; }
+static inline int group_of(const H4Seq *s, int cls, int band, uint32_t len)
 {
-    if (!n_words) return 0;
-    if (is_ipic) return t != 6;
-    return !(t & 0x60) && (t & 0xF) != 6;
+    return (cls * s->nbands + band) * SYM_LEN_BUCKETS + len_bucket(len);
 }
 
-/* Assigns every block its slot in the side-word array, in the order the warps of
-   recon.cu walk the picture (see symbuf.h), and fills the segment table. */
-static void assign_offsets(H4Seq *s, int is_ipic)
+/*
+ * Counts the records of every (class, band, length) group from the final type maps, lays the
+ * groups out back to back (class-major, so that raw/intra chunks precede inter chunks) and
+ * builds the chunk table.  Records of the last bucket ("long", >= SYM_LEN_BUCKETS words: only
+ * I-picture luma types > 16, which no encoder emits) have individual lengths; they are packed
+ * in emission order and get one chunk each.
+ */
+static void plan_records(H4Seq *s, int is_ipic)
 {
-    uint32_t word = 0;
+    memset(s->grp_count, 0, (size_t)s->ngroups * sizeof(uint32_t));
+    memset(s->grp_next, 0, (size_t)s->ngroups * sizeof(uint32_t));
+    /* long-bucket word totals live in grp_base until the prefix pass below */
+    memset(s->grp_base, 0, (size_t)s->ngroups * sizeof(uint32_t));
     int need_nest = 0;
-    for (int row = 0; row < s->mbh; ++row)
-        for (int sg = 0; sg < s->nseg; ++sg)
+    uint32_t n_records = 0;
+    for (int p = 0; p < 3; ++p)
+        for (int by = 0; by < s->bh[p]; ++by)
         {
-            s->seg[row * s->nseg + sg] = word;
-            int mx0 = sg * SYM_SEG_MCBS, mx1 = mx0 + SYM_SEG_MCBS;
-            if (mx1 > s->mbw) mx1 = s->mbw;
-            for (int half = 0; half < 2; ++half)
+            const uint8_t *ty = s->type[p] + cell_at(s, p, 0, by);
+            const int band = (p ? by : by >> 1) / SYM_BAND_MCB_ROWS;
+            for (int bx = 0; bx < s->bw[p]; ++bx)
             {
-                int by = row * 2 + half;
-                const uint8_t *ty = s->type[0] + cell_at(s, 0, 0, by);
-                uint32_t *off = s->blk_off[0] + (size_t)by * s->bw[0];
-                for (int bx = mx0 * 2; bx < mx1 * 2; ++bx)
-                {
-                    uint32_t t = ty[bx], n = sym_side_words(t, is_ipic);
-                    off[bx] = word;
-                    word += n;
-                    need_nest |= block_needs_nest(t, n, is_ipic);
-                }
-            }
-            for (int p = 1; p < 3; ++p)
-            {
-                const uint8_t *ty = s->type[p] + cell_at(s, p, 0, row);
-                uint32_t *off = s->blk_off[p] + (size_t)row * s->bw[p];
-                for (int bx = mx0; bx < mx1; ++bx)
-                {
-                    uint32_t t = ty[bx], n = sym_side_words(t, is_ipic);
-                    off[bx] = word;
-                    word += n;
-                    need_nest |= block_needs_nest(t, n, is_ipic);
-                }
+                int cls = 0;
+                const uint32_t len = sym_record_len(ty[bx], is_ipic, &cls);
+                if (!len) continue;
+                const int g = group_of(s, cls, band, len);
+                s->grp_count[g]++;
+                if (len >= SYM_LEN_BUCKETS) s->grp_base[g] += len;
+                need_nest |= cls == SYM_REC_INTRA;
+                ++n_records;
             }
         }
-    s->seg[s->nseg * s->mbh] = word;
-    s->n_side = word;
+    uint32_t word = 0, chunk = 0;
+    s->n_chunks_nest = 0;
+    for (int cls = 0; cls < SYM_REC_CLASSES; ++cls)
+    {
+        for (int band = 0; band < s->nbands; ++band)
+            for (int lb = 0; lb < SYM_LEN_BUCKETS; ++lb)
+            {
+                const int g = (cls * s->nbands + band) * SYM_LEN_BUCKETS + lb;
+                const uint32_t n = s->grp_count[g];
+                const uint32_t long_words = s->grp_base[g];
+                s->grp_base[g] = word;
+                s->grp_chunk[g] = chunk;
+                if (!n) continue;
+                if (lb < SYM_LEN_BUCKETS - 1)
+                {
+                    const uint32_t len = (uint32_t)lb + 1;
+                    for (uint32_t i = 0; i < n; i += SYM_CHUNK)
+                    {
+                        const uint32_t cnt = n - i < SYM_CHUNK ? n - i : SYM_CHUNK;
+                        s->chunks[2 * chunk] = word + i * len;
+                        s->chunks[2 * chunk + 1] = cnt | (len - 1) << 8 | (uint32_t)cls << 16;
+                        ++chunk;
+                    }
+                    word += n * len;
+                }
+                else
+                {   /* one chunk per long record, filled in when the record is placed */
+                    chunk += n;
+                    word += long_words;
+                }
+            }
+        if (cls == SYM_REC_INTRA) s->n_chunks_nest = chunk;
+    }
+    s->n_rec_words = word;
+    s->n_chunks = chunk;
+    s->n_records = n_records;
     s->need_nest = is_ipic ? 1 : need_nest;
+}
+
+/* Reserves the record of the block (plane,bx,by) with type byte t; returns its payload (word 1..). */
+static inline uint32_t *place_record(H4Seq *s, uint32_t t, int is_ipic, int p, int bx, int by)
+{
+    int cls = 0;
+    const uint32_t len = sym_record_len(t, is_ipic, &cls);
+    const int band = (p ? by : by >> 1) / SYM_BAND_MCB_ROWS;
+    const int g = group_of(s, cls, band, len);
+    uint32_t at;
+    if (len < SYM_LEN_BUCKETS)
+        at = s->grp_base[g] + s->grp_next[g]++ * len;
+    else
+    {
+        const uint32_t c = s->grp_chunk[g]++;
+        at = s->grp_base[g];
+        s->grp_base[g] += len;
+        s->chunks[2 * c] = at;
+        s->chunks[2 * c + 1] = 1u | ((len - 1) & 0xFF) << 8 | (uint32_t)cls << 16;
+    }
+    uint32_t *rec = s->rec_base + at;
+    rec[0] = sym_record_header(t, p, bx, by);
+    return rec + 1;
 }
 
 static void plan_blob(H4Seq *s)
@@ -399,8 +462,8 @@ static void plan_blob(H4Seq *s)
     h->mcb_h = (uint16_t)s->mbh;
     h->nseg = (uint16_t)s->nseg;
     size_t at = sizeof(SymHeader);
-    h->off_seg = (uint32_t)at;
-    at = align16(at + ((size_t)s->nseg * s->mbh + 1) * 4);
+    h->off_chunks = (uint32_t)at;
+    at = align16(at + (size_t)s->n_chunks * 8);
     if (s->pic_type != SYM_PIC_I)
     {
         h->off_mv = (uint32_t)at;
@@ -421,9 +484,12 @@ static void plan_blob(H4Seq *s)
         h->off_nest = (uint32_t)at;
         at = align16(at + SYM_NEST_BYTES);
     }
-    h->off_side = (uint32_t)at;
-    h->n_side_words = s->n_side;
-    at = align16(at + (size_t)s->n_side * 4);
+    h->off_rec = (uint32_t)at;
+    h->n_rec_words = s->n_rec_words;
+    h->n_chunks = s->n_chunks;
+    h->n_chunks_nest = s->n_chunks_nest;
+    h->n_records = s->n_records;
+    at = align16(at + (size_t)s->n_rec_words * 4);
     h->total_bytes = (uint32_t)at;
     s->blob_bytes = at;
 }
@@ -577,10 +643,14 @@ static inline void emit_pair(H4Seq *s, int p, uint32_t *dst)
     *dst = ((uint32_t)a & 0xFFFF) | (uint32_t)f << 16;
 }
 
-static inline void emit_intra_block(H4Seq *s, int p, uint32_t t, uint32_t *dst)
+/* t = type byte of an intra block (full byte in I pictures, tag | nibble in P/B) */
+static inline void emit_intra_block(H4Seq *s, int p, uint32_t t, int is_ipic, int bx, int by)
 {
-    if (t == 6) emit_raw(s, p, dst);
-    else if (t != 0 && t != 8) emit_bases(s, p, t, dst);
+    const uint32_t nib = is_ipic ? t : (t & 0xF);
+    if (nib == 0 || nib == 8) return;
+    uint32_t *dst = place_record(s, t, is_ipic, p, bx, by);
+    if (nib == 6) emit_raw(s, p, dst);
+    else emit_bases(s, p, nib, dst);
 }
 
 /* ------------------------------------------------------------------ P/B picture, pass 1 */
@@ -756,7 +826,7 @@ static int mcb_refs_in_surface(const H4Seq *s, int32_t rx, int32_t ry, int needs
 }
 
 /* BpicPlaneDec pass 2, h4m:1922-1967, symbol part only */
-static void pb_pass2(H4Seq *s, int16_t *mv_out, uint32_t *side)
+static void pb_pass2(H4Seq *s, int16_t *mv_out)
 {
     int32_t mvx = 0, mvy = 0;
     int cur_ref = -1;
@@ -766,8 +836,6 @@ static void pb_pass2(H4Seq *s, int16_t *mv_out, uint32_t *side)
     {
         const uint8_t *ty0 = s->type[0] + cell_at(s, 0, 0, my * 2);
         const uint8_t *ty1 = s->type[1] + cell_at(s, 1, 0, my), *ty2 = s->type[2] + cell_at(s, 2, 0, my);
-        const uint32_t *of0 = s->blk_off[0] + (size_t)(my * 2) * s->bw[0];
-        const uint32_t *of1 = s->blk_off[1] + (size_t)my * s->bw[1], *of2 = s->blk_off[2] + (size_t)my * s->bw[2];
         for (int mx = 0; mx < s->mbw; ++mx)
         {
             const int lx = mx * 2;
@@ -778,9 +846,9 @@ static void pb_pass2(H4Seq *s, int16_t *mv_out, uint32_t *side)
             {   /* MCBlockDecDCNest, h4m:1789-1827 */
                 mvp[0] = mvp[1] = 0;
                 for (int k = 0; k < 4; ++k)
-                    emit_intra_block(s, 0, ty0[SUBY[k] * st0 + lx + SUBX[k]] & 0xF, side + of0[SUBY[k] * s->bw[0] + lx + SUBX[k]]);
-                emit_intra_block(s, 1, ty1[mx] & 0xF, side + of1[mx]);
-                emit_intra_block(s, 2, ty2[mx] & 0xF, side + of2[mx]);
+                    emit_intra_block(s, 0, ty0[SUBY[k] * st0 + lx + SUBX[k]], 0, lx + SUBX[k], my * 2 + SUBY[k]);
+                emit_intra_block(s, 1, ty1[mx], 0, mx, my);
+                emit_intra_block(s, 2, ty2[mx], 0, mx, my);
                 continue;
             }
             const int ref = mt - 1;
@@ -798,20 +866,14 @@ static void pb_pass2(H4Seq *s, int16_t *mv_out, uint32_t *side)
             {   /* MCBlockDecMCNest, h4m:1871-1909 */
                 for (int k = 0; k < 6; ++k)
                 {
-                    int p = k < 4 ? 0 : k - 3;
-                    uint32_t nib, *dst;
-                    if (k < 4)
-                    {
-                        nib = ty0[SUBY[k] * st0 + lx + SUBX[k]] & 0xF;
-                        dst = side + of0[SUBY[k] * s->bw[0] + lx + SUBX[k]];
-                    }
-                    else
-                    {
-                        nib = (k == 4 ? ty1[mx] : ty2[mx]) & 0xF;
-                        dst = side + (k == 4 ? of1[mx] : of2[mx]);
-                    }
+                    const int p = k < 4 ? 0 : k - 3;
+                    const int bx = k < 4 ? lx + SUBX[k] : mx, by = k < 4 ? my * 2 + SUBY[k] : my;
+                    const uint32_t t = k < 4 ? ty0[SUBY[k] * st0 + lx + SUBX[k]] : k == 4 ? ty1[mx] : ty2[mx];
+                    const uint32_t nib = t & 0xF;
+                    if (!nib) continue;
+                    uint32_t *dst = place_record(s, t, 0, p, bx, by);
                     if (nib == 6) emit_raw(s, p, dst);
-                    else if (nib)
+                    else
                     {
                         emit_bases(s, p, nib - 1, dst);
                         emit_pair(s, p, dst + nib - 1);
@@ -921,7 +983,7 @@ size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_t pic_le
     }
     else
         pb_pass1(s);
-    assign_offsets(s, is_i);
+    plan_records(s, is_i);
     plan_blob(s);
     return s->blob_bytes;
 }
@@ -931,20 +993,19 @@ uint32_t h4e_parse_finish(H4Seq *s, uint8_t *blob)
     const SymHeader *h = &s->hdr;
     const int is_i = s->pic_type == SYM_PIC_I;
     if (s->blob_bytes == 0) return s->err;
-    uint32_t *side = (uint32_t *)(blob + h->off_side);
+    s->rec_base = (uint32_t *)(blob + h->off_rec);
     if (is_i)
     {   /* IpicPlaneDec order: plane by plane, raster (h4m:2011-2015, 1487-1518) */
         for (int p = 0; p < 3; ++p)
             for (int by = 0; by < s->bh[p]; ++by)
             {
                 const uint8_t *ty = s->type[p] + cell_at(s, p, 0, by);
-                const uint32_t *off = s->blk_off[p] + (size_t)by * s->bw[p];
                 for (int bx = 0; bx < s->bw[p]; ++bx)
-                    if (ty[bx] != 0 && ty[bx] != 8) emit_intra_block(s, p, ty[bx], side + off[bx]);
+                    if (ty[bx] != 0 && ty[bx] != 8) emit_intra_block(s, p, ty[bx], 1, bx, by);
             }
     }
     else
-        pb_pass2(s, (int16_t *)(blob + h->off_mv), side);
+        pb_pass2(s, (int16_t *)(blob + h->off_mv));
 
     /* every reader must have stayed inside its section */
     {
@@ -960,7 +1021,7 @@ uint32_t h4e_parse_finish(H4Seq *s, uint8_t *blob)
         else if (br_overrun(&s->mvh) || br_overrun(&s->mvv) || br_overrun(&s->mcbt) || br_overrun(&s->mcbp))
             s->err |= SYM_ERR_TRUNCATED;
     }
-    memcpy(blob + h->off_seg, s->seg, ((size_t)s->nseg * s->mbh + 1) * 4);
+    memcpy(blob + h->off_chunks, s->chunks, (size_t)s->n_chunks * 8);
     for (int p = 0; p < 3; ++p)
     {
         memcpy(blob + h->off_type[p], s->type[p], s->map_cells[p]);

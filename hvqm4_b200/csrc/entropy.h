@@ -44,6 +44,8 @@ uint32_t h4e_parse_finish(H4Seq *s, uint8_t *blob);
 
 /* inter-coded macroblocks of the last parsed picture (for bandwidth accounting) */
 uint32_t h4e_last_inter_mcbs(const H4Seq *s);
+/* record-kernel chunks of the picture planned by the last h4e_parse_begin */
+uint32_t h4e_last_chunks(const H4Seq *s);
 
 /* geometry helpers */
 size_t h4e_frame_bytes(const H4Seq *s);    /* planar Y|U|V bytes = W*H*3/2 */

@@ -4,6 +4,9 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 
+/* chunks (of <= 32 records) one CTA of the record kernel works through */
+#define HVQM4_REC_CHUNKS_PER_CTA 32
+
 /* One picture to reconstruct.  All pointers are device pointers; surfaces are planar
    Y|U|V, contiguous, stride = plane width (the reference's frame layout, h4m:2343-2349). */
 typedef struct ReconJob
@@ -12,13 +15,24 @@ typedef struct ReconJob
     uint8_t *present;
     const uint8_t *past;
     const uint8_t *future;
+    uint32_t rec_cta_begin;  /* first CTA of the record kernel that belongs to this picture (exclusive prefix) */
+    uint32_t n_chunks;       /* chunk-table entries of the picture */
+    uint32_t pad[2];
 } ReconJob;
 
 #ifdef __cplusplus
 extern "C" {
 #endif
-/* Reconstructs n_jobs pictures of identical geometry in one launch.  Returns a cudaError_t. */
-int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, cudaStream_t stream);
+/* CTAs of the record kernel a picture with n_chunks chunks needs */
+static inline uint32_t hvqm4_rec_ctas(uint32_t n_chunks)
+{
+    return (n_chunks + HVQM4_REC_CHUNKS_PER_CTA - 1) / HVQM4_REC_CHUNKS_PER_CTA;
+}
+/* Reconstructs n_jobs pictures of identical geometry: one launch of the map kernel, then (if
+   total_rec_ctas > 0) one launch of the record kernel.  Returns a cudaError_t.  *launches is
+   incremented by the number of kernels launched. */
+int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, uint32_t total_rec_ctas,
+                       cudaStream_t stream, int *launches);
 #ifdef __cplusplus
 }
 #endif

@@ -88,11 +88,11 @@ struct ReconView
     int unk_shift;
     uint32_t off_type[3], off_dc[3], off_mv;
     int mcb_w;
-    /* used by the kernel only */
+    /* used by the kernels only */
     uint8_t *present;
-    const uint32_t *side, *segtab;
+    const uint32_t *rec, *chunks;
     int nseg, mcb_h, has_nest;
-    uint32_t off_nest;
+    uint32_t off_nest, n_chunks, n_chunks_nest;
 };
 
 RC_HD void rc_make_view(ReconView &v, const uint8_t *blob, const SymHeader &h, const uint32_t *nest_tab,
@@ -107,10 +107,10 @@ RC_HD void rc_make_view(ReconView &v, const uint8_t *blob, const SymHeader &h, c
     v.off_mv = h.off_mv;
     v.mcb_w = h.mcb_w;
     v.present = nullptr;
-    v.side = reinterpret_cast<const uint32_t *>(blob + h.off_side);
-    v.segtab = reinterpret_cast<const uint32_t *>(blob + h.off_seg);
+    v.rec = reinterpret_cast<const uint32_t *>(blob + h.off_rec);
+    v.chunks = reinterpret_cast<const uint32_t *>(blob + h.off_chunks);
     v.nseg = h.nseg; v.mcb_h = h.mcb_h; v.has_nest = h.has_nest;
-    v.off_nest = h.off_nest;
+    v.off_nest = h.off_nest; v.n_chunks = h.n_chunks; v.n_chunks_nest = h.n_chunks_nest;
 }
 
 /* Entry (y, x), x in 0..63: the nibbles x..x+7 of packed nest row y (zero past column 69). */
@@ -388,21 +388,6 @@ RC_HD void rc_motion(const ReconView &v, int plane, int bx, int by, uint32_t t, 
     m.stride = pw;
 }
 
-/* flat DC (nibble 8) or raw (nibble 6) */
-RC_HD void rc_direct_block(const ReconView &v, int plane, int bx, int by, uint32_t t, const uint32_t *side, uint32_t rows[4])
-{
-    const uint32_t nib = v.is_ipic ? t : (t & 0xF);
-    if (nib == 6)
-    {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) rows[r] = RC_LD32(side + r);
-        return;
-    }
-    const int bstride = ((v.width >> (plane ? 1 : 0)) >> 2) + 2;
-    const uint32_t V = RC_LD8(v.blob + rc_pick3(v.off_dc, plane) + (by + 1) * bstride + bx + 1);
-    rows[0] = rows[1] = rows[2] = rows[3] = V * 0x01010101u;
-}
-
 RC_HD void rc_weighted_block(const ReconView &v, int plane, int bx, int by, uint32_t rows[4])
 {
     const int bstride = ((v.width >> (plane ? 1 : 0)) >> 2) + 2;
@@ -428,32 +413,68 @@ RC_HD void rc_mc_block(const ReconView &v, int plane, int bx, int by, uint32_t t
     rc_predict(rows, m.src, m.stride, m.hx, m.hy);
 }
 
-RC_HD void rc_aot_intra_block(const ReconView &v, int plane, int bx, int by, uint32_t t, const uint32_t *side, uint32_t rows[4])
-{
-    const int bstride = ((v.width >> (plane ? 1 : 0)) >> 2) + 2;
-    const int V = RC_LD8(v.blob + rc_pick3(v.off_dc, plane) + (by + 1) * bstride + bx + 1);
-    rc_intra_aot(v, rows, side, (int)(v.is_ipic ? t : (t & 0xF)), V);
-}
-
-RC_HD void rc_aot_inter_block(const ReconView &v, int plane, int bx, int by, uint32_t t, const uint32_t *side, uint32_t rows[4])
-{
-    RcMotion m;
-    rc_motion(v, plane, bx, by, t, m);
-    if (m.poisoned) { rows[0] = rows[1] = rows[2] = rows[3] = 0x80808080u; return; }
-    rc_predict(rows, m.src, m.stride, m.hx, m.hy);
-    rc_predicted_aot(v, rows, side, (int)(t & 0xF), m.window);
-}
-
-/* one block, all cases (used by the CPU emulation; the kernel drains one class at a time) */
-RC_HD void rc_block(const ReconView &v, int plane, int bx, int by, uint32_t t, const uint32_t *side, uint32_t rows[4])
+/* ---- MAP kernel: what can be reconstructed from the maps (and reference frames) alone -------
+ * Returns false when the block is left to the record kernel (raw, intra AOT).  Predicted-AOT
+ * blocks get their motion-compensated prediction here; the record kernel reads it back from
+ * the picture and adds the AOT residual (h4m:1387-1417 use the same prediction `mdst`). */
+RC_HD bool rc_map_block(const ReconView &v, int plane, int bx, int by, uint32_t t, uint32_t rows[4])
 {
     switch (rc_classify(t, v.is_ipic))
     {
-    case RC_AOT_INTRA: rc_aot_intra_block(v, plane, bx, by, t, side, rows); break;
-    case RC_AOT_INTER: rc_aot_inter_block(v, plane, bx, by, t, side, rows); break;
-    case RC_WEIGHTED: rc_weighted_block(v, plane, bx, by, rows); break;
-    case RC_MC: rc_mc_block(v, plane, bx, by, t, rows); break;
-    default: rc_direct_block(v, plane, bx, by, t, side, rows); break;
+    case RC_WEIGHTED:
+        rc_weighted_block(v, plane, bx, by, rows);
+        return true;
+    case RC_MC:
+    case RC_AOT_INTER:
+        rc_mc_block(v, plane, bx, by, t, rows);
+        return true;
+    case RC_DIRECT:
+        if ((v.is_ipic ? t : (t & 0xF)) == 8)
+        {
+            const int bstride = ((v.width >> (plane ? 1 : 0)) >> 2) + 2;
+            const uint32_t V = RC_LD8(v.blob + rc_pick3(v.off_dc, plane) + (by + 1) * bstride + bx + 1);
+            rows[0] = rows[1] = rows[2] = rows[3] = V * 0x01010101u;
+            return true;
+        }
+        return false;
+    default:
+        return false;
+    }
+}
+
+/* ---- RECORD kernel: one record (header word + payload) --------------------------------------
+ * rows[] must hold the block's current pixels for SYM_REC_INTER (the prediction written by the
+ * map kernel); it is ignored for the other classes. */
+RC_HD void rc_record_coords(uint32_t hdr, uint32_t &t, int &plane, int &bx, int &by)
+{
+    t = hdr & 0xFF;
+    plane = (int)((hdr >> 8) & 3);
+    bx = (int)((hdr >> 10) & 0x7FF);
+    by = (int)(hdr >> 21);
+}
+
+RC_HD void rc_record_block(const ReconView &v, int cls, uint32_t len, const uint32_t *rec, uint32_t rows[4])
+{
+    uint32_t t;
+    int plane, bx, by;
+    rc_record_coords(RC_LD32(rec), t, plane, bx, by);
+    if (cls == SYM_REC_RAW)
+    {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) rows[r] = RC_LD32(rec + 1 + r);
+    }
+    else if (cls == SYM_REC_INTRA)
+    {
+        const int bstride = ((v.width >> (plane ? 1 : 0)) >> 2) + 2;
+        const int V = RC_LD8(v.blob + rc_pick3(v.off_dc, plane) + (by + 1) * bstride + bx + 1);
+        rc_intra_aot(v, rows, rec + 1, (int)len - 1, V);
+    }
+    else
+    {
+        RcMotion m;
+        rc_motion(v, plane, bx, by, t, m);
+        if (m.poisoned) return;                       /* the map kernel painted it grey */
+        rc_predicted_aot(v, rows, rec + 1, (int)len - 1, m.window);
     }
 }
 

@@ -13,6 +13,8 @@
  *                  {dc 0x7F, type 0xFF} of h4m:951-955.  type byte layout as h4m:1296-1304:
  *                  bits 6:5 macroblock type (0 intra, 1 past, 2 future), bit 4 proc,
  *                  bits 3:0 block nibble (I pictures: the whole byte is the basis count).
+ *                  The MAP kernel reconstructs every block that needs nothing else from
+ *                  these two maps: weighted-DC, flat-DC and motion-compensated blocks.
  *   mv table       per macroblock, absolute half-sample luma position of the prediction
  *                  (ref_x, ref_y of h4m:1954-1955) as int16 x 2; predictor chain,
  *                  wrap-around and reference switches (h4m:1846-1860,1943-1949) are
@@ -20,21 +22,25 @@
  *   nest           the 70x38 4-bit nest of the last I picture (h4m:1166-1239), packed two
  *                  samples per byte (even x in the low nibble); present in every I picture
  *                  and in P/B pictures that contain intra AOT blocks.
- *   side words     variable-length per-block data, one 32-bit word per item:
- *                    basis word   bits 15:0  descriptor exactly as read from fixvl (h4m:691),
- *                                 bits 23:16 scale symbol = decodeHuff(bufTree0) >> 2 (h4m:726)
- *                    raw block    4 words = the 16 fixvl bytes of h4m:543-549, row by row
- *                    pair word    predicted-AOT block: low 16 = S1 >> dc_shift, high 16 =
- *                                 S2 >> dc_shift (both int16; h4m:1405-1406)
- *                  A block owns  n  words (intra AOT with n bases),  4  words (raw),
- *                  k  words (inter nibble k: k-1 bases + 1 pair word) or none.
- *   segment table  side words are stored in GPU WORK ORDER, not bitstream order: the
- *                  picture is cut into segments of 16 macroblocks of one macroblock row;
- *                  inside a segment the order is: upper luma block row (32 blocks left to
- *                  right), lower luma block row, 16 U blocks, 16 V blocks.  seg[i] is the
- *                  word offset of segment i; a warp finds each block's words with a
- *                  prefix sum over the per-block word counts, which are a pure function
- *                  of the type byte (sym_side_words()).
+ *   records        one variable-length record per block that carries side data, i.e. raw
+ *                  blocks (h4m:543-549) and blocks with an AOT basis loop (h4m:1358-1420):
+ *                    word 0     [7:0] type byte, [9:8] plane, [20:10] block x, [31:21] block y
+ *                    raw        4 words = the 16 fixvl bytes, row by row
+ *                    intra AOT  n basis words
+ *                    inter AOT  (nibble-1) basis words + 1 pair word
+ *                  basis word: bits 15:0 descriptor exactly as read from fixvl (h4m:691),
+ *                              bits 23:16 scale symbol = decodeHuff(bufTree0) >> 2 (h4m:726)
+ *                  pair word:  low 16 = S1 >> dc_shift, high 16 = S2 >> dc_shift (int16; h4m:1405-1406)
+ *                  The host already knows every block's type before it emits side data, so it
+ *                  stores the records GROUPED: by class (raw, intra AOT, inter AOT), then by
+ *                  band of SYM_BAND_MCB_ROWS macroblock rows (locality), then by record
+ *                  length.  Records of a group have the same length, so record i of a group is
+ *                  at first + i * length -- no prefix sums on the GPU -- and every lane of a
+ *                  warp of the RECORD kernel runs the same number of basis iterations.
+ *   chunk table    the record kernel's work list: one entry per <= 32 records of one group:
+ *                    word 0  offset of the first record (words from off_rec)
+ *                    word 1  [7:0] count, [15:8] record length - 1, [23:16] class (SYM_REC_*)
+ *                  Chunks [0, n_chunks_nest) are raw/intra (need the nest), the rest inter.
  */
 #ifndef HVQM4_SYMBUF_H
 #define HVQM4_SYMBUF_H
@@ -42,13 +48,17 @@
 #include <stdint.h>
 
 #define SYM_MAGIC 0x42533448u /* "H4SB" */
-#define SYM_SEG_MCBS 16       /* macroblocks per segment (= 32 luma blocks = one warp) */
+#define SYM_SEG_MCBS 16       /* macroblocks per segment of the map kernel (= 32 luma blocks = one warp) */
+#define SYM_BAND_MCB_ROWS 2   /* record groups are formed per band of this many macroblock rows */
+#define SYM_CHUNK 32          /* records per chunk (= one warp of the record kernel) */
+#define SYM_LEN_BUCKETS 18    /* record lengths 1..17 words get their own group; longer ones one chunk each */
 #define SYM_NEST_W 70
 #define SYM_NEST_H 38
 #define SYM_NEST_ROW_BYTES 35 /* packed nibbles */
 #define SYM_NEST_BYTES (SYM_NEST_ROW_BYTES * SYM_NEST_H)
 
 enum { SYM_PIC_I = 0x10, SYM_PIC_P = 0x20, SYM_PIC_B = 0x30 };
+enum { SYM_REC_RAW = 0, SYM_REC_INTRA = 1, SYM_REC_INTER = 2, SYM_REC_CLASSES = 3 };
 
 /* error bits raised by the host stage (the SDK entry points return void) */
 enum
@@ -80,11 +90,14 @@ typedef struct SymHeader
     uint32_t off_type[3];      /* byte offsets from the blob start; bordered (bw+2)x(bh+2) */
     uint32_t off_dc[3];
     uint32_t off_mv;           /* int16[2] per macroblock; 0 for I pictures */
-    uint32_t off_seg;          /* uint32 per segment (+1 terminator) */
+    uint32_t off_chunks;       /* uint32[2] per chunk */
     uint32_t off_nest;         /* SYM_NEST_BYTES; 0 if !has_nest */
-    uint32_t off_side;         /* uint32 words */
-    uint32_t n_side_words;
-    uint32_t pad2[13];
+    uint32_t off_rec;          /* records, uint32 words */
+    uint32_t n_rec_words;
+    uint32_t n_chunks;
+    uint32_t n_chunks_nest;    /* leading chunks that are raw / intra AOT */
+    uint32_t n_records;
+    uint32_t pad2[10];
 } SymHeader;                   /* 128 bytes */
 
 #ifdef __cplusplus
@@ -100,20 +113,32 @@ _Static_assert(sizeof(SymHeader) == 128, "SymHeader must be 128 bytes");
 #endif
 
 /*
- * Number of side words owned by a block, from its type byte alone.
- *   I picture:           type is the full byte: 0/8 -> 0, 6 -> 4 (raw), n -> n bases
+ * Record class and length (in words, header included) of a block, from its type byte alone;
+ * length 0 = the block has no record (the map kernel reconstructs it completely).
+ *   I picture:           type is the full byte: 0/8 -> none, 6 -> raw, n -> n bases
  *   P/B intra MCB:       nibble as above
- *   P/B inter, proc 1:   0 (whole-macroblock motion compensation, h4m:1673-1683)
- *   P/B inter, proc 0:   nibble 0 -> 0, 6 -> 4, k -> (k-1) bases + 1 pair = k
+ *   P/B inter, proc 1:   none (whole-macroblock motion compensation, h4m:1673-1683)
+ *   P/B inter, proc 0:   nibble 0 -> none, 6 -> raw, k -> (k-1) bases + 1 pair
  */
-SYM_HD uint32_t sym_side_words(uint32_t type, int is_ipic)
+SYM_HD uint32_t sym_record_len(uint32_t type, int is_ipic, int *cls)
 {
-    if (is_ipic)
-        return type == 6 ? 4u : (type == 0 || type == 8) ? 0u : type;
-    uint32_t nib = type & 0xF;
-    if (type & 0x60)
-        return (type & 0x10) ? 0u : nib == 6 ? 4u : nib;
-    return nib == 6 ? 4u : (nib == 0 || nib == 8) ? 0u : nib;
+    const uint32_t nib = is_ipic ? type : (type & 0xF);
+    if (!is_ipic && (type & 0x60))
+    {
+        if ((type & 0x10) || nib == 0) return 0;
+        if (nib == 6) { *cls = SYM_REC_RAW; return 5; }
+        *cls = SYM_REC_INTER;
+        return 1 + nib;
+    }
+    if (nib == 0 || nib == 8) return 0;
+    if (nib == 6) { *cls = SYM_REC_RAW; return 5; }
+    *cls = SYM_REC_INTRA;
+    return 1 + nib;
+}
+
+SYM_HD uint32_t sym_record_header(uint32_t type, int plane, int bx, int by)
+{
+    return (type & 0xFF) | (uint32_t)plane << 8 | (uint32_t)bx << 10 | (uint32_t)by << 21;
 }
 
 #endif

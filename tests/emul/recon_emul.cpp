@@ -1,12 +1,13 @@
 /*
  * tests/emul/recon_emul.cpp -- TEST INFRASTRUCTURE ONLY.
  *
- * Serial CPU driver for hvqm4_b200/csrc/recon_core.h: walks a symbol buffer in exactly
- * the work order of the CUDA kernel (segments of 16 macroblocks; upper luma block row,
- * lower luma block row, U, V; running prefix sum of sym_side_words) and calls the same
- * __host__ __device__ block functions.  It exists so that the host stage (entropy.c)
- * and the block arithmetic can be checked against the oracle in a container without a
- * GPU.  It is never built into, or reachable from, the product library.
+ * Serial CPU driver for hvqm4_b200/csrc/recon_core.h: runs the work of the two CUDA kernels
+ * in the same order of phases -- MAP phase (every block from the type/DC maps: weighted, flat,
+ * motion compensation), then RECORD phase (chunk table -> grouped records: raw, intra AOT,
+ * predicted AOT on top of the prediction written by the map phase) -- calling the same
+ * __host__ __device__ block functions.  It exists so that the host stage (entropy.c) and the
+ * block arithmetic can be checked against the oracle in a container without a GPU.  It is
+ * never built into, or reachable from, the product library.
  */
 #include <cstdint>
 #include <cstring>
@@ -14,11 +15,6 @@
 
 static int32_t g_div[16], g_mcdiv[512];
 static bool g_init;
-
-static void store_rows(uint8_t *plane, int pw, int bx, int by, const uint32_t rows[4])
-{
-    for (int r = 0; r < 4; ++r) memcpy(plane + (by * 4 + r) * pw + bx * 4, &rows[r], 4);
-}
 
 extern "C" __attribute__((visibility("default")))
 int emul_recon_picture(const uint8_t *blob, uint8_t *present, const uint8_t *past, const uint8_t *future)
@@ -38,32 +34,47 @@ int emul_recon_picture(const uint8_t *blob, uint8_t *present, const uint8_t *pas
             for (int x = 0; x < 64; ++x) nest_tab[y * 64 + x] = rc_nest_table_entry(blob + h.off_nest, y, x);
     ReconView v;
     rc_make_view(v, blob, h, nest_tab, g_div, g_mcdiv, past, future);
-    const uint32_t *seg = (const uint32_t *)(blob + h.off_seg);
-    const uint32_t *side = (const uint32_t *)(blob + h.off_side);
     uint8_t *planes[3] = {present, present + h.width * h.height, present + h.width * h.height * 5 / 4};
-    const int is_i = h.pic_type == SYM_PIC_I;
-    for (int row = 0; row < h.mcb_h; ++row)
-        for (int sg = 0; sg < h.nseg; ++sg)
+
+    /* MAP phase */
+    for (int plane = 0; plane < 3; ++plane)
+    {
+        const int pw = h.width >> (plane ? 1 : 0), ph = h.height >> (plane ? 1 : 0);
+        const int bstride = (pw >> 2) + 2;
+        for (int by = 0; by < ph / 4; ++by)
+            for (int bx = 0; bx < pw / 4; ++bx)
+            {
+                const uint32_t t = blob[h.off_type[plane] + (by + 1) * bstride + bx + 1];
+                uint32_t rows[4];
+                if (!rc_map_block(v, plane, bx, by, t, rows)) continue;
+                for (int r = 0; r < 4; ++r) memcpy(planes[plane] + (by * 4 + r) * pw + bx * 4, &rows[r], 4);
+            }
+    }
+    /* RECORD phase */
+    uint32_t seen = 0;
+    for (uint32_t c = 0; c < h.n_chunks; ++c)
+    {
+        const uint32_t first = v.chunks[2 * c], desc = v.chunks[2 * c + 1];
+        const uint32_t count = desc & 0xFF, len = ((desc >> 8) & 0xFF) + 1;
+        const int cls = (int)((desc >> 16) & 0xFF);
+        if (count == 0 || count > SYM_CHUNK) return -3;
+        if ((c < h.n_chunks_nest) != (cls != SYM_REC_INTER)) return -4;
+        for (uint32_t i = 0; i < count; ++i)
         {
-            uint32_t word = seg[row * h.nseg + sg];
-            const int mx0 = sg * SYM_SEG_MCBS;
-            for (int pass = 0; pass < 3; ++pass)
-                for (int lane = 0; lane < 32; ++lane)
-                {
-                    int plane, bx, by;
-                    bool valid;
-                    if (pass < 2) { plane = 0; bx = mx0 * 2 + lane; by = row * 2 + pass; valid = bx < h.mcb_w * 2; }
-                    else { plane = 1 + (lane >> 4); bx = mx0 + (lane & 15); by = row; valid = bx < h.mcb_w; }
-                    if (!valid) continue;
-                    const int pw = h.width >> (plane ? 1 : 0);
-                    const int bstride = (pw >> 2) + 2;
-                    const uint32_t t = blob[h.off_type[plane] + (by + 1) * bstride + bx + 1];
-                    uint32_t rows[4];
-                    rc_block(v, plane, bx, by, t, side + word, rows);
-                    word += sym_side_words(t, is_i);
-                    store_rows(planes[plane], pw, bx, by, rows);
-                }
-            if (word != seg[row * h.nseg + sg + 1]) return -2;   /* segment table and prefix sum must agree */
+            const uint32_t *rec = v.rec + first + i * len;
+            if (first + (i + 1) * len > h.n_rec_words) return -5;
+            uint32_t t;
+            int plane, bx, by;
+            rc_record_coords(rec[0], t, plane, bx, by);
+            const int pw = h.width >> (plane ? 1 : 0);
+            uint8_t *dst = planes[plane] + (by * 4) * pw + bx * 4;
+            uint32_t rows[4];
+            for (int r = 0; r < 4; ++r) memcpy(&rows[r], dst + r * pw, 4);
+            rc_record_block(v, cls, len, rec, rows);
+            for (int r = 0; r < 4; ++r) memcpy(dst + r * pw, &rows[r], 4);
+            ++seen;
         }
+    }
+    if (seen != h.n_records) return -2;   /* chunk table must cover every record exactly once */
     return 0;
 }
