@@ -457,6 +457,25 @@ H4_API int HVQM4BatchReadFrameAsync(HVQM4Batch *b, int stream_id, void *host_dst
 H4_API int HVQM4BatchReadFramesAsync(HVQM4Batch *b, int n, const int32_t *stream_ids, void *host_base, size_t host_stride)
 {
     if (!b || n <= 0 || !stream_ids || !host_base || host_stride < b->frame_bytes) return HVQM4_ERR_ARGUMENT;
+    /* streams decoded in lock step sit at a constant pitch in the surface slab: one 2-D copy */
+    bool regular = true;
+    for (int i = 0; i < n && regular; ++i)
+    {
+        const int s = stream_ids[i];
+        if (s < 0 || s >= b->n_streams || b->st[s].last < 0) return HVQM4_ERR_ARGUMENT;
+        regular = s == stream_ids[0] + i && b->st[s].last == b->st[stream_ids[0]].last;
+    }
+    if (regular && n > 1)
+    {
+        cudaSetDevice(b->device);
+        if (!b->d2h_pending) cudaStreamWaitEvent(b->s_d2h, b->ev_kernel, 0);
+        if (!cuda_ok(cudaMemcpy2DAsync(host_base, host_stride, b->surface(stream_ids[0], b->st[stream_ids[0]].last), 3 * b->surf_stride,
+                                       b->frame_bytes, (size_t)n, cudaMemcpyDeviceToHost, b->s_d2h), "cudaMemcpy2DAsync(D2H)"))
+            return HVQM4_ERR_CUDA;
+        cudaEventRecord(b->ev_d2h, b->s_d2h);
+        b->d2h_pending = true;
+        return HVQM4_OK;
+    }
     for (int i = 0; i < n; ++i)
     {
         int rc = HVQM4BatchReadFrameAsync(b, stream_ids[i], static_cast<uint8_t *>(host_base) + (size_t)i * host_stride);

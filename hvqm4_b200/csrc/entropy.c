@@ -346,44 +346,49 @@ static void open_bytes(H4Seq *s, ByteSec *b, const uint8_t *data, size_t len, ui
 
 /* ------------------------------------------------------------------ record groups */
 
+/* block rows per band, as shifts */
+#define SYM_BAND_SHIFT_CHROMA 3
+#define SYM_BAND_SHIFT_LUMA 4
+_Static_assert((1 << SYM_BAND_SHIFT_CHROMA) == SYM_BAND_MCB_ROWS, "band shift must match SYM_BAND_MCB_ROWS");
+
 static inline int len_bucket(uint32_t len) { return len < SYM_LEN_BUCKETS ? (int)len - 1 : SYM_LEN_BUCKETS - 1; }
 static inline int group_of(const H4Seq *s, int cls, int band, uint32_t len)
 {
     return (cls * s->nbands + band) * SYM_LEN_BUCKETS + len_bucket(len);
 }
 
-/*
- * Counts the records of every (class, band, length) group from the final type maps, lays the
- * groups out back to back (class-major, so that raw/intra chunks precede inter chunks) and
- * builds the chunk table.  Records of the last bucket ("long", >= SYM_LEN_BUCKETS words: only
- * I-picture luma types > 16, which no encoder emits) have individual lengths; they are packed
- * in emission order and get one chunk each.
- */
-static void plan_records(H4Seq *s, int is_ipic)
+/* Called wherever a block's final type byte is written (ipic_types, pb_pass1): counts the
+   record the block will own in its (class, band, length) group.  band_shift: log2 of block rows
+   per band (luma 4, chroma 3 for SYM_BAND_MCB_ROWS = 8). */
+static inline void count_record(H4Seq *s, uint32_t t, int is_ipic, int by, int band_shift)
+{
+    int cls = 0;
+    const uint32_t len = sym_record_len(t, is_ipic, &cls);
+    if (!len) return;
+    const int g = group_of(s, cls, by >> band_shift, len);
+    s->grp_count[g]++;
+    if (len >= SYM_LEN_BUCKETS) s->grp_base[g] += len;   /* long-bucket word total, see plan_records */
+    s->n_records++;
+}
+
+static void reset_record_counts(H4Seq *s)
 {
     memset(s->grp_count, 0, (size_t)s->ngroups * sizeof(uint32_t));
     memset(s->grp_next, 0, (size_t)s->ngroups * sizeof(uint32_t));
-    /* long-bucket word totals live in grp_base until the prefix pass below */
     memset(s->grp_base, 0, (size_t)s->ngroups * sizeof(uint32_t));
+    s->n_records = 0;
+}
+
+/*
+ * Lays the (class, band, length) groups counted by count_record() out back to back
+ * (class-major, so that raw/intra chunks precede inter chunks) and builds the chunk table.
+ * Records of the last bucket ("long", >= SYM_LEN_BUCKETS words: only I-picture luma types
+ * > 16, which no encoder emits) have individual lengths; they are packed in emission order
+ * and get one chunk each.
+ */
+static void plan_records(H4Seq *s, int is_ipic)
+{
     int need_nest = 0;
-    uint32_t n_records = 0;
-    for (int p = 0; p < 3; ++p)
-        for (int by = 0; by < s->bh[p]; ++by)
-        {
-            const uint8_t *ty = s->type[p] + cell_at(s, p, 0, by);
-            const int band = (p ? by : by >> 1) / SYM_BAND_MCB_ROWS;
-            for (int bx = 0; bx < s->bw[p]; ++bx)
-            {
-                int cls = 0;
-                const uint32_t len = sym_record_len(ty[bx], is_ipic, &cls);
-                if (!len) continue;
-                const int g = group_of(s, cls, band, len);
-                s->grp_count[g]++;
-                if (len >= SYM_LEN_BUCKETS) s->grp_base[g] += len;
-                need_nest |= cls == SYM_REC_INTRA;
-                ++n_records;
-            }
-        }
     uint32_t word = 0, chunk = 0;
     s->n_chunks_nest = 0;
     for (int cls = 0; cls < SYM_REC_CLASSES; ++cls)
@@ -397,6 +402,7 @@ static void plan_records(H4Seq *s, int is_ipic)
                 s->grp_base[g] = word;
                 s->grp_chunk[g] = chunk;
                 if (!n) continue;
+                need_nest |= cls == SYM_REC_INTRA;
                 if (lb < SYM_LEN_BUCKETS - 1)
                 {
                     const uint32_t len = (uint32_t)lb + 1;
@@ -419,7 +425,6 @@ static void plan_records(H4Seq *s, int is_ipic)
     }
     s->n_rec_words = word;
     s->n_chunks = chunk;
-    s->n_records = n_records;
     s->need_nest = is_ipic ? 1 : need_nest;
 }
 
@@ -428,7 +433,7 @@ static inline uint32_t *place_record(H4Seq *s, uint32_t t, int is_ipic, int p, i
 {
     int cls = 0;
     const uint32_t len = sym_record_len(t, is_ipic, &cls);
-    const int band = (p ? by : by >> 1) / SYM_BAND_MCB_ROWS;
+    const int band = by >> (p ? SYM_BAND_SHIFT_CHROMA : SYM_BAND_SHIFT_LUMA);
     const int g = group_of(s, cls, band, len);
     uint32_t at;
     if (len < SYM_LEN_BUCKETS)
@@ -501,6 +506,9 @@ static void ipic_types(H4Seq *s)
 {
     const HTab *tn = &s->tree[T_BNUM], *tr = &s->tree[T_RUN];
     uint32_t run = 0;
+    /* readers are copied to locals in every hot loop: the byte stores into the maps may alias
+       anything, which would otherwise force the reader state back to memory after every symbol */
+    BR bn = s->bn[0], bnr = s->bnr[0];
     for (int by = 0; by < s->bh[0]; ++by)
     {
         uint8_t *row = s->type[0] + cell_at(s, 0, 0, by);
@@ -512,11 +520,16 @@ static void ipic_types(H4Seq *s)
                 --run;
                 continue;
             }
-            int32_t n = ht_get(tn, &s->bn[0]);
-            if ((int16_t)n == 0) run = (uint32_t)ht_get(tr, &s->bnr[0]);
+            int32_t n = ht_get(tn, &bn);
+            if ((int16_t)n == 0) run = (uint32_t)ht_get(tr, &bnr);
+            else count_record(s, (uint8_t)n, 1, by, SYM_BAND_SHIFT_LUMA);
             row[bx] = (uint8_t)n;
         }
     }
+    s->bn[0] = bn;
+    s->bnr[0] = bnr;
+    bn = s->bn[1];
+    bnr = s->bnr[1];
     run = 0;
     for (int by = 0; by < s->bh[1]; ++by)
     {
@@ -529,12 +542,16 @@ static void ipic_types(H4Seq *s)
                 --run;
                 continue;
             }
-            int32_t n = ht_get(tn, &s->bn[1]);
-            if ((int16_t)n == 0) run = (uint32_t)ht_get(tr, &s->bnr[1]);
+            int32_t n = ht_get(tn, &bn);
+            if ((int16_t)n == 0) run = (uint32_t)ht_get(tr, &bnr);
             ru[bx] = n & 0xF;
             rv[bx] = (n >> 4) & 0xF;
+            count_record(s, n & 0xF, 1, by, SYM_BAND_SHIFT_CHROMA);
+            count_record(s, (n >> 4) & 0xF, 1, by, SYM_BAND_SHIFT_CHROMA);
         }
     }
+    s->bn[1] = bn;
+    s->bnr[1] = bnr;
 }
 
 /* IpicDcvDec + getDeltaDC, h4m:1043-1058, 1132-1164 */
@@ -544,6 +561,8 @@ static void ipic_dcs(H4Seq *s)
     for (int p = 0; p < 3; ++p)
     {
         uint32_t run = 0;
+        BR dcv = s->dcv[p], rle = s->rle[p];
+        const int32_t lo = s->dc_lo, hi = s->dc_hi;
         for (int by = 0; by < s->bh[p]; ++by)
         {
             uint8_t *cur = s->dc[p] + cell_at(s, p, 0, by);
@@ -554,14 +573,16 @@ static void ipic_dcs(H4Seq *s)
                 if (run) --run;
                 else
                 {
-                    uint32_t delta = (uint32_t)ht_get_sovf(td, &s->dcv[p], s->dc_lo, s->dc_hi);
-                    if (delta == 0) run = (uint32_t)ht_get(tr, &s->rle[p]);
+                    uint32_t delta = (uint32_t)ht_get_sovf(td, &dcv, lo, hi);
+                    if (delta == 0) run = (uint32_t)ht_get(tr, &rle);
                     v = (uint8_t)(v + delta);
                 }
                 cur[bx] = v;
                 v = (uint8_t)((v + up[bx + 1] + 1) >> 1);
             }
         }
+        s->dcv[p] = dcv;
+        s->rle[p] = rle;
     }
 }
 
@@ -591,49 +612,76 @@ static void make_nest(H4Seq *s, int nx, int ny)
 
 /* ------------------------------------------------------------------ side-word emitters */
 
-static inline int fix_has(H4Seq *s, int p, uint32_t n)
+/* readers used while emitting records, kept in a local struct by the callers (see ipic_types) */
+typedef struct
 {
-    if (s->fix[p].base && s->fix[p].pos + n <= s->fix[p].size) return 1;
+    BR sc[3], dcv[3];
+    ByteSec fix[3];
+} EmitCtx;
+
+static inline void emit_ctx_load(EmitCtx *c, const H4Seq *s)
+{
+    for (int p = 0; p < 3; ++p)
+    {
+        c->sc[p] = s->sc[p];
+        c->dcv[p] = s->dcv[p];
+        c->fix[p] = s->fix[p];
+    }
+}
+
+static inline void emit_ctx_store(const EmitCtx *c, H4Seq *s)
+{
+    for (int p = 0; p < 3; ++p)
+    {
+        s->sc[p] = c->sc[p];
+        s->dcv[p] = c->dcv[p];
+        s->fix[p] = c->fix[p];
+    }
+}
+
+static inline int fix_has(H4Seq *s, EmitCtx *c, int p, uint32_t n)
+{
+    if (c->fix[p].base && c->fix[p].pos + n <= c->fix[p].size) return 1;
     s->err |= SYM_ERR_TRUNCATED;
     return 0;
 }
 
 /* n x (descriptor, scale symbol): read16(fixvl) + decodeHuff(bufTree0), h4m:691,726 / 738,767 */
-static inline void emit_bases(H4Seq *s, int p, uint32_t n, uint32_t *dst)
+static inline void emit_bases(H4Seq *s, EmitCtx *c, int p, uint32_t n, uint32_t *dst)
 {
     const HTab *ts = &s->tree[T_SCALE];
     for (uint32_t k = 0; k < n; ++k)
     {
         uint32_t desc = 0;
-        if (fix_has(s, p, 2))
+        if (fix_has(s, c, p, 2))
         {
-            const uint8_t *f = s->fix[p].base + s->fix[p].pos;
+            const uint8_t *f = c->fix[p].base + c->fix[p].pos;
             desc = (uint32_t)f[0] << 8 | f[1];
-            s->fix[p].pos += 2;
+            c->fix[p].pos += 2;
         }
-        uint32_t sym = (uint32_t)ht_get(ts, &s->sc[p]);
+        uint32_t sym = (uint32_t)ht_get(ts, &c->sc[p]);
         dst[k] = desc | ((sym >> 2) & 0xFF) << 16;
     }
 }
 
 /* OrgBlock, h4m:543-549 */
-static inline void emit_raw(H4Seq *s, int p, uint32_t *dst)
+static inline void emit_raw(H4Seq *s, EmitCtx *c, int p, uint32_t *dst)
 {
-    if (fix_has(s, p, 16))
+    if (fix_has(s, c, p, 16))
     {
-        memcpy(dst, s->fix[p].base + s->fix[p].pos, 16);
-        s->fix[p].pos += 16;
+        memcpy(dst, c->fix[p].base + c->fix[p].pos, 16);
+        c->fix[p].pos += 16;
     }
     else
         memset(dst, 0x80, 16);
 }
 
 /* the two decodeSOvfSym reads of PrediAotBlock, h4m:1405-1406, pre-shifted by dc_shift */
-static inline void emit_pair(H4Seq *s, int p, uint32_t *dst)
+static inline void emit_pair(H4Seq *s, EmitCtx *c, int p, uint32_t *dst)
 {
     const HTab *td = &s->tree[T_DC];
-    int32_t a = ht_get_sovf(td, &s->dcv[p], s->dc_lo, s->dc_hi) >> s->dc_shift;
-    int32_t f = ht_get_sovf(td, &s->dcv[p], s->dc_lo, s->dc_hi) >> s->dc_shift;
+    int32_t a = ht_get_sovf(td, &c->dcv[p], s->dc_lo, s->dc_hi) >> s->dc_shift;
+    int32_t f = ht_get_sovf(td, &c->dcv[p], s->dc_lo, s->dc_hi) >> s->dc_shift;
     if (a < -32768 || a > 32767 || f < -32768 || f > 32767)
     {
         s->err |= SYM_ERR_PAIR_RANGE;
@@ -644,13 +692,13 @@ static inline void emit_pair(H4Seq *s, int p, uint32_t *dst)
 }
 
 /* t = type byte of an intra block (full byte in I pictures, tag | nibble in P/B) */
-static inline void emit_intra_block(H4Seq *s, int p, uint32_t t, int is_ipic, int bx, int by)
+static inline void emit_intra_block(H4Seq *s, EmitCtx *c, int p, uint32_t t, int is_ipic, int bx, int by)
 {
     const uint32_t nib = is_ipic ? t : (t & 0xF);
     if (nib == 0 || nib == 8) return;
     uint32_t *dst = place_record(s, t, is_ipic, p, bx, by);
-    if (nib == 6) emit_raw(s, p, dst);
-    else emit_bases(s, p, nib, dst);
+    if (nib == 6) emit_raw(s, c, p, dst);
+    else emit_bases(s, c, p, nib, dst);
 }
 
 /* ------------------------------------------------------------------ P/B picture, pass 1 */
@@ -666,15 +714,18 @@ static void pb_pass1(H4Seq *s)
     static const uint8_t next_type[2][4] = {{1, 2, 0, 0}, {2, 0, 1, 0}};   /* mcbtypetrans, h4m:1591-1594 */
     const HTab *tm = &s->tree[T_MCB], *td = &s->tree[T_DC], *tn = &s->tree[T_BNUM], *tr = &s->tree[T_RUN];
     RunLen proc = {0, 0}, type = {0, 0};
-    if (s->mcbp.base)
+    BR mcbp = s->mcbp, mcbt = s->mcbt, bn0 = s->bn[0], bn1 = s->bn[1], bnr0 = s->bnr[0], bnr1 = s->bnr[1];
+    BR dcv0 = s->dcv[0], dcv1 = s->dcv[1], dcv2 = s->dcv[2];
+    const int32_t dlo = s->dc_lo, dhi = s->dc_hi;
+    if (mcbp.base)
     {
-        proc.value = br_bit(&s->mcbp);
-        proc.count = (uint32_t)ht_get_uovf(tm, &s->mcbp);
+        proc.value = br_bit(&mcbp);
+        proc.count = (uint32_t)ht_get_uovf(tm, &mcbp);
     }
-    if (s->mcbt.base)
+    if (mcbt.base)
     {
-        type.value = br_bits(&s->mcbt, 2);
-        type.count = (uint32_t)ht_get_uovf(tm, &s->mcbt);
+        type.value = br_bits(&mcbt, 2);
+        type.count = (uint32_t)ht_get_uovf(tm, &mcbt);
     }
     else
         s->err |= SYM_ERR_TRUNCATED;   /* the reference would use an uninitialised type here */
@@ -688,10 +739,10 @@ static void pb_pass1(H4Seq *s)
         uint8_t *ty2 = s->type[2] + cell_at(s, 2, 0, my), *dc2 = s->dc[2] + cell_at(s, 2, 0, my);
         for (int mx = 0; mx < s->mbw; ++mx)
         {
-            if (type.count == 0 && s->mcbt.base)
+            if (type.count == 0 && mcbt.base)
             {
-                type.value = next_type[br_bit(&s->mcbt)][type.value & 3];
-                type.count = (uint32_t)ht_get_uovf(tm, &s->mcbt);
+                type.value = next_type[br_bit(&mcbt)][type.value & 3];
+                type.count = (uint32_t)ht_get_uovf(tm, &mcbt);
             }
             --type.count;
             uint32_t mt = type.value;
@@ -708,21 +759,21 @@ static void pb_pass1(H4Seq *s)
             {
                 for (int k = 0; k < 4; ++k)
                 {
-                    acc[0] += (uint32_t)ht_get_sovf(td, &s->dcv[0], s->dc_lo, s->dc_hi);
+                    acc[0] += (uint32_t)ht_get_sovf(td, &dcv0, dlo, dhi);
                     dc0[SUBY[k] * st0 + lx + SUBX[k]] = (uint8_t)acc[0];
                 }
-                acc[1] += (uint32_t)ht_get_sovf(td, &s->dcv[1], s->dc_lo, s->dc_hi);
+                acc[1] += (uint32_t)ht_get_sovf(td, &dcv1, dlo, dhi);
                 dc1[mx] = (uint8_t)acc[1];
-                acc[2] += (uint32_t)ht_get_sovf(td, &s->dcv[2], s->dc_lo, s->dc_hi);
+                acc[2] += (uint32_t)ht_get_sovf(td, &dcv2, dlo, dhi);
                 dc2[mx] = (uint8_t)acc[2];
             }
             else
             {
                 acc[0] = acc[1] = acc[2] = 0x7F;
-                if (proc.count == 0 && s->mcbp.base)
+                if (proc.count == 0 && mcbp.base)
                 {
                     proc.value ^= 1;
-                    proc.count = (uint32_t)ht_get_uovf(tm, &s->mcbp);
+                    proc.count = (uint32_t)ht_get_uovf(tm, &mcbp);
                 }
                 --proc.count;
                 pr = proc.value & 1;
@@ -743,7 +794,7 @@ static void pb_pass1(H4Seq *s)
                     --run_y;
                     continue;
                 }
-                int32_t n = (int16_t)ht_get(tn, &s->bn[0]);
+                int32_t n = (int16_t)ht_get(tn, &bn0);
                 if (n)
                 {
                     if (n & ~0xF)
@@ -752,11 +803,12 @@ static void pb_pass1(H4Seq *s)
                         n &= 0xF;
                     }
                     *c = (uint8_t)(tag | n);
+                    count_record(s, *c, 0, my * 2 + SUBY[k], SYM_BAND_SHIFT_LUMA);
                 }
                 else
                 {
                     *c = tag;
-                    run_y = (uint32_t)ht_get(tr, &s->bnr[0]);
+                    run_y = (uint32_t)ht_get(tr, &bnr0);
                 }
             }
             if (run_c)
@@ -766,20 +818,25 @@ static void pb_pass1(H4Seq *s)
             }
             else
             {
-                int32_t n = (int16_t)ht_get(tn, &s->bn[1]);
+                int32_t n = (int16_t)ht_get(tn, &bn1);
                 if (n)
                 {
                     ty1[mx] = (uint8_t)(tag | (n & 0xF));
                     ty2[mx] = (uint8_t)(tag | ((n >> 4) & 0xF));
+                    count_record(s, ty1[mx], 0, my, SYM_BAND_SHIFT_CHROMA);
+                    count_record(s, ty2[mx], 0, my, SYM_BAND_SHIFT_CHROMA);
                 }
                 else
                 {
                     ty1[mx] = ty2[mx] = tag;
-                    run_c = (uint32_t)ht_get(tr, &s->bnr[1]);
+                    run_c = (uint32_t)ht_get(tr, &bnr1);
                 }
             }
         }
     }
+    s->mcbp = mcbp; s->mcbt = mcbt;
+    s->bn[0] = bn0; s->bn[1] = bn1; s->bnr[0] = bnr0; s->bnr[1] = bnr1;
+    s->dcv[0] = dcv0; s->dcv[1] = dcv1; s->dcv[2] = dcv2;
 }
 
 /* getMVector, h4m:1846-1860 */
@@ -832,6 +889,9 @@ static void pb_pass2(H4Seq *s, int16_t *mv_out)
     int cur_ref = -1;
     const int st0 = s->stride[0];
     s->n_inter_mcb = 0;
+    EmitCtx ctx;
+    emit_ctx_load(&ctx, s);
+    BR mvh = s->mvh, mvv = s->mvv;
     for (int my = 0; my < s->mbh; ++my)
     {
         const uint8_t *ty0 = s->type[0] + cell_at(s, 0, 0, my * 2);
@@ -846,9 +906,9 @@ static void pb_pass2(H4Seq *s, int16_t *mv_out)
             {   /* MCBlockDecDCNest, h4m:1789-1827 */
                 mvp[0] = mvp[1] = 0;
                 for (int k = 0; k < 4; ++k)
-                    emit_intra_block(s, 0, ty0[SUBY[k] * st0 + lx + SUBX[k]], 0, lx + SUBX[k], my * 2 + SUBY[k]);
-                emit_intra_block(s, 1, ty1[mx], 0, mx, my);
-                emit_intra_block(s, 2, ty2[mx], 0, mx, my);
+                    emit_intra_block(s, &ctx, 0, ty0[SUBY[k] * st0 + lx + SUBX[k]], 0, lx + SUBX[k], my * 2 + SUBY[k]);
+                emit_intra_block(s, &ctx, 1, ty1[mx], 0, mx, my);
+                emit_intra_block(s, &ctx, 2, ty2[mx], 0, mx, my);
                 continue;
             }
             const int ref = mt - 1;
@@ -858,8 +918,8 @@ static void pb_pass2(H4Seq *s, int16_t *mv_out)
                 cur_ref = ref;
                 mvx = mvy = 0;
             }
-            read_mv(s, &s->mvh, &mvx, s->rb[ref][0]);
-            read_mv(s, &s->mvv, &mvy, s->rb[ref][1]);
+            read_mv(s, &mvh, &mvx, s->rb[ref][0]);
+            read_mv(s, &mvv, &mvy, s->rb[ref][1]);
             const int32_t rx = mx * 16 + mvx, ry = my * 16 + mvy;   /* h4m:1954-1955 */
             int needs_window = 0;
             if (!(tag & 0x10))
@@ -872,11 +932,11 @@ static void pb_pass2(H4Seq *s, int16_t *mv_out)
                     const uint32_t nib = t & 0xF;
                     if (!nib) continue;
                     uint32_t *dst = place_record(s, t, 0, p, bx, by);
-                    if (nib == 6) emit_raw(s, p, dst);
+                    if (nib == 6) emit_raw(s, &ctx, p, dst);
                     else
                     {
-                        emit_bases(s, p, nib - 1, dst);
-                        emit_pair(s, p, dst + nib - 1);
+                        emit_bases(s, &ctx, p, nib - 1, dst);
+                        emit_pair(s, &ctx, p, dst + nib - 1);
                         if (nib > 1) needs_window = 1;
                     }
                 }
@@ -893,6 +953,9 @@ static void pb_pass2(H4Seq *s, int16_t *mv_out)
             }
         }
     }
+    emit_ctx_store(&ctx, s);
+    s->mvh = mvh;
+    s->mvv = mvv;
 }
 
 /* ------------------------------------------------------------------ entry points */
@@ -975,6 +1038,7 @@ size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_t pic_le
     s->dc_hi = 0x7F * (1 << s->dc_shift);   /* h4m:2001-2002, 2052-2053 */
     s->dc_lo = -0x80 * (1 << s->dc_shift);
 
+    reset_record_counts(s);
     if (is_i)
     {
         ipic_types(s);
@@ -996,13 +1060,16 @@ uint32_t h4e_parse_finish(H4Seq *s, uint8_t *blob)
     s->rec_base = (uint32_t *)(blob + h->off_rec);
     if (is_i)
     {   /* IpicPlaneDec order: plane by plane, raster (h4m:2011-2015, 1487-1518) */
+        EmitCtx ctx;
+        emit_ctx_load(&ctx, s);
         for (int p = 0; p < 3; ++p)
             for (int by = 0; by < s->bh[p]; ++by)
             {
                 const uint8_t *ty = s->type[p] + cell_at(s, p, 0, by);
                 for (int bx = 0; bx < s->bw[p]; ++bx)
-                    if (ty[bx] != 0 && ty[bx] != 8) emit_intra_block(s, p, ty[bx], 1, bx, by);
+                    if (ty[bx] != 0 && ty[bx] != 8) emit_intra_block(s, &ctx, p, ty[bx], 1, bx, by);
             }
+        emit_ctx_store(&ctx, s);
     }
     else
         pb_pass2(s, (int16_t *)(blob + h->off_mv));

@@ -73,32 +73,29 @@ recon_map_kernel(const ReconJob *__restrict__ jobs, int units_per_pic, int ctas_
         const int unit = (cta * kUnitsPerWarp + it) * kWarps + warp;
         if (unit >= units_per_pic) break;
         const int row = unit / v.nseg, mx0 = (unit - row * v.nseg) * SYM_SEG_MCBS;
+        /* luma: two passes over the segment's two block rows (plane is a compile-time 0 here) */
 #pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass)
+        for (int pass = 0; pass < 2; ++pass)
         {
-            int plane, bx, by;
-            bool valid;
-            if (pass < 2)
-            {
-                plane = 0;
-                bx = mx0 * 2 + lane;
-                by = row * 2 + pass;
-                valid = bx < v.mcb_w * 2;
-            }
-            else
-            {
-                plane = 1 + (lane >> 4);
-                bx = mx0 + (lane & 15);
-                by = row;
-                valid = bx < v.mcb_w;
-            }
-            if (!valid) continue;
-            const int pw = plane ? v.width >> 1 : v.width;
-            const int bstride = (pw >> 2) + 2;
-            const uint32_t t = __ldg(v.blob + rc_pick3(v.off_type, plane) + (by + 1) * bstride + bx + 1);
+            const int bx = mx0 * 2 + lane, by = row * 2 + pass;
+            if (bx >= v.mcb_w * 2) continue;
+            const int pw = v.width, bstride = (pw >> 2) + 2;
+            const uint32_t t = __ldg(v.blob + v.off_type[0] + (by + 1) * bstride + bx + 1);
+            uint32_t rows[4];
+            if (!rc_map_block(v, 0, bx, by, t, rows)) continue;
+            uint8_t *dst = v.present + (by * 4) * pw + bx * 4;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];
+        }
+        /* chroma: lanes 0-15 U, 16-31 V */
+        {
+            const int plane = 1 + (lane >> 4), bx = mx0 + (lane & 15), by = row;
+            if (bx >= v.mcb_w) continue;
+            const int pw = v.width >> 1, bstride = (pw >> 2) + 2;
+            const uint32_t t = __ldg(v.blob + (plane == 1 ? v.off_type[1] : v.off_type[2]) + (by + 1) * bstride + bx + 1);
             uint32_t rows[4];
             if (!rc_map_block(v, plane, bx, by, t, rows)) continue;
-            const int plane_off = plane == 0 ? 0 : plane == 1 ? v.width * v.height : v.width * v.height + (v.width >> 1) * (v.height >> 1);
+            const int plane_off = v.width * v.height + (plane == 2 ? pw * (v.height >> 1) : 0);
             uint8_t *dst = v.present + plane_off + (by * 4) * pw + bx * 4;
 #pragma unroll
             for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];

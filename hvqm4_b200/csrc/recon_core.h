@@ -133,10 +133,11 @@ RC_HD uint32_t rc_clamp255(int32_t x) { return x < 0 ? 0u : x > 255 ? 255u : (ui
 /* byte-wise (a + b + c + d + 2) >> 2 on four packed bytes, via two 16-bit lanes */
 RC_HD uint32_t rc_avg4x4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
-    const uint32_t M = 0x00FF00FFu;
-    const uint32_t lo = (a & M) + (b & M) + (c & M) + (d & M) + 0x00020002u;
-    const uint32_t hi = ((a >> 8) & M) + ((b >> 8) & M) + ((c >> 8) & M) + ((d >> 8) & M) + 0x00020002u;
-    return ((lo >> 2) & M) | (((hi >> 2) & M) << 8);
+    /* even bytes -> 16-bit lanes (PRMT 0x4240 = [b0,0,b2,0]); odd bytes (0x4341 = [b1,0,b3,0]) */
+    const uint32_t lo = RC_PRMT(a, 0u, 0x4240) + RC_PRMT(b, 0u, 0x4240) + RC_PRMT(c, 0u, 0x4240) + RC_PRMT(d, 0u, 0x4240) + 0x00020002u;
+    const uint32_t hi = RC_PRMT(a, 0u, 0x4341) + RC_PRMT(b, 0u, 0x4341) + RC_PRMT(c, 0u, 0x4341) + RC_PRMT(d, 0u, 0x4341) + 0x00020002u;
+    /* each lane sum <= 1022; after >> 2 bytes 0 and 2 hold the two results of the lane pair */
+    return RC_PRMT(lo >> 2, hi >> 2, 0x6240);
 }
 
 /* ---- weighted DC fill (h4m:293-383) ------------------------------------------------
@@ -238,7 +239,14 @@ RC_HD int32_t rc_aot_sum(const ReconView &v, const uint32_t *side, int n, const 
     int32_t scale_sum = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0;
-    for (int k = 0; k < n; ++k) rc_add_basis(v, RC_LD32(side + k), window, scale_sum, acc);
+    /* the first four basis words are fetched together (one memory latency instead of one per basis) */
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = k < n ? RC_LD32(side + k) : 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < n) rc_add_basis(v, w[k], window, scale_sum, acc);
+    for (int k = 4; k < n; ++k) rc_add_basis(v, RC_LD32(side + k), window, scale_sum, acc);
     uint32_t total = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) total += (uint32_t)acc[i];
