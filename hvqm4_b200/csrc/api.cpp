@@ -183,7 +183,7 @@ struct RecordedStep
 {
     uint8_t *d = nullptr;   /* jobs + blobs */
     int n = 0;
-    uint32_t rec_ctas = 0;
+    std::vector<uint32_t> rec_prefix;   /* n + 1 entries */
 };
 
 struct HVQM4Batch
@@ -204,6 +204,7 @@ struct HVQM4Batch
     std::vector<RecordedStep> recorded;
     uint64_t stats[8] = {0};
     std::vector<size_t> sizes, offs;
+    std::vector<uint32_t> rec_prefix;
     std::vector<uint8_t> seen;
 
     uint8_t *surface(int stream, int idx) const { return d_surfaces + ((size_t)stream * 3 + idx) * surf_stride; }
@@ -354,16 +355,17 @@ H4_API int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, con
     }
     /* record-kernel CTA ranges (chunk counts are known since phase A) */
     ReconJob *jobs = reinterpret_cast<ReconJob *>(a.h);
-    uint32_t rec_ctas = 0;
+    b->rec_prefix.resize((size_t)n + 1);
+    b->rec_prefix[0] = 0;
     for (int i = 0; i < n; ++i)
     {
         const uint32_t chunks = h4e_last_chunks(b->st[stream_ids[i]].seq);
-        jobs[i].rec_cta_begin = rec_ctas;
+        jobs[i].rec_cta_begin = b->rec_prefix[i];
         jobs[i].n_chunks = chunks;
         jobs[i].pad[0] = jobs[i].pad[1] = 0;
-        rec_ctas += hvqm4_rec_ctas(chunks);
+        b->rec_prefix[i + 1] = b->rec_prefix[i] + hvqm4_rec_ctas(chunks);
     }
-    if (b->recording) b->recorded.back().rec_ctas = rec_ctas;
+    if (b->recording) b->recorded.back().rec_prefix = b->rec_prefix;
     /* phase B: side words, motion vectors, maps -> pinned arena */
     std::atomic<uint32_t> err{0};
     std::atomic<uint64_t> inter{0};
@@ -399,7 +401,7 @@ H4_API int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, con
         b->d2h_pending = false;
     }
     int launched = 0;
-    int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(d_base), n, b->mcb_w, b->mcb_h, rec_ctas, b->s_comp, &launched);
+    int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(d_base), n, b->mcb_w, b->mcb_h, b->rec_prefix.data(), b->s_comp, &launched);
     g_launches += launched;
     b->stats[1] += (uint64_t)launched;
     if (rc != 0)
@@ -515,7 +517,7 @@ H4_API float HVQM4BatchReplay(HVQM4Batch *b, int repeats)
         for (auto &st : b->recorded)
         {
             int launched = 0;
-            int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(st.d), st.n, b->mcb_w, b->mcb_h, st.rec_ctas, b->s_comp, &launched);
+            int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(st.d), st.n, b->mcb_w, b->mcb_h, st.rec_prefix.data(), b->s_comp, &launched);
             g_launches += launched;
             b->stats[1] += (uint64_t)launched;
             if (rc != 0)
@@ -690,8 +692,8 @@ void compat_decode(SeqObj *so, int type, const uint8_t *frame, void *present, vo
     if (ok)
     {
         int launched = 0;
-        int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(c->d_blob), 1, c->mcb_w, c->mcb_h,
-                                    hvqm4_rec_ctas(job->n_chunks), c->stream, &launched);
+        const uint32_t prefix[2] = {0, hvqm4_rec_ctas(job->n_chunks)};
+        int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(c->d_blob), 1, c->mcb_w, c->mcb_h, prefix, c->stream, &launched);
         g_launches += launched;
         ok = rc == 0 || cuda_ok((cudaError_t)rc, "recon kernel launch");
     }

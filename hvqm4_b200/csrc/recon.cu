@@ -113,7 +113,7 @@ constexpr int kRecSmem = RC_SMEM_TABLE_BYTES + SYM_NEST_H * 40 + 16;
 
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kRecWarps * 32, kMinBlocks)
-recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs)
+recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs, uint32_t cta_base)
 {
     uint32_t *s_nest_tab = reinterpret_cast<uint32_t *>(rc_smem + RC_SMEM_NEST_OFF);
     int32_t *s_mcdiv = reinterpret_cast<int32_t *>(rc_smem + RC_SMEM_MCDIV_OFF);
@@ -124,14 +124,15 @@ recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs)
     /* which picture does this CTA belong to: last job with rec_cta_begin <= blockIdx.x */
     if (threadIdx.x == 0)
     {
+        const uint32_t gcta = blockIdx.x + cta_base;     /* rec_cta_begin is a prefix over the whole step */
         int lo = 0, hi = n_jobs - 1;
         while (lo < hi)
         {
             const int mid = (lo + hi + 1) >> 1;
-            if (__ldg(&jobs[mid].rec_cta_begin) <= blockIdx.x) lo = mid;
+            if (__ldg(&jobs[mid].rec_cta_begin) <= gcta) lo = mid;
             else hi = mid - 1;
         }
-        s_cta_in_pic = blockIdx.x - __ldg(&jobs[lo].rec_cta_begin);
+        s_cta_in_pic = gcta - __ldg(&jobs[lo].rec_cta_begin);
         load_view(vw, jobs[lo]);
     }
     for (int i = threadIdx.x; i < 256; i += kRecWarps * 32) s_mcdiv[i] = i ? 0x1000 / i : 0;   /* h4m:272 */
@@ -205,9 +206,9 @@ int launch_map(const ReconJob *d_jobs, int n_jobs, int units, cudaStream_t strea
 }
 
 template <int kMinBlocks>
-int launch_record(const ReconJob *d_jobs, int n_jobs, uint32_t total_ctas, cudaStream_t stream)
+int launch_record(const ReconJob *d_jobs, int n_jobs, uint32_t cta_base, uint32_t n_ctas, cudaStream_t stream)
 {
-    recon_record_kernel<kMinBlocks><<<total_ctas, kRecWarps * 32, kRecSmem, stream>>>(d_jobs, n_jobs);
+    recon_record_kernel<kMinBlocks><<<n_ctas, kRecWarps * 32, kRecSmem, stream>>>(d_jobs, n_jobs, cta_base);
     return (int)cudaGetLastError();
 }
 
@@ -219,38 +220,64 @@ int env_int(const char *name)
 
 }  // namespace
 
-extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, uint32_t total_rec_ctas,
+static int launch_map_cfg(int cfg, const ReconJob *d_jobs, int n_jobs, int units, cudaStream_t stream)
+{
+    switch (cfg)
+    {
+    case 1: return launch_map<4, 1, 1>(d_jobs, n_jobs, units, stream);
+    case 2: return launch_map<4, 2, 8>(d_jobs, n_jobs, units, stream);
+    case 3: return launch_map<8, 2, 4>(d_jobs, n_jobs, units, stream);
+    case 4: return launch_map<8, 4, 4>(d_jobs, n_jobs, units, stream);
+    case 5: return launch_map<4, 4, 10>(d_jobs, n_jobs, units, stream);
+    default:
+        /* few pictures: one segment per warp (latency); large batches: fewer, fatter CTAs */
+        return (long long)n_jobs * units >= 148ll * 64 ? launch_map<4, 2, 8>(d_jobs, n_jobs, units, stream)
+                                                       : launch_map<4, 1, 1>(d_jobs, n_jobs, units, stream);
+    }
+}
+
+static int launch_record_cfg(int cfg, const ReconJob *d_jobs, int n_jobs, uint32_t cta_base, uint32_t n_ctas, cudaStream_t stream)
+{
+    switch (cfg)
+    {
+    case 1: return launch_record<1>(d_jobs, n_jobs, cta_base, n_ctas, stream);
+    case 2: return launch_record<2>(d_jobs, n_jobs, cta_base, n_ctas, stream);
+    case 3: return launch_record<3>(d_jobs, n_jobs, cta_base, n_ctas, stream);
+    default: return launch_record<4>(d_jobs, n_jobs, cta_base, n_ctas, stream);   /* 64 registers, 4 CTAs/SM: measured best */
+    }
+}
+
+/*
+ * h_rec_prefix[i] = record-kernel CTAs of pictures 0..i-1 (n_jobs + 1 entries, host memory).
+ * The step can be issued in SUB-BATCHES of pictures (map kernel then record kernel per
+ * sub-batch) so that the record kernel finds the sectors the map kernel has just written still
+ * in L2; by default the sub-batch is the whole step (see below).
+ */
+extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const uint32_t *h_rec_prefix,
                                   cudaStream_t stream, int *launches)
 {
     if (n_jobs <= 0) return 0;
     const int nseg = (mcb_w + SYM_SEG_MCBS - 1) / SYM_SEG_MCBS;
     const int units = nseg * mcb_h;
-    /* HVQM4_MAP_CFG / HVQM4_REC_CFG pin a configuration (tuning experiments) */
-    static const int map_cfg = env_int("HVQM4_MAP_CFG"), rec_cfg = env_int("HVQM4_REC_CFG");
-    int rc;
-    switch (map_cfg)
+    /* HVQM4_MAP_CFG / HVQM4_REC_CFG / HVQM4_SUBBATCH pin a configuration (tuning experiments) */
+    static const int map_cfg = env_int("HVQM4_MAP_CFG"), rec_cfg = env_int("HVQM4_REC_CFG"), sub_env = env_int("HVQM4_SUBBATCH");
+    /* measured on B200 (1024 x 640x480 pictures): the whole step as ONE sub-batch is fastest -- grid
+       tails cost more than the L2 misses of the record kernel's read-modify-writes; sub-batching
+       stays available for experiments */
+    const int sub = sub_env > 0 ? sub_env : n_jobs;
+    for (int j0 = 0; j0 < n_jobs; j0 += sub)
     {
-    case 1: rc = launch_map<4, 1, 1>(d_jobs, n_jobs, units, stream); break;
-    case 2: rc = launch_map<4, 2, 8>(d_jobs, n_jobs, units, stream); break;
-    case 3: rc = launch_map<8, 2, 4>(d_jobs, n_jobs, units, stream); break;
-    case 4: rc = launch_map<8, 4, 4>(d_jobs, n_jobs, units, stream); break;
-    case 5: rc = launch_map<4, 4, 10>(d_jobs, n_jobs, units, stream); break;
-    default:
-        /* few pictures: one segment per warp (latency); large batches: fewer, fatter CTAs */
-        rc = (long long)n_jobs * units >= 148ll * 64 ? launch_map<4, 2, 8>(d_jobs, n_jobs, units, stream)
-                                                     : launch_map<4, 1, 1>(d_jobs, n_jobs, units, stream);
-        break;
+        const int nj = n_jobs - j0 < sub ? n_jobs - j0 : sub;
+        int rc = launch_map_cfg(map_cfg, d_jobs + j0, nj, units, stream);
+        if (rc != 0) return rc;
+        if (launches) ++*launches;
+        const uint32_t c0 = h_rec_prefix[j0], c1 = h_rec_prefix[j0 + nj];
+        if (c1 > c0)
+        {
+            rc = launch_record_cfg(rec_cfg, d_jobs, n_jobs, c0, c1 - c0, stream);
+            if (rc != 0) return rc;
+            if (launches) ++*launches;
+        }
     }
-    if (rc != 0) return rc;
-    if (launches) ++*launches;
-    if (total_rec_ctas == 0) return 0;
-    switch (rec_cfg)
-    {
-    case 1: rc = launch_record<1>(d_jobs, n_jobs, total_rec_ctas, stream); break;
-    case 2: rc = launch_record<2>(d_jobs, n_jobs, total_rec_ctas, stream); break;
-    case 4: rc = launch_record<4>(d_jobs, n_jobs, total_rec_ctas, stream); break;
-    default: rc = launch_record<3>(d_jobs, n_jobs, total_rec_ctas, stream); break;
-    }
-    if (rc == 0 && launches) ++*launches;
-    return rc;
+    return 0;
 }

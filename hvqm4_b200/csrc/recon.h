@@ -28,10 +28,12 @@ static inline uint32_t hvqm4_rec_ctas(uint32_t n_chunks)
 {
     return (n_chunks + HVQM4_REC_CHUNKS_PER_CTA - 1) / HVQM4_REC_CHUNKS_PER_CTA;
 }
-/* Reconstructs n_jobs pictures of identical geometry: one launch of the map kernel, then (if
-   total_rec_ctas > 0) one launch of the record kernel.  Returns a cudaError_t.  *launches is
-   incremented by the number of kernels launched. */
-int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, uint32_t total_rec_ctas,
+/* Reconstructs n_jobs pictures of identical geometry: per sub-batch of pictures one launch of
+   the map kernel, then one of the record kernel.  h_rec_prefix (host memory, n_jobs + 1 entries)
+   is the exclusive prefix of hvqm4_rec_ctas(n_chunks) over the pictures, the same values the
+   jobs carry in rec_cta_begin.  Returns a cudaError_t.  *launches is incremented by the number
+   of kernels launched. */
+int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const uint32_t *h_rec_prefix,
                        cudaStream_t stream, int *launches);
 #ifdef __cplusplus
 }
