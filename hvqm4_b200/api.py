@@ -78,6 +78,7 @@ SIGNATURES = {
     "HVQM4BatchReplay": (c_float, [c_void_p, c_int]),
     "HVQM4BatchStats": (None, [c_void_p, POINTER(c_uint64)]),
     "HVQM4KernelLaunches": (ctypes.c_longlong, []),
+    "HVQM4SetReconMode": (None, [c_int]),
     "HVQM4HostAlloc": (c_void_p, [c_size_t]),
     "HVQM4HostFree": (None, [c_void_p]),
     "HVQM4ParseFile": (c_int, [c_char_p, c_size_t, POINTER(FileInfo), POINTER(FrameRef), c_int]),
@@ -272,6 +273,11 @@ class Batch:
         lib().HVQM4BatchStats(self._h, out)
         keys = ("pictures", "launches", "symbol_bytes", "algorithmic_bytes", "host_ns", "inter_mcbs", "total_mcbs", "reserved")
         return dict(zip(keys, list(out)))
+
+
+def set_recon_mode(mode: int) -> None:
+    """0 auto, >0 fused band kernel, <0 map + record kernels (see include/hvqm4.h)."""
+    lib().HVQM4SetReconMode(mode)
 
 
 def kernel_launches() -> int:

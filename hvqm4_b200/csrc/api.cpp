@@ -824,6 +824,8 @@ H4_API void HVQM4DecodeBpic(SeqObj *seqobj, uint8_t const *frame, void *present,
 
 H4_API long long HVQM4KernelLaunches(void) { return g_launches.load(); }
 
+H4_API void HVQM4SetReconMode(int mode) { hvqm4_recon_set_mode(mode); }
+
 /* ====================================================================== container walker */
 
 static inline uint32_t be32(const uint8_t *p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }

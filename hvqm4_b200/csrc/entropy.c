@@ -212,6 +212,7 @@ struct H4Seq
     uint32_t *grp_count, *grp_base, *grp_next, *grp_chunk;
     uint32_t *chunks;                    /* chunk table under construction (2 words per chunk) */
     uint32_t chunks_cap;
+    uint32_t *band_first;                /* [SYM_REC_CLASSES][nbands + 1] */
     uint32_t errors_total;
 
     /* per picture, between parse_begin and parse_finish */
@@ -275,6 +276,7 @@ H4Seq *h4e_seq_create(int width, int height, int h_samp, int v_samp, int version
     /* upper bound on chunks: one per group plus one per 32 blocks, or one per block in the long bucket */
     s->chunks_cap = (uint32_t)s->ngroups + (uint32_t)(s->bw[0] * s->bh[0] + 2 * s->bw[1] * s->bh[1]);
     s->chunks = calloc((size_t)s->chunks_cap * 2, sizeof(uint32_t));
+    s->band_first = calloc((size_t)SYM_REC_CLASSES * (s->nbands + 1), sizeof(uint32_t));
     return s;
 }
 
@@ -291,6 +293,7 @@ void h4e_seq_destroy(H4Seq *s)
     free(s->grp_next);
     free(s->grp_chunk);
     free(s->chunks);
+    free(s->band_first);
     free(s);
 }
 
@@ -394,6 +397,8 @@ static void plan_records(H4Seq *s, int is_ipic)
     for (int cls = 0; cls < SYM_REC_CLASSES; ++cls)
     {
         for (int band = 0; band < s->nbands; ++band)
+        {
+            s->band_first[cls * (s->nbands + 1) + band] = chunk;
             for (int lb = 0; lb < SYM_LEN_BUCKETS; ++lb)
             {
                 const int g = (cls * s->nbands + band) * SYM_LEN_BUCKETS + lb;
@@ -421,6 +426,8 @@ static void plan_records(H4Seq *s, int is_ipic)
                     word += long_words;
                 }
             }
+        }
+        s->band_first[cls * (s->nbands + 1) + s->nbands] = chunk;
         if (cls == SYM_REC_INTRA) s->n_chunks_nest = chunk;
     }
     s->n_rec_words = word;
@@ -469,6 +476,9 @@ static void plan_blob(H4Seq *s)
     size_t at = sizeof(SymHeader);
     h->off_chunks = (uint32_t)at;
     at = align16(at + (size_t)s->n_chunks * 8);
+    h->off_bands = (uint32_t)at;
+    h->n_bands = (uint32_t)s->nbands;
+    at = align16(at + (size_t)SYM_REC_CLASSES * (s->nbands + 1) * 4);
     if (s->pic_type != SYM_PIC_I)
     {
         h->off_mv = (uint32_t)at;
@@ -1089,6 +1099,7 @@ uint32_t h4e_parse_finish(H4Seq *s, uint8_t *blob)
             s->err |= SYM_ERR_TRUNCATED;
     }
     memcpy(blob + h->off_chunks, s->chunks, (size_t)s->n_chunks * 8);
+    memcpy(blob + h->off_bands, s->band_first, (size_t)SYM_REC_CLASSES * (s->nbands + 1) * 4);
     for (int p = 0; p < 3; ++p)
     {
         memcpy(blob + h->off_type[p], s->type[p], s->map_cells[p]);

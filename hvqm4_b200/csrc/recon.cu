@@ -53,58 +53,128 @@ __device__ __forceinline__ void load_view(ReconView &vw, const ReconJob &J)
 }
 
 /* ------------------------------------------------------------------------------------------
- * map kernel
+ * building blocks shared by the kernels
+ * ------------------------------------------------------------------------------------------ */
+
+/* MAP work of one segment (16 macroblocks of macroblock row `row` starting at macroblock mx0):
+   three passes, one 4x4 block per lane and pass, 128 contiguous bytes per warp row store */
+__device__ __forceinline__ void map_segment(const ReconView &v, int row, int mx0, int lane)
+{
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass)
+    {   /* luma: the segment's two block rows (plane is a compile-time 0 here) */
+        const int bx = mx0 * 2 + lane, by = row * 2 + pass;
+        if (bx >= v.mcb_w * 2) continue;
+        const int pw = v.width, bstride = (pw >> 2) + 2;
+        const uint32_t t = __ldg(v.blob + v.off_type[0] + (by + 1) * bstride + bx + 1);
+        uint32_t rows[4];
+        if (!rc_map_block(v, 0, bx, by, t, rows)) continue;
+        uint8_t *dst = v.present + (by * 4) * pw + bx * 4;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];
+    }
+    {   /* chroma: lanes 0-15 U, 16-31 V */
+        const int plane = 1 + (lane >> 4), bx = mx0 + (lane & 15), by = row;
+        if (bx >= v.mcb_w) return;
+        const int pw = v.width >> 1, bstride = (pw >> 2) + 2;
+        const uint32_t t = __ldg(v.blob + (plane == 1 ? v.off_type[1] : v.off_type[2]) + (by + 1) * bstride + bx + 1);
+        uint32_t rows[4];
+        if (!rc_map_block(v, plane, bx, by, t, rows)) return;
+        const int plane_off = v.width * v.height + (plane == 2 ? pw * (v.height >> 1) : 0);
+        uint8_t *dst = v.present + plane_off + (by * 4) * pw + bx * 4;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];
+    }
+}
+
+/* RECORD work of one chunk: one record per lane */
+__device__ __forceinline__ void record_chunk(const ReconView &v, uint32_t c, int lane)
+{
+    const uint2 cd = __ldg(reinterpret_cast<const uint2 *>(v.chunks) + c);
+    const uint32_t count = cd.y & 0xFF, len = ((cd.y >> 8) & 0xFF) + 1;
+    const int cls = (int)((cd.y >> 16) & 0xFF);
+    if ((uint32_t)lane >= count) return;
+    const uint32_t *rec = v.rec + cd.x + lane * len;
+    uint32_t t;
+    int plane, bx, by;
+    rc_record_coords(__ldg(rec), t, plane, bx, by);
+    const int pw = plane ? v.width >> 1 : v.width;
+    const int plane_off = plane == 0 ? 0 : plane == 1 ? v.width * v.height : v.width * v.height + (v.width >> 1) * (v.height >> 1);
+    uint8_t *dst = v.present + plane_off + (by * 4) * pw + bx * 4;
+    uint32_t rows[4];
+    if (cls == SYM_REC_INTER)
+    {   /* the prediction left by the map work; L2-coherent loads (it may have been written by another warp) */
+#pragma unroll
+        for (int r = 0; r < 4; ++r) rows[r] = __ldcg(reinterpret_cast<const uint32_t *>(dst + r * pw));
+    }
+    rc_record_block(v, cls, len, rec, rows);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];
+}
+
+/* h4m:262-273 into shared memory */
+template <int kThreads>
+__device__ __forceinline__ void build_div_tables()
+{
+    int32_t *s_mcdiv = reinterpret_cast<int32_t *>(rc_smem + RC_SMEM_MCDIV_OFF);
+    int32_t *s_div = reinterpret_cast<int32_t *>(rc_smem + RC_SMEM_DIV_OFF);
+    for (int i = threadIdx.x; i < 256; i += kThreads) s_mcdiv[i] = i ? 0x1000 / i : 0;
+    if (threadIdx.x < 16) s_div[threadIdx.x] = threadIdx.x ? 0x1000 / (threadIdx.x * 16) * 16 : 0;
+}
+
+/* expands the packed nest of the CTA's picture into the shared-memory lookup table; the caller
+   provides 38 * 40 bytes of scratch and must __syncthreads() afterwards */
+template <int kThreads>
+__device__ __forceinline__ void build_nest_table(const ReconView &v, uint8_t *packed)
+{
+    uint32_t *s_nest_tab = reinterpret_cast<uint32_t *>(rc_smem + RC_SMEM_NEST_OFF);
+    /* stage the packed rows (35 B) at a 40-byte pitch, zero padded */
+    const uint8_t *src = v.blob + v.off_nest;
+    for (int i = threadIdx.x; i < SYM_NEST_H * 40; i += kThreads)
+    {
+        const int y = i / 40, x = i - y * 40;
+        packed[i] = x < SYM_NEST_ROW_BYTES ? __ldg(src + y * SYM_NEST_ROW_BYTES + x) : (uint8_t)0;
+    }
+    __syncthreads();
+    /* table entry (y, x) = nibbles x..x+7 of row y; (y, 2j) and (y, 2j+1) share bytes j..j+4 */
+    const uint32_t *pw = reinterpret_cast<const uint32_t *>(packed);
+    for (int i = threadIdx.x; i < SYM_NEST_H * 32; i += kThreads)
+    {
+        const int y = i >> 5, j = i & 31;
+        const int w = y * 10 + (j >> 2), sh = (j & 3) * 8;
+        const uint32_t w0 = pw[w], w1 = pw[w + 1], w2 = (j & 3) ? pw[w + 2] : 0u;
+        const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+        s_nest_tab[y * 64 + 2 * j] = lo;
+        s_nest_tab[y * 64 + 2 * j + 1] = (lo >> 4) | (hi << 28);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * map kernel (small batches: many CTAs per picture)
  * ------------------------------------------------------------------------------------------ */
 template <int kWarps, int kUnitsPerWarp, int kMinBlocks>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 recon_map_kernel(const ReconJob *__restrict__ jobs, int units_per_pic, int ctas_per_pic)
 {
-    ReconView &vw = *reinterpret_cast<ReconView *>(rc_smem);
+    ReconView &vw = *reinterpret_cast<ReconView *>(rc_smem + RC_SMEM_VIEW_OFF);
     const int job = blockIdx.x / ctas_per_pic;
     const int cta = blockIdx.x - job * ctas_per_pic;
     if (threadIdx.x == 0) load_view(vw, jobs[job]);
     __syncthreads();
     const ReconView &v = vw;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
 #pragma unroll 1
     for (int it = 0; it < kUnitsPerWarp; ++it)
     {
         const int unit = (cta * kUnitsPerWarp + it) * kWarps + warp;
         if (unit >= units_per_pic) break;
-        const int row = unit / v.nseg, mx0 = (unit - row * v.nseg) * SYM_SEG_MCBS;
-        /* luma: two passes over the segment's two block rows (plane is a compile-time 0 here) */
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass)
-        {
-            const int bx = mx0 * 2 + lane, by = row * 2 + pass;
-            if (bx >= v.mcb_w * 2) continue;
-            const int pw = v.width, bstride = (pw >> 2) + 2;
-            const uint32_t t = __ldg(v.blob + v.off_type[0] + (by + 1) * bstride + bx + 1);
-            uint32_t rows[4];
-            if (!rc_map_block(v, 0, bx, by, t, rows)) continue;
-            uint8_t *dst = v.present + (by * 4) * pw + bx * 4;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];
-        }
-        /* chroma: lanes 0-15 U, 16-31 V */
-        {
-            const int plane = 1 + (lane >> 4), bx = mx0 + (lane & 15), by = row;
-            if (bx >= v.mcb_w) continue;
-            const int pw = v.width >> 1, bstride = (pw >> 2) + 2;
-            const uint32_t t = __ldg(v.blob + (plane == 1 ? v.off_type[1] : v.off_type[2]) + (by + 1) * bstride + bx + 1);
-            uint32_t rows[4];
-            if (!rc_map_block(v, plane, bx, by, t, rows)) continue;
-            const int plane_off = v.width * v.height + (plane == 2 ? pw * (v.height >> 1) : 0);
-            uint8_t *dst = v.present + plane_off + (by * 4) * pw + bx * 4;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];
-        }
+        const int row = unit / v.nseg;
+        map_segment(v, row, (unit - row * v.nseg) * SYM_SEG_MCBS, lane);
     }
 }
 
 /* ------------------------------------------------------------------------------------------
- * record kernel
+ * record kernel (small batches)
  * shared memory: [nest table | mcdiv | div | view] at the fixed offsets of recon_core.h, then
  * a scratch area used only while the nest table is being built
  * ------------------------------------------------------------------------------------------ */
@@ -115,9 +185,6 @@ template <int kMinBlocks>
 __global__ void __launch_bounds__(kRecWarps * 32, kMinBlocks)
 recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs, uint32_t cta_base)
 {
-    uint32_t *s_nest_tab = reinterpret_cast<uint32_t *>(rc_smem + RC_SMEM_NEST_OFF);
-    int32_t *s_mcdiv = reinterpret_cast<int32_t *>(rc_smem + RC_SMEM_MCDIV_OFF);
-    int32_t *s_div = reinterpret_cast<int32_t *>(rc_smem + RC_SMEM_DIV_OFF);
     ReconView &vw = *reinterpret_cast<ReconView *>(rc_smem + RC_SMEM_VIEW_OFF);
     __shared__ uint32_t s_cta_in_pic;
 
@@ -135,63 +202,65 @@ recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs, uint32_t cta_
         s_cta_in_pic = gcta - __ldg(&jobs[lo].rec_cta_begin);
         load_view(vw, jobs[lo]);
     }
-    for (int i = threadIdx.x; i < 256; i += kRecWarps * 32) s_mcdiv[i] = i ? 0x1000 / i : 0;   /* h4m:272 */
-    if (threadIdx.x < 16) s_div[threadIdx.x] = threadIdx.x ? 0x1000 / (threadIdx.x * 16) * 16 : 0;   /* h4m:270 */
+    build_div_tables<kRecWarps * 32>();
     __syncthreads();
     const ReconView &v = vw;
     const uint32_t chunk0 = s_cta_in_pic * HVQM4_REC_CHUNKS_PER_CTA;
     const uint32_t chunk_end = min(chunk0 + HVQM4_REC_CHUNKS_PER_CTA, v.n_chunks);
-
     if (chunk0 < v.n_chunks_nest)
     {
-        /* stage the packed nest rows (35 B) at a 40-byte pitch, zero padded */
-        uint8_t *packed = rc_smem + RC_SMEM_TABLE_BYTES;
-        const uint8_t *src = v.blob + v.off_nest;
-        for (int i = threadIdx.x; i < SYM_NEST_H * 40; i += kRecWarps * 32)
-        {
-            const int y = i / 40, x = i - y * 40;
-            packed[i] = x < SYM_NEST_ROW_BYTES ? __ldg(src + y * SYM_NEST_ROW_BYTES + x) : (uint8_t)0;
-        }
-        __syncthreads();
-        /* table entry (y, x) = nibbles x..x+7 of row y; (y, 2j) and (y, 2j+1) share bytes j..j+4 */
-        const uint32_t *pw = reinterpret_cast<const uint32_t *>(packed);
-        for (int i = threadIdx.x; i < SYM_NEST_H * 32; i += kRecWarps * 32)
-        {
-            const int y = i >> 5, j = i & 31;
-            const int w = y * 10 + (j >> 2), sh = (j & 3) * 8;
-            const uint32_t w0 = pw[w], w1 = pw[w + 1], w2 = (j & 3) ? pw[w + 2] : 0u;
-            const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-            s_nest_tab[y * 64 + 2 * j] = lo;
-            s_nest_tab[y * 64 + 2 * j + 1] = (lo >> 4) | (hi << 28);
-        }
+        build_nest_table<kRecWarps * 32>(v, rc_smem + RC_SMEM_TABLE_BYTES);
         __syncthreads();
     }
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll 1
-    for (uint32_t c = chunk0 + warp; c < chunk_end; c += kRecWarps)
+    for (uint32_t c = chunk0 + warp; c < chunk_end; c += kRecWarps) record_chunk(v, c, lane);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * band kernel (large batches): one CTA reconstructs one BAND (SYM_BAND_MCB_ROWS macroblock rows)
+ * of one picture completely -- the map work of its segments, a block barrier, then exactly the
+ * records that lie in the band (the host groups records per band, symbuf.h).  The sectors the
+ * record work rewrites, and the reference rows both phases read, are then still in L2/L1
+ * instead of making a second round trip to HBM between two kernels.
+ * ------------------------------------------------------------------------------------------ */
+constexpr int kBandWarps = 8;
+
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kBandWarps * 32, kMinBlocks)
+recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands)
+{
+    ReconView &vw = *reinterpret_cast<ReconView *>(rc_smem + RC_SMEM_VIEW_OFF);
+    const int job = blockIdx.x / n_bands;
+    const int band = blockIdx.x - job * n_bands;
+    if (threadIdx.x == 0) load_view(vw, jobs[job]);
+    build_div_tables<kBandWarps * 32>();
+    __syncthreads();
+    const ReconView &v = vw;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    /* map phase: the band's segments */
+    const int row0 = band * SYM_BAND_MCB_ROWS, row1 = min(row0 + SYM_BAND_MCB_ROWS, v.mcb_h);
+    const int units = (row1 - row0) * v.nseg;
+#pragma unroll 1
+    for (int u = warp; u < units; u += kBandWarps)
     {
-        const uint2 cd = __ldg(reinterpret_cast<const uint2 *>(v.chunks) + c);
-        const uint32_t count = cd.y & 0xFF, len = ((cd.y >> 8) & 0xFF) + 1;
-        const int cls = (int)((cd.y >> 16) & 0xFF);
-        if ((uint32_t)lane >= count) continue;
-        const uint32_t *rec = v.rec + cd.x + lane * len;
-        uint32_t t;
-        int plane, bx, by;
-        rc_record_coords(__ldg(rec), t, plane, bx, by);
-        const int pw = plane ? v.width >> 1 : v.width;
-        const int plane_off = plane == 0 ? 0 : plane == 1 ? v.width * v.height : v.width * v.height + (v.width >> 1) * (v.height >> 1);
-        uint8_t *dst = v.present + plane_off + (by * 4) * pw + bx * 4;
-        uint32_t rows[4];
-        if (cls == SYM_REC_INTER)
-        {   /* the prediction written by the map kernel (plain loads: written by the previous launch) */
-#pragma unroll
-            for (int r = 0; r < 4; ++r) rows[r] = *reinterpret_cast<const uint32_t *>(dst + r * pw);
-        }
-        rc_record_block(v, cls, len, rec, rows);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];
+        const int r = u / v.nseg;
+        map_segment(v, row0 + r, (u - r * v.nseg) * SYM_SEG_MCBS, lane);
     }
+    /* record phase */
+    const uint32_t nb1 = v.n_bands + 1;
+    const uint32_t raw0 = __ldg(v.bands + band), raw1 = __ldg(v.bands + band + 1);
+    const uint32_t intra0 = __ldg(v.bands + nb1 + band), intra1 = __ldg(v.bands + nb1 + band + 1);
+    const uint32_t inter0 = __ldg(v.bands + 2 * nb1 + band), inter1 = __ldg(v.bands + 2 * nb1 + band + 1);
+    if (intra1 > intra0) build_nest_table<kBandWarps * 32>(v, rc_smem + RC_SMEM_TABLE_BYTES);
+    __syncthreads();     /* map stores of the band visible to the whole CTA; nest table complete */
+#pragma unroll 1
+    for (uint32_t c = raw0 + warp; c < raw1; c += kBandWarps) record_chunk(v, c, lane);
+#pragma unroll 1
+    for (uint32_t c = intra0 + warp; c < intra1; c += kBandWarps) record_chunk(v, c, lane);
+#pragma unroll 1
+    for (uint32_t c = inter0 + warp; c < inter1; c += kBandWarps) record_chunk(v, c, lane);
 }
 
 template <int kWarps, int kUnitsPerWarp, int kMinBlocks>
@@ -201,7 +270,7 @@ int launch_map(const ReconJob *d_jobs, int n_jobs, int units, cudaStream_t strea
     const int ctas_per_pic = (units + per_cta - 1) / per_cta;
     const long long grid = (long long)ctas_per_pic * n_jobs;
     if (grid > 0x7FFFFFFFll) return (int)cudaErrorInvalidConfiguration;
-    recon_map_kernel<kWarps, kUnitsPerWarp, kMinBlocks><<<(unsigned)grid, kWarps * 32, sizeof(ReconView), stream>>>(d_jobs, units, ctas_per_pic);
+    recon_map_kernel<kWarps, kUnitsPerWarp, kMinBlocks><<<(unsigned)grid, kWarps * 32, RC_SMEM_TABLE_BYTES, stream>>>(d_jobs, units, ctas_per_pic);
     return (int)cudaGetLastError();
 }
 
@@ -219,6 +288,17 @@ int env_int(const char *name)
 }
 
 }  // namespace
+
+template <int kMinBlocks>
+int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, cudaStream_t stream)
+{
+    const long long grid = (long long)n_jobs * n_bands;
+    if (grid > 0x7FFFFFFFll) return (int)cudaErrorInvalidConfiguration;
+    recon_band_kernel<kMinBlocks><<<(unsigned)grid, kBandWarps * 32, kRecSmem, stream>>>(d_jobs, n_bands);
+    return (int)cudaGetLastError();
+}
+
+int g_band_mode = 0;   /* set by hvqm4_recon_set_mode: 0 auto, >0 force band kernel, <0 force map+record kernels */
 
 static int launch_map_cfg(int cfg, const ReconJob *d_jobs, int n_jobs, int units, cudaStream_t stream)
 {
@@ -253,6 +333,8 @@ static int launch_record_cfg(int cfg, const ReconJob *d_jobs, int n_jobs, uint32
  * sub-batch) so that the record kernel finds the sectors the map kernel has just written still
  * in L2; by default the sub-batch is the whole step (see below).
  */
+extern "C" void hvqm4_recon_set_mode(int band_mode) { g_band_mode = band_mode; }
+
 extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const uint32_t *h_rec_prefix,
                                   cudaStream_t stream, int *launches)
 {
@@ -261,6 +343,25 @@ extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w,
     const int units = nseg * mcb_h;
     /* HVQM4_MAP_CFG / HVQM4_REC_CFG / HVQM4_SUBBATCH pin a configuration (tuning experiments) */
     static const int map_cfg = env_int("HVQM4_MAP_CFG"), rec_cfg = env_int("HVQM4_REC_CFG"), sub_env = env_int("HVQM4_SUBBATCH");
+    static const int band_env = env_int("HVQM4_BAND");   /* 1..4: force the band kernel (min blocks), -1: never */
+    const int n_bands = (mcb_h + SYM_BAND_MCB_ROWS - 1) / SYM_BAND_MCB_ROWS;
+    const int band_mode = g_band_mode != 0 ? g_band_mode : band_env;
+    /* auto: the fused band kernel pays off when the batch fills the GPU with bands AND the pictures are
+       record-heavy (measured: +4..8 % on dense content, -15 % on sparse content, where the map work
+       dominates and prefers the map kernel's higher occupancy) */
+    const bool record_heavy = h_rec_prefix[n_jobs] >= 8u * (uint32_t)n_jobs;
+    if (band_mode > 0 || (band_mode == 0 && record_heavy && (long long)n_jobs * n_bands >= 148ll * 4))
+    {
+        int rc;
+        switch (band_mode)
+        {
+        case 2: rc = launch_band<2>(d_jobs, n_jobs, n_bands, stream); break;
+        case 3: rc = launch_band<3>(d_jobs, n_jobs, n_bands, stream); break;
+        default: rc = launch_band<4>(d_jobs, n_jobs, n_bands, stream); break;
+        }
+        if (rc == 0 && launches) ++*launches;
+        return rc;
+    }
     /* measured on B200 (1024 x 640x480 pictures): the whole step as ONE sub-batch is fastest -- grid
        tails cost more than the L2 misses of the record kernel's read-modify-writes; sub-batching
        stays available for experiments */

@@ -33,6 +33,9 @@ static inline uint32_t hvqm4_rec_ctas(uint32_t n_chunks)
    is the exclusive prefix of hvqm4_rec_ctas(n_chunks) over the pictures, the same values the
    jobs carry in rec_cta_begin.  Returns a cudaError_t.  *launches is incremented by the number
    of kernels launched. */
+/* 0 = choose by batch size (default), > 0 = always the fused band kernel, < 0 = always the
+   map + record kernel pair */
+void hvqm4_recon_set_mode(int band_mode);
 int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const uint32_t *h_rec_prefix,
                        cudaStream_t stream, int *launches);
 #ifdef __cplusplus

@@ -90,9 +90,9 @@ struct ReconView
     int mcb_w;
     /* used by the kernels only */
     uint8_t *present;
-    const uint32_t *rec, *chunks;
+    const uint32_t *rec, *chunks, *bands;
     int nseg, mcb_h, has_nest;
-    uint32_t off_nest, n_chunks, n_chunks_nest;
+    uint32_t off_nest, n_chunks, n_chunks_nest, n_bands;
 };
 
 RC_HD void rc_make_view(ReconView &v, const uint8_t *blob, const SymHeader &h, const uint32_t *nest_tab,
@@ -109,6 +109,8 @@ RC_HD void rc_make_view(ReconView &v, const uint8_t *blob, const SymHeader &h, c
     v.present = nullptr;
     v.rec = reinterpret_cast<const uint32_t *>(blob + h.off_rec);
     v.chunks = reinterpret_cast<const uint32_t *>(blob + h.off_chunks);
+    v.bands = reinterpret_cast<const uint32_t *>(blob + h.off_bands);
+    v.n_bands = h.n_bands;
     v.nseg = h.nseg; v.mcb_h = h.mcb_h; v.has_nest = h.has_nest;
     v.off_nest = h.off_nest; v.n_chunks = h.n_chunks; v.n_chunks_nest = h.n_chunks_nest;
 }

@@ -41,6 +41,9 @@
  *                    word 0  offset of the first record (words from off_rec)
  *                    word 1  [7:0] count, [15:8] record length - 1, [23:16] class (SYM_REC_*)
  *                  Chunks [0, n_chunks_nest) are raw/intra (need the nest), the rest inter.
+ *   band table     first chunk of every (class, band) pair, so that one CTA can reconstruct a
+ *                  whole band of the picture -- its map blocks first, then exactly the records
+ *                  that lie in it -- while the band's output sectors are still in cache.
  */
 #ifndef HVQM4_SYMBUF_H
 #define HVQM4_SYMBUF_H
@@ -97,7 +100,10 @@ typedef struct SymHeader
     uint32_t n_chunks;
     uint32_t n_chunks_nest;    /* leading chunks that are raw / intra AOT */
     uint32_t n_records;
-    uint32_t pad2[10];
+    uint32_t off_bands;        /* uint32 [SYM_REC_CLASSES][n_bands + 1]: first chunk of (class, band); the
+                                  chunks of a (class, band) pair are contiguous */
+    uint32_t n_bands;
+    uint32_t pad2[8];
 } SymHeader;                   /* 128 bytes */
 
 #ifdef __cplusplus

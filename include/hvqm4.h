@@ -176,6 +176,11 @@ void HVQM4BatchStats(HVQM4Batch *b, uint64_t out[8]);
    SDK-mode decodes); used by benchmarks to report how much work really ran on the GPU. */
 long long HVQM4KernelLaunches(void);
 
+/* Reconstruction schedule: 0 = chosen by batch size (default); > 0 = always the fused per-band
+   kernel (one launch per step); < 0 = always the map kernel + record kernel pair.  Both give
+   identical pictures; the switch exists for tests and measurements.  Process-wide. */
+void HVQM4SetReconMode(int mode);
+
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA toolchain. */
 void *HVQM4HostAlloc(size_t bytes);
 void HVQM4HostFree(void *p);

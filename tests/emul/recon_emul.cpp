@@ -1,11 +1,12 @@
 /*
  * tests/emul/recon_emul.cpp -- TEST INFRASTRUCTURE ONLY.
  *
- * Serial CPU driver for hvqm4_b200/csrc/recon_core.h: runs the work of the two CUDA kernels
- * in the same order of phases -- MAP phase (every block from the type/DC maps: weighted, flat,
- * motion compensation), then RECORD phase (chunk table -> grouped records: raw, intra AOT,
+ * Serial CPU driver for hvqm4_b200/csrc/recon_core.h: runs the work of the CUDA kernels band by
+ * band -- MAP phase (every block of the band from the type/DC maps: weighted, flat, motion
+ * compensation), then RECORD phase (band table -> chunk table -> grouped records: raw, intra AOT,
  * predicted AOT on top of the prediction written by the map phase) -- calling the same
- * __host__ __device__ block functions.  It exists so that the host stage (entropy.c) and the
+ * __host__ __device__ block functions, and checks that the band and chunk tables cover every
+ * record exactly once.  It exists so that the host stage (entropy.c) and the
  * block arithmetic can be checked against the oracle in a container without a GPU.  It is
  * never built into, or reachable from, the product library.
  */
@@ -36,45 +37,58 @@ int emul_recon_picture(const uint8_t *blob, uint8_t *present, const uint8_t *pas
     rc_make_view(v, blob, h, nest_tab, g_div, g_mcdiv, past, future);
     uint8_t *planes[3] = {present, present + h.width * h.height, present + h.width * h.height * 5 / 4};
 
-    /* MAP phase */
-    for (int plane = 0; plane < 3; ++plane)
+    /* band by band, like the fused CUDA kernel: the band's map blocks, then the records of the band
+       (the chunks of every (class, band) pair are contiguous; the band table gives their start) */
+    uint32_t seen = 0, chunks_seen = 0;
+    if (h.n_bands != (uint32_t)((h.mcb_h + SYM_BAND_MCB_ROWS - 1) / SYM_BAND_MCB_ROWS)) return -6;
+    for (uint32_t band = 0; band < h.n_bands; ++band)
     {
-        const int pw = h.width >> (plane ? 1 : 0), ph = h.height >> (plane ? 1 : 0);
-        const int bstride = (pw >> 2) + 2;
-        for (int by = 0; by < ph / 4; ++by)
-            for (int bx = 0; bx < pw / 4; ++bx)
-            {
-                const uint32_t t = blob[h.off_type[plane] + (by + 1) * bstride + bx + 1];
-                uint32_t rows[4];
-                if (!rc_map_block(v, plane, bx, by, t, rows)) continue;
-                for (int r = 0; r < 4; ++r) memcpy(planes[plane] + (by * 4 + r) * pw + bx * 4, &rows[r], 4);
-            }
-    }
-    /* RECORD phase */
-    uint32_t seen = 0;
-    for (uint32_t c = 0; c < h.n_chunks; ++c)
-    {
-        const uint32_t first = v.chunks[2 * c], desc = v.chunks[2 * c + 1];
-        const uint32_t count = desc & 0xFF, len = ((desc >> 8) & 0xFF) + 1;
-        const int cls = (int)((desc >> 16) & 0xFF);
-        if (count == 0 || count > SYM_CHUNK) return -3;
-        if ((c < h.n_chunks_nest) != (cls != SYM_REC_INTER)) return -4;
-        for (uint32_t i = 0; i < count; ++i)
+        const int my0 = (int)band * SYM_BAND_MCB_ROWS, my1 = my0 + SYM_BAND_MCB_ROWS < h.mcb_h ? my0 + SYM_BAND_MCB_ROWS : h.mcb_h;
+        for (int plane = 0; plane < 3; ++plane)
         {
-            const uint32_t *rec = v.rec + first + i * len;
-            if (first + (i + 1) * len > h.n_rec_words) return -5;
-            uint32_t t;
-            int plane, bx, by;
-            rc_record_coords(rec[0], t, plane, bx, by);
             const int pw = h.width >> (plane ? 1 : 0);
-            uint8_t *dst = planes[plane] + (by * 4) * pw + bx * 4;
-            uint32_t rows[4];
-            for (int r = 0; r < 4; ++r) memcpy(&rows[r], dst + r * pw, 4);
-            rc_record_block(v, cls, len, rec, rows);
-            for (int r = 0; r < 4; ++r) memcpy(dst + r * pw, &rows[r], 4);
-            ++seen;
+            const int bstride = (pw >> 2) + 2;
+            const int by0 = plane ? my0 : my0 * 2, by1 = plane ? my1 : my1 * 2;
+            for (int by = by0; by < by1; ++by)
+                for (int bx = 0; bx < pw / 4; ++bx)
+                {
+                    const uint32_t t = blob[h.off_type[plane] + (by + 1) * bstride + bx + 1];
+                    uint32_t rows[4];
+                    if (!rc_map_block(v, plane, bx, by, t, rows)) continue;
+                    for (int r = 0; r < 4; ++r) memcpy(planes[plane] + (by * 4 + r) * pw + bx * 4, &rows[r], 4);
+                }
+        }
+        for (int cls = 0; cls < SYM_REC_CLASSES; ++cls)
+        {
+            const uint32_t c0 = v.bands[cls * (h.n_bands + 1) + band], c1 = v.bands[cls * (h.n_bands + 1) + band + 1];
+            if (c0 > c1 || c1 > h.n_chunks) return -7;
+            for (uint32_t c = c0; c < c1; ++c, ++chunks_seen)
+            {
+                const uint32_t first = v.chunks[2 * c], desc = v.chunks[2 * c + 1];
+                const uint32_t count = desc & 0xFF, len = ((desc >> 8) & 0xFF) + 1;
+                if ((int)((desc >> 16) & 0xFF) != cls) return -8;
+                if (count == 0 || count > SYM_CHUNK) return -3;
+                if ((c < h.n_chunks_nest) != (cls != SYM_REC_INTER)) return -4;
+                for (uint32_t i = 0; i < count; ++i)
+                {
+                    const uint32_t *rec = v.rec + first + i * len;
+                    if (first + (i + 1) * len > h.n_rec_words) return -5;
+                    uint32_t t;
+                    int plane, bx, by;
+                    rc_record_coords(rec[0], t, plane, bx, by);
+                    if ((uint32_t)((plane ? by : by >> 1) / SYM_BAND_MCB_ROWS) != band) return -9;
+                    const int pw = h.width >> (plane ? 1 : 0);
+                    uint8_t *dst = planes[plane] + (by * 4) * pw + bx * 4;
+                    uint32_t rows[4];
+                    for (int r = 0; r < 4; ++r) memcpy(&rows[r], dst + r * pw, 4);
+                    rc_record_block(v, cls, len, rec, rows);
+                    for (int r = 0; r < 4; ++r) memcpy(dst + r * pw, &rows[r], 4);
+                    ++seen;
+                }
+            }
         }
     }
+    if (chunks_seen != h.n_chunks) return -10;
     if (seen != h.n_records) return -2;   /* chunk table must cover every record exactly once */
     return 0;
 }

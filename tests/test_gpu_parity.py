@@ -11,13 +11,21 @@ from tests.h4m_util import md5
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(params=["two_kernels", "band_kernel"])
+def recon_mode(request, native_lib):
+    """Every parity test runs under both reconstruction schedules (include/hvqm4.h HVQM4SetReconMode)."""
+    native_lib.set_recon_mode(-1 if request.param == "two_kernels" else 4)
+    yield request.param
+    native_lib.set_recon_mode(0)
+
 SDK_CASES = ["cfg1_320x240_v15_I30", "cfg2_640x480_v15_IP15", "cfg3_640x480_v15_IPB", "cfg4_320x240_v13_IPB",
              "realistic_640x480_v15_IPB", "realistic_320x240_v13_IPB", "min_280x152_v15_IPB",
              "ragged_328x248_v15_IPB", "wide_1024x576_v13_IPB"]
 
 
 @pytest.mark.parametrize("name", SDK_CASES)
-def test_sdk_entry_points_match_golden(native_lib, golden, name):
+def test_sdk_entry_points_match_golden(native_lib, golden, name, recon_mode):
     """HVQM4InitSeqObj/BuffSize/SetBuffer/DecodeIpic/Ppic/Bpic with host buffers, driven like the
     reference's decode_video(): per-frame MD5 must equal the reference decoder's."""
     case = golden[name]
@@ -29,7 +37,7 @@ def test_sdk_entry_points_match_golden(native_lib, golden, name):
     assert [m for _, _, m in got] == case["md5"]
 
 
-def test_sdk_entry_points_match_oracle_port_bytes(native_lib, oracle):
+def test_sdk_entry_points_match_oracle_port_bytes(native_lib, oracle, recon_mode):
     """Same seeds, fresh streams, byte comparison against the oracle port (reports the first
     differing block instead of just a hash)."""
     for seed in range(4):
@@ -44,7 +52,7 @@ def test_sdk_entry_points_match_oracle_port_bytes(native_lib, oracle):
         player.close()
 
 
-def test_batch_runtime_matches_golden_cfg5(native_lib, golden):
+def test_batch_runtime_matches_golden_cfg5(native_lib, golden, recon_mode):
     """Config 5 in miniature: independent streams batched per launch; every stream's every
     frame must match the reference MD5."""
     names = ["cfg5_stream0", "cfg5_stream1", "cfg5_stream511", "cfg5_stream1023"]
@@ -58,7 +66,7 @@ def test_batch_runtime_matches_golden_cfg5(native_lib, golden):
     assert step == 16
 
 
-def test_batch_runtime_many_streams_vs_oracle(native_lib, oracle):
+def test_batch_runtime_many_streams_vs_oracle(native_lib, oracle, recon_mode):
     """48 streams with distinct seeds in one batch (partial warps, several CTAs per SM)."""
     n = 48
     files = [synth.generate(320, 240, 15, "IPBBP", 1, seed=9000 + i, profile=i % 2) for i in range(n)]
@@ -70,6 +78,7 @@ def test_batch_runtime_many_streams_vs_oracle(native_lib, oracle):
 
 def test_record_replay_is_idempotent_and_counts_launches(native_lib, golden):
     """Reconstruction-only replay (what bench.py times) must reproduce the same pictures."""
+    native_lib.set_recon_mode(-1)
     case = golden["cfg5_stream1"]
     data = synth.generate(**case["args"])
     info, frames = native_lib.parse_file(data)
@@ -93,9 +102,10 @@ def test_record_replay_is_idempotent_and_counts_launches(native_lib, golden):
     st = batch.stats()
     assert st["pictures"] == n * len(frames) and st["algorithmic_bytes"] > st["pictures"] * batch.frame_bytes
     batch.close()
+    native_lib.set_recon_mode(0)
 
 
-def test_full_size_properties_640x480(native_lib):
+def test_full_size_properties_640x480(native_lib, recon_mode):
     """Size-independent properties at BASELINE.json's full size (no oracle needed):
     (1) a stream decoded alone and inside a batch of different streams gives identical frames;
     (2) decoding the same stream twice is deterministic;
