@@ -20,6 +20,16 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifdef H4E_PROFILE   /* developer aid: cycle counters per phase (tools only, never defined in the product build) */
+#include <x86intrin.h>
+unsigned long long h4e_prof[8];
+#define PROF_T0() unsigned long long prof_t = __rdtsc()
+#define PROF_ADD(i) do { unsigned long long n_ = __rdtsc(); h4e_prof[i] += n_ - prof_t; prof_t = n_; } while (0)
+#else
+#define PROF_T0() do { } while (0)
+#define PROF_ADD(i) do { } while (0)
+#endif
+
 /* ------------------------------------------------------------------ bit reader */
 
 typedef struct
@@ -991,6 +1001,7 @@ size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_t pic_le
         pic = zero_hdr;
         pic_len = sizeof zero_hdr;
     }
+    PROF_T0();
     const uint8_t *tab = pic + 8, *data = tab + nsec * 4;
     const size_t dlen = pic_len - 8 - (size_t)nsec * 4;
     int nest_x = 0, nest_y = 0;
@@ -1047,6 +1058,7 @@ size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_t pic_le
         if (s->tree[t].bad) s->err |= SYM_ERR_BAD_TREE;
     s->dc_hi = 0x7F * (1 << s->dc_shift);   /* h4m:2001-2002, 2052-2053 */
     s->dc_lo = -0x80 * (1 << s->dc_shift);
+    PROF_ADD(0);
 
     reset_record_counts(s);
     if (is_i)
@@ -1057,8 +1069,10 @@ size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_t pic_le
     }
     else
         pb_pass1(s);
+    PROF_ADD(1);
     plan_records(s, is_i);
     plan_blob(s);
+    PROF_ADD(2);
     return s->blob_bytes;
 }
 
@@ -1067,6 +1081,7 @@ uint32_t h4e_parse_finish(H4Seq *s, uint8_t *blob)
     const SymHeader *h = &s->hdr;
     const int is_i = s->pic_type == SYM_PIC_I;
     if (s->blob_bytes == 0) return s->err;
+    PROF_T0();
     s->rec_base = (uint32_t *)(blob + h->off_rec);
     if (is_i)
     {   /* IpicPlaneDec order: plane by plane, raster (h4m:2011-2015, 1487-1518) */
@@ -1084,6 +1099,7 @@ uint32_t h4e_parse_finish(H4Seq *s, uint8_t *blob)
     else
         pb_pass2(s, (int16_t *)(blob + h->off_mv));
 
+    PROF_ADD(3);
     /* every reader must have stayed inside its section */
     {
         BR *all[] = {&s->bn[0], &s->bnr[0], &s->bn[1], &s->bnr[1], &s->dcv[0], &s->dcv[1], &s->dcv[2],
@@ -1110,5 +1126,6 @@ uint32_t h4e_parse_finish(H4Seq *s, uint8_t *blob)
     out.errors = s->err;
     memcpy(blob, &out, sizeof out);
     s->errors_total |= s->err;
+    PROF_ADD(4);
     return s->err;
 }
