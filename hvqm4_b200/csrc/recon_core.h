@@ -271,10 +271,22 @@ RC_HD void rc_intra_aot(const ReconView &v, uint32_t rows[4], const uint32_t *si
     }
 }
 
-/* ---- half-sample prediction (h4m:1242-1294), branch-free on the phase ------------------
- * Rows are read as two aligned 32-bit words (covers the 5 bytes a row can need). */
+/* ---- half-sample prediction (h4m:1242-1294) ----------------------------------------------
+ * Rows are read as two aligned 32-bit words (covers the 5 bytes a row can need).  Two exact
+ * formulations, chosen per WARP so that lanes do not diverge:
+ *   no lane needs both half steps:  out = (a + o + 1) >> 1 with o = the tap one step right, or
+ *                                   one step down, or a itself ((a + a + 1) >> 1 = a);
+ *   otherwise:                      out = (p00 + p01 + p10 + p11 + 2) >> 2 with taps aliased when
+ *                                   a phase bit is 0 ((4a+2)>>2 = a, (2a+2b+2)>>2 = (a+b+1)>>1). */
+RC_HD uint32_t rc_avg4(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) & 0xFEFEFEFEu) >> 1); }
+
 RC_HD void rc_predict(uint32_t rows[4], const uint8_t *src, int stride, int hx, int hy)
 {
+#if defined(__CUDA_ARCH__)
+    const bool any_diag = __any_sync(__activemask(), hx & hy);
+#else
+    const bool any_diag = hx & hy;
+#endif
     const uint32_t a = (uint32_t)((uintptr_t)src & 3);
     const uint8_t *base = src - a;
     uint32_t A[5], Bx[5];
@@ -291,10 +303,10 @@ RC_HD void rc_predict(uint32_t rows[4], const uint8_t *src, int stride, int hx, 
         else
             A[r] = Bx[r] = 0;
     }
-    if (!hx && !hy)
+    if (!any_diag)
     {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) rows[r] = A[r];
+        for (int r = 0; r < 4; ++r) rows[r] = rc_avg4(A[r], hx ? Bx[r] : hy ? A[r + 1] : A[r]);
         return;
     }
 #pragma unroll
