@@ -144,3 +144,42 @@ def test_device_pointer_mode_skips_copies(native_lib, golden):
         if fr.frame_type != 0x30:
             present, future = future, present
     dec.close()
+
+
+def test_corrupt_pictures_do_not_fault_the_gpu(native_lib):
+    """Bit-flipped and truncated pictures through the SDK entry points: the host stage must flag
+    them (HVQM4GetLastError) and the kernels must stay inside the surfaces (no CUDA error, and the
+    library keeps decoding valid pictures afterwards)."""
+    import numpy as np
+    data = synth.generate(320, 240, 15, "IPB", 1, seed=4242, profile=0)
+    info, frames = native_lib.parse_file(data)
+    rng = np.random.default_rng(7)
+    flagged = 0
+    for trial in range(12):
+        dec = native_lib.SeqDecoder(info.width, info.height, info.version)
+        bufs = [(ctypes.c_uint8 * dec.frame_bytes)() for _ in range(3)]
+        past, present, future = 0, 1, 2
+        for fr in frames:
+            if fr.frame_type != 0x30:
+                past, future = future, past
+            pic = bytearray(data[fr.offset:fr.offset + fr.bytes])
+            if fr.frame_type != 0x10:                      # keep the I picture intact, damage P and B
+                if trial % 2:
+                    pic = pic[: max(80, len(pic) * (1 + trial % 5) // 6)]
+                else:
+                    for _ in range(60):
+                        pic[int(rng.integers(76, len(pic)))] ^= 1 << int(rng.integers(0, 8))
+            try:
+                dec.decode(fr.frame_type, bytes(pic), bufs[present], bufs[past], bufs[future])
+            except native_lib.HVQM4Error as e:
+                assert e.bits < (1 << 16), f"runtime error, not a stream error: {e}"
+                flagged += 1
+            if fr.frame_type != 0x30:
+                present, future = future, present
+        dec.close()
+    assert flagged > 0
+    assert native_lib.lib().HVQM4GetLastCudaError() == 0
+    # the library still decodes a valid stream bit-exactly afterwards
+    a = [yuv for _, _, yuv in native_lib.Player(data)]
+    b = [yuv for _, _, yuv in native_lib.Player(data)]
+    assert a == b
