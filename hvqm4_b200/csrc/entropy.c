@@ -203,6 +203,174 @@ static inline int32_t ht_get_uovf(const HTab *t, BR *b)
     return sum;
 }
 
+/* ------------------------------------------------------------------ flat symbol streams
+ * Sections that hold nothing but Huffman symbols are decoded in ONE tight loop each, straight
+ * after the trees are known, into arrays; the syntax loops below then consume plain array
+ * elements.  Decoding a section needs no syntax knowledge (one tree per section), and taking
+ * the serial bit-reader dependency chain out of the branchy syntax code is worth ~1.6x on the
+ * host stage.  Sections that mix raw bits with symbols (mcb_type, mcb_proc, mv_h, mv_v) stay
+ * interleaved; they are small. */
+
+typedef struct
+{
+    int32_t *v;          /* decoded values (escape-extended sums for the DC sections) */
+    uint32_t pos, n, cap;
+    int32_t cval;        /* value of a constant stream */
+    uint8_t is_const;    /* single-leaf or absent tree: every symbol costs 0 bits (h4m:638-650) */
+    uint8_t over;        /* consumer ran past the end */
+} SymStream;
+
+static inline int32_t ss_get(SymStream *q)
+{
+    if (q->pos < q->n) return q->v[q->pos++];
+    if (q->is_const) return q->cval;
+    q->over = 1;
+    return 0;
+}
+
+static int ss_reserve(SymStream *q, uint32_t need)
+{
+    if (need <= q->cap) return 1;
+    uint32_t cap = q->cap ? q->cap : 1024;
+    while (cap < need) cap *= 2;
+    int32_t *nv = realloc(q->v, (size_t)cap * sizeof(int32_t));
+    if (!nv) return 0;
+    q->v = nv;
+    q->cap = cap;
+    return 1;
+}
+
+/* plain symbols until the section's bits are exhausted (trailing pad bits may yield a few extra
+   symbols that nobody consumes) */
+static void ss_decode(SymStream *q, const HTab *t, BR *b)
+{
+    q->pos = q->n = 0;
+    q->over = 0;
+    q->is_const = !t->tab[0].walk && t->tab[0].len == 0;
+    q->cval = q->is_const ? t->tab[0].val : 0;
+    if (q->is_const || !b->base) return;
+    const int64_t end_bits = (int64_t)(b->end - b->base) * 8;
+    uint32_t n = 0;
+    while (br_pos(b) < end_bits)
+    {
+        if (n + 64 > q->cap && !ss_reserve(q, n + 64)) break;
+        const uint32_t stop = q->cap - 8 < n + 4096 ? q->cap - 8 : n + 4096;
+        int32_t *v = q->v;
+        /* inner loop without capacity checks */
+        while (n < stop && br_pos(b) < end_bits) v[n++] = ht_get(t, b);
+    }
+    q->n = n;
+}
+
+/* Two sections decoded in lock step: each section's decode is one serial dependency chain
+   (window -> table entry -> length -> window); running two chains in the same loop roughly
+   doubles the symbols per cycle.  sovf0/sovf1 select escape-summed value decoding. */
+static void ss_decode2(SymStream *q0, const HTab *t0, BR *b0, int sovf0,
+                       SymStream *q1, const HTab *t1, BR *b1, int sovf1, int32_t lo, int32_t hi);
+
+/* signed escape-extended values (decodeSOvfSym, h4m:654-664): a value ends at the first symbol
+   strictly inside (lo, hi); a trailing unfinished escape run is dropped */
+static void ss_decode_sovf(SymStream *q, const HTab *t, BR *b, int32_t lo, int32_t hi)
+{
+    q->pos = q->n = 0;
+    q->over = 0;
+    q->is_const = !t->tab[0].walk && t->tab[0].len == 0;
+    q->cval = q->is_const ? t->tab[0].val : 0;
+    if (q->is_const)
+    {   /* a constant escape symbol would never terminate in the reference either */
+        if (q->cval <= lo || q->cval >= hi) q->cval = 0;
+        return;
+    }
+    if (!b->base) return;
+    const int64_t end_bits = (int64_t)(b->end - b->base) * 8;
+    uint32_t n = 0;
+    int32_t sum = 0;
+    while (br_pos(b) < end_bits)
+    {
+        if (n + 64 > q->cap && !ss_reserve(q, n + 64)) break;
+        const uint32_t stop = q->cap - 8 < n + 4096 ? q->cap - 8 : n + 4096;
+        int32_t *v = q->v;
+        while (n < stop && br_pos(b) < end_bits)
+        {
+            const int32_t x = ht_get(t, b);
+            sum += x;
+            if (x > lo && x < hi)
+            {
+                v[n++] = sum;
+                sum = 0;
+            }
+        }
+    }
+    q->n = n;
+}
+
+static void ss_decode2(SymStream *q0, const HTab *t0, BR *b0, int sovf0,
+                       SymStream *q1, const HTab *t1, BR *b1, int sovf1, int32_t lo, int32_t hi)
+{
+    const int c0 = !t0->tab[0].walk && t0->tab[0].len == 0, c1 = !t1->tab[0].walk && t1->tab[0].len == 0;
+    if (!c0 && !c1 && b0->base && b1->base)
+    {
+        q0->pos = q0->n = 0; q0->over = 0; q0->is_const = 0; q0->cval = 0;
+        q1->pos = q1->n = 0; q1->over = 0; q1->is_const = 0; q1->cval = 0;
+        const int64_t e0 = (int64_t)(b0->end - b0->base) * 8, e1 = (int64_t)(b1->end - b1->base) * 8;
+        /* a symbol costs at least one bit: capacity for the worst case of the lock-step part */
+        BR x = *b0, y = *b1;
+        uint32_t n0 = 0, n1 = 0;
+        int32_t s0 = 0, s1 = 0;
+        for (;;)
+        {
+            if ((n0 + 4100 > q0->cap && !ss_reserve(q0, n0 + 8200)) || (n1 + 4100 > q1->cap && !ss_reserve(q1, n1 + 8200))) break;
+            int32_t *v0 = q0->v, *v1 = q1->v;
+            int k = 0;
+            for (; k < 4096 && br_pos(&x) < e0 && br_pos(&y) < e1; ++k)
+            {
+                const int32_t a = ht_get(t0, &x), c = ht_get(t1, &y);
+                if (sovf0)
+                {
+                    s0 += a;
+                    v0[n0] = s0;
+                    const int done = a > lo && a < hi;
+                    n0 += (uint32_t)done;
+                    s0 = done ? 0 : s0;
+                }
+                else
+                    v0[n0++] = a;
+                if (sovf1)
+                {
+                    s1 += c;
+                    v1[n1] = s1;
+                    const int done = c > lo && c < hi;
+                    n1 += (uint32_t)done;
+                    s1 = done ? 0 : s1;
+                }
+                else
+                    v1[n1++] = c;
+            }
+            if (k < 4096) break;
+        }
+        /* the longer section finishes alone (an unfinished escape run carries over in s0/s1) */
+        while (br_pos(&x) < e0)
+        {
+            if (n0 + 8 > q0->cap && !ss_reserve(q0, n0 + 4096)) break;
+            const int32_t a = ht_get(t0, &x);
+            if (sovf0) { s0 += a; if (a > lo && a < hi) { q0->v[n0++] = s0; s0 = 0; } }
+            else q0->v[n0++] = a;
+        }
+        while (br_pos(&y) < e1)
+        {
+            if (n1 + 8 > q1->cap && !ss_reserve(q1, n1 + 4096)) break;
+            const int32_t c = ht_get(t1, &y);
+            if (sovf1) { s1 += c; if (c > lo && c < hi) { q1->v[n1++] = s1; s1 = 0; } }
+            else q1->v[n1++] = c;
+        }
+        q0->n = n0; q1->n = n1;
+        *b0 = x; *b1 = y;
+        return;
+    }
+    if (sovf0) ss_decode_sovf(q0, t0, b0, lo, hi); else ss_decode(q0, t0, b0);
+    if (sovf1) ss_decode_sovf(q1, t1, b1, lo, hi); else ss_decode(q1, t1, b1);
+}
+
 /* ------------------------------------------------------------------ stream state */
 
 enum { T_DC = 0, T_RUN = 1, T_SCALE = 2, T_BNUM = 3, T_MV = 4, T_MCB = 5 };   /* tree sharing, h4m:977-999 */
@@ -219,7 +387,7 @@ struct H4Seq
     uint8_t nest[SYM_NEST_BYTES];        /* packed nibbles of the last I picture's nest */
     HTab tree[6];
     int nbands, ngroups;                 /* record groups: [class][band][length bucket] */
-    uint32_t *grp_count, *grp_base, *grp_next, *grp_chunk;
+    uint32_t *grp_count, *grp_base, *grp_next, *grp_chunk, *grp_ord;
     uint32_t *chunks;                    /* chunk table under construction (2 words per chunk) */
     uint32_t chunks_cap;
     uint32_t *band_first;                /* [SYM_REC_CLASSES][nbands + 1] */
@@ -235,6 +403,7 @@ struct H4Seq
     int dc_shift, unk_shift, rb[2][2];
     int32_t dc_lo, dc_hi;
     BR bn[2], bnr[2], dcv[3], sc[3], rle[3], mvh, mvv, mcbt, mcbp;
+    SymStream q_bn[2], q_bnr[2], q_dcv[3], q_sc[3], q_rle[3];   /* flat-decoded sections (buffers persist) */
     ByteSec fix[3];
     size_t blob_bytes;
     SymHeader hdr;
@@ -242,8 +411,12 @@ struct H4Seq
 
 static inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+static uint32_t g_rec_lut[2][256];
+static void init_rec_lut(void);
+
 H4Seq *h4e_seq_create(int width, int height, int h_samp, int v_samp, int version15)
 {
+    if (!g_rec_lut[0][1]) init_rec_lut();   /* idempotent; identical values from every thread */
     /* 4:2:0 landscape only: the only layout HVQM4 content uses (h4m:872,896; README:23) */
     if (width <= 0 || height <= 0 || (width & 7) || (height & 7) || h_samp != 2 || v_samp != 2 || width < height)
         return NULL;
@@ -283,6 +456,7 @@ H4Seq *h4e_seq_create(int width, int height, int h_samp, int v_samp, int version
     s->grp_base = calloc((size_t)s->ngroups, sizeof(uint32_t));
     s->grp_next = calloc((size_t)s->ngroups, sizeof(uint32_t));
     s->grp_chunk = calloc((size_t)s->ngroups, sizeof(uint32_t));
+    s->grp_ord = calloc((size_t)s->ngroups, sizeof(uint32_t));
     /* upper bound on chunks: one per group plus one per 32 blocks, or one per block in the long bucket */
     s->chunks_cap = (uint32_t)s->ngroups + (uint32_t)(s->bw[0] * s->bh[0] + 2 * s->bw[1] * s->bh[1]);
     s->chunks = calloc((size_t)s->chunks_cap * 2, sizeof(uint32_t));
@@ -298,10 +472,13 @@ void h4e_seq_destroy(H4Seq *s)
         free(s->type[p]);
         free(s->dc[p]);
     }
+    for (int i = 0; i < 2; ++i) { free(s->q_bn[i].v); free(s->q_bnr[i].v); }
+    for (int i = 0; i < 3; ++i) { free(s->q_dcv[i].v); free(s->q_sc[i].v); free(s->q_rle[i].v); }
     free(s->grp_count);
     free(s->grp_base);
     free(s->grp_next);
     free(s->grp_chunk);
+    free(s->grp_ord);
     free(s->chunks);
     free(s->band_first);
     free(s);
@@ -375,9 +552,10 @@ static inline int group_of(const H4Seq *s, int cls, int band, uint32_t len)
    per band (luma 4, chroma 3 for SYM_BAND_MCB_ROWS = 8). */
 static inline void count_record(H4Seq *s, uint32_t t, int is_ipic, int by, int band_shift)
 {
-    int cls = 0;
-    const uint32_t len = sym_record_len(t, is_ipic, &cls);
-    if (!len) return;
+    const uint32_t lut = g_rec_lut[is_ipic][t & 0xFF];
+    if (!lut) return;
+    const int cls = (int)(lut >> 16);
+    const uint32_t len = lut & 0xFFFF;
     const int g = group_of(s, cls, by >> band_shift, len);
     s->grp_count[g]++;
     if (len >= SYM_LEN_BUCKETS) s->grp_base[g] += len;   /* long-bucket word total, see plan_records */
@@ -402,7 +580,7 @@ static void reset_record_counts(H4Seq *s)
 static void plan_records(H4Seq *s, int is_ipic)
 {
     int need_nest = 0;
-    uint32_t word = 0, chunk = 0;
+    uint32_t word = 0, chunk = 0, ord = 0;
     s->n_chunks_nest = 0;
     for (int cls = 0; cls < SYM_REC_CLASSES; ++cls)
     {
@@ -416,6 +594,8 @@ static void plan_records(H4Seq *s, int is_ipic)
                 const uint32_t long_words = s->grp_base[g];
                 s->grp_base[g] = word;
                 s->grp_chunk[g] = chunk;
+                s->grp_ord[g] = ord;
+                ord += n;
                 if (!n) continue;
                 need_nest |= cls == SYM_REC_INTRA;
                 if (lb < SYM_LEN_BUCKETS - 1)
@@ -445,27 +625,138 @@ static void plan_records(H4Seq *s, int is_ipic)
     s->need_nest = is_ipic ? 1 : need_nest;
 }
 
-/* Reserves the record of the block (plane,bx,by) with type byte t; returns its payload (word 1..). */
-static inline uint32_t *place_record(H4Seq *s, uint32_t t, int is_ipic, int p, int bx, int by)
+/*
+ * Record emission is split in two so that the expensive part runs over records sorted by
+ * (class, length) -- uniform loop trip counts, predictable branches -- instead of in bitstream
+ * order, where every block takes a different path:
+ *   schedule_record()  bitstream order: reserves the record's slot in its group, writes the header
+ *                      word and notes WHERE the block's side data starts in the flat-decoded
+ *                      sections (the amounts consumed follow from the type byte alone);
+ *   fill_records()     group order: copies descriptors / scale symbols / pairs / raw bytes.
+ */
+typedef struct
 {
-    int cls = 0;
-    const uint32_t len = sym_record_len(t, is_ipic, &cls);
+    uint32_t at;                       /* record position (words from rec_base) */
+    uint32_t fix_off, sc_off, dcv_off; /* consumption offsets in fixvl[p] (bytes), sc[p], dcv[p] (values) */
+    uint16_t len;
+    uint8_t cls, plane;
+} Work;
+
+typedef struct { uint32_t fix[3], sc[3], dcv[3]; } Cursors;
+
+/* sym_record_len() for all 256 type bytes: [is_ipic][type] = len | cls << 16 (0 = no record) */
+static void init_rec_lut(void)
+{
+    for (int ip = 0; ip < 2; ++ip)
+        for (int t = 0; t < 256; ++t)
+        {
+            int cls = 0;
+            const uint32_t len = sym_record_len((uint32_t)t, ip, &cls);
+            g_rec_lut[ip][t] = len ? (len | (uint32_t)cls << 16) : 0;
+        }
+}
+
+static __thread Work *tl_work;         /* per host thread, grows to the largest picture seen */
+static __thread uint32_t tl_work_cap;
+
+static Work *work_scratch(uint32_t n)
+{
+    if (n > tl_work_cap)
+    {
+        free(tl_work);
+        tl_work_cap = n + n / 4 + 256;
+        tl_work = malloc((size_t)tl_work_cap * sizeof(Work));
+        if (!tl_work) tl_work_cap = 0;
+    }
+    return tl_work;
+}
+
+static inline void schedule_record(H4Seq *s, Work *work, Cursors *c, uint32_t t, int is_ipic, int p, int bx, int by)
+{
+    const uint32_t lut = g_rec_lut[is_ipic][t & 0xFF];
+    const int cls = (int)(lut >> 16);
+    const uint32_t len = lut & 0xFFFF;
     const int band = by >> (p ? SYM_BAND_SHIFT_CHROMA : SYM_BAND_SHIFT_LUMA);
     const int g = group_of(s, cls, band, len);
+    const uint32_t idx = s->grp_next[g]++;
     uint32_t at;
     if (len < SYM_LEN_BUCKETS)
-        at = s->grp_base[g] + s->grp_next[g]++ * len;
+        at = s->grp_base[g] + idx * len;
     else
     {
-        const uint32_t c = s->grp_chunk[g]++;
+        const uint32_t ch = s->grp_chunk[g]++;
         at = s->grp_base[g];
         s->grp_base[g] += len;
-        s->chunks[2 * c] = at;
-        s->chunks[2 * c + 1] = 1u | ((len - 1) & 0xFF) << 8 | (uint32_t)cls << 16;
+        s->chunks[2 * ch] = at;
+        s->chunks[2 * ch + 1] = 1u | ((len - 1) & 0xFF) << 8 | (uint32_t)cls << 16;
     }
-    uint32_t *rec = s->rec_base + at;
-    rec[0] = sym_record_header(t, p, bx, by);
-    return rec + 1;
+    s->rec_base[at] = sym_record_header(t, p, bx, by);
+    Work *w = &work[s->grp_ord[g] + idx];
+    w->at = at;
+    w->fix_off = c->fix[p];
+    w->sc_off = c->sc[p];
+    w->dcv_off = c->dcv[p];
+    w->len = (uint16_t)len;
+    w->cls = (uint8_t)cls;
+    w->plane = (uint8_t)p;
+    /* what the block consumes: raw 16 bytes | n x (2 descriptor bytes + 1 scale symbol) [+ 2 pair values] */
+    const uint32_t nb = cls == SYM_REC_RAW ? 0 : len - 1 - (cls == SYM_REC_INTER);
+    c->fix[p] += cls == SYM_REC_RAW ? 16 : 2 * nb;
+    c->sc[p] += nb;
+    c->dcv[p] += cls == SYM_REC_INTER ? 2 : 0;
+}
+
+static inline int32_t ss_at(SymStream *q, uint32_t i)
+{
+    if (i < q->n) return q->v[i];
+    if (q->is_const) return q->cval;
+    q->over = 1;
+    return 0;
+}
+
+static void fill_records(H4Seq *s, const Work *work, uint32_t n)
+{
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const Work w = work[i];
+        uint32_t *rec = s->rec_base + w.at + 1;
+        const int p = w.plane;
+        const ByteSec *fx = &s->fix[p];
+        if (w.cls == SYM_REC_RAW)
+        {   /* OrgBlock, h4m:543-549 */
+            if (fx->base && w.fix_off + 16 <= fx->size) memcpy(rec, fx->base + w.fix_off, 16);
+            else
+            {
+                memset(rec, 0x80, 16);
+                s->err |= SYM_ERR_TRUNCATED;
+            }
+            continue;
+        }
+        /* n x (descriptor, scale symbol): read16(fixvl) + decodeHuff(bufTree0), h4m:691,726 / 738,767 */
+        const uint32_t nb = (uint32_t)w.len - 1 - (w.cls == SYM_REC_INTER);
+        const int fix_ok = fx->base && w.fix_off + 2 * nb <= fx->size;
+        if (!fix_ok && nb) s->err |= SYM_ERR_TRUNCATED;
+        const uint8_t *f = fix_ok ? fx->base + w.fix_off : NULL;
+        SymStream *sc = &s->q_sc[p];
+        for (uint32_t k = 0; k < nb; ++k)
+        {
+            const uint32_t desc = f ? (uint32_t)f[2 * k] << 8 | f[2 * k + 1] : 0u;
+            const uint32_t sym = (uint32_t)ss_at(sc, w.sc_off + k);
+            rec[k] = desc | ((sym >> 2) & 0xFF) << 16;
+        }
+        if (w.cls == SYM_REC_INTER)
+        {   /* the two decodeSOvfSym reads of PrediAotBlock, h4m:1405-1406, pre-shifted by dc_shift */
+            int32_t a = ss_at(&s->q_dcv[p], w.dcv_off) >> s->dc_shift;
+            int32_t g = ss_at(&s->q_dcv[p], w.dcv_off + 1) >> s->dc_shift;
+            if (a < -32768 || a > 32767 || g < -32768 || g > 32767)
+            {
+                s->err |= SYM_ERR_PAIR_RANGE;
+                a = a < -32768 ? -32768 : a > 32767 ? 32767 : a;
+                g = g < -32768 ? -32768 : g > 32767 ? 32767 : g;
+            }
+            rec[nb] = ((uint32_t)a & 0xFFFF) | (uint32_t)g << 16;
+        }
+    }
 }
 
 static void plan_blob(H4Seq *s)
@@ -524,11 +815,10 @@ static void plan_blob(H4Seq *s)
 /* Ipic_BasisNumDec, h4m:1073-1130 */
 static void ipic_types(H4Seq *s)
 {
-    const HTab *tn = &s->tree[T_BNUM], *tr = &s->tree[T_RUN];
     uint32_t run = 0;
     /* readers are copied to locals in every hot loop: the byte stores into the maps may alias
        anything, which would otherwise force the reader state back to memory after every symbol */
-    BR bn = s->bn[0], bnr = s->bnr[0];
+    SymStream bn = s->q_bn[0], bnr = s->q_bnr[0];
     for (int by = 0; by < s->bh[0]; ++by)
     {
         uint8_t *row = s->type[0] + cell_at(s, 0, 0, by);
@@ -540,16 +830,16 @@ static void ipic_types(H4Seq *s)
                 --run;
                 continue;
             }
-            int32_t n = ht_get(tn, &bn);
-            if ((int16_t)n == 0) run = (uint32_t)ht_get(tr, &bnr);
+            int32_t n = ss_get(&bn);
+            if ((int16_t)n == 0) run = (uint32_t)ss_get(&bnr);
             else count_record(s, (uint8_t)n, 1, by, SYM_BAND_SHIFT_LUMA);
             row[bx] = (uint8_t)n;
         }
     }
-    s->bn[0] = bn;
-    s->bnr[0] = bnr;
-    bn = s->bn[1];
-    bnr = s->bnr[1];
+    s->q_bn[0] = bn;
+    s->q_bnr[0] = bnr;
+    bn = s->q_bn[1];
+    bnr = s->q_bnr[1];
     run = 0;
     for (int by = 0; by < s->bh[1]; ++by)
     {
@@ -562,27 +852,25 @@ static void ipic_types(H4Seq *s)
                 --run;
                 continue;
             }
-            int32_t n = ht_get(tn, &bn);
-            if ((int16_t)n == 0) run = (uint32_t)ht_get(tr, &bnr);
+            int32_t n = ss_get(&bn);
+            if ((int16_t)n == 0) run = (uint32_t)ss_get(&bnr);
             ru[bx] = n & 0xF;
             rv[bx] = (n >> 4) & 0xF;
             count_record(s, n & 0xF, 1, by, SYM_BAND_SHIFT_CHROMA);
             count_record(s, (n >> 4) & 0xF, 1, by, SYM_BAND_SHIFT_CHROMA);
         }
     }
-    s->bn[1] = bn;
-    s->bnr[1] = bnr;
+    s->q_bn[1] = bn;
+    s->q_bnr[1] = bnr;
 }
 
 /* IpicDcvDec + getDeltaDC, h4m:1043-1058, 1132-1164 */
 static void ipic_dcs(H4Seq *s)
 {
-    const HTab *td = &s->tree[T_DC], *tr = &s->tree[T_RUN];
     for (int p = 0; p < 3; ++p)
     {
         uint32_t run = 0;
-        BR dcv = s->dcv[p], rle = s->rle[p];
-        const int32_t lo = s->dc_lo, hi = s->dc_hi;
+        SymStream dcv = s->q_dcv[p], rle = s->q_rle[p];
         for (int by = 0; by < s->bh[p]; ++by)
         {
             uint8_t *cur = s->dc[p] + cell_at(s, p, 0, by);
@@ -593,16 +881,16 @@ static void ipic_dcs(H4Seq *s)
                 if (run) --run;
                 else
                 {
-                    uint32_t delta = (uint32_t)ht_get_sovf(td, &dcv, lo, hi);
-                    if (delta == 0) run = (uint32_t)ht_get(tr, &rle);
+                    uint32_t delta = (uint32_t)ss_get(&dcv);
+                    if (delta == 0) run = (uint32_t)ss_get(&rle);
                     v = (uint8_t)(v + delta);
                 }
                 cur[bx] = v;
                 v = (uint8_t)((v + up[bx + 1] + 1) >> 1);
             }
         }
-        s->dcv[p] = dcv;
-        s->rle[p] = rle;
+        s->q_dcv[p] = dcv;
+        s->q_rle[p] = rle;
     }
 }
 
@@ -630,97 +918,6 @@ static void make_nest(H4Seq *s, int nx, int ny)
             s->nest[i * SYM_NEST_ROW_BYTES + j] = (uint8_t)(full[i][2 * j] | full[i][2 * j + 1] << 4);
 }
 
-/* ------------------------------------------------------------------ side-word emitters */
-
-/* readers used while emitting records, kept in a local struct by the callers (see ipic_types) */
-typedef struct
-{
-    BR sc[3], dcv[3];
-    ByteSec fix[3];
-} EmitCtx;
-
-static inline void emit_ctx_load(EmitCtx *c, const H4Seq *s)
-{
-    for (int p = 0; p < 3; ++p)
-    {
-        c->sc[p] = s->sc[p];
-        c->dcv[p] = s->dcv[p];
-        c->fix[p] = s->fix[p];
-    }
-}
-
-static inline void emit_ctx_store(const EmitCtx *c, H4Seq *s)
-{
-    for (int p = 0; p < 3; ++p)
-    {
-        s->sc[p] = c->sc[p];
-        s->dcv[p] = c->dcv[p];
-        s->fix[p] = c->fix[p];
-    }
-}
-
-static inline int fix_has(H4Seq *s, EmitCtx *c, int p, uint32_t n)
-{
-    if (c->fix[p].base && c->fix[p].pos + n <= c->fix[p].size) return 1;
-    s->err |= SYM_ERR_TRUNCATED;
-    return 0;
-}
-
-/* n x (descriptor, scale symbol): read16(fixvl) + decodeHuff(bufTree0), h4m:691,726 / 738,767 */
-static inline void emit_bases(H4Seq *s, EmitCtx *c, int p, uint32_t n, uint32_t *dst)
-{
-    const HTab *ts = &s->tree[T_SCALE];
-    for (uint32_t k = 0; k < n; ++k)
-    {
-        uint32_t desc = 0;
-        if (fix_has(s, c, p, 2))
-        {
-            const uint8_t *f = c->fix[p].base + c->fix[p].pos;
-            desc = (uint32_t)f[0] << 8 | f[1];
-            c->fix[p].pos += 2;
-        }
-        uint32_t sym = (uint32_t)ht_get(ts, &c->sc[p]);
-        dst[k] = desc | ((sym >> 2) & 0xFF) << 16;
-    }
-}
-
-/* OrgBlock, h4m:543-549 */
-static inline void emit_raw(H4Seq *s, EmitCtx *c, int p, uint32_t *dst)
-{
-    if (fix_has(s, c, p, 16))
-    {
-        memcpy(dst, c->fix[p].base + c->fix[p].pos, 16);
-        c->fix[p].pos += 16;
-    }
-    else
-        memset(dst, 0x80, 16);
-}
-
-/* the two decodeSOvfSym reads of PrediAotBlock, h4m:1405-1406, pre-shifted by dc_shift */
-static inline void emit_pair(H4Seq *s, EmitCtx *c, int p, uint32_t *dst)
-{
-    const HTab *td = &s->tree[T_DC];
-    int32_t a = ht_get_sovf(td, &c->dcv[p], s->dc_lo, s->dc_hi) >> s->dc_shift;
-    int32_t f = ht_get_sovf(td, &c->dcv[p], s->dc_lo, s->dc_hi) >> s->dc_shift;
-    if (a < -32768 || a > 32767 || f < -32768 || f > 32767)
-    {
-        s->err |= SYM_ERR_PAIR_RANGE;
-        a = a < -32768 ? -32768 : a > 32767 ? 32767 : a;
-        f = f < -32768 ? -32768 : f > 32767 ? 32767 : f;
-    }
-    *dst = ((uint32_t)a & 0xFFFF) | (uint32_t)f << 16;
-}
-
-/* t = type byte of an intra block (full byte in I pictures, tag | nibble in P/B) */
-static inline void emit_intra_block(H4Seq *s, EmitCtx *c, int p, uint32_t t, int is_ipic, int bx, int by)
-{
-    const uint32_t nib = is_ipic ? t : (t & 0xF);
-    if (nib == 0 || nib == 8) return;
-    uint32_t *dst = place_record(s, t, is_ipic, p, bx, by);
-    if (nib == 6) emit_raw(s, c, p, dst);
-    else emit_bases(s, c, p, nib, dst);
-}
-
 /* ------------------------------------------------------------------ P/B picture, pass 1 */
 
 typedef struct { uint32_t value, count; } RunLen;
@@ -732,11 +929,11 @@ static const int SUBX[4] = {0, 0, 1, 1}, SUBY[4] = {0, 1, 1, 0};   /* TL, BL, BR
 static void pb_pass1(H4Seq *s)
 {
     static const uint8_t next_type[2][4] = {{1, 2, 0, 0}, {2, 0, 1, 0}};   /* mcbtypetrans, h4m:1591-1594 */
-    const HTab *tm = &s->tree[T_MCB], *td = &s->tree[T_DC], *tn = &s->tree[T_BNUM], *tr = &s->tree[T_RUN];
+    const HTab *tm = &s->tree[T_MCB];
     RunLen proc = {0, 0}, type = {0, 0};
-    BR mcbp = s->mcbp, mcbt = s->mcbt, bn0 = s->bn[0], bn1 = s->bn[1], bnr0 = s->bnr[0], bnr1 = s->bnr[1];
-    BR dcv0 = s->dcv[0], dcv1 = s->dcv[1], dcv2 = s->dcv[2];
-    const int32_t dlo = s->dc_lo, dhi = s->dc_hi;
+    BR mcbp = s->mcbp, mcbt = s->mcbt;
+    SymStream bn0 = s->q_bn[0], bn1 = s->q_bn[1], bnr0 = s->q_bnr[0], bnr1 = s->q_bnr[1];
+    SymStream dcv0 = s->q_dcv[0], dcv1 = s->q_dcv[1], dcv2 = s->q_dcv[2];
     if (mcbp.base)
     {
         proc.value = br_bit(&mcbp);
@@ -779,12 +976,12 @@ static void pb_pass1(H4Seq *s)
             {
                 for (int k = 0; k < 4; ++k)
                 {
-                    acc[0] += (uint32_t)ht_get_sovf(td, &dcv0, dlo, dhi);
+                    acc[0] += (uint32_t)ss_get(&dcv0);
                     dc0[SUBY[k] * st0 + lx + SUBX[k]] = (uint8_t)acc[0];
                 }
-                acc[1] += (uint32_t)ht_get_sovf(td, &dcv1, dlo, dhi);
+                acc[1] += (uint32_t)ss_get(&dcv1);
                 dc1[mx] = (uint8_t)acc[1];
-                acc[2] += (uint32_t)ht_get_sovf(td, &dcv2, dlo, dhi);
+                acc[2] += (uint32_t)ss_get(&dcv2);
                 dc2[mx] = (uint8_t)acc[2];
             }
             else
@@ -814,7 +1011,7 @@ static void pb_pass1(H4Seq *s)
                     --run_y;
                     continue;
                 }
-                int32_t n = (int16_t)ht_get(tn, &bn0);
+                int32_t n = (int16_t)ss_get(&bn0);
                 if (n)
                 {
                     if (n & ~0xF)
@@ -828,7 +1025,7 @@ static void pb_pass1(H4Seq *s)
                 else
                 {
                     *c = tag;
-                    run_y = (uint32_t)ht_get(tr, &bnr0);
+                    run_y = (uint32_t)ss_get(&bnr0);
                 }
             }
             if (run_c)
@@ -838,7 +1035,7 @@ static void pb_pass1(H4Seq *s)
             }
             else
             {
-                int32_t n = (int16_t)ht_get(tn, &bn1);
+                int32_t n = (int16_t)ss_get(&bn1);
                 if (n)
                 {
                     ty1[mx] = (uint8_t)(tag | (n & 0xF));
@@ -849,14 +1046,14 @@ static void pb_pass1(H4Seq *s)
                 else
                 {
                     ty1[mx] = ty2[mx] = tag;
-                    run_c = (uint32_t)ht_get(tr, &bnr1);
+                    run_c = (uint32_t)ss_get(&bnr1);
                 }
             }
         }
     }
     s->mcbp = mcbp; s->mcbt = mcbt;
-    s->bn[0] = bn0; s->bn[1] = bn1; s->bnr[0] = bnr0; s->bnr[1] = bnr1;
-    s->dcv[0] = dcv0; s->dcv[1] = dcv1; s->dcv[2] = dcv2;
+    s->q_bn[0] = bn0; s->q_bn[1] = bn1; s->q_bnr[0] = bnr0; s->q_bnr[1] = bnr1;
+    s->q_dcv[0] = dcv0; s->q_dcv[1] = dcv1; s->q_dcv[2] = dcv2;
 }
 
 /* getMVector, h4m:1846-1860 */
@@ -879,6 +1076,14 @@ static inline void read_mv(H4Seq *s, BR *b, int32_t *mv, int rbits)
  */
 static int mcb_refs_in_surface(const H4Seq *s, int32_t rx, int32_t ry, int needs_window)
 {
+    /* fast accept: the whole 9x9 luma patch (and the 70x38 window) strictly inside the luma plane
+       implies every chroma access is inside its plane too (positions and sizes halve) */
+    {
+        const int32_t ix = rx >> 1, iy = ry >> 1;
+        if (!needs_window ? (ix >= 0 && iy >= 0 && ix + 9 <= s->width && iy + 9 <= s->height)
+                          : (ix >= 32 && iy >= 16 && ix + 38 <= s->width && iy + 22 <= s->height))
+            return 1;
+    }
     const int64_t total = (int64_t)s->width * s->height * 3 / 2;
     int64_t plane_base = 0;
     int hx = rx & 1, hy = ry & 1;
@@ -903,14 +1108,12 @@ static int mcb_refs_in_surface(const H4Seq *s, int32_t rx, int32_t ry, int needs
 }
 
 /* BpicPlaneDec pass 2, h4m:1922-1967, symbol part only */
-static void pb_pass2(H4Seq *s, int16_t *mv_out)
+static void pb_pass2(H4Seq *s, int16_t *mv_out, Work *work, Cursors *cur)
 {
     int32_t mvx = 0, mvy = 0;
     int cur_ref = -1;
     const int st0 = s->stride[0];
     s->n_inter_mcb = 0;
-    EmitCtx ctx;
-    emit_ctx_load(&ctx, s);
     BR mvh = s->mvh, mvv = s->mvv;
     for (int my = 0; my < s->mbh; ++my)
     {
@@ -925,10 +1128,14 @@ static void pb_pass2(H4Seq *s, int16_t *mv_out)
             if (mt == 0)
             {   /* MCBlockDecDCNest, h4m:1789-1827 */
                 mvp[0] = mvp[1] = 0;
-                for (int k = 0; k < 4; ++k)
-                    emit_intra_block(s, &ctx, 0, ty0[SUBY[k] * st0 + lx + SUBX[k]], 0, lx + SUBX[k], my * 2 + SUBY[k]);
-                emit_intra_block(s, &ctx, 1, ty1[mx], 0, mx, my);
-                emit_intra_block(s, &ctx, 2, ty2[mx], 0, mx, my);
+                for (int k = 0; k < 6; ++k)
+                {
+                    const int p = k < 4 ? 0 : k - 3;
+                    const int bx = k < 4 ? lx + SUBX[k] : mx, by = k < 4 ? my * 2 + SUBY[k] : my;
+                    const uint32_t t = k < 4 ? ty0[SUBY[k] * st0 + lx + SUBX[k]] : k == 4 ? ty1[mx] : ty2[mx];
+                    const uint32_t nib = t & 0xF;
+                    if (nib != 0 && nib != 8) schedule_record(s, work, cur, t, 0, p, bx, by);
+                }
                 continue;
             }
             const int ref = mt - 1;
@@ -951,14 +1158,8 @@ static void pb_pass2(H4Seq *s, int16_t *mv_out)
                     const uint32_t t = k < 4 ? ty0[SUBY[k] * st0 + lx + SUBX[k]] : k == 4 ? ty1[mx] : ty2[mx];
                     const uint32_t nib = t & 0xF;
                     if (!nib) continue;
-                    uint32_t *dst = place_record(s, t, 0, p, bx, by);
-                    if (nib == 6) emit_raw(s, &ctx, p, dst);
-                    else
-                    {
-                        emit_bases(s, &ctx, p, nib - 1, dst);
-                        emit_pair(s, &ctx, p, dst + nib - 1);
-                        if (nib > 1) needs_window = 1;
-                    }
+                    schedule_record(s, work, cur, t, 0, p, bx, by);
+                    if (nib > 1 && nib != 6) needs_window = 1;
                 }
             }
             if (rx < -32000 || rx > 32000 || ry < -32000 || ry > 32000 || !mcb_refs_in_surface(s, rx, ry, needs_window))
@@ -973,7 +1174,6 @@ static void pb_pass2(H4Seq *s, int16_t *mv_out)
             }
         }
     }
-    emit_ctx_store(&ctx, s);
     s->mvh = mvh;
     s->mvv = mvv;
 }
@@ -1059,6 +1259,22 @@ size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_t pic_le
     s->dc_hi = 0x7F * (1 << s->dc_shift);   /* h4m:2001-2002, 2052-2053 */
     s->dc_lo = -0x80 * (1 << s->dc_shift);
     PROF_ADD(0);
+    {
+        const HTab *tb = &s->tree[T_BNUM], *tr = &s->tree[T_RUN], *td = &s->tree[T_DC], *ts = &s->tree[T_SCALE];
+        const int32_t lo = s->dc_lo, hi = s->dc_hi;
+        /* paired by typical size so that the lock-step part covers most of both sections */
+        ss_decode2(&s->q_dcv[0], td, &s->dcv[0], 1, &s->q_bn[0], tb, &s->bn[0], 0, lo, hi);
+        ss_decode2(&s->q_sc[0], ts, &s->sc[0], 0, &s->q_bnr[0], tr, &s->bnr[0], 0, lo, hi);
+        ss_decode2(&s->q_dcv[1], td, &s->dcv[1], 1, &s->q_dcv[2], td, &s->dcv[2], 1, lo, hi);
+        ss_decode2(&s->q_sc[1], ts, &s->sc[1], 0, &s->q_sc[2], ts, &s->sc[2], 0, lo, hi);
+        ss_decode2(&s->q_bn[1], tb, &s->bn[1], 0, &s->q_bnr[1], tr, &s->bnr[1], 0, lo, hi);
+        if (is_i)
+        {
+            ss_decode2(&s->q_rle[0], tr, &s->rle[0], 0, &s->q_rle[1], tr, &s->rle[1], 0, lo, hi);
+            ss_decode(&s->q_rle[2], tr, &s->rle[2]);
+        }
+    }
+    PROF_ADD(5);
 
     reset_record_counts(s);
     if (is_i)
@@ -1083,36 +1299,43 @@ uint32_t h4e_parse_finish(H4Seq *s, uint8_t *blob)
     if (s->blob_bytes == 0) return s->err;
     PROF_T0();
     s->rec_base = (uint32_t *)(blob + h->off_rec);
+    Work *work = work_scratch(s->n_records);
+    if (!work && s->n_records)
+    {
+        s->err |= SYM_ERR_OVERFLOW;
+        s->errors_total |= s->err;
+        return s->err;
+    }
+    Cursors cur;
+    for (int p = 0; p < 3; ++p)
+    {
+        cur.fix[p] = s->fix[p].pos;
+        cur.sc[p] = s->q_sc[p].pos;
+        cur.dcv[p] = s->q_dcv[p].pos;   /* P/B: the pass-1 DC deltas come first in dc_values[p] */
+    }
     if (is_i)
     {   /* IpicPlaneDec order: plane by plane, raster (h4m:2011-2015, 1487-1518) */
-        EmitCtx ctx;
-        emit_ctx_load(&ctx, s);
         for (int p = 0; p < 3; ++p)
             for (int by = 0; by < s->bh[p]; ++by)
             {
                 const uint8_t *ty = s->type[p] + cell_at(s, p, 0, by);
                 for (int bx = 0; bx < s->bw[p]; ++bx)
-                    if (ty[bx] != 0 && ty[bx] != 8) emit_intra_block(s, &ctx, p, ty[bx], 1, bx, by);
+                    if (ty[bx] != 0 && ty[bx] != 8) schedule_record(s, work, &cur, ty[bx], 1, p, bx, by);
             }
-        emit_ctx_store(&ctx, s);
     }
     else
-        pb_pass2(s, (int16_t *)(blob + h->off_mv));
-
+        pb_pass2(s, (int16_t *)(blob + h->off_mv), work, &cur);
     PROF_ADD(3);
-    /* every reader must have stayed inside its section */
+    fill_records(s, work, s->n_records);
+
+    PROF_ADD(6);
+    /* every consumer must have stayed inside its section */
     {
-        BR *all[] = {&s->bn[0], &s->bnr[0], &s->bn[1], &s->bnr[1], &s->dcv[0], &s->dcv[1], &s->dcv[2],
-                     &s->sc[0], &s->sc[1], &s->sc[2]};
-        for (size_t i = 0; i < sizeof all / sizeof *all; ++i)
-            if (br_overrun(all[i])) s->err |= SYM_ERR_TRUNCATED;
-        if (is_i)
-        {
-            for (int p = 0; p < 3; ++p)
-                if (br_overrun(&s->rle[p])) s->err |= SYM_ERR_TRUNCATED;
-        }
-        else if (br_overrun(&s->mvh) || br_overrun(&s->mvv) || br_overrun(&s->mcbt) || br_overrun(&s->mcbp))
-            s->err |= SYM_ERR_TRUNCATED;
+        int over = 0;
+        for (int i = 0; i < 2; ++i) over |= s->q_bn[i].over | s->q_bnr[i].over;
+        for (int p = 0; p < 3; ++p) over |= s->q_dcv[p].over | s->q_sc[p].over | (is_i ? s->q_rle[p].over : 0);
+        if (!is_i) over |= br_overrun(&s->mvh) | br_overrun(&s->mvv) | br_overrun(&s->mcbt) | br_overrun(&s->mcbp);
+        if (over) s->err |= SYM_ERR_TRUNCATED;
     }
     memcpy(blob + h->off_chunks, s->chunks, (size_t)s->n_chunks * 8);
     memcpy(blob + h->off_bands, s->band_first, (size_t)SYM_REC_CLASSES * (s->nbands + 1) * 4);
