@@ -271,7 +271,7 @@ class Batch:
     def stats(self) -> dict:
         out = (c_uint64 * 8)()
         lib().HVQM4BatchStats(self._h, out)
-        keys = ("pictures", "launches", "symbol_bytes", "algorithmic_bytes", "host_ns", "inter_mcbs", "total_mcbs", "reserved")
+        keys = ("pictures", "launches", "symbol_bytes", "algorithmic_bytes", "host_ns", "inter_mcbs", "total_mcbs", "band_launches")
         return dict(zip(keys, list(out)))
 
 

@@ -536,6 +536,7 @@ H4_API float HVQM4BatchReplay(HVQM4Batch *b, int repeats)
 H4_API void HVQM4BatchStats(HVQM4Batch *b, uint64_t out[8])
 {
     for (int i = 0; i < 8; ++i) out[i] = b ? b->stats[i] : 0;
+    out[7] = (uint64_t)hvqm4_recon_band_launches();   /* process-wide */
 }
 
 H4_API void *HVQM4HostAlloc(size_t bytes)

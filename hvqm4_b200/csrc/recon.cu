@@ -298,7 +298,8 @@ int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, cudaStream_t st
     return (int)cudaGetLastError();
 }
 
-int g_band_mode = 0;   /* set by hvqm4_recon_set_mode: 0 auto, >0 force band kernel, <0 force map+record kernels */
+int g_band_mode = 0;
+long long g_band_launches = 0;   /* steps issued as one fused band kernel (diagnostics) */   /* set by hvqm4_recon_set_mode: 0 auto, >0 force band kernel, <0 force map+record kernels */
 
 static int launch_map_cfg(int cfg, const ReconJob *d_jobs, int n_jobs, int units, cudaStream_t stream)
 {
@@ -334,6 +335,7 @@ static int launch_record_cfg(int cfg, const ReconJob *d_jobs, int n_jobs, uint32
  * in L2; by default the sub-batch is the whole step (see below).
  */
 extern "C" void hvqm4_recon_set_mode(int band_mode) { g_band_mode = band_mode; }
+extern "C" long long hvqm4_recon_band_launches(void) { return g_band_launches; }
 
 extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const uint32_t *h_rec_prefix,
                                   cudaStream_t stream, int *launches)
@@ -360,6 +362,7 @@ extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w,
         default: rc = launch_band<4>(d_jobs, n_jobs, n_bands, stream); break;
         }
         if (rc == 0 && launches) ++*launches;
+        if (rc == 0) ++g_band_launches;
         return rc;
     }
     /* measured on B200 (1024 x 640x480 pictures): the whole step as ONE sub-batch is fastest -- grid

@@ -169,7 +169,7 @@ float HVQM4BatchReplay(HVQM4Batch *b, int repeats);
 /* Counters since creation: out[0] pictures, out[1] kernel launches, out[2] symbol bytes
    uploaded, out[3] algorithmic bytes (frame bytes written + reference bytes predicted from
    + symbol bytes), out[4] host-stage nanoseconds summed over threads, out[5] inter-coded
-   macroblocks, out[6] total macroblocks, out[7] reserved. */
+   macroblocks, out[6] total macroblocks, out[7] launches of the fused band kernel (process-wide). */
 void HVQM4BatchStats(HVQM4Batch *b, uint64_t out[8]);
 
 /* Number of reconstruction kernel launches issued by this process so far (all batches and
