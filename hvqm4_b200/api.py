@@ -69,6 +69,7 @@ SIGNATURES = {
     "HVQM4BatchCreate": (c_void_p, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "HVQM4BatchDestroy": (None, [c_void_p]),
     "HVQM4BatchDecode": (c_int, [c_void_p, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_void_p), POINTER(c_uint32)]),
+    "HVQM4BatchSetEntropyMode": (c_int, [c_void_p, c_int]),
     "HVQM4BatchSync": (c_int, [c_void_p]),
     "HVQM4BatchReadFrame": (c_int, [c_void_p, c_int, c_void_p]),
     "HVQM4BatchReadFrameAsync": (c_int, [c_void_p, c_int, c_void_p]),
@@ -193,10 +194,15 @@ class Player:
 class Batch:
     """n_streams independent streams of one geometry on one GPU (HVQM4Batch*)."""
 
-    def __init__(self, n_streams: int, width: int, height: int, version: int = 15, device: int = -1, host_threads: int = 0):
+    def __init__(self, n_streams: int, width: int, height: int, version: int = 15, device: int = -1, host_threads: int = 0,
+                 gpu_entropy: bool = False):
         self._h = lib().HVQM4BatchCreate(device, n_streams, width, height, version, host_threads)
         if not self._h:
             raise HVQM4Error(ERR_NO_DEVICE, "HVQM4BatchCreate failed (no CUDA device, or unsupported geometry)")
+        if gpu_entropy:
+            rc = lib().HVQM4BatchSetEntropyMode(self._h, 1)
+            if rc:
+                raise HVQM4Error(rc, "HVQM4BatchSetEntropyMode")
         self.n_streams = n_streams
         self.frame_bytes = width * height * 3 // 2
         self._keep = None
@@ -284,7 +290,7 @@ def kernel_launches() -> int:
     return lib().HVQM4KernelLaunches()
 
 
-def decode_streams(files, device: int = -1, host_threads: int = 0):
+def decode_streams(files, device: int = -1, host_threads: int = 0, gpu_entropy: bool = False):
     """Decodes several .h4m images of identical geometry/GOP structure in lock step through
     the batch runtime.  Yields, per step, a list of (frame_type, disp_id, yuv bytes), one per stream."""
     parsed = [parse_file(f) for f in files]
@@ -292,7 +298,7 @@ def decode_streams(files, device: int = -1, host_threads: int = 0):
     n = len(files)
     bufs = [ctypes.create_string_buffer(f, len(f) + 8) for f in files]
     bases = [ctypes.addressof(b) for b in bufs]
-    batch = Batch(n, info0.width, info0.height, info0.version, device, host_threads)
+    batch = Batch(n, info0.width, info0.height, info0.version, device, host_threads, gpu_entropy=gpu_entropy)
     try:
         steps = len(parsed[0][1])
         for k in range(steps):

@@ -32,6 +32,7 @@
 
 #include "../../include/hvqm4.h"
 #include "entropy.h"
+#include "entropy_dev.h"
 #include "recon.h"
 
 #define H4_API extern "C" __attribute__((visibility("default")))
@@ -207,6 +208,15 @@ struct HVQM4Batch
     std::vector<uint32_t> rec_prefix;
     std::vector<uint8_t> seen;
 
+    /* GPU entropy stage (HVQM4BatchSetEntropyMode): per-stream parser state, blob arena, counters */
+    bool gpu_entropy = false;
+    uint8_t *d_estate = nullptr;
+    size_t eslot = 0;
+    uint8_t *d_blobs = nullptr;
+    size_t blobs_cap = 0;
+    unsigned long long *d_blob_used = nullptr;
+    uint32_t *d_eerrors = nullptr;
+
     uint8_t *surface(int stream, int idx) const { return d_surfaces + ((size_t)stream * 3 + idx) * surf_stride; }
 };
 
@@ -304,12 +314,139 @@ H4_API void HVQM4BatchDestroy(HVQM4Batch *b)
         if (a.consumed) cudaEventDestroy(a.consumed);
     }
     if (b->d_surfaces) cudaFree(b->d_surfaces);
+    if (b->d_estate) cudaFree(b->d_estate);
+    if (b->d_blobs) cudaFree(b->d_blobs);
+    if (b->d_blob_used) cudaFree(b->d_blob_used);
+    if (b->d_eerrors) cudaFree(b->d_eerrors);
     if (b->s_copy) cudaStreamDestroy(b->s_copy);
     if (b->s_comp) cudaStreamDestroy(b->s_comp);
     if (b->s_d2h) cudaStreamDestroy(b->s_d2h);
     for (cudaEvent_t e : {b->ev_h2d, b->ev_kernel, b->ev_d2h, b->ev_t0, b->ev_t1})
         if (e) cudaEventDestroy(e);
     delete b;
+}
+
+/*
+ * Step with the bitstream stage on the GPU: the host only gathers the raw picture bytes into the
+ * pinned arena (parallel memcpy) and fills in the surface pointers; one H2D copy, then the parse
+ * kernel (one warp per picture, entropy_dev.cu) writes the symbol buffers into a device arena and
+ * the fused band kernel reconstructs from them.  Symbol buffers never exist on the host.
+ */
+static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_ids, const int32_t *frame_types,
+                                    const uint8_t *const *frames, const uint32_t *frame_bytes)
+{
+    if (b->recording) return HVQM4_ERR_ARGUMENT;
+    auto t_host0 = std::chrono::steady_clock::now();
+    const size_t pics_bytes = align_up((size_t)n * sizeof(H4DevPicture), 256);
+    const size_t jobs_bytes = align_up((size_t)n * sizeof(ReconJob), 256);
+    size_t total = pics_bytes + jobs_bytes;
+    for (int i = 0; i < n; ++i)
+    {
+        b->offs[i] = total;
+        total += align_up((size_t)frame_bytes[i] + 16, 16);
+    }
+    Arena &a = b->arena[b->cur];
+    if (a.in_flight)
+    {
+        if (!cuda_ok(cudaEventSynchronize(a.consumed), "cudaEventSynchronize")) return HVQM4_ERR_CUDA;
+        a.in_flight = false;
+    }
+    if (!arena_reserve(b, a, total)) return HVQM4_ERR_NOMEM;
+    H4DevPicture *pics = reinterpret_cast<H4DevPicture *>(a.h);
+    ReconJob *jobs = reinterpret_cast<ReconJob *>(a.h + pics_bytes);
+    b->pool->parallel_for(n, [&](int i) {
+        uint8_t *dst = a.h + b->offs[i];
+        memcpy(dst, frames[i], frame_bytes[i]);
+        memset(dst + frame_bytes[i], 0, 16);
+    });
+    for (int i = 0; i < n; ++i)
+    {
+        StreamState &s = b->st[stream_ids[i]];
+        const int t = frame_types[i];
+        pics[i].data = a.d + b->offs[i];
+        pics[i].bytes = frame_bytes[i];
+        pics[i].pic_type = t;
+        pics[i].stream = stream_ids[i];
+        pics[i].pad = 0;
+        if (t != SYM_PIC_B) std::swap(s.past, s.future);
+        jobs[i].blob = nullptr;
+        jobs[i].present = b->surface(stream_ids[i], s.present);
+        jobs[i].past = b->surface(stream_ids[i], s.past);
+        jobs[i].future = b->surface(stream_ids[i], t == SYM_PIC_P ? s.present : s.future);
+        jobs[i].rec_cta_begin = 0;
+        jobs[i].n_chunks = 0;
+        jobs[i].pad[0] = jobs[i].pad[1] = 0;
+        s.last = s.present;
+        if (t != SYM_PIC_B) std::swap(s.present, s.future);
+    }
+    auto t_host1 = std::chrono::steady_clock::now();
+    b->stats[4] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_host1 - t_host0).count();
+
+    if (!cuda_ok(cudaMemcpyAsync(a.d, a.h, total, cudaMemcpyHostToDevice, b->s_copy), "cudaMemcpyAsync(H2D)")) return HVQM4_ERR_CUDA;
+    cudaEventRecord(b->ev_h2d, b->s_copy);
+    cudaStreamWaitEvent(b->s_comp, b->ev_h2d, 0);
+    if (b->d2h_pending)
+    {
+        cudaStreamWaitEvent(b->s_comp, b->ev_d2h, 0);
+        b->d2h_pending = false;
+    }
+    cudaMemsetAsync(b->d_blob_used, 0, sizeof(unsigned long long), b->s_comp);
+    ReconJob *d_jobs = reinterpret_cast<ReconJob *>(a.d + pics_bytes);
+    int rc = hvqm4_dev_entropy_parse(b->d_estate, b->eslot, reinterpret_cast<const H4DevPicture *>(a.d), n, b->d_blobs, b->d_blob_used,
+                                     (unsigned long long)b->blobs_cap, d_jobs, b->d_eerrors, b->s_comp);
+    if (rc == 0)
+    {
+        ++g_launches;
+        b->stats[1] += 1;
+        rc = hvqm4_recon_launch_band(d_jobs, n, b->mcb_h, b->s_comp);
+        if (rc == 0)
+        {
+            ++g_launches;
+            b->stats[1] += 1;
+        }
+    }
+    if (rc != 0)
+    {
+        cuda_ok((cudaError_t)rc, "GPU entropy / recon kernel launch");
+        return HVQM4_ERR_CUDA;
+    }
+    cudaEventRecord(a.consumed, b->s_comp);
+    cudaEventRecord(b->ev_kernel, b->s_comp);
+    a.in_flight = true;
+    b->cur ^= 1;
+    b->stats[0] += n;
+    b->stats[2] += total;
+    return HVQM4_OK;
+}
+
+H4_API int HVQM4BatchSetEntropyMode(HVQM4Batch *b, int gpu)
+{
+    if (!b) return HVQM4_ERR_ARGUMENT;
+    cudaSetDevice(b->device);
+    if (!cuda_ok(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return HVQM4_ERR_CUDA;
+    if (!gpu)
+    {
+        b->gpu_entropy = false;
+        return HVQM4_OK;
+    }
+    if (!b->d_estate)
+    {
+        const uint32_t blocks = (uint32_t)(b->mcb_w * b->mcb_h * 6);
+        const uint32_t sym_cap = blocks * 2 > 32768u ? blocks * 2 : 32768u, work_cap = blocks;
+        b->eslot = hvqm4_dev_entropy_slot_bytes(b->width, b->height, sym_cap, work_cap);
+        if (!b->eslot) return HVQM4_ERR_GEOMETRY;
+        b->blobs_cap = (size_t)b->n_streams * align_up(2 * b->frame_bytes, 256);
+        if (!cuda_ok(cudaMalloc((void **)&b->d_estate, b->eslot * (size_t)b->n_streams), "cudaMalloc(entropy state)") ||
+            !cuda_ok(cudaMalloc((void **)&b->d_blobs, b->blobs_cap), "cudaMalloc(blob arena)") ||
+            !cuda_ok(cudaMalloc((void **)&b->d_blob_used, sizeof(unsigned long long)), "cudaMalloc") ||
+            !cuda_ok(cudaMalloc((void **)&b->d_eerrors, sizeof(uint32_t)), "cudaMalloc") ||
+            !cuda_ok(cudaMemset(b->d_eerrors, 0, sizeof(uint32_t)), "cudaMemset"))
+            return HVQM4_ERR_NOMEM;
+        int rc = hvqm4_dev_entropy_init(b->d_estate, b->eslot, b->n_streams, b->width, b->height, b->version15, sym_cap, work_cap, b->s_comp);
+        if (rc != 0 || !cuda_ok(cudaStreamSynchronize(b->s_comp), "GPU entropy state init")) return HVQM4_ERR_CUDA;
+    }
+    b->gpu_entropy = true;
+    return HVQM4_OK;
 }
 
 H4_API int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, const int32_t *frame_types,
@@ -324,6 +461,7 @@ H4_API int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, con
         if (s < 0 || s >= b->n_streams || b->seen[s] || (t != SYM_PIC_I && t != SYM_PIC_P && t != SYM_PIC_B)) return HVQM4_ERR_ARGUMENT;
         b->seen[s] = 1;
     }
+    if (b->gpu_entropy) return batch_decode_gpu_entropy(b, n, stream_ids, frame_types, frames, frame_bytes);
     auto t_host0 = std::chrono::steady_clock::now();
     /* phase A: headers, trees, maps, work-order offsets -> exact blob sizes */
     b->pool->parallel_for(n, [&](int i) {
@@ -434,6 +572,15 @@ H4_API int HVQM4BatchSync(HVQM4Batch *b)
               cuda_ok(cudaStreamSynchronize(b->s_d2h), "sync d2h");
     for (auto &a : b->arena) a.in_flight = false;
     b->d2h_pending = false;
+    if (ok && b->d_eerrors)
+    {   /* stream errors raised by the GPU entropy stage since the last sync */
+        uint32_t de = 0;
+        if (cuda_ok(cudaMemcpy(&de, b->d_eerrors, sizeof de, cudaMemcpyDeviceToHost), "cudaMemcpy(errors)") && de)
+        {
+            e |= de;
+            cudaMemset(b->d_eerrors, 0, sizeof de);
+        }
+    }
     if (!ok) e |= HVQM4_ERR_CUDA;
     return (int)e;
 }

@@ -15,10 +15,38 @@
  *     into its slot of the work-ordered symbol buffer;
  *   - malformed input raises SYM_ERR_* bits instead of reading out of bounds.
  */
+#if defined(H4E_DEVICE)
+#include <stddef.h>
+#include <stdint.h>
+#include "symbuf.h"
+typedef struct H4Seq H4Seq;     /* the device build defines the entry points as static __device__ functions */
+#else
 #include "entropy.h"
+#endif
 
 #include <stdlib.h>
 #include <string.h>
+
+/*
+ * This file is compiled twice: by gcc as the host serial stage, and -- #include'd by
+ * entropy_dev.cu with H4E_DEVICE defined -- by nvcc as __device__ code, so that the very same
+ * parser can also run on the GPU (one picture per warp; see entropy_dev.cu).  The macros below
+ * are the only difference: function qualifiers, table storage, and where scratch memory comes
+ * from (the device build never allocates: every buffer is carved from a per-stream arena).
+ */
+#if defined(H4E_DEVICE)
+#define H4E_FN static __device__
+#define H4E_INL static __device__ __forceinline__
+#define H4E_TABLE static __device__ const
+#define H4E_API static __device__
+#define H4E_STATIC_ASSERT(c, m) static_assert(c, m)
+#else
+#define H4E_FN static
+#define H4E_INL static inline
+#define H4E_TABLE static const
+#define H4E_API
+#define H4E_STATIC_ASSERT(c, m) _Static_assert(c, m)
+#endif
 
 #ifdef H4E_PROFILE   /* developer aid: cycle counters per phase (tools only, never defined in the product build) */
 #include <x86intrin.h>
@@ -39,12 +67,12 @@ typedef struct
     int n;          /* number of valid bits in buf */
 } BR;
 
-static inline uint32_t rd_be32(const uint8_t *p)
+H4E_INL uint32_t rd_be32(const uint8_t *p)
 {
     return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
 }
 
-static inline void br_open(BR *b, const uint8_t *base, uint32_t size)
+H4E_INL void br_open(BR *b, const uint8_t *base, uint32_t size)
 {
     b->base = b->p = base;
     b->end = base ? base + size : base;
@@ -52,13 +80,21 @@ static inline void br_open(BR *b, const uint8_t *base, uint32_t size)
     b->n = 0;
 }
 
-static inline void br_refill(BR *b)
+H4E_INL void br_refill(BR *b)
 {
     if (b->end - b->p >= 8)
     {
         uint64_t w;
+#if defined(H4E_DEVICE)
+        {   /* byte-wise big-endian gather: the pointer is arbitrarily aligned */
+            const uint8_t *q = b->p;
+            w = (uint64_t)q[0] << 56 | (uint64_t)q[1] << 48 | (uint64_t)q[2] << 40 | (uint64_t)q[3] << 32 |
+                (uint64_t)q[4] << 24 | (uint64_t)q[5] << 16 | (uint64_t)q[6] << 8 | q[7];
+        }
+#else
         memcpy(&w, b->p, 8);
         w = __builtin_bswap64(w);
+#endif
         b->buf |= w >> b->n;
         int adv = (63 - b->n) >> 3;
         b->p += adv;
@@ -76,7 +112,7 @@ static inline void br_refill(BR *b)
     }
 }
 
-static inline uint32_t br_bit(BR *b)
+H4E_INL uint32_t br_bit(BR *b)
 {
     if (b->n < 1) br_refill(b);
     uint32_t v = (uint32_t)(b->buf >> 63);
@@ -85,7 +121,7 @@ static inline uint32_t br_bit(BR *b)
     return v;
 }
 
-static inline uint32_t br_bits(BR *b, int k)   /* 0 <= k <= 16 */
+H4E_INL uint32_t br_bits(BR *b, int k)   /* 0 <= k <= 16 */
 {
     if (k == 0) return 0;
     if (b->n < k) br_refill(b);
@@ -96,8 +132,8 @@ static inline uint32_t br_bits(BR *b, int k)   /* 0 <= k <= 16 */
 }
 
 /* bits consumed so far, and whether the reader went past the section */
-static inline int64_t br_pos(const BR *b) { return (int64_t)(b->p - b->base) * 8 - b->n; }
-static inline int br_overrun(const BR *b) { return br_pos(b) > (int64_t)(b->end - b->base) * 8; }
+H4E_INL int64_t br_pos(const BR *b) { return (int64_t)(b->p - b->base) * 8 - b->n; }
+H4E_INL int br_overrun(const BR *b) { return br_pos(b) > (int64_t)(b->end - b->base) * 8; }
 
 /* ------------------------------------------------------------------ Huffman (h4m:385-394, 607-651) */
 
@@ -115,59 +151,95 @@ typedef struct
     HEnt tab[1 << HT_BITS];
 } HTab;
 
-static int ht_parse(HTab *t, BR *b, int is_signed, int scale, int depth)
+/* _readTree, h4m:607-630, without recursion (the same code runs as a GPU thread): `stk` holds
+   the internal nodes whose subtrees are still open; bit 15 marks "0-side done". */
+H4E_FN int ht_parse(HTab *t, BR *b, int is_signed, int scale)
 {
-    if (br_bit(b) == 0)
+    uint16_t stk[260];
+    int sp = 0;
+    for (;;)
     {
-        uint32_t byte = br_bits(b, 8);
-        int32_t v = (is_signed && byte > 0x7F) ? (int32_t)byte - 256 : (int32_t)byte;
-        t->leaf[byte] = (int32_t)(int16_t)((uint32_t)v << scale);   /* int16_t symbol <<= scale, h4m:613-617 */
-        return (int)byte;
+        int id;
+        if (br_bit(b) == 0)
+        {
+            const uint32_t byte = br_bits(b, 8);
+            const int32_t v = (is_signed && byte > 0x7F) ? (int32_t)byte - 256 : (int32_t)byte;
+            t->leaf[byte] = (int32_t)(int16_t)((uint32_t)v << scale);   /* int16_t symbol <<= scale, h4m:613-617 */
+            id = (int)byte;
+        }
+        else
+        {
+            if (t->used >= 256 || sp >= 258 || br_overrun(b))
+            {
+                t->bad = 1;
+                return 0;
+            }
+            stk[sp++] = (uint16_t)t->used++;
+            continue;                                   /* read the 0 side of the new node */
+        }
+        /* a subtree is complete: hang it under the innermost open node, closing nodes as they fill */
+        for (;;)
+        {
+            if (sp == 0) return id;
+            const int node = stk[sp - 1] & 0x7FFF;
+            if (!(stk[sp - 1] & 0x8000))
+            {
+                t->kid[0][node] = (int16_t)id;
+                stk[sp - 1] |= 0x8000;
+                break;                                  /* now read the 1 side */
+            }
+            t->kid[1][node] = (int16_t)id;
+            --sp;
+            id = node + 256;
+        }
     }
-    if (t->used >= 256 || depth > 300 || br_overrun(b))
-    {
-        t->bad = 1;
-        return 0;
-    }
-    int node = t->used++;
-    int a = ht_parse(t, b, is_signed, scale, depth + 1);
-    int c = ht_parse(t, b, is_signed, scale, depth + 1);
-    t->kid[0][node] = (int16_t)a;
-    t->kid[1][node] = (int16_t)c;
-    return node + 256;
 }
 
-static void ht_fill(HTab *t, int node, int depth, uint32_t code)
+/* prefix table: every leaf at depth <= HT_BITS fills its 2^(HT_BITS-depth) entries; deeper
+   subtrees get one "walk from this node" entry */
+H4E_FN void ht_fill(HTab *t)
 {
-    if (node < 256)
+    struct { int16_t node; uint8_t depth; uint32_t code; } stk[2 * HT_BITS + 4];
+    int sp = 0;
+    stk[sp].node = (int16_t)t->root; stk[sp].depth = 0; stk[sp].code = 0; ++sp;
+    while (sp)
     {
-        HEnt e = {(int16_t)t->leaf[node], (uint8_t)depth, 0};
-        uint32_t lo = code << (HT_BITS - depth), hi = (code + 1) << (HT_BITS - depth);
-        for (uint32_t i = lo; i < hi; ++i) t->tab[i] = e;
-        return;
+        --sp;
+        const int node = stk[sp].node, depth = stk[sp].depth;
+        const uint32_t code = stk[sp].code;
+        if (node < 256)
+        {
+            HEnt e;
+            e.val = (int16_t)t->leaf[node]; e.len = (uint8_t)depth; e.walk = 0;
+            const uint32_t lo = code << (HT_BITS - depth), hi = (code + 1) << (HT_BITS - depth);
+            for (uint32_t i = lo; i < hi; ++i) t->tab[i] = e;
+        }
+        else if (depth == HT_BITS)
+        {
+            HEnt e;
+            e.val = (int16_t)node; e.len = HT_BITS; e.walk = 1;
+            t->tab[code] = e;
+        }
+        else
+        {
+            stk[sp].node = t->kid[1][node - 256]; stk[sp].depth = (uint8_t)(depth + 1); stk[sp].code = code << 1 | 1; ++sp;
+            stk[sp].node = t->kid[0][node - 256]; stk[sp].depth = (uint8_t)(depth + 1); stk[sp].code = code << 1; ++sp;
+        }
     }
-    if (depth == HT_BITS)
-    {
-        HEnt e = {(int16_t)node, HT_BITS, 1};
-        t->tab[code] = e;
-        return;
-    }
-    ht_fill(t, t->kid[0][node - 256], depth + 1, code << 1);
-    ht_fill(t, t->kid[1][node - 256], depth + 1, code << 1 | 1);
 }
 
 /* readTree, h4m:632-642: an empty leader section leaves root = 0, i.e. every symbol
    decodes to the stale leaf[0] without consuming bits. */
-static void ht_read(HTab *t, BR *leader, uint32_t leader_size, int is_signed, int scale)
+H4E_FN void ht_read(HTab *t, BR *leader, uint32_t leader_size, int is_signed, int scale)
 {
     t->used = 0;
     t->bad = 0;
-    t->root = leader_size ? ht_parse(t, leader, is_signed, scale, 0) : 0;
+    t->root = leader_size ? ht_parse(t, leader, is_signed, scale) : 0;
     if (t->bad) t->root = 0;
-    ht_fill(t, t->root, 0, 0);
+    ht_fill(t);
 }
 
-static inline int32_t ht_get(const HTab *t, BR *b)
+H4E_INL int32_t ht_get(const HTab *t, BR *b)
 {
     if (b->n < 32) br_refill(b);
     HEnt e = t->tab[b->buf >> (64 - HT_BITS)];
@@ -180,7 +252,7 @@ static inline int32_t ht_get(const HTab *t, BR *b)
 }
 
 /* decodeSOvfSym, h4m:654-664 */
-static inline int32_t ht_get_sovf(const HTab *t, BR *b, int32_t lo, int32_t hi)
+H4E_INL int32_t ht_get_sovf(const HTab *t, BR *b, int32_t lo, int32_t hi)
 {
     int32_t sum = 0, v;
     do
@@ -192,7 +264,7 @@ static inline int32_t ht_get_sovf(const HTab *t, BR *b, int32_t lo, int32_t hi)
 }
 
 /* decodeUOvfSym, h4m:667-677 */
-static inline int32_t ht_get_uovf(const HTab *t, BR *b)
+H4E_INL int32_t ht_get_uovf(const HTab *t, BR *b)
 {
     int32_t sum = 0, v;
     do
@@ -220,7 +292,7 @@ typedef struct
     uint8_t over;        /* consumer ran past the end */
 } SymStream;
 
-static inline int32_t ss_get(SymStream *q)
+H4E_INL int32_t ss_get(SymStream *q)
 {
     if (q->pos < q->n) return q->v[q->pos++];
     if (q->is_const) return q->cval;
@@ -228,21 +300,25 @@ static inline int32_t ss_get(SymStream *q)
     return 0;
 }
 
-static int ss_reserve(SymStream *q, uint32_t need)
+H4E_FN int ss_reserve(SymStream *q, uint32_t need)
 {
     if (need <= q->cap) return 1;
+#if defined(H4E_DEVICE)
+    return 0;                                            /* fixed capacity on the GPU */
+#else
     uint32_t cap = q->cap ? q->cap : 1024;
     while (cap < need) cap *= 2;
-    int32_t *nv = realloc(q->v, (size_t)cap * sizeof(int32_t));
+    int32_t *nv = (int32_t *)realloc(q->v, (size_t)cap * sizeof(int32_t));
     if (!nv) return 0;
     q->v = nv;
     q->cap = cap;
     return 1;
+#endif
 }
 
 /* plain symbols until the section's bits are exhausted (trailing pad bits may yield a few extra
    symbols that nobody consumes) */
-static void ss_decode(SymStream *q, const HTab *t, BR *b)
+H4E_FN void ss_decode(SymStream *q, const HTab *t, BR *b)
 {
     q->pos = q->n = 0;
     q->over = 0;
@@ -265,12 +341,12 @@ static void ss_decode(SymStream *q, const HTab *t, BR *b)
 /* Two sections decoded in lock step: each section's decode is one serial dependency chain
    (window -> table entry -> length -> window); running two chains in the same loop roughly
    doubles the symbols per cycle.  sovf0/sovf1 select escape-summed value decoding. */
-static void ss_decode2(SymStream *q0, const HTab *t0, BR *b0, int sovf0,
+H4E_FN void ss_decode2(SymStream *q0, const HTab *t0, BR *b0, int sovf0,
                        SymStream *q1, const HTab *t1, BR *b1, int sovf1, int32_t lo, int32_t hi);
 
 /* signed escape-extended values (decodeSOvfSym, h4m:654-664): a value ends at the first symbol
    strictly inside (lo, hi); a trailing unfinished escape run is dropped */
-static void ss_decode_sovf(SymStream *q, const HTab *t, BR *b, int32_t lo, int32_t hi)
+H4E_FN void ss_decode_sovf(SymStream *q, const HTab *t, BR *b, int32_t lo, int32_t hi)
 {
     q->pos = q->n = 0;
     q->over = 0;
@@ -304,7 +380,7 @@ static void ss_decode_sovf(SymStream *q, const HTab *t, BR *b, int32_t lo, int32
     q->n = n;
 }
 
-static void ss_decode2(SymStream *q0, const HTab *t0, BR *b0, int sovf0,
+H4E_FN void ss_decode2(SymStream *q0, const HTab *t0, BR *b0, int sovf0,
                        SymStream *q1, const HTab *t1, BR *b1, int sovf1, int32_t lo, int32_t hi)
 {
     const int c0 = !t0->tab[0].walk && t0->tab[0].len == 0, c1 = !t1->tab[0].walk && t1->tab[0].len == 0;
@@ -377,6 +453,15 @@ enum { T_DC = 0, T_RUN = 1, T_SCALE = 2, T_BNUM = 3, T_MV = 4, T_MCB = 5 };   /*
 
 typedef struct { const uint8_t *base; uint32_t size, pos; } ByteSec;   /* fixvl: plain byte stream */
 
+/* one scheduled record (see schedule_record / fill_records below) */
+typedef struct Work
+{
+    uint32_t at;                       /* record position (words from rec_base) */
+    uint32_t fix_off, sc_off, dcv_off; /* consumption offsets in fixvl[p] (bytes), sc[p], dcv[p] (values) */
+    uint16_t len;
+    uint8_t cls, plane;
+} Work;
+
 struct H4Seq
 {
     int width, height, version15;
@@ -407,23 +492,45 @@ struct H4Seq
     ByteSec fix[3];
     size_t blob_bytes;
     SymHeader hdr;
+    struct Work *dev_work;               /* GPU build only: per-stream record schedule scratch */
+    uint32_t dev_work_cap;
 };
 
-static inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+H4E_INL size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-static uint32_t g_rec_lut[2][256];
-static void init_rec_lut(void);
-
-H4Seq *h4e_seq_create(int width, int height, int h_samp, int v_samp, int version15)
+/* record class/length of every possible type byte: [is_ipic][type] = len | cls << 16 (0 = none) */
+#if defined(H4E_DEVICE)
+H4E_INL uint32_t rec_lut(int is_ipic, uint32_t t)
 {
-    if (!g_rec_lut[0][1]) init_rec_lut();   /* idempotent; identical values from every thread */
-    /* 4:2:0 landscape only: the only layout HVQM4 content uses (h4m:872,896; README:23) */
-    if (width <= 0 || height <= 0 || (width & 7) || (height & 7) || h_samp != 2 || v_samp != 2 || width < height)
-        return NULL;
-    if (width > 8192 || height > 8192)
-        return NULL;
-    H4Seq *s = calloc(1, sizeof *s);
-    if (!s) return NULL;
+    int cls = 0;
+    const uint32_t len = sym_record_len(t & 0xFF, is_ipic, &cls);
+    return len ? (len | (uint32_t)cls << 16) : 0u;
+}
+#else
+static uint32_t g_rec_lut[2][256];
+static void init_rec_lut(void)
+{
+    for (int ip = 0; ip < 2; ++ip)
+        for (int t = 0; t < 256; ++t)
+        {
+            int cls = 0;
+            const uint32_t len = sym_record_len((uint32_t)t, ip, &cls);
+            g_rec_lut[ip][t] = len ? (len | (uint32_t)cls << 16) : 0;
+        }
+}
+H4E_INL uint32_t rec_lut(int is_ipic, uint32_t t) { return g_rec_lut[is_ipic][t & 0xFF]; }
+#endif
+
+/* geometry checks shared by both builds; 4:2:0 landscape only: the only layout HVQM4 content uses
+   (h4m:872,896; README:23) */
+H4E_FN int seq_geometry_ok(int width, int height, int h_samp, int v_samp)
+{
+    if (width <= 0 || height <= 0 || (width & 7) || (height & 7) || h_samp != 2 || v_samp != 2 || width < height) return 0;
+    return width <= 8192 && height <= 8192;
+}
+
+H4E_FN void seq_set_dims(H4Seq *s, int width, int height, int version15)
+{
     s->width = width;
     s->height = height;
     s->version15 = version15 ? 1 : 0;
@@ -432,14 +539,61 @@ H4Seq *h4e_seq_create(int width, int height, int h_samp, int v_samp, int version
     s->nseg = (s->mbw + SYM_SEG_MCBS - 1) / SYM_SEG_MCBS;
     for (int p = 0; p < 3; ++p)
     {
-        int sh = p ? 1 : 0;
+        const int sh = p ? 1 : 0;
         s->bw[p] = (width >> sh) / 4;
         s->bh[p] = (height >> sh) / 4;
         s->stride[p] = s->bw[p] + 2;
         s->map_cells[p] = (size_t)s->stride[p] * (s->bh[p] + 2);
-        s->type[p] = malloc(s->map_cells[p]);
-        s->dc[p] = malloc(s->map_cells[p]);
-        /* border cells {0x7F, 0xFF} (h4m:951-955); payload starts zeroed */
+    }
+    s->nbands = (s->mbh + SYM_BAND_MCB_ROWS - 1) / SYM_BAND_MCB_ROWS;
+    s->ngroups = SYM_REC_CLASSES * s->nbands * SYM_LEN_BUCKETS;
+    /* upper bound on chunks: one per group plus one per 32 blocks, or one per block in the long bucket */
+    s->chunks_cap = (uint32_t)s->ngroups + (uint32_t)(s->bw[0] * s->bh[0] + 2 * s->bw[1] * s->bh[1]);
+}
+
+/* Assigns every per-stream array a slice of one allocation (mem == NULL: only measures).
+   sym_cap / work_cap: fixed capacities of the flat symbol streams and of the record schedule
+   (GPU build; the host build grows those on demand and passes 0). */
+H4E_FN size_t seq_carve(H4Seq *s, uint8_t *mem, uint32_t sym_cap, uint32_t work_cap)
+{
+    size_t at = 0;
+#define CARVE(ptr, type, count) do { if (mem) (ptr) = (type *)(mem + at); at = align16(at + (size_t)(count) * sizeof(type)); } while (0)
+    for (int p = 0; p < 3; ++p)
+    {
+        CARVE(s->type[p], uint8_t, s->map_cells[p]);
+        CARVE(s->dc[p], uint8_t, s->map_cells[p]);
+    }
+    CARVE(s->grp_count, uint32_t, s->ngroups);
+    CARVE(s->grp_base, uint32_t, s->ngroups);
+    CARVE(s->grp_next, uint32_t, s->ngroups);
+    CARVE(s->grp_chunk, uint32_t, s->ngroups);
+    CARVE(s->grp_ord, uint32_t, s->ngroups);
+    CARVE(s->chunks, uint32_t, (size_t)s->chunks_cap * 2);
+    CARVE(s->band_first, uint32_t, (size_t)SYM_REC_CLASSES * (s->nbands + 1));
+    if (sym_cap)
+    {
+        SymStream *all[13] = {&s->q_bn[0], &s->q_bn[1], &s->q_bnr[0], &s->q_bnr[1], &s->q_dcv[0], &s->q_dcv[1], &s->q_dcv[2],
+                              &s->q_sc[0], &s->q_sc[1], &s->q_sc[2], &s->q_rle[0], &s->q_rle[1], &s->q_rle[2]};
+        for (int i = 0; i < 13; ++i)
+        {
+            CARVE(all[i]->v, int32_t, sym_cap);
+            if (mem) all[i]->cap = sym_cap;
+        }
+    }
+    if (work_cap)
+    {
+        CARVE(s->dev_work, struct Work, work_cap);
+        if (mem) s->dev_work_cap = work_cap;
+    }
+#undef CARVE
+    return at;
+}
+
+/* border cells {0x7F, 0xFF} (h4m:951-955); everything else starts zeroed */
+H4E_FN void seq_init_maps(H4Seq *s)
+{
+    for (int p = 0; p < 3; ++p)
+    {
         memset(s->type[p], 0, s->map_cells[p]);
         memset(s->dc[p], 0, s->map_cells[p]);
         for (int y = 0; y < s->bh[p] + 2; ++y)
@@ -450,56 +604,51 @@ H4Seq *h4e_seq_create(int width, int height, int h_samp, int v_samp, int version
                     s->dc[p][y * s->stride[p] + x] = 0x7F;
                 }
     }
-    s->nbands = (s->mbh + SYM_BAND_MCB_ROWS - 1) / SYM_BAND_MCB_ROWS;
-    s->ngroups = SYM_REC_CLASSES * s->nbands * SYM_LEN_BUCKETS;
-    s->grp_count = calloc((size_t)s->ngroups, sizeof(uint32_t));
-    s->grp_base = calloc((size_t)s->ngroups, sizeof(uint32_t));
-    s->grp_next = calloc((size_t)s->ngroups, sizeof(uint32_t));
-    s->grp_chunk = calloc((size_t)s->ngroups, sizeof(uint32_t));
-    s->grp_ord = calloc((size_t)s->ngroups, sizeof(uint32_t));
-    /* upper bound on chunks: one per group plus one per 32 blocks, or one per block in the long bucket */
-    s->chunks_cap = (uint32_t)s->ngroups + (uint32_t)(s->bw[0] * s->bh[0] + 2 * s->bw[1] * s->bh[1]);
-    s->chunks = calloc((size_t)s->chunks_cap * 2, sizeof(uint32_t));
-    s->band_first = calloc((size_t)SYM_REC_CLASSES * (s->nbands + 1), sizeof(uint32_t));
+}
+
+#if !defined(H4E_DEVICE)
+H4Seq *h4e_seq_create(int width, int height, int h_samp, int v_samp, int version15)
+{
+    if (!g_rec_lut[0][1]) init_rec_lut();   /* idempotent; identical values from every thread */
+    if (!seq_geometry_ok(width, height, h_samp, v_samp)) return NULL;
+    H4Seq tmp;
+    memset(&tmp, 0, sizeof tmp);
+    seq_set_dims(&tmp, width, height, version15);
+    const size_t bytes = seq_carve(&tmp, NULL, 0, 0);
+    uint8_t *mem = (uint8_t *)calloc(1, align16(sizeof(H4Seq)) + bytes);
+    if (!mem) return NULL;
+    H4Seq *s = (H4Seq *)mem;
+    seq_set_dims(s, width, height, version15);
+    seq_carve(s, mem + align16(sizeof(H4Seq)), 0, 0);
+    seq_init_maps(s);
     return s;
 }
 
 void h4e_seq_destroy(H4Seq *s)
 {
     if (!s) return;
-    for (int p = 0; p < 3; ++p)
-    {
-        free(s->type[p]);
-        free(s->dc[p]);
-    }
     for (int i = 0; i < 2; ++i) { free(s->q_bn[i].v); free(s->q_bnr[i].v); }
     for (int i = 0; i < 3; ++i) { free(s->q_dcv[i].v); free(s->q_sc[i].v); free(s->q_rle[i].v); }
-    free(s->grp_count);
-    free(s->grp_base);
-    free(s->grp_next);
-    free(s->grp_chunk);
-    free(s->grp_ord);
-    free(s->chunks);
-    free(s->band_first);
     free(s);
 }
+#endif
 
-void h4e_seq_set_version(H4Seq *s, int version15) { s->version15 = version15 ? 1 : 0; }
-uint32_t h4e_seq_errors(const H4Seq *s) { return s->errors_total; }
-size_t h4e_frame_bytes(const H4Seq *s) { return (size_t)s->width * s->height * 3 / 2; }
+H4E_API void h4e_seq_set_version(H4Seq *s, int version15) { s->version15 = version15 ? 1 : 0; }
+H4E_API uint32_t h4e_seq_errors(const H4Seq *s) { return s->errors_total; }
+H4E_API size_t h4e_frame_bytes(const H4Seq *s) { return (size_t)s->width * s->height * 3 / 2; }
 
-uint32_t h4e_last_inter_mcbs(const H4Seq *s) { return s->n_inter_mcb; }
-uint32_t h4e_last_chunks(const H4Seq *s) { return s->n_chunks; }
+H4E_API uint32_t h4e_last_inter_mcbs(const H4Seq *s) { return s->n_inter_mcb; }
+H4E_API uint32_t h4e_last_chunks(const H4Seq *s) { return s->n_chunks; }
 
-void h4e_seq_dims(const H4Seq *s, int out[6])
+H4E_API void h4e_seq_dims(const H4Seq *s, int out[6])
 {
     out[0] = s->width; out[1] = s->height; out[2] = s->mbw; out[3] = s->mbh; out[4] = s->nseg; out[5] = s->version15;
 }
 
-static inline size_t cell_at(const H4Seq *s, int p, int bx, int by) { return (size_t)(by + 1) * s->stride[p] + bx + 1; }
+H4E_INL size_t cell_at(const H4Seq *s, int p, int bx, int by) { return (size_t)(by + 1) * s->stride[p] + bx + 1; }
 
 /* setCode, h4m:1061-1071, with bounds */
-static void open_section(H4Seq *s, const uint8_t *data, size_t data_len, uint32_t off, const uint8_t **base, uint32_t *size)
+H4E_FN void open_section(H4Seq *s, const uint8_t *data, size_t data_len, uint32_t off, const uint8_t **base, uint32_t *size)
 {
     *base = NULL;
     *size = 0;
@@ -520,7 +669,7 @@ static void open_section(H4Seq *s, const uint8_t *data, size_t data_len, uint32_
     *size = sz;
 }
 
-static void open_bits(H4Seq *s, BR *b, const uint8_t *data, size_t len, uint32_t off)
+H4E_FN void open_bits(H4Seq *s, BR *b, const uint8_t *data, size_t len, uint32_t off)
 {
     const uint8_t *base;
     uint32_t size;
@@ -528,7 +677,7 @@ static void open_bits(H4Seq *s, BR *b, const uint8_t *data, size_t len, uint32_t
     br_open(b, base, size);
 }
 
-static void open_bytes(H4Seq *s, ByteSec *b, const uint8_t *data, size_t len, uint32_t off)
+H4E_FN void open_bytes(H4Seq *s, ByteSec *b, const uint8_t *data, size_t len, uint32_t off)
 {
     open_section(s, data, len, off, &b->base, &b->size);
     b->pos = 0;
@@ -539,10 +688,10 @@ static void open_bytes(H4Seq *s, ByteSec *b, const uint8_t *data, size_t len, ui
 /* block rows per band, as shifts */
 #define SYM_BAND_SHIFT_CHROMA 3
 #define SYM_BAND_SHIFT_LUMA 4
-_Static_assert((1 << SYM_BAND_SHIFT_CHROMA) == SYM_BAND_MCB_ROWS, "band shift must match SYM_BAND_MCB_ROWS");
+H4E_STATIC_ASSERT((1 << SYM_BAND_SHIFT_CHROMA) == SYM_BAND_MCB_ROWS, "band shift must match SYM_BAND_MCB_ROWS");
 
-static inline int len_bucket(uint32_t len) { return len < SYM_LEN_BUCKETS ? (int)len - 1 : SYM_LEN_BUCKETS - 1; }
-static inline int group_of(const H4Seq *s, int cls, int band, uint32_t len)
+H4E_INL int len_bucket(uint32_t len) { return len < SYM_LEN_BUCKETS ? (int)len - 1 : SYM_LEN_BUCKETS - 1; }
+H4E_INL int group_of(const H4Seq *s, int cls, int band, uint32_t len)
 {
     return (cls * s->nbands + band) * SYM_LEN_BUCKETS + len_bucket(len);
 }
@@ -550,9 +699,9 @@ static inline int group_of(const H4Seq *s, int cls, int band, uint32_t len)
 /* Called wherever a block's final type byte is written (ipic_types, pb_pass1): counts the
    record the block will own in its (class, band, length) group.  band_shift: log2 of block rows
    per band (luma 4, chroma 3 for SYM_BAND_MCB_ROWS = 8). */
-static inline void count_record(H4Seq *s, uint32_t t, int is_ipic, int by, int band_shift)
+H4E_INL void count_record(H4Seq *s, uint32_t t, int is_ipic, int by, int band_shift)
 {
-    const uint32_t lut = g_rec_lut[is_ipic][t & 0xFF];
+    const uint32_t lut = rec_lut(is_ipic, t);
     if (!lut) return;
     const int cls = (int)(lut >> 16);
     const uint32_t len = lut & 0xFFFF;
@@ -562,7 +711,7 @@ static inline void count_record(H4Seq *s, uint32_t t, int is_ipic, int by, int b
     s->n_records++;
 }
 
-static void reset_record_counts(H4Seq *s)
+H4E_FN void reset_record_counts(H4Seq *s)
 {
     memset(s->grp_count, 0, (size_t)s->ngroups * sizeof(uint32_t));
     memset(s->grp_next, 0, (size_t)s->ngroups * sizeof(uint32_t));
@@ -577,7 +726,7 @@ static void reset_record_counts(H4Seq *s)
  * > 16, which no encoder emits) have individual lengths; they are packed in emission order
  * and get one chunk each.
  */
-static void plan_records(H4Seq *s, int is_ipic)
+H4E_FN void plan_records(H4Seq *s, int is_ipic)
 {
     int need_nest = 0;
     uint32_t word = 0, chunk = 0, ord = 0;
@@ -634,46 +783,31 @@ static void plan_records(H4Seq *s, int is_ipic)
  *                      sections (the amounts consumed follow from the type byte alone);
  *   fill_records()     group order: copies descriptors / scale symbols / pairs / raw bytes.
  */
-typedef struct
-{
-    uint32_t at;                       /* record position (words from rec_base) */
-    uint32_t fix_off, sc_off, dcv_off; /* consumption offsets in fixvl[p] (bytes), sc[p], dcv[p] (values) */
-    uint16_t len;
-    uint8_t cls, plane;
-} Work;
-
 typedef struct { uint32_t fix[3], sc[3], dcv[3]; } Cursors;
 
-/* sym_record_len() for all 256 type bytes: [is_ipic][type] = len | cls << 16 (0 = no record) */
-static void init_rec_lut(void)
-{
-    for (int ip = 0; ip < 2; ++ip)
-        for (int t = 0; t < 256; ++t)
-        {
-            int cls = 0;
-            const uint32_t len = sym_record_len((uint32_t)t, ip, &cls);
-            g_rec_lut[ip][t] = len ? (len | (uint32_t)cls << 16) : 0;
-        }
-}
-
+#if defined(H4E_DEVICE)
+H4E_FN Work *work_scratch(H4Seq *s, uint32_t n) { return n <= s->dev_work_cap ? s->dev_work : NULL; }
+#else
 static __thread Work *tl_work;         /* per host thread, grows to the largest picture seen */
 static __thread uint32_t tl_work_cap;
 
-static Work *work_scratch(uint32_t n)
+static Work *work_scratch(H4Seq *s, uint32_t n)
 {
+    (void)s;
     if (n > tl_work_cap)
     {
         free(tl_work);
         tl_work_cap = n + n / 4 + 256;
-        tl_work = malloc((size_t)tl_work_cap * sizeof(Work));
+        tl_work = (Work *)malloc((size_t)tl_work_cap * sizeof(Work));
         if (!tl_work) tl_work_cap = 0;
     }
     return tl_work;
 }
+#endif
 
-static inline void schedule_record(H4Seq *s, Work *work, Cursors *c, uint32_t t, int is_ipic, int p, int bx, int by)
+H4E_INL void schedule_record(H4Seq *s, Work *work, Cursors *c, uint32_t t, int is_ipic, int p, int bx, int by)
 {
-    const uint32_t lut = g_rec_lut[is_ipic][t & 0xFF];
+    const uint32_t lut = rec_lut(is_ipic, t);
     const int cls = (int)(lut >> 16);
     const uint32_t len = lut & 0xFFFF;
     const int band = by >> (p ? SYM_BAND_SHIFT_CHROMA : SYM_BAND_SHIFT_LUMA);
@@ -706,7 +840,7 @@ static inline void schedule_record(H4Seq *s, Work *work, Cursors *c, uint32_t t,
     c->dcv[p] += cls == SYM_REC_INTER ? 2 : 0;
 }
 
-static inline int32_t ss_at(SymStream *q, uint32_t i)
+H4E_INL int32_t ss_at(SymStream *q, uint32_t i)
 {
     if (i < q->n) return q->v[i];
     if (q->is_const) return q->cval;
@@ -714,7 +848,7 @@ static inline int32_t ss_at(SymStream *q, uint32_t i)
     return 0;
 }
 
-static void fill_records(H4Seq *s, const Work *work, uint32_t n)
+H4E_FN void fill_records(H4Seq *s, const Work *work, uint32_t n)
 {
     for (uint32_t i = 0; i < n; ++i)
     {
@@ -759,7 +893,7 @@ static void fill_records(H4Seq *s, const Work *work, uint32_t n)
     }
 }
 
-static void plan_blob(H4Seq *s)
+H4E_FN void plan_blob(H4Seq *s)
 {
     SymHeader *h = &s->hdr;
     memset(h, 0, sizeof *h);
@@ -813,7 +947,7 @@ static void plan_blob(H4Seq *s)
 /* ------------------------------------------------------------------ I picture, symbol part */
 
 /* Ipic_BasisNumDec, h4m:1073-1130 */
-static void ipic_types(H4Seq *s)
+H4E_FN void ipic_types(H4Seq *s)
 {
     uint32_t run = 0;
     /* readers are copied to locals in every hot loop: the byte stores into the maps may alias
@@ -865,7 +999,7 @@ static void ipic_types(H4Seq *s)
 }
 
 /* IpicDcvDec + getDeltaDC, h4m:1043-1058, 1132-1164 */
-static void ipic_dcs(H4Seq *s)
+H4E_FN void ipic_dcs(H4Seq *s)
 {
     for (int p = 0; p < 3; ++p)
     {
@@ -895,7 +1029,7 @@ static void ipic_dcs(H4Seq *s)
 }
 
 /* MakeNest, h4m:1166-1239 (including the mirror / zero-fill path), packed to nibbles */
-static void make_nest(H4Seq *s, int nx, int ny)
+H4E_FN void make_nest(H4Seq *s, int nx, int ny)
 {
     uint8_t full[SYM_NEST_H][SYM_NEST_W];
     int bw = s->bw[0], bh = s->bh[0];
@@ -922,13 +1056,13 @@ static void make_nest(H4Seq *s, int nx, int ny)
 
 typedef struct { uint32_t value, count; } RunLen;
 
-static const int SUBX[4] = {0, 0, 1, 1}, SUBY[4] = {0, 1, 1, 0};   /* TL, BL, BR, TR: mcb_offset, h4m:862-865 */
+H4E_TABLE uint8_t next_type[2][4] = {{1, 2, 0, 0}, {2, 0, 1, 0}};   /* mcbtypetrans, h4m:1591-1594 */
+H4E_TABLE int SUBX[4] = {0, 0, 1, 1}, SUBY[4] = {0, 1, 1, 0};   /* TL, BL, BR, TR: mcb_offset, h4m:862-865 */
 
 /* spread_PB_descMap, h4m:1742-1776, with decode_PB_dc (1649), decode_PB_cc (1670),
    getMCBtype (1596), getMCBproc (1613), initMCBtype/proc (1551-1569) */
-static void pb_pass1(H4Seq *s)
+H4E_FN void pb_pass1(H4Seq *s)
 {
-    static const uint8_t next_type[2][4] = {{1, 2, 0, 0}, {2, 0, 1, 0}};   /* mcbtypetrans, h4m:1591-1594 */
     const HTab *tm = &s->tree[T_MCB];
     RunLen proc = {0, 0}, type = {0, 0};
     BR mcbp = s->mcbp, mcbt = s->mcbt;
@@ -1057,7 +1191,7 @@ static void pb_pass1(H4Seq *s)
 }
 
 /* getMVector, h4m:1846-1860 */
-static inline void read_mv(H4Seq *s, BR *b, int32_t *mv, int rbits)
+H4E_INL void read_mv(H4Seq *s, BR *b, int32_t *mv, int rbits)
 {
     if (rbits > 16) rbits = 16;
     int32_t lim = 1 << (rbits + 5);
@@ -1074,7 +1208,7 @@ static inline void read_mv(H4Seq *s, BR *b, int32_t *mv, int rbits)
  * (h4m:1344, 1866, 1897), so "inside" means inside the contiguous Y|U|V buffer, not inside
  * the plane; recon.cu addresses the same way, which keeps even row-wrapping vectors exact.
  */
-static int mcb_refs_in_surface(const H4Seq *s, int32_t rx, int32_t ry, int needs_window)
+H4E_FN int mcb_refs_in_surface(const H4Seq *s, int32_t rx, int32_t ry, int needs_window)
 {
     /* fast accept: the whole 9x9 luma patch (and the 70x38 window) strictly inside the luma plane
        implies every chroma access is inside its plane too (positions and sizes halve) */
@@ -1108,7 +1242,7 @@ static int mcb_refs_in_surface(const H4Seq *s, int32_t rx, int32_t ry, int needs
 }
 
 /* BpicPlaneDec pass 2, h4m:1922-1967, symbol part only */
-static void pb_pass2(H4Seq *s, int16_t *mv_out, Work *work, Cursors *cur)
+H4E_FN void pb_pass2(H4Seq *s, int16_t *mv_out, Work *work, Cursors *cur)
 {
     int32_t mvx = 0, mvy = 0;
     int cur_ref = -1;
@@ -1180,7 +1314,7 @@ static void pb_pass2(H4Seq *s, int16_t *mv_out, Work *work, Cursors *cur)
 
 /* ------------------------------------------------------------------ entry points */
 
-size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_t pic_len)
+H4E_API size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_t pic_len)
 {
     s->pic_type = pic_type;
     s->err = 0;
@@ -1292,14 +1426,14 @@ size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_t pic_le
     return s->blob_bytes;
 }
 
-uint32_t h4e_parse_finish(H4Seq *s, uint8_t *blob)
+H4E_API uint32_t h4e_parse_finish(H4Seq *s, uint8_t *blob)
 {
     const SymHeader *h = &s->hdr;
     const int is_i = s->pic_type == SYM_PIC_I;
     if (s->blob_bytes == 0) return s->err;
     PROF_T0();
     s->rec_base = (uint32_t *)(blob + h->off_rec);
-    Work *work = work_scratch(s->n_records);
+    Work *work = work_scratch(s, s->n_records);
     if (!work && s->n_records)
     {
         s->err |= SYM_ERR_OVERFLOW;

@@ -1,0 +1,117 @@
+/*
+ * entropy_dev.cu -- the serial bitstream stage, run on the GPU.
+ *
+ * The host stage (entropy.c) is the end-to-end bottleneck: one B200 reconstructs a dense picture
+ * in ~1 us, one host core parses it in ~0.6 ms.  A picture's parse is serial, but a batch has a
+ * thousand independent pictures, so the same C code is compiled here as __device__ functions
+ * (entropy.c is #include'd with H4E_DEVICE; see the macro block at its top) and run with ONE
+ * PICTURE PER WARP: lane 0 executes the parser exactly as a host thread would, against
+ * per-stream state that lives in device memory, and writes the symbol buffer straight into a
+ * device arena that the reconstruction kernel reads next.  Nothing but the raw picture bytes
+ * crosses PCIe on the way in.  A single lane is slow (~10x a host core) but there are thousands
+ * of warp slots; what matters is that the whole step's pictures parse concurrently.
+ *
+ * Because it is the same source, parity with the host stage (and through it with the reference)
+ * is structural; tests/test_gpu_parity.py still checks the decoded frames in this mode.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define H4E_DEVICE 1
+#include "entropy.c"
+
+#include "entropy_dev.h"
+#include "recon.h"
+
+namespace {
+
+__device__ __forceinline__ H4Seq *slot_seq(uint8_t *arena, size_t slot_bytes, int stream)
+{
+    return reinterpret_cast<H4Seq *>(arena + (size_t)stream * slot_bytes);
+}
+
+__global__ void dev_measure_kernel(int width, int height, uint32_t sym_cap, uint32_t work_cap, unsigned long long *out)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    H4Seq tmp;
+    memset(&tmp, 0, sizeof tmp);
+    if (!seq_geometry_ok(width, height, 2, 2))
+    {
+        *out = 0;
+        return;
+    }
+    seq_set_dims(&tmp, width, height, 1);
+    *out = (unsigned long long)(align16(sizeof(H4Seq)) + seq_carve(&tmp, nullptr, sym_cap, work_cap));
+}
+
+__global__ void dev_init_kernel(uint8_t *arena, size_t slot_bytes, int n_streams, int width, int height, int version15,
+                                uint32_t sym_cap, uint32_t work_cap)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_streams) return;
+    H4Seq *s = slot_seq(arena, slot_bytes, i);
+    memset(s, 0, sizeof(H4Seq));
+    seq_set_dims(s, width, height, version15);
+    seq_carve(s, reinterpret_cast<uint8_t *>(s) + align16(sizeof(H4Seq)), sym_cap, work_cap);
+    seq_init_maps(s);
+}
+
+/* one warp per picture; lane 0 runs the parser */
+__global__ void __launch_bounds__(32)
+dev_parse_kernel(uint8_t *arena, size_t slot_bytes, const H4DevPicture *pics, int n_pics, uint8_t *blob_arena,
+                 unsigned long long *blob_used, unsigned long long blob_cap, ReconJob *jobs, uint32_t *errors)
+{
+    const int i = blockIdx.x;
+    if (i >= n_pics || threadIdx.x != 0) return;
+    const H4DevPicture pic = pics[i];
+    H4Seq *s = slot_seq(arena, slot_bytes, pic.stream);
+    const size_t bytes = h4e_parse_begin(s, pic.pic_type, pic.data, pic.bytes);
+    uint32_t err = s->err;
+    jobs[i].blob = nullptr;
+    jobs[i].n_chunks = 0;
+    if (bytes)
+    {
+        const unsigned long long need = (bytes + 127) & ~127ull;
+        const unsigned long long at = atomicAdd(blob_used, need);
+        if (at + need <= blob_cap)
+        {
+            err |= h4e_parse_finish(s, blob_arena + at);
+            jobs[i].blob = blob_arena + at;
+            jobs[i].n_chunks = s->n_chunks;
+        }
+        else
+            err |= SYM_ERR_OVERFLOW;
+    }
+    else
+        err |= SYM_ERR_GEOMETRY;
+    if (err) atomicOr(errors, err);
+}
+
+}  // namespace
+
+extern "C" size_t hvqm4_dev_entropy_slot_bytes(int width, int height, uint32_t sym_cap, uint32_t work_cap)
+{
+    unsigned long long *d = nullptr, h = 0;
+    if (cudaMalloc((void **)&d, sizeof h) != cudaSuccess) return 0;
+    dev_measure_kernel<<<1, 1>>>(width, height, sym_cap, work_cap, d);
+    const cudaError_t e = cudaMemcpy(&h, d, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return 0;
+    return (size_t)((h + 255) & ~255ull);
+}
+
+extern "C" int hvqm4_dev_entropy_init(uint8_t *arena, size_t slot_bytes, int n_streams, int width, int height, int version15,
+                                      uint32_t sym_cap, uint32_t work_cap, cudaStream_t stream)
+{
+    dev_init_kernel<<<(n_streams + 63) / 64, 64, 0, stream>>>(arena, slot_bytes, n_streams, width, height, version15, sym_cap, work_cap);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int hvqm4_dev_entropy_parse(uint8_t *arena, size_t slot_bytes, const H4DevPicture *d_pics, int n_pics, uint8_t *blob_arena,
+                                       unsigned long long *d_blob_used, unsigned long long blob_cap, ReconJob *d_jobs,
+                                       uint32_t *d_errors, cudaStream_t stream)
+{
+    if (n_pics <= 0) return 0;
+    dev_parse_kernel<<<n_pics, 32, 0, stream>>>(arena, slot_bytes, d_pics, n_pics, blob_arena, d_blob_used, blob_cap, d_jobs, d_errors);
+    return (int)cudaGetLastError();
+}

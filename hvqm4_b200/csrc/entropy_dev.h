@@ -1,0 +1,36 @@
+/* entropy_dev.h -- launch interface of the GPU-resident entropy stage (internal). */
+#ifndef HVQM4_ENTROPY_DEV_H
+#define HVQM4_ENTROPY_DEV_H
+#include <stddef.h>
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+/* one picture to parse on the GPU: raw bytes (device pointer, starting at the picture header =
+   4 bytes into the frame record, like the SDK calls), its length, frame type, owning stream */
+typedef struct H4DevPicture
+{
+    const uint8_t *data;
+    uint32_t bytes;
+    int32_t pic_type;
+    int32_t stream;
+    int32_t pad;
+} H4DevPicture;
+
+struct ReconJob;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* bytes of device memory one stream's parser state needs (0 on unsupported geometry) */
+size_t hvqm4_dev_entropy_slot_bytes(int width, int height, uint32_t sym_cap, uint32_t work_cap);
+int hvqm4_dev_entropy_init(uint8_t *arena, size_t slot_bytes, int n_streams, int width, int height, int version15,
+                           uint32_t sym_cap, uint32_t work_cap, cudaStream_t stream);
+/* parses n_pics pictures (one warp each), bump-allocates their symbol buffers in blob_arena and
+   fills jobs[i].blob / jobs[i].n_chunks (the surface pointers of jobs[] are filled by the host) */
+int hvqm4_dev_entropy_parse(uint8_t *arena, size_t slot_bytes, const H4DevPicture *d_pics, int n_pics, uint8_t *blob_arena,
+                            unsigned long long *d_blob_used, unsigned long long blob_cap, struct ReconJob *d_jobs,
+                            uint32_t *d_errors, cudaStream_t stream);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -43,6 +43,12 @@ namespace {
  * ------------------------------------------------------------------------------------------ */
 __device__ __forceinline__ void load_view(ReconView &vw, const ReconJob &J)
 {
+    if (!J.blob)
+    {   /* the GPU entropy stage rejected this picture: nothing to reconstruct */
+        vw.blob = nullptr;
+        vw.mcb_h = 0; vw.mcb_w = 0; vw.nseg = 1; vw.n_bands = 0; vw.n_chunks = 0; vw.n_chunks_nest = 0; vw.has_nest = 0;
+        return;
+    }
     SymHeader h;
     const uint4 *src = reinterpret_cast<const uint4 *>(J.blob);
     uint4 *dst = reinterpret_cast<uint4 *>(&h);
@@ -237,6 +243,7 @@ recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands)
     build_div_tables<kBandWarps * 32>();
     __syncthreads();
     const ReconView &v = vw;
+    if (!v.blob) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     /* map phase: the band's segments */
@@ -335,6 +342,16 @@ static int launch_record_cfg(int cfg, const ReconJob *d_jobs, int n_jobs, uint32
  * in L2; by default the sub-batch is the whole step (see below).
  */
 extern "C" void hvqm4_recon_set_mode(int band_mode) { g_band_mode = band_mode; }
+
+/* the fused band kernel only (no host-side record prefix needed): used behind the GPU entropy stage */
+extern "C" int hvqm4_recon_launch_band(const ReconJob *d_jobs, int n_jobs, int mcb_h, cudaStream_t stream)
+{
+    if (n_jobs <= 0) return 0;
+    const int n_bands = (mcb_h + SYM_BAND_MCB_ROWS - 1) / SYM_BAND_MCB_ROWS;
+    const int rc = launch_band<4>(d_jobs, n_jobs, n_bands, stream);
+    if (rc == 0) ++g_band_launches;
+    return rc;
+}
 extern "C" long long hvqm4_recon_band_launches(void) { return g_band_launches; }
 
 extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const uint32_t *h_rec_prefix,

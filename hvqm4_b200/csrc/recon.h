@@ -36,7 +36,9 @@ static inline uint32_t hvqm4_rec_ctas(uint32_t n_chunks)
 /* 0 = choose by batch size (default), > 0 = always the fused band kernel, < 0 = always the
    map + record kernel pair */
 void hvqm4_recon_set_mode(int band_mode);
-long long hvqm4_recon_band_launches(void);   /* steps issued as one fused band kernel so far */
+long long hvqm4_recon_band_launches(void);
+/* one launch of the fused band kernel; jobs whose blob is NULL are skipped */
+int hvqm4_recon_launch_band(const ReconJob *d_jobs, int n_jobs, int mcb_h, cudaStream_t stream);   /* steps issued as one fused band kernel so far */
 int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const uint32_t *h_rec_prefix,
                        cudaStream_t stream, int *launches);
 #ifdef __cplusplus

@@ -139,6 +139,15 @@ void HVQM4BatchDestroy(HVQM4Batch *b);
 int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, const int32_t *frame_types,
                      const uint8_t *const *frames, const uint32_t *frame_bytes);
 
+/*
+ * Where the serial bitstream stage of this batch runs: 0 = host threads (default), 1 = on the GPU
+ * (one warp per picture runs the same parser, compiled as device code; only raw picture bytes are
+ * uploaded, symbol buffers never exist on the host).  Both give identical pictures.  The switch
+ * must be made before the first HVQM4BatchDecode of the batch: the two stages keep separate
+ * per-stream state.  Recording (HVQM4BatchRecord) needs the host stage.
+ */
+int HVQM4BatchSetEntropyMode(HVQM4Batch *b, int gpu);
+
 /* Waits for all enqueued work; returns accumulated error bits and clears them. */
 int HVQM4BatchSync(HVQM4Batch *b);
 

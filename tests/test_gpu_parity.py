@@ -183,3 +183,24 @@ def test_corrupt_pictures_do_not_fault_the_gpu(native_lib):
     a = [yuv for _, _, yuv in native_lib.Player(data)]
     b = [yuv for _, _, yuv in native_lib.Player(data)]
     assert a == b
+
+
+def test_gpu_entropy_stage_matches_golden(native_lib, golden):
+    """The bitstream stage compiled as device code (one warp per picture, entropy_dev.cu): the
+    frames must equal the reference MD5s exactly like with the host stage."""
+    names = ["cfg5_stream0", "cfg5_stream1", "cfg5_stream511", "cfg5_stream1023"]
+    files = [synth.generate(**golden[n]["args"]) for n in names]
+    step = 0
+    for frames in native_lib.decode_streams(files, gpu_entropy=True):
+        for n, (t, d, yuv) in zip(names, frames):
+            assert md5(yuv) == golden[n]["md5"][step], (n, step)
+        step += 1
+    assert step == 16
+
+
+@pytest.mark.parametrize("name", ["cfg4_320x240_v13_IPB", "realistic_640x480_v15_IPB", "ragged_328x248_v15_IPB", "wide_1024x576_v13_IPB"])
+def test_gpu_entropy_stage_other_geometries(native_lib, golden, name):
+    case = golden[name]
+    data = synth.generate(**case["args"])
+    got = [md5(frames[0][2]) for frames in native_lib.decode_streams([data, data], gpu_entropy=True)]
+    assert got == case["md5"]
