@@ -70,6 +70,7 @@ SIGNATURES = {
     "HVQM4BatchDestroy": (None, [c_void_p]),
     "HVQM4BatchDecode": (c_int, [c_void_p, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_void_p), POINTER(c_uint32)]),
     "HVQM4BatchSetEntropyMode": (c_int, [c_void_p, c_int]),
+    "HVQM4DevEntropyProfile": (None, [POINTER(c_uint64)]),
     "HVQM4BatchSync": (c_int, [c_void_p]),
     "HVQM4BatchReadFrame": (c_int, [c_void_p, c_int, c_void_p]),
     "HVQM4BatchReadFrameAsync": (c_int, [c_void_p, c_int, c_void_p]),

@@ -382,7 +382,15 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
     auto t_host1 = std::chrono::steady_clock::now();
     b->stats[4] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_host1 - t_host0).count();
 
+    /* the parser runs behind the upload on the copy stream, so that step n+1 parses while step n
+       reconstructs and reads back; only the reconstruction waits for the previous read-back.
+       Blobs are double-buffered like the arenas. */
     if (!cuda_ok(cudaMemcpyAsync(a.d, a.h, total, cudaMemcpyHostToDevice, b->s_copy), "cudaMemcpyAsync(H2D)")) return HVQM4_ERR_CUDA;
+    cudaMemsetAsync(b->d_blob_used, 0, sizeof(unsigned long long), b->s_copy);
+    ReconJob *d_jobs = reinterpret_cast<ReconJob *>(a.d + pics_bytes);
+    int rc = hvqm4_dev_entropy_parse(b->d_estate, b->eslot, reinterpret_cast<const H4DevPicture *>(a.d), n,
+                                     b->d_blobs + (size_t)b->cur * b->blobs_cap, b->d_blob_used, (unsigned long long)b->blobs_cap,
+                                     d_jobs, b->d_eerrors, b->s_copy);
     cudaEventRecord(b->ev_h2d, b->s_copy);
     cudaStreamWaitEvent(b->s_comp, b->ev_h2d, 0);
     if (b->d2h_pending)
@@ -390,10 +398,6 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
         cudaStreamWaitEvent(b->s_comp, b->ev_d2h, 0);
         b->d2h_pending = false;
     }
-    cudaMemsetAsync(b->d_blob_used, 0, sizeof(unsigned long long), b->s_comp);
-    ReconJob *d_jobs = reinterpret_cast<ReconJob *>(a.d + pics_bytes);
-    int rc = hvqm4_dev_entropy_parse(b->d_estate, b->eslot, reinterpret_cast<const H4DevPicture *>(a.d), n, b->d_blobs, b->d_blob_used,
-                                     (unsigned long long)b->blobs_cap, d_jobs, b->d_eerrors, b->s_comp);
     if (rc == 0)
     {
         ++g_launches;
@@ -419,6 +423,13 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
     return HVQM4_OK;
 }
 
+H4_API void HVQM4DevEntropyProfile(uint64_t out[8])
+{
+    unsigned long long tmp[8];
+    hvqm4_dev_entropy_profile(tmp);
+    for (int i = 0; i < 8; ++i) out[i] = tmp[i];
+}
+
 H4_API int HVQM4BatchSetEntropyMode(HVQM4Batch *b, int gpu)
 {
     if (!b) return HVQM4_ERR_ARGUMENT;
@@ -437,7 +448,7 @@ H4_API int HVQM4BatchSetEntropyMode(HVQM4Batch *b, int gpu)
         if (!b->eslot) return HVQM4_ERR_GEOMETRY;
         b->blobs_cap = (size_t)b->n_streams * align_up(2 * b->frame_bytes, 256);
         if (!cuda_ok(cudaMalloc((void **)&b->d_estate, b->eslot * (size_t)b->n_streams), "cudaMalloc(entropy state)") ||
-            !cuda_ok(cudaMalloc((void **)&b->d_blobs, b->blobs_cap), "cudaMalloc(blob arena)") ||
+            !cuda_ok(cudaMalloc((void **)&b->d_blobs, 2 * b->blobs_cap), "cudaMalloc(blob arena)") ||
             !cuda_ok(cudaMalloc((void **)&b->d_blob_used, sizeof(unsigned long long)), "cudaMalloc") ||
             !cuda_ok(cudaMalloc((void **)&b->d_eerrors, sizeof(uint32_t)), "cudaMalloc") ||
             !cuda_ok(cudaMemset(b->d_eerrors, 0, sizeof(uint32_t)), "cudaMemset"))

@@ -35,12 +35,22 @@ typedef struct H4Seq H4Seq;     /* the device build defines the entry points as 
  * from (the device build never allocates: every buffer is carved from a per-stream arena).
  */
 #if defined(H4E_DEVICE)
+/* on the GPU the entry points are WARP-COLLECTIVE: all 32 lanes call them; serial parts run on
+   lane 0, the data-parallel parts (flat section decode, record fill, copies) on all lanes */
+#define H4E_LANE ((int)(threadIdx.x & 31))
+#define H4E_LANES 32
+#define H4E_SYNC() __syncwarp()
+#define H4E_ERR(s, bits) atomicOr(&(s)->err, (uint32_t)(bits))
 #define H4E_FN static __device__
 #define H4E_INL static __device__ __forceinline__
 #define H4E_TABLE static __device__ const
 #define H4E_API static __device__
 #define H4E_STATIC_ASSERT(c, m) static_assert(c, m)
 #else
+#define H4E_LANE 0
+#define H4E_LANES 1
+#define H4E_SYNC() ((void)0)
+#define H4E_ERR(s, bits) ((s)->err |= (uint32_t)(bits))
 #define H4E_FN static
 #define H4E_INL static inline
 #define H4E_TABLE static const
@@ -48,7 +58,11 @@ typedef struct H4Seq H4Seq;     /* the device build defines the entry points as 
 #define H4E_STATIC_ASSERT(c, m) _Static_assert(c, m)
 #endif
 
-#ifdef H4E_PROFILE   /* developer aid: cycle counters per phase (tools only, never defined in the product build) */
+#if defined(H4E_DEVICE)   /* GPU build: per-phase clock64() totals, read back by tools/profile_e2e.py */
+__device__ unsigned long long h4e_dev_prof[8];
+#define PROF_T0() long long prof_t = clock64()
+#define PROF_ADD(i) do { long long n_ = clock64(); if (H4E_LANE == 0) atomicAdd(&h4e_dev_prof[i], (unsigned long long)(n_ - prof_t)); prof_t = n_; } while (0)
+#elif defined(H4E_PROFILE)   /* developer aid: cycle counters per phase (tools only, never defined in the product build) */
 #include <x86intrin.h>
 unsigned long long h4e_prof[8];
 #define PROF_T0() unsigned long long prof_t = __rdtsc()
@@ -380,6 +394,55 @@ H4E_FN void ss_decode_sovf(SymStream *q, const HTab *t, BR *b, int32_t lo, int32
     q->n = n;
 }
 
+#if defined(H4E_DEVICE)
+/* GPU: every lane of the warp decodes its own section (q == NULL: idle lane) through one common
+   instruction stream, so that the lanes run in SIMT lock step instead of one after the other */
+H4E_FN void ss_decode_lane(SymStream *q, const HTab *t, BR *b, int sovf, int32_t lo, int32_t hi)
+{
+    int live = 0;
+    int64_t end_bits = 0;
+    uint32_t n = 0, cap = 0;
+    int32_t sum = 0;
+    int32_t *v = 0;
+    BR x;
+    memset(&x, 0, sizeof x);
+    if (q)
+    {
+        q->pos = q->n = 0;
+        q->over = 0;
+        q->is_const = !t->tab[0].walk && t->tab[0].len == 0;
+        q->cval = q->is_const ? t->tab[0].val : 0;
+        if (q->is_const)
+        {
+            if (sovf && (q->cval <= lo || q->cval >= hi)) q->cval = 0;
+        }
+        else if (b->base && q->cap > 8)
+        {
+            x = *b;
+            end_bits = (int64_t)(b->end - b->base) * 8;
+            v = q->v;
+            cap = q->cap - 8;
+            live = br_pos(&x) < end_bits;
+        }
+    }
+    while (live)
+    {
+        const int32_t a = ht_get(t, &x);
+        sum += a;
+        const int done = !sovf || (a > lo && a < hi);
+        v[n] = sum;
+        n += (uint32_t)done;
+        sum = done ? 0 : sum;
+        live = br_pos(&x) < end_bits && n < cap;
+    }
+    if (v)
+    {
+        q->n = n;
+        *b = x;
+    }
+}
+#endif
+
 H4E_FN void ss_decode2(SymStream *q0, const HTab *t0, BR *b0, int sovf0,
                        SymStream *q1, const HTab *t1, BR *b1, int sovf1, int32_t lo, int32_t hi)
 {
@@ -494,6 +557,8 @@ struct H4Seq
     SymHeader hdr;
     struct Work *dev_work;               /* GPU build only: per-stream record schedule scratch */
     uint32_t dev_work_cap;
+    struct Work *cur_work;               /* schedule of the picture being finished */
+    int setup_ok, nest_x, nest_y;
 };
 
 H4E_INL size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -850,7 +915,7 @@ H4E_INL int32_t ss_at(SymStream *q, uint32_t i)
 
 H4E_FN void fill_records(H4Seq *s, const Work *work, uint32_t n)
 {
-    for (uint32_t i = 0; i < n; ++i)
+    for (uint32_t i = (uint32_t)H4E_LANE; i < n; i += H4E_LANES)
     {
         const Work w = work[i];
         uint32_t *rec = s->rec_base + w.at + 1;
@@ -862,14 +927,14 @@ H4E_FN void fill_records(H4Seq *s, const Work *work, uint32_t n)
             else
             {
                 memset(rec, 0x80, 16);
-                s->err |= SYM_ERR_TRUNCATED;
+                H4E_ERR(s, SYM_ERR_TRUNCATED);
             }
             continue;
         }
         /* n x (descriptor, scale symbol): read16(fixvl) + decodeHuff(bufTree0), h4m:691,726 / 738,767 */
         const uint32_t nb = (uint32_t)w.len - 1 - (w.cls == SYM_REC_INTER);
         const int fix_ok = fx->base && w.fix_off + 2 * nb <= fx->size;
-        if (!fix_ok && nb) s->err |= SYM_ERR_TRUNCATED;
+        if (!fix_ok && nb) H4E_ERR(s, SYM_ERR_TRUNCATED);
         const uint8_t *f = fix_ok ? fx->base + w.fix_off : NULL;
         SymStream *sc = &s->q_sc[p];
         for (uint32_t k = 0; k < nb; ++k)
@@ -884,7 +949,7 @@ H4E_FN void fill_records(H4Seq *s, const Work *work, uint32_t n)
             int32_t g = ss_at(&s->q_dcv[p], w.dcv_off + 1) >> s->dc_shift;
             if (a < -32768 || a > 32767 || g < -32768 || g > 32767)
             {
-                s->err |= SYM_ERR_PAIR_RANGE;
+                H4E_ERR(s, SYM_ERR_PAIR_RANGE);
                 a = a < -32768 ? -32768 : a > 32767 ? 32767 : a;
                 g = g < -32768 ? -32768 : g > 32767 ? 32767 : g;
             }
@@ -1314,37 +1379,58 @@ H4E_FN void pb_pass2(H4Seq *s, int16_t *mv_out, Work *work, Cursors *cur)
 
 /* ------------------------------------------------------------------ entry points */
 
-H4E_API size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_t pic_len)
+/* bulk copy into the blob: memcpy on the host, lane-strided on the GPU */
+H4E_FN void blob_copy(uint8_t *dst, const void *src_, size_t n)
+{
+#if defined(H4E_DEVICE)
+    const uint8_t *src = (const uint8_t *)src_;
+    size_t words = 0;
+    if (!(((uintptr_t)dst | (uintptr_t)src) & 3))
+    {
+        words = n >> 2;
+        for (size_t i = (size_t)H4E_LANE; i < words; i += H4E_LANES) ((uint32_t *)dst)[i] = ((const uint32_t *)src)[i];
+    }
+    for (size_t i = words * 4 + (size_t)H4E_LANE; i < n; i += H4E_LANES) dst[i] = src[i];
+#else
+    memcpy(dst, src_, n);
+#endif
+}
+
+H4E_TABLE uint8_t zero_pic_header[8 + 17 * 4] = {0};
+
+
+/* serial: header, sections, trees */
+H4E_FN void begin_setup(H4Seq *s, int pic_type, const uint8_t *pic, size_t pic_len)
 {
     s->pic_type = pic_type;
     s->err = 0;
     s->n_inter_mcb = 0;
     s->blob_bytes = 0;
+    s->setup_ok = 0;
+    s->nest_x = s->nest_y = 0;
     const int is_i = pic_type == SYM_PIC_I;
     const int nsec = is_i ? 16 : 17;
     if (pic_type != SYM_PIC_I && pic_type != SYM_PIC_P && pic_type != SYM_PIC_B)
     {
         s->err |= SYM_ERR_GEOMETRY;
         s->errors_total |= s->err;
-        return 0;
+        return;
     }
-    uint8_t zero_hdr[8 + 17 * 4] = {0};
     if (pic_len < (size_t)(8 + nsec * 4))
     {
         s->err |= SYM_ERR_TRUNCATED;
-        pic = zero_hdr;
-        pic_len = sizeof zero_hdr;
+        pic = zero_pic_header;
+        pic_len = sizeof zero_pic_header;
     }
     PROF_T0();
     const uint8_t *tab = pic + 8, *data = tab + nsec * 4;
     const size_t dlen = pic_len - 8 - (size_t)nsec * 4;
-    int nest_x = 0, nest_y = 0;
     if (is_i)
     {   /* h4m:1973-1977: the I picture keeps dc_shift local; state->dc_shift is P/B only */
         s->dc_shift = pic[0];
         s->unk_shift = pic[1];
-        nest_x = pic[4] << 8 | pic[5];
-        nest_y = pic[6] << 8 | pic[7];
+        s->nest_x = pic[4] << 8 | pic[5];
+        s->nest_y = pic[6] << 8 | pic[7];
     }
     else
     {   /* h4m:2021-2026 */
@@ -1392,30 +1478,64 @@ H4E_API size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_
         if (s->tree[t].bad) s->err |= SYM_ERR_BAD_TREE;
     s->dc_hi = 0x7F * (1 << s->dc_shift);   /* h4m:2001-2002, 2052-2053 */
     s->dc_lo = -0x80 * (1 << s->dc_shift);
+    s->setup_ok = 1;
     PROF_ADD(0);
-    {
-        const HTab *tb = &s->tree[T_BNUM], *tr = &s->tree[T_RUN], *td = &s->tree[T_DC], *ts = &s->tree[T_SCALE];
-        const int32_t lo = s->dc_lo, hi = s->dc_hi;
-        /* paired by typical size so that the lock-step part covers most of both sections */
-        ss_decode2(&s->q_dcv[0], td, &s->dcv[0], 1, &s->q_bn[0], tb, &s->bn[0], 0, lo, hi);
-        ss_decode2(&s->q_sc[0], ts, &s->sc[0], 0, &s->q_bnr[0], tr, &s->bnr[0], 0, lo, hi);
-        ss_decode2(&s->q_dcv[1], td, &s->dcv[1], 1, &s->q_dcv[2], td, &s->dcv[2], 1, lo, hi);
-        ss_decode2(&s->q_sc[1], ts, &s->sc[1], 0, &s->q_sc[2], ts, &s->sc[2], 0, lo, hi);
-        ss_decode2(&s->q_bn[1], tb, &s->bn[1], 0, &s->q_bnr[1], tr, &s->bnr[1], 0, lo, hi);
-        if (is_i)
-        {
-            ss_decode2(&s->q_rle[0], tr, &s->rle[0], 0, &s->q_rle[1], tr, &s->rle[1], 0, lo, hi);
-            ss_decode(&s->q_rle[2], tr, &s->rle[2]);
-        }
-    }
-    PROF_ADD(5);
+}
 
+/* flat decode of every symbol-only section: pairs in lock step on a host thread, one section per
+   lane on the GPU */
+H4E_FN void begin_flat(H4Seq *s, int is_i)
+{
+    const HTab *tb = &s->tree[T_BNUM], *tr = &s->tree[T_RUN], *td = &s->tree[T_DC], *ts = &s->tree[T_SCALE];
+    const int32_t lo = s->dc_lo, hi = s->dc_hi;
+#if defined(H4E_DEVICE)
+    SymStream *q = 0;
+    const HTab *t = 0;
+    BR *b = 0;
+    int sovf = 0;
+    switch (H4E_LANE)
+    {   /* the large sections first; every lane then runs the SAME loop on its own section */
+    case 0: q = &s->q_dcv[0]; t = td; b = &s->dcv[0]; sovf = 1; break;
+    case 1: q = &s->q_bn[0]; t = tb; b = &s->bn[0]; break;
+    case 2: q = &s->q_sc[0]; t = ts; b = &s->sc[0]; break;
+    case 3: q = &s->q_dcv[1]; t = td; b = &s->dcv[1]; sovf = 1; break;
+    case 4: q = &s->q_dcv[2]; t = td; b = &s->dcv[2]; sovf = 1; break;
+    case 5: q = &s->q_sc[1]; t = ts; b = &s->sc[1]; break;
+    case 6: q = &s->q_sc[2]; t = ts; b = &s->sc[2]; break;
+    case 7: q = &s->q_bn[1]; t = tb; b = &s->bn[1]; break;
+    case 8: q = &s->q_bnr[0]; t = tr; b = &s->bnr[0]; break;
+    case 9: q = &s->q_bnr[1]; t = tr; b = &s->bnr[1]; break;
+    case 10: if (is_i) { q = &s->q_rle[0]; t = tr; b = &s->rle[0]; } break;
+    case 11: if (is_i) { q = &s->q_rle[1]; t = tr; b = &s->rle[1]; } break;
+    case 12: if (is_i) { q = &s->q_rle[2]; t = tr; b = &s->rle[2]; } break;
+    default: break;
+    }
+    ss_decode_lane(q, t, b, sovf, lo, hi);
+#else
+    /* paired by typical size so that the lock-step part covers most of both sections */
+    ss_decode2(&s->q_dcv[0], td, &s->dcv[0], 1, &s->q_bn[0], tb, &s->bn[0], 0, lo, hi);
+    ss_decode2(&s->q_sc[0], ts, &s->sc[0], 0, &s->q_bnr[0], tr, &s->bnr[0], 0, lo, hi);
+    ss_decode2(&s->q_dcv[1], td, &s->dcv[1], 1, &s->q_dcv[2], td, &s->dcv[2], 1, lo, hi);
+    ss_decode2(&s->q_sc[1], ts, &s->sc[1], 0, &s->q_sc[2], ts, &s->sc[2], 0, lo, hi);
+    ss_decode2(&s->q_bn[1], tb, &s->bn[1], 0, &s->q_bnr[1], tr, &s->bnr[1], 0, lo, hi);
+    if (is_i)
+    {
+        ss_decode2(&s->q_rle[0], tr, &s->rle[0], 0, &s->q_rle[1], tr, &s->rle[1], 0, lo, hi);
+        ss_decode(&s->q_rle[2], tr, &s->rle[2]);
+    }
+#endif
+}
+
+/* serial: maps (I) or pass 1 (P/B), record groups, blob plan */
+H4E_FN void begin_maps(H4Seq *s, int is_i)
+{
+    PROF_T0();
     reset_record_counts(s);
     if (is_i)
     {
         ipic_types(s);
         ipic_dcs(s);
-        make_nest(s, nest_x, nest_y);
+        make_nest(s, s->nest_x, s->nest_y);
     }
     else
         pb_pass1(s);
@@ -1423,22 +1543,38 @@ H4E_API size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_
     plan_records(s, is_i);
     plan_blob(s);
     PROF_ADD(2);
+}
+
+H4E_API size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_t pic_len)
+{
+    if (H4E_LANE == 0) begin_setup(s, pic_type, pic, pic_len);
+    H4E_SYNC();
+    if (!s->setup_ok) return 0;
+    const int is_i = pic_type == SYM_PIC_I;
+    {
+        PROF_T0();
+        begin_flat(s, is_i);
+        H4E_SYNC();
+        PROF_ADD(5);
+    }
+    if (H4E_LANE == 0) begin_maps(s, is_i);
+    H4E_SYNC();
     return s->blob_bytes;
 }
 
-H4E_API uint32_t h4e_parse_finish(H4Seq *s, uint8_t *blob)
+/* serial: bitstream-order walk that resolves vectors and schedules every record */
+H4E_FN void finish_schedule(H4Seq *s, uint8_t *blob)
 {
     const SymHeader *h = &s->hdr;
     const int is_i = s->pic_type == SYM_PIC_I;
-    if (s->blob_bytes == 0) return s->err;
     PROF_T0();
     s->rec_base = (uint32_t *)(blob + h->off_rec);
     Work *work = work_scratch(s, s->n_records);
+    s->cur_work = work;
     if (!work && s->n_records)
     {
         s->err |= SYM_ERR_OVERFLOW;
-        s->errors_total |= s->err;
-        return s->err;
+        return;
     }
     Cursors cur;
     for (int p = 0; p < 3; ++p)
@@ -1460,29 +1596,47 @@ H4E_API uint32_t h4e_parse_finish(H4Seq *s, uint8_t *blob)
     else
         pb_pass2(s, (int16_t *)(blob + h->off_mv), work, &cur);
     PROF_ADD(3);
-    fill_records(s, work, s->n_records);
+}
 
-    PROF_ADD(6);
-    /* every consumer must have stayed inside its section */
+H4E_API uint32_t h4e_parse_finish(H4Seq *s, uint8_t *blob)
+{
+    const SymHeader *h = &s->hdr;
+    const int is_i = s->pic_type == SYM_PIC_I;
+    if (s->blob_bytes == 0) return s->err;
+    if (H4E_LANE == 0) finish_schedule(s, blob);
+    H4E_SYNC();
+    if (!s->cur_work && s->n_records)
     {
+        if (H4E_LANE == 0) s->errors_total |= s->err;
+        return s->err;
+    }
+    PROF_T0();
+    fill_records(s, s->cur_work, s->n_records);
+    H4E_SYNC();
+    PROF_ADD(6);
+    blob_copy(blob + h->off_chunks, s->chunks, (size_t)s->n_chunks * 8);
+    blob_copy(blob + h->off_bands, s->band_first, (size_t)SYM_REC_CLASSES * (s->nbands + 1) * 4);
+    for (int p = 0; p < 3; ++p)
+    {
+        blob_copy(blob + h->off_type[p], s->type[p], s->map_cells[p]);
+        blob_copy(blob + h->off_dc[p], s->dc[p], s->map_cells[p]);
+    }
+    if (h->has_nest) blob_copy(blob + h->off_nest, s->nest, SYM_NEST_BYTES);
+    H4E_SYNC();
+    if (H4E_LANE == 0)
+    {
+        /* every consumer must have stayed inside its section */
         int over = 0;
         for (int i = 0; i < 2; ++i) over |= s->q_bn[i].over | s->q_bnr[i].over;
         for (int p = 0; p < 3; ++p) over |= s->q_dcv[p].over | s->q_sc[p].over | (is_i ? s->q_rle[p].over : 0);
         if (!is_i) over |= br_overrun(&s->mvh) | br_overrun(&s->mvv) | br_overrun(&s->mcbt) | br_overrun(&s->mcbp);
         if (over) s->err |= SYM_ERR_TRUNCATED;
+        SymHeader out = *h;
+        out.errors = s->err;
+        memcpy(blob, &out, sizeof out);
+        s->errors_total |= s->err;
     }
-    memcpy(blob + h->off_chunks, s->chunks, (size_t)s->n_chunks * 8);
-    memcpy(blob + h->off_bands, s->band_first, (size_t)SYM_REC_CLASSES * (s->nbands + 1) * 4);
-    for (int p = 0; p < 3; ++p)
-    {
-        memcpy(blob + h->off_type[p], s->type[p], s->map_cells[p]);
-        memcpy(blob + h->off_dc[p], s->dc[p], s->map_cells[p]);
-    }
-    if (h->has_nest) memcpy(blob + h->off_nest, s->nest, SYM_NEST_BYTES);
-    SymHeader out = *h;
-    out.errors = s->err;
-    memcpy(blob, &out, sizeof out);
-    s->errors_total |= s->err;
+    H4E_SYNC();
     PROF_ADD(4);
     return s->err;
 }

@@ -5,9 +5,11 @@
  * in ~1 us, one host core parses it in ~0.6 ms.  A picture's parse is serial, but a batch has a
  * thousand independent pictures, so the same C code is compiled here as __device__ functions
  * (entropy.c is #include'd with H4E_DEVICE; see the macro block at its top) and run with ONE
- * PICTURE PER WARP: lane 0 executes the parser exactly as a host thread would, against
- * per-stream state that lives in device memory, and writes the symbol buffer straight into a
- * device arena that the reconstruction kernel reads next.  Nothing but the raw picture bytes
+ * PICTURE PER WARP: lane 0 executes the serial parts of the parser exactly as a host thread
+ * would, against per-stream state that lives in device memory; the parts that are parallel
+ * inside a picture -- the flat decode of the symbol sections (one section per lane), the
+ * group-ordered record fill and the map copies -- use all lanes.  The symbol buffer is written
+ * straight into a device arena that the reconstruction kernel reads next.  Nothing but the raw picture bytes
  * crosses PCIe on the way in.  A single lane is slow (~10x a host core) but there are thousands
  * of warp slots; what matters is that the whole step's pictures parse concurrently.
  *
@@ -56,38 +58,53 @@ __global__ void dev_init_kernel(uint8_t *arena, size_t slot_bytes, int n_streams
     seq_init_maps(s);
 }
 
-/* one warp per picture; lane 0 runs the parser */
+/* one warp per picture: the entry points of entropy.c are warp-collective in the device build */
 __global__ void __launch_bounds__(32)
 dev_parse_kernel(uint8_t *arena, size_t slot_bytes, const H4DevPicture *pics, int n_pics, uint8_t *blob_arena,
                  unsigned long long *blob_used, unsigned long long blob_cap, ReconJob *jobs, uint32_t *errors)
 {
     const int i = blockIdx.x;
-    if (i >= n_pics || threadIdx.x != 0) return;
+    if (i >= n_pics) return;
+    const int lane = threadIdx.x;
     const H4DevPicture pic = pics[i];
     H4Seq *s = slot_seq(arena, slot_bytes, pic.stream);
     const size_t bytes = h4e_parse_begin(s, pic.pic_type, pic.data, pic.bytes);
-    uint32_t err = s->err;
-    jobs[i].blob = nullptr;
-    jobs[i].n_chunks = 0;
+    uint32_t err = 0;
+    uint8_t *blob = nullptr;
     if (bytes)
     {
         const unsigned long long need = (bytes + 127) & ~127ull;
-        const unsigned long long at = atomicAdd(blob_used, need);
+        unsigned long long at = 0;
+        if (lane == 0) at = atomicAdd(blob_used, need);
+        at = __shfl_sync(0xFFFFFFFFu, at, 0);
         if (at + need <= blob_cap)
         {
-            err |= h4e_parse_finish(s, blob_arena + at);
-            jobs[i].blob = blob_arena + at;
-            jobs[i].n_chunks = s->n_chunks;
+            blob = blob_arena + at;
+            err = h4e_parse_finish(s, blob);
         }
         else
-            err |= SYM_ERR_OVERFLOW;
+            err = s->err | SYM_ERR_OVERFLOW;
     }
     else
-        err |= SYM_ERR_GEOMETRY;
-    if (err) atomicOr(errors, err);
+        err = s->err | SYM_ERR_GEOMETRY;
+    if (lane == 0)
+    {
+        jobs[i].blob = blob;
+        jobs[i].n_chunks = blob ? s->n_chunks : 0;
+        if (err) atomicOr(errors, err);
+    }
 }
 
 }  // namespace
+
+/* per-phase cycle totals of the GPU parser since the last call (diagnostics): hdr+trees, pass 1,
+   plan, pass 2 scheduling, map copies, flat decode, record fill */
+extern "C" void hvqm4_dev_entropy_profile(unsigned long long out[8])
+{
+    cudaMemcpyFromSymbol(out, h4e_dev_prof, sizeof(unsigned long long) * 8);
+    unsigned long long zero[8] = {0};
+    cudaMemcpyToSymbol(h4e_dev_prof, zero, sizeof zero);
+}
 
 extern "C" size_t hvqm4_dev_entropy_slot_bytes(int width, int height, uint32_t sym_cap, uint32_t work_cap)
 {

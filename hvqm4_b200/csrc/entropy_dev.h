@@ -30,6 +30,7 @@ int hvqm4_dev_entropy_init(uint8_t *arena, size_t slot_bytes, int n_streams, int
 int hvqm4_dev_entropy_parse(uint8_t *arena, size_t slot_bytes, const H4DevPicture *d_pics, int n_pics, uint8_t *blob_arena,
                             unsigned long long *d_blob_used, unsigned long long blob_cap, struct ReconJob *d_jobs,
                             uint32_t *d_errors, cudaStream_t stream);
+void hvqm4_dev_entropy_profile(unsigned long long out[8]);
 #ifdef __cplusplus
 }
 #endif

@@ -148,6 +148,11 @@ int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, const int3
  */
 int HVQM4BatchSetEntropyMode(HVQM4Batch *b, int gpu);
 
+/* Diagnostics: SM cycles the GPU bitstream stage spent per phase since the last call, summed over
+   pictures: header+trees, pass 1 (maps), record planning, pass 2 (scheduling), map copies, flat
+   section decode, record fill, unused. */
+void HVQM4DevEntropyProfile(uint64_t out[8]);
+
 /* Waits for all enqueued work; returns accumulated error bits and clears them. */
 int HVQM4BatchSync(HVQM4Batch *b);
 

@@ -50,4 +50,11 @@ h1 = batch.stats()["host_ns"]
 n = S * 16 * GOPS
 print(f"gpu_entropy={GPU_ENTROPY} S={S} threads={T or os.cpu_count()} d2h={D2H} profile={PROFILE}: {n / (t1 - t0):.0f} fps e2e; "
       f"host stage alone {(h1 - h0) / 1e9:.3f} s of {t1 - t0:.3f} s wall -> {n / ((h1 - h0) / 1e9):.0f} fps if host-only")
+if GPU_ENTROPY:
+    prof = (ctypes.c_uint64 * 8)()
+    api.lib().HVQM4DevEntropyProfile(prof)
+    names = ["hdr+trees", "pass1", "plan", "pass2 schedule", "copies", "flat decode", "fill records"]
+    tot = sum(prof[:7]) or 1
+    npic = S * 16 * (GOPS + 1)
+    print("   GPU parser, per picture: " + ", ".join(f"{nm} {prof[i] / npic / 1.9e3:.0f} us ({100 * prof[i] / tot:.0f}%)" for i, nm in enumerate(names)))
 batch.close()
