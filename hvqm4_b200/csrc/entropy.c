@@ -41,6 +41,7 @@ typedef struct H4Seq H4Seq;     /* the device build defines the entry points as 
 #define H4E_LANES 32
 #define H4E_SYNC() __syncwarp()
 #define H4E_ERR(s, bits) atomicOr(&(s)->err, (uint32_t)(bits))
+#define H4E_FETCH_ADD(ptr, v) atomicAdd((ptr), (uint32_t)(v))
 #define H4E_FN static __device__
 #define H4E_INL static __device__ __forceinline__
 #define H4E_TABLE static __device__ const
@@ -51,12 +52,18 @@ typedef struct H4Seq H4Seq;     /* the device build defines the entry points as 
 #define H4E_LANES 1
 #define H4E_SYNC() ((void)0)
 #define H4E_ERR(s, bits) ((s)->err |= (uint32_t)(bits))
+#define H4E_FETCH_ADD(ptr, v) h4e_fetch_add((ptr), (uint32_t)(v))
 #define H4E_FN static
 #define H4E_INL static inline
 #define H4E_TABLE static const
 #define H4E_API
 #define H4E_STATIC_ASSERT(c, m) _Static_assert(c, m)
 #endif
+
+#if !defined(H4E_DEVICE)
+static inline uint32_t h4e_fetch_add(uint32_t *p, uint32_t v) { const uint32_t o = *p; *p = o + v; return o; }
+#endif
+
 
 #if defined(H4E_DEVICE)   /* GPU build: per-phase clock64() totals, read back by tools/profile_e2e.py */
 __device__ unsigned long long h4e_dev_prof[8];
@@ -559,6 +566,7 @@ struct H4Seq
     uint32_t dev_work_cap;
     struct Work *cur_work;               /* schedule of the picture being finished */
     int setup_ok, nest_x, nest_y;
+    int split_schedule;                  /* host only: run the GPU's pb_mvs + schedule_rows split (tests) */
 };
 
 H4E_INL size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -702,6 +710,7 @@ H4E_API void h4e_seq_set_version(H4Seq *s, int version15) { s->version15 = versi
 H4E_API uint32_t h4e_seq_errors(const H4Seq *s) { return s->errors_total; }
 H4E_API size_t h4e_frame_bytes(const H4Seq *s) { return (size_t)s->width * s->height * 3 / 2; }
 
+H4E_API void h4e_seq_set_split_schedule(H4Seq *s, int on) { s->split_schedule = on; }
 H4E_API uint32_t h4e_last_inter_mcbs(const H4Seq *s) { return s->n_inter_mcb; }
 H4E_API uint32_t h4e_last_chunks(const H4Seq *s) { return s->n_chunks; }
 
@@ -850,6 +859,8 @@ H4E_FN void plan_records(H4Seq *s, int is_ipic)
  */
 typedef struct { uint32_t fix[3], sc[3], dcv[3]; } Cursors;
 
+H4E_TABLE int SUBX[4] = {0, 0, 1, 1}, SUBY[4] = {0, 1, 1, 0};   /* TL, BL, BR, TR: mcb_offset, h4m:862-865 */
+
 #if defined(H4E_DEVICE)
 H4E_FN Work *work_scratch(H4Seq *s, uint32_t n) { return n <= s->dev_work_cap ? s->dev_work : NULL; }
 #else
@@ -870,6 +881,20 @@ static Work *work_scratch(H4Seq *s, uint32_t n)
 }
 #endif
 
+/* what a record's block consumes from its plane's sections: raw 16 bytes | n x (2 descriptor
+   bytes + 1 scale symbol) [+ 2 pair values] */
+H4E_INL void cursors_advance(Cursors *c, int p, uint32_t lut)
+{
+    const int cls = (int)(lut >> 16);
+    const uint32_t len = lut & 0xFFFF;
+    const uint32_t nb = cls == SYM_REC_RAW ? 0 : len - 1 - (cls == SYM_REC_INTER);
+    c->fix[p] += cls == SYM_REC_RAW ? 16 : 2 * nb;
+    c->sc[p] += nb;
+    c->dcv[p] += cls == SYM_REC_INTER ? 2 : 0;
+}
+
+/* slots inside a group are handed out with fetch-and-add: on the GPU the rows of a picture are
+   scheduled by different lanes, and the order of records inside a group is free */
 H4E_INL void schedule_record(H4Seq *s, Work *work, Cursors *c, uint32_t t, int is_ipic, int p, int bx, int by)
 {
     const uint32_t lut = rec_lut(is_ipic, t);
@@ -877,15 +902,14 @@ H4E_INL void schedule_record(H4Seq *s, Work *work, Cursors *c, uint32_t t, int i
     const uint32_t len = lut & 0xFFFF;
     const int band = by >> (p ? SYM_BAND_SHIFT_CHROMA : SYM_BAND_SHIFT_LUMA);
     const int g = group_of(s, cls, band, len);
-    const uint32_t idx = s->grp_next[g]++;
+    const uint32_t idx = H4E_FETCH_ADD(&s->grp_next[g], 1);
     uint32_t at;
     if (len < SYM_LEN_BUCKETS)
         at = s->grp_base[g] + idx * len;
     else
     {
-        const uint32_t ch = s->grp_chunk[g]++;
-        at = s->grp_base[g];
-        s->grp_base[g] += len;
+        const uint32_t ch = H4E_FETCH_ADD(&s->grp_chunk[g], 1);
+        at = H4E_FETCH_ADD(&s->grp_base[g], len);
         s->chunks[2 * ch] = at;
         s->chunks[2 * ch + 1] = 1u | ((len - 1) & 0xFF) << 8 | (uint32_t)cls << 16;
     }
@@ -898,11 +922,96 @@ H4E_INL void schedule_record(H4Seq *s, Work *work, Cursors *c, uint32_t t, int i
     w->len = (uint16_t)len;
     w->cls = (uint8_t)cls;
     w->plane = (uint8_t)p;
-    /* what the block consumes: raw 16 bytes | n x (2 descriptor bytes + 1 scale symbol) [+ 2 pair values] */
-    const uint32_t nb = cls == SYM_REC_RAW ? 0 : len - 1 - (cls == SYM_REC_INTER);
-    c->fix[p] += cls == SYM_REC_RAW ? 16 : 2 * nb;
-    c->sc[p] += nb;
-    c->dcv[p] += cls == SYM_REC_INTER ? 2 : 0;
+    cursors_advance(c, p, lut);
+}
+
+/* exclusive prefix sum of `v` over the lanes (total in *sum); the identity on a host thread */
+H4E_INL uint32_t lane_scan(uint32_t v, uint32_t *sum)
+{
+#if defined(H4E_DEVICE)
+    uint32_t inc = v;
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (H4E_LANE >= d) inc += o;
+    }
+    *sum = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    return inc - v;
+#else
+    *sum = v;
+    return 0;
+#endif
+}
+
+/* Records of one row in bitstream order: one macroblock row of a P/B picture (all three planes,
+   MCBlockDecDCNest h4m:1789-1827 / MCBlockDecMCNest h4m:1871-1909), or one block row of plane p of
+   an I picture (IpicPlaneDec, h4m:1487-1518).  work == NULL: only advance the cursors. */
+H4E_FN void row_records(H4Seq *s, int is_ipic, int p, int row, Work *work, Cursors *c)
+{
+    if (is_ipic)
+    {
+        const uint8_t *ty = s->type[p] + cell_at(s, p, 0, row);
+        for (int bx = 0; bx < s->bw[p]; ++bx)
+        {
+            const uint32_t t = ty[bx];
+            if (t == 0 || t == 8) continue;
+            if (work) schedule_record(s, work, c, t, 1, p, bx, row);
+            else cursors_advance(c, p, rec_lut(1, t));
+        }
+        return;
+    }
+    const int st0 = s->stride[0], my = row;
+    const uint8_t *ty0 = s->type[0] + cell_at(s, 0, 0, my * 2);
+    const uint8_t *ty1 = s->type[1] + cell_at(s, 1, 0, my), *ty2 = s->type[2] + cell_at(s, 2, 0, my);
+    for (int mx = 0; mx < s->mbw; ++mx)
+    {
+        const int lx = mx * 2;
+        const uint8_t tag = ty0[lx];
+        const int intra = ((tag >> 5) & 3) == 0;
+        if (!intra && (tag & 0x10)) continue;                 /* plain motion compensation: no records */
+        for (int k = 0; k < 6; ++k)
+        {
+            const int pl = k < 4 ? 0 : k - 3;
+            const int bx = k < 4 ? lx + SUBX[k] : mx, by = k < 4 ? my * 2 + SUBY[k] : my;
+            const uint32_t t = k < 4 ? ty0[SUBY[k] * st0 + lx + SUBX[k]] : k == 4 ? ty1[mx] : ty2[mx];
+            const uint32_t nib = t & 0xF;
+            if (nib == 0 || (intra && nib == 8)) continue;
+            if (work) schedule_record(s, work, c, t, 0, pl, bx, by);
+            else cursors_advance(c, pl, rec_lut(0, t));
+        }
+    }
+}
+
+/* Schedules every record of the picture, rows dealt to the lanes: a row first adds up what it
+   consumes, a prefix sum over the rows turns that into each row's starting cursors, then the row
+   is walked again for real.  On a host thread (one lane) this degenerates to two serial walks. */
+H4E_FN void schedule_rows(H4Seq *s, int is_ipic, Work *work, const Cursors *start)
+{
+    for (int p = 0; p < (is_ipic ? 3 : 1); ++p)
+    {
+        const int rows = is_ipic ? s->bh[p] : s->mbh;
+#if !defined(H4E_DEVICE)
+        Cursors one = *start;
+        for (int row = 0; row < rows; ++row) row_records(s, is_ipic, p, row, work, &one);
+        continue;
+#endif
+        Cursors base = *start;
+        for (int r0 = 0; r0 < rows; r0 += H4E_LANES)
+        {
+            const int row = r0 + H4E_LANE;
+            Cursors mine, at;
+            memset(&mine, 0, sizeof mine);
+            if (row < rows) row_records(s, is_ipic, p, row, NULL, &mine);
+            for (int q = 0; q < 3; ++q)
+            {
+                uint32_t sum;
+                at.fix[q] = base.fix[q] + lane_scan(mine.fix[q], &sum); base.fix[q] += sum;
+                at.sc[q] = base.sc[q] + lane_scan(mine.sc[q], &sum); base.sc[q] += sum;
+                at.dcv[q] = base.dcv[q] + lane_scan(mine.dcv[q], &sum); base.dcv[q] += sum;
+            }
+            if (row < rows) row_records(s, is_ipic, p, row, work, &at);
+        }
+    }
 }
 
 H4E_INL int32_t ss_at(SymStream *q, uint32_t i)
@@ -1122,7 +1231,6 @@ H4E_FN void make_nest(H4Seq *s, int nx, int ny)
 typedef struct { uint32_t value, count; } RunLen;
 
 H4E_TABLE uint8_t next_type[2][4] = {{1, 2, 0, 0}, {2, 0, 1, 0}};   /* mcbtypetrans, h4m:1591-1594 */
-H4E_TABLE int SUBX[4] = {0, 0, 1, 1}, SUBY[4] = {0, 1, 1, 0};   /* TL, BL, BR, TR: mcb_offset, h4m:862-865 */
 
 /* spread_PB_descMap, h4m:1742-1776, with decode_PB_dc (1649), decode_PB_cc (1670),
    getMCBtype (1596), getMCBproc (1613), initMCBtype/proc (1551-1569) */
@@ -1306,7 +1414,71 @@ H4E_FN int mcb_refs_in_surface(const H4Seq *s, int32_t rx, int32_t ry, int needs
     return 1;
 }
 
-/* BpicPlaneDec pass 2, h4m:1922-1967, symbol part only */
+/* BpicPlaneDec pass 2, h4m:1922-1967, motion vectors only: the vector chain (getMVector) is the
+   serial part of pass 2; the records of the same macroblocks are scheduled by schedule_rows() */
+H4E_FN void pb_mvs(H4Seq *s, int16_t *mv_out)
+{
+    int32_t mvx = 0, mvy = 0;
+    int cur_ref = -1;
+    const int st0 = s->stride[0];
+    uint32_t n_inter = 0;
+    BR mvh = s->mvh, mvv = s->mvv;
+    for (int my = 0; my < s->mbh; ++my)
+    {
+        const uint8_t *ty0 = s->type[0] + cell_at(s, 0, 0, my * 2);
+        const uint8_t *ty1 = s->type[1] + cell_at(s, 1, 0, my), *ty2 = s->type[2] + cell_at(s, 2, 0, my);
+        for (int mx = 0; mx < s->mbw; ++mx)
+        {
+            const int lx = mx * 2;
+            const uint8_t tag = ty0[lx];
+            int16_t *mvp = mv_out + 2 * ((size_t)my * s->mbw + mx);
+            const int mt = (tag >> 5) & 3;
+            if (mt == 0)
+            {
+                mvp[0] = mvp[1] = 0;
+                continue;
+            }
+            const int ref = mt - 1;
+            ++n_inter;
+            if (ref != cur_ref)
+            {   /* h4m:1943-1949 */
+                cur_ref = ref;
+                mvx = mvy = 0;
+            }
+            read_mv(s, &mvh, &mvx, s->rb[ref][0]);
+            read_mv(s, &mvv, &mvy, s->rb[ref][1]);
+            const int32_t rx = mx * 16 + mvx, ry = my * 16 + mvy;   /* h4m:1954-1955 */
+            int needs_window = 0;
+            if (!(tag & 0x10))
+            {   /* a PrediAot block with bases reads the 70x38 window around the vector (h4m:1334-1348) */
+                const uint32_t t6[6] = {ty0[lx], ty0[st0 + lx], ty0[st0 + lx + 1], ty0[lx + 1], ty1[mx], ty2[mx]};
+                for (int k = 0; k < 6; ++k)
+                {
+                    const uint32_t nib = t6[k] & 0xF;
+                    if (nib > 1 && nib != 6) needs_window = 1;
+                }
+            }
+            if (rx < -32000 || rx > 32000 || ry < -32000 || ry > 32000 || !mcb_refs_in_surface(s, rx, ry, needs_window))
+            {
+                s->err |= SYM_ERR_MV_RANGE;
+                mvp[0] = mvp[1] = -32768;   /* poison: recon.cu paints the macroblock grey */
+            }
+            else
+            {
+                mvp[0] = (int16_t)rx;
+                mvp[1] = (int16_t)ry;
+            }
+        }
+    }
+    s->n_inter_mcb = n_inter;
+    s->mvh = mvh;
+    s->mvv = mvv;
+}
+
+/* BpicPlaneDec pass 2, h4m:1922-1967, symbol part only: vectors and records in ONE walk.  This is
+   what a host thread runs (7% faster there than pb_mvs + schedule_rows, which the GPU uses and
+   which h4e_seq_set_split_schedule selects on the host so that tests can compare the two). */
+#if !defined(H4E_DEVICE)
 H4E_FN void pb_pass2(H4Seq *s, int16_t *mv_out, Work *work, Cursors *cur)
 {
     int32_t mvx = 0, mvy = 0;
@@ -1376,6 +1548,7 @@ H4E_FN void pb_pass2(H4Seq *s, int16_t *mv_out, Work *work, Cursors *cur)
     s->mvh = mvh;
     s->mvv = mvv;
 }
+#endif
 
 /* ------------------------------------------------------------------ entry points */
 
@@ -1562,20 +1735,24 @@ H4E_API size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_
     return s->blob_bytes;
 }
 
-/* serial: bitstream-order walk that resolves vectors and schedules every record */
+/* resolves the motion vectors (serial) and schedules every record (rows dealt to the lanes) */
 H4E_FN void finish_schedule(H4Seq *s, uint8_t *blob)
 {
     const SymHeader *h = &s->hdr;
     const int is_i = s->pic_type == SYM_PIC_I;
     PROF_T0();
-    s->rec_base = (uint32_t *)(blob + h->off_rec);
-    Work *work = work_scratch(s, s->n_records);
-    s->cur_work = work;
-    if (!work && s->n_records)
+    if (H4E_LANE == 0)
     {
-        s->err |= SYM_ERR_OVERFLOW;
-        return;
+        s->rec_base = (uint32_t *)(blob + h->off_rec);
+        s->cur_work = work_scratch(s, s->n_records);
+        if (!s->cur_work && s->n_records) s->err |= SYM_ERR_OVERFLOW;
+#if defined(H4E_DEVICE)
+        else if (!is_i) pb_mvs(s, (int16_t *)(blob + h->off_mv));
+#endif
     }
+    H4E_SYNC();
+    PROF_ADD(7);
+    if (!s->cur_work && s->n_records) return;
     Cursors cur;
     for (int p = 0; p < 3; ++p)
     {
@@ -1583,18 +1760,17 @@ H4E_FN void finish_schedule(H4Seq *s, uint8_t *blob)
         cur.sc[p] = s->q_sc[p].pos;
         cur.dcv[p] = s->q_dcv[p].pos;   /* P/B: the pass-1 DC deltas come first in dc_values[p] */
     }
-    if (is_i)
-    {   /* IpicPlaneDec order: plane by plane, raster (h4m:2011-2015, 1487-1518) */
-        for (int p = 0; p < 3; ++p)
-            for (int by = 0; by < s->bh[p]; ++by)
-            {
-                const uint8_t *ty = s->type[p] + cell_at(s, p, 0, by);
-                for (int bx = 0; bx < s->bw[p]; ++bx)
-                    if (ty[bx] != 0 && ty[bx] != 8) schedule_record(s, work, &cur, ty[bx], 1, p, bx, by);
-            }
+#if !defined(H4E_DEVICE)
+    if (!is_i && !s->split_schedule)
+    {
+        pb_pass2(s, (int16_t *)(blob + h->off_mv), s->cur_work, &cur);
+        PROF_ADD(3);
+        return;
     }
-    else
-        pb_pass2(s, (int16_t *)(blob + h->off_mv), work, &cur);
+    if (!is_i) pb_mvs(s, (int16_t *)(blob + h->off_mv));
+#endif
+    schedule_rows(s, is_i, s->cur_work, &cur);
+    H4E_SYNC();
     PROF_ADD(3);
 }
 
@@ -1603,8 +1779,7 @@ H4E_API uint32_t h4e_parse_finish(H4Seq *s, uint8_t *blob)
     const SymHeader *h = &s->hdr;
     const int is_i = s->pic_type == SYM_PIC_I;
     if (s->blob_bytes == 0) return s->err;
-    if (H4E_LANE == 0) finish_schedule(s, blob);
-    H4E_SYNC();
+    finish_schedule(s, blob);
     if (!s->cur_work && s->n_records)
     {
         if (H4E_LANE == 0) s->errors_total |= s->err;

@@ -43,6 +43,8 @@ size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_t pic_le
 uint32_t h4e_parse_finish(H4Seq *s, uint8_t *blob);
 
 /* inter-coded macroblocks of the last parsed picture (for bandwidth accounting) */
+/* test hook: use the split pass 2 of the GPU build (serial vector chain + row-wise scheduling) on the host */
+void h4e_seq_set_split_schedule(H4Seq *s, int on);
 uint32_t h4e_last_inter_mcbs(const H4Seq *s);
 /* record-kernel chunks of the picture planned by the last h4e_parse_begin */
 uint32_t h4e_last_chunks(const H4Seq *s);

@@ -41,6 +41,7 @@ def emul_lib():
     lib.h4e_parse_begin.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]
     lib.h4e_parse_finish.restype = ctypes.c_uint32
     lib.h4e_parse_finish.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.h4e_seq_set_split_schedule.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.h4e_seq_errors.restype = ctypes.c_uint32
     lib.h4e_seq_errors.argtypes = [ctypes.c_void_p]
     lib.emul_recon_picture.argtypes = [ctypes.c_void_p] * 4

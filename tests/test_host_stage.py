@@ -27,6 +27,31 @@ def test_emulated_pipeline_matches_port_on_fresh_seeds(emul_lib, oracle):
         assert got == want
 
 
+@pytest.mark.parametrize("args", [
+    dict(width=320, height=240, version=15, gop="IPBBPBB", n_gops=1, seed=811, profile=0),
+    dict(width=640, height=480, version=13, gop="IPB", n_gops=1, seed=812, profile=1),
+    dict(width=328, height=248, version=15, gop="IPB", n_gops=1, seed=813, profile=0)])
+def test_split_schedule_builds_the_same_symbol_buffer(emul_lib, args):
+    """The GPU build of the entropy stage resolves vectors serially and schedules records row by
+    row (pb_mvs + schedule_rows); a host thread runs the fused pb_pass2.  One lane must give the
+    same bytes either way."""
+    version, w, h, recs = demux(synth.generate(**args))
+    seqs = [emul_lib.h4e_seq_create(w, h, 2, 2, 1 if version == 15 else 0) for _ in range(2)]
+    emul_lib.h4e_seq_set_split_schedule(seqs[1], 1)
+    for ty, _, pic in recs:
+        buf = bytes(pic) + b"\0" * 8
+        blobs = []
+        for seq in seqs:
+            n = emul_lib.h4e_parse_begin(seq, ty, buf, len(pic))
+            assert n
+            blob = np.zeros(n, np.uint8)
+            assert emul_lib.h4e_parse_finish(seq, blob.ctypes.data) == 0
+            blobs.append(blob.tobytes())
+        assert blobs[0] == blobs[1]
+    for seq in seqs:
+        emul_lib.h4e_seq_destroy(seq)
+
+
 def test_truncated_and_corrupt_pictures_raise_error_bits_not_crashes(emul_lib):
     """The reference has no input validation; the host stage must stay in bounds."""
     data = synth.generate(320, 240, 15, "IPB", 1, seed=42, profile=0)
