@@ -107,10 +107,15 @@ H4E_INL void br_refill(BR *b)
     {
         uint64_t w;
 #if defined(H4E_DEVICE)
-        {   /* byte-wise big-endian gather: the pointer is arbitrarily aligned */
-            const uint8_t *q = b->p;
-            w = (uint64_t)q[0] << 56 | (uint64_t)q[1] << 48 | (uint64_t)q[2] << 40 | (uint64_t)q[3] << 32 |
-                (uint64_t)q[4] << 24 | (uint64_t)q[5] << 16 | (uint64_t)q[6] << 8 | q[7];
+        {   /* two aligned 8-byte loads around the (arbitrarily aligned) pointer, funnel-shifted and
+               byte-swapped; this may touch up to 15 bytes past p + 8, which the batch runtime's
+               16 bytes of padding behind every picture cover */
+            const uintptr_t a = (uintptr_t)b->p;
+            const unsigned long long *q = (const unsigned long long *)(a & ~(uintptr_t)7);
+            const unsigned sh = (unsigned)(a & 7) * 8;
+            const unsigned long long lo = q[0], hi = q[1];
+            const unsigned long long x = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+            w = (uint64_t)__byte_perm((unsigned)x, 0, 0x0123) << 32 | __byte_perm((unsigned)(x >> 32), 0, 0x0123);
         }
 #else
         memcpy(&w, b->p, 8);
@@ -543,6 +548,9 @@ struct H4Seq
     HTab tree[6];
     int nbands, ngroups;                 /* record groups: [class][band][length bucket] */
     uint32_t *grp_count, *grp_base, *grp_next, *grp_chunk, *grp_ord;
+    uint8_t *mcb_tag;                    /* P/B pass 1, split form: type/proc tag of every macroblock ... */
+    uint32_t *mcb_list, n_list;          /* ... and the macroblocks that carry block types, in bitstream order */
+    int32_t *mv_raw;                     /* split pass 2: accumulated vector (h, v) of every macroblock */
     uint32_t *chunks;                    /* chunk table under construction (2 words per chunk) */
     uint32_t chunks_cap;
     uint32_t *band_first;                /* [SYM_REC_CLASSES][nbands + 1] */
@@ -643,6 +651,9 @@ H4E_FN size_t seq_carve(H4Seq *s, uint8_t *mem, uint32_t sym_cap, uint32_t work_
     CARVE(s->grp_ord, uint32_t, s->ngroups);
     CARVE(s->chunks, uint32_t, (size_t)s->chunks_cap * 2);
     CARVE(s->band_first, uint32_t, (size_t)SYM_REC_CLASSES * (s->nbands + 1));
+    CARVE(s->mcb_tag, uint8_t, (size_t)s->mbw * s->mbh);
+    CARVE(s->mcb_list, uint32_t, (size_t)s->mbw * s->mbh);
+    CARVE(s->mv_raw, int32_t, (size_t)s->mbw * s->mbh * 2);
     if (sym_cap)
     {
         SymStream *all[13] = {&s->q_bn[0], &s->q_bn[1], &s->q_bnr[0], &s->q_bnr[1], &s->q_dcv[0], &s->q_dcv[1], &s->q_dcv[2],
@@ -780,9 +791,9 @@ H4E_INL void count_record(H4Seq *s, uint32_t t, int is_ipic, int by, int band_sh
     const int cls = (int)(lut >> 16);
     const uint32_t len = lut & 0xFFFF;
     const int g = group_of(s, cls, by >> band_shift, len);
-    s->grp_count[g]++;
-    if (len >= SYM_LEN_BUCKETS) s->grp_base[g] += len;   /* long-bucket word total, see plan_records */
-    s->n_records++;
+    H4E_FETCH_ADD(&s->grp_count[g], 1);
+    if (len >= SYM_LEN_BUCKETS) H4E_FETCH_ADD(&s->grp_base[g], len);   /* long-bucket word total, see plan_records */
+    H4E_FETCH_ADD(&s->n_records, 1);
 }
 
 H4E_FN void reset_record_counts(H4Seq *s)
@@ -940,6 +951,16 @@ H4E_INL uint32_t lane_scan(uint32_t v, uint32_t *sum)
 #else
     *sum = v;
     return 0;
+#endif
+}
+
+/* number of lanes whose predicate holds */
+H4E_INL uint32_t lane_count(int pred)
+{
+#if defined(H4E_DEVICE)
+    return (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, pred));
+#else
+    return pred ? 1u : 0u;
 #endif
 }
 
@@ -1363,6 +1384,326 @@ H4E_FN void pb_pass1(H4Seq *s)
     s->q_dcv[0] = dcv0; s->q_dcv[1] = dcv1; s->q_dcv[2] = dcv2;
 }
 
+/* ------------------------------------------------------------------ block types, data-parallel form
+ *
+ * Ipic_BasisNumDec (h4m:1073-1130) and decode_PB_cc (h4m:1670-1740) are the same automaton over a
+ * SEQUENCE of blocks: take a type symbol; a zero symbol is followed by a run length and leaves
+ * that many further blocks without a symbol.  Symbol j therefore lands on sequence element
+ *     pos(j) = j + (sum of the first z(j) run lengths),   z(j) = zero symbols before j,
+ * which is two prefix sums instead of a serial walk.  The GPU build runs this form with the
+ * symbols dealt to the lanes; one lane (host, h4e_seq_set_split_schedule) gives the same maps,
+ * and the tests compare it with the serial loops above.
+ */
+#define RUN_CAP (1u << 23)   /* more than any sequence length (2048 x 2048 blocks); run sums saturate here */
+
+H4E_INL uint32_t sat_run(uint32_t a, uint32_t b) { return a + b > RUN_CAP ? RUN_CAP : a + b; }
+
+/* exclusive saturating prefix sum of v over the lanes */
+H4E_INL uint32_t lane_scan_sat(uint32_t v, uint32_t *sum)
+{
+#if defined(H4E_DEVICE)
+    uint32_t inc = v;
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (H4E_LANE >= d) inc = sat_run(inc, o);
+    }
+    *sum = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    const uint32_t ex = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
+    return H4E_LANE ? ex : 0u;
+#else
+    *sum = v;
+    return 0;
+#endif
+}
+
+/* replaces the run lengths by their exclusive prefix sums, in place; returns the total */
+H4E_FN uint32_t runs_prefix(SymStream *q)
+{
+    uint32_t carry = 0;
+    for (uint32_t b = 0; b < q->n; b += H4E_LANES)
+    {
+        const uint32_t i = b + (uint32_t)H4E_LANE;
+        uint32_t v = 0, sum;
+        if (i < q->n)
+        {
+            v = (uint32_t)q->v[i];
+            if (v > RUN_CAP) v = RUN_CAP;
+        }
+        const uint32_t ex = sat_run(carry, lane_scan_sat(v, &sum));
+        if (i < q->n) q->v[i] = (int32_t)ex;
+        carry = sat_run(carry, sum);
+    }
+    return carry;
+}
+
+/* sum of the first z run lengths (after runs_prefix) */
+H4E_INL uint32_t runs_before(const SymStream *q, uint32_t total, uint32_t z)
+{
+    if (z < q->n) return (uint32_t)q->v[z];
+    if (!q->is_const || z == q->n) return total;          /* an exhausted section reads as 0 (ss_get) */
+    uint32_t c = (uint32_t)q->cval;
+    if (c > RUN_CAP) c = RUN_CAP;
+    const uint64_t r = (uint64_t)total + (uint64_t)(z - q->n) * c;
+    return r > RUN_CAP ? RUN_CAP : (uint32_t)r;
+}
+
+H4E_INL int32_t ss_peek(const SymStream *q, uint32_t i) { return i < q->n ? q->v[i] : q->is_const ? q->cval : 0; }
+
+enum { SEQ_I_LUMA, SEQ_I_CHROMA, SEQ_PB_LUMA, SEQ_PB_CHROMA, SEQ_I_DC /* + plane */ };
+
+/* the type symbol `sym` belongs to element `pos` of the block sequence */
+H4E_INL void place_type(H4Seq *s, int seq, uint32_t pos, int32_t sym)
+{
+    switch (seq)
+    {
+    case SEQ_I_LUMA:
+    {   /* raster over the luma blocks, h4m:1082-1101 */
+        const int by = (int)(pos / (uint32_t)s->bw[0]), bx = (int)(pos % (uint32_t)s->bw[0]);
+        s->type[0][cell_at(s, 0, bx, by)] = (uint8_t)sym;
+        if ((int16_t)sym != 0) count_record(s, (uint8_t)sym, 1, by, SYM_BAND_SHIFT_LUMA);
+        break;
+    }
+    case SEQ_I_CHROMA:
+    {   /* one symbol carries the U and the V nibble, h4m:1103-1129 */
+        const int by = (int)(pos / (uint32_t)s->bw[1]), bx = (int)(pos % (uint32_t)s->bw[1]);
+        s->type[1][cell_at(s, 1, bx, by)] = sym & 0xF;
+        s->type[2][cell_at(s, 2, bx, by)] = (sym >> 4) & 0xF;
+        count_record(s, sym & 0xF, 1, by, SYM_BAND_SHIFT_CHROMA);
+        count_record(s, (sym >> 4) & 0xF, 1, by, SYM_BAND_SHIFT_CHROMA);
+        break;
+    }
+    case SEQ_PB_LUMA:
+    {   /* four luma blocks per listed macroblock, h4m:1689-1712 */
+        int32_t n = (int16_t)sym;
+        if (!n) break;
+        const uint32_t mcb = s->mcb_list[pos >> 2];
+        const int k = (int)(pos & 3), my = (int)(mcb / (uint32_t)s->mbw), mx = (int)(mcb % (uint32_t)s->mbw);
+        if (n & ~0xF)
+        {
+            H4E_ERR(s, SYM_ERR_MCB_TYPE);   /* would corrupt the macroblock bits, h4m:1701 */
+            n &= 0xF;
+        }
+        const uint8_t t = (uint8_t)(s->mcb_tag[mcb] | n);
+        s->type[0][cell_at(s, 0, mx * 2 + SUBX[k], my * 2 + SUBY[k])] = t;
+        count_record(s, t, 0, my * 2 + SUBY[k], SYM_BAND_SHIFT_LUMA);
+        break;
+    }
+    case SEQ_I_DC: case SEQ_I_DC + 1: case SEQ_I_DC + 2:
+    {   /* DC delta of a block, raster over plane p (IpicDcvDec, h4m:1132-1164); resolved by ipic_dcs_split */
+        const int p = seq - SEQ_I_DC;
+        const int by = (int)(pos / (uint32_t)s->bw[p]), bx = (int)(pos % (uint32_t)s->bw[p]);
+        s->dc[p][cell_at(s, p, bx, by)] = (uint8_t)sym;
+        break;
+    }
+    default:
+    {   /* one symbol per listed macroblock: U and V nibble, h4m:1714-1739 */
+        const int32_t n = (int16_t)sym;
+        if (!n) break;
+        const uint32_t mcb = s->mcb_list[pos];
+        const int my = (int)(mcb / (uint32_t)s->mbw), mx = (int)(mcb % (uint32_t)s->mbw);
+        const uint8_t tag = s->mcb_tag[mcb];
+        const uint8_t tu = (uint8_t)(tag | (n & 0xF)), tv = (uint8_t)(tag | ((n >> 4) & 0xF));
+        s->type[1][cell_at(s, 1, mx, my)] = tu;
+        s->type[2][cell_at(s, 2, mx, my)] = tv;
+        count_record(s, tu, 0, my, SYM_BAND_SHIFT_CHROMA);
+        count_record(s, tv, 0, my, SYM_BAND_SHIFT_CHROMA);
+        break;
+    }
+    }
+}
+
+/* Runs the automaton over a sequence of seq_len blocks whose cells already hold the "no symbol"
+   value.  Collective; bn / bnr are at position 0 (fresh from the flat decode). */
+H4E_FN void types_scatter(H4Seq *s, int seq, SymStream *bn, SymStream *bnr, uint32_t seq_len)
+{
+    const uint32_t total = runs_prefix(bnr);
+    H4E_SYNC();
+    uint32_t zbase = 0, used = 0, zused = 0;
+    for (uint32_t b = 0;; b += H4E_LANES)
+    {
+        const uint32_t j = b + (uint32_t)H4E_LANE;
+        const int32_t sym = ss_peek(bn, j);
+        const int isz = seq >= SEQ_I_DC ? sym == 0 : (int16_t)sym == 0;   /* h4m:1146 tests the full value */
+        uint32_t zs;
+        const uint32_t z = zbase + lane_scan((uint32_t)isz, &zs);
+        const uint32_t pos = j + runs_before(bnr, total, z);
+        const int act = pos < seq_len;
+        if (act) place_type(s, seq, pos, sym);
+        const uint32_t n_act = lane_count(act);
+        used += n_act;
+        zused += lane_count(act && isz);
+        zbase += zs;
+        if (n_act < H4E_LANES) break;                      /* pos(j) increases with j */
+    }
+    H4E_SYNC();
+    if (H4E_LANE == 0)
+    {   /* what the serial walk would have consumed */
+        if (used > bn->n && !bn->is_const) bn->over = 1;
+        if (zused > bnr->n && !bnr->is_const) bnr->over = 1;
+        bn->pos = used < bn->n ? used : bn->n;
+        bnr->pos = zused < bnr->n ? zused : bnr->n;
+    }
+}
+
+/* Ipic_BasisNumDec in the form above */
+H4E_FN void ipic_types_split(H4Seq *s)
+{
+    for (int p = 0; p < 3; ++p)
+        for (int by = H4E_LANE; by < s->bh[p]; by += H4E_LANES) memset(s->type[p] + cell_at(s, p, 0, by), 0, (size_t)s->bw[p]);
+    H4E_SYNC();
+    types_scatter(s, SEQ_I_LUMA, &s->q_bn[0], &s->q_bnr[0], (uint32_t)(s->bw[0] * s->bh[0]));
+    types_scatter(s, SEQ_I_CHROMA, &s->q_bn[1], &s->q_bnr[1], (uint32_t)(s->bw[1] * s->bh[1]));
+    H4E_SYNC();
+}
+
+/* value the lane below produced in the previous wavefront step */
+H4E_INL uint32_t lane_above(uint32_t v)
+{
+#if defined(H4E_DEVICE)
+    return __shfl_up_sync(0xFFFFFFFFu, v, 1);
+#else
+    return v;
+#endif
+}
+
+/* IpicDcvDec + getDeltaDC (h4m:1043-1058, 1132-1164) in two steps: the deltas land on their blocks
+   through the same automaton as the types (a zero delta is followed by a run of blocks without
+   one); then the predictor recurrence -- each block starts from the average of its left
+   neighbour and the block above its right neighbour -- runs as a wavefront, one row per lane,
+   each row two blocks behind the row above. */
+H4E_FN void ipic_dcs_split(H4Seq *s)
+{
+    for (int p = 0; p < 3; ++p)
+        for (int by = H4E_LANE; by < s->bh[p]; by += H4E_LANES) memset(s->dc[p] + cell_at(s, p, 0, by), 0, (size_t)s->bw[p]);
+    H4E_SYNC();
+    for (int p = 0; p < 3; ++p) types_scatter(s, SEQ_I_DC + p, &s->q_dcv[p], &s->q_rle[p], (uint32_t)(s->bw[p] * s->bh[p]));
+    H4E_SYNC();
+    for (int p = 0; p < 3; ++p)
+    {
+        const int bw = s->bw[p], bh = s->bh[p], steps = bw + 2 * (H4E_LANES - 1);
+        for (int r0 = 0; r0 < bh; r0 += H4E_LANES)
+        {
+            const int row = r0 + H4E_LANE;
+            uint8_t *cur = s->dc[p] + cell_at(s, p, 0, row < bh ? row : 0);
+            const uint8_t *up = cur - s->stride[p];
+            const uint32_t edge = cur[bw];                  /* border cell right of the row */
+            uint32_t v = 0, out = 0;
+            for (int t = 0; t < steps; ++t)
+            {
+                H4E_SYNC();
+                const int x = t - 2 * H4E_LANE;
+                uint32_t above = lane_above(out);           /* up[x + 1], stored by the lane above one step ago */
+                if (row < bh && x >= 0 && x < bw)
+                {
+                    if (H4E_LANE == 0) above = up[x + 1];   /* the row above belongs to the previous group */
+                    if (x == 0) v = up[0];
+                    v = (uint8_t)(v + cur[x]);
+                    cur[x] = (uint8_t)v;
+                    out = v;
+                    v = (uint8_t)((v + above + 1) >> 1);
+                }
+                else if (x >= bw)
+                    out = edge;
+            }
+        }
+    }
+    H4E_SYNC();
+}
+
+/* spread_PB_descMap in three steps: (1) one lane walks the macroblocks for what is serial per
+   macroblock -- type and proc runs (getMCBtype/getMCBproc), the DC chain of intra macroblocks
+   (decode_PB_dc) -- and lists the macroblocks that carry block types; (2) the tags are spread over
+   the maps; (3) the block types land through types_scatter */
+H4E_FN void pb_pass1_split(H4Seq *s)
+{
+    if (H4E_LANE == 0)
+    {
+        const HTab *tm = &s->tree[T_MCB];
+        RunLen proc = {0, 0}, type = {0, 0};
+        BR mcbp = s->mcbp, mcbt = s->mcbt;
+        SymStream dcv0 = s->q_dcv[0], dcv1 = s->q_dcv[1], dcv2 = s->q_dcv[2];
+        if (mcbp.base)
+        {
+            proc.value = br_bit(&mcbp);
+            proc.count = (uint32_t)ht_get_uovf(tm, &mcbp);
+        }
+        if (mcbt.base)
+        {
+            type.value = br_bits(&mcbt, 2);
+            type.count = (uint32_t)ht_get_uovf(tm, &mcbt);
+        }
+        else
+            s->err |= SYM_ERR_TRUNCATED;
+        uint32_t acc[3] = {0x7F, 0x7F, 0x7F}, n_list = 0, mcb = 0;
+        const int st0 = s->stride[0];
+        for (int my = 0; my < s->mbh; ++my)
+        {
+            uint8_t *dc0 = s->dc[0] + cell_at(s, 0, 0, my * 2);
+            uint8_t *dc1 = s->dc[1] + cell_at(s, 1, 0, my), *dc2 = s->dc[2] + cell_at(s, 2, 0, my);
+            for (int mx = 0; mx < s->mbw; ++mx, ++mcb)
+            {
+                if (type.count == 0 && mcbt.base)
+                {
+                    type.value = next_type[br_bit(&mcbt)][type.value & 3];
+                    type.count = (uint32_t)ht_get_uovf(tm, &mcbt);
+                }
+                --type.count;
+                uint32_t mt = type.value;
+                if (mt == 3 || (mt == 2 && s->pic_type == SYM_PIC_P))
+                {
+                    s->err |= SYM_ERR_MCB_TYPE;
+                    mt = 1;
+                }
+                uint32_t pr = 0;
+                if (mt == 0)
+                {
+                    const int lx = mx * 2;
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        acc[0] += (uint32_t)ss_get(&dcv0);
+                        dc0[SUBY[k] * st0 + lx + SUBX[k]] = (uint8_t)acc[0];
+                    }
+                    acc[1] += (uint32_t)ss_get(&dcv1);
+                    dc1[mx] = (uint8_t)acc[1];
+                    acc[2] += (uint32_t)ss_get(&dcv2);
+                    dc2[mx] = (uint8_t)acc[2];
+                }
+                else
+                {
+                    acc[0] = acc[1] = acc[2] = 0x7F;
+                    if (proc.count == 0 && mcbp.base)
+                    {
+                        proc.value ^= 1;
+                        proc.count = (uint32_t)ht_get_uovf(tm, &mcbp);
+                    }
+                    --proc.count;
+                    pr = proc.value & 1;
+                }
+                s->mcb_tag[mcb] = (uint8_t)(mt << 5 | pr << 4);
+                if (!pr) s->mcb_list[n_list++] = mcb;
+            }
+        }
+        s->n_list = n_list;
+        s->mcbp = mcbp; s->mcbt = mcbt;
+        s->q_dcv[0] = dcv0; s->q_dcv[1] = dcv1; s->q_dcv[2] = dcv2;
+    }
+    H4E_SYNC();
+    const int st0 = s->stride[0], n_mcb = s->mbw * s->mbh;
+    for (int mcb = H4E_LANE; mcb < n_mcb; mcb += H4E_LANES)
+    {
+        const int my = mcb / s->mbw, mx = mcb % s->mbw;
+        const uint8_t tag = s->mcb_tag[mcb];
+        uint8_t *ty0 = s->type[0] + cell_at(s, 0, mx * 2, my * 2);
+        ty0[0] = ty0[1] = ty0[st0] = ty0[st0 + 1] = tag;
+        s->type[1][cell_at(s, 1, mx, my)] = s->type[2][cell_at(s, 2, mx, my)] = tag;
+    }
+    H4E_SYNC();
+    types_scatter(s, SEQ_PB_LUMA, &s->q_bn[0], &s->q_bnr[0], 4 * s->n_list);
+    types_scatter(s, SEQ_PB_CHROMA, &s->q_bn[1], &s->q_bnr[1], s->n_list);
+    H4E_SYNC();
+}
+
 /* getMVector, h4m:1846-1860 */
 H4E_INL void read_mv(H4Seq *s, BR *b, int32_t *mv, int rbits)
 {
@@ -1414,65 +1755,84 @@ H4E_FN int mcb_refs_in_surface(const H4Seq *s, int32_t rx, int32_t ry, int needs
     return 1;
 }
 
-/* BpicPlaneDec pass 2, h4m:1922-1967, motion vectors only: the vector chain (getMVector) is the
-   serial part of pass 2; the records of the same macroblocks are scheduled by schedule_rows() */
+/* BpicPlaneDec pass 2, h4m:1922-1967, motion vectors only (the records of the same macroblocks
+   are scheduled by schedule_rows()).  The horizontal and the vertical component live in
+   separate sections and accumulate separately, so two lanes run the two serial chains
+   (getMVector) side by side into mv_raw; then all lanes turn the vectors into checked absolute
+   positions.  Needs mcb_tag, i.e. pb_pass1_split. */
 H4E_FN void pb_mvs(H4Seq *s, int16_t *mv_out)
 {
-    int32_t mvx = 0, mvy = 0;
-    int cur_ref = -1;
+    const int n_mcb = s->mbw * s->mbh;
+#if defined(H4E_DEVICE)
+    const int c_lo = H4E_LANE, c_hi = H4E_LANE < 2 ? H4E_LANE + 1 : 0;
+#else
+    const int c_lo = 0, c_hi = 2;
+#endif
+    for (int c = c_lo; c < c_hi; ++c)
+    {
+        BR b = c ? s->mvv : s->mvh;
+        int32_t mv = 0;
+        int cur_ref = -1;
+        for (int mcb = 0; mcb < n_mcb; ++mcb)
+        {
+            const int mt = (s->mcb_tag[mcb] >> 5) & 3;
+            if (mt)
+            {
+                if (mt - 1 != cur_ref)
+                {   /* h4m:1943-1949 */
+                    cur_ref = mt - 1;
+                    mv = 0;
+                }
+                read_mv(s, &b, &mv, s->rb[cur_ref][c]);
+            }
+            s->mv_raw[2 * mcb + c] = mv;
+        }
+        if (c) s->mvv = b;
+        else s->mvh = b;
+    }
+    H4E_SYNC();
     const int st0 = s->stride[0];
     uint32_t n_inter = 0;
-    BR mvh = s->mvh, mvv = s->mvv;
-    for (int my = 0; my < s->mbh; ++my)
+    for (int m0 = 0; m0 < n_mcb; m0 += H4E_LANES)
     {
-        const uint8_t *ty0 = s->type[0] + cell_at(s, 0, 0, my * 2);
-        const uint8_t *ty1 = s->type[1] + cell_at(s, 1, 0, my), *ty2 = s->type[2] + cell_at(s, 2, 0, my);
-        for (int mx = 0; mx < s->mbw; ++mx)
+        const int mcb = m0 + H4E_LANE;
+        int inter = 0;
+        if (mcb < n_mcb)
         {
-            const int lx = mx * 2;
-            const uint8_t tag = ty0[lx];
-            int16_t *mvp = mv_out + 2 * ((size_t)my * s->mbw + mx);
-            const int mt = (tag >> 5) & 3;
-            if (mt == 0)
-            {
-                mvp[0] = mvp[1] = 0;
-                continue;
-            }
-            const int ref = mt - 1;
-            ++n_inter;
-            if (ref != cur_ref)
-            {   /* h4m:1943-1949 */
-                cur_ref = ref;
-                mvx = mvy = 0;
-            }
-            read_mv(s, &mvh, &mvx, s->rb[ref][0]);
-            read_mv(s, &mvv, &mvy, s->rb[ref][1]);
-            const int32_t rx = mx * 16 + mvx, ry = my * 16 + mvy;   /* h4m:1954-1955 */
-            int needs_window = 0;
-            if (!(tag & 0x10))
-            {   /* a PrediAot block with bases reads the 70x38 window around the vector (h4m:1334-1348) */
-                const uint32_t t6[6] = {ty0[lx], ty0[st0 + lx], ty0[st0 + lx + 1], ty0[lx + 1], ty1[mx], ty2[mx]};
-                for (int k = 0; k < 6; ++k)
-                {
-                    const uint32_t nib = t6[k] & 0xF;
-                    if (nib > 1 && nib != 6) needs_window = 1;
-                }
-            }
-            if (rx < -32000 || rx > 32000 || ry < -32000 || ry > 32000 || !mcb_refs_in_surface(s, rx, ry, needs_window))
-            {
-                s->err |= SYM_ERR_MV_RANGE;
-                mvp[0] = mvp[1] = -32768;   /* poison: recon.cu paints the macroblock grey */
-            }
+            const int my = mcb / s->mbw, mx = mcb % s->mbw, lx = mx * 2;
+            const uint8_t tag = s->mcb_tag[mcb];
+            int16_t *mvp = mv_out + 2 * (size_t)mcb;
+            inter = ((tag >> 5) & 3) != 0;
+            if (!inter) mvp[0] = mvp[1] = 0;
             else
             {
-                mvp[0] = (int16_t)rx;
-                mvp[1] = (int16_t)ry;
+                const int32_t rx = mx * 16 + s->mv_raw[2 * mcb], ry = my * 16 + s->mv_raw[2 * mcb + 1];   /* h4m:1954-1955 */
+                int needs_window = 0;
+                if (!(tag & 0x10))
+                {   /* a PrediAot block with bases reads the 70x38 window around the vector (h4m:1334-1348) */
+                    const uint8_t *ty0 = s->type[0] + cell_at(s, 0, lx, my * 2);
+                    const uint32_t t6[6] = {ty0[0], ty0[st0], ty0[st0 + 1], ty0[1], s->type[1][cell_at(s, 1, mx, my)], s->type[2][cell_at(s, 2, mx, my)]};
+                    for (int k = 0; k < 6; ++k)
+                    {
+                        const uint32_t nib = t6[k] & 0xF;
+                        if (nib > 1 && nib != 6) needs_window = 1;
+                    }
+                }
+                if (rx < -32000 || rx > 32000 || ry < -32000 || ry > 32000 || !mcb_refs_in_surface(s, rx, ry, needs_window))
+                {
+                    H4E_ERR(s, SYM_ERR_MV_RANGE);
+                    mvp[0] = mvp[1] = -32768;   /* poison: recon.cu paints the macroblock grey */
+                }
+                else
+                {
+                    mvp[0] = (int16_t)rx;
+                    mvp[1] = (int16_t)ry;
+                }
             }
         }
+        n_inter += lane_count(inter);
     }
-    s->n_inter_mcb = n_inter;
-    s->mvh = mvh;
-    s->mvv = mvv;
+    if (H4E_LANE == 0) s->n_inter_mcb = n_inter;
 }
 
 /* BpicPlaneDec pass 2, h4m:1922-1967, symbol part only: vectors and records in ONE walk.  This is
@@ -1699,22 +2059,43 @@ H4E_FN void begin_flat(H4Seq *s, int is_i)
 #endif
 }
 
-/* serial: maps (I) or pass 1 (P/B), record groups, blob plan */
+/* maps (I) or pass 1 (P/B), record groups, blob plan */
 H4E_FN void begin_maps(H4Seq *s, int is_i)
 {
     PROF_T0();
-    reset_record_counts(s);
+    if (H4E_LANE == 0) reset_record_counts(s);
+    H4E_SYNC();
+#if defined(H4E_DEVICE)
+    const int split = 1;
+#else
+    const int split = s->split_schedule;
+#endif
     if (is_i)
     {
-        ipic_types(s);
-        ipic_dcs(s);
-        make_nest(s, s->nest_x, s->nest_y);
+        if (split)
+        {
+            ipic_types_split(s);
+            ipic_dcs_split(s);
+        }
+        else
+        {
+            ipic_types(s);
+            ipic_dcs(s);
+        }
+        if (H4E_LANE == 0) make_nest(s, s->nest_x, s->nest_y);
     }
+    else if (split)
+        pb_pass1_split(s);
     else
         pb_pass1(s);
+    H4E_SYNC();
     PROF_ADD(1);
-    plan_records(s, is_i);
-    plan_blob(s);
+    if (H4E_LANE == 0)
+    {
+        plan_records(s, is_i);
+        plan_blob(s);
+    }
+    H4E_SYNC();
     PROF_ADD(2);
 }
 
@@ -1730,8 +2111,7 @@ H4E_API size_t h4e_parse_begin(H4Seq *s, int pic_type, const uint8_t *pic, size_
         H4E_SYNC();
         PROF_ADD(5);
     }
-    if (H4E_LANE == 0) begin_maps(s, is_i);
-    H4E_SYNC();
+    begin_maps(s, is_i);
     return s->blob_bytes;
 }
 
@@ -1746,13 +2126,14 @@ H4E_FN void finish_schedule(H4Seq *s, uint8_t *blob)
         s->rec_base = (uint32_t *)(blob + h->off_rec);
         s->cur_work = work_scratch(s, s->n_records);
         if (!s->cur_work && s->n_records) s->err |= SYM_ERR_OVERFLOW;
-#if defined(H4E_DEVICE)
-        else if (!is_i) pb_mvs(s, (int16_t *)(blob + h->off_mv));
-#endif
     }
     H4E_SYNC();
-    PROF_ADD(7);
     if (!s->cur_work && s->n_records) return;
+#if defined(H4E_DEVICE)
+    if (!is_i) pb_mvs(s, (int16_t *)(blob + h->off_mv));
+    H4E_SYNC();
+#endif
+    PROF_ADD(7);
     Cursors cur;
     for (int p = 0; p < 3; ++p)
     {

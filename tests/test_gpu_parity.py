@@ -204,3 +204,64 @@ def test_gpu_entropy_stage_other_geometries(native_lib, golden, name):
     data = synth.generate(**case["args"])
     got = [md5(frames[0][2]) for frames in native_lib.decode_streams([data, data], gpu_entropy=True)]
     assert got == case["md5"]
+
+
+def _decode_damaged(native_lib, files, gpu_entropy):
+    """Decodes damaged streams through the batch runtime, tolerating stream-error bits."""
+    parsed = [native_lib.parse_file(f) for f in files]
+    info = parsed[0][0]
+    n = len(files)
+    bufs = [ctypes.create_string_buffer(f, len(f) + 8) for f in files]
+    bases = [ctypes.addressof(b) for b in bufs]
+    batch = native_lib.Batch(n, info.width, info.height, info.version, gpu_entropy=gpu_entropy)
+    frames, bits = [], 0
+    try:
+        for k in range(len(parsed[0][1])):
+            frs = [p[1][k] for p in parsed]
+            for call in (lambda: batch.decode(list(range(n)), [f.frame_type for f in frs],
+                                              [bases[i] + frs[i].offset for i in range(n)], [f.bytes for f in frs]),
+                         batch.sync):
+                try:
+                    call()
+                except native_lib.HVQM4Error as e:
+                    assert e.bits < (1 << 16), f"runtime error, not a stream error: {e}"
+                    bits |= e.bits
+            frames.append([batch.read_frame(i) for i in range(n)])
+    finally:
+        batch.close()
+    return frames, bits
+
+
+@pytest.mark.parametrize("profile", [0, 1])
+def test_gpu_entropy_stage_equals_host_stage_on_damaged_streams(native_lib, profile):
+    """Bit-flipped pictures (I, P and B): whatever the host stage makes of them -- clamped types,
+    exhausted sections, poisoned vectors -- the warp-parallel GPU build of the same code must
+    make the same frames and raise the same error bits."""
+    import numpy as np
+    rng = np.random.default_rng(99 + profile)
+    files = []
+    for i in range(6):
+        data = bytearray(synth.generate(320, 240, 15, "IPBBPB", 1, seed=900 + i, profile=profile))
+        _, recs = native_lib.parse_file(bytes(data))
+        for fr in recs:
+            if i == 0:
+                continue                                    # one intact stream
+            for _ in range(1 + 4 * (i % 3)):
+                at = fr.offset + int(rng.integers(76, fr.bytes))
+                data[at] ^= 1 << int(rng.integers(0, 8))
+        files.append(bytes(data))
+    host, host_bits = _decode_damaged(native_lib, files, False)
+    dev, dev_bits = _decode_damaged(native_lib, files, True)
+    assert host == dev
+    assert host_bits == dev_bits and host_bits != 0
+    assert native_lib.lib().HVQM4GetLastCudaError() == 0
+
+
+def test_gpu_entropy_stage_matches_oracle_on_fresh_seeds(native_lib, oracle):
+    files = [synth.generate(320, 240, 15 if seed % 2 else 13, "IPBBPBB", 1, seed=7100 + seed, profile=(seed // 2) % 2)
+             for seed in range(2)]
+    # same geometry and version per batch: two batches
+    for data in files:
+        want = [yuv for _, _, _, yuv in oracle.PortDecoder(data).frames()]
+        got = [frames[0][2] for frames in native_lib.decode_streams([data, data, data], gpu_entropy=True)]
+        assert got == want

@@ -53,8 +53,8 @@ print(f"gpu_entropy={GPU_ENTROPY} S={S} threads={T or os.cpu_count()} d2h={D2H} 
 if GPU_ENTROPY:
     prof = (ctypes.c_uint64 * 8)()
     api.lib().HVQM4DevEntropyProfile(prof)
-    names = ["hdr+trees", "pass1", "plan", "pass2 schedule", "copies", "flat decode", "fill records"]
-    tot = sum(prof[:7]) or 1
+    names = ["hdr+trees", "pass1", "plan", "schedule", "copies", "flat decode", "fill records", "vector chain"]
+    tot = sum(prof[:8]) or 1
     npic = S * 16 * (GOPS + 1)
     print("   GPU parser, per picture: " + ", ".join(f"{nm} {prof[i] / npic / 1.9e3:.0f} us ({100 * prof[i] / tot:.0f}%)" for i, nm in enumerate(names)))
 batch.close()
