@@ -113,6 +113,7 @@ H4E_INL void br_refill(BR *b)
             const uintptr_t a = (uintptr_t)b->p;
             const unsigned long long *q = (const unsigned long long *)(a & ~(uintptr_t)7);
             const unsigned sh = (unsigned)(a & 7) * 8;
+            if (!((uintptr_t)q & 127)) asm volatile("prefetch.global.L1 [%0];" ::"l"(q + 32));   /* two lines ahead */
             const unsigned long long lo = q[0], hi = q[1];
             const unsigned long long x = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
             w = (uint64_t)__byte_perm((unsigned)x, 0, 0x0123) << 32 | __byte_perm((unsigned)(x >> 32), 0, 0x0123);
@@ -268,7 +269,8 @@ H4E_FN void ht_read(HTab *t, BR *leader, uint32_t leader_size, int is_signed, in
 H4E_INL int32_t ht_get(const HTab *t, BR *b)
 {
     if (b->n < 32) br_refill(b);
-    HEnt e = t->tab[b->buf >> (64 - HT_BITS)];
+    HEnt e;
+    memcpy(&e, &t->tab[b->buf >> (64 - HT_BITS)], sizeof e);   /* one 32-bit load */
     b->buf <<= e.len;
     b->n -= e.len;
     if (!e.walk) return e.val;
@@ -435,6 +437,92 @@ H4E_FN void ss_decode_lane(SymStream *q, const HTab *t, BR *b, int sovf, int32_t
             v = q->v;
             cap = q->cap - 8;
             live = br_pos(&x) < end_bits;
+        }
+    }
+    /* Fast part: a 2 x 32-bit window fed by aligned words and a plain count of the bits left,
+       while the section still holds more bits than any symbol can take (a code is at most 256
+       deep); the generic reader below finishes the tail, where bits past the end must read as 0. */
+    {
+        const int64_t left64 = end_bits - br_pos(&x);
+        int fast = live && left64 > 600 && left64 < (1ll << 30);
+        if (fast)
+        {   /* word-align the read pointer: hand whole bytes of the window back (the sections that
+               lead with their tree arrive with a full window), or feed single bytes forward */
+            const int k = (int)((uintptr_t)x.p & 3);
+            if (k && x.n >= 8 * k)
+            {
+                x.p -= k;
+                x.n -= 8 * k;
+            }
+            while (((uintptr_t)x.p & 3) && x.n <= 56)
+            {
+                x.buf |= (uint64_t)*x.p++ << (56 - x.n);
+                x.n += 8;
+            }
+            fast = !((uintptr_t)x.p & 3);
+        }
+        uint32_t whi = (uint32_t)(x.buf >> 32), wlo = (uint32_t)x.buf;
+        int nb = x.n, left = fast ? (int)left64 : 0;
+        const uint32_t *wp = (const uint32_t *)x.p;
+        const uint32_t *tab32 = t ? (const uint32_t *)t->tab : 0;
+        fast = fast && left > 600 && n < cap;
+        if (fast)
+        {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(wp));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + 32));
+        }
+        while (fast)
+        {
+            if (nb <= 32)
+            {
+                /* the lanes run in lock step, so every lane's cache miss stalls all of them:
+                   fetch each 128-byte line of the section two lines ahead of its first use */
+                if (!((uintptr_t)wp & 127)) asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + 64));
+                const uint32_t w = __byte_perm(*wp++, 0, 0x0123);
+                whi |= __funnelshift_rc(w, 0, nb);
+                wlo = __funnelshift_rc(0, w, nb);
+                nb += 32;
+            }
+            const uint32_t e = tab32[whi >> (32 - HT_BITS)];
+            const uint32_t len = (e >> 16) & 0xFF;
+            int32_t a = (int16_t)(e & 0xFFFF);
+            whi = __funnelshift_l(wlo, whi, len);
+            wlo <<= len;
+            nb -= (int)len;
+            left -= (int)len;
+            if (e >> 24)
+            {   /* code longer than the table: walk the tree bit by bit */
+                int node = a;
+                while (node >= 256)
+                {
+                    if (nb == 0)
+                    {
+                        whi = __byte_perm(*wp++, 0, 0x0123);
+                        wlo = 0;
+                        nb = 32;
+                    }
+                    const uint32_t bit = whi >> 31;
+                    whi = __funnelshift_l(wlo, whi, 1);
+                    wlo <<= 1;
+                    --nb;
+                    --left;
+                    node = t->kid[bit][node - 256];
+                }
+                a = t->leaf[node];
+            }
+            sum += a;
+            const int done = !sovf || (a > lo && a < hi);
+            v[n] = sum;
+            n += (uint32_t)done;
+            sum = done ? 0 : sum;
+            fast = left > 600 && n < cap;
+        }
+        if (v)
+        {
+            x.buf = (uint64_t)whi << 32 | wlo;
+            x.n = nb;
+            x.p = (const uint8_t *)wp;
+            live = live && br_pos(&x) < end_bits && n < cap;
         }
     }
     while (live)
@@ -793,7 +881,6 @@ H4E_INL void count_record(H4Seq *s, uint32_t t, int is_ipic, int by, int band_sh
     const int g = group_of(s, cls, by >> band_shift, len);
     H4E_FETCH_ADD(&s->grp_count[g], 1);
     if (len >= SYM_LEN_BUCKETS) H4E_FETCH_ADD(&s->grp_base[g], len);   /* long-bucket word total, see plan_records */
-    H4E_FETCH_ADD(&s->n_records, 1);
 }
 
 H4E_FN void reset_record_counts(H4Seq *s)
@@ -855,6 +942,7 @@ H4E_FN void plan_records(H4Seq *s, int is_ipic)
         if (cls == SYM_REC_INTRA) s->n_chunks_nest = chunk;
     }
     s->n_rec_words = word;
+    s->n_records = ord;
     s->n_chunks = chunk;
     s->need_nest = is_ipic ? 1 : need_nest;
 }
@@ -1611,82 +1699,192 @@ H4E_FN void ipic_dcs_split(H4Seq *s)
     H4E_SYNC();
 }
 
-/* spread_PB_descMap in three steps: (1) one lane walks the macroblocks for what is serial per
-   macroblock -- type and proc runs (getMCBtype/getMCBproc), the DC chain of intra macroblocks
-   (decode_PB_dc) -- and lists the macroblocks that carry block types; (2) the tags are spread over
-   the maps; (3) the block types land through types_scatter */
+/* inclusive running maximum of v over the lanes */
+H4E_INL uint32_t lane_scan_max(uint32_t v, uint32_t *last)
+{
+#if defined(H4E_DEVICE)
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (H4E_LANE >= d && o > v) v = o;
+    }
+    *last = __shfl_sync(0xFFFFFFFFu, v, 31);
+    return v;
+#else
+    *last = v;
+    return v;
+#endif
+}
+
+/* One run-length coded macroblock attribute -- getMCBtype (h4m:1596-1611, with initMCBtype
+   h4m:1551-1559) or getMCBproc (h4m:1613-1628, initMCBproc h4m:1561-1569) -- for `need`
+   macroblocks, as run starts + values.  Serial, but only one step per RUN.  Reads exactly what
+   the per-macroblock loop would: a run is fetched when a macroblock finds the count at zero, the
+   initial run may be empty, and a later zero count wraps around to "the rest". */
+H4E_FN uint32_t mcb_runs(H4Seq *s, BR *b, int is_type, uint32_t need, uint32_t *start, uint32_t *value)
+{
+    if (!b->base)
+    {   /* no section: value 0 for everybody (the reference would use an uninitialised type here) */
+        if (is_type) s->err |= SYM_ERR_TRUNCATED;
+        start[0] = 0;
+        value[0] = 0;
+        return need ? 1 : 0;
+    }
+    const HTab *tm = &s->tree[T_MCB];
+    uint32_t val = br_bits(b, is_type ? 2 : 1), cnt = (uint32_t)ht_get_uovf(tm, b), n = 0, total = 0;
+    for (int first = 1; total < need; first = 0)
+    {
+        if (cnt || !first)
+        {
+            start[n] = total;
+            value[n] = val;
+            ++n;
+            if (cnt == 0 || cnt >= need - total) break;
+            total += cnt;
+        }
+        val = is_type ? next_type[br_bit(b)][val & 3] : val ^ 1;
+        cnt = (uint32_t)ht_get_uovf(tm, b);
+    }
+    return n;
+}
+
+/* value of the run that covers element j (binary search over the run starts) */
+H4E_INL uint32_t run_value_at(const uint32_t *start, const uint32_t *value, uint32_t n, uint32_t j)
+{
+    uint32_t lo = 0, hi = n;          /* start[lo] <= j < start[hi] */
+    while (hi - lo > 1)
+    {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (start[mid] <= j) lo = mid;
+        else hi = mid;
+    }
+    return value[lo];
+}
+
+/* inclusive prefix sums (mod 2^32) of the first `count` values, in place */
+H4E_FN void vals_prefix(SymStream *q, uint32_t count)
+{
+    if (count > q->n) count = q->n;
+    uint32_t carry = 0;
+    for (uint32_t b = 0; b < count; b += H4E_LANES)
+    {
+        const uint32_t i = b + (uint32_t)H4E_LANE;
+        const uint32_t v = i < count ? (uint32_t)q->v[i] : 0;
+        uint32_t sum;
+        const uint32_t inc = carry + lane_scan(v, &sum) + v;
+        if (i < count) q->v[i] = (int32_t)inc;
+        carry += sum;
+    }
+}
+
+/* sum of values 0..j of a stream whose first `count` values went through vals_prefix; what lies
+   past the end of the section reads as ss_get() would give it */
+H4E_INL uint32_t prefix_at(const SymStream *q, uint32_t j)
+{
+    if (j < q->n) return (uint32_t)q->v[j];
+    const uint32_t base = q->n ? (uint32_t)q->v[q->n - 1] : 0;
+    return q->is_const ? base + (j - q->n + 1) * (uint32_t)q->cval : base;
+}
+
+/* spread_PB_descMap (h4m:1742-1776), data-parallel:
+   (1) the type runs, expanded over the macroblocks; (2) the proc runs, expanded over the
+   macroblocks that are not intra; (3) the DC chains of the intra macroblocks (decode_PB_dc,
+   h4m:1649-1668: every maximal run of intra macroblocks accumulates from 0x7F) as differences
+   of prefix sums; (4) the tags spread over the maps; (5) the block types through types_scatter
+   (decode_PB_cc).  Only the run decode of (1) and (2) is serial. */
 H4E_FN void pb_pass1_split(H4Seq *s)
 {
-    if (H4E_LANE == 0)
+    const uint32_t n_all = (uint32_t)(s->mbw * s->mbh);
+    uint32_t *run_start = (uint32_t *)s->mv_raw, *run_value = run_start + n_all;   /* mv_raw is free until pass 2 */
+    /* (1) */
+    if (H4E_LANE == 0) s->n_list = mcb_runs(s, &s->mcbt, 1, n_all, run_start, run_value);
+    H4E_SYNC();
+    uint32_t n_inter = 0;
     {
-        const HTab *tm = &s->tree[T_MCB];
-        RunLen proc = {0, 0}, type = {0, 0};
-        BR mcbp = s->mcbp, mcbt = s->mcbt;
-        SymStream dcv0 = s->q_dcv[0], dcv1 = s->q_dcv[1], dcv2 = s->q_dcv[2];
-        if (mcbp.base)
+        const uint32_t n_runs = s->n_list;
+        for (uint32_t m0 = 0; m0 < n_all; m0 += H4E_LANES)
         {
-            proc.value = br_bit(&mcbp);
-            proc.count = (uint32_t)ht_get_uovf(tm, &mcbp);
-        }
-        if (mcbt.base)
-        {
-            type.value = br_bits(&mcbt, 2);
-            type.count = (uint32_t)ht_get_uovf(tm, &mcbt);
-        }
-        else
-            s->err |= SYM_ERR_TRUNCATED;
-        uint32_t acc[3] = {0x7F, 0x7F, 0x7F}, n_list = 0, mcb = 0;
-        const int st0 = s->stride[0];
-        for (int my = 0; my < s->mbh; ++my)
-        {
-            uint8_t *dc0 = s->dc[0] + cell_at(s, 0, 0, my * 2);
-            uint8_t *dc1 = s->dc[1] + cell_at(s, 1, 0, my), *dc2 = s->dc[2] + cell_at(s, 2, 0, my);
-            for (int mx = 0; mx < s->mbw; ++mx, ++mcb)
+            const uint32_t mcb = m0 + (uint32_t)H4E_LANE;
+            uint32_t mt = 0;
+            if (mcb < n_all)
             {
-                if (type.count == 0 && mcbt.base)
-                {
-                    type.value = next_type[br_bit(&mcbt)][type.value & 3];
-                    type.count = (uint32_t)ht_get_uovf(tm, &mcbt);
-                }
-                --type.count;
-                uint32_t mt = type.value;
+                mt = run_value_at(run_start, run_value, n_runs, mcb);
                 if (mt == 3 || (mt == 2 && s->pic_type == SYM_PIC_P))
-                {
-                    s->err |= SYM_ERR_MCB_TYPE;
+                {   /* type 3 indexes outside mcbtypetrans in the reference; type 2 in a P picture
+                       would predict from the picture being written (h4m:2060) */
+                    H4E_ERR(s, SYM_ERR_MCB_TYPE);
                     mt = 1;
                 }
-                uint32_t pr = 0;
-                if (mt == 0)
+                s->mcb_tag[mcb] = (uint8_t)(mt << 5);
+            }
+            uint32_t sum;
+            const uint32_t at = n_inter + lane_scan(mt != 0, &sum);
+            if (mt) s->mcb_list[at] = mcb;                 /* the macroblocks that own a proc flag, in order */
+            n_inter += sum;
+        }
+    }
+    H4E_SYNC();
+    /* (2) */
+    if (H4E_LANE == 0) s->n_list = mcb_runs(s, &s->mcbp, 0, n_inter, run_start, run_value);
+    H4E_SYNC();
+    {
+        const uint32_t n_runs = s->n_list;
+        for (uint32_t j = (uint32_t)H4E_LANE; j < n_inter; j += H4E_LANES)
+            if (run_value_at(run_start, run_value, n_runs, j) & 1) s->mcb_tag[s->mcb_list[j]] |= 0x10;
+    }
+    H4E_SYNC();
+    /* (3) + the list of macroblocks that carry block types */
+    const uint32_t n_intra = n_all - n_inter;
+    vals_prefix(&s->q_dcv[0], 4 * n_intra);
+    vals_prefix(&s->q_dcv[1], n_intra);
+    vals_prefix(&s->q_dcv[2], n_intra);
+    H4E_SYNC();
+    {
+        const int st0 = s->stride[0];
+        uint32_t seen_intra = 0, seg_carry = 0, n_list = 0;
+        for (uint32_t m0 = 0; m0 < n_all; m0 += H4E_LANES)
+        {
+            const uint32_t mcb = m0 + (uint32_t)H4E_LANE;
+            const uint32_t tag = mcb < n_all ? s->mcb_tag[mcb] : 0x20;
+            const int intra = (tag >> 5) == 0, typed = mcb < n_all && !(tag & 0x10);
+            uint32_t sum, last;
+            const uint32_t idx = seen_intra + lane_scan(intra, &sum);
+            seen_intra += sum;
+            /* 1 + index of the first macroblock of this intra run, carried along the run */
+            const int opens = intra && (mcb == 0 || (s->mcb_tag[mcb - 1] >> 5) != 0);
+            uint32_t seg = lane_scan_max(opens ? idx + 1 : 0, &last);
+            if (seg < seg_carry) seg = seg_carry;
+            seg_carry = last > seg_carry ? last : seg_carry;
+            if (intra)
+            {
+                const uint32_t first = seg - 1;
+                const int my = (int)(mcb / (uint32_t)s->mbw), mx = (int)(mcb % (uint32_t)s->mbw);
+                const uint32_t b0 = first ? prefix_at(&s->q_dcv[0], 4 * first - 1) : 0;
+                uint8_t *dc0 = s->dc[0] + cell_at(s, 0, mx * 2, my * 2);
+                for (int k = 0; k < 4; ++k)
+                    dc0[SUBY[k] * st0 + SUBX[k]] = (uint8_t)(0x7F + prefix_at(&s->q_dcv[0], 4 * idx + (uint32_t)k) - b0);
+                for (int p = 1; p < 3; ++p)
                 {
-                    const int lx = mx * 2;
-                    for (int k = 0; k < 4; ++k)
-                    {
-                        acc[0] += (uint32_t)ss_get(&dcv0);
-                        dc0[SUBY[k] * st0 + lx + SUBX[k]] = (uint8_t)acc[0];
-                    }
-                    acc[1] += (uint32_t)ss_get(&dcv1);
-                    dc1[mx] = (uint8_t)acc[1];
-                    acc[2] += (uint32_t)ss_get(&dcv2);
-                    dc2[mx] = (uint8_t)acc[2];
+                    const uint32_t bp = first ? prefix_at(&s->q_dcv[p], first - 1) : 0;
+                    s->dc[p][cell_at(s, p, mx, my)] = (uint8_t)(0x7F + prefix_at(&s->q_dcv[p], idx) - bp);
                 }
-                else
-                {
-                    acc[0] = acc[1] = acc[2] = 0x7F;
-                    if (proc.count == 0 && mcbp.base)
-                    {
-                        proc.value ^= 1;
-                        proc.count = (uint32_t)ht_get_uovf(tm, &mcbp);
-                    }
-                    --proc.count;
-                    pr = proc.value & 1;
-                }
-                s->mcb_tag[mcb] = (uint8_t)(mt << 5 | pr << 4);
-                if (!pr) s->mcb_list[n_list++] = mcb;
+            }
+            const uint32_t at = n_list + lane_scan((uint32_t)typed, &sum);
+            n_list += sum;
+            if (typed) s->mcb_list[at] = mcb;              /* (2) is done with the old contents */
+        }
+        H4E_SYNC();
+        if (H4E_LANE == 0)
+        {
+            s->n_list = n_list;
+            for (int p = 0; p < 3; ++p)
+            {
+                SymStream *q = &s->q_dcv[p];
+                const uint32_t used = p ? n_intra : 4 * n_intra;
+                if (used > q->n && !q->is_const) q->over = 1;
+                q->pos = used < q->n ? used : q->n;
             }
         }
-        s->n_list = n_list;
-        s->mcbp = mcbp; s->mcbt = mcbt;
-        s->q_dcv[0] = dcv0; s->q_dcv[1] = dcv1; s->q_dcv[2] = dcv2;
     }
     H4E_SYNC();
     const int st0 = s->stride[0], n_mcb = s->mbw * s->mbh;

@@ -52,6 +52,39 @@ def test_split_schedule_builds_the_same_symbol_buffer(emul_lib, args):
         emul_lib.h4e_seq_destroy(seq)
 
 
+def test_split_schedule_equals_serial_walk_on_damaged_pictures(emul_lib):
+    """Same comparison on bit-flipped and truncated pictures: exhausted sections, zero-length runs,
+    clamped types and poisoned vectors must come out of the prefix-sum forms exactly as out of
+    the serial loops -- same bytes, same error bits."""
+    rng = np.random.default_rng(5)
+    checked = flagged = 0
+    for seed, profile in ((31, 0), (32, 1), (33, 1)):
+        version, w, h, recs = demux(synth.generate(320, 240, 15, "IPBPB", 1, seed=seed, profile=profile))
+        for trial in range(10):
+            seqs = [emul_lib.h4e_seq_create(w, h, 2, 2, 1) for _ in range(2)]
+            emul_lib.h4e_seq_set_split_schedule(seqs[1], 1)
+            for ty, _, pic in recs:
+                bad = bytearray(pic)
+                if trial % 5 == 4:
+                    bad = bad[: max(80, len(bad) * (1 + trial) // 12)]
+                else:
+                    for _ in range(1 + 6 * (trial % 4)):
+                        bad[int(rng.integers(0, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+                buf = bytes(bad) + b"\0" * 24
+                out = []
+                for seq in seqs:
+                    n = emul_lib.h4e_parse_begin(seq, ty, buf, len(bad))
+                    blob = np.zeros(max(n, 1), np.uint8)
+                    err = emul_lib.h4e_parse_finish(seq, blob.ctypes.data) if n else -1
+                    out.append((n, err, blob.tobytes()))
+                assert out[0] == out[1], (seed, trial, ty)
+                checked += 1
+                flagged += out[0][1] != 0
+            for seq in seqs:
+                emul_lib.h4e_seq_destroy(seq)
+    assert checked == 150 and flagged > 20
+
+
 def test_truncated_and_corrupt_pictures_raise_error_bits_not_crashes(emul_lib):
     """The reference has no input validation; the host stage must stay in bounds."""
     data = synth.generate(320, 240, 15, "IPB", 1, seed=42, profile=0)
