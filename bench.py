@@ -16,8 +16,11 @@ Printed JSON (one line, rank 0):
              kernels of a GOP replayed K times, timed with CUDA events on the launching
              stream inside the library (HVQM4BatchReplay), max over ranks.
   e2e        same metric through the C ABI with HOST buffers: bitstreams in host memory ->
-             host entropy threads -> pinned symbol arena -> H2D -> kernels -> D2H of every
-             decoded frame into pinned host memory, all inside the timed region.
+             H2D of the raw pictures -> entropy stage on the GPU (entropy.c compiled as device
+             code, one warp per picture) -> reconstruction kernels -> D2H of every decoded frame
+             into pinned host memory, all inside the timed region.
+  e2e_host_entropy  the same with the entropy stage on host threads (north_star's layout):
+             host threads -> pinned symbol arena -> H2D -> kernels -> D2H.
   roofline   recon kernel: algorithmic bytes per launch (frame bytes written + reference
              bytes of inter macroblocks + symbol bytes read) / measured launch time,
              against the measured HBM copy peak of MEASURED_PEAKS.json.
@@ -293,39 +296,57 @@ def main():
     achieved_gbs = alg_bytes_per_gop / n_pics / (launch_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak_gbs()
 
-    # ---- end to end through the C ABI with host buffers
+    # ---- end to end through the C ABI with host buffers, once per entropy-stage placement
     e2e = None
+    e2e_host = None
     e2e_launches = 0
     if not args.no_e2e:
-        def one_gop():
-            for st in steps:
-                batch.decode_prepared(st)
-                batch.read_frames_async(ids_arr, S, pinned, frame_bytes)
-        tw0 = time.perf_counter()
-        one_gop()
-        batch.sync()
-        est = max_over_ranks(time.perf_counter() - tw0)
-        # the end-to-end region is host bound; keep it near 25 s whatever K and the core count are
-        e2e_steps = max(2, min(args.steps, int(25.0 / max(est, 1e-3))))
-        for _ in range(min(args.warmup, 3) - 1):
+        def measure_e2e(b, seconds, what):
+            """K GOPs through HVQM4BatchDecode + HVQM4BatchReadFramesAsync: bitstreams in host memory in,
+            every decoded frame in pinned host memory out, wall clock, max over ranks."""
+            nonlocal e2e_launches
+
+            def one_gop():
+                for st in steps:
+                    b.decode_prepared(st)
+                    b.read_frames_async(ids_arr, S, pinned, frame_bytes)
+            up0 = b.stats()["symbol_bytes"]
+            tw0 = time.perf_counter()
             one_gop()
-        batch.sync()
-        barrier()
-        launches1 = api.kernel_launches()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            one_gop()
-        batch.sync()
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        windows.append((t0, t1))
-        e2e_s = max_over_ranks(t1 - t0)
-        barrier()
-        e2e_launches = api.kernel_launches() - launches1
-        e2e = {"value": world * frames_per_step * e2e_steps / e2e_s, "unit": UNIT,
-               "h2d_bytes_per_step": sym_bytes_per_gop, "d2h_bytes_per_step": frames_per_step * frame_bytes,
-               "host_threads_per_gpu": threads, "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
-               "note": "wall clock around K GOPs: host entropy + H2D + kernels + D2H of every frame to pinned host memory"}
+            b.sync()
+            est = max_over_ranks(time.perf_counter() - tw0)
+            h2d = b.stats()["symbol_bytes"] - up0
+            k = max(2, min(args.steps, int(seconds / max(est, 1e-3))))
+            for _ in range(min(args.warmup, 3) - 1):
+                one_gop()
+            b.sync()
+            barrier()
+            l0 = api.kernel_launches()
+            t0 = time.perf_counter()
+            for _ in range(k):
+                one_gop()
+            b.sync()
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            windows.append((t0, t1))
+            sec = max_over_ranks(t1 - t0)
+            barrier()
+            e2e_launches += api.kernel_launches() - l0
+            return {"value": world * frames_per_step * k / sec, "unit": UNIT,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": frames_per_step * frame_bytes,
+                    "ms_per_step": 1e3 * sec / k, "steps": k, "entropy_stage": what}
+
+        # (a) the layout BASELINE.json's north_star describes: entropy stage on host threads
+        e2e_host = measure_e2e(batch, 12.0, "host threads")
+        e2e_host["host_threads_per_gpu"] = threads
+        e2e_host["note"] = ("wall clock around K GOPs: host entropy threads -> pinned symbol arena -> H2D -> kernels -> "
+                            "D2H of every frame to pinned host memory")
+        # (b) the same C source compiled as device code (entropy_dev.cu): raw pictures up, frames down
+        gb = api.Batch(S, W, H, 15, device=local, host_threads=threads, gpu_entropy=True)
+        e2e = measure_e2e(gb, 12.0, "gpu (one warp per picture)")
+        e2e["note"] = ("wall clock around K GOPs: raw picture bytes H2D -> entropy stage on the GPU -> reconstruction kernels -> "
+                       "D2H of every frame to pinned host memory; HVQM4BatchSetEntropyMode(1)")
+        gb.close()
     sampler.stop()
     clocks = sampler.summary(windows)
 
@@ -404,6 +425,8 @@ def main():
                          "frac_of_nominal_8TBs": achieved_gbs / 8000.0},
             "e2e": e2e, "gpu_launches": int(recon_launches + e2e_launches), "clocks": clocks,
         }
+        if e2e_host:
+            line["e2e_host_entropy"] = e2e_host
         if realistic:
             line["realistic_profile"] = realistic
         if single:

@@ -443,7 +443,9 @@ H4_API int HVQM4BatchSetEntropyMode(HVQM4Batch *b, int gpu)
     if (!b->d_estate)
     {
         const uint32_t blocks = (uint32_t)(b->mcb_w * b->mcb_h * 6);
-        const uint32_t sym_cap = blocks * 2 > 32768u ? blocks * 2 : 32768u, work_cap = blocks;
+        /* 16 symbols per block of a section's plane: every type an encoder emits fits (a block has
+           at most 15 bases); a pathological section beyond that is flagged HVQM4_ERR_TRUNCATED */
+        const uint32_t sym_cap = 16, work_cap = blocks;
         b->eslot = hvqm4_dev_entropy_slot_bytes(b->width, b->height, sym_cap, work_cap);
         if (!b->eslot) return HVQM4_ERR_GEOMETRY;
         b->blobs_cap = (size_t)b->n_streams * align_up(2 * b->frame_bytes, 256);

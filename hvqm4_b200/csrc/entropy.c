@@ -721,8 +721,9 @@ H4E_FN void seq_set_dims(H4Seq *s, int width, int height, int version15)
 }
 
 /* Assigns every per-stream array a slice of one allocation (mem == NULL: only measures).
-   sym_cap / work_cap: fixed capacities of the flat symbol streams and of the record schedule
-   (GPU build; the host build grows those on demand and passes 0). */
+   sym_cap / work_cap: fixed capacities of the flat symbol streams (symbols per block of the
+   section's plane) and of the record schedule (GPU build; the host build grows those on demand
+   and passes 0).  A section with more symbols than its capacity decodes as truncated. */
 H4E_FN size_t seq_carve(H4Seq *s, uint8_t *mem, uint32_t sym_cap, uint32_t work_cap)
 {
     size_t at = 0;
@@ -746,10 +747,14 @@ H4E_FN size_t seq_carve(H4Seq *s, uint8_t *mem, uint32_t sym_cap, uint32_t work_
     {
         SymStream *all[13] = {&s->q_bn[0], &s->q_bn[1], &s->q_bnr[0], &s->q_bnr[1], &s->q_dcv[0], &s->q_dcv[1], &s->q_dcv[2],
                               &s->q_sc[0], &s->q_sc[1], &s->q_sc[2], &s->q_rle[0], &s->q_rle[1], &s->q_rle[2]};
+        /* plane of every section above: bn/bnr 1 carry the U and V nibbles of the chroma blocks */
+        static const uint8_t plane_of[13] = {0, 1, 0, 1, 0, 1, 2, 0, 1, 2, 0, 1, 2};
         for (int i = 0; i < 13; ++i)
         {
-            CARVE(all[i]->v, int32_t, sym_cap);
-            if (mem) all[i]->cap = sym_cap;
+            const int p = plane_of[i];
+            const uint32_t cap = (uint32_t)(s->bw[p] * s->bh[p]) * sym_cap + 1024;
+            CARVE(all[i]->v, int32_t, cap);
+            if (mem) all[i]->cap = cap;
         }
     }
     if (work_cap)
