@@ -5,13 +5,14 @@
  * in ~1 us, one host core parses it in ~0.6 ms.  A picture's parse is serial, but a batch has a
  * thousand independent pictures, so the same C code is compiled here as __device__ functions
  * (entropy.c is #include'd with H4E_DEVICE; see the macro block at its top) and run with ONE
- * PICTURE PER WARP: lane 0 executes the serial parts of the parser exactly as a host thread
- * would, against per-stream state that lives in device memory; the parts that are parallel
- * inside a picture -- the flat decode of the symbol sections (one section per lane), the
- * group-ordered record fill and the map copies -- use all lanes.  The symbol buffer is written
- * straight into a device arena that the reconstruction kernel reads next.  Nothing but the raw picture bytes
- * crosses PCIe on the way in.  A single lane is slow (~10x a host core) but there are thousands
- * of warp slots; what matters is that the whole step's pictures parse concurrently.
+ * PICTURE PER WARP against per-stream state that lives in device memory.  The entry points are
+ * warp-collective: lane 0 runs what is inherently serial (section table, trees, run decode), the
+ * rest uses all lanes -- one symbol section per lane in SIMT lock step, block types and DC
+ * values through prefix sums, record scheduling by rows, lane-strided fill and copies (DESIGN.md
+ * section 4c has the table).  The symbol buffer is written straight into a device arena that the
+ * reconstruction kernel reads next; nothing but the raw picture bytes crosses PCIe on the way in.
+ * A warp is latency bound (~8 ms per dense picture) but a step keeps a thousand of them in
+ * flight.
  *
  * Because it is the same source, parity with the host stage (and through it with the reference)
  * is structural; tests/test_gpu_parity.py still checks the decoded frames in this mode.
