@@ -66,6 +66,7 @@ SIGNATURES = {
     "HVQM4GetLastCudaError": (c_int, []),
     "HVQM4ReleaseBuffer": (None, [POINTER(SeqObj)]),
     "HVQM4InvalidateFrame": (None, [POINTER(SeqObj), c_void_p]),
+    "HVQM4ConvertRGB": (c_int, [POINTER(SeqObj), c_void_p, c_void_p]),
     "HVQM4BatchCreate": (c_void_p, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "HVQM4BatchDestroy": (None, [c_void_p]),
     "HVQM4BatchDecode": (c_int, [c_void_p, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_void_p), POINTER(c_uint32)]),
@@ -75,6 +76,7 @@ SIGNATURES = {
     "HVQM4BatchReadFrame": (c_int, [c_void_p, c_int, c_void_p]),
     "HVQM4BatchReadFrameAsync": (c_int, [c_void_p, c_int, c_void_p]),
     "HVQM4BatchReadFramesAsync": (c_int, [c_void_p, c_int, POINTER(c_int32), c_void_p, c_size_t]),
+    "HVQM4BatchReadFramesRGBAsync": (c_int, [c_void_p, c_int, POINTER(c_int32), c_void_p, c_size_t]),
     "HVQM4BatchFramePtr": (c_void_p, [c_void_p, c_int]),
     "HVQM4BatchRecord": (c_int, [c_void_p, c_int]),
     "HVQM4BatchReplay": (c_float, [c_void_p, c_int]),
@@ -131,6 +133,7 @@ class SeqDecoder:
         l.HVQM4SetBuffer(ctypes.byref(self.seq), self._work)
         if l.HVQM4SetVersion(ctypes.byref(self.seq), version) != 0:
             raise HVQM4Error(ERR_ARGUMENT, "unsupported geometry or version")
+        self.width, self.height = width, height
         self.frame_bytes = width * height * 3 // 2
 
     def close(self):
@@ -165,11 +168,24 @@ class SeqDecoder:
         self._check()
 
 
+    def to_rgb(self, frame) -> bytes:
+        """The reference's dumpRGB (h4m:895-926) of a planar frame (a buffer passed to decode(), or bytes)."""
+        out = (c_uint8 * (self.width * self.height * 3))()
+        if isinstance(frame, (bytes, bytearray)):
+            frame = (c_uint8 * len(frame)).from_buffer_copy(frame)
+        rc = lib().HVQM4ConvertRGB(ctypes.byref(self.seq), frame, out)
+        if rc:
+            raise HVQM4Error(rc, "HVQM4ConvertRGB")
+        return bytes(out)
+
+
 class Player:
     """The reference's decode_video() loop minus file output: demux + buffer rotation + SDK calls."""
 
-    def __init__(self, data: bytes):
+    def __init__(self, data: bytes, rgb: bool = False):
         self.data = data
+        self.rgb = rgb
+        self.last_rgb = None
         self.info, self.frames = parse_file(data)
         self.dec = SeqDecoder(self.info.width, self.info.height, self.info.version, self.info.h_samp, self.info.v_samp)
         n = self.dec.frame_bytes
@@ -184,6 +200,7 @@ class Player:
                 self.past, self.future = self.future, self.past
             pic = self.data[fr.offset: fr.offset + fr.bytes]
             self.dec.decode(t, pic, self.present, self.past, self.future)
+            self.last_rgb = self.dec.to_rgb(self.present) if self.rgb else None   # dumpRGB, h4m:2126
             yield t, fr.disp_id, bytes(self.present)
             if t != B_FRAME:
                 self.present, self.future = self.future, self.present
@@ -205,6 +222,7 @@ class Batch:
             if rc:
                 raise HVQM4Error(rc, "HVQM4BatchSetEntropyMode")
         self.n_streams = n_streams
+        self.width, self.height = width, height
         self.frame_bytes = width * height * 3 // 2
         self._keep = None
 
@@ -262,6 +280,21 @@ class Batch:
         rc = lib().HVQM4BatchReadFramesAsync(self._h, n, ids_array, host_base, host_stride)
         if rc:
             raise HVQM4Error(rc, "HVQM4BatchReadFramesAsync")
+
+    def read_frames_rgb_async(self, ids_array, n: int, host_base: int, host_stride: int):
+        """The reference's dumpRGB of the last decoded picture of n streams, into (pinned) host memory."""
+        rc = lib().HVQM4BatchReadFramesRGBAsync(self._h, n, ids_array, host_base, host_stride)
+        if rc:
+            raise HVQM4Error(rc, "HVQM4BatchReadFramesRGBAsync")
+
+    def read_frames_rgb(self, stream_ids) -> list:
+        n = len(stream_ids)
+        size = self.width * self.height * 3
+        out = (c_uint8 * (n * size))()
+        self.read_frames_rgb_async((c_int32 * n)(*stream_ids), n, ctypes.addressof(out), size)
+        self.sync()
+        raw = bytes(out)
+        return [raw[i * size:(i + 1) * size] for i in range(n)]
 
     def frame_ptr(self, stream_id: int) -> int:
         return lib().HVQM4BatchFramePtr(self._h, stream_id)

@@ -217,6 +217,13 @@ struct HVQM4Batch
     unsigned long long *d_blob_used = nullptr;
     uint32_t *d_eerrors = nullptr;
 
+    /* RGB read-back (HVQM4BatchReadFramesRGBAsync): staging frames + two rings of surface pointers */
+    uint8_t *d_rgb = nullptr;
+    const uint8_t **h_rgb_src[2] = {nullptr, nullptr};
+    const uint8_t **d_rgb_src[2] = {nullptr, nullptr};
+    cudaEvent_t ev_rgb_src[2] = {nullptr, nullptr}, ev_rgb = nullptr;
+    int rgb_cur = 0;
+
     uint8_t *surface(int stream, int idx) const { return d_surfaces + ((size_t)stream * 3 + idx) * surf_stride; }
 };
 
@@ -314,6 +321,14 @@ H4_API void HVQM4BatchDestroy(HVQM4Batch *b)
         if (a.consumed) cudaEventDestroy(a.consumed);
     }
     if (b->d_surfaces) cudaFree(b->d_surfaces);
+    if (b->d_rgb) cudaFree(b->d_rgb);
+    for (int i = 0; i < 2; ++i)
+    {
+        if (b->h_rgb_src[i]) cudaFreeHost((void *)b->h_rgb_src[i]);
+        if (b->d_rgb_src[i]) cudaFree((void *)b->d_rgb_src[i]);
+        if (b->ev_rgb_src[i]) cudaEventDestroy(b->ev_rgb_src[i]);
+    }
+    if (b->ev_rgb) cudaEventDestroy(b->ev_rgb);
     if (b->d_estate) cudaFree(b->d_estate);
     if (b->d_blobs) cudaFree(b->d_blobs);
     if (b->d_blob_used) cudaFree(b->d_blob_used);
@@ -653,6 +668,58 @@ H4_API int HVQM4BatchReadFrame(HVQM4Batch *b, int stream_id, void *host_dst)
     return cuda_ok(cudaStreamSynchronize(b->s_d2h), "sync d2h") ? HVQM4_OK : HVQM4_ERR_CUDA;
 }
 
+/* dumpRGB (h4m:895-926) for the last decoded picture of n streams: conversion kernel on the
+   compute stream (behind the reconstruction it reads), then one pitched copy on the read-back stream */
+H4_API int HVQM4BatchReadFramesRGBAsync(HVQM4Batch *b, int n, const int32_t *stream_ids, void *host_base, size_t host_stride)
+{
+    if (!b) return HVQM4_ERR_ARGUMENT;
+    const size_t rgb_bytes = (size_t)b->width * b->height * 3;
+    if (n <= 0 || n > b->n_streams || !stream_ids || !host_base || host_stride < rgb_bytes) return HVQM4_ERR_ARGUMENT;
+    for (int i = 0; i < n; ++i)
+        if (stream_ids[i] < 0 || stream_ids[i] >= b->n_streams || b->st[stream_ids[i]].last < 0) return HVQM4_ERR_ARGUMENT;
+    cudaSetDevice(b->device);
+    if (!b->d_rgb)
+    {
+        bool ok = cuda_ok(cudaMalloc((void **)&b->d_rgb, rgb_bytes * b->n_streams), "cudaMalloc(rgb staging)") &&
+                  cuda_ok(cudaEventCreateWithFlags(&b->ev_rgb, cudaEventDisableTiming), "cudaEventCreate");
+        for (int i = 0; i < 2 && ok; ++i)
+            ok = cuda_ok(cudaHostAlloc((void **)&b->h_rgb_src[i], sizeof(void *) * b->n_streams, cudaHostAllocDefault), "cudaHostAlloc") &&
+                 cuda_ok(cudaMalloc((void **)&b->d_rgb_src[i], sizeof(void *) * b->n_streams), "cudaMalloc") &&
+                 cuda_ok(cudaEventCreateWithFlags(&b->ev_rgb_src[i], cudaEventDisableTiming), "cudaEventCreate");
+        if (!ok) return HVQM4_ERR_NOMEM;
+    }
+    const int r = b->rgb_cur;
+    b->rgb_cur ^= 1;
+    cudaEventSynchronize(b->ev_rgb_src[r]);               /* the copy that last used this pointer ring is done */
+    for (int i = 0; i < n; ++i) b->h_rgb_src[r][i] = b->surface(stream_ids[i], b->st[stream_ids[i]].last);
+    if (b->d2h_pending)
+    {   /* the staging frames may still be on their way out */
+        cudaStreamWaitEvent(b->s_comp, b->ev_d2h, 0);
+        b->d2h_pending = false;
+    }
+    if (!cuda_ok(cudaMemcpyAsync((void *)b->d_rgb_src[r], (const void *)b->h_rgb_src[r], sizeof(void *) * n, cudaMemcpyHostToDevice, b->s_comp),
+                 "cudaMemcpyAsync(frame pointers)"))
+        return HVQM4_ERR_CUDA;
+    cudaEventRecord(b->ev_rgb_src[r], b->s_comp);
+    const int rc = hvqm4_rgb_launch(b->d_rgb_src[r], n, b->d_rgb, rgb_bytes, b->width, b->height, b->s_comp);
+    if (rc != 0)
+    {
+        cuda_ok((cudaError_t)rc, "yuv2rgb kernel launch");
+        return HVQM4_ERR_CUDA;
+    }
+    ++g_launches;
+    b->stats[1] += 1;
+    cudaEventRecord(b->ev_rgb, b->s_comp);
+    cudaEventRecord(b->ev_kernel, b->s_comp);
+    cudaStreamWaitEvent(b->s_d2h, b->ev_rgb, 0);
+    if (!cuda_ok(cudaMemcpy2DAsync(host_base, host_stride, b->d_rgb, rgb_bytes, rgb_bytes, (size_t)n, cudaMemcpyDeviceToHost, b->s_d2h),
+                 "cudaMemcpy2DAsync(D2H rgb)"))
+        return HVQM4_ERR_CUDA;
+    cudaEventRecord(b->ev_d2h, b->s_d2h);
+    b->d2h_pending = true;
+    return HVQM4_OK;
+}
+
 H4_API int HVQM4BatchRecord(HVQM4Batch *b, int enable)
 {
     if (!b) return HVQM4_ERR_ARGUMENT;
@@ -735,6 +802,7 @@ struct Compat
     size_t frame_bytes = 0, surf_bytes = 0;
     int mcb_w = 0, mcb_h = 0;
     uint8_t *h_blob = nullptr, *d_blob = nullptr;   /* job descriptor (256 B) + blob */
+    uint8_t *d_rgb = nullptr;                       /* HVQM4ConvertRGB staging */
     size_t blob_cap = 0;
     Twin twin[kTwins];
     uint64_t clock = 0;
@@ -926,6 +994,7 @@ H4_API void HVQM4ReleaseBuffer(SeqObj *seqobj)
         if (t.dev) cudaFree(t.dev);
     if (c->h_blob) cudaFreeHost(c->h_blob);
     if (c->d_blob) cudaFree(c->d_blob);
+    if (c->d_rgb) cudaFree(c->d_rgb);
     h4e_seq_destroy(c->seq);
     delete c;
     static_cast<WorkHeader *>(seqobj->state)->magic = 0;
@@ -966,6 +1035,41 @@ H4_API void HVQM4InvalidateFrame(SeqObj *seqobj, void *host_frame)
             t.host = nullptr;
             t.stamp = 0;
         }
+}
+
+/* dumpRGB (h4m:895-926) of one frame: `frame` is a planar picture of this SeqObj's geometry (host
+   pointer: uploaded; device pointer: used in place); `rgb` receives width * height * 3 bytes of
+   interleaved R, G, B in host memory. */
+H4_API int HVQM4ConvertRGB(SeqObj *seqobj, const void *frame, void *rgb)
+{
+    Compat *c = compat_of(seqobj);
+    if (!c || !frame || !rgb) return HVQM4_ERR_ARGUMENT;
+    if (!have_device() || !c->stream) return HVQM4_ERR_NO_DEVICE;
+    const size_t rgb_bytes = (size_t)c->width * c->height * 3;
+    /* staging: [RGB frame | surface pointer | planar input].  A host frame is always uploaded:
+       the cached device twins are keyed by address only, and nothing says this buffer still
+       holds what the decoder wrote there. */
+    const size_t ptr_off = align_up(rgb_bytes, 256), in_off = ptr_off + 256;
+    if (!c->d_rgb && !cuda_ok(cudaMalloc((void **)&c->d_rgb, in_off + c->surf_bytes), "cudaMalloc(rgb)")) return HVQM4_ERR_NOMEM;
+    const uint8_t *src = static_cast<const uint8_t *>(frame);
+    bool ok = true;
+    if (!is_device_ptr(frame))
+    {
+        src = c->d_rgb + in_off;
+        ok = cuda_ok(cudaMemcpyAsync(c->d_rgb + in_off, frame, c->frame_bytes, cudaMemcpyHostToDevice, c->stream), "upload frame");
+    }
+    const uint8_t **d_ptr = reinterpret_cast<const uint8_t **>(c->d_rgb + ptr_off);
+    ok = ok && cuda_ok(cudaMemcpyAsync((void *)d_ptr, &src, sizeof src, cudaMemcpyHostToDevice, c->stream), "cudaMemcpyAsync");
+    ok = ok && cuda_ok(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");   /* &src is a stack address */
+    if (ok)
+    {
+        const int rc = hvqm4_rgb_launch(d_ptr, 1, c->d_rgb, rgb_bytes, c->width, c->height, c->stream);
+        ok = rc == 0 || cuda_ok((cudaError_t)rc, "yuv2rgb kernel launch");
+        if (rc == 0) ++g_launches;
+    }
+    ok = ok && cuda_ok(cudaMemcpyAsync(rgb, c->d_rgb, rgb_bytes, cudaMemcpyDeviceToHost, c->stream), "download rgb");
+    ok = ok && cuda_ok(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
+    return ok ? HVQM4_OK : HVQM4_ERR_CUDA;
 }
 
 H4_API void HVQM4DecodeIpic(SeqObj *seqobj, uint8_t const *frame, void *present)

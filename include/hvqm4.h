@@ -116,6 +116,12 @@ void HVQM4ReleaseBuffer(SeqObj *seqobj);
    the host address.  Call this if the application modified such a buffer itself. */
 void HVQM4InvalidateFrame(SeqObj *seqobj, void *host_frame);
 
+/* dumpRGB (h4m:895-926) of one frame through the GPU: `frame` is a planar picture of
+   width * height * 3 / 2 bytes (host buffer: uploaded; device pointer: used in place); `rgb`
+   (host) receives width * height * 3 bytes of interleaved R, G, B, identical to the reference's
+   PPM payload.  Returns HVQM4_OK or HVQM4_ERR_* bits. */
+int HVQM4ConvertRGB(SeqObj *seqobj, const void *frame, void *rgb);
+
 /* ---------------------------------------------------------------- batched decoding
  * A batch is a pool of `n_streams` independent streams of identical geometry living on
  * one GPU: three device-resident frame surfaces per stream (past/present/future, rotated
@@ -166,6 +172,15 @@ int HVQM4BatchReadFrameAsync(HVQM4Batch *b, int stream_id, void *host_dst);
 
 /* Same for n streams: frame of stream_ids[i] goes to host_base + i * host_stride. */
 int HVQM4BatchReadFramesAsync(HVQM4Batch *b, int n, const int32_t *stream_ids, void *host_base, size_t host_stride);
+
+/*
+ * The reference's only observable output is every decoded frame converted to RGB (dumpRGB,
+ * h4m:895-926, called from decode_video at h4m:2126: JPEG matrix in float, chroma replicated,
+ * truncation, clamp).  Same result, bit for bit, from a conversion kernel on the GPU: the last
+ * decoded picture of stream_ids[i] arrives at host_base + i * host_stride as width * height * 3
+ * bytes of interleaved R, G, B.
+ */
+int HVQM4BatchReadFramesRGBAsync(HVQM4Batch *b, int n, const int32_t *stream_ids, void *host_base, size_t host_stride);
 
 /* Device pointer of the most recently decoded picture of a stream (zero-copy consumers). */
 void *HVQM4BatchFramePtr(HVQM4Batch *b, int stream_id);

@@ -76,8 +76,20 @@ class _Decoder:
             getattr(lib, p + "bench").argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
             getattr(lib, p + "bench_mp").argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
             getattr(lib, p + "bench_mp").restype = ctypes.c_int
+            getattr(lib, p + "yuv_to_rgb").argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+            getattr(lib, p + "yuv_to_rgb").restype = ctypes.c_int
             cls._libs[cls._path] = lib
         return lib
+
+    @classmethod
+    def yuv_to_rgb(cls, yuv: bytes, width: int, height: int) -> bytes:
+        """Planar Y|U|V 4:2:0 -> interleaved RGB exactly as the reference's dumpRGB (h4m:895-926)."""
+        assert len(yuv) == width * height * 3 // 2
+        out = (ctypes.c_uint8 * (width * height * 3))()
+        rc = getattr(cls._lib(), cls._prefix + "yuv_to_rgb")(yuv, width, height, out)
+        if rc:
+            raise RuntimeError(f"yuv_to_rgb failed ({rc})")
+        return bytes(out)
 
     def close(self):
         if self._h:

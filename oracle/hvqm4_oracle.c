@@ -912,3 +912,23 @@ PORT_API int port_bench_mp(const uint8_t *data, size_t len, int nproc, int reps,
     free(pipes); free(pids);
     return rc;
 }
+
+/* ---- planar 4:2:0 -> interleaved RGB as the reference's dumpRGB does it (h4m:895-926): JPEG
+   matrix in single-precision float, chroma replicated 2x2 (no interpolation), results truncated
+   towards zero and clamped to 0..255.  Returns 0 (same contract as ref_yuv_to_rgb). ---- */
+static uint8_t rgb_clamp(float f) { return f < 0 ? 0 : f > 255 ? 255 : (uint8_t)f; }   /* h4m:896-899 */
+
+PORT_API int port_yuv_to_rgb(const uint8_t *yuv, int w, int h, uint8_t *rgb)
+{
+    const uint8_t *yp = yuv, *up = yp + (size_t)w * h, *vp = up + (size_t)w * h / 4;
+    for (int i = 0; i < h; ++i)
+        for (int j = 0; j < w; ++j)
+        {
+            const float y = yp[(size_t)i * w + j];
+            const float u = up[(size_t)(i / 2) * (w / 2) + j / 2], v = vp[(size_t)(i / 2) * (w / 2) + j / 2];
+            *rgb++ = rgb_clamp(y + 1.402f * (v - 128.f));                                  /* h4m:918 */
+            *rgb++ = rgb_clamp(y - 0.34414f * (u - 128.f) - 0.71414f * (v - 128.f));       /* h4m:919 */
+            *rgb++ = rgb_clamp(y + 1.772f * (u - 128.f));                                  /* h4m:920 */
+        }
+    return 0;
+}

@@ -423,3 +423,25 @@ REF_API void ref_tables(int32_t div[16], int32_t mcdiv[512])
     memcpy(div, divTable, sizeof divTable);
     memcpy(mcdiv, mcdivTable, sizeof mcdivTable);
 }
+
+/* ---- the reference's only observable output: dumpRGB (h4m:895-926), run on a caller-supplied frame.
+   It writes a binary PPM; the pixel payload after the "P6\n<w> <h>\n255\n" header is returned. ---- */
+REF_API int ref_yuv_to_rgb(const uint8_t *yuv, int w, int h, uint8_t *rgb)
+{
+    char path[64];
+    snprintf(path, sizeof path, "/tmp/hvqm4_ref_rgb_%d.ppm", (int)getpid());
+    Player pl;
+    memset(&pl, 0, sizeof pl);
+    pl.seqobj.width = (uint16_t)w;
+    pl.seqobj.height = (uint16_t)h;
+    pl.present = (void *)yuv;
+    dumpRGB(&pl, path);
+    FILE *f = fopen(path, "rb");
+    if (!f) return -1;
+    int pw = 0, ph = 0, maxv = 0, rc = -2;
+    if (fscanf(f, "P6 %d %d %d", &pw, &ph, &maxv) == 3 && pw == w && ph == h && maxv == 255 && fgetc(f) == '\n')
+        rc = fread(rgb, 1, (size_t)w * h * 3, f) == (size_t)w * h * 3 ? 0 : -3;
+    fclose(f);
+    unlink(path);
+    return rc;
+}

@@ -60,3 +60,21 @@ def emul_decode(lib, data: bytes):
 
 def md5(b: bytes) -> str:
     return hashlib.md5(b).hexdigest()
+
+
+def all_triples_pictures():
+    """Eight 2048x1024 planar 4:2:0 pictures that together contain every (y, u, v) byte triple:
+    the chroma planes enumerate the 65536 (u, v) pairs eight times over, and the 4 luma samples
+    of a 2x2 tile x 8 copies x 8 pictures enumerate the 256 luma values.  Yields (yuv, w, h)."""
+    import numpy as np
+    w, h = 2048, 1024
+    idx = np.arange((w // 2) * (h // 2), dtype=np.uint32)
+    u = (idx & 0xFF).astype(np.uint8).tobytes()
+    v = ((idx >> 8) & 0xFF).astype(np.uint8).tobytes()
+    copy = (idx >> 16).reshape(h // 2, w // 2)                      # 0..7
+    for pic in range(8):
+        y = np.empty((h, w), np.uint8)
+        for dy in range(2):
+            for dx in range(2):
+                y[dy::2, dx::2] = ((pic * 8 + copy) * 4 + dy * 2 + dx).astype(np.uint8)
+        yield y.tobytes() + u + v, w, h

@@ -89,3 +89,16 @@ def test_reference_constants_and_sat_mean8_quirk(oracle):
     assert out[5] == 255
     lib.ref_WeightImBlock(out, 4, 0, 0, 2, 0, 1)
     assert out[5] == 0
+
+
+def test_rgb_conversion_port_equals_reference_on_every_triple(oracle):
+    """dumpRGB (h4m:895-926) on pictures that together hold all 2^24 (y, u, v) triples: the port
+    must equal the reference build (which also pins that FMA contraction cannot matter here)."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from tests.h4m_util import all_triples_pictures
+    n = 0
+    for yuv, w, h in all_triples_pictures():
+        assert oracle.RefDecoder.yuv_to_rgb(yuv, w, h) == oracle.PortDecoder.yuv_to_rgb(yuv, w, h)
+        n += 1
+    assert n == 8
