@@ -417,7 +417,7 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
     {
         ++g_launches;
         b->stats[1] += 1;
-        rc = hvqm4_recon_launch_band(d_jobs, n, b->mcb_h, b->s_comp);
+        rc = hvqm4_recon_launch_band(d_jobs, n, b->mcb_w, b->mcb_h, b->s_comp);
         if (rc == 0)
         {
             ++g_launches;

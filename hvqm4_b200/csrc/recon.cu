@@ -225,18 +225,119 @@ recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs, uint32_t cta_
 
 /* ------------------------------------------------------------------------------------------
  * band kernel (large batches): one CTA reconstructs one BAND (SYM_BAND_MCB_ROWS macroblock rows)
- * of one picture completely -- the map work of its segments, a block barrier, then exactly the
- * records that lie in the band (the host groups records per band, symbuf.h).  The sectors the
- * record work rewrites, and the reference rows both phases read, are then still in L2/L1
- * instead of making a second round trip to HBM between two kernels.
+ * of one picture completely -- its map work, a block barrier, then exactly the records that lie
+ * in the band (the host groups records per band, symbuf.h).  The sectors the record work
+ * rewrites, and the reference rows both phases read, are then still in L2/L1 instead of making a
+ * second round trip to HBM between two kernels.
+ *
+ * Map work is CLASS-SORTED: a warp that takes 32 neighbouring blocks as they come runs the
+ * weighted-fill code, the motion-compensation code and the flat fill one after the other with
+ * a third of its lanes each (measured: 15 of 32 lanes active, 63 % of the kernel's
+ * instructions).  Instead every warp first walks the type map of its block rows (coalesced byte
+ * loads, one block per lane), finishes flat blocks on the spot, and pushes the other blocks into
+ * its private shared-memory queue -- weighted blocks from the front, motion-compensated blocks
+ * from the back, positions from a ballot -- and then drains 32 entries of ONE class at a time.
+ * Wide pictures are walked in column tiles of kTileMcbs macroblocks so that the queue has a
+ * fixed upper size.
  * ------------------------------------------------------------------------------------------ */
 constexpr int kBandWarps = 8;
+constexpr int kTileMcbs = 128;
+
+/* queue capacity of one warp in entries: its four block rows (two luma, one U, one V) of one column tile */
+static inline int band_queue_entries(int mcb_w)
+{
+    return (mcb_w < kTileMcbs ? mcb_w : kTileMcbs) * 6;
+}
+
+__device__ __forceinline__ uint8_t *block_dst(const ReconView &v, int plane, int bx, int by, int &pw)
+{
+    pw = plane ? v.width >> 1 : v.width;
+    const int plane_off = plane == 0 ? 0 : plane == 1 ? v.width * v.height : v.width * v.height + (v.width >> 1) * (v.height >> 1);
+    return v.present + (uint32_t)(plane_off + (by * 4) * pw + bx * 4);
+}
+
+/* map work of macroblock rows [row0, row1) x macroblock columns [mx0, mx1) of the CTA's picture.
+   Every warp owns up to four block rows (two luma, one U, one V) and a private queue of `cap`
+   entries: no atomics, no block barrier, counters in (warp-uniform) registers. */
+__device__ __forceinline__ void band_map_tile(const ReconView &v, int row0, int row1, int mx0, int mx1, uint32_t *q, int cap)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const bool ipic = v.is_ipic != 0;
+    uint32_t n_w = 0, n_mc = 0;
+    /* classify: row tasks = 2 luma block rows per macroblock row, then the U rows, then the V rows */
+    const int mrows = row1 - row0, n_tasks = mrows * 4;
+#pragma unroll 1
+    for (int task = warp; task < n_tasks; task += kBandWarps)
+    {
+        const int plane = task < 2 * mrows ? 0 : task < 3 * mrows ? 1 : 2;
+        const int by = plane == 0 ? row0 * 2 + task : row0 + (task - (plane + 1) * mrows);
+        const int sh = plane ? 0 : 1;
+        const int x0 = mx0 << sh, x1 = mx1 << sh;
+        const int pw = v.width >> (plane ? 1 : 0), bstride = (pw >> 2) + 2;
+        const uint8_t *trow = v.blob + (rc_pick3(v.off_type, plane) + (by + 1) * bstride + 1);
+        const uint8_t *drow = v.blob + (rc_pick3(v.off_dc, plane) + (by + 1) * bstride + 1);
+        int pw2;
+        uint8_t *dst_row = block_dst(v, plane, 0, by, pw2);
+        const uint32_t entry_row = sym_record_header(0, plane, 0, by);
+#pragma unroll 1
+        for (int xb = x0; xb < x1; xb += 32)
+        {
+            const int bx = xb + lane;
+            /* lanes past the row end get type 6 (raw: nothing to do here) */
+            const uint32_t t = bx < x1 ? __ldg(trow + bx) : 6u;
+            const bool inter = !ipic && (t & 0x60);
+            const uint32_t nib = ipic ? t : (t & 0xF);
+            const bool is_w = !inter && nib == 0;
+            const bool is_mc = inter && ((t & 0x10) || nib != 6);
+            const uint32_t entry = entry_row + ((uint32_t)bx << 10) + t;
+            const uint32_t m_w = __ballot_sync(0xFFFFFFFFu, is_w), m_mc = __ballot_sync(0xFFFFFFFFu, is_mc);
+            if (is_w) q[n_w + __popc(m_w & lt)] = entry;
+            if (is_mc) q[cap - 1 - (int)(n_mc + __popc(m_mc & lt))] = entry;
+            n_w += __popc(m_w);
+            n_mc += __popc(m_mc);
+            if (!inter && nib == 8)
+            {   /* flat fill, h4m:281 */
+                const uint32_t V = __ldg(drow + bx) * 0x01010101u;
+                uint8_t *dst = dst_row + bx * 4;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = V;
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (uint32_t i = lane; i < n_w; i += 32)
+    {
+        uint32_t t, rows[4];
+        int plane, bx, by, pw;
+        rc_record_coords(q[i], t, plane, bx, by);
+        rc_weighted_block(v, plane, bx, by, rows);
+        uint8_t *dst = block_dst(v, plane, bx, by, pw);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];
+    }
+#pragma unroll 1
+    for (uint32_t i = lane; i < n_mc; i += 32)
+    {
+        uint32_t t, rows[4];
+        int plane, bx, by, pw;
+        rc_record_coords(q[cap - 1 - (int)i], t, plane, bx, by);
+        rc_mc_block(v, plane, bx, by, t, rows);
+        uint8_t *dst = block_dst(v, plane, bx, by, pw);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];
+    }
+    __syncwarp();
+}
 
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kBandWarps * 32, kMinBlocks)
-recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands)
+recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap)
 {
     ReconView &vw = *reinterpret_cast<ReconView *>(rc_smem + RC_SMEM_VIEW_OFF);
+    /* dynamic shared memory: [tables + view | nest staging scratch | queue counters | queue] */
+    uint32_t *queue = reinterpret_cast<uint32_t *>(rc_smem + kRecSmem) + (threadIdx.x >> 5) * queue_cap;   /* the warp's own */
     const int job = blockIdx.x / n_bands;
     const int band = blockIdx.x - job * n_bands;
     if (threadIdx.x == 0) load_view(vw, jobs[job]);
@@ -246,15 +347,11 @@ recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands)
     if (!v.blob) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    /* map phase: the band's segments */
+    /* map phase */
     const int row0 = band * SYM_BAND_MCB_ROWS, row1 = min(row0 + SYM_BAND_MCB_ROWS, v.mcb_h);
-    const int units = (row1 - row0) * v.nseg;
 #pragma unroll 1
-    for (int u = warp; u < units; u += kBandWarps)
-    {
-        const int r = u / v.nseg;
-        map_segment(v, row0 + r, (u - r * v.nseg) * SYM_SEG_MCBS, lane);
-    }
+    for (int mx0 = 0; mx0 < v.mcb_w; mx0 += kTileMcbs)
+        band_map_tile(v, row0, row1, mx0, min(mx0 + kTileMcbs, v.mcb_w), queue, queue_cap);
     /* record phase */
     const uint32_t nb1 = v.n_bands + 1;
     const uint32_t raw0 = __ldg(v.bands + band), raw1 = __ldg(v.bands + band + 1);
@@ -297,11 +394,12 @@ int env_int(const char *name)
 }  // namespace
 
 template <int kMinBlocks>
-int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, cudaStream_t stream)
+int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, int mcb_w, cudaStream_t stream)
 {
     const long long grid = (long long)n_jobs * n_bands;
     if (grid > 0x7FFFFFFFll) return (int)cudaErrorInvalidConfiguration;
-    recon_band_kernel<kMinBlocks><<<(unsigned)grid, kBandWarps * 32, kRecSmem, stream>>>(d_jobs, n_bands);
+    const int cap = band_queue_entries(mcb_w);
+    recon_band_kernel<kMinBlocks><<<(unsigned)grid, kBandWarps * 32, kRecSmem + kBandWarps * cap * 4, stream>>>(d_jobs, n_bands, cap);
     return (int)cudaGetLastError();
 }
 
@@ -344,11 +442,11 @@ static int launch_record_cfg(int cfg, const ReconJob *d_jobs, int n_jobs, uint32
 extern "C" void hvqm4_recon_set_mode(int band_mode) { g_band_mode = band_mode; }
 
 /* the fused band kernel only (no host-side record prefix needed): used behind the GPU entropy stage */
-extern "C" int hvqm4_recon_launch_band(const ReconJob *d_jobs, int n_jobs, int mcb_h, cudaStream_t stream)
+extern "C" int hvqm4_recon_launch_band(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, cudaStream_t stream)
 {
     if (n_jobs <= 0) return 0;
     const int n_bands = (mcb_h + SYM_BAND_MCB_ROWS - 1) / SYM_BAND_MCB_ROWS;
-    const int rc = launch_band<4>(d_jobs, n_jobs, n_bands, stream);
+    const int rc = launch_band<4>(d_jobs, n_jobs, n_bands, mcb_w, stream);
     if (rc == 0) ++g_band_launches;
     return rc;
 }
@@ -374,9 +472,9 @@ extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w,
         int rc;
         switch (band_mode)
         {
-        case 2: rc = launch_band<2>(d_jobs, n_jobs, n_bands, stream); break;
-        case 3: rc = launch_band<3>(d_jobs, n_jobs, n_bands, stream); break;
-        default: rc = launch_band<4>(d_jobs, n_jobs, n_bands, stream); break;
+        case 2: rc = launch_band<2>(d_jobs, n_jobs, n_bands, mcb_w, stream); break;
+        case 3: rc = launch_band<3>(d_jobs, n_jobs, n_bands, mcb_w, stream); break;
+        default: rc = launch_band<4>(d_jobs, n_jobs, n_bands, mcb_w, stream); break;
         }
         if (rc == 0 && launches) ++*launches;
         if (rc == 0) ++g_band_launches;

@@ -39,6 +39,7 @@
 #define RC_LD32(p) __ldg((const uint32_t *)(p))
 #define RC_LD64(p) __ldg((const unsigned long long *)(p))
 #define RC_PRMT(a, b, s) __byte_perm((a), (b), (s))
+#define RC_ADDMIN_U16X2(a, b, c) __viaddmin_u16x2((a), (b), (c))   /* VIADDMNMX.U16x2: per half min((a + b) mod 2^16, c) */
 #else
 #define RC_LD8(p) (*(const uint8_t *)(p))
 #define RC_LD32(p) (*(const uint32_t *)(p))
@@ -51,6 +52,13 @@ static inline uint32_t rc_prmt_host(uint32_t a, uint32_t b, uint32_t s)
     return r;
 }
 #define RC_PRMT(a, b, s) rc_prmt_host((a), (b), (s))
+static inline uint32_t rc_addmin_u16x2_host(uint32_t a, uint32_t b, uint32_t c)
+{
+    const uint32_t lo = (a + b) & 0xFFFFu, hi = ((a >> 16) + (b >> 16)) & 0xFFFFu;
+    const uint32_t clo = c & 0xFFFFu, chi = c >> 16;
+    return (lo < clo ? lo : clo) | (hi < chi ? hi : chi) << 16;
+}
+#define RC_ADDMIN_U16X2(a, b, c) rc_addmin_u16x2_host((a), (b), (c))
 #endif
 
 #define RC_NEST_TABLE_WORDS (SYM_NEST_H * 64)
@@ -153,17 +161,28 @@ RC_HD uint32_t rc_sat_mean8(int32_t sum)
     return q > 255u ? 255u : q;
 }
 
+/* Two columns per 32-bit word in 16-bit halves (the sixteen sums lie in -765..2805):
+ *   s' = sum + 4 + 1024 > 0 in every half, so packed words add without carries between halves
+ *        (row term + 516 replicated by one IMAD, column terms + 512 packed pairwise);
+ *   q' = s' >> 3 = floor((sum + 4) / 8) + 128;
+ *   out = min_u16((q' - 128) mod 2^16, 255): a negative quotient wraps to >= 0xFFA0 and clamps to
+ *        255 exactly like the reference's unsigned division (h4m:293-296).
+ * 9 instructions per row of four pixels. */
 RC_HD void rc_weighted(uint32_t rows[4], int V, int T, int B, int L, int R)
 {
-    const int c0 = 2 * L - R - V, c1 = V - R, c2 = V - L, c3 = 2 * R - L - V;
-    const int r0 = 7 * V + 2 * T - B, r1 = 9 * V - B, r2 = 9 * V - T, r3 = 7 * V + 2 * B - T;
-    /* r_k = 8V + rowterm[k] */
-#define RC_WROW(b) (rc_sat_mean8((b) + c0) | rc_sat_mean8((b) + c1) << 8 | rc_sat_mean8((b) + c2) << 16 | rc_sat_mean8((b) + c3) << 24)
-    rows[0] = RC_WROW(r0);
-    rows[1] = RC_WROW(r1);
-    rows[2] = RC_WROW(r2);
-    rows[3] = RC_WROW(r3);
-#undef RC_WROW
+    const uint32_t c0 = (uint32_t)(2 * L - R - V + 512), c1 = (uint32_t)(V - R + 512);
+    const uint32_t c2 = (uint32_t)(V - L + 512), c3 = (uint32_t)(2 * R - L - V + 512);
+    const uint32_t c01 = c1 * 0x10000u + c0, c23 = c3 * 0x10000u + c2;
+    /* r_k = 8V + rowterm[k] + 4 + 512 */
+    const uint32_t r[4] = {(uint32_t)(7 * V + 2 * T - B + 516), (uint32_t)(9 * V - B + 516),
+                           (uint32_t)(9 * V - T + 516), (uint32_t)(7 * V + 2 * B - T + 516)};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        const uint32_t q01 = ((r[k] * 0x10001u + c01) >> 3) & 0x1FFF1FFFu;
+        const uint32_t q23 = ((r[k] * 0x10001u + c23) >> 3) & 0x1FFF1FFFu;
+        rows[k] = RC_PRMT(RC_ADDMIN_U16X2(q01, 0xFF80FF80u, 0x00FF00FFu), RC_ADDMIN_U16X2(q23, 0xFF80FF80u, 0x00FF00FFu), 0x6420);
+    }
 }
 
 /* ---- AOT bases (h4m:679-817) --------------------------------------------------------

@@ -92,3 +92,21 @@ int emul_recon_picture(const uint8_t *blob, uint8_t *present, const uint8_t *pas
     if (seen != h.n_records) return -2;   /* chunk table must cover every record exactly once */
     return 0;
 }
+
+/* ---- leaf operators of recon_core.h, exported so that tests can sweep them against the
+   reference's leaf functions (oracle/ref_wrap.c: ref_WeightImBlock, ref_MotionComp4x4) ---- */
+extern "C" __attribute__((visibility("default")))
+void emul_weighted(uint8_t *dst16, int V, int T, int B, int L, int R)
+{
+    uint32_t rows[4];
+    rc_weighted(rows, V, T, B, L, R);
+    memcpy(dst16, rows, 16);
+}
+
+extern "C" __attribute__((visibility("default")))
+void emul_predict(uint8_t *dst16, const uint8_t *src, int stride, int hx, int hy)
+{
+    uint32_t rows[4];
+    rc_predict(rows, src, stride, hx, hy);
+    memcpy(dst16, rows, 16);
+}

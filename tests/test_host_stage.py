@@ -113,3 +113,33 @@ def test_unsupported_geometry_is_rejected(emul_lib):
     assert not emul_lib.h4e_seq_create(322, 240, 2, 2, 1)     # not a multiple of 8
     assert not emul_lib.h4e_seq_create(320, 240, 1, 1, 1)     # 4:4:4
     assert not emul_lib.h4e_seq_create(240, 320, 2, 2, 1)     # portrait (untested upstream, README:23)
+
+
+def test_kernel_leaf_arithmetic_equals_reference_leaves(emul_lib, oracle):
+    """The packed 16-bit weighted fill and the packed half-sample filters of recon_core.h (the
+    code the CUDA kernels run) against the reference's own WeightImBlock (h4m:299-383) and
+    _MotionComp (h4m:1242-1294): extremes, the sat_mean8 wrap, and 20 000 random neighbourhoods."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    ref = ctypes.CDLL(oracle.REF_LIB)
+    rng = np.random.default_rng(7)
+    want = (ctypes.c_uint8 * 16)()
+    got = (ctypes.c_uint8 * 16)()
+    ext = [0, 1, 2, 127, 128, 254, 255]
+    cases = [(v, t, b, l, r) for v in ext for t in ext for b in ext for l in (0, 128, 255) for r in (0, 3, 255)]
+    cases += [tuple(int(x) for x in rng.integers(0, 256, 5)) for _ in range(20000)]
+    for V, T, B, L, R in cases:
+        ref.ref_WeightImBlock(want, 4, V, T, B, L, R)
+        emul_lib.emul_weighted(got, V, T, B, L, R)
+        assert bytes(got) == bytes(want), (V, T, B, L, R)
+    src = rng.integers(0, 256, (12, 16), dtype=np.uint8)
+    src[:4] = 255
+    src[4:6] = 0
+    for oy in range(6):
+        for ox in range(8):
+            for hx in (0, 1):
+                for hy in (0, 1):
+                    p = src.ctypes.data + oy * 16 + ox
+                    ref.ref_MotionComp4x4(want, 4, ctypes.c_void_p(p), 16, hx, hy)
+                    emul_lib.emul_predict(got, ctypes.c_void_p(p), 16, hx, hy)
+                    assert bytes(got) == bytes(want), (oy, ox, hx, hy)
