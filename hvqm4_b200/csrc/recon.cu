@@ -125,7 +125,7 @@ __device__ __forceinline__ void build_div_tables()
     int32_t *s_mcdiv = reinterpret_cast<int32_t *>(rc_smem + RC_SMEM_MCDIV_OFF);
     int32_t *s_div = reinterpret_cast<int32_t *>(rc_smem + RC_SMEM_DIV_OFF);
     for (int i = threadIdx.x; i < 256; i += kThreads) s_mcdiv[i] = i ? 0x1000 / i : 0;
-    if (threadIdx.x < 16) s_div[threadIdx.x] = threadIdx.x ? 0x1000 / (threadIdx.x * 16) * 16 : 0;
+    if (threadIdx.x < 16) s_div[threadIdx.x] = threadIdx.x ? 0x1000 / (threadIdx.x * 16) : 0;   /* divTable / 16 (recon_core.h) */
 }
 
 /* expands the packed nest of the CTA's picture into the shared-memory lookup table; the caller
@@ -142,7 +142,7 @@ __device__ __forceinline__ void build_nest_table(const ReconView &v, uint8_t *pa
         packed[i] = x < SYM_NEST_ROW_BYTES ? __ldg(src + y * SYM_NEST_ROW_BYTES + x) : (uint8_t)0;
     }
     __syncthreads();
-    /* table entry (y, x) = nibbles x..x+7 of row y; (y, 2j) and (y, 2j+1) share bytes j..j+4 */
+    /* nibbles x..x+7 of row y, spread into the step-1 and step-2 tables; (y, 2j) and (y, 2j+1) share bytes j..j+4 */
     const uint32_t *pw = reinterpret_cast<const uint32_t *>(packed);
     for (int i = threadIdx.x; i < SYM_NEST_H * 32; i += kThreads)
     {
@@ -150,8 +150,11 @@ __device__ __forceinline__ void build_nest_table(const ReconView &v, uint8_t *pa
         const int w = y * 10 + (j >> 2), sh = (j & 3) * 8;
         const uint32_t w0 = pw[w], w1 = pw[w + 1], w2 = (j & 3) ? pw[w + 2] : 0u;
         const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-        s_nest_tab[y * 64 + 2 * j] = lo;
-        s_nest_tab[y * 64 + 2 * j + 1] = (lo >> 4) | (hi << 28);
+        const uint32_t odd = (lo >> 4) | (hi << 28);
+        s_nest_tab[y * 64 + 2 * j] = rc_nest_spread_step1(lo);
+        s_nest_tab[y * 64 + 2 * j + 1] = rc_nest_spread_step1(odd);
+        s_nest_tab[RC_NEST_STEP2_OFF + y * 64 + 2 * j] = rc_nest_spread_step2(lo);
+        s_nest_tab[RC_NEST_STEP2_OFF + y * 64 + 2 * j + 1] = rc_nest_spread_step2(odd);
     }
 }
 
@@ -258,7 +261,11 @@ __device__ __forceinline__ uint8_t *block_dst(const ReconView &v, int plane, int
 
 /* map work of macroblock rows [row0, row1) x macroblock columns [mx0, mx1) of the CTA's picture.
    Every warp owns up to four block rows (two luma, one U, one V) and a private queue of `cap`
-   entries: no atomics, no block barrier, counters in (warp-uniform) registers. */
+   entries: no atomics, no block barrier, counters in (warp-uniform) registers.  The classifying
+   walk stays minimal and uniform (type and DC of the next 32 blocks are loaded while the current
+   32 are classified); everything that costs instructions runs in the drains, where all lanes of
+   a warp do the same thing, two queue entries per lane at a time so that twice as many
+   reference rows are in flight. */
 __device__ __forceinline__ void band_map_tile(const ReconView &v, int row0, int row1, int mx0, int mx1, uint32_t *q, int cap)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -280,12 +287,24 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, int row0, int 
         int pw2;
         uint8_t *dst_row = block_dst(v, plane, 0, by, pw2);
         const uint32_t entry_row = sym_record_header(0, plane, 0, by);
+        /* lanes past the row end get type 6 (raw: nothing to do here) */
+        int bx = x0 + lane;
+        uint32_t t = 6u, dc = 0u;
+        if (bx < x1)
+        {
+            t = __ldg(trow + bx);
+            dc = __ldg(drow + bx);
+        }
 #pragma unroll 1
         for (int xb = x0; xb < x1; xb += 32)
         {
-            const int bx = xb + lane;
-            /* lanes past the row end get type 6 (raw: nothing to do here) */
-            const uint32_t t = bx < x1 ? __ldg(trow + bx) : 6u;
+            const int bx_n = bx + 32;
+            uint32_t t_n = 6u, dc_n = 0u;
+            if (bx_n < x1)
+            {
+                t_n = __ldg(trow + bx_n);
+                dc_n = __ldg(drow + bx_n);
+            }
             const bool inter = !ipic && (t & 0x60);
             const uint32_t nib = ipic ? t : (t & 0xF);
             const bool is_w = !inter && nib == 0;
@@ -298,11 +317,12 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, int row0, int 
             n_mc += __popc(m_mc);
             if (!inter && nib == 8)
             {   /* flat fill, h4m:281 */
-                const uint32_t V = __ldg(drow + bx) * 0x01010101u;
+                const uint32_t V = dc * 0x01010101u;
                 uint8_t *dst = dst_row + bx * 4;
 #pragma unroll
                 for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = V;
             }
+            bx = bx_n; t = t_n; dc = dc_n;
         }
     }
     __syncwarp();
@@ -317,16 +337,28 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, int row0, int 
 #pragma unroll
         for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];
     }
+    /* motion compensation: two entries per lane and round */
+    const uint32_t *q_mc = q + cap - 1;
 #pragma unroll 1
-    for (uint32_t i = lane; i < n_mc; i += 32)
+    for (uint32_t i = lane; i < n_mc; i += 64)
     {
-        uint32_t t, rows[4];
-        int plane, bx, by, pw;
-        rc_record_coords(q[cap - 1 - (int)i], t, plane, bx, by);
-        rc_mc_block(v, plane, bx, by, t, rows);
-        uint8_t *dst = block_dst(v, plane, bx, by, pw);
+        const bool two = i + 32 < n_mc;
+        uint32_t t0, t1, rows0[4], rows1[4];
+        int plane0, bx0, by0, plane1, bx1, by1, pw0, pw1;
+        rc_record_coords(q_mc[-(int)i], t0, plane0, bx0, by0);
+        rc_record_coords(q_mc[-(int)(two ? i + 32 : i)], t1, plane1, bx1, by1);
+        const uint32_t mv0 = rc_mv_word(v, plane0, bx0, by0), mv1 = rc_mv_word(v, plane1, bx1, by1);
+        const uint32_t mp0 = rc_motion_pack(v, plane0, bx0, by0, t0, mv0), mp1 = rc_motion_pack(v, plane1, bx1, by1, t1, mv1);
+        rc_mc_packed2(v, plane0, mp0, rows0, plane1, mp1, rows1);
+        uint8_t *dst0 = block_dst(v, plane0, bx0, by0, pw0);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];
+        for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst0 + r * pw0) = rows0[r];
+        if (two)
+        {
+            uint8_t *dst1 = block_dst(v, plane1, bx1, by1, pw1);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst1 + r * pw1) = rows1[r];
+        }
     }
     __syncwarp();
 }
@@ -399,7 +431,13 @@ int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, int mcb_w, cuda
     const long long grid = (long long)n_jobs * n_bands;
     if (grid > 0x7FFFFFFFll) return (int)cudaErrorInvalidConfiguration;
     const int cap = band_queue_entries(mcb_w);
-    recon_band_kernel<kMinBlocks><<<(unsigned)grid, kBandWarps * 32, kRecSmem + kBandWarps * cap * 4, stream>>>(d_jobs, n_bands, cap);
+    const int smem = kRecSmem + kBandWarps * cap * 4;
+    if (smem > 48 * 1024)
+    {   /* wide pictures: opt in (per device, so not cached) */
+        const cudaError_t e = cudaFuncSetAttribute(recon_band_kernel<kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    recon_band_kernel<kMinBlocks><<<(unsigned)grid, kBandWarps * 32, smem, stream>>>(d_jobs, n_bands, cap);
     return (int)cudaGetLastError();
 }
 

@@ -40,6 +40,7 @@
 #define RC_LD64(p) __ldg((const unsigned long long *)(p))
 #define RC_PRMT(a, b, s) __byte_perm((a), (b), (s))
 #define RC_ADDMIN_U16X2(a, b, c) __viaddmin_u16x2((a), (b), (c))   /* VIADDMNMX.U16x2: per half min((a + b) mod 2^16, c) */
+#define RC_DP4A(a, b, c) __dp4a((uint32_t)(a), (uint32_t)(b), (uint32_t)(c))   /* IDP.4A.U8.U8: c + sum of byte products */
 #else
 #define RC_LD8(p) (*(const uint8_t *)(p))
 #define RC_LD32(p) (*(const uint32_t *)(p))
@@ -59,9 +60,16 @@ static inline uint32_t rc_addmin_u16x2_host(uint32_t a, uint32_t b, uint32_t c)
     return (lo < clo ? lo : clo) | (hi < chi ? hi : chi) << 16;
 }
 #define RC_ADDMIN_U16X2(a, b, c) rc_addmin_u16x2_host((a), (b), (c))
+static inline uint32_t rc_dp4a_host(uint32_t a, uint32_t b, uint32_t c)
+{
+    for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 0xFF) * ((b >> (8 * i)) & 0xFF);
+    return c;
+}
+#define RC_DP4A(a, b, c) rc_dp4a_host((a), (b), (c))
 #endif
 
-#define RC_NEST_TABLE_WORDS (SYM_NEST_H * 64)
+#define RC_NEST_TABLE_WORDS (2 * SYM_NEST_H * 64)   /* step-1 entries, then step-2 entries */
+#define RC_NEST_STEP2_OFF (SYM_NEST_H * 64)
 
 /* The three lookup tables live at fixed offsets at the start of dynamic shared memory on the
    GPU (no pointer registers); on the CPU they are reached through the view. */
@@ -76,11 +84,11 @@ extern __shared__ __align__(16) uint8_t rc_smem[];
 #if defined(__CUDA_ARCH__)
 #define RC_NEST_TAB(v) (reinterpret_cast<const uint32_t *>(rc_smem + RC_SMEM_NEST_OFF))
 #define RC_MCDIV(v, i) (reinterpret_cast<const int32_t *>(rc_smem + RC_SMEM_MCDIV_OFF)[i])
-#define RC_DIV(v, i) (reinterpret_cast<const int32_t *>(rc_smem + RC_SMEM_DIV_OFF)[i])
+#define RC_DIV16(v, i) (reinterpret_cast<const int32_t *>(rc_smem + RC_SMEM_DIV_OFF)[i])   /* divTable[i] / 16 */
 #else
 #define RC_NEST_TAB(v) ((v).nest_tab)
 #define RC_MCDIV(v, i) ((v).mcdiv_tab[i])
-#define RC_DIV(v, i) ((v).div_tab[i])
+#define RC_DIV16(v, i) ((v).div_tab[i] >> 4)
 #endif
 
 /* Read-only view of one picture job. */
@@ -123,7 +131,20 @@ RC_HD void rc_make_view(ReconView &v, const uint8_t *blob, const SymHeader &h, c
     v.off_nest = h.off_nest; v.n_chunks = h.n_chunks; v.n_chunks_nest = h.n_chunks_nest;
 }
 
-/* Entry (y, x), x in 0..63: the nibbles x..x+7 of packed nest row y (zero past column 69). */
+/* Nest lookup tables.  rc_nest_table_entry: the nibbles x..x+7 of packed nest row y (zero past
+   column 69) as one word; the two tables the kernels read are derived from it: entry (y, x) of
+   the step-1 table = samples x, x+1, x+2, x+3 and of the step-2 table = samples x, x+2, x+4, x+6,
+   one per byte and ALREADY MULTIPLIED BY 16 (the sample sits in the high nibble, exactly like a
+   reference pixel masked with 0xF0), so that a basis row is one load and intra and inter bases
+   share the arithmetic below. */
+RC_HD uint32_t rc_nest_spread_step1(uint32_t nibbles8)
+{
+    uint32_t x = nibbles8 & 0xFFFFu;                   /* nibbles 0,1,2,3 -> one per byte */
+    x = (x | x << 8) & 0x00FF00FFu;
+    return ((x | x << 4) & 0x0F0F0F0Fu) << 4;
+}
+RC_HD uint32_t rc_nest_spread_step2(uint32_t nibbles8) { return (nibbles8 & 0x0F0F0F0Fu) << 4; }   /* nibbles 0,2,4,6 */
+
 RC_HD uint32_t rc_nest_table_entry(const uint8_t *packed, int y, int x)
 {
     const uint8_t *row = packed + y * SYM_NEST_ROW_BYTES;
@@ -139,16 +160,6 @@ RC_HD uint32_t rc_nest_table_entry(const uint8_t *packed, int y, int x)
 RC_HD uint32_t rc_pick3(const uint32_t a[3], int i) { return i == 0 ? a[0] : i == 1 ? a[1] : a[2]; }
 
 RC_HD uint32_t rc_clamp255(int32_t x) { return x < 0 ? 0u : x > 255 ? 255u : (uint32_t)x; }
-
-/* byte-wise (a + b + c + d + 2) >> 2 on four packed bytes, via two 16-bit lanes */
-RC_HD uint32_t rc_avg4x4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
-{
-    /* even bytes -> 16-bit lanes (PRMT 0x4240 = [b0,0,b2,0]); odd bytes (0x4341 = [b1,0,b3,0]) */
-    const uint32_t lo = RC_PRMT(a, 0u, 0x4240) + RC_PRMT(b, 0u, 0x4240) + RC_PRMT(c, 0u, 0x4240) + RC_PRMT(d, 0u, 0x4240) + 0x00020002u;
-    const uint32_t hi = RC_PRMT(a, 0u, 0x4341) + RC_PRMT(b, 0u, 0x4341) + RC_PRMT(c, 0u, 0x4341) + RC_PRMT(d, 0u, 0x4341) + 0x00020002u;
-    /* each lane sum <= 1022; after >> 2 bytes 0 and 2 hold the two results of the lane pair */
-    return RC_PRMT(lo >> 2, hi >> 2, 0x6240);
-}
 
 /* ---- weighted DC fill (h4m:293-383) ------------------------------------------------
  * out(r,c) = sat_mean8(8V + rowterm[r] + colterm[c]) with
@@ -189,37 +200,35 @@ RC_HD void rc_weighted(uint32_t rows[4], int V, int T, int B, int L, int R)
  * side word: bits 15:0 descriptor ([5:0] x, [10:6] y, [11] x step 2, [12] y step 2,
  * [14:13] scale offset, [15] negate), bits 23:16 scale symbol (>> 2). */
 
-/* four samples of one basis row as packed bytes, from the I-picture nest table */
-RC_HD uint32_t rc_row_nest(const uint32_t *tab, int y, int ox, uint32_t step2)
+/* Basis rows are handled as four bytes holding 16 * sample (sample in the high nibble).  The
+ * reference's factor (scale_sum + offset) * +-divTable[range] (h4m:712-731) is a multiple of 16
+ * because every divTable entry is (h4m:270), so  factor * sample == (factor / 16) * (16 * sample)
+ * as integers, hence also mod 2^32: the kernels multiply by RC_DIV16 = divTable / 16 and never
+ * shift the samples down.
+ *
+ * Pipe balance (measured on B200, tools/ubench/pipes.cu): LOP3/SHF/PRMT issue at half rate on the
+ * ALU pipe, IMAD and IDP.4A at half rate on the FMA pipe, and the two pipes run side by side.  The
+ * byte extracts are therefore split: IDP.4A with a one-hot weight (FMA pipe) and PRMT (ALU pipe). */
+
+/* bytes a .. a+7 of the aligned words w0, w1, w2 (a = 0..3), then samples at step 1 or 2, masked to the high nibbles */
+RC_HD uint32_t rc_row_window(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t sel_align, uint32_t sel_step)
 {
-    const uint32_t w = tab[y * 64 + ox];
-    if (step2) return w & 0x0F0F0F0Fu;                 /* nibbles 0,2,4,6 */
-    uint32_t x = w & 0xFFFFu;                          /* nibbles 0,1,2,3 -> one per byte */
-    x = (x | x << 8) & 0x00FF00FFu;
-    return (x | x << 4) & 0x0F0F0F0Fu;
+    const uint32_t lo = RC_PRMT(w0, w1, sel_align), hi = RC_PRMT(w1, w2, sel_align);
+    return RC_PRMT(lo, hi, sel_step) & 0xF0F0F0F0u;
 }
 
-/* same from the reference-frame window: sample = (pixel >> 4) & 0xF (h4m:756-761) */
-RC_HD uint32_t rc_row_window(const uint8_t *p, uint32_t step2)
-{
-    const uint32_t a = (uint32_t)((uintptr_t)p & 7);
-    const uint8_t *base = p - a;
-    const uint64_t lo = RC_LD64(base), hi = RC_LD64(base + 8);
-    const uint64_t bytes = a ? (lo >> (8 * a)) | (hi << (64 - 8 * a)) : lo;   /* the 8 bytes at p */
-    const uint32_t b03 = (uint32_t)bytes, b47 = (uint32_t)(bytes >> 32);
-    const uint32_t v = step2 ? RC_PRMT(b03, b47, 0x6420) : b03;
-    return (v >> 4) & 0x0F0F0F0Fu;
-}
-
-/* accumulates one basis given its four packed rows */
+/* accumulates one basis given its four packed rows (bytes = 16 * sample); kFmaExtracts of the
+   four byte extracts per row go through IDP.4A, the rest through PRMT */
+template <int kFmaExtracts>
 RC_HD void rc_accumulate(const ReconView &v, uint32_t word, const uint32_t R[4], int32_t &scale_sum, int32_t acc[16])
 {
-    int b[16];
+    uint32_t b[16];
 #pragma unroll
     for (int y = 0; y < 4; ++y)
 #pragma unroll
-        for (int x = 0; x < 4; ++x) b[y * 4 + x] = (int)((R[y] >> (8 * x)) & 0xFF);
-    int lo = b[0], hi = b[0];
+        for (int x = 0; x < 4; ++x)
+            b[y * 4 + x] = x < kFmaExtracts ? RC_DP4A(R[y], 1u << (8 * x), 0u) : RC_PRMT(R[y], 0u, 0x4440 + x);
+    uint32_t lo = b[0], hi = b[0];
 #pragma unroll
     for (int i = 1; i < 16; ++i)
     {
@@ -227,14 +236,14 @@ RC_HD void rc_accumulate(const ReconView &v, uint32_t word, const uint32_t R[4],
         hi = b[i] > hi ? b[i] : hi;
     }
     scale_sum += (int32_t)((word >> 16) & 0xFF) << 2;            /* cumulative within the block, h4m:726,781 */
-    int32_t inv = RC_DIV(v, hi - lo);
+    int32_t inv = RC_DIV16(v, (hi - lo) >> 4);
     if (word & 0x8000) inv = -inv;
     const uint32_t factor = (uint32_t)(scale_sum + (int32_t)((word >> 13) & 3)) * (uint32_t)inv;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = (int32_t)((uint32_t)acc[i] + factor * (uint32_t)b[i]);   /* mod 2^32 */
+    for (int i = 0; i < 16; ++i) acc[i] = (int32_t)((uint32_t)acc[i] + factor * b[i]);   /* mod 2^32 */
 }
 
-/* window == nullptr: intra (nest table); else inter (reference luma window, stride = luma width) */
+/* window == nullptr: intra (nest tables); else inter (reference luma window, stride = luma width) */
 RC_HD void rc_add_basis(const ReconView &v, uint32_t word, const uint8_t *window, int32_t &scale_sum, int32_t acc[16])
 {
     const int ox = word & 0x3F, oy = (word >> 6) & 0x1F;
@@ -243,16 +252,27 @@ RC_HD void rc_add_basis(const ReconView &v, uint32_t word, const uint8_t *window
     uint32_t R[4];
     if (window)
     {
+        /* sample = (pixel >> 4) & 0xF (h4m:756-761): rows are fetched as three aligned words */
         const uint8_t *p = window + oy * v.width + ox;
+        const uint32_t a = (uint32_t)((uintptr_t)p & 3);
+        const uint8_t *base = p - a;
+        const uint32_t sel_align = 0x3210u + 0x1111u * a, sel_step = xs2 ? 0x6420u : 0x3210u;
+        const int pitch = ys * v.width;
 #pragma unroll
-        for (int y = 0; y < 4; ++y) R[y] = rc_row_window(p + y * ys * v.width, xs2);
+        for (int y = 0; y < 4; ++y)
+        {
+            const uint8_t *q = base + y * pitch;
+            R[y] = rc_row_window(RC_LD32(q), RC_LD32(q + 4), RC_LD32(q + 8), sel_align, sel_step);
+        }
+        rc_accumulate<4>(v, word, R, scale_sum, acc);
     }
     else
     {
+        const uint32_t *tab = RC_NEST_TAB(v) + (xs2 ? RC_NEST_STEP2_OFF : 0) + oy * 64 + ox;
 #pragma unroll
-        for (int y = 0; y < 4; ++y) R[y] = rc_row_nest(RC_NEST_TAB(v), oy + y * ys, ox, xs2);
+        for (int y = 0; y < 4; ++y) R[y] = tab[y * ys * 64];
+        rc_accumulate<2>(v, word, R, scale_sum, acc);
     }
-    rc_accumulate(v, word, R, scale_sum, acc);
 }
 
 RC_HD int32_t rc_aot_sum(const ReconView &v, const uint32_t *side, int n, const uint8_t *window, int32_t acc[16])
@@ -299,6 +319,64 @@ RC_HD void rc_intra_aot(const ReconView &v, uint32_t rows[4], const uint32_t *si
  *                                   a phase bit is 0 ((4a+2)>>2 = a, (2a+2b+2)>>2 = (a+b+1)>>1). */
 RC_HD uint32_t rc_avg4(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) & 0xFEFEFEFEu) >> 1); }
 
+/* rows W[2r], W[2r+1] = the two aligned words that cover the 5 bytes of reference row r */
+RC_HD void rc_predict_load(uint32_t W[10], const uint8_t *src, int stride, int hy)
+{
+    const uint8_t *base = src - ((uintptr_t)src & 3);
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+    {
+        if (r < 4 || hy)
+        {
+            W[2 * r] = RC_LD32(base + r * stride);
+            W[2 * r + 1] = RC_LD32(base + r * stride + 4);
+        }
+        else
+            W[2 * r] = W[2 * r + 1] = 0;
+    }
+}
+
+/* a = src & 3.  Alignment is a byte permute (A = bytes a..a+3, B = bytes a+1..a+4 of a row).
+ *   no lane needs both half steps:  out = (A + O + 1) >> 1 byte-wise with O = B, the next row's A,
+ *                                   or A itself;
+ *   otherwise:  every output pixel is two IDP.4A (FMA pipe) -- 2 + this row's taps, + the next
+ *               row's taps -- with per-lane weight words that encode the phase: hx picks taps
+ *               {x, x+1} with weight 1 or tap {x} with weight 2, hy moves half of the weight to
+ *               the next row or doubles this row's.  (4a+2)>>2 = a, (2a+2b+2)>>2 = (a+b+1)>>1, so
+ *               this is exactly the four _MotionComp_xy variants (h4m:1242-1294), without a
+ *               divergent branch and with the ALU pipe left to the alignment and the packing. */
+RC_HD void rc_predict_filter(uint32_t rows[4], const uint32_t W[10], uint32_t a, int hx, int hy, bool any_diag)
+{
+    const uint32_t sel = 0x3210u + 0x1111u * a;
+    uint32_t A[5], B[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+    {
+        A[r] = RC_PRMT(W[2 * r], W[2 * r + 1], sel);
+        B[r] = RC_PRMT(W[2 * r], W[2 * r + 1], sel + 0x1111u);
+    }
+    if (!any_diag)
+    {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) rows[r] = rc_avg4(A[r], hx ? B[r] : hy ? A[r + 1] : A[r]);
+        return;
+    }
+    /* weights of pixel 0 on A (pixels 1, 2: shifted left by 8, 16) and of pixel 3 on B */
+    const uint32_t wx = hx ? 0x0101u : 0x0002u, wx3 = hx ? 0x01010000u : 0x00020000u;
+    const uint32_t m0 = hy ? 1u : 2u, m1 = hy ? 1u : 0u;     /* this row, next row */
+    const uint32_t u0 = wx * m0, u3 = wx3 * m0, v0 = wx * m1, v3 = wx3 * m1;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+    {
+        const uint32_t p0 = RC_DP4A(A[r + 1], v0, RC_DP4A(A[r], u0, 2u));
+        const uint32_t p1 = RC_DP4A(A[r + 1], v0 << 8, RC_DP4A(A[r], u0 << 8, 2u));
+        const uint32_t p2 = RC_DP4A(A[r + 1], v0 << 16, RC_DP4A(A[r], u0 << 16, 2u));
+        const uint32_t p3 = RC_DP4A(B[r + 1], v3, RC_DP4A(B[r], u3, 2u));
+        /* two 16-bit lanes per word (sums <= 1022), >> 2, then bytes 0 and 2 of each */
+        rows[r] = RC_PRMT((p1 * 0x10000u + p0) >> 2, (p3 * 0x10000u + p2) >> 2, 0x6420);
+    }
+}
+
 RC_HD void rc_predict(uint32_t rows[4], const uint8_t *src, int stride, int hx, int hy)
 {
 #if defined(__CUDA_ARCH__)
@@ -306,34 +384,9 @@ RC_HD void rc_predict(uint32_t rows[4], const uint8_t *src, int stride, int hx, 
 #else
     const bool any_diag = hx & hy;
 #endif
-    const uint32_t a = (uint32_t)((uintptr_t)src & 3);
-    const uint8_t *base = src - a;
-    uint32_t A[5], Bx[5];
-#pragma unroll
-    for (int r = 0; r < 5; ++r)
-    {
-        if (r < 4 || hy)
-        {
-            const uint32_t w0 = RC_LD32(base + r * stride), w1 = RC_LD32(base + r * stride + 4);
-            const uint64_t w = ((uint64_t)w1 << 32 | w0) >> (8 * a);
-            A[r] = (uint32_t)w;
-            Bx[r] = hx ? (uint32_t)(w >> 8) : A[r];
-        }
-        else
-            A[r] = Bx[r] = 0;
-    }
-    if (!any_diag)
-    {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) rows[r] = rc_avg4(A[r], hx ? Bx[r] : hy ? A[r + 1] : A[r]);
-        return;
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-    {
-        const uint32_t C = hy ? A[r + 1] : A[r], D = hy ? Bx[r + 1] : Bx[r];
-        rows[r] = rc_avg4x4(A[r], Bx[r], C, D);
-    }
+    uint32_t W[10];
+    rc_predict_load(W, src, stride, hy);
+    rc_predict_filter(rows, W, (uint32_t)((uintptr_t)src & 3), hx, hy, any_diag);
 }
 
 /* ---- predicted AOT block (h4m:1379-1420); rows[] holds the MC prediction on entry ------
@@ -400,33 +453,77 @@ RC_HD int rc_classify(uint32_t t, int is_ipic)
     return nib == 0 ? RC_WEIGHTED : (nib == 8 || nib == 6) ? RC_DIRECT : RC_AOT_INTRA;
 }
 
-struct RcMotion
-{
-    const uint8_t *src;      /* integer-sample position of this 4x4 block in the reference plane */
-    const uint8_t *window;   /* origin of the 70x38 luma window (h4m:1864-1868) */
-    int stride, hx, hy;
-    bool poisoned;
-};
+/* ---- motion of one 4x4 block of an inter macroblock -----------------------------------------
+ * Resolved in two steps so that the band kernel can do the first one while it classifies blocks
+ * (vector table rows read coalesced) and queue the result:
+ *   rc_motion_pack   (vector word, block coordinates) -> one word: [26:0] byte offset of the
+ *                    integer-sample position inside the reference surface, [27] hx, [28] hy,
+ *                    [29] reference (0 past, 1 future), [30] poisoned (SYM_ERR_MV_RANGE: never
+ *                    dereferenced, painted grey)
+ *   rc_mc_packed     that word -> the prediction                                              */
+#define RC_MP_HX (1u << 27)
+#define RC_MP_HY (1u << 28)
+#define RC_MP_FUTURE (1u << 29)
+#define RC_MP_POISON (1u << 30)
+#define RC_MP_OFFSET(w) ((w) & 0x07FFFFFFu)
 
-/* per-plane MC address and phase of the block at (plane,bx,by) of an inter macroblock */
-RC_HD void rc_motion(const ReconView &v, int plane, int bx, int by, uint32_t t, RcMotion &m)
+RC_HD uint32_t rc_mv_word(const ReconView &v, int plane, int bx, int by)
+{
+    const int sh = plane ? 1 : 0;
+    const int mx = bx >> (1 - sh), my = by >> (1 - sh);
+    return RC_LD32(v.blob + v.off_mv + 4 * (my * v.mcb_w + mx));
+}
+
+RC_HD uint32_t rc_motion_pack(const ReconView &v, int plane, int bx, int by, uint32_t t, uint32_t mvw)
 {
     const int sh = plane ? 1 : 0;
     const int pw = v.width >> sh;
-    const int mx = bx >> (1 - sh), my = by >> (1 - sh);
-    const uint32_t mvw = RC_LD32(v.blob + v.off_mv + 4 * (my * v.mcb_w + mx));
     const int rx = (int16_t)(mvw & 0xFFFF), ry = (int16_t)(mvw >> 16);
-    m.poisoned = rx == -32768;                        /* SYM_ERR_MV_RANGE: never dereference */
-    const uint8_t *ref = ((t >> 5) & 3) == 2 ? v.ref[1] : v.ref[0];
+    if (rx == -32768) return RC_MP_POISON;
     const int px = rx >> sh, py = ry >> sh;
-    m.hx = rx & 1; m.hy = ry & 1;                     /* 1.3: luma phase for every plane (h4m:1329-1330,1869-1870) */
-    if (v.version15) { m.hx = px & 1; m.hy = py & 1; }/* 1.5: per-plane phase (h4m:1337-1343,1890-1896) */
+    /* 1.3: luma phase for every plane (h4m:1329-1330,1869-1870); 1.5: per-plane phase (h4m:1337-1343,1890-1896) */
+    const uint32_t hx = (uint32_t)(v.version15 ? px : rx) & 1u, hy = (uint32_t)(v.version15 ? py : ry) & 1u;
     const int plane_off = plane == 0 ? 0 : plane == 1 ? v.width * v.height : v.width * v.height + (v.width >> 1) * (v.height >> 1);
     /* linear addressing, no clamping (h4m:1344,1897); sub-block offset = pb_offset (h4m:866-869) */
     const int subx = plane == 0 ? (bx & 1) * 4 : 0, suby = plane == 0 ? (by & 1) * 4 : 0;
-    m.src = ref + plane_off + ((py >> 1) + suby) * pw + (px >> 1) + subx;
-    m.window = ref + rx / 2 + (ry / 2 - 16) * v.width - 32;
-    m.stride = pw;
+    const uint32_t off = (uint32_t)(plane_off + ((py >> 1) + suby) * pw + (px >> 1) + subx);
+    return (off & 0x07FFFFFFu) | hx << 27 | hy << 28 | (((t >> 5) & 3) == 2 ? RC_MP_FUTURE : 0u);
+}
+
+/* origin of the 70x38 luma window of the macroblock's reference position (h4m:1864-1868); NULL if poisoned */
+RC_HD const uint8_t *rc_motion_window(const ReconView &v, uint32_t t, uint32_t mvw)
+{
+    const int rx = (int16_t)(mvw & 0xFFFF), ry = (int16_t)(mvw >> 16);
+    if (rx == -32768) return nullptr;
+    const uint8_t *ref = ((t >> 5) & 3) == 2 ? v.ref[1] : v.ref[0];
+    return ref + rx / 2 + (ry / 2 - 16) * v.width - 32;
+}
+
+RC_HD void rc_mc_packed(const ReconView &v, int plane, uint32_t mp, uint32_t rows[4])
+{
+    if (mp & RC_MP_POISON) { rows[0] = rows[1] = rows[2] = rows[3] = 0x80808080u; return; }
+    const uint8_t *ref = (mp & RC_MP_FUTURE) ? v.ref[1] : v.ref[0];
+    rc_predict(rows, ref + RC_MP_OFFSET(mp), v.width >> (plane ? 1 : 0), (int)((mp >> 27) & 1), (int)((mp >> 28) & 1));
+}
+
+RC_HD void rc_mc_packed2(const ReconView &v, int plane0, uint32_t mp0, uint32_t rows0[4], int plane1, uint32_t mp1, uint32_t rows1[4])
+{
+    const int hx0 = (int)((mp0 >> 27) & 1), hy0 = (int)((mp0 >> 28) & 1), hx1 = (int)((mp1 >> 27) & 1), hy1 = (int)((mp1 >> 28) & 1);
+#if defined(__CUDA_ARCH__)
+    const bool any_diag = __any_sync(__activemask(), (hx0 & hy0) | (hx1 & hy1));
+#else
+    const bool any_diag = (hx0 & hy0) | (hx1 & hy1);
+#endif
+    const uint8_t *src0 = ((mp0 & RC_MP_FUTURE) ? v.ref[1] : v.ref[0]) + RC_MP_OFFSET(mp0);
+    const uint8_t *src1 = ((mp1 & RC_MP_FUTURE) ? v.ref[1] : v.ref[0]) + RC_MP_OFFSET(mp1);
+    uint32_t W0[10], W1[10];
+    const bool ok0 = !(mp0 & RC_MP_POISON), ok1 = !(mp1 & RC_MP_POISON);
+    if (ok0) rc_predict_load(W0, src0, v.width >> (plane0 ? 1 : 0), hy0);
+    if (ok1) rc_predict_load(W1, src1, v.width >> (plane1 ? 1 : 0), hy1);
+    if (ok0) rc_predict_filter(rows0, W0, (uint32_t)((uintptr_t)src0 & 3), hx0, hy0, any_diag);
+    else rows0[0] = rows0[1] = rows0[2] = rows0[3] = 0x80808080u;
+    if (ok1) rc_predict_filter(rows1, W1, (uint32_t)((uintptr_t)src1 & 3), hx1, hy1, any_diag);
+    else rows1[0] = rows1[1] = rows1[2] = rows1[3] = 0x80808080u;
 }
 
 RC_HD void rc_weighted_block(const ReconView &v, int plane, int bx, int by, uint32_t rows[4])
@@ -448,10 +545,7 @@ RC_HD void rc_weighted_block(const ReconView &v, int plane, int bx, int by, uint
 
 RC_HD void rc_mc_block(const ReconView &v, int plane, int bx, int by, uint32_t t, uint32_t rows[4])
 {
-    RcMotion m;
-    rc_motion(v, plane, bx, by, t, m);
-    if (m.poisoned) { rows[0] = rows[1] = rows[2] = rows[3] = 0x80808080u; return; }
-    rc_predict(rows, m.src, m.stride, m.hx, m.hy);
+    rc_mc_packed(v, plane, rc_motion_pack(v, plane, bx, by, t, rc_mv_word(v, plane, bx, by)), rows);
 }
 
 /* ---- MAP kernel: what can be reconstructed from the maps (and reference frames) alone -------
@@ -512,10 +606,9 @@ RC_HD void rc_record_block(const ReconView &v, int cls, uint32_t len, const uint
     }
     else
     {
-        RcMotion m;
-        rc_motion(v, plane, bx, by, t, m);
-        if (m.poisoned) return;                       /* the map kernel painted it grey */
-        rc_predicted_aot(v, rows, rec + 1, (int)len - 1, m.window);
+        const uint8_t *window = rc_motion_window(v, t, rc_mv_word(v, plane, bx, by));
+        if (!window) return;                          /* the map work painted it grey */
+        rc_predicted_aot(v, rows, rec + 1, (int)len - 1, window);
     }
 }
 

@@ -47,6 +47,7 @@ def emul_lib():
     lib.emul_recon_picture.argtypes = [ctypes.c_void_p] * 4
     lib.emul_weighted.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 5
     lib.emul_predict.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.emul_predict_diag.argtypes = lib.emul_predict.argtypes
     return lib
 
 

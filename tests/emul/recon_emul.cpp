@@ -32,7 +32,12 @@ int emul_recon_picture(const uint8_t *blob, uint8_t *present, const uint8_t *pas
     static uint32_t nest_tab[RC_NEST_TABLE_WORDS];
     if (h.has_nest)
         for (int y = 0; y < SYM_NEST_H; ++y)
-            for (int x = 0; x < 64; ++x) nest_tab[y * 64 + x] = rc_nest_table_entry(blob + h.off_nest, y, x);
+            for (int x = 0; x < 64; ++x)
+            {
+                const uint32_t nibbles8 = rc_nest_table_entry(blob + h.off_nest, y, x);
+                nest_tab[y * 64 + x] = rc_nest_spread_step1(nibbles8);
+                nest_tab[RC_NEST_STEP2_OFF + y * 64 + x] = rc_nest_spread_step2(nibbles8);
+            }
     ReconView v;
     rc_make_view(v, blob, h, nest_tab, g_div, g_mcdiv, past, future);
     uint8_t *planes[3] = {present, present + h.width * h.height, present + h.width * h.height * 5 / 4};
@@ -108,5 +113,15 @@ void emul_predict(uint8_t *dst16, const uint8_t *src, int stride, int hx, int hy
 {
     uint32_t rows[4];
     rc_predict(rows, src, stride, hx, hy);
+    memcpy(dst16, rows, 16);
+}
+
+/* the warp-uniform "some lane needs both half steps" formulation, forced for any phase */
+extern "C" __attribute__((visibility("default")))
+void emul_predict_diag(uint8_t *dst16, const uint8_t *src, int stride, int hx, int hy)
+{
+    uint32_t rows[4], W[10];
+    rc_predict_load(W, src, stride, hy);
+    rc_predict_filter(rows, W, (uint32_t)((uintptr_t)src & 3), hx, hy, true);
     memcpy(dst16, rows, 16);
 }

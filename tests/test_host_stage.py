@@ -143,3 +143,5 @@ def test_kernel_leaf_arithmetic_equals_reference_leaves(emul_lib, oracle):
                     ref.ref_MotionComp4x4(want, 4, ctypes.c_void_p(p), 16, hx, hy)
                     emul_lib.emul_predict(got, ctypes.c_void_p(p), 16, hx, hy)
                     assert bytes(got) == bytes(want), (oy, ox, hx, hy)
+                    emul_lib.emul_predict_diag(got, ctypes.c_void_p(p), 16, hx, hy)
+                    assert bytes(got) == bytes(want), ("diag form", oy, ox, hx, hy)
