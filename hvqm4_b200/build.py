@@ -25,6 +25,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         return LIB
     objs = []
     common = ["-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unknown-pragmas"]
+    common += os.environ.get("HVQM4_EXTRA_CFLAGS", "").split()   # tuning experiments, e.g. -DHVQM4_BAND_WARPS=16
     for src in SOURCES:
         obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
         cmd = [NVCC] + ARCH + common

@@ -243,7 +243,10 @@ recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs, uint32_t cta_
  * Wide pictures are walked in column tiles of kTileMcbs macroblocks so that the queue has a
  * fixed upper size.
  * ------------------------------------------------------------------------------------------ */
-constexpr int kBandWarps = 8;
+#ifndef HVQM4_BAND_WARPS
+#define HVQM4_BAND_WARPS 8
+#endif
+constexpr int kBandWarps = HVQM4_BAND_WARPS;
 constexpr int kTileMcbs = 128;
 
 /* queue capacity of one warp in entries: its four block rows (two luma, one U, one V) of one column tile */
