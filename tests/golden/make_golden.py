@@ -36,6 +36,8 @@ CASES = {
     "min_280x152_v15_IPB": dict(width=280, height=152, version=15, gop="IPBB", n_gops=2, seed=203, profile=0),
     "ragged_328x248_v15_IPB": dict(width=328, height=248, version=15, gop="IPBBP", n_gops=1, seed=204, profile=0),
     "wide_1024x576_v13_IPB": dict(width=1024, height=576, version=13, gop="IPBB", n_gops=1, seed=205, profile=0),
+    # 160 macroblocks per row: more than one column tile of the band kernel (recon.cu kTileMcbs)
+    "hd_1280x720_v15_IPB": dict(width=1280, height=720, version=15, gop="IPBB", n_gops=1, seed=206, profile=0),
 }
 
 
