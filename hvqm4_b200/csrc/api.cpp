@@ -9,7 +9,7 @@
  *     stage (entropy.c) in two parallel phases (sizes, then emission straight into a
  *     pinned arena), ONE cudaMemcpyAsync uploads the whole arena on the copy stream, ONE
  *     kernel launch reconstructs all n pictures on the compute stream;
- *   - arenas are double buffered, so the host stage of step k+1 overlaps upload and
+ *   - arenas form a ring of kArenas, so the host stage of the following steps overlaps upload and
  *     reconstruction of step k; frame surfaces never leave HBM unless asked for.
  *
  * The reference equivalents: the call protocol of main()/decode_video()
@@ -171,6 +171,11 @@ struct StreamState
     int last = -1;                           /* surface holding the most recently decoded picture */
 };
 
+/* arenas (pinned host + device staging of one step) form a ring: the host may run this many steps
+   ahead of the reconstruction, so that a step's gather / entropy work and upload never wait for the
+   read-back chain of the step two before (measured: depth 2 left the copy stream idle ~1 ms per step) */
+constexpr int kArenas = 4;
+
 struct Arena
 {
     uint8_t *h = nullptr;   /* pinned */
@@ -194,7 +199,7 @@ struct HVQM4Batch
     size_t frame_bytes = 0, surf_stride = 0;
     uint8_t *d_surfaces = nullptr;
     std::vector<StreamState> st;
-    Arena arena[2];
+    Arena arena[kArenas];
     int cur = 0;
     cudaStream_t s_copy = nullptr, s_comp = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_d2h = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
@@ -399,7 +404,7 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
 
     /* the parser runs behind the upload on the copy stream, so that step n+1 parses while step n
        reconstructs and reads back; only the reconstruction waits for the previous read-back.
-       Blobs are double-buffered like the arenas. */
+       Blobs are buffered like the arenas. */
     if (!cuda_ok(cudaMemcpyAsync(a.d, a.h, total, cudaMemcpyHostToDevice, b->s_copy), "cudaMemcpyAsync(H2D)")) return HVQM4_ERR_CUDA;
     cudaMemsetAsync(b->d_blob_used, 0, sizeof(unsigned long long), b->s_copy);
     ReconJob *d_jobs = reinterpret_cast<ReconJob *>(a.d + pics_bytes);
@@ -432,7 +437,7 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
     cudaEventRecord(a.consumed, b->s_comp);
     cudaEventRecord(b->ev_kernel, b->s_comp);
     a.in_flight = true;
-    b->cur ^= 1;
+    b->cur = (b->cur + 1) % kArenas;
     b->stats[0] += n;
     b->stats[2] += total;
     return HVQM4_OK;
@@ -465,7 +470,7 @@ H4_API int HVQM4BatchSetEntropyMode(HVQM4Batch *b, int gpu)
         if (!b->eslot) return HVQM4_ERR_GEOMETRY;
         b->blobs_cap = (size_t)b->n_streams * align_up(2 * b->frame_bytes, 256);
         if (!cuda_ok(cudaMalloc((void **)&b->d_estate, b->eslot * (size_t)b->n_streams), "cudaMalloc(entropy state)") ||
-            !cuda_ok(cudaMalloc((void **)&b->d_blobs, 2 * b->blobs_cap), "cudaMalloc(blob arena)") ||
+            !cuda_ok(cudaMalloc((void **)&b->d_blobs, kArenas * b->blobs_cap), "cudaMalloc(blob arena)") ||
             !cuda_ok(cudaMalloc((void **)&b->d_blob_used, sizeof(unsigned long long)), "cudaMalloc") ||
             !cuda_ok(cudaMalloc((void **)&b->d_eerrors, sizeof(uint32_t)), "cudaMalloc") ||
             !cuda_ok(cudaMemset(b->d_eerrors, 0, sizeof(uint32_t)), "cudaMemset"))
@@ -578,7 +583,7 @@ H4_API int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, con
     cudaEventRecord(a.consumed, b->s_comp);
     cudaEventRecord(b->ev_kernel, b->s_comp);
     a.in_flight = true;
-    b->cur ^= 1;
+    b->cur = (b->cur + 1) % kArenas;
 
     const uint64_t mcbs = (uint64_t)b->mcb_w * b->mcb_h * n;
     b->stats[0] += n;
