@@ -168,6 +168,7 @@ struct StreamState
 {
     H4Seq *seq = nullptr;
     int past = 0, present = 1, future = 2;   /* surface indices, rotated like the reference's Player */
+    int spare = 3;                           /* B pictures alternate between `present` and this one (see batch_after_picture) */
     int last = -1;                           /* surface holding the most recently decoded picture */
 };
 
@@ -175,6 +176,14 @@ struct StreamState
    ahead of the reconstruction, so that a step's gather / entropy work and upload never wait for the
    read-back chain of the step two before (measured: depth 2 left the copy stream idle ~1 ms per step) */
 constexpr int kArenas = 4;
+
+/* Frame surfaces per stream: the reference's three (past / present / future, h4m:2343-2349) plus a
+   spare.  A B picture is never a reference (h4m:2063-2064), so the next picture may be written
+   into a different surface than the B picture that is still being read back: `present` and the
+   spare swap after every B picture, and a step only has to wait for the read-backs issued before
+   the PREVIOUS step instead of for the previous step's own (which would put every reconstruction
+   between two read-backs on the PCIe critical path). */
+constexpr int kSurfaces = 4;
 
 struct Arena
 {
@@ -202,8 +211,14 @@ struct HVQM4Batch
     Arena arena[kArenas];
     int cur = 0;
     cudaStream_t s_copy = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    cudaStream_t s_copy2 = nullptr;                 /* GPU entropy mode: odd steps upload + parse here, even steps on s_copy */
+    cudaEvent_t ev_parse[2] = {nullptr, nullptr};
+    bool prev_step_had_ipic = false;
+    int step_parity = 0;
     cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_d2h = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     bool d2h_pending = false;
+    cudaEvent_t ev_d2h_mark[2] = {nullptr, nullptr};   /* read-backs issued before step n, n - 1 (batch_wait_readbacks) */
+    unsigned step_no = 0;
     Pool *pool = nullptr;
     uint32_t errors = 0;
     bool recording = false;
@@ -229,8 +244,20 @@ struct HVQM4Batch
     cudaEvent_t ev_rgb_src[2] = {nullptr, nullptr}, ev_rgb = nullptr;
     int rgb_cur = 0;
 
-    uint8_t *surface(int stream, int idx) const { return d_surfaces + ((size_t)stream * 3 + idx) * surf_stride; }
+    uint8_t *surface(int stream, int idx) const { return d_surfaces + ((size_t)stream * kSurfaces + idx) * surf_stride; }
 };
+
+/* Called once per step before its reconstruction is enqueued: the surfaces the step writes were
+   last read back two steps ago or earlier (kSurfaces), so the compute stream waits for the
+   read-backs that had been issued when the previous step was submitted. */
+static void batch_wait_readbacks(HVQM4Batch *b)
+{
+    const unsigned slot = b->step_no & 1;
+    cudaEventRecord(b->ev_d2h_mark[slot], b->s_d2h);
+    cudaStreamWaitEvent(b->s_comp, b->ev_d2h_mark[slot ^ 1], 0);
+    ++b->step_no;
+    b->d2h_pending = false;
+}
 
 static bool arena_reserve(HVQM4Batch *b, Arena &a, size_t need)
 {
@@ -277,15 +304,20 @@ H4_API HVQM4Batch *HVQM4BatchCreate(int device, int n_streams, int width, int he
     /* 256-byte aligned surfaces with a tail so that the aligned 8-byte row reads of the
        half-sample filter never leave the allocation */
     b->surf_stride = align_up(b->frame_bytes + 64, 256);
-    size_t total = b->surf_stride * 3 * (size_t)n_streams + 256;
+    size_t total = b->surf_stride * kSurfaces * (size_t)n_streams + 256;
     if (!cuda_ok(cudaMalloc((void **)&b->d_surfaces, total), "cudaMalloc(surfaces)") ||
         !cuda_ok(cudaMemset(b->d_surfaces, 0, total), "cudaMemset(surfaces)") ||
         !cuda_ok(cudaStreamCreateWithFlags(&b->s_copy, cudaStreamNonBlocking), "cudaStreamCreate") ||
+        !cuda_ok(cudaStreamCreateWithFlags(&b->s_copy2, cudaStreamNonBlocking), "cudaStreamCreate") ||
+        !cuda_ok(cudaEventCreateWithFlags(&b->ev_parse[0], cudaEventDisableTiming), "cudaEventCreate") ||
+        !cuda_ok(cudaEventCreateWithFlags(&b->ev_parse[1], cudaEventDisableTiming), "cudaEventCreate") ||
         !cuda_ok(cudaStreamCreateWithFlags(&b->s_comp, cudaStreamNonBlocking), "cudaStreamCreate") ||
         !cuda_ok(cudaStreamCreateWithFlags(&b->s_d2h, cudaStreamNonBlocking), "cudaStreamCreate") ||
         !cuda_ok(cudaEventCreateWithFlags(&b->ev_h2d, cudaEventDisableTiming), "cudaEventCreate") ||
         !cuda_ok(cudaEventCreateWithFlags(&b->ev_kernel, cudaEventDisableTiming), "cudaEventCreate") ||
         !cuda_ok(cudaEventCreateWithFlags(&b->ev_d2h, cudaEventDisableTiming), "cudaEventCreate") ||
+        !cuda_ok(cudaEventCreateWithFlags(&b->ev_d2h_mark[0], cudaEventDisableTiming), "cudaEventCreate") ||
+        !cuda_ok(cudaEventCreateWithFlags(&b->ev_d2h_mark[1], cudaEventDisableTiming), "cudaEventCreate") ||
         !cuda_ok(cudaEventCreate(&b->ev_t0), "cudaEventCreate") || !cuda_ok(cudaEventCreate(&b->ev_t1), "cudaEventCreate"))
     {
         HVQM4BatchDestroy(b);
@@ -339,9 +371,12 @@ H4_API void HVQM4BatchDestroy(HVQM4Batch *b)
     if (b->d_blob_used) cudaFree(b->d_blob_used);
     if (b->d_eerrors) cudaFree(b->d_eerrors);
     if (b->s_copy) cudaStreamDestroy(b->s_copy);
+    if (b->s_copy2) cudaStreamDestroy(b->s_copy2);
+    for (cudaEvent_t e : b->ev_parse)
+        if (e) cudaEventDestroy(e);
     if (b->s_comp) cudaStreamDestroy(b->s_comp);
     if (b->s_d2h) cudaStreamDestroy(b->s_d2h);
-    for (cudaEvent_t e : {b->ev_h2d, b->ev_kernel, b->ev_d2h, b->ev_t0, b->ev_t1})
+    for (cudaEvent_t e : {b->ev_h2d, b->ev_kernel, b->ev_d2h, b->ev_t0, b->ev_t1, b->ev_d2h_mark[0], b->ev_d2h_mark[1]})
         if (e) cudaEventDestroy(e);
     delete b;
 }
@@ -398,26 +433,33 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
         jobs[i].pad[0] = jobs[i].pad[1] = 0;
         s.last = s.present;
         if (t != SYM_PIC_B) std::swap(s.present, s.future);
+        else std::swap(s.present, s.spare);
     }
     auto t_host1 = std::chrono::steady_clock::now();
     b->stats[4] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_host1 - t_host0).count();
 
-    /* the parser runs behind the upload on the copy stream, so that step n+1 parses while step n
-       reconstructs and reads back; only the reconstruction waits for the previous read-back.
-       Blobs are buffered like the arenas. */
-    if (!cuda_ok(cudaMemcpyAsync(a.d, a.h, total, cudaMemcpyHostToDevice, b->s_copy), "cudaMemcpyAsync(H2D)")) return HVQM4_ERR_CUDA;
-    cudaMemsetAsync(b->d_blob_used, 0, sizeof(unsigned long long), b->s_copy);
+    /* Upload and parser run on one of two streams, alternating per step, so that the parse kernels
+       of two consecutive steps are in flight together (a warp per picture is latency bound: a
+       thousand warps leave most of the GPU idle) while the steps before reconstruct and read
+       back.  Parser slots and blob counters alternate with the stream; blob arenas follow the
+       staging ring.  A step that contains an I picture runs alone: it rewrites the nest that both
+       slots of its stream read. */
+    const int par = b->step_parity;
+    b->step_parity ^= 1;
+    cudaStream_t sp = par ? b->s_copy2 : b->s_copy;
+    bool has_ipic = false;
+    for (int i = 0; i < n && !has_ipic; ++i) has_ipic = frame_types[i] == SYM_PIC_I;
+    if (has_ipic || b->prev_step_had_ipic) cudaStreamWaitEvent(sp, b->ev_parse[par ^ 1], 0);
+    b->prev_step_had_ipic = has_ipic;
+    if (!cuda_ok(cudaMemcpyAsync(a.d, a.h, total, cudaMemcpyHostToDevice, sp), "cudaMemcpyAsync(H2D)")) return HVQM4_ERR_CUDA;
+    cudaMemsetAsync(b->d_blob_used + par, 0, sizeof(unsigned long long), sp);
     ReconJob *d_jobs = reinterpret_cast<ReconJob *>(a.d + pics_bytes);
-    int rc = hvqm4_dev_entropy_parse(b->d_estate, b->eslot, reinterpret_cast<const H4DevPicture *>(a.d), n,
-                                     b->d_blobs + (size_t)b->cur * b->blobs_cap, b->d_blob_used, (unsigned long long)b->blobs_cap,
-                                     d_jobs, b->d_eerrors, b->s_copy);
-    cudaEventRecord(b->ev_h2d, b->s_copy);
-    cudaStreamWaitEvent(b->s_comp, b->ev_h2d, 0);
-    if (b->d2h_pending)
-    {
-        cudaStreamWaitEvent(b->s_comp, b->ev_d2h, 0);
-        b->d2h_pending = false;
-    }
+    int rc = hvqm4_dev_entropy_parse(b->d_estate, b->eslot, reinterpret_cast<const H4DevPicture *>(a.d), n, par,
+                                     b->d_blobs + (size_t)b->cur * b->blobs_cap, b->d_blob_used + par, (unsigned long long)b->blobs_cap,
+                                     d_jobs, b->d_eerrors, sp);
+    cudaEventRecord(b->ev_parse[par], sp);
+    cudaStreamWaitEvent(b->s_comp, b->ev_parse[par], 0);
+    batch_wait_readbacks(b);
     if (rc == 0)
     {
         ++g_launches;
@@ -469,9 +511,9 @@ H4_API int HVQM4BatchSetEntropyMode(HVQM4Batch *b, int gpu)
         b->eslot = hvqm4_dev_entropy_slot_bytes(b->width, b->height, sym_cap, work_cap);
         if (!b->eslot) return HVQM4_ERR_GEOMETRY;
         b->blobs_cap = (size_t)b->n_streams * align_up(2 * b->frame_bytes, 256);
-        if (!cuda_ok(cudaMalloc((void **)&b->d_estate, b->eslot * (size_t)b->n_streams), "cudaMalloc(entropy state)") ||
+        if (!cuda_ok(cudaMalloc((void **)&b->d_estate, b->eslot * (size_t)b->n_streams * 2), "cudaMalloc(entropy state)") ||
             !cuda_ok(cudaMalloc((void **)&b->d_blobs, kArenas * b->blobs_cap), "cudaMalloc(blob arena)") ||
-            !cuda_ok(cudaMalloc((void **)&b->d_blob_used, sizeof(unsigned long long)), "cudaMalloc") ||
+            !cuda_ok(cudaMalloc((void **)&b->d_blob_used, 2 * sizeof(unsigned long long)), "cudaMalloc") ||
             !cuda_ok(cudaMalloc((void **)&b->d_eerrors, sizeof(uint32_t)), "cudaMalloc") ||
             !cuda_ok(cudaMemset(b->d_eerrors, 0, sizeof(uint32_t)), "cudaMemset"))
             return HVQM4_ERR_NOMEM;
@@ -559,6 +601,7 @@ H4_API int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, con
         jobs[i].future = b->surface(stream_ids[i], t == SYM_PIC_P ? s.present : s.future);
         s.last = s.present;
         if (t != SYM_PIC_B) std::swap(s.present, s.future);
+        else std::swap(s.present, s.spare);
     }
     auto t_host1 = std::chrono::steady_clock::now();
     b->stats[4] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_host1 - t_host0).count();
@@ -566,11 +609,7 @@ H4_API int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, con
     if (!cuda_ok(cudaMemcpyAsync(d_base, a.h, total, cudaMemcpyHostToDevice, b->s_copy), "cudaMemcpyAsync(H2D)")) return HVQM4_ERR_CUDA;
     cudaEventRecord(b->ev_h2d, b->s_copy);
     cudaStreamWaitEvent(b->s_comp, b->ev_h2d, 0);
-    if (b->d2h_pending)
-    {   /* the previous step's read-backs must finish before surfaces are overwritten */
-        cudaStreamWaitEvent(b->s_comp, b->ev_d2h, 0);
-        b->d2h_pending = false;
-    }
+    batch_wait_readbacks(b);
     int launched = 0;
     int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(d_base), n, b->mcb_w, b->mcb_h, b->rec_prefix.data(), b->s_comp, &launched);
     g_launches += launched;
@@ -601,7 +640,8 @@ H4_API int HVQM4BatchSync(HVQM4Batch *b)
     cudaSetDevice(b->device);
     uint32_t e = b->errors;
     b->errors = 0;
-    bool ok = cuda_ok(cudaStreamSynchronize(b->s_copy), "sync copy") & cuda_ok(cudaStreamSynchronize(b->s_comp), "sync compute") &
+    bool ok = cuda_ok(cudaStreamSynchronize(b->s_copy), "sync copy") & cuda_ok(cudaStreamSynchronize(b->s_copy2), "sync copy 2") &
+              cuda_ok(cudaStreamSynchronize(b->s_comp), "sync compute") &
               cuda_ok(cudaStreamSynchronize(b->s_d2h), "sync d2h");
     for (auto &a : b->arena) a.in_flight = false;
     b->d2h_pending = false;
@@ -651,7 +691,7 @@ H4_API int HVQM4BatchReadFramesAsync(HVQM4Batch *b, int n, const int32_t *stream
     {
         cudaSetDevice(b->device);
         if (!b->d2h_pending) cudaStreamWaitEvent(b->s_d2h, b->ev_kernel, 0);
-        if (!cuda_ok(cudaMemcpy2DAsync(host_base, host_stride, b->surface(stream_ids[0], b->st[stream_ids[0]].last), 3 * b->surf_stride,
+        if (!cuda_ok(cudaMemcpy2DAsync(host_base, host_stride, b->surface(stream_ids[0], b->st[stream_ids[0]].last), kSurfaces * b->surf_stride,
                                        b->frame_bytes, (size_t)n, cudaMemcpyDeviceToHost, b->s_d2h), "cudaMemcpy2DAsync(D2H)"))
             return HVQM4_ERR_CUDA;
         cudaEventRecord(b->ev_d2h, b->s_d2h);
@@ -697,11 +737,9 @@ H4_API int HVQM4BatchReadFramesRGBAsync(HVQM4Batch *b, int n, const int32_t *str
     b->rgb_cur ^= 1;
     cudaEventSynchronize(b->ev_rgb_src[r]);               /* the copy that last used this pointer ring is done */
     for (int i = 0; i < n; ++i) b->h_rgb_src[r][i] = b->surface(stream_ids[i], b->st[stream_ids[i]].last);
-    if (b->d2h_pending)
-    {   /* the staging frames may still be on their way out */
-        cudaStreamWaitEvent(b->s_comp, b->ev_d2h, 0);
-        b->d2h_pending = false;
-    }
+    /* the staging frames of the previous call may still be on their way out */
+    cudaStreamWaitEvent(b->s_comp, b->ev_d2h, 0);
+    b->d2h_pending = false;
     if (!cuda_ok(cudaMemcpyAsync((void *)b->d_rgb_src[r], (const void *)b->h_rgb_src[r], sizeof(void *) * n, cudaMemcpyHostToDevice, b->s_comp),
                  "cudaMemcpyAsync(frame pointers)"))
         return HVQM4_ERR_CUDA;

@@ -124,10 +124,12 @@ int HVQM4ConvertRGB(SeqObj *seqobj, const void *frame, void *rgb);
 
 /* ---------------------------------------------------------------- batched decoding
  * A batch is a pool of `n_streams` independent streams of identical geometry living on
- * one GPU: three device-resident frame surfaces per stream (past/present/future, rotated
- * by the library with the reference's rule), per-stream host entropy state, a pool of
- * host threads, and double-buffered pinned/device symbol arenas so that the entropy
- * decode of step k+1 overlaps the upload and reconstruction of step k.
+ * one GPU: four device-resident frame surfaces per stream (past/present/future, rotated by
+ * the library with the reference's rule, plus a spare that consecutive B pictures alternate
+ * with so that a picture can be read back while the next one is reconstructed), per-stream
+ * entropy state, a pool of host threads, and a ring of pinned/device staging arenas so that
+ * the entropy decode and upload of the following steps overlap the reconstruction and
+ * read-back of step k.
  */
 typedef struct HVQM4Batch HVQM4Batch;
 

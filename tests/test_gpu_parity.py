@@ -307,3 +307,42 @@ def test_rgb_of_decoded_frames_sdk_and_batch(native_lib, oracle):
                 assert rgb == [want[k]] * 3, k
         finally:
             batch.close()
+
+
+@pytest.mark.parametrize("gpu_entropy", [False, True])
+def test_pipelined_steps_with_async_readback_match_oracle(native_lib, oracle, gpu_entropy):
+    """The way bench.py's end-to-end arm drives the batch runtime: every step of a GOP submitted
+    back to back, each followed by an asynchronous read-back of all frames into its own pinned
+    buffer, one sync at the end.  Uploads, entropy stage, reconstruction and read-backs of
+    neighbouring steps overlap (staging ring, alternating parser slots, spare B surface), so every
+    frame of every step is compared with the oracle: a missing dependency shows up as a torn frame."""
+    S, distinct, gop = 96, 3, "IPBBPBBPBB"
+    files = [synth.generate(640, 480, 15, gop, 1, seed=8300 + i, profile=i & 1) for i in range(distinct)]
+    want = [[md5(yuv) for _, _, _, yuv in oracle.PortDecoder(f).frames()] for f in files]
+    parsed = [native_lib.parse_file(f) for f in files]
+    bufs = [ctypes.create_string_buffer(f, len(f) + 8) for f in files]
+    bases = [ctypes.addressof(b) for b in bufs]
+    n_steps = len(parsed[0][1])
+    batch = native_lib.Batch(S, 640, 480, 15, gpu_entropy=gpu_entropy)
+    fb = batch.frame_bytes
+    pinned = native_lib.lib().HVQM4HostAlloc(n_steps * S * fb)
+    assert pinned
+    try:
+        ids = list(range(S))
+        ids_arr = (ctypes.c_int32 * S)(*ids)
+        for rep in range(2):            # second GOP: the rings have wrapped and every surface has been in every role
+            for k in range(n_steps):
+                frs = [parsed[i % distinct][1][k] for i in range(S)]
+                step = native_lib.Batch.prepare_step(ids, [f.frame_type for f in frs], [bases[i % distinct] + frs[i].offset for i in range(S)],
+                                                     [f.bytes for f in frs])
+                batch.decode_prepared(step)
+                batch.read_frames_async(ids_arr, S, pinned + k * S * fb, fb)
+            batch.sync()
+            raw = ctypes.string_at(pinned, n_steps * S * fb)
+            for k in range(n_steps):
+                for i in range(S):
+                    got = md5(raw[(k * S + i) * fb:(k * S + i + 1) * fb])
+                    assert got == want[i % distinct][k], (rep, k, i)
+    finally:
+        batch.close()
+        native_lib.lib().HVQM4HostFree(pinned)
