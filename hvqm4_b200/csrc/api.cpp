@@ -211,10 +211,10 @@ struct HVQM4Batch
     Arena arena[kArenas];
     int cur = 0;
     cudaStream_t s_copy = nullptr, s_comp = nullptr, s_d2h = nullptr;
-    cudaStream_t s_copy2 = nullptr;                 /* GPU entropy mode: odd steps upload + parse here, even steps on s_copy */
-    cudaEvent_t ev_parse[2] = {nullptr, nullptr};
-    bool prev_step_had_ipic = false;
-    int step_parity = 0;
+    /* GPU entropy mode: consecutive steps upload + parse on these streams in turn (s_parse[0] = s_copy) */
+    cudaStream_t s_parse[H4_PARSE_SLOTS] = {};
+    cudaEvent_t ev_parse[H4_PARSE_SLOTS] = {};
+    int parse_turn = 0, ipic_slot = 0, ipic_fence_left = 0;
     cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_d2h = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     bool d2h_pending = false;
     cudaEvent_t ev_d2h_mark[2] = {nullptr, nullptr};   /* read-backs issued before step n, n - 1 (batch_wait_readbacks) */
@@ -246,6 +246,17 @@ struct HVQM4Batch
 
     uint8_t *surface(int stream, int idx) const { return d_surfaces + ((size_t)stream * kSurfaces + idx) * surf_stride; }
 };
+
+static bool batch_create_parse_streams(HVQM4Batch *b)
+{
+    b->s_parse[0] = b->s_copy;
+    for (int j = 0; j < H4_PARSE_SLOTS; ++j)
+    {
+        if (j && !cuda_ok(cudaStreamCreateWithFlags(&b->s_parse[j], cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+        if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_parse[j], cudaEventDisableTiming), "cudaEventCreate")) return false;
+    }
+    return true;
+}
 
 /* Called once per step before its reconstruction is enqueued: the surfaces the step writes were
    last read back two steps ago or earlier (kSurfaces), so the compute stream waits for the
@@ -308,9 +319,7 @@ H4_API HVQM4Batch *HVQM4BatchCreate(int device, int n_streams, int width, int he
     if (!cuda_ok(cudaMalloc((void **)&b->d_surfaces, total), "cudaMalloc(surfaces)") ||
         !cuda_ok(cudaMemset(b->d_surfaces, 0, total), "cudaMemset(surfaces)") ||
         !cuda_ok(cudaStreamCreateWithFlags(&b->s_copy, cudaStreamNonBlocking), "cudaStreamCreate") ||
-        !cuda_ok(cudaStreamCreateWithFlags(&b->s_copy2, cudaStreamNonBlocking), "cudaStreamCreate") ||
-        !cuda_ok(cudaEventCreateWithFlags(&b->ev_parse[0], cudaEventDisableTiming), "cudaEventCreate") ||
-        !cuda_ok(cudaEventCreateWithFlags(&b->ev_parse[1], cudaEventDisableTiming), "cudaEventCreate") ||
+        !batch_create_parse_streams(b) ||
         !cuda_ok(cudaStreamCreateWithFlags(&b->s_comp, cudaStreamNonBlocking), "cudaStreamCreate") ||
         !cuda_ok(cudaStreamCreateWithFlags(&b->s_d2h, cudaStreamNonBlocking), "cudaStreamCreate") ||
         !cuda_ok(cudaEventCreateWithFlags(&b->ev_h2d, cudaEventDisableTiming), "cudaEventCreate") ||
@@ -371,7 +380,8 @@ H4_API void HVQM4BatchDestroy(HVQM4Batch *b)
     if (b->d_blob_used) cudaFree(b->d_blob_used);
     if (b->d_eerrors) cudaFree(b->d_eerrors);
     if (b->s_copy) cudaStreamDestroy(b->s_copy);
-    if (b->s_copy2) cudaStreamDestroy(b->s_copy2);
+    for (int j = 1; j < H4_PARSE_SLOTS; ++j)
+        if (b->s_parse[j]) cudaStreamDestroy(b->s_parse[j]);
     for (cudaEvent_t e : b->ev_parse)
         if (e) cudaEventDestroy(e);
     if (b->s_comp) cudaStreamDestroy(b->s_comp);
@@ -438,19 +448,29 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
     auto t_host1 = std::chrono::steady_clock::now();
     b->stats[4] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_host1 - t_host0).count();
 
-    /* Upload and parser run on one of two streams, alternating per step, so that the parse kernels
-       of two consecutive steps are in flight together (a warp per picture is latency bound: a
+    /* Upload and parser run on one of H4_PARSE_SLOTS streams, taken in turn, so that the parse
+       kernels of consecutive steps are in flight together (a warp per picture is latency bound: a
        thousand warps leave most of the GPU idle) while the steps before reconstruct and read
-       back.  Parser slots and blob counters alternate with the stream; blob arenas follow the
-       staging ring.  A step that contains an I picture runs alone: it rewrites the nest that both
-       slots of its stream read. */
-    const int par = b->step_parity;
-    b->step_parity ^= 1;
-    cudaStream_t sp = par ? b->s_copy2 : b->s_copy;
+       back.  Parser slots and blob counters go with the stream; blob arenas follow the staging
+       ring.  A step that contains an I picture runs alone: it rewrites the nest that every slot of
+       its stream reads -- it waits for the parsers in flight, and the next steps wait for it. */
+    const int par = b->parse_turn;
+    b->parse_turn = (par + 1) % H4_PARSE_SLOTS;
+    cudaStream_t sp = b->s_parse[par];
     bool has_ipic = false;
     for (int i = 0; i < n && !has_ipic; ++i) has_ipic = frame_types[i] == SYM_PIC_I;
-    if (has_ipic || b->prev_step_had_ipic) cudaStreamWaitEvent(sp, b->ev_parse[par ^ 1], 0);
-    b->prev_step_had_ipic = has_ipic;
+    if (has_ipic)
+    {
+        for (int j = 0; j < H4_PARSE_SLOTS; ++j)
+            if (j != par) cudaStreamWaitEvent(sp, b->ev_parse[j], 0);
+        b->ipic_slot = par;
+        b->ipic_fence_left = H4_PARSE_SLOTS - 1;
+    }
+    else if (b->ipic_fence_left > 0)
+    {
+        cudaStreamWaitEvent(sp, b->ev_parse[b->ipic_slot], 0);
+        --b->ipic_fence_left;
+    }
     if (!cuda_ok(cudaMemcpyAsync(a.d, a.h, total, cudaMemcpyHostToDevice, sp), "cudaMemcpyAsync(H2D)")) return HVQM4_ERR_CUDA;
     cudaMemsetAsync(b->d_blob_used + par, 0, sizeof(unsigned long long), sp);
     ReconJob *d_jobs = reinterpret_cast<ReconJob *>(a.d + pics_bytes);
@@ -511,9 +531,9 @@ H4_API int HVQM4BatchSetEntropyMode(HVQM4Batch *b, int gpu)
         b->eslot = hvqm4_dev_entropy_slot_bytes(b->width, b->height, sym_cap, work_cap);
         if (!b->eslot) return HVQM4_ERR_GEOMETRY;
         b->blobs_cap = (size_t)b->n_streams * align_up(2 * b->frame_bytes, 256);
-        if (!cuda_ok(cudaMalloc((void **)&b->d_estate, b->eslot * (size_t)b->n_streams * 2), "cudaMalloc(entropy state)") ||
+        if (!cuda_ok(cudaMalloc((void **)&b->d_estate, b->eslot * (size_t)b->n_streams * H4_PARSE_SLOTS), "cudaMalloc(entropy state)") ||
             !cuda_ok(cudaMalloc((void **)&b->d_blobs, kArenas * b->blobs_cap), "cudaMalloc(blob arena)") ||
-            !cuda_ok(cudaMalloc((void **)&b->d_blob_used, 2 * sizeof(unsigned long long)), "cudaMalloc") ||
+            !cuda_ok(cudaMalloc((void **)&b->d_blob_used, H4_PARSE_SLOTS * sizeof(unsigned long long)), "cudaMalloc") ||
             !cuda_ok(cudaMalloc((void **)&b->d_eerrors, sizeof(uint32_t)), "cudaMalloc") ||
             !cuda_ok(cudaMemset(b->d_eerrors, 0, sizeof(uint32_t)), "cudaMemset"))
             return HVQM4_ERR_NOMEM;
@@ -640,9 +660,9 @@ H4_API int HVQM4BatchSync(HVQM4Batch *b)
     cudaSetDevice(b->device);
     uint32_t e = b->errors;
     b->errors = 0;
-    bool ok = cuda_ok(cudaStreamSynchronize(b->s_copy), "sync copy") & cuda_ok(cudaStreamSynchronize(b->s_copy2), "sync copy 2") &
-              cuda_ok(cudaStreamSynchronize(b->s_comp), "sync compute") &
+    bool ok = cuda_ok(cudaStreamSynchronize(b->s_comp), "sync compute") &
               cuda_ok(cudaStreamSynchronize(b->s_d2h), "sync d2h");
+    for (cudaStream_t sp : b->s_parse) ok = cuda_ok(cudaStreamSynchronize(sp), "sync copy") && ok;
     for (auto &a : b->arena) a.in_flight = false;
     b->d2h_pending = false;
     if (ok && b->d_eerrors)

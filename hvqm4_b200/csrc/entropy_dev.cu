@@ -60,10 +60,10 @@ __global__ void dev_init_kernel(uint8_t *arena, size_t slot_bytes, int n_streams
 }
 
 /* one warp per picture: the entry points of entropy.c are warp-collective in the device build.
-   Every stream owns TWO parser slots (scratch + state) used by alternating steps (`parity`), so
-   that the parse kernels of two consecutive steps can be in flight together; the only state a
-   picture inherits is the nest of the last I picture, which an I picture therefore also writes
-   into the sibling slot (the runtime keeps I-picture steps exclusive, api.cpp). */
+   Every stream owns H4_PARSE_SLOTS parser slots (scratch + state) used by consecutive steps in
+   turn (`parity`), so that the parse kernels of consecutive steps can be in flight together; the
+   only state a picture inherits is the nest of the last I picture, which an I picture therefore
+   also writes into the sibling slots (the runtime keeps I-picture steps exclusive, api.cpp). */
 __global__ void __launch_bounds__(32)
 dev_parse_kernel(uint8_t *arena, size_t slot_bytes, const H4DevPicture *pics, int n_pics, int parity, uint8_t *blob_arena,
                  unsigned long long *blob_used, unsigned long long blob_cap, ReconJob *jobs, uint32_t *errors)
@@ -72,7 +72,7 @@ dev_parse_kernel(uint8_t *arena, size_t slot_bytes, const H4DevPicture *pics, in
     if (i >= n_pics) return;
     const int lane = threadIdx.x;
     const H4DevPicture pic = pics[i];
-    H4Seq *s = slot_seq(arena, slot_bytes, pic.stream * 2 + parity);
+    H4Seq *s = slot_seq(arena, slot_bytes, pic.stream * H4_PARSE_SLOTS + parity);
     const size_t bytes = h4e_parse_begin(s, pic.pic_type, pic.data, pic.bytes);
     uint32_t err = 0;
     uint8_t *blob = nullptr;
@@ -88,9 +88,13 @@ dev_parse_kernel(uint8_t *arena, size_t slot_bytes, const H4DevPicture *pics, in
             err = h4e_parse_finish(s, blob);
             if (pic.pic_type == SYM_PIC_I)
             {
-                H4Seq *sibling = slot_seq(arena, slot_bytes, pic.stream * 2 + (parity ^ 1));
                 __syncwarp();
-                for (int k = lane; k < SYM_NEST_BYTES; k += 32) sibling->nest[k] = s->nest[k];
+                for (int j = 0; j < H4_PARSE_SLOTS; ++j)
+                {
+                    if (j == parity) continue;
+                    H4Seq *sibling = slot_seq(arena, slot_bytes, pic.stream * H4_PARSE_SLOTS + j);
+                    for (int k = lane; k < SYM_NEST_BYTES; k += 32) sibling->nest[k] = s->nest[k];
+                }
             }
         }
         else
@@ -131,7 +135,7 @@ extern "C" size_t hvqm4_dev_entropy_slot_bytes(int width, int height, uint32_t s
 extern "C" int hvqm4_dev_entropy_init(uint8_t *arena, size_t slot_bytes, int n_streams, int width, int height, int version15,
                                       uint32_t sym_cap, uint32_t work_cap, cudaStream_t stream)
 {
-    const int n_slots = 2 * n_streams;   /* two per stream, see dev_parse_kernel */
+    const int n_slots = H4_PARSE_SLOTS * n_streams;   /* see dev_parse_kernel */
     dev_init_kernel<<<(n_slots + 63) / 64, 64, 0, stream>>>(arena, slot_bytes, n_slots, width, height, version15, sym_cap, work_cap);
     return (int)cudaGetLastError();
 }
@@ -141,6 +145,6 @@ extern "C" int hvqm4_dev_entropy_parse(uint8_t *arena, size_t slot_bytes, const 
                                        uint32_t *d_errors, cudaStream_t stream)
 {
     if (n_pics <= 0) return 0;
-    dev_parse_kernel<<<n_pics, 32, 0, stream>>>(arena, slot_bytes, d_pics, n_pics, parity & 1, blob_arena, d_blob_used, blob_cap, d_jobs, d_errors);
+    dev_parse_kernel<<<n_pics, 32, 0, stream>>>(arena, slot_bytes, d_pics, n_pics, parity, blob_arena, d_blob_used, blob_cap, d_jobs, d_errors);
     return (int)cudaGetLastError();
 }

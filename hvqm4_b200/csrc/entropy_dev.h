@@ -21,12 +21,17 @@ struct ReconJob;
 #ifdef __cplusplus
 extern "C" {
 #endif
-/* bytes of device memory ONE parser slot needs (0 on unsupported geometry); a stream owns two
-   slots, used by alternating steps, so the arena is 2 * n_streams slots */
+/* Parser slots per stream = parse kernels of consecutive steps that may be in flight together. */
+#ifndef H4_PARSE_SLOTS
+#define H4_PARSE_SLOTS 2
+#endif
+
+/* bytes of device memory ONE parser slot needs (0 on unsupported geometry); a stream owns
+   H4_PARSE_SLOTS slots, used by consecutive steps in turn, so the arena is H4_PARSE_SLOTS * n_streams slots */
 size_t hvqm4_dev_entropy_slot_bytes(int width, int height, uint32_t sym_cap, uint32_t work_cap);
 int hvqm4_dev_entropy_init(uint8_t *arena, size_t slot_bytes, int n_streams, int width, int height, int version15,
                            uint32_t sym_cap, uint32_t work_cap, cudaStream_t stream);
-/* parses n_pics pictures (one warp each) in the slots of `parity`, bump-allocates their symbol
+/* parses n_pics pictures (one warp each) in the slots number `parity` (0 .. H4_PARSE_SLOTS - 1), bump-allocates their symbol
    buffers in blob_arena and fills jobs[i].blob / jobs[i].n_chunks (the surface pointers of jobs[]
    are filled by the host) */
 int hvqm4_dev_entropy_parse(uint8_t *arena, size_t slot_bytes, const H4DevPicture *d_pics, int n_pics, int parity, uint8_t *blob_arena,
