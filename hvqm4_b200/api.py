@@ -23,6 +23,8 @@ from .build import LIB
 
 I_FRAME, P_FRAME, B_FRAME = 0x10, 0x20, 0x30
 
+ERR_TRUNCATED = 1 << 0
+ERR_OVERFLOW = 1 << 6
 ERR_NO_DEVICE = 1 << 16
 ERR_CUDA = 1 << 17
 ERR_ARGUMENT = 1 << 18
@@ -44,11 +46,20 @@ class VideoInfo(ctypes.Structure):
 
 
 class FileInfo(ctypes.Structure):
-    _fields_ = [(n, c_int32) for n in ("version", "width", "height", "h_samp", "v_samp", "n_gops", "n_video_frames", "usec_per_frame")]
+    _fields_ = [(n, c_int32) for n in ("version", "width", "height", "h_samp", "v_samp", "n_gops", "n_video_frames", "usec_per_frame",
+                                       "n_audio_frames", "audio_channels", "audio_bits", "audio_format", "audio_sample_rate")]
 
 
 class FrameRef(ctypes.Structure):
     _fields_ = [("offset", c_uint32), ("bytes", c_uint32), ("frame_type", c_uint16), ("gop", c_uint16), ("disp_id", c_uint32)]
+
+
+class AudioRef(ctypes.Structure):
+    _fields_ = [("offset", c_uint32), ("bytes", c_uint32), ("gop", c_uint16), ("first", c_uint16), ("samples", c_uint32)]
+
+
+class AudioState(ctypes.Structure):
+    _fields_ = [("hist", ctypes.c_int16 * 2), ("idx", ctypes.c_int8 * 2), ("pad", ctypes.c_int8 * 2)]
 
 
 # every symbol include/hvqm4.h declares: (restype, argtypes)
@@ -86,6 +97,16 @@ SIGNATURES = {
     "HVQM4HostAlloc": (c_void_p, [c_size_t]),
     "HVQM4HostFree": (None, [c_void_p]),
     "HVQM4ParseFile": (c_int, [c_char_p, c_size_t, POINTER(FileInfo), POINTER(FrameRef), c_int]),
+    "HVQM4ParseFileAudio": (c_int, [c_char_p, c_size_t, POINTER(AudioRef), c_int]),
+    "HVQM4DecodeAudioBatch": (c_int, [c_int, c_int, POINTER(AudioState), POINTER(c_int32), POINTER(c_void_p), POINTER(c_uint32),
+                                      POINTER(c_void_p), POINTER(c_uint32), POINTER(c_uint32)]),
+    "HVQM4PlayerOpen": (c_void_p, [c_void_p, c_size_t]),
+    "HVQM4PlayerClose": (None, [c_void_p]),
+    "HVQM4PlayerInfo": (c_int, [c_void_p, POINTER(FileInfo)]),
+    "HVQM4PlayerNextFrame": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_uint32), POINTER(c_uint32)]),
+    "HVQM4PlayerFrameRGB": (c_int, [c_void_p, c_void_p]),
+    "HVQM4PlayerNextAudio": (c_int, [c_void_p, c_void_p, c_uint32]),
+    "HVQM4PlayerErrors": (c_uint32, [c_void_p]),
 }
 
 _lib = None
@@ -118,6 +139,85 @@ def parse_file(data: bytes):
     frames = (FrameRef * n)()
     lib().HVQM4ParseFile(data, len(data), ctypes.byref(info), frames, n)
     return info, list(frames)
+
+
+def parse_file_audio(data: bytes):
+    """The audio records of a .h4m container -> [AudioRef]."""
+    n = lib().HVQM4ParseFileAudio(data, len(data), None, 0)
+    if n < 0:
+        raise ValueError(f"malformed .h4m container ({n})")
+    refs = (AudioRef * max(n, 1))()
+    lib().HVQM4ParseFileAudio(data, len(data), refs, n)
+    return list(refs[:n])
+
+
+def decode_audio_batch(channels: int, states, first, payloads, capacity: int = 1 << 16):
+    """HVQM4DecodeAudioBatch: payloads[i] = one audio record payload (sample count + data) of an
+    independent stream, states[i] an AudioState carried between the records of a GOP block.
+    Returns (error bits, [interleaved int16 samples per stream])."""
+    n = len(payloads)
+    st = (AudioState * n)(*states)
+    bufs = [ctypes.create_string_buffer(p, len(p)) for p in payloads]
+    ptrs = (c_void_p * n)(*[ctypes.addressof(b) for b in bufs])
+    lens = (c_uint32 * n)(*[len(p) for p in payloads])
+    outs = [(ctypes.c_int16 * (capacity * channels))() for _ in range(n)]
+    optrs = (c_void_p * n)(*[ctypes.addressof(o) for o in outs])
+    caps = (c_uint32 * n)(*([capacity] * n))
+    got = (c_uint32 * n)()
+    rc = lib().HVQM4DecodeAudioBatch(n, channels, st, (c_int32 * n)(*[int(f) for f in first]), ptrs, lens, optrs, caps, got)
+    for i in range(n):
+        states[i] = st[i]
+    return rc, [list(outs[i][:got[i] * channels]) for i in range(n)]
+
+
+class FilePlayer:
+    """The reference program as a library (HVQM4Player*): pictures in file order, display index, RGB, audio."""
+
+    def __init__(self, data: bytes):
+        self._buf = ctypes.create_string_buffer(data, len(data) + 8)
+        self._h = lib().HVQM4PlayerOpen(ctypes.addressof(self._buf), len(data))
+        if not self._h:
+            raise HVQM4Error(ERR_ARGUMENT, "HVQM4PlayerOpen")
+        self.info = FileInfo()
+        lib().HVQM4PlayerInfo(self._h, ctypes.byref(self.info))
+        self.frame_bytes = self.info.width * self.info.height * 3 // 2
+
+    def frames(self):
+        """Yields (frame_type, display_index, planar bytes) per video record."""
+        ptr, disp, ftype = c_void_p(), c_uint32(), c_uint32()
+        while True:
+            rc = lib().HVQM4PlayerNextFrame(self._h, ctypes.byref(ptr), ctypes.byref(disp), ctypes.byref(ftype))
+            if rc == 0:
+                return
+            if rc < 0:
+                raise HVQM4Error(ERR_CUDA, f"HVQM4PlayerNextFrame ({rc})")
+            yield ftype.value, disp.value, ctypes.string_at(ptr.value, self.frame_bytes)
+
+    def rgb(self) -> bytes:
+        out = (c_uint8 * (self.info.width * self.info.height * 3))()
+        rc = lib().HVQM4PlayerFrameRGB(self._h, out)
+        if rc:
+            raise HVQM4Error(rc, "HVQM4PlayerFrameRGB")
+        return bytes(out)
+
+    def audio(self, capacity: int = 1 << 16):
+        """Yields the interleaved int16 samples of every audio record."""
+        out = (ctypes.c_int16 * (capacity * max(1, self.info.audio_channels)))()
+        while True:
+            n = lib().HVQM4PlayerNextAudio(self._h, out, capacity)
+            if n == 0:
+                return
+            if n < 0:
+                raise HVQM4Error(ERR_ARGUMENT, f"HVQM4PlayerNextAudio ({n})")
+            yield list(out[:n * self.info.audio_channels])
+
+    def errors(self) -> int:
+        return lib().HVQM4PlayerErrors(self._h)
+
+    def close(self):
+        if self._h:
+            lib().HVQM4PlayerClose(self._h)
+            self._h = None
 
 
 class SeqDecoder:

@@ -1173,6 +1173,11 @@ H4_API int HVQM4ParseFile(const uint8_t *data, size_t len, HVQM4FileInfo *info, 
     info->height = (int32_t)be16(data + 0x36);
     info->h_samp = data[0x38];
     info->v_samp = data[0x39];
+    info->n_audio_frames = (int32_t)be32(data + 0x20);
+    info->audio_channels = data[0x3C];
+    info->audio_bits = data[0x3D];
+    info->audio_format = data[0x3E];
+    info->audio_sample_rate = (int32_t)be32(data + 0x40);
     if (info->n_gops == 0) return -4;                               /* h4m:2215-2219 */
     size_t pos = 0x44;
     int count = 0;
@@ -1210,6 +1215,42 @@ H4_API int HVQM4ParseFile(const uint8_t *data, size_t len, HVQM4FileInfo *info, 
             }
             else
                 return -9;                                          /* h4m:2509-2512 */
+            pos += size;
+        }
+    }
+    return count;
+}
+
+H4_API int HVQM4ParseFileAudio(const uint8_t *data, size_t len, HVQM4AudioRef *refs, int max_refs)
+{
+    HVQM4FileInfo info;
+    const int nv = HVQM4ParseFile(data, len, &info, nullptr, 0);     /* validates the whole walk */
+    if (nv < 0) return nv;
+    size_t pos = 0x44;
+    int count = 0;
+    for (int g = 0; g < info.n_gops; ++g)
+    {
+        uint32_t left = be32(data + pos + 8) + be32(data + pos + 12);
+        pos += 20;
+        bool first = true;
+        while (left--)
+        {
+            const uint32_t id1 = be16(data + pos), size = be32(data + pos + 4);
+            pos += 8;
+            if (id1 == 0)
+            {
+                if (size < 4) return -7;
+                if (refs && count < max_refs)
+                {
+                    refs[count].offset = (uint32_t)pos;
+                    refs[count].bytes = size;
+                    refs[count].gop = (uint16_t)g;
+                    refs[count].first = first ? 1 : 0;
+                    refs[count].samples = be32(data + pos);
+                }
+                first = false;
+                ++count;
+            }
             pos += size;
         }
     }

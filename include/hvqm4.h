@@ -227,6 +227,9 @@ typedef struct HVQM4FileInfo
     int32_t h_samp, v_samp;
     int32_t n_gops, n_video_frames;
     int32_t usec_per_frame;
+    /* audio track (header bytes 0x20, 0x3C-0x43, h4m:2196,2206-2210) */
+    int32_t n_audio_frames;
+    int32_t audio_channels, audio_bits, audio_format, audio_sample_rate;
 } HVQM4FileInfo;
 
 typedef struct HVQM4FrameRef
@@ -241,6 +244,64 @@ typedef struct HVQM4FrameRef
 /* Returns the number of video frames (<0 on a malformed container); fills at most
    max_frames entries. */
 int HVQM4ParseFile(const uint8_t *data, size_t len, HVQM4FileInfo *info, HVQM4FrameRef *frames, int max_frames);
+
+typedef struct HVQM4AudioRef
+{
+    uint32_t offset;       /* of the audio record payload (BE32 sample count, then data; h4m:2486-2488) */
+    uint32_t bytes;        /* record size */
+    uint16_t gop;
+    uint16_t first;        /* 1: first audio record of its GOP block (state reset + seed, h4m:2446-2452) */
+    uint32_t samples;      /* the payload's sample count */
+} HVQM4AudioRef;
+
+/* Same walk for the audio records: returns their number (<0 on a malformed container). */
+int HVQM4ParseFileAudio(const uint8_t *data, size_t len, HVQM4AudioRef *refs, int max_refs);
+
+/* ---------------------------------------------------------------- audio track
+ * The IMA-ADPCM decoder of the reference (decode_audio, h4m:185-258; upstream keeps its call
+ * disabled, h4m:2486-2507), batched over independent streams on the GPU (one thread per
+ * stream: the recurrence is serial).  frames[i] = one audio record payload as HVQM4AudioRef
+ * points at it, first[i] as in HVQM4AudioRef.  states[i] carries the predictor between the
+ * records of a GOP block (zeroed by the library when first[i] is set).  pcm[i] receives
+ * samples * channels int16 (interleaved, channel 0 first; native byte order), at most
+ * pcm_capacity[i] samples; samples_out[i] (optional) = samples written.
+ * Returns HVQM4_OK or error bits: HVQM4_ERR_TRUNCATED (payload shorter than its sample count
+ * needs), HVQM4_ERR_ARGUMENT (seed step index > 88: the reference exits), HVQM4_ERR_OVERFLOW. */
+#define HVQM4_AUDIO_MAX_CHANNELS 2
+typedef struct HVQM4AudioState
+{
+    int16_t hist[HVQM4_AUDIO_MAX_CHANNELS];
+    int8_t idx[HVQM4_AUDIO_MAX_CHANNELS];
+    int8_t pad[2];
+} HVQM4AudioState;
+
+int HVQM4DecodeAudioBatch(int n, int channels, HVQM4AudioState *states, const int32_t *first, const uint8_t *const *frames,
+                          const uint32_t *frame_bytes, int16_t *const *pcm, const uint32_t *pcm_capacity, uint32_t *samples_out);
+
+/* ---------------------------------------------------------------- file player
+ * The reference program as a library (main's container walk h4m:2427-2537 + decode_video
+ * h4m:2078-2138): open a file image, then pull decoded pictures in file (= decode) order.  The
+ * player owns the SeqObj, the work buffer and the three frame buffers and rotates them with the
+ * reference's rule; pictures come back in host memory.  `data` must stay valid until Close.
+ */
+typedef struct HVQM4Player HVQM4Player;
+
+HVQM4Player *HVQM4PlayerOpen(const uint8_t *data, size_t len);      /* NULL: malformed container, unsupported geometry or no device */
+void HVQM4PlayerClose(HVQM4Player *p);
+int HVQM4PlayerInfo(const HVQM4Player *p, HVQM4FileInfo *info);
+/* Decodes the next video record.  *frame = the planar Y|U|V picture (valid until the next call),
+   *display_index = video frames of the earlier GOP blocks + the record's disp_id (the number in
+   the reference's output file name, h4m:2122), *frame_type = 0x10 / 0x20 / 0x30.
+   Returns 1, 0 at the end of the file, < 0 on error. */
+int HVQM4PlayerNextFrame(HVQM4Player *p, const uint8_t **frame, uint32_t *display_index, uint32_t *frame_type);
+/* The reference's RGB conversion (dumpRGB, h4m:895-926) of the picture NextFrame returned last:
+   width * height * 3 bytes.  Returns HVQM4_OK or error bits. */
+int HVQM4PlayerFrameRGB(HVQM4Player *p, void *rgb);
+/* Decodes the next audio record into pcm (interleaved int16, at most capacity samples per
+   channel).  Returns the number of samples per channel, 0 at the end of the track, < 0 on error. */
+int HVQM4PlayerNextAudio(HVQM4Player *p, int16_t *pcm, uint32_t capacity);
+/* OR of the error bits raised since the last call (stream errors of the pictures, audio errors). */
+uint32_t HVQM4PlayerErrors(HVQM4Player *p);
 
 #ifdef __cplusplus
 }

@@ -78,6 +78,9 @@ class _Decoder:
             getattr(lib, p + "bench_mp").restype = ctypes.c_int
             getattr(lib, p + "yuv_to_rgb").argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
             getattr(lib, p + "yuv_to_rgb").restype = ctypes.c_int
+            getattr(lib, p + "decode_audio").argtypes = [ctypes.POINTER(ctypes.c_int32), ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
+                                                         ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p]
+            getattr(lib, p + "decode_audio").restype = ctypes.c_int
             cls._libs[cls._path] = lib
         return lib
 
@@ -90,6 +93,18 @@ class _Decoder:
         if rc:
             raise RuntimeError(f"yuv_to_rgb failed ({rc})")
         return bytes(out)
+
+    @classmethod
+    def decode_audio(cls, state, channels: int, first: bool, sample_count: int, data: bytes):
+        """One audio record as the reference's decode_audio (h4m:185-258).  state = [hist0, idx0, hist1, idx1, ...]
+        (updated in place); data = the record payload behind its sample count.  Returns the int16 samples."""
+        st = (ctypes.c_int32 * (2 * channels))(*state)
+        out = (ctypes.c_int16 * max(1, (sample_count + 1) * channels))()
+        n = getattr(cls._lib(), cls._prefix + "decode_audio")(st, channels, int(first), sample_count, data, len(data), out)
+        if n < 0:
+            raise RuntimeError(f"decode_audio failed ({n})")
+        state[:] = list(st)
+        return list(out[:n])
 
     def close(self):
         if self._h:

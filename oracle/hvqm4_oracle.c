@@ -932,3 +932,60 @@ PORT_API int port_yuv_to_rgb(const uint8_t *yuv, int w, int h, uint8_t *rgb)
         }
     return 0;
 }
+
+/* ---- IMA-ADPCM audio track as the reference's decode_audio does it (h4m:185-258): same contract
+   as ref_decode_audio in ref_wrap.c.  Seed (first record of a GOP block): per channel, DESCENDING,
+   predictor high byte, then bit 7 = predictor bit 7 and bits 6:0 = step index; codes are 4 bits,
+   high nibble first, channels descending inside a sample, fresh byte at every record. ---- */
+static const int16_t ima_steps[89] = {
+    7, 8, 9, 10, 11, 12, 13, 14, 16, 17, 19, 21, 23, 25, 28, 31, 34, 37, 41, 45, 50, 55, 60, 66, 73, 80, 88, 97, 107, 118, 130, 143,
+    157, 173, 190, 209, 230, 253, 279, 307, 337, 371, 408, 449, 494, 544, 598, 658, 724, 796, 876, 963, 1060, 1166, 1282, 1411,
+    1552, 1707, 1878, 2066, 2272, 2499, 2749, 3024, 3327, 3660, 4026, 4428, 4871, 5358, 5894, 6484, 7132, 7845, 8630, 9493, 10442,
+    11487, 12635, 13899, 15289, 16818, 18500, 20350, 22385, 24623, 27086, 29794, 32767};
+static const int8_t ima_index[16] = {-1, -1, -1, -1, 2, 4, 6, 8, -1, -1, -1, -1, 2, 4, 6, 8};   /* h4m:170-176 */
+
+PORT_API int port_decode_audio(int32_t *state, int channels, int first, uint32_t sample_count, const uint8_t *data, size_t len, int16_t *pcm)
+{
+    size_t pos = 0;
+    uint32_t i = 0, t = 0;
+    if (first)
+    {   /* h4m:190-212 */
+        for (int c = channels - 1; c >= 0; --c)
+        {
+            if (pos + 2 > len) return -1;
+            const uint8_t hi = data[pos++], b = data[pos++];
+            state[2 * c] = (int16_t)((uint16_t)hi << 8 | (b & 0x80));
+            state[2 * c + 1] = b & 0x7F;
+            if (state[2 * c + 1] > 88) return -2;       /* the reference exits */
+        }
+        for (int c = 0; c < channels; ++c) pcm[t++] = (int16_t)state[2 * c];
+        ++i;
+    }
+    uint8_t b = 0;
+    int bitsleft = 0;
+    for (; i < sample_count; ++i)
+    {   /* h4m:216-246 */
+        for (int c = channels - 1; c >= 0; --c)
+        {
+            if (bitsleft == 0)
+            {
+                if (pos >= len) return -1;
+                b = data[pos++];
+                bitsleft = 8;
+            }
+            const int32_t step = ima_steps[state[2 * c + 1]];
+            int32_t delta = step >> 3;
+            if (b & 0x10) delta += step >> 2;
+            if (b & 0x20) delta += step >> 1;
+            if (b & 0x40) delta += step;
+            int32_t h = (b & 0x80) ? state[2 * c] - delta : state[2 * c] + delta;
+            state[2 * c] = h > 32767 ? 32767 : h < -32768 ? -32768 : h;
+            int32_t idx = state[2 * c + 1] + ima_index[(b & 0xF0) >> 4];
+            state[2 * c + 1] = idx > 88 ? 88 : idx < 0 ? 0 : idx;
+            b = (uint8_t)(b << 4);
+            bitsleft -= 4;
+        }
+        for (int c = 0; c < channels; ++c) pcm[t++] = (int16_t)state[2 * c];
+    }
+    return (int)t;
+}

@@ -445,3 +445,45 @@ REF_API int ref_yuv_to_rgb(const uint8_t *yuv, int w, int h, uint8_t *rgb)
     unlink(path);
     return rc;
 }
+
+/* ---- the reference's audio decoder (decode_audio, h4m:185-258; its call is disabled upstream,
+   h4m:2486-2507, but the function is compiled) run on caller-supplied bytes.  `state` = {hist, idx}
+   per channel (int32 pairs) in and out; `data` starts BEHIND the sample count; returns the number
+   of int16 values written to pcm (sample_count * channels), < 0 on failure. ---- */
+REF_API int ref_decode_audio(int32_t *state, int channels, int first, uint32_t sample_count, const uint8_t *data, size_t len, int16_t *pcm)
+{
+    struct audio_state st;
+    st.ch = calloc((size_t)channels, sizeof *st.ch);
+    for (int c = 0; c < channels; ++c)
+    {
+        st.ch[c].hist = (int16_t)state[2 * c];
+        st.ch[c].idx = (int8_t)state[2 * c + 1];
+    }
+    /* pad generously: the reference reads without bounds (the harness never asks for more samples than the bytes hold) */
+    size_t padded = len + 16;
+    uint8_t *copy = calloc(1, padded);
+    memcpy(copy, data, len);
+    FILE *in = fmemopen(copy, padded, "rb");
+    char *out_buf = NULL;
+    size_t out_len = 0;
+    FILE *out = open_memstream(&out_buf, &out_len);
+    int rc = -1;
+    if (in && out)
+    {
+        decode_audio(&st, first, sample_count, in, out, channels);
+        fflush(out);
+        memcpy(pcm, out_buf, out_len);
+        rc = (int)(out_len / 2);
+    }
+    if (in) fclose(in);
+    if (out) fclose(out);
+    free(out_buf);
+    free(copy);
+    for (int c = 0; c < channels; ++c)
+    {
+        state[2 * c] = st.ch[c].hist;
+        state[2 * c + 1] = st.ch[c].idx;
+    }
+    free(st.ch);
+    return rc;
+}

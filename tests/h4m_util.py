@@ -78,3 +78,44 @@ def all_triples_pictures():
             for dx in range(2):
                 y[dy::2, dx::2] = ((pic * 8 + copy) * 4 + dy * 2 + dx).astype(np.uint8)
         yield y.tobytes() + u + v, w, h
+
+
+def with_audio(data: bytes, channels: int, per_gop: int, samples: int, seed: int):
+    """Splices `per_gop` IMA-ADPCM audio records (random codes, valid seeds) into every GOP block
+    of a generated .h4m file, the way the container interleaves them (h4m:2456-2507), and patches
+    the header counts.  Returns (file, [(gop, first, payload)])."""
+    import random
+    rng = random.Random(seed)
+    n_gops = struct.unpack(">I", data[0x18:0x1C])[0]
+    out = bytearray(data[:0x44])
+    pos, records = 0x44, []
+    for g in range(n_gops):
+        hdr = bytearray(data[pos:pos + 20])
+        nv, na = struct.unpack(">II", hdr[8:16])
+        assert na == 0
+        pos += 20
+        body = bytearray()
+        for k in range(nv):
+            id1, id2, size = struct.unpack(">HHI", data[pos:pos + 8])
+            body += data[pos:pos + 8 + size]
+            pos += 8 + size
+            if k < per_gop:
+                first = k == 0
+                n = samples + rng.randrange(8)
+                seed_bytes = b""
+                if first:
+                    for _ in range(channels):
+                        seed_bytes += bytes([rng.randrange(256), (rng.randrange(2) << 7) | rng.randrange(89)])
+                codes = bytes(rng.randrange(256) for _ in range(((n - (1 if first else 0)) * channels + 1) // 2 + rng.randrange(3)))
+                payload = struct.pack(">I", n) + seed_bytes + codes
+                body += struct.pack(">HHI", 0, 0, len(payload)) + payload
+                records.append((g, first, payload))
+        struct.pack_into(">I", hdr, 4, len(body))
+        struct.pack_into(">I", hdr, 12, min(per_gop, nv))
+        out += hdr + body
+    struct.pack_into(">I", out, 0x14, len(out) - 0x44)
+    struct.pack_into(">I", out, 0x20, len(records))
+    out[0x3C] = channels
+    out[0x3D] = 16
+    struct.pack_into(">I", out, 0x40, 22050)
+    return bytes(out), records

@@ -346,3 +346,71 @@ def test_pipelined_steps_with_async_readback_match_oracle(native_lib, oracle, gp
     finally:
         batch.close()
         native_lib.lib().HVQM4HostFree(pinned)
+
+
+def test_audio_kernel_equals_oracle(native_lib, oracle):
+    """HVQM4DecodeAudioBatch (audio.cu) against the reference's decode_audio (h4m:185-258): 48
+    independent streams per call, mono and stereo, a seeded first record and two continuation
+    records each (the predictor state travels through HVQM4AudioState); a short record raises
+    HVQM4_ERR_TRUNCATED and a seed index > 88 HVQM4_ERR_ARGUMENT."""
+    import random
+    import struct
+    checker = oracle.RefDecoder if oracle.have_ref() else oracle.PortDecoder
+    rng = random.Random(21)
+    for ch in (1, 2):
+        n = 48
+        states = [native_lib.AudioState() for _ in range(n)]
+        ref_states = [[0] * (2 * ch) for _ in range(n)]
+        for k in range(3):
+            payloads, want = [], []
+            for i in range(n):
+                samples = rng.randint(1, 700)
+                body = bytearray(rng.randrange(256) for _ in range(2 * ch + samples * ch))
+                if k == 0:
+                    for c in range(ch):
+                        body[2 * c + 1] = (body[2 * c + 1] & 0x80) | rng.randint(0, 88)
+                payloads.append(struct.pack(">I", samples) + bytes(body))
+                want.append(checker.decode_audio(ref_states[i], ch, k == 0, samples, bytes(body)))
+            rc, got = native_lib.decode_audio_batch(ch, states, [k == 0] * n, payloads)
+            assert rc == 0
+            assert got == want
+            for i in range(n):
+                assert [states[i].hist[c] for c in range(ch)] == [ref_states[i][2 * c] for c in range(ch)]
+                assert [states[i].idx[c] for c in range(ch)] == [ref_states[i][2 * c + 1] for c in range(ch)]
+    st = [native_lib.AudioState()]
+    rc, got = native_lib.decode_audio_batch(1, st, [True], [struct.pack(">I", 100) + bytes([1, 5]) + bytes(10)])
+    assert rc == native_lib.ERR_TRUNCATED and len(got[0]) == 21          # seed sample + 2 per byte
+    rc, _ = native_lib.decode_audio_batch(1, st, [True], [struct.pack(">I", 4) + bytes([1, 0x7F]) + bytes(10)])
+    assert rc & native_lib.ERR_ARGUMENT
+
+
+def test_file_player_matches_the_reference_program(native_lib, oracle):
+    """HVQM4Player* = the reference program as a library: every video record of a two-GOP file with
+    an interleaved stereo audio track, in file order, with the display index of the reference's
+    output file name (h4m:2122), its RGB conversion (h4m:2126) and the audio track (h4m:185-258)."""
+    from tests.h4m_util import with_audio
+    checker = oracle.RefDecoder if oracle.have_ref() else oracle.PortDecoder
+    for version, gop in ((15, "IPBBPBB"), (13, "IPB")):
+        data = synth.generate(320, 240, version, gop, 2, seed=90 + version, profile=0)
+        spliced, records = with_audio(data, 2, 2, 300, seed=version)
+        want = list(checker(spliced).frames())
+        player = native_lib.FilePlayer(spliced)
+        assert (player.info.n_audio_frames, player.info.audio_channels, player.info.audio_sample_rate) == (len(records), 2, 22050)
+        n = 0
+        for (t, disp, yuv), (wt, wd, wdisp, wyuv) in zip(player.frames(), want):
+            assert (t, disp) == (wt, wdisp) and wdisp == (n // len(gop)) * len(gop) + wd, n
+            assert yuv == wyuv, n
+            if n % 3 == 0:
+                assert player.rgb() == checker.yuv_to_rgb(wyuv, 320, 240), n
+            n += 1
+        assert n == len(want) == 2 * len(gop)
+        state = [0, 0, 0, 0]
+        pcm = list(player.audio())
+        assert len(pcm) == len(records)
+        for got, (g, first, payload) in zip(pcm, records):
+            if first:
+                state = [0, 0, 0, 0]
+            samples = int.from_bytes(payload[:4], "big")
+            assert got == checker.decode_audio(state, 2, first, samples, payload[4:])
+        assert player.errors() == 0
+        player.close()

@@ -102,3 +102,36 @@ def test_rgb_conversion_port_equals_reference_on_every_triple(oracle):
         assert oracle.RefDecoder.yuv_to_rgb(yuv, w, h) == oracle.PortDecoder.yuv_to_rgb(yuv, w, h)
         n += 1
     assert n == 8
+
+
+def test_audio_port_equals_reference_decode_audio(oracle):
+    """IMA-ADPCM track (decode_audio, h4m:185-258): the port against the reference's own function on
+    random records, mono and stereo, seeded first record then two continuation records."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    import random
+    rng = random.Random(11)
+    for ch in (1, 2):
+        for _ in range(100):
+            s_ref, s_port = [0] * (2 * ch), [0] * (2 * ch)
+            for k in range(3):
+                n = rng.randint(1, 400)
+                data = bytearray(rng.randrange(256) for _ in range(2 * ch + n * ch))
+                if k == 0:
+                    for c in range(ch):
+                        data[2 * c + 1] = (data[2 * c + 1] & 0x80) | rng.randint(0, 88)
+                a = oracle.RefDecoder.decode_audio(s_ref, ch, k == 0, n, bytes(data))
+                b = oracle.PortDecoder.decode_audio(s_port, ch, k == 0, n, bytes(data))
+                assert a == b and s_ref == s_port and len(a) == n * ch
+
+
+def test_spliced_audio_container_is_what_the_reference_walks(oracle):
+    """tests/h4m_util.with_audio builds files the reference's container walk accepts: its video
+    frames decode to the same pictures as without the audio records."""
+    from hvqm4_b200 import synth
+    from tests.h4m_util import with_audio
+    data = synth.generate(320, 240, 15, "IPBB", 2, seed=77, profile=1)
+    spliced, records = with_audio(data, 2, 3, 200, seed=5)
+    assert len(records) == 6 and [r[1] for r in records] == [True, False, False] * 2
+    checker = oracle.RefDecoder if oracle.have_ref() else oracle.PortDecoder
+    assert [f[3] for f in checker(spliced).frames()] == [f[3] for f in checker(data).frames()]
