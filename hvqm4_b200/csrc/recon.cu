@@ -66,26 +66,42 @@ __device__ __forceinline__ void load_view(ReconView &vw, const ReconJob &J)
    three passes, one 4x4 block per lane and pass, 128 contiguous bytes per warp row store */
 __device__ __forceinline__ void map_segment(const ReconView &v, int row, int mx0, int lane)
 {
+    /* the type bytes of the three passes and the two vector words a lane needs (its luma blocks share a
+       macroblock) are fetched up front: three dependent memory latencies per pass (type -> vector ->
+       reference rows) become one plus the rows */
+    const int lbx = mx0 * 2 + lane, cbx = mx0 + (lane & 15), cplane = 1 + (lane >> 4);
+    const bool l_ok = lbx < v.mcb_w * 2, c_ok = cbx < v.mcb_w;
+    const int lstride = (v.width >> 2) + 2, cstride = (v.width >> 3) + 2;
+    uint32_t t0 = 0, t1 = 0, t2 = 0, mv_l = 0, mv_c = 0;
+    if (l_ok)
+    {
+        t0 = __ldg(v.blob + v.off_type[0] + (row * 2 + 1) * lstride + lbx + 1);
+        t1 = __ldg(v.blob + v.off_type[0] + (row * 2 + 2) * lstride + lbx + 1);
+        if (!v.is_ipic) mv_l = __ldg(reinterpret_cast<const uint32_t *>(v.blob + v.off_mv) + row * v.mcb_w + (lbx >> 1));
+    }
+    if (c_ok)
+    {
+        t2 = __ldg(v.blob + (cplane == 1 ? v.off_type[1] : v.off_type[2]) + (row + 1) * cstride + cbx + 1);
+        if (!v.is_ipic) mv_c = __ldg(reinterpret_cast<const uint32_t *>(v.blob + v.off_mv) + row * v.mcb_w + cbx);
+    }
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass)
     {   /* luma: the segment's two block rows (plane is a compile-time 0 here) */
-        const int bx = mx0 * 2 + lane, by = row * 2 + pass;
-        if (bx >= v.mcb_w * 2) continue;
-        const int pw = v.width, bstride = (pw >> 2) + 2;
-        const uint32_t t = __ldg(v.blob + v.off_type[0] + (by + 1) * bstride + bx + 1);
+        const int bx = lbx, by = row * 2 + pass;
+        if (!l_ok) continue;
+        const int pw = v.width;
         uint32_t rows[4];
-        if (!rc_map_block(v, 0, bx, by, t, rows)) continue;
+        if (!rc_map_block_mv(v, 0, bx, by, pass ? t1 : t0, mv_l, rows)) continue;
         uint8_t *dst = v.present + (by * 4) * pw + bx * 4;
 #pragma unroll
         for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];
     }
     {   /* chroma: lanes 0-15 U, 16-31 V */
-        const int plane = 1 + (lane >> 4), bx = mx0 + (lane & 15), by = row;
-        if (bx >= v.mcb_w) return;
-        const int pw = v.width >> 1, bstride = (pw >> 2) + 2;
-        const uint32_t t = __ldg(v.blob + (plane == 1 ? v.off_type[1] : v.off_type[2]) + (by + 1) * bstride + bx + 1);
+        const int plane = cplane, bx = cbx, by = row;
+        if (!c_ok) return;
+        const int pw = v.width >> 1;
         uint32_t rows[4];
-        if (!rc_map_block(v, plane, bx, by, t, rows)) return;
+        if (!rc_map_block_mv(v, plane, bx, by, t2, mv_c, rows)) return;
         const int plane_off = v.width * v.height + (plane == 2 ? pw * (v.height >> 1) : 0);
         uint8_t *dst = v.present + plane_off + (by * 4) * pw + bx * 4;
 #pragma unroll
