@@ -9,7 +9,8 @@ Workload (config.workload): BASELINE.json config 5 -- 1024 independent synthetic
 cyclically with independent decoder state), one picture per stream per step, batched per launch.
 Multi-GPU: every rank owns its own 1024 streams (weak scaling, --streams-per-gpu fixed as N
 grows), no collective -- streams are independent.  One STEP = one GOP (16 pictures) of every
-stream of the rank = 16 x (map kernel + record kernel).
+stream of the rank = 16 launches of the fused band kernel (dense content; sparse content runs a
+map kernel + record kernel pair per picture step).
 
 Printed JSON (one line, rank 0):
   value      reconstruction-only frames/s: symbol buffers already resident in HBM, the 16
@@ -217,6 +218,8 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ..." when NCCL_DEBUG is set) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
