@@ -4,42 +4,78 @@
  *
  * The reference converts every decoded frame before it writes it out (h4m:2126): JPEG matrix in
  * single-precision float, chroma replicated 2x2 without interpolation, truncation towards zero,
- * clamp to 0..255 (clamp255, h4m:896-899).  The arithmetic below is the same expression tree in
- * IEEE single precision with round-to-nearest multiplies and adds and NO contraction, i.e. the
- * strict reading of the C source (contracted evaluation gives the same bytes on all 2^24
- * (y, u, v) triples; tests/test_gpu_parity.py checks every triple against the reference build).
+ * clamp to 0..255 (clamp255, h4m:896-899):
+ *     R = clamp(y + 1.402f (v-128))   G = clamp(y - 0.34414f (u-128) - 0.71414f (v-128))   B = clamp(y + 1.772f (u-128))
+ * For a fixed chroma pair each channel is EXACTLY clamp(y + d) with an integer d that does not
+ * depend on y (truncation of a clamped value and the float roundings never disagree with it; the
+ * G offset is NOT a sum of a u term and a v term -- it is a table over all 65 536 pairs).  So the
+ * float expression tree is evaluated once per chroma value, by rgb_tables_kernel with explicit
+ * round-to-nearest multiplies and adds and no contraction (the strict reading of the C source),
+ * into three small tables per device, and the conversion itself is packed 16-bit integer
+ * arithmetic: two pixels per VIADD.16x2 / VIMNMX.S16x2.RELU.  tests/test_gpu_parity.py checks all
+ * 2^24 (y, u, v) triples against the reference build, which is what pins the decomposition.
  *
- * One thread converts an 8 x 2 pixel tile: two 8-byte luma loads, two 4-byte chroma loads, six
- * 8-byte stores.  Algorithmic bytes: 1.5 read + 3 written per pixel; bound by HBM.
+ * One thread converts an 8 x 2 pixel tile: two 8-byte luma loads, two 4-byte chroma loads, twelve
+ * table reads (L1-resident: 129 KB), six 8-byte stores.  Algorithmic bytes: 1.5 read + 3 written
+ * per pixel; bound by HBM.
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <mutex>
 
 #include "recon.h"
 
 namespace {
 
-__device__ __forceinline__ uint32_t rgb_clamp(float f)      /* clamp255, h4m:896-899 */
+__device__ __forceinline__ int rgb_clamp_f(float f)      /* clamp255, h4m:896-899 */
 {
-    return f < 0.f ? 0u : f > 255.f ? 255u : (uint32_t)__float2uint_rz(f);
+    return f < 0.f ? 0 : f > 255.f ? 255 : (int)__float2uint_rz(f);
 }
 
-/* the three channels of one pixel packed as R | G << 8 | B << 16 */
-__device__ __forceinline__ uint32_t rgb_pixel(float y, float rv, float gu, float gv, float bu)
+/* channel value of the reference for one (y, u, v): 0 R, 1 G, 2 B */
+__device__ __forceinline__ int rgb_reference(int ch, int y, int u, int v)
 {
-    const uint32_t r = rgb_clamp(__fadd_rn(y, rv));                          /* h4m:918 */
-    const uint32_t g = rgb_clamp(__fsub_rn(__fsub_rn(y, gu), gv));           /* h4m:919 */
-    const uint32_t b = rgb_clamp(__fadd_rn(y, bu));                          /* h4m:920 */
-    return r | g << 8 | b << 16;
+    const float fy = (float)y, du = __fsub_rn((float)u, 128.f), dv = __fsub_rn((float)v, 128.f);
+    if (ch == 0) return rgb_clamp_f(__fadd_rn(fy, __fmul_rn(1.402f, dv)));                                          /* h4m:918 */
+    if (ch == 2) return rgb_clamp_f(__fadd_rn(fy, __fmul_rn(1.772f, du)));                                          /* h4m:920 */
+    return rgb_clamp_f(__fsub_rn(__fsub_rn(fy, __fmul_rn(0.34414f, du)), __fmul_rn(0.71414f, dv)));                 /* h4m:919 */
+}
+
+constexpr int kTabR = 0, kTabB = 256, kTabG = 512, kTabEntries = 512 + 65536;
+
+/* offset d with channel = clamp(y + d) for every y: taken from a y whose result is strictly inside
+   0..255 (there the clamp is inactive); +-300 when every y saturates */
+__global__ void rgb_tables_kernel(int16_t *tab)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kTabEntries) return;
+    const int ch = i < kTabB ? 0 : i < kTabG ? 2 : 1;
+    const int u = ch == 2 ? i - kTabB : ch == 1 ? (i - kTabG) >> 8 : 0, v = ch == 0 ? i : ch == 1 ? (i - kTabG) & 0xFF : 0;
+    int d = rgb_reference(ch, 0, u, v) == 255 ? 300 : -300;
+    for (int y = 0; y < 256; ++y)
+    {
+        const int c = rgb_reference(ch, y, u, v);
+        if (c > 0 && c < 255) { d = c - y; break; }
+    }
+    tab[i] = (int16_t)d;
+}
+
+/* two pixels in 16-bit lanes: clamp(y + d) */
+__device__ __forceinline__ uint32_t rgb_pair(uint32_t y2, uint32_t d2)
+{
+    return __vimin_s16x2_relu(__vadd2(y2, d2), 0x00FF00FFu);
 }
 
 __global__ void __launch_bounds__(256)
-yuv2rgb_kernel(const uint8_t *const *__restrict__ frames, uint8_t *__restrict__ dst, size_t dst_stride, int width, int height)
+yuv2rgb_kernel(const uint8_t *const *__restrict__ frames, uint8_t *__restrict__ dst, size_t dst_stride, int width, int height,
+               const int16_t *__restrict__ tab)
 {
     const uint8_t *src = frames[blockIdx.y];
     const int tiles_x = width >> 3, tiles = tiles_x * (height >> 1);
-    const int idx = blockIdx.x * 256 + threadIdx.x;
-    if (idx >= tiles) return;
+    const int idx_raw = blockIdx.x * 256 + threadIdx.x;
+    const bool valid = idx_raw < tiles;
+    const int idx = valid ? idx_raw : tiles - 1;          /* tail lanes recompute the last tile and store nothing */
     const int ty = idx / tiles_x, tx = idx - ty * tiles_x;
     const uint8_t *yp = src + (size_t)(2 * ty) * width + 8 * tx;
     const uint8_t *up = src + (size_t)width * height + (size_t)ty * (width >> 1) + 4 * tx;
@@ -48,40 +84,81 @@ yuv2rgb_kernel(const uint8_t *const *__restrict__ frames, uint8_t *__restrict__ 
     const uint2 y1 = __ldcs(reinterpret_cast<const uint2 *>(yp + width));
     const uint32_t u4 = __ldcs(reinterpret_cast<const uint32_t *>(up));
     const uint32_t v4 = __ldcs(reinterpret_cast<const uint32_t *>(vp));
-    uint32_t px[2][8];
+    /* per chroma sample c and row r: R, G, B of its two pixels in 16-bit lanes (values 0..255) */
+    uint32_t R[2][4], G[2][4], B[2][4];
 #pragma unroll
     for (int c = 0; c < 4; ++c)
     {
-        const float du = __fsub_rn((float)((u4 >> (8 * c)) & 0xFF), 128.f);
-        const float dv = __fsub_rn((float)((v4 >> (8 * c)) & 0xFF), 128.f);
-        const float rv = __fmul_rn(1.402f, dv), gu = __fmul_rn(0.34414f, du), gv = __fmul_rn(0.71414f, dv), bu = __fmul_rn(1.772f, du);
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-        {
-            const int x = 2 * c + k;
-            const uint32_t w0 = x < 4 ? y0.x : y0.y, w1 = x < 4 ? y1.x : y1.y;
-            px[0][x] = rgb_pixel((float)((w0 >> (8 * (x & 3))) & 0xFF), rv, gu, gv, bu);
-            px[1][x] = rgb_pixel((float)((w1 >> (8 * (x & 3))) & 0xFF), rv, gu, gv, bu);
-        }
+        const uint32_t u = (u4 >> (8 * c)) & 0xFF, v = (v4 >> (8 * c)) & 0xFF;
+        const uint32_t dr = (uint16_t)__ldg(tab + kTabR + v), db = (uint16_t)__ldg(tab + kTabB + u), dg = (uint16_t)__ldg(tab + kTabG + (u << 8 | v));
+        const uint32_t dr2 = dr * 0x10001u, dg2 = dg * 0x10001u, db2 = db * 0x10001u;
+        const uint32_t w0 = c < 2 ? y0.x : y0.y, w1 = c < 2 ? y1.x : y1.y;
+        const uint32_t sel = (c & 1) ? 0x4342u : 0x4140u;            /* bytes (2c, 2c+1) of the word -> 16-bit lanes */
+        const uint32_t p0 = __byte_perm(w0, 0u, sel), p1 = __byte_perm(w1, 0u, sel);
+        R[0][c] = rgb_pair(p0, dr2); G[0][c] = rgb_pair(p0, dg2); B[0][c] = rgb_pair(p0, db2);
+        R[1][c] = rgb_pair(p1, dr2); G[1][c] = rgb_pair(p1, dg2); B[1][c] = rgb_pair(p1, db2);
     }
-    uint8_t *out = dst + blockIdx.y * dst_stride + ((size_t)(2 * ty) * width + 8 * tx) * 3;
+    /* Stores: a thread's own 24-byte run would touch a sector with 8 bytes per instruction.  When the
+       32 tiles of the warp lie in one tile row (always, if the tile row length is a multiple of 32;
+       otherwise for most warps) their 768 output bytes per picture row are contiguous: stage them in
+       shared memory and write 16 bytes per lane, 512 + 256 contiguous bytes per instruction pair. */
+    __shared__ uint4 stage[8][2][48];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int idx0 = idx_raw - lane;
+    const int ty0 = idx0 / tiles_x;
+    const bool whole = valid && idx0 + 31 < tiles && (idx0 + 31) / tiles_x == ty0 && ((width * 3) & 15) == 0 && ((idx0 - ty0 * tiles_x) & 1) == 0;
+    uint32_t w[2][6];
 #pragma unroll
     for (int r = 0; r < 2; ++r)
-    {   /* 8 pixels x 3 bytes = six words */
-        const uint32_t *p = px[r];
-        uint2 a, b, c;
-        a.x = p[0] | p[1] << 24;
-        a.y = p[1] >> 8 | p[2] << 16;
-        b.x = p[2] >> 16 | p[3] << 8;
-        b.y = p[4] | p[5] << 24;
-        c.x = p[5] >> 8 | p[6] << 16;
-        c.y = p[6] >> 16 | p[7] << 8;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+        {   /* samples 2h (pixels a, b) and 2h + 1 (pixels c, d) -> Ra Ga Ba Rb | Gb Bb Rc Gc | Bc Rd Gd Bd */
+            const uint32_t rg0 = G[r][2 * h] * 256u + R[r][2 * h];             /* Ra Ga Rb Gb */
+            const uint32_t rg1 = G[r][2 * h + 1] * 256u + R[r][2 * h + 1];     /* Rc Gc Rd Gd */
+            const uint32_t b0 = B[r][2 * h], b1 = B[r][2 * h + 1];             /* Ba 0 Bb 0, Bc 0 Bd 0 */
+            w[r][3 * h + 0] = __byte_perm(rg0, b0, 0x2410);
+            w[r][3 * h + 1] = __byte_perm(__byte_perm(rg0, b0, 0x0063), rg1, 0x5410);
+            w[r][3 * h + 2] = __byte_perm(rg1, b1, 0x6324);
+        }
+    uint8_t *out = dst + blockIdx.y * dst_stride + ((size_t)(2 * ty) * width + 8 * tx) * 3;
+    if (__all_sync(0xFFFFFFFFu, whole))
+    {
+        uint8_t *out0 = dst + blockIdx.y * dst_stride + ((size_t)(2 * ty0) * width + 8 * (idx0 - ty0 * tiles_x)) * 3;
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+        {
+            uint2 *s2 = reinterpret_cast<uint2 *>(stage[warp][r]);
+            s2[lane * 3 + 0] = make_uint2(w[r][0], w[r][1]);
+            s2[lane * 3 + 1] = make_uint2(w[r][2], w[r][3]);
+            s2[lane * 3 + 2] = make_uint2(w[r][4], w[r][5]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+        {
+            uint4 *o = reinterpret_cast<uint4 *>(out0 + (size_t)r * width * 3);
+            __stcs(o + lane, stage[warp][r][lane]);
+            if (lane < 16) __stcs(o + 32 + lane, stage[warp][r][32 + lane]);
+        }
+        return;
+    }
+    if (!valid) return;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+    {
         uint2 *o = reinterpret_cast<uint2 *>(out + (size_t)r * width * 3);
-        __stcs(o, a);
-        __stcs(o + 1, b);
-        __stcs(o + 2, c);
+        __stcs(o, make_uint2(w[r][0], w[r][1]));
+        __stcs(o + 1, make_uint2(w[r][2], w[r][3]));
+        __stcs(o + 2, make_uint2(w[r][4], w[r][5]));
     }
 }
+
+struct RgbTables
+{
+    std::mutex lock;
+    int16_t *tab[64] = {};
+};
+RgbTables g_tables;
 
 }  // namespace
 
@@ -91,8 +168,29 @@ extern "C" int hvqm4_rgb_launch(const uint8_t *const *d_frames, int n, uint8_t *
                                 cudaStream_t stream)
 {
     if (n <= 0) return 0;
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return (int)e;
+    if (device < 0 || device >= 64) return (int)cudaErrorInvalidDevice;
+    int16_t *tab;
+    {
+        std::lock_guard<std::mutex> guard(g_tables.lock);
+        if (!g_tables.tab[device])
+        {   /* once per device; ordered before the first conversion by the synchronize */
+            int16_t *t = nullptr;
+            if ((e = cudaMalloc((void **)&t, kTabEntries * sizeof(int16_t))) != cudaSuccess) return (int)e;
+            rgb_tables_kernel<<<(kTabEntries + 255) / 256, 256, 0, stream>>>(t);
+            if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaStreamSynchronize(stream)) != cudaSuccess)
+            {
+                cudaFree(t);
+                return (int)e;
+            }
+            g_tables.tab[device] = t;
+        }
+        tab = g_tables.tab[device];
+    }
     const int tiles = (width >> 3) * (height >> 1);
     const dim3 grid((unsigned)((tiles + 255) / 256), (unsigned)n);
-    yuv2rgb_kernel<<<grid, 256, 0, stream>>>(d_frames, d_dst, dst_stride, width, height);
+    yuv2rgb_kernel<<<grid, 256, 0, stream>>>(d_frames, d_dst, dst_stride, width, height, tab);
     return (int)cudaGetLastError();
 }
