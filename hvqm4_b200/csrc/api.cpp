@@ -530,7 +530,9 @@ H4_API int HVQM4BatchSetEntropyMode(HVQM4Batch *b, int gpu)
         const uint32_t sym_cap = 16, work_cap = blocks;
         b->eslot = hvqm4_dev_entropy_slot_bytes(b->width, b->height, sym_cap, work_cap);
         if (!b->eslot) return HVQM4_ERR_GEOMETRY;
-        b->blobs_cap = (size_t)b->n_streams * align_up(2 * b->frame_bytes, 256);
+        /* symbol buffers of one step: twice the frame size covers the densest records; the constant covers the
+           fixed parts (header, bordered maps, nest, tables) that dominate in tiny pictures */
+        b->blobs_cap = (size_t)b->n_streams * align_up(2 * b->frame_bytes + 8192, 256);
         if (!cuda_ok(cudaMalloc((void **)&b->d_estate, b->eslot * (size_t)b->n_streams * H4_PARSE_SLOTS), "cudaMalloc(entropy state)") ||
             !cuda_ok(cudaMalloc((void **)&b->d_blobs, kArenas * b->blobs_cap), "cudaMalloc(blob arena)") ||
             !cuda_ok(cudaMalloc((void **)&b->d_blob_used, H4_PARSE_SLOTS * sizeof(unsigned long long)), "cudaMalloc") ||

@@ -38,6 +38,11 @@ CASES = {
     "wide_1024x576_v13_IPB": dict(width=1024, height=576, version=13, gop="IPBB", n_gops=1, seed=205, profile=0),
     # 160 macroblocks per row: more than one column tile of the band kernel (recon.cu kTileMcbs)
     "hd_1280x720_v15_IPB": dict(width=1280, height=720, version=15, gop="IPBB", n_gops=1, seed=206, profile=0),
+    # pictures smaller than the 70x38-block nest: MakeNest mirrors, then zero-fills (h4m:1173-1203)
+    "tiny_16x16_v15_IPB": dict(width=16, height=16, version=15, gop="IPBBPB", n_gops=2, seed=207, profile=0),
+    "small_64x48_v13_IPB": dict(width=64, height=48, version=13, gop="IPBBPB", n_gops=2, seed=208, profile=0),
+    "mirror_h_200x152_v15_IPB": dict(width=200, height=152, version=15, gop="IPBB", n_gops=2, seed=209, profile=0),
+    "mirror_v_320x104_v15_IPB": dict(width=320, height=104, version=15, gop="IPBB", n_gops=2, seed=210, profile=0),
 }
 
 

@@ -12,7 +12,7 @@ from tests.h4m_util import demux, emul_decode, md5
 @pytest.mark.parametrize("name", [
     "cfg1_320x240_v15_I30", "cfg3_640x480_v15_IPB", "cfg4_320x240_v13_IPB", "cfg5_stream511",
     "realistic_640x480_v15_IPB", "min_280x152_v15_IPB", "ragged_328x248_v15_IPB", "wide_1024x576_v13_IPB",
-    "hd_1280x720_v15_IPB"])
+    "hd_1280x720_v15_IPB", "tiny_16x16_v15_IPB", "small_64x48_v13_IPB", "mirror_h_200x152_v15_IPB", "mirror_v_320x104_v15_IPB"])
 def test_emulated_pipeline_matches_golden(emul_lib, golden, name):
     case = golden[name]
     got = list(emul_decode(emul_lib, synth.generate(**case["args"])))

@@ -37,7 +37,7 @@
 
 typedef struct
 {
-    int32_t width, height;   /* multiples of 8; >= 280x152 (no nest mirroring) */
+    int32_t width, height;   /* multiples of 8, >= 16; below 280x152 the nest is mirrored / zero-filled (h4m:1173-1203) */
     int32_t version;         /* 13 or 15 */
     int32_t n_gops;
     int32_t profile;         /* 0 = dense (worst case), 1 = realistic (sparse, coherent motion) */
@@ -319,7 +319,8 @@ static void gen_ipic(Gen *g, Pic *p, uint8_t hdr[8])
     Rng *r = &g->rng;
     int dc_shift = rnd(r, 2);
     int unk_shift = g->prm->profile == 0 ? rnd_range(r, 8, 10) : 10;
-    int nest_x = rnd(r, g->bw[0] - 70 + 1), nest_y = rnd(r, g->bh[0] - 38 + 1);
+    /* pictures narrower / lower than the nest take MakeNest's mirror + zero-fill path (h4m:1173-1203): origin 0 */
+    int nest_x = g->bw[0] >= 70 ? (int)rnd(r, g->bw[0] - 70 + 1) : 0, nest_y = g->bh[0] >= 38 ? (int)rnd(r, g->bh[0] - 38 + 1) : 0;
     hdr[0] = dc_shift; hdr[1] = unk_shift; hdr[2] = 0; hdr[3] = 0;
     hdr[4] = nest_x >> 8; hdr[5] = nest_x; hdr[6] = nest_y >> 8; hdr[7] = nest_y;
 
@@ -663,7 +664,7 @@ static void write_picture(Gen *g, Bytes *out, int type)
 GEN_API int h4mgen_generate(const H4MGenParams *prm, uint8_t **out_data, uint64_t *out_len)
 {
     if (!prm || !prm->gop || prm->gop[0] != 'I') return -1;
-    if (prm->width % 8 || prm->height % 8 || prm->width < 280 || prm->height < 152) return -2;
+    if (prm->width % 8 || prm->height % 8 || prm->width < 16 || prm->height < 16) return -2;
     if (prm->width < prm->height) return -3;   /* portrait is untested upstream (README:23) */
     if (prm->version != 13 && prm->version != 15) return -4;
     Gen g;
