@@ -415,3 +415,47 @@ def test_file_player_matches_the_reference_program(native_lib, oracle):
             assert got == checker.decode_audio(state, 2, first, samples, payload[4:])
         assert player.errors() == 0
         player.close()
+
+
+@pytest.mark.parametrize("gpu_entropy", [False, True])
+def test_staggered_streams_and_partial_steps_match_oracle(native_lib, oracle, gpu_entropy):
+    """Streams that are out of phase with each other (stream i joins at step i % 4 and sits out every
+    step where (step + i) % 5 == 0): every step mixes I, P and B pictures and addresses a different
+    subset of the batch, read-backs are asynchronous, nothing is synchronised until the end.  The
+    per-stream surface rotation, the alternating parser slots (a stream may use the same slot twice
+    in a row), the I-picture fences and the read-back dependencies all have to hold."""
+    n, gop = 24, "IPBBPBPB"
+    files = [synth.generate(320, 240, 15, gop, 2, seed=8600 + i, profile=i % 2) for i in range(n)]
+    want = [[md5(yuv) for _, _, _, yuv in oracle.PortDecoder(f).frames()] for f in files]
+    parsed = [native_lib.parse_file(f)[1] for f in files]
+    bufs = [ctypes.create_string_buffer(f, len(f) + 8) for f in files]
+    bases = [ctypes.addressof(b) for b in bufs]
+    batch = native_lib.Batch(n, 320, 240, 15, gpu_entropy=gpu_entropy)
+    fb = batch.frame_bytes
+    total_frames = sum(len(p) for p in parsed)
+    pinned = native_lib.lib().HVQM4HostAlloc(total_frames * fb)
+    assert pinned
+    try:
+        cursor = [0] * n
+        slots, slot = [], 0          # (stream, frame index) of every read-back, in order
+        step = 0
+        while any(cursor[i] < len(parsed[i]) for i in range(n)):
+            ids = [i for i in range(n) if step >= i % 4 and (step + i) % 5 != 0 and cursor[i] < len(parsed[i])]
+            if ids:
+                frs = [parsed[i][cursor[i]] for i in ids]
+                batch.decode(ids, [f.frame_type for f in frs], [bases[i] + f.offset for i, f in zip(ids, frs)], [f.bytes for f in frs])
+                arr = (ctypes.c_int32 * len(ids))(*ids)
+                batch.read_frames_async(arr, len(ids), pinned + slot * fb, fb)
+                for i in ids:
+                    slots.append((i, cursor[i]))
+                    cursor[i] += 1
+                slot += len(ids)
+            step += 1
+        batch.sync()
+        raw = ctypes.string_at(pinned, total_frames * fb)
+        assert len(slots) == total_frames
+        for k, (i, f) in enumerate(slots):
+            assert md5(raw[k * fb:(k + 1) * fb]) == want[i][f], (i, f)
+    finally:
+        batch.close()
+        native_lib.lib().HVQM4HostFree(pinned)
