@@ -218,10 +218,20 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ..." when NCCL_DEBUG is set) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries exactly one JSON line: NCCL prints its banner ("NCCL version ...", when NCCL_DEBUG is
+        # set) to file descriptor 1 while the communicator is created, so that happens with fd 1 pointing at stderr
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     import __graft_entry__
     if rank == 0:
