@@ -84,6 +84,31 @@ __device__ __forceinline__ void map_segment(const ReconView &v, int row, int mx0
         t2 = __ldg(v.blob + (cplane == 1 ? v.off_type[1] : v.off_type[2]) + (row + 1) * cstride + cbx + 1);
         if (!v.is_ipic) mv_c = __ldg(reinterpret_cast<const uint32_t *>(v.blob + v.off_mv) + row * v.mcb_w + cbx);
     }
+    /* ask L2 for the reference rows of the lower luma block and of the chroma block while the upper luma block is
+       done (+2.4 % on realistic content; the same in the band kernel's classifying walk loses 7 % on dense content) */
+    if (!v.is_ipic)
+    {
+        if (l_ok && (t1 & 0x60))
+        {
+            const uint32_t mp = rc_motion_pack(v, 0, lbx, row * 2 + 1, t1, mv_l);
+            if (!(mp & RC_MP_POISON))
+            {
+                const uint8_t *src = ((mp & RC_MP_FUTURE) ? v.ref[1] : v.ref[0]) + RC_MP_OFFSET(mp);
+#pragma unroll
+                for (int r = 0; r < 5; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + r * v.width));
+            }
+        }
+        if (c_ok && (t2 & 0x60))
+        {
+            const uint32_t mp = rc_motion_pack(v, cplane, cbx, row, t2, mv_c);
+            if (!(mp & RC_MP_POISON))
+            {
+                const uint8_t *src = ((mp & RC_MP_FUTURE) ? v.ref[1] : v.ref[0]) + RC_MP_OFFSET(mp);
+#pragma unroll
+                for (int r = 0; r < 5; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + r * (v.width >> 1)));
+            }
+        }
+    }
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass)
     {   /* luma: the segment's two block rows (plane is a compile-time 0 here) */
