@@ -62,28 +62,41 @@ __device__ __forceinline__ void load_view(ReconView &vw, const ReconJob &J)
  * building blocks shared by the kernels
  * ------------------------------------------------------------------------------------------ */
 
-/* MAP work of one segment (16 macroblocks of macroblock row `row` starting at macroblock mx0):
-   three passes, one 4x4 block per lane and pass, 128 contiguous bytes per warp row store */
-__device__ __forceinline__ void map_segment(const ReconView &v, int row, int mx0, int lane)
+/* what a lane needs before it can start on a segment: the type bytes of its three blocks (upper luma,
+   lower luma, chroma) and the two vector words (its luma blocks share a macroblock) */
+struct SegHead
 {
-    /* the type bytes of the three passes and the two vector words a lane needs (its luma blocks share a
-       macroblock) are fetched up front: three dependent memory latencies per pass (type -> vector ->
-       reference rows) become one plus the rows */
+    uint32_t t0, t1, t2, mv_l, mv_c;
+};
+
+__device__ __forceinline__ SegHead segment_head(const ReconView &v, int row, int mx0, int lane)
+{
+    const int lbx = mx0 * 2 + lane, cbx = mx0 + (lane & 15), cplane = 1 + (lane >> 4);
+    const int lstride = (v.width >> 2) + 2, cstride = (v.width >> 3) + 2;
+    SegHead h = {0, 0, 0, 0, 0};
+    if (lbx < v.mcb_w * 2)
+    {
+        h.t0 = __ldg(v.blob + v.off_type[0] + (row * 2 + 1) * lstride + lbx + 1);
+        h.t1 = __ldg(v.blob + v.off_type[0] + (row * 2 + 2) * lstride + lbx + 1);
+        if (!v.is_ipic) h.mv_l = __ldg(reinterpret_cast<const uint32_t *>(v.blob + v.off_mv) + row * v.mcb_w + (lbx >> 1));
+    }
+    if (cbx < v.mcb_w)
+    {
+        h.t2 = __ldg(v.blob + (cplane == 1 ? v.off_type[1] : v.off_type[2]) + (row + 1) * cstride + cbx + 1);
+        if (!v.is_ipic) h.mv_c = __ldg(reinterpret_cast<const uint32_t *>(v.blob + v.off_mv) + row * v.mcb_w + cbx);
+    }
+    return h;
+}
+
+/* MAP work of one segment (16 macroblocks of macroblock row `row` starting at macroblock mx0):
+   three passes, one 4x4 block per lane and pass, 128 contiguous bytes per warp row store.  The head is
+   fetched by the caller ahead of time (the next segment's while this one is reconstructed): three
+   dependent memory latencies per pass (type -> vector -> reference rows) become the rows alone. */
+__device__ __forceinline__ void map_segment(const ReconView &v, int row, int mx0, int lane, const SegHead &head)
+{
     const int lbx = mx0 * 2 + lane, cbx = mx0 + (lane & 15), cplane = 1 + (lane >> 4);
     const bool l_ok = lbx < v.mcb_w * 2, c_ok = cbx < v.mcb_w;
-    const int lstride = (v.width >> 2) + 2, cstride = (v.width >> 3) + 2;
-    uint32_t t0 = 0, t1 = 0, t2 = 0, mv_l = 0, mv_c = 0;
-    if (l_ok)
-    {
-        t0 = __ldg(v.blob + v.off_type[0] + (row * 2 + 1) * lstride + lbx + 1);
-        t1 = __ldg(v.blob + v.off_type[0] + (row * 2 + 2) * lstride + lbx + 1);
-        if (!v.is_ipic) mv_l = __ldg(reinterpret_cast<const uint32_t *>(v.blob + v.off_mv) + row * v.mcb_w + (lbx >> 1));
-    }
-    if (c_ok)
-    {
-        t2 = __ldg(v.blob + (cplane == 1 ? v.off_type[1] : v.off_type[2]) + (row + 1) * cstride + cbx + 1);
-        if (!v.is_ipic) mv_c = __ldg(reinterpret_cast<const uint32_t *>(v.blob + v.off_mv) + row * v.mcb_w + cbx);
-    }
+    const uint32_t t0 = head.t0, t1 = head.t1, t2 = head.t2, mv_l = head.mv_l, mv_c = head.mv_c;
     /* ask L2 for the reference rows of the lower luma block and of the chroma block while the upper luma block is
        done (+2.4 % on realistic content; the same in the band kernel's classifying walk loses 7 % on dense content) */
     if (!v.is_ipic)
@@ -213,13 +226,21 @@ recon_map_kernel(const ReconJob *__restrict__ jobs, int units_per_pic, int ctas_
     __syncthreads();
     const ReconView &v = vw;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int unit = cta * kUnitsPerWarp * kWarps + warp;
+    if (unit >= units_per_pic) return;
+    int row = unit / v.nseg, mx0 = (unit - row * v.nseg) * SYM_SEG_MCBS;
+    SegHead head = segment_head(v, row, mx0, lane);
 #pragma unroll 1
     for (int it = 0; it < kUnitsPerWarp; ++it)
     {
-        const int unit = (cta * kUnitsPerWarp + it) * kWarps + warp;
-        if (unit >= units_per_pic) break;
-        const int row = unit / v.nseg;
-        map_segment(v, row, (unit - row * v.nseg) * SYM_SEG_MCBS, lane);
+        const int next = unit + kWarps;
+        const bool more = it + 1 < kUnitsPerWarp && next < units_per_pic;
+        const int nrow = next / v.nseg, nmx0 = (next - nrow * v.nseg) * SYM_SEG_MCBS;
+        SegHead nhead = {0, 0, 0, 0, 0};
+        if (more) nhead = segment_head(v, nrow, nmx0, lane);
+        map_segment(v, row, mx0, lane, head);
+        if (!more) break;
+        unit = next; row = nrow; mx0 = nmx0; head = nhead;
     }
 }
 
@@ -499,7 +520,7 @@ static int launch_map_cfg(int cfg, const ReconJob *d_jobs, int n_jobs, int units
     case 5: return launch_map<4, 4, 10>(d_jobs, n_jobs, units, stream);
     default:
         /* few pictures: one segment per warp (latency); large batches: fewer, fatter CTAs */
-        return (long long)n_jobs * units >= 148ll * 64 ? launch_map<4, 2, 8>(d_jobs, n_jobs, units, stream)
+        return (long long)n_jobs * units >= 148ll * 64 ? launch_map<4, 4, 10>(d_jobs, n_jobs, units, stream)   /* 48 registers, heads pipelined over 4 segments */
                                                        : launch_map<4, 1, 1>(d_jobs, n_jobs, units, stream);
     }
 }
