@@ -62,6 +62,11 @@ __device__ __forceinline__ void load_view(ReconView &vw, const ReconJob &J)
  * building blocks shared by the kernels
  * ------------------------------------------------------------------------------------------ */
 
+/* pictures with more record chunks than this (dense content: random vectors, ~400 chunks at 640x480) do not
+   prefetch reference rows: their gathers already keep the SM's outstanding requests full and the extra
+   requests only delay them (measured: -30 % on dense content with the kernel pair, +2.4 % on sparse) */
+constexpr uint32_t kPrefetchMaxChunks = 160;
+
 /* what a lane needs before it can start on a segment: the type bytes of its three blocks (upper luma,
    lower luma, chroma) and the two vector words (its luma blocks share a macroblock) */
 struct SegHead
@@ -99,7 +104,7 @@ __device__ __forceinline__ void map_segment(const ReconView &v, int row, int mx0
     const uint32_t t0 = head.t0, t1 = head.t1, t2 = head.t2, mv_l = head.mv_l, mv_c = head.mv_c;
     /* ask L2 for the reference rows of the lower luma block and of the chroma block while the upper luma block is
        done (+2.4 % on realistic content; the same in the band kernel's classifying walk loses 7 % on dense content) */
-    if (!v.is_ipic)
+    if (!v.is_ipic && v.n_chunks < kPrefetchMaxChunks)
     {
         if (l_ok && (t1 & 0x60))
         {
@@ -509,7 +514,7 @@ int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, int mcb_w, cuda
 int g_band_mode = 0;
 long long g_band_launches = 0;   /* steps issued as one fused band kernel (diagnostics) */   /* set by hvqm4_recon_set_mode: 0 auto, >0 force band kernel, <0 force map+record kernels */
 
-static int launch_map_cfg(int cfg, const ReconJob *d_jobs, int n_jobs, int units, cudaStream_t stream)
+static int launch_map_cfg(int cfg, const ReconJob *d_jobs, int n_jobs, int units, bool record_heavy, cudaStream_t stream)
 {
     switch (cfg)
     {
@@ -519,9 +524,11 @@ static int launch_map_cfg(int cfg, const ReconJob *d_jobs, int n_jobs, int units
     case 4: return launch_map<8, 4, 4>(d_jobs, n_jobs, units, stream);
     case 5: return launch_map<4, 4, 10>(d_jobs, n_jobs, units, stream);
     default:
-        /* few pictures: one segment per warp (latency); large batches: fewer, fatter CTAs */
-        return (long long)n_jobs * units >= 148ll * 64 ? launch_map<4, 4, 10>(d_jobs, n_jobs, units, stream)   /* 48 registers, heads pipelined over 4 segments */
-                                                       : launch_map<4, 1, 1>(d_jobs, n_jobs, units, stream);
+        /* few pictures: one segment per warp (latency); large batches: fewer, fatter CTAs -- four segments per
+           warp with pipelined heads on sparse content (2.73 M vs 2.56 M frames/s realistic), two on record-heavy
+           content, whose scattered gathers prefer more, shorter CTAs (950 k vs 672 k frames/s dense) */
+        if ((long long)n_jobs * units < 148ll * 64) return launch_map<4, 1, 1>(d_jobs, n_jobs, units, stream);
+        return record_heavy ? launch_map<4, 2, 8>(d_jobs, n_jobs, units, stream) : launch_map<4, 4, 10>(d_jobs, n_jobs, units, stream);
     }
 }
 
@@ -566,11 +573,12 @@ extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w,
     static const int band_env = env_int("HVQM4_BAND");   /* 1..4: force the band kernel (min blocks), -1: never */
     const int n_bands = (mcb_h + SYM_BAND_MCB_ROWS - 1) / SYM_BAND_MCB_ROWS;
     const int band_mode = g_band_mode != 0 ? g_band_mode : band_env;
-    /* auto: the fused band kernel pays off when the batch fills the GPU with bands AND the pictures are
-       record-heavy (measured: +4..8 % on dense content, -15 % on sparse content, where the map work
-       dominates and prefers the map kernel's higher occupancy) */
+    /* auto: the fused band kernel pays off when the pictures are record-heavy and there are enough bands
+       (measured on dense 640x480 content: 16 pictures = 128 bands 444 k vs 424 k frames/s, 64 pictures 862 k vs
+       729 k, 1024 pictures 1.14 M vs 0.94 M; 8 pictures 253 k vs 296 k).  Sparse content, where the map work
+       dominates, keeps the kernel pair (2.73 M vs 2.3 M) */
     const bool record_heavy = h_rec_prefix[n_jobs] >= 8u * (uint32_t)n_jobs;
-    if (band_mode > 0 || (band_mode == 0 && record_heavy && (long long)n_jobs * n_bands >= 148ll * 4))
+    if (band_mode > 0 || (band_mode == 0 && record_heavy && (long long)n_jobs * n_bands >= 128))
     {
         int rc;
         switch (band_mode)
@@ -590,7 +598,7 @@ extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w,
     for (int j0 = 0; j0 < n_jobs; j0 += sub)
     {
         const int nj = n_jobs - j0 < sub ? n_jobs - j0 : sub;
-        int rc = launch_map_cfg(map_cfg, d_jobs + j0, nj, units, stream);
+        int rc = launch_map_cfg(map_cfg, d_jobs + j0, nj, units, record_heavy, stream);
         if (rc != 0) return rc;
         if (launches) ++*launches;
         const uint32_t c0 = h_rec_prefix[j0], c1 = h_rec_prefix[j0 + nj];
