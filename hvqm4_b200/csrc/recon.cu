@@ -102,26 +102,31 @@ __device__ __forceinline__ void map_segment(const ReconView &v, int row, int mx0
     const int lbx = mx0 * 2 + lane, cbx = mx0 + (lane & 15), cplane = 1 + (lane >> 4);
     const bool l_ok = lbx < v.mcb_w * 2, c_ok = cbx < v.mcb_w;
     const uint32_t t0 = head.t0, t1 = head.t1, t2 = head.t2, mv_l = head.mv_l, mv_c = head.mv_c;
-    /* ask L2 for the reference rows of the lower luma block and of the chroma block while the upper luma block is
-       done (+2.4 % on realistic content; the same in the band kernel's classifying walk loses 7 % on dense content) */
-    if (!v.is_ipic && v.n_chunks < kPrefetchMaxChunks)
+    /* motion of the three blocks, resolved once: the two luma blocks share the macroblock's vector and
+       reference, the lower one starts four rows further down */
+    uint32_t mp0 = 0, mp1 = 0, mpc = 0;
+    if (!v.is_ipic)
     {
-        if (l_ok && (t1 & 0x60))
+        if (l_ok && (t0 & 0x60))
         {
-            const uint32_t mp = rc_motion_pack(v, 0, lbx, row * 2 + 1, t1, mv_l);
-            if (!(mp & RC_MP_POISON))
+            mp0 = rc_motion_pack(v, 0, lbx, row * 2, t0, mv_l);
+            mp1 = (mp0 & RC_MP_POISON) ? mp0 : mp0 + 4u * (uint32_t)v.width;
+        }
+        if (c_ok && (t2 & 0x60)) mpc = rc_motion_pack(v, cplane, cbx, row, t2, mv_c);
+        /* ask L2 for the reference rows of the lower luma block and of the chroma block while the upper luma
+           block is done (+2.4 % on realistic content; the same in the band kernel's classifying walk loses 7 %
+           on dense content, see kPrefetchMaxChunks) */
+        if (v.n_chunks < kPrefetchMaxChunks)
+        {
+            if (l_ok && (t0 & 0x60) && !(mp1 & RC_MP_POISON))
             {
-                const uint8_t *src = ((mp & RC_MP_FUTURE) ? v.ref[1] : v.ref[0]) + RC_MP_OFFSET(mp);
+                const uint8_t *src = ((mp1 & RC_MP_FUTURE) ? v.ref[1] : v.ref[0]) + RC_MP_OFFSET(mp1);
 #pragma unroll
                 for (int r = 0; r < 5; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + r * v.width));
             }
-        }
-        if (c_ok && (t2 & 0x60))
-        {
-            const uint32_t mp = rc_motion_pack(v, cplane, cbx, row, t2, mv_c);
-            if (!(mp & RC_MP_POISON))
+            if (c_ok && (t2 & 0x60) && !(mpc & RC_MP_POISON))
             {
-                const uint8_t *src = ((mp & RC_MP_FUTURE) ? v.ref[1] : v.ref[0]) + RC_MP_OFFSET(mp);
+                const uint8_t *src = ((mpc & RC_MP_FUTURE) ? v.ref[1] : v.ref[0]) + RC_MP_OFFSET(mpc);
 #pragma unroll
                 for (int r = 0; r < 5; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + r * (v.width >> 1)));
             }
@@ -134,7 +139,7 @@ __device__ __forceinline__ void map_segment(const ReconView &v, int row, int mx0
         if (!l_ok) continue;
         const int pw = v.width;
         uint32_t rows[4];
-        if (!rc_map_block_mv(v, 0, bx, by, pass ? t1 : t0, mv_l, rows)) continue;
+        if (!rc_map_block_mp(v, 0, bx, by, pass ? t1 : t0, pass ? mp1 : mp0, rows)) continue;
         uint8_t *dst = v.present + (by * 4) * pw + bx * 4;
 #pragma unroll
         for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];
@@ -144,7 +149,7 @@ __device__ __forceinline__ void map_segment(const ReconView &v, int row, int mx0
         if (!c_ok) return;
         const int pw = v.width >> 1;
         uint32_t rows[4];
-        if (!rc_map_block_mv(v, plane, bx, by, t2, mv_c, rows)) return;
+        if (!rc_map_block_mp(v, plane, bx, by, t2, mpc, rows)) return;
         const int plane_off = v.width * v.height + (plane == 2 ? pw * (v.height >> 1) : 0);
         uint8_t *dst = v.present + plane_off + (by * 4) * pw + bx * 4;
 #pragma unroll

@@ -552,9 +552,9 @@ RC_HD void rc_mc_block(const ReconView &v, int plane, int bx, int by, uint32_t t
  * Returns false when the block is left to the record kernel (raw, intra AOT).  Predicted-AOT
  * blocks get their motion-compensated prediction here; the record kernel reads it back from
  * the picture and adds the AOT residual (h4m:1387-1417 use the same prediction `mdst`). */
-/* mvw = the macroblock's vector word (rc_mv_word), loaded by the caller ahead of time; it is only
+/* mp = the block's resolved motion (rc_motion_pack), computed by the caller ahead of time; it is only
    looked at for inter blocks */
-RC_HD bool rc_map_block_mv(const ReconView &v, int plane, int bx, int by, uint32_t t, uint32_t mvw, uint32_t rows[4])
+RC_HD bool rc_map_block_mp(const ReconView &v, int plane, int bx, int by, uint32_t t, uint32_t mp, uint32_t rows[4])
 {
     switch (rc_classify(t, v.is_ipic))
     {
@@ -563,7 +563,7 @@ RC_HD bool rc_map_block_mv(const ReconView &v, int plane, int bx, int by, uint32
         return true;
     case RC_MC:
     case RC_AOT_INTER:
-        rc_mc_packed(v, plane, rc_motion_pack(v, plane, bx, by, t, mvw), rows);
+        rc_mc_packed(v, plane, mp, rows);
         return true;
     case RC_DIRECT:
         if ((v.is_ipic ? t : (t & 0xF)) == 8)
@@ -582,7 +582,7 @@ RC_HD bool rc_map_block_mv(const ReconView &v, int plane, int bx, int by, uint32
 RC_HD bool rc_map_block(const ReconView &v, int plane, int bx, int by, uint32_t t, uint32_t rows[4])
 {
     const bool inter = !v.is_ipic && (t & 0x60);
-    return rc_map_block_mv(v, plane, bx, by, t, inter ? rc_mv_word(v, plane, bx, by) : 0u, rows);
+    return rc_map_block_mp(v, plane, bx, by, t, inter ? rc_motion_pack(v, plane, bx, by, t, rc_mv_word(v, plane, bx, by)) : 0u, rows);
 }
 
 /* ---- RECORD kernel: one record (header word + payload) --------------------------------------
