@@ -238,19 +238,21 @@ recon_map_kernel(const ReconJob *__restrict__ jobs, int units_per_pic, int ctas_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int unit = cta * kUnitsPerWarp * kWarps + warp;
     if (unit >= units_per_pic) return;
-    int row = unit / v.nseg, mx0 = (unit - row * v.nseg) * SYM_SEG_MCBS;
-    SegHead head = segment_head(v, row, mx0, lane);
+    const int nseg = v.nseg;
+    int row = unit / nseg, seg = unit - row * nseg;       /* one division per warp; then stepped */
+    SegHead head = segment_head(v, row, seg * SYM_SEG_MCBS, lane);
 #pragma unroll 1
     for (int it = 0; it < kUnitsPerWarp; ++it)
     {
         const int next = unit + kWarps;
         const bool more = it + 1 < kUnitsPerWarp && next < units_per_pic;
-        const int nrow = next / v.nseg, nmx0 = (next - nrow * v.nseg) * SYM_SEG_MCBS;
+        int nrow = row, nseg_i = seg + kWarps;
+        while (nseg_i >= nseg) { nseg_i -= nseg; ++nrow; }
         SegHead nhead = {0, 0, 0, 0, 0};
-        if (more) nhead = segment_head(v, nrow, nmx0, lane);
-        map_segment(v, row, mx0, lane, head);
+        if (more) nhead = segment_head(v, nrow, nseg_i * SYM_SEG_MCBS, lane);
+        map_segment(v, row, seg * SYM_SEG_MCBS, lane, head);
         if (!more) break;
-        unit = next; row = nrow; mx0 = nmx0; head = nhead;
+        unit = next; row = nrow; seg = nseg_i; head = nhead;
     }
 }
 
