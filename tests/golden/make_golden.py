@@ -38,6 +38,8 @@ CASES = {
     "wide_1024x576_v13_IPB": dict(width=1024, height=576, version=13, gop="IPBB", n_gops=1, seed=205, profile=0),
     # 160 macroblocks per row: more than one column tile of the band kernel (recon.cu kTileMcbs)
     "hd_1280x720_v15_IPB": dict(width=1280, height=720, version=15, gop="IPBB", n_gops=1, seed=206, profile=0),
+    # 512 macroblocks per row: four column tiles of the band kernel, queues at their fixed maximum size
+    "uhd_4096x2160_v15_IPB": dict(width=4096, height=2160, version=15, gop="IPB", n_gops=1, seed=211, profile=0),
     # pictures smaller than the 70x38-block nest: MakeNest mirrors, then zero-fills (h4m:1173-1203)
     "tiny_16x16_v15_IPB": dict(width=16, height=16, version=15, gop="IPBBPB", n_gops=2, seed=207, profile=0),
     "small_64x48_v13_IPB": dict(width=64, height=48, version=13, gop="IPBBPB", n_gops=2, seed=208, profile=0),

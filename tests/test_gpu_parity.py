@@ -22,7 +22,8 @@ def recon_mode(request, native_lib):
 SDK_CASES = ["cfg1_320x240_v15_I30", "cfg2_640x480_v15_IP15", "cfg3_640x480_v15_IPB", "cfg4_320x240_v13_IPB",
              "realistic_640x480_v15_IPB", "realistic_320x240_v13_IPB", "min_280x152_v15_IPB",
              "ragged_328x248_v15_IPB", "wide_1024x576_v13_IPB", "hd_1280x720_v15_IPB",
-             "tiny_16x16_v15_IPB", "small_64x48_v13_IPB", "mirror_h_200x152_v15_IPB", "mirror_v_320x104_v15_IPB"]
+             "tiny_16x16_v15_IPB", "small_64x48_v13_IPB", "mirror_h_200x152_v15_IPB", "mirror_v_320x104_v15_IPB",
+             "uhd_4096x2160_v15_IPB"]
 
 
 @pytest.mark.parametrize("name", SDK_CASES)
@@ -200,7 +201,8 @@ def test_gpu_entropy_stage_matches_golden(native_lib, golden):
 
 
 @pytest.mark.parametrize("name", ["cfg4_320x240_v13_IPB", "realistic_640x480_v15_IPB", "ragged_328x248_v15_IPB", "wide_1024x576_v13_IPB",
-                                  "hd_1280x720_v15_IPB", "tiny_16x16_v15_IPB", "small_64x48_v13_IPB", "mirror_h_200x152_v15_IPB"])
+                                  "hd_1280x720_v15_IPB", "tiny_16x16_v15_IPB", "small_64x48_v13_IPB", "mirror_h_200x152_v15_IPB",
+                                  "uhd_4096x2160_v15_IPB"])
 def test_gpu_entropy_stage_other_geometries(native_lib, golden, name):
     case = golden[name]
     data = synth.generate(**case["args"])
