@@ -96,6 +96,8 @@ SIGNATURES = {
     "HVQM4SetReconMode": (None, [c_int]),
     "HVQM4HostAlloc": (c_void_p, [c_size_t]),
     "HVQM4HostFree": (None, [c_void_p]),
+    "HVQM4HostRegister": (c_int, [c_void_p, c_size_t]),
+    "HVQM4HostUnregister": (c_int, [c_void_p]),
     "HVQM4ParseFile": (c_int, [c_char_p, c_size_t, POINTER(FileInfo), POINTER(FrameRef), c_int]),
     "HVQM4ParseFileAudio": (c_int, [c_char_p, c_size_t, POINTER(AudioRef), c_int]),
     "HVQM4DecodeAudioBatch": (c_int, [c_int, c_int, POINTER(AudioState), POINTER(c_int32), POINTER(c_void_p), POINTER(c_uint32),

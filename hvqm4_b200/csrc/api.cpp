@@ -216,6 +216,7 @@ struct HVQM4Batch
     cudaEvent_t ev_parse[H4_PARSE_SLOTS] = {};
     int parse_turn = 0, ipic_slot = 0, ipic_fence_left = 0;
     cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_d2h = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    std::vector<const uint8_t *> gather_src;        /* GPU entropy mode: device-visible source of every picture of the step */
     bool d2h_pending = false;
     cudaEvent_t ev_d2h_mark[2] = {nullptr, nullptr};   /* read-backs issued before step n, n - 1 (batch_wait_readbacks) */
     unsigned step_no = 0;
@@ -256,6 +257,119 @@ static bool batch_create_parse_streams(HVQM4Batch *b)
         if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_parse[j], cudaEventDisableTiming), "cudaEventCreate")) return false;
     }
     return true;
+}
+
+/* ---- page-locked application memory (HVQM4HostRegister): the GPU entropy mode fetches pictures that lie in
+   such a range itself (entropy_dev.cu: dev_gather_kernel) instead of having host threads copy them ---- */
+struct HostRange
+{
+    uintptr_t begin, end;       /* as the application sees it */
+    uintptr_t lo, hi;           /* the pages it touches */
+    uint8_t *dev[16];           /* device-visible address of `begin` per device (filled on demand) */
+};
+/* Ranges of separate allocations may share pages, and a page can be registered only once: the
+   pages are kept as disjoint registered segments, each counting the ranges that touch it. */
+struct PageSegment
+{
+    uintptr_t lo, hi;
+    int refs;
+};
+static std::mutex g_ranges_lock;
+static std::vector<HostRange> g_ranges;
+static std::vector<PageSegment> g_segments;
+
+static void release_segments(uintptr_t lo, uintptr_t hi)
+{
+    for (size_t i = 0; i < g_segments.size();)
+    {
+        PageSegment &sg = g_segments[i];
+        if (sg.lo < hi && lo < sg.hi && --sg.refs == 0)
+        {
+            cuda_ok(cudaHostUnregister((void *)sg.lo), "cudaHostUnregister");
+            g_segments.erase(g_segments.begin() + (long)i);
+        }
+        else
+            ++i;
+    }
+}
+
+H4_API int HVQM4HostRegister(void *ptr, size_t bytes)
+{
+    if (!ptr || !bytes) return HVQM4_ERR_ARGUMENT;
+    if (!have_device()) return HVQM4_ERR_NO_DEVICE;
+    const uintptr_t page = 4096, lo = (uintptr_t)ptr & ~(page - 1), hi = ((uintptr_t)ptr + bytes + page - 1) & ~(page - 1);
+    std::lock_guard<std::mutex> guard(g_ranges_lock);
+    /* pages of [lo, hi) not yet registered: walk the segments that overlap in address order */
+    std::vector<PageSegment> gaps;
+    uintptr_t at = lo;
+    while (at < hi)
+    {
+        const PageSegment *next = nullptr;
+        for (const PageSegment &sg : g_segments)
+            if (sg.hi > at && sg.lo < hi && (!next || sg.lo < next->lo)) next = &sg;
+        const uintptr_t gap_end = next ? (next->lo > at ? next->lo : at) : hi;
+        if (gap_end > at) gaps.push_back(PageSegment{at, gap_end, 0});
+        at = next ? next->hi : hi;
+    }
+    size_t done = 0;
+    for (; done < gaps.size(); ++done)
+        if (!cuda_ok(cudaHostRegister((void *)gaps[done].lo, gaps[done].hi - gaps[done].lo, cudaHostRegisterPortable | cudaHostRegisterMapped),
+                     "cudaHostRegister"))
+            break;
+    if (done < gaps.size())
+    {
+        for (size_t i = 0; i < done; ++i) cudaHostUnregister((void *)gaps[i].lo);
+        return HVQM4_ERR_CUDA;
+    }
+    for (const PageSegment &g : gaps) g_segments.push_back(g);
+    for (PageSegment &sg : g_segments)
+        if (sg.lo < hi && lo < sg.hi) ++sg.refs;
+    HostRange r{};
+    r.begin = (uintptr_t)ptr;
+    r.end = r.begin + bytes;
+    r.lo = lo;
+    r.hi = hi;
+    g_ranges.push_back(r);
+    return HVQM4_OK;
+}
+
+H4_API int HVQM4HostUnregister(void *ptr)
+{
+    std::lock_guard<std::mutex> guard(g_ranges_lock);
+    for (size_t i = 0; i < g_ranges.size(); ++i)
+        if (g_ranges[i].begin == (uintptr_t)ptr)
+        {
+            release_segments(g_ranges[i].lo, g_ranges[i].hi);
+            g_ranges.erase(g_ranges.begin() + (long)i);
+            return HVQM4_OK;
+        }
+    return HVQM4_ERR_ARGUMENT;
+}
+
+/* device-visible address of [p, p + bytes) if it lies in a registered range, else NULL (caller holds the lock) */
+static const uint8_t *registered_device_ptr(const uint8_t *p, size_t bytes, int device)
+{
+    const uintptr_t a = (uintptr_t)p;
+    for (HostRange &r : g_ranges)
+        if (a >= r.begin && a + bytes <= r.end)
+        {
+            if (device < 0 || device >= 16) return nullptr;
+            if (!r.dev[device])
+            {
+                void *d = nullptr;
+                if (cudaHostGetDevicePointer(&d, (void *)r.begin, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+                if (d != (void *)r.begin)
+                {
+                    /* no identity mapping: device addresses are contiguous only inside one registered segment */
+                    bool one = false;
+                    for (const PageSegment &sg : g_segments) one = one || (sg.lo <= r.lo && r.hi <= sg.hi);
+                    if (!one) return nullptr;
+                }
+                r.dev[device] = static_cast<uint8_t *>(d);
+            }
+            return r.dev[device] + (a - r.begin);
+        }
+    return nullptr;
 }
 
 /* Called once per step before its reconstruction is enqueued: the surfaces the step writes were
@@ -404,11 +518,26 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
     auto t_host0 = std::chrono::steady_clock::now();
     const size_t pics_bytes = align_up((size_t)n * sizeof(H4DevPicture), 256);
     const size_t jobs_bytes = align_up((size_t)n * sizeof(ReconJob), 256);
-    size_t total = pics_bytes + jobs_bytes;
+    const size_t gather_bytes = align_up((size_t)n * sizeof(H4Gather), 256);
+    /* pictures in registered (page-locked, mapped) memory are fetched by the GPU; all of a step or none */
+    bool gather = true;
+    {
+        std::lock_guard<std::mutex> guard(g_ranges_lock);
+        gather = !g_ranges.empty();
+        b->gather_src.resize((size_t)n);
+        for (int i = 0; i < n && gather; ++i)
+        {
+            b->gather_src[i] = registered_device_ptr(frames[i], frame_bytes[i], b->device);
+            gather = b->gather_src[i] != nullptr;
+        }
+    }
+    const size_t head_bytes = pics_bytes + jobs_bytes + (gather ? gather_bytes : 0);
+    size_t total = head_bytes;
     for (int i = 0; i < n; ++i)
     {
-        b->offs[i] = total;
-        total += align_up((size_t)frame_bytes[i] + 16, 16);
+        /* the device copy keeps the source's alignment modulo 16 when the GPU gathers it */
+        b->offs[i] = total + (gather ? (size_t)((uintptr_t)b->gather_src[i] & 15u) : 0);
+        total += align_up((size_t)frame_bytes[i] + 16, 16) + (gather ? 16 : 0);
     }
     Arena &a = b->arena[b->cur];
     if (a.in_flight)
@@ -419,13 +548,21 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
     if (!arena_reserve(b, a, total)) return HVQM4_ERR_NOMEM;
     H4DevPicture *pics = reinterpret_cast<H4DevPicture *>(a.h);
     ReconJob *jobs = reinterpret_cast<ReconJob *>(a.h + pics_bytes);
-    b->pool->parallel_for(n, [&](int i) {
-        uint8_t *dst = a.h + b->offs[i];
-        memcpy(dst, frames[i], frame_bytes[i]);
-        memset(dst + frame_bytes[i], 0, 16);
-    });
+    H4Gather *gd = reinterpret_cast<H4Gather *>(a.h + pics_bytes + jobs_bytes);
+    if (!gather)
+        b->pool->parallel_for(n, [&](int i) {
+            uint8_t *dst = a.h + b->offs[i];
+            memcpy(dst, frames[i], frame_bytes[i]);
+            memset(dst + frame_bytes[i], 0, 16);
+        });
     for (int i = 0; i < n; ++i)
     {
+        if (gather)
+        {
+            gd[i].src = b->gather_src[i];
+            gd[i].dst_off = (uint32_t)b->offs[i];
+            gd[i].bytes = frame_bytes[i];
+        }
         StreamState &s = b->st[stream_ids[i]];
         const int t = frame_types[i];
         pics[i].data = a.d + b->offs[i];
@@ -471,7 +608,19 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
         cudaStreamWaitEvent(sp, b->ev_parse[b->ipic_slot], 0);
         --b->ipic_fence_left;
     }
-    if (!cuda_ok(cudaMemcpyAsync(a.d, a.h, total, cudaMemcpyHostToDevice, sp), "cudaMemcpyAsync(H2D)")) return HVQM4_ERR_CUDA;
+    if (total > 0xFFFFFFFFull) return HVQM4_ERR_OVERFLOW;
+    if (!cuda_ok(cudaMemcpyAsync(a.d, a.h, gather ? head_bytes : total, cudaMemcpyHostToDevice, sp), "cudaMemcpyAsync(H2D)")) return HVQM4_ERR_CUDA;
+    if (gather)
+    {
+        const int grc = hvqm4_dev_gather(reinterpret_cast<const H4Gather *>(a.d + pics_bytes + jobs_bytes), n, a.d, sp);
+        if (grc != 0)
+        {
+            cuda_ok((cudaError_t)grc, "gather kernel launch");
+            return HVQM4_ERR_CUDA;
+        }
+        ++g_launches;
+        b->stats[1] += 1;
+    }
     cudaMemsetAsync(b->d_blob_used + par, 0, sizeof(unsigned long long), sp);
     ReconJob *d_jobs = reinterpret_cast<ReconJob *>(a.d + pics_bytes);
     int rc = hvqm4_dev_entropy_parse(b->d_estate, b->eslot, reinterpret_cast<const H4DevPicture *>(a.d), n, par,

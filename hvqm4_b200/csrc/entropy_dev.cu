@@ -110,7 +110,39 @@ dev_parse_kernel(uint8_t *arena, size_t slot_bytes, const H4DevPicture *pics, in
     }
 }
 
+/* The bitstreams of a step fetched by the GPU itself from page-locked, mapped host memory
+   (HVQM4HostRegister): no host thread touches the picture bytes, only a 16-byte descriptor per
+   picture is uploaded.  Source and destination share their alignment modulo 16, so the body is
+   16-byte words; every thread keeps several PCIe reads in flight. */
+__global__ void __launch_bounds__(128)
+dev_gather_kernel(const H4Gather *__restrict__ descs, uint8_t *__restrict__ base)
+{
+    const H4Gather d = descs[blockIdx.x];
+    const uint8_t *src = d.src;
+    uint8_t *dst = base + d.dst_off;
+    const uint32_t head = min((16u - (uint32_t)((uintptr_t)src & 15u)) & 15u, d.bytes);
+    const uint32_t n16 = (d.bytes - head) >> 4, tail0 = head + (n16 << 4);
+    if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
+    const uint4 *s16 = reinterpret_cast<const uint4 *>(src + head);
+    uint4 *d16 = reinterpret_cast<uint4 *>(dst + head);
+#pragma unroll 4
+    for (uint32_t i = threadIdx.x; i < n16; i += 128) d16[i] = s16[i];
+    /* tail bytes, then 16 bytes of zeros (the bit reader's slack, h4m:2080-2082) */
+    if (threadIdx.x < d.bytes - tail0 + 16)
+    {
+        const uint32_t o = tail0 + threadIdx.x;
+        dst[o] = o < d.bytes ? src[o] : (uint8_t)0;
+    }
+}
+
 }  // namespace
+
+extern "C" int hvqm4_dev_gather(const H4Gather *d_descs, int n, uint8_t *d_base, cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    dev_gather_kernel<<<n, 128, 0, stream>>>(d_descs, d_base);
+    return (int)cudaGetLastError();
+}
 
 /* per-phase cycle totals of the GPU parser since the last call (diagnostics): hdr+trees, pass 1,
    plan, pass 2 scheduling, map copies, flat decode, record fill */

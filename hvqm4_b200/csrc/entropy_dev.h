@@ -16,6 +16,14 @@ typedef struct H4DevPicture
     int32_t pad;
 } H4DevPicture;
 
+/* one picture to fetch from page-locked, mapped host memory into the step's device arena */
+typedef struct H4Gather
+{
+    const uint8_t *src;     /* device-visible address of the picture bytes */
+    uint32_t dst_off;       /* byte offset in the arena; (dst_off & 15) == (src & 15) */
+    uint32_t bytes;
+} H4Gather;
+
 struct ReconJob;
 
 #ifdef __cplusplus
@@ -37,6 +45,8 @@ int hvqm4_dev_entropy_init(uint8_t *arena, size_t slot_bytes, int n_streams, int
 int hvqm4_dev_entropy_parse(uint8_t *arena, size_t slot_bytes, const H4DevPicture *d_pics, int n_pics, int parity, uint8_t *blob_arena,
                             unsigned long long *d_blob_used, unsigned long long blob_cap, struct ReconJob *d_jobs,
                             uint32_t *d_errors, cudaStream_t stream);
+/* copies n pictures out of mapped host memory (one CTA each, 16-byte words) and clears 16 bytes behind each */
+int hvqm4_dev_gather(const H4Gather *d_descs, int n, uint8_t *d_base, cudaStream_t stream);
 void hvqm4_dev_entropy_profile(unsigned long long out[8]);
 #ifdef __cplusplus
 }

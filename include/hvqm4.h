@@ -215,6 +215,17 @@ void HVQM4SetReconMode(int mode);
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA toolchain. */
 void *HVQM4HostAlloc(size_t bytes);
 void HVQM4HostFree(void *p);
+/* Page-locks and maps memory the application already owns (e.g. the file images the bitstreams
+   live in).  With HVQM4BatchSetEntropyMode(batch, 1), a step whose pictures all lie in registered
+   ranges is fetched by the GPU itself (a gather kernel over PCIe): no host thread copies picture
+   bytes, the host's share of a step is one 16-byte descriptor per picture.  Ranges may share pages
+   (separately allocated buffers): a page stays registered until its last range is unregistered.
+   It frees host cores, it is not faster (measured on B200, 1 024 streams, frames read back: dense
+   97.6 k vs 105 k frames/s with 16 host threads, 95 k vs 92 k with 2; realistic 122 k vs 121 k and
+   109 k vs 119 k), so nothing registers memory implicitly.  Unregister before the memory is freed.
+   Returns HVQM4_OK or error bits. */
+int HVQM4HostRegister(void *ptr, size_t bytes);
+int HVQM4HostUnregister(void *ptr);
 
 /* ---------------------------------------------------------------- container helper
  * Minimal .h4m walker (header h4m:2175-2247, GOP blocks h4m:2429-2438, frame records

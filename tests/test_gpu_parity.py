@@ -461,3 +461,50 @@ def test_staggered_streams_and_partial_steps_match_oracle(native_lib, oracle, gp
     finally:
         batch.close()
         native_lib.lib().HVQM4HostFree(pinned)
+
+
+def test_registered_host_memory_is_gathered_by_the_gpu(native_lib, oracle):
+    """HVQM4HostRegister: with the bitstreams in page-locked, mapped application memory the GPU entropy mode
+    fetches the pictures itself (dev_gather_kernel) -- same frames as the oracle, every source alignment
+    modulo 16 occurs (the pictures sit at arbitrary offsets inside the file images), and a step that mixes
+    registered and unregistered pictures falls back to the host copy.  The files are registered one by one:
+    neighbours share pages, which are registered once and released with their last user."""
+    n, gop = 20, "IPBBPB"
+    files = [synth.generate(320, 240, 15, gop, 1, seed=8700 + i, profile=i % 2) for i in range(n)]
+    want = [[md5(yuv) for _, _, _, yuv in oracle.PortDecoder(f).frames()] for f in files]
+    parsed = [native_lib.parse_file(f)[1] for f in files]
+    # one shared image with the files at odd offsets, registered file by file; plus an unregistered copy of stream 0
+    offs, blob = [], bytearray()
+    for i, f in enumerate(files):
+        blob += bytes(i % 7 + 1)
+        offs.append(len(blob))
+        blob += f
+    blob += bytes(64)
+    image = ctypes.create_string_buffer(bytes(blob), len(blob))
+    loose = ctypes.create_string_buffer(files[0], len(files[0]) + 8)
+    base = ctypes.addressof(image)
+    lib = native_lib.lib()
+    for i, f in enumerate(files):
+        assert lib.HVQM4HostRegister(base + offs[i], len(f)) == 0
+    batch = native_lib.Batch(n, 320, 240, 15, gpu_entropy=True)
+    try:
+        assert {(base + offs[i] + parsed[i][k].offset) & 15 for i in range(n) for k in range(len(gop))} == set(range(16))
+        launches0 = native_lib.kernel_launches()
+        for k in range(len(gop)):
+            ptrs = [base + offs[i] + parsed[i][k].offset for i in range(n)]
+            if k == 3:
+                ptrs[0] = ctypes.addressof(loose) + parsed[0][k].offset      # mixed step: host copy path
+            batch.decode(list(range(n)), [parsed[i][k].frame_type for i in range(n)], ptrs, [parsed[i][k].bytes for i in range(n)])
+            batch.sync()
+            for i in range(n):
+                assert md5(batch.read_frame(i)) == want[i][k], (i, k)
+        # gather + parse + band kernel per gathered step, parse + band for the mixed one
+        assert native_lib.kernel_launches() - launches0 == 3 * (len(gop) - 1) + 2
+    finally:
+        batch.close()
+        for i in range(n):
+            assert lib.HVQM4HostUnregister(base + offs[i]) == 0
+        assert lib.HVQM4HostUnregister(base + offs[0]) != 0
+        # every page was released with its last user: the whole image can be registered again
+        assert lib.HVQM4HostRegister(base, len(blob)) == 0
+        assert lib.HVQM4HostUnregister(base) == 0

@@ -21,6 +21,9 @@ files = [synth.generate(640, 480, 15, GOP, 1, seed=5000 + i, profile=PROFILE) fo
 parsed = [api.parse_file(f) for f in files]
 bufs = [ctypes.create_string_buffer(f, len(f) + 8) for f in files]
 bases = [ctypes.addressof(b) for b in bufs]
+if os.environ.get('E2E_REGISTER'):
+    for b in bufs:
+        assert api.lib().HVQM4HostRegister(ctypes.addressof(b), len(b)) == 0
 batch = api.Batch(S, 640, 480, 15, host_threads=T, gpu_entropy=bool(GPU_ENTROPY))
 ids = list(range(S))
 steps = []
