@@ -429,13 +429,19 @@ def main():
     if rank == 0 and not args.no_e2e:
         from hvqm4_b200 import synth
         one = synth.generate(W, H, 15, "I" + "P" * 14, 2, seed=102, profile=args.profile)
+        ptr, disp, ftype = ctypes.c_void_p(), ctypes.c_uint32(), ctypes.c_uint32()
         for _ in range(2):                              # first pass warms allocations and the driver
-            pl = api.Player(one)
-            it = iter(pl)
-            next(it)                                    # the first picture allocates the device twins
+            # the reference program's loop in C (player.cpp: demux, rotation, HVQM4Decode?pic into host frame
+            # buffers); the frame pointer is handed back, nothing is copied on the Python side
+            pl = api.FilePlayer(one)
+            nxt = lambda: api.lib().HVQM4PlayerNextFrame(pl._h, ctypes.byref(ptr), ctypes.byref(disp), ctypes.byref(ftype))
+            assert nxt() == 1                           # the first picture allocates the device twins
             t0 = time.perf_counter()
-            nfr = sum(1 for _ in it)
+            nfr = 0
+            while nxt() == 1:
+                nfr += 1
             t_sdk = time.perf_counter() - t0
+            assert pl.errors() == 0
             pl.close()
         single = {"workload": "BASELINE config 2: one synthetic 640x480 HVQM4 1.5 I/P GOP-15 stream, HVQM4Decode?pic with host buffers",
                   "sdk_fps": nfr / t_sdk, "frames": nfr}

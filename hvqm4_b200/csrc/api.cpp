@@ -1023,6 +1023,10 @@ struct Compat
     cudaStream_t stream = nullptr;
     uint32_t errors = 0;
     uint32_t next_frame_bytes = 0;
+    /* HVQM4_SDK_TRACE=1: seconds spent per phase of the synchronous calls, printed by HVQM4ReleaseBuffer */
+    bool trace = false;
+    double t_phase[4] = {0, 0, 0, 0};   /* parse_begin, parse_finish, resolve + enqueue, wait */
+    unsigned n_calls = 0;
 };
 
 /* what lives in the caller's work buffer */
@@ -1091,7 +1095,11 @@ void compat_decode(SeqObj *so, int type, const uint8_t *frame, void *present, vo
     }
     const size_t len = c->next_frame_bytes ? c->next_frame_bytes : (size_t)1 << 30;
     c->next_frame_bytes = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const auto t0 = now();
     const size_t need = h4e_parse_begin(c->seq, type, frame, len);
+    const auto t1 = now();
     if (!need)
     {
         c->errors |= HVQM4_ERR_GEOMETRY;
@@ -1114,7 +1122,9 @@ void compat_decode(SeqObj *so, int type, const uint8_t *frame, void *present, vo
         }
         c->blob_cap = cap;
     }
+    const auto t1b = now();
     c->errors |= h4e_parse_finish(c->seq, c->h_blob + 256);
+    const auto t2 = now();
     ReconJob *job = reinterpret_cast<ReconJob *>(c->h_blob);
     uint8_t *d_present = resolve(c, present, false);
     uint8_t *d_past = past ? resolve(c, past, true) : d_present;
@@ -1142,8 +1152,17 @@ void compat_decode(SeqObj *so, int type, const uint8_t *frame, void *present, vo
     }
     if (ok && !is_device_ptr(present))
         ok = cuda_ok(cudaMemcpyAsync(present, d_present, c->frame_bytes, cudaMemcpyDeviceToHost, c->stream), "download frame");
+    const auto t3 = now();
     ok = ok && cuda_ok(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
     if (!ok) c->errors |= HVQM4_ERR_CUDA;
+    if (c->trace)
+    {
+        c->t_phase[0] += secs(t0, t1);
+        c->t_phase[1] += secs(t1b, t2);
+        c->t_phase[2] += secs(t2, t3);
+        c->t_phase[3] += secs(t3, now());
+        ++c->n_calls;
+    }
 }
 
 }  // namespace
@@ -1191,6 +1210,7 @@ H4_API void HVQM4SetBuffer(SeqObj *seqobj, void *workbuff)
     c->surf_bytes = align_up(c->frame_bytes + 64, 256);
     if (have_device() && !cuda_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate"))
         c->stream = nullptr;
+    c->trace = getenv("HVQM4_SDK_TRACE") != nullptr;
     w->impl = c;
     w->magic = kCompatMagic;
 }
@@ -1199,6 +1219,9 @@ H4_API void HVQM4ReleaseBuffer(SeqObj *seqobj)
 {
     Compat *c = compat_of(seqobj);
     if (!c) return;
+    if (c->trace && c->n_calls)
+        fprintf(stderr, "hvqm4_b200: %u SDK calls, per call: parse_begin %.1f us, parse_finish %.1f us, enqueue %.1f us, wait %.1f us\n", c->n_calls,
+                1e6 * c->t_phase[0] / c->n_calls, 1e6 * c->t_phase[1] / c->n_calls, 1e6 * c->t_phase[2] / c->n_calls, 1e6 * c->t_phase[3] / c->n_calls);
     if (c->stream)
     {
         cudaStreamSynchronize(c->stream);

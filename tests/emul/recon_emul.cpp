@@ -121,7 +121,7 @@ extern "C" __attribute__((visibility("default")))
 void emul_predict_diag(uint8_t *dst16, const uint8_t *src, int stride, int hx, int hy)
 {
     uint32_t rows[4], W[10];
-    rc_predict_load(W, src, stride, hy);
+    rc_predict_load<true>(W, src, stride, hx, hy);
     rc_predict_filter(rows, W, (uint32_t)((uintptr_t)src & 3), hx, hy, true);
     memcpy(dst16, rows, 16);
 }
