@@ -198,21 +198,20 @@ template <int kThreads>
 __device__ __forceinline__ void build_nest_table(const ReconView &v, uint8_t *packed)
 {
     uint32_t *s_nest_tab = reinterpret_cast<uint32_t *>(rc_smem + RC_SMEM_NEST_OFF);
-    /* stage the packed rows (35 B) at a 40-byte pitch, zero padded */
-    const uint8_t *src = v.blob + v.off_nest;
-    for (int i = threadIdx.x; i < SYM_NEST_H * 40; i += kThreads)
-    {
-        const int y = i / 40, x = i - y * 40;
-        packed[i] = x < SYM_NEST_ROW_BYTES ? __ldg(src + y * SYM_NEST_ROW_BYTES + x) : (uint8_t)0;
-    }
+    /* stage the packed rows as they are (35-byte pitch, the blob keeps them 16-byte aligned): word copies */
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(v.blob + v.off_nest);
+    uint32_t *stage = reinterpret_cast<uint32_t *>(packed);
+    for (int i = threadIdx.x; i < (SYM_NEST_BYTES + 3) / 4; i += kThreads) stage[i] = __ldg(src + i);
     __syncthreads();
-    /* nibbles x..x+7 of row y, spread into the step-1 and step-2 tables; (y, 2j) and (y, 2j+1) share bytes j..j+4 */
-    const uint32_t *pw = reinterpret_cast<const uint32_t *>(packed);
+    /* nibbles x..x+7 of row y, spread into the step-1 and step-2 tables; (y, 2j) and (y, 2j+1) share bytes
+       j..j+4 of the row.  Entries near the end of a row run into the next row: those nibbles lie beyond
+       column 69, which no descriptor reaches (offset <= 63, largest pattern + 6). */
+    const uint32_t *pw = stage;
     for (int i = threadIdx.x; i < SYM_NEST_H * 32; i += kThreads)
     {
         const int y = i >> 5, j = i & 31;
-        const int w = y * 10 + (j >> 2), sh = (j & 3) * 8;
-        const uint32_t w0 = pw[w], w1 = pw[w + 1], w2 = (j & 3) ? pw[w + 2] : 0u;
+        const int b = y * SYM_NEST_ROW_BYTES + j, w = b >> 2, sh = (b & 3) * 8;
+        const uint32_t w0 = pw[w], w1 = pw[w + 1], w2 = sh ? pw[w + 2] : 0u;
         const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
         const uint32_t odd = (lo >> 4) | (hi << 28);
         s_nest_tab[y * 64 + 2 * j] = rc_nest_spread_step1(lo);
