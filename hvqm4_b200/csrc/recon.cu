@@ -182,6 +182,30 @@ __device__ __forceinline__ void record_chunk(const ReconView &v, uint32_t c, int
     for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];
 }
 
+/* the same with the chunk descriptor, the lane's header word and rc_record_extra() fetched by the caller ahead of time */
+__device__ __forceinline__ void record_chunk_pre(const ReconView &v, uint2 cd, int lane, uint32_t hdr, uint32_t extra)
+{
+    const uint32_t count = cd.y & 0xFF, len = ((cd.y >> 8) & 0xFF) + 1;
+    const int cls = (int)((cd.y >> 16) & 0xFF);
+    if ((uint32_t)lane >= count) return;
+    const uint32_t *rec = v.rec + cd.x + lane * len;
+    uint32_t t;
+    int plane, bx, by;
+    rc_record_coords(hdr, t, plane, bx, by);
+    const int pw = plane ? v.width >> 1 : v.width;
+    const int plane_off = plane == 0 ? 0 : plane == 1 ? v.width * v.height : v.width * v.height + (v.width >> 1) * (v.height >> 1);
+    uint8_t *dst = v.present + plane_off + (by * 4) * pw + bx * 4;
+    uint32_t rows[4];
+    if (cls == SYM_REC_INTER)
+    {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) rows[r] = __ldcg(reinterpret_cast<const uint32_t *>(dst + r * pw));
+    }
+    rc_record_block_pre(v, cls, len, rec, hdr, extra, rows);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];
+}
+
 /* h4m:262-273 into shared memory */
 template <int kThreads>
 __device__ __forceinline__ void build_div_tables()
@@ -270,33 +294,78 @@ recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs, uint32_t cta_
     ReconView &vw = *reinterpret_cast<ReconView *>(rc_smem + RC_SMEM_VIEW_OFF);
     __shared__ uint32_t s_cta_in_pic;
 
-    /* which picture does this CTA belong to: last job with rec_cta_begin <= blockIdx.x */
-    if (threadIdx.x == 0)
+    /* which picture does this CTA belong to: last job with rec_cta_begin <= blockIdx.x.  Warp 0 searches 32 ways
+       (two rounds of independent loads for 1 024 pictures instead of ten dependent ones) */
+    if (threadIdx.x < 32)
     {
         const uint32_t gcta = blockIdx.x + cta_base;     /* rec_cta_begin is a prefix over the whole step */
-        int lo = 0, hi = n_jobs - 1;
-        while (lo < hi)
+        const int l = (int)threadIdx.x;
+        int lo = 0, hi = n_jobs;                         /* answer in [lo, hi); jobs[lo].rec_cta_begin <= gcta */
+        while (hi - lo > 1)
         {
-            const int mid = (lo + hi + 1) >> 1;
-            if (__ldg(&jobs[mid].rec_cta_begin) <= gcta) lo = mid;
-            else hi = mid - 1;
+            const int step = (hi - lo + 31) >> 5, idx = lo + l * step;
+            const bool ok = idx < hi && __ldg(&jobs[idx].rec_cta_begin) <= gcta;
+            const int k = 31 - __clz((int)(__ballot_sync(0xFFFFFFFFu, ok) | 1u));
+            lo += k * step;
+            hi = min(lo + step, hi);
         }
-        s_cta_in_pic = gcta - __ldg(&jobs[lo].rec_cta_begin);
-        load_view(vw, jobs[lo]);
+        if (l == 0)
+        {
+            s_cta_in_pic = gcta - __ldg(&jobs[lo].rec_cta_begin);
+            load_view(vw, jobs[lo]);
+        }
     }
     build_div_tables<kRecWarps * 32>();
     __syncthreads();
     const ReconView &v = vw;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t chunk0 = s_cta_in_pic * HVQM4_REC_CHUNKS_PER_CTA;
     const uint32_t chunk_end = min(chunk0 + HVQM4_REC_CHUNKS_PER_CTA, v.n_chunks);
+    /* A warp has up to four chunks (chunk0 + warp + k * kRecWarps).  On the content this kernel runs on -- few
+       records per picture -- a chunk holds only a few records (9 of 32 lanes were active) and every record is
+       reached through a chain of dependent loads (chunk descriptor -> header word -> vector word or DC ->
+       reference window rows) with an idle memory system around it.  So the warp's chunks are FLATTENED: lane i
+       fetches the descriptor of the i-th chunk, the record counts are prefix-summed, and the records of all its
+       chunks are dealt to the lanes 32 at a time (descriptor by shuffle from the owning lane): typically one walk
+       of the chain per warp instead of four, classes diverging inside the pass.  Full chunks (dense content) still
+       come out as one chunk per pass.  Descriptors and the first headers are requested before the nest table is
+       built, the next pass's headers before the current pass is computed. */
+    constexpr uint32_t kPerWarp = (HVQM4_REC_CHUNKS_PER_CTA + kRecWarps - 1) / kRecWarps;
+    static_assert(kPerWarp == 4, "the prefix below is written for four chunks per warp");
+    const uint32_t first = chunk0 + (uint32_t)warp;
+    const uint32_t n = first < chunk_end ? (chunk_end - first + kRecWarps - 1) / kRecWarps : 0u;
+    const uint2 my_cd = (uint32_t)lane < n ? __ldg(reinterpret_cast<const uint2 *>(v.chunks) + first + (uint32_t)lane * kRecWarps) : make_uint2(0u, 0u);
+    const uint32_t my_count = my_cd.y & 0xFF;           /* 0 beyond the warp's chunks */
+    const uint32_t s1 = __shfl_sync(0xFFFFFFFFu, my_count, 0), s2 = s1 + __shfl_sync(0xFFFFFFFFu, my_count, 1);
+    const uint32_t s3 = s2 + __shfl_sync(0xFFFFFFFFu, my_count, 2), total = s3 + __shfl_sync(0xFFFFFFFFu, my_count, 3);
+    /* record g of the warp -> (descriptor, index inside its chunk, header word) */
+    auto fetch = [&](uint32_t g, uint2 &cd, uint32_t &r, uint32_t &hdr) {
+        const uint32_t i = (g >= s1) + (g >= s2) + (g >= s3);
+        r = g - (i == 0 ? 0u : i == 1 ? s1 : i == 2 ? s2 : s3);
+        cd = make_uint2(__shfl_sync(0xFFFFFFFFu, my_cd.x, (int)i), __shfl_sync(0xFFFFFFFFu, my_cd.y, (int)i));
+        hdr = g < total ? __ldg(v.rec + cd.x + r * (((cd.y >> 8) & 0xFF) + 1)) : 0u;
+    };
+    uint2 cd;
+    uint32_t r, hdr;
+    fetch((uint32_t)lane, cd, r, hdr);
     if (chunk0 < v.n_chunks_nest)
     {
         build_nest_table<kRecWarps * 32>(v, rc_smem + RC_SMEM_TABLE_BYTES);
         __syncthreads();
     }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll 1
-    for (uint32_t c = chunk0 + warp; c < chunk_end; c += kRecWarps) record_chunk(v, c, lane);
+    for (uint32_t base = 0; base < total; base += 32)
+    {
+        const bool active = base + (uint32_t)lane < total;
+        const uint32_t extra = active ? rc_record_extra(v, (int)((cd.y >> 16) & 0xFF), hdr) : 0u;
+        uint2 cd_n = make_uint2(0u, 0u);
+        uint32_t r_n = 0, hdr_n = 0;
+        if (base + 32 < total) fetch(base + 32 + (uint32_t)lane, cd_n, r_n, hdr_n);     /* warp-uniform condition */
+        if (active) record_chunk_pre(v, cd, (int)r, hdr, extra);
+        cd = cd_n;
+        r = r_n;
+        hdr = hdr_n;
+    }
 }
 
 /* ------------------------------------------------------------------------------------------

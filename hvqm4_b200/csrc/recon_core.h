@@ -604,6 +604,39 @@ RC_HD void rc_record_coords(uint32_t hdr, uint32_t &t, int &plane, int &bx, int 
     by = (int)(hdr >> 21);
 }
 
+/* what a record needs from outside its own words: the macroblock's vector word (predicted AOT) or the block's
+   DC (intra AOT); 0 for raw records.  Separate from rc_record_block_pre so that a caller can fetch it early. */
+RC_HD uint32_t rc_record_extra(const ReconView &v, int cls, uint32_t hdr)
+{
+    uint32_t t;
+    int plane, bx, by;
+    rc_record_coords(hdr, t, plane, bx, by);
+    if (cls == SYM_REC_INTRA)
+    {
+        const int bstride = ((v.width >> (plane ? 1 : 0)) >> 2) + 2;
+        return RC_LD8(v.blob + rc_pick3(v.off_dc, plane) + (by + 1) * bstride + bx + 1);
+    }
+    return cls == SYM_REC_INTER ? rc_mv_word(v, plane, bx, by) : 0u;
+}
+
+/* hdr = rec[0], extra = rc_record_extra(v, cls, hdr) */
+RC_HD void rc_record_block_pre(const ReconView &v, int cls, uint32_t len, const uint32_t *rec, uint32_t hdr, uint32_t extra, uint32_t rows[4])
+{
+    if (cls == SYM_REC_RAW)
+    {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) rows[r] = RC_LD32(rec + 1 + r);
+    }
+    else if (cls == SYM_REC_INTRA)
+        rc_intra_aot(v, rows, rec + 1, (int)len - 1, (int)extra);
+    else
+    {
+        const uint8_t *window = rc_motion_window(v, hdr & 0xFF, extra);
+        if (!window) return;                          /* the map work painted it grey */
+        rc_predicted_aot(v, rows, rec + 1, (int)len - 1, window);
+    }
+}
+
 RC_HD void rc_record_block(const ReconView &v, int cls, uint32_t len, const uint32_t *rec, uint32_t rows[4])
 {
     uint32_t t;
