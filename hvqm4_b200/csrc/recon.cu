@@ -321,27 +321,33 @@ recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs, uint32_t cta_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t chunk0 = s_cta_in_pic * HVQM4_REC_CHUNKS_PER_CTA;
     const uint32_t chunk_end = min(chunk0 + HVQM4_REC_CHUNKS_PER_CTA, v.n_chunks);
-    /* A warp has up to four chunks (chunk0 + warp + k * kRecWarps).  On the content this kernel runs on -- few
+    /* A warp has up to kPerWarp chunks (chunk0 + warp + k * kRecWarps).  On the content this kernel runs on -- few
        records per picture -- a chunk holds only a few records (9 of 32 lanes were active) and every record is
        reached through a chain of dependent loads (chunk descriptor -> header word -> vector word or DC ->
        reference window rows) with an idle memory system around it.  So the warp's chunks are FLATTENED: lane i
        fetches the descriptor of the i-th chunk, the record counts are prefix-summed, and the records of all its
        chunks are dealt to the lanes 32 at a time (descriptor by shuffle from the owning lane): typically one walk
-       of the chain per warp instead of four, classes diverging inside the pass.  Full chunks (dense content) still
+       of the chain per warp instead of one per chunk, classes diverging inside the pass.  Full chunks (dense content) still
        come out as one chunk per pass.  Descriptors and the first headers are requested before the nest table is
        built, the next pass's headers before the current pass is computed. */
     constexpr uint32_t kPerWarp = (HVQM4_REC_CHUNKS_PER_CTA + kRecWarps - 1) / kRecWarps;
-    static_assert(kPerWarp == 4, "the prefix below is written for four chunks per warp");
+    static_assert(kPerWarp >= 1 && kPerWarp <= 32, "one descriptor per lane");
     const uint32_t first = chunk0 + (uint32_t)warp;
     const uint32_t n = first < chunk_end ? (chunk_end - first + kRecWarps - 1) / kRecWarps : 0u;
     const uint2 my_cd = (uint32_t)lane < n ? __ldg(reinterpret_cast<const uint2 *>(v.chunks) + first + (uint32_t)lane * kRecWarps) : make_uint2(0u, 0u);
     const uint32_t my_count = my_cd.y & 0xFF;           /* 0 beyond the warp's chunks */
-    const uint32_t s1 = __shfl_sync(0xFFFFFFFFu, my_count, 0), s2 = s1 + __shfl_sync(0xFFFFFFFFu, my_count, 1);
-    const uint32_t s3 = s2 + __shfl_sync(0xFFFFFFFFu, my_count, 2), total = s3 + __shfl_sync(0xFFFFFFFFu, my_count, 3);
+    uint32_t start[kPerWarp + 1];                       /* first record of chunk k; start[kPerWarp] = all of them */
+    start[0] = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kPerWarp; ++k) start[k + 1] = start[k] + __shfl_sync(0xFFFFFFFFu, my_count, (int)k);
+    const uint32_t total = start[kPerWarp];
     /* record g of the warp -> (descriptor, index inside its chunk, header word) */
     auto fetch = [&](uint32_t g, uint2 &cd, uint32_t &r, uint32_t &hdr) {
-        const uint32_t i = (g >= s1) + (g >= s2) + (g >= s3);
-        r = g - (i == 0 ? 0u : i == 1 ? s1 : i == 2 ? s2 : s3);
+        uint32_t i = 0, s0 = 0;
+#pragma unroll
+        for (uint32_t k = 1; k < kPerWarp; ++k)
+            if (g >= start[k]) { i = k; s0 = start[k]; }
+        r = g - s0;
         cd = make_uint2(__shfl_sync(0xFFFFFFFFu, my_cd.x, (int)i), __shfl_sync(0xFFFFFFFFu, my_cd.y, (int)i));
         hdr = g < total ? __ldg(v.rec + cd.x + r * (((cd.y >> 8) & 0xFF) + 1)) : 0u;
     };

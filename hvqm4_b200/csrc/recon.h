@@ -5,7 +5,9 @@
 #include <cuda_runtime.h>
 
 /* chunks (of <= 32 records) one CTA of the record kernel works through */
+#ifndef HVQM4_REC_CHUNKS_PER_CTA
 #define HVQM4_REC_CHUNKS_PER_CTA 32
+#endif
 
 /* One picture to reconstruct.  All pointers are device pointers; surfaces are planar
    Y|U|V, contiguous, stride = plane width (the reference's frame layout, h4m:2343-2349). */
