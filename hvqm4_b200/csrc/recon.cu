@@ -37,6 +37,14 @@
 
 namespace {
 
+/* Map and record kernels are launched with programmatic stream serialization: a kernel may become resident
+   while the kernel in front of it in the stream drains, reads what does not depend on it (job, picture header,
+   segment heads / chunk descriptors, record headers, nest table -- symbol data uploaded earlier) and waits in
+   pdl_wait() before it touches a frame surface.  Every CTA passes pdl_wait(), also on its early exits, so that
+   a kernel's completion implies the completion of everything in front of it. */
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 /* ------------------------------------------------------------------------------------------
  * picture parameters: one ReconView per CTA in shared memory (constant-offset LDS, no live
  * registers across the block functions)
@@ -260,10 +268,16 @@ recon_map_kernel(const ReconJob *__restrict__ jobs, int units_per_pic, int ctas_
     const ReconView &v = vw;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int unit = cta * kUnitsPerWarp * kWarps + warp;
-    if (unit >= units_per_pic) return;
+    pdl_release();
+    if (unit >= units_per_pic)
+    {
+        pdl_wait();
+        return;
+    }
     const int nseg = v.nseg;
     int row = unit / nseg, seg = unit - row * nseg;       /* one division per warp; then stepped */
     SegHead head = segment_head(v, row, seg * SYM_SEG_MCBS, lane);
+    pdl_wait();                                           /* the surfaces belong to the kernels in front until here */
 #pragma unroll 1
     for (int it = 0; it < kUnitsPerWarp; ++it)
     {
@@ -316,6 +330,7 @@ recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs, uint32_t cta_
         }
     }
     build_div_tables<kRecWarps * 32>();
+    pdl_release();
     __syncthreads();
     const ReconView &v = vw;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -359,6 +374,7 @@ recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs, uint32_t cta_
         build_nest_table<kRecWarps * 32>(v, rc_smem + RC_SMEM_TABLE_BYTES);
         __syncthreads();
     }
+    pdl_wait();                                           /* the map kernel's predictions, and the surfaces at all */
 #pragma unroll 1
     for (uint32_t base = 0; base < total; base += 32)
     {
@@ -550,6 +566,22 @@ recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap)
     for (uint32_t c = inter0 + warp; c < inter1; c += kBandWarps) record_chunk(v, c, lane);
 }
 
+template <typename... KArgs, typename... Args>
+int launch_overlapped(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <int kWarps, int kUnitsPerWarp, int kMinBlocks>
 int launch_map(const ReconJob *d_jobs, int n_jobs, int units, cudaStream_t stream)
 {
@@ -557,15 +589,14 @@ int launch_map(const ReconJob *d_jobs, int n_jobs, int units, cudaStream_t strea
     const int ctas_per_pic = (units + per_cta - 1) / per_cta;
     const long long grid = (long long)ctas_per_pic * n_jobs;
     if (grid > 0x7FFFFFFFll) return (int)cudaErrorInvalidConfiguration;
-    recon_map_kernel<kWarps, kUnitsPerWarp, kMinBlocks><<<(unsigned)grid, kWarps * 32, RC_SMEM_TABLE_BYTES, stream>>>(d_jobs, units, ctas_per_pic);
-    return (int)cudaGetLastError();
+    return launch_overlapped(recon_map_kernel<kWarps, kUnitsPerWarp, kMinBlocks>, (unsigned)grid, kWarps * 32, RC_SMEM_TABLE_BYTES, stream, d_jobs, units,
+                             ctas_per_pic);
 }
 
 template <int kMinBlocks>
 int launch_record(const ReconJob *d_jobs, int n_jobs, uint32_t cta_base, uint32_t n_ctas, cudaStream_t stream)
 {
-    recon_record_kernel<kMinBlocks><<<n_ctas, kRecWarps * 32, kRecSmem, stream>>>(d_jobs, n_jobs, cta_base);
-    return (int)cudaGetLastError();
+    return launch_overlapped(recon_record_kernel<kMinBlocks>, n_ctas, kRecWarps * 32, kRecSmem, stream, d_jobs, n_jobs, cta_base);
 }
 
 int env_int(const char *name)
