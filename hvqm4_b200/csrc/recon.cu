@@ -224,17 +224,26 @@ __device__ __forceinline__ void build_div_tables()
     if (threadIdx.x < 16) s_div[threadIdx.x] = threadIdx.x ? 0x1000 / (threadIdx.x * 16) : 0;   /* divTable / 16 (recon_core.h) */
 }
 
-/* expands the packed nest of the CTA's picture into the shared-memory lookup table; the caller
-   provides 38 * 40 bytes of scratch and must __syncthreads() afterwards */
+/* The packed nest of the CTA's picture (35-byte pitch, 16-byte aligned in the blob) is staged in shared memory
+   by asynchronous copies -- no registers, nothing waits for it -- and expanded into the lookup tables later:
+   nest_stage_begin() ... (other work) ... nest_stage_wait(); __syncthreads(); nest_spread(); __syncthreads().
+   The caller provides 38 * 40 bytes of scratch. */
 template <int kThreads>
-__device__ __forceinline__ void build_nest_table(const ReconView &v, uint8_t *packed)
+__device__ __forceinline__ void nest_stage_begin(const ReconView &v, uint8_t *packed)
+{
+    const uint8_t *src = v.blob + v.off_nest;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(packed);
+    for (int i = threadIdx.x; i < (SYM_NEST_BYTES + 15) / 16; i += kThreads)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16 * i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void nest_stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int kThreads>
+__device__ __forceinline__ void nest_spread(uint8_t *packed)
 {
     uint32_t *s_nest_tab = reinterpret_cast<uint32_t *>(rc_smem + RC_SMEM_NEST_OFF);
-    /* stage the packed rows as they are (35-byte pitch, the blob keeps them 16-byte aligned): word copies */
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(v.blob + v.off_nest);
     uint32_t *stage = reinterpret_cast<uint32_t *>(packed);
-    for (int i = threadIdx.x; i < (SYM_NEST_BYTES + 3) / 4; i += kThreads) stage[i] = __ldg(src + i);
-    __syncthreads();
     /* nibbles x..x+7 of row y, spread into the step-1 and step-2 tables; (y, 2j) and (y, 2j+1) share bytes
        j..j+4 of the row.  Entries near the end of a row run into the next row: those nibbles lie beyond
        column 69, which no descriptor reaches (offset <= 63, largest pattern + 6). */
@@ -336,6 +345,7 @@ recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs, uint32_t cta_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t chunk0 = s_cta_in_pic * HVQM4_REC_CHUNKS_PER_CTA;
     const uint32_t chunk_end = min(chunk0 + HVQM4_REC_CHUNKS_PER_CTA, v.n_chunks);
+    if (chunk0 < v.n_chunks_nest) nest_stage_begin<kRecWarps * 32>(v, rc_smem + RC_SMEM_TABLE_BYTES);
     /* A warp has up to kPerWarp chunks (chunk0 + warp + k * kRecWarps).  On the content this kernel runs on -- few
        records per picture -- a chunk holds only a few records (9 of 32 lanes were active) and every record is
        reached through a chain of dependent loads (chunk descriptor -> header word -> vector word or DC ->
@@ -371,7 +381,9 @@ recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs, uint32_t cta_
     fetch((uint32_t)lane, cd, r, hdr);
     if (chunk0 < v.n_chunks_nest)
     {
-        build_nest_table<kRecWarps * 32>(v, rc_smem + RC_SMEM_TABLE_BYTES);
+        nest_stage_wait();
+        __syncthreads();
+        nest_spread<kRecWarps * 32>(rc_smem + RC_SMEM_TABLE_BYTES);
         __syncthreads();
     }
     pdl_wait();                                           /* the map kernel's predictions, and the surfaces at all */
@@ -545,6 +557,7 @@ recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap)
     const ReconView &v = vw;
     if (!v.blob) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (v.has_nest) nest_stage_begin<kBandWarps * 32>(v, rc_smem + RC_SMEM_TABLE_BYTES);   /* lands during the map phase */
 
     /* map phase */
     const int row0 = band * SYM_BAND_MCB_ROWS, row1 = min(row0 + SYM_BAND_MCB_ROWS, v.mcb_h);
@@ -556,7 +569,12 @@ recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap)
     const uint32_t raw0 = __ldg(v.bands + band), raw1 = __ldg(v.bands + band + 1);
     const uint32_t intra0 = __ldg(v.bands + nb1 + band), intra1 = __ldg(v.bands + nb1 + band + 1);
     const uint32_t inter0 = __ldg(v.bands + 2 * nb1 + band), inter1 = __ldg(v.bands + 2 * nb1 + band + 1);
-    if (intra1 > intra0) build_nest_table<kBandWarps * 32>(v, rc_smem + RC_SMEM_TABLE_BYTES);
+    if (intra1 > intra0)
+    {
+        nest_stage_wait();
+        __syncthreads();
+        nest_spread<kBandWarps * 32>(rc_smem + RC_SMEM_TABLE_BYTES);
+    }
     __syncthreads();     /* map stores of the band visible to the whole CTA; nest table complete */
 #pragma unroll 1
     for (uint32_t c = raw0 + warp; c < raw1; c += kBandWarps) record_chunk(v, c, lane);
