@@ -217,6 +217,9 @@ struct HVQM4Batch
     int parse_turn = 0, ipic_slot = 0, ipic_fence_left = 0;
     cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_d2h = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     std::vector<const uint8_t *> gather_src;        /* GPU entropy mode: device-visible source of every picture of the step */
+    /* HVQM4_BATCH_TRACE=1: where the submitting thread spends a GPU-entropy step (printed by HVQM4BatchDestroy) */
+    double t_trace[4] = {0, 0, 0, 0};               /* waiting for a staging arena, copying pictures, descriptors, enqueueing */
+    unsigned n_trace = 0, steps_seen = 0;
     bool d2h_pending = false;
     cudaEvent_t ev_d2h_mark[2] = {nullptr, nullptr};   /* read-backs issued before step n, n - 1 (batch_wait_readbacks) */
     unsigned step_no = 0;
@@ -471,6 +474,9 @@ H4_API void HVQM4BatchDestroy(HVQM4Batch *b)
     if (!b) return;
     cudaSetDevice(b->device);
     cudaDeviceSynchronize();
+    if (b->n_trace && getenv("HVQM4_BATCH_TRACE"))
+        fprintf(stderr, "hvqm4_b200: %u GPU-entropy steps, submitting thread per step: arena wait %.2f ms, picture copies %.2f ms, descriptors %.2f ms, enqueue %.2f ms\n",
+                b->n_trace, 1e3 * b->t_trace[0] / b->n_trace, 1e3 * b->t_trace[1] / b->n_trace, 1e3 * b->t_trace[2] / b->n_trace, 1e3 * b->t_trace[3] / b->n_trace);
     delete b->pool;
     for (auto &s : b->st) h4e_seq_destroy(s.seq);
     for (auto &r : b->recorded) cudaFree(r.d);
@@ -540,11 +546,13 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
         total += align_up((size_t)frame_bytes[i] + 16, 16) + (gather ? 16 : 0);
     }
     Arena &a = b->arena[b->cur];
+    const auto t_w0 = std::chrono::steady_clock::now();
     if (a.in_flight)
     {
         if (!cuda_ok(cudaEventSynchronize(a.consumed), "cudaEventSynchronize")) return HVQM4_ERR_CUDA;
         a.in_flight = false;
     }
+    const auto t_w1 = std::chrono::steady_clock::now();
     if (!arena_reserve(b, a, total)) return HVQM4_ERR_NOMEM;
     H4DevPicture *pics = reinterpret_cast<H4DevPicture *>(a.h);
     ReconJob *jobs = reinterpret_cast<ReconJob *>(a.h + pics_bytes);
@@ -555,6 +563,7 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
             memcpy(dst, frames[i], frame_bytes[i]);
             memset(dst + frame_bytes[i], 0, 16);
         });
+    const auto t_w2 = std::chrono::steady_clock::now();
     for (int i = 0; i < n; ++i)
     {
         if (gather)
@@ -584,6 +593,14 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
     }
     auto t_host1 = std::chrono::steady_clock::now();
     b->stats[4] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_host1 - t_host0).count();
+    const bool traced = ++b->steps_seen > 32;       /* the first steps size the arenas (allocations synchronise the device) */
+    if (traced)
+    {
+        b->t_trace[0] += std::chrono::duration<double>(t_w1 - t_w0).count();
+        b->t_trace[1] += std::chrono::duration<double>(t_w2 - t_w1).count();
+        b->t_trace[2] += std::chrono::duration<double>(t_host1 - t_w2).count() + std::chrono::duration<double>(t_w0 - t_host0).count();
+        ++b->n_trace;
+    }
 
     /* Upload and parser run on one of H4_PARSE_SLOTS streams, taken in turn, so that the parse
        kernels of consecutive steps are in flight together (a warp per picture is latency bound: a
@@ -651,6 +668,7 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
     b->cur = (b->cur + 1) % kArenas;
     b->stats[0] += n;
     b->stats[2] += total;
+    if (traced) b->t_trace[3] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host1).count();
     return HVQM4_OK;
 }
 
