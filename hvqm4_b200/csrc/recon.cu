@@ -18,13 +18,16 @@
  *                      prefix sums, no queues, few registers: occupancy hides the latency of
  *                      the scattered reference reads.
  * recon_record_kernel  blocks with side data, from the host-grouped record list: raw blocks
- *                      and AOT basis loops.  warp -> one chunk of <= 32 records of one
- *                      (class, band, length) group; lane -> one record.  All lanes of a warp
- *                      run the same class with the same number of bases, records are at
- *                      first + lane * length (no searching), and the per-picture nest is
- *                      expanded once per CTA into a shared-memory table in which a basis row
- *                      is a single 32-bit load.  Predicted-AOT blocks read back the
- *                      prediction the map kernel left in the picture (L2 resident).
+ *                      and AOT basis loops.  Chunks hold <= 32 records of one (class, band,
+ *                      length) group, records are at first + index * length (no searching);
+ *                      a warp takes up to four chunks and deals their records to its lanes
+ *                      32 at a time (full chunks: one chunk per pass, all lanes in one class
+ *                      with the same number of bases; the few-record chunks of sparse content:
+ *                      one pass for all of them).  The per-picture nest is expanded once per
+ *                      CTA into a shared-memory table in which a basis row is a single 32-bit
+ *                      load.  Predicted-AOT blocks read back the prediction the map kernel
+ *                      left in the picture (L2 resident).
+ * Both are launched with programmatic stream serialization (pdl_release / pdl_wait below).
  *
  * The block arithmetic itself lives in recon_core.h.
  */
