@@ -1914,9 +1914,12 @@ H4E_INL void read_mv(H4Seq *s, BR *b, int32_t *mv, int rbits)
     int32_t lim = 1 << (rbits + 5);
     int32_t v = ht_get(&s->tree[T_MV], b) * (1 << rbits);
     v += (int32_t)br_bits(b, rbits);
-    *mv += v;
-    if (*mv >= lim) *mv -= lim << 1;
-    else if (*mv < -lim) *mv += lim << 1;
+    /* Modulo 2^32 like the reference's int32 on its targets: with damaged residual-bit counts a step can exceed
+       the wrap range and the predictor then grows without bound (the vector is range-checked afterwards). */
+    uint32_t acc = (uint32_t)*mv + (uint32_t)v;
+    if ((int32_t)acc >= lim) acc -= (uint32_t)lim << 1;
+    else if ((int32_t)acc < -lim) acc += (uint32_t)lim << 1;
+    *mv = (int32_t)acc;
 }
 
 /*
