@@ -302,13 +302,14 @@ RC_HD void rc_intra_aot(const ReconView &v, uint32_t rows[4], const uint32_t *si
 {
     int32_t acc[16];
     const int32_t mean = rc_aot_sum(v, side, n, nullptr, acc);
-    const int32_t delta = (int32_t)((uint32_t)V << v.unk_shift) - mean;
+    /* modulo 2^32 like the reference's int32 on its targets (damaged scale symbols overflow it) */
+    const uint32_t delta = ((uint32_t)V << v.unk_shift) - (uint32_t)mean;
 #pragma unroll
     for (int r = 0; r < 4; ++r)
     {
         uint32_t out = 0;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) out |= rc_clamp255((acc[r * 4 + c] + delta) >> v.unk_shift) << (8 * c);
+        for (int c = 0; c < 4; ++c) out |= rc_clamp255((int32_t)((uint32_t)acc[r * 4 + c] + delta) >> v.unk_shift) << (8 * c);
         rows[r] = out;
     }
 }

@@ -11,6 +11,11 @@
  * heap block of EXACTLY the size h4e_parse_begin asked for, so that any read past the picture and
  * any write past the blob is an AddressSanitizer report (h4m:2080-2082 lets the reference read
  * three bytes past the record; this stage claims to need none).
+ * Every parsed picture is then RECONSTRUCTED by tests/emul/recon_emul.cpp -- the block functions and the
+ * addressing of the CUDA kernels (recon_core.h) run serially -- into frame surfaces that are heap blocks of
+ * exactly frame bytes + 64 (the tail slack the library gives its device surfaces): a vector, a window or a
+ * record of a damaged picture that reached outside a surface or the blob would be a report here, where
+ * compute-sanitizer cannot be run on the GPU pool.
  * split = 1 selects the pass structure of the GPU build (h4e_seq_set_split_schedule): the device
  * code is this same file, so this is also the closest a CPU sanitizer gets to the GPU parser.
  */
@@ -20,6 +25,9 @@
 #include <string.h>
 
 #include "entropy.h"
+
+/* tests/emul/recon_emul.cpp */
+int emul_recon_picture(const uint8_t *blob, uint8_t *present, const uint8_t *past, const uint8_t *future);
 
 static uint64_t rng_state;
 static uint32_t rnd(void)
@@ -52,15 +60,20 @@ int main(int argc, char **argv)
     while (n < 4096 && fscanf(l, "%ld %ld %d", &off[n], &len[n], &type[n]) == 3) ++n;
     fclose(l);
 
-    unsigned long parsed = 0, flagged = 0, refused = 0;
+    unsigned long parsed = 0, flagged = 0, refused = 0, painted = 0;
     uint32_t all_bits = 0;
+    const size_t surf_bytes = (size_t)width * height * 3 / 2 + 64;
     for (int round = 0; round < rounds; ++round)
     {
         H4Seq *s = h4e_seq_create(width, height, 2, 2, v15);
         if (!s) return 3;
         h4e_seq_set_split_schedule(s, split);
+        uint8_t *surf[3];
+        for (int k = 0; k < 3; ++k) surf[k] = calloc(1, surf_bytes);
+        int past = 0, present = 1, future = 2;                            /* rotation of decode_video, h4m:2087-2093, 2131-2137 */
         for (int i = 0; i < n; ++i)
         {
+            if (type[i] != 0x30) { const int t = past; past = future; future = t; }
             if (off[i] < 0 || len[i] <= 0 || off[i] + len[i] > flen) return 2;
             size_t bytes = (size_t)len[i];
             const int mode = round == 0 ? 0 : 1 + (int)(rnd() % 3);
@@ -79,15 +92,20 @@ int main(int argc, char **argv)
                 all_bits |= bits;
                 flagged += bits != 0;
                 ++parsed;
+                const int rc = emul_recon_picture(blob, surf[present], surf[past], type[i] == 0x20 ? surf[present] : surf[future]);
+                if (rc != 0 && bits == 0) return 4;                       /* an intact picture must reconstruct */
+                painted += rc == 0;
                 free(blob);
             }
             else
                 ++refused;
             free(pic);
+            if (type[i] != 0x30) { const int t = present; present = future; future = t; }
         }
+        for (int k = 0; k < 3; ++k) free(surf[k]);
         h4e_seq_destroy(s);
     }
     free(file);
-    printf("%lu parsed %lu flagged %lu refused bits 0x%x\n", parsed, flagged, refused, all_bits);
+    printf("%lu parsed %lu flagged %lu refused %lu reconstructed bits 0x%x\n", parsed, flagged, refused, painted, all_bits);
     return 0;
 }

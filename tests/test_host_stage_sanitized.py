@@ -6,8 +6,11 @@ behaviour; this stage claims the opposite: no read past the p
 undefined arithmetic, error bits instead.  tests/san/entropy_san.c hands every picture over in a heap block
 of exactly its size and the blob in a heap block of exactly `h4e_parse_begin`'s answer, intact and damaged
 (byte flips, corrupted header / section table, truncation), in the host pass structure and in the pass
-structure of the GPU build (the device parser is the same source file; compute-sanitizer is not available
-on the GPU pool, so this is the sanitizer coverage the GPU parser gets)."""
+structure of the GPU build (the device parser is the same source file).  Every parsed picture is then
+reconstructed by tests/emul -- the block functions and addressing of the CUDA kernels (recon_core.h) --
+into surfaces of exactly frame bytes + 64: a vector, window or record of a damaged picture that left a
+surface or the blob would be a report.  compute-sanitizer is not available on the GPU pool, so this is
+the sanitizer coverage the GPU parser and the kernels' arithmetic get."""
 import os
 import shutil
 import subprocess
@@ -24,14 +27,23 @@ CSRC = os.path.join(ROOT, "hvqm4_b200", "csrc")
 
 @pytest.fixture(scope="module")
 def harness():
-    if not shutil.which("gcc"):
-        pytest.skip("gcc not available")
-    cmd = ["gcc", "-std=gnu11", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-fno-omit-frame-pointer",
-           "-I", CSRC, "-I", os.path.join(ROOT, "include"), SRC, os.path.join(CSRC, "entropy.c"), "-o", EXE]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0 and ("asan" in r.stderr or "ubsan" in r.stderr or "sanitize" in r.stderr):
-        pytest.skip("sanitizer runtimes not installed: " + r.stderr.strip()[-200:])
-    assert r.returncode == 0, r.stderr[-2000:]
+    if not shutil.which("gcc") or not shutil.which("g++"):
+        pytest.skip("gcc / g++ not available")
+    san = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-fno-omit-frame-pointer"]
+    inc = ["-I", CSRC, "-I", os.path.join(ROOT, "include")]
+    obj = lambda name: os.path.join(ROOT, "tests", "san", name + ".san.o")
+    steps = [
+        ["gcc", "-std=gnu11"] + san + inc + ["-c", os.path.join(CSRC, "entropy.c"), "-o", obj("entropy")],
+        ["gcc", "-std=gnu11"] + san + inc + ["-c", SRC, "-o", obj("harness")],
+        # the kernels' block functions and addressing (recon_core.h) as the serial emulation runs them
+        ["g++", "-std=c++17", "-Wno-unknown-pragmas"] + san + ["-c", os.path.join(ROOT, "tests", "emul", "recon_emul.cpp"), "-o", obj("recon")],
+        ["g++"] + san + [obj("entropy"), obj("harness"), obj("recon"), "-o", EXE],
+    ]
+    for cmd in steps:
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0 and ("asan" in r.stderr or "ubsan" in r.stderr or "sanitize" in r.stderr):
+            pytest.skip("sanitizer runtimes not installed: " + r.stderr.strip()[-200:])
+        assert r.returncode == 0, r.stderr[-2000:]
     return EXE
 
 
@@ -60,7 +72,9 @@ def test_serial_stage_is_clean_under_asan_and_ubsan(harness, tmp_path, case, spl
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr, r.stderr[-3000:]
-    parsed, _, flagged, _, refused = r.stdout.split()[:5]
+    words = r.stdout.split()
+    parsed, flagged, refused, reconstructed = int(words[0]), int(words[2]), int(words[4]), int(words[6])
     # round 0 is the intact stream: no error bits there, so at most (rounds - 1) x pictures can be flagged
-    assert int(parsed) + int(refused) == rounds * len(frames)
-    assert int(flagged) <= (rounds - 1) * len(frames)
+    assert parsed + refused == rounds * len(frames)
+    assert flagged <= (rounds - 1) * len(frames)
+    assert reconstructed == parsed
