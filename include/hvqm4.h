@@ -208,8 +208,9 @@ void HVQM4BatchStats(HVQM4Batch *b, uint64_t out[8]);
 long long HVQM4KernelLaunches(void);
 
 /* Reconstruction schedule: 0 = chosen by batch size (default); > 0 = always the fused per-band
-   kernel (one launch per step); < 0 = always the map kernel + record kernel pair.  Both give
-   identical pictures; the switch exists for tests and measurements.  Process-wide. */
+   kernel (one launch per step; 2, 3 or 4 also pins its CTAs per SM, 1 leaves that to the grid
+   size); < 0 = always the map kernel + record kernel pair.  All give identical pictures; the
+   switch exists for tests and measurements.  Process-wide. */
 void HVQM4SetReconMode(int mode);
 
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA toolchain. */

@@ -68,6 +68,23 @@ def test_batch_runtime_matches_golden_cfg5(native_lib, golden, recon_mode):
     assert step == 16
 
 
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_band_kernel_register_budgets_match_golden(native_lib, golden, mode):
+    """The fused band kernel exists with 2, 3 and 4 CTAs per SM (92 / 80 / 64 registers; HVQM4SetReconMode 2..4,
+    1 = by grid size, which large batches resolve to 3): same pictures from every instantiation."""
+    names = ["cfg5_stream0", "cfg5_stream1", "cfg5_stream511", "cfg5_stream1023"]
+    files = [synth.generate(**golden[n]["args"]) for n in names]
+    native_lib.set_recon_mode(mode)
+    try:
+        before = native_lib.lib().HVQM4KernelLaunches()
+        for step, frames in enumerate(native_lib.decode_streams(files, host_threads=4)):
+            for n, (_, _, yuv) in zip(names, frames):
+                assert md5(yuv) == golden[n]["md5"][step], (n, step, mode)
+        assert native_lib.lib().HVQM4KernelLaunches() - before == 16        # one band kernel per step
+    finally:
+        native_lib.set_recon_mode(0)
+
+
 def test_batch_runtime_many_streams_vs_oracle(native_lib, oracle, recon_mode):
     """48 streams with distinct seeds in one batch (partial warps, several CTAs per SM)."""
     n = 48
