@@ -714,12 +714,14 @@ extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w,
     const bool record_heavy = h_rec_prefix[n_jobs] >= 8u * (uint32_t)n_jobs;
     if (band_mode > 0 || (band_mode == 0 && record_heavy && (long long)n_jobs * n_bands >= 128))
     {
-        /* CTAs per SM (the kernel's register budget): 2, 3 or 4 pins one; otherwise by grid size.  Four 64-register
-           CTAs per SM hold 592 bands at once and win while that is most of the grid (512 bands: 892 k vs 750 k
-           frames/s); from a few waves on, three 80-register CTAs are faster (2 048 bands: 1.08 M vs 1.03 M, 8 192:
-           1.21 M vs 1.17 M; two 92-register CTAs the same) -- no spills, a larger L1, and on a memory system that
-           is saturated with sector requests fewer warps in the queue. */
-        const int per_sm = band_mode >= 2 && band_mode <= 4 ? band_mode : (long long)n_jobs * n_bands >= 2 * 592 ? 3 : 4;
+        /* CTAs per SM (the kernel's register budget): 2, 3 or 4 pins one; otherwise by grid size.  Three 80-register
+           CTAs per SM (no spills, a larger L1, fewer pictures in flight: -19 % DRAM bytes) finish a wave of 3 x 148
+           bands in 0.72 of the time four 64-register CTAs need for 4 x 148 (8 192 bands: 1.21 M vs 1.17 M frames/s;
+           two 92-register CTAs the same), so the choice is a matter of whole waves: 512 bands 750 k vs 892 k,
+           768 bands 926 k vs 783 k, 1 024 bands 919 k vs 935 k, 1 536 bands 1.01 M vs 0.98 M. */
+        const long long grid = (long long)n_jobs * n_bands;
+        const long long waves4 = (grid + 4 * 148 - 1) / (4 * 148), waves3 = (grid + 3 * 148 - 1) / (3 * 148);
+        const int per_sm = band_mode >= 2 && band_mode <= 4 ? band_mode : 1000 * waves4 <= 724 * waves3 ? 4 : 3;
         int rc;
         switch (per_sm)
         {
