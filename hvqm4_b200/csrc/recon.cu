@@ -247,21 +247,19 @@ __device__ __forceinline__ void nest_spread(uint8_t *packed)
 {
     uint32_t *s_nest_tab = reinterpret_cast<uint32_t *>(rc_smem + RC_SMEM_NEST_OFF);
     uint32_t *stage = reinterpret_cast<uint32_t *>(packed);
-    /* nibbles x..x+7 of row y, spread into the step-1 and step-2 tables; (y, 2j) and (y, 2j+1) share bytes
-       j..j+4 of the row.  Entries near the end of a row run into the next row: those nibbles lie beyond
-       column 69, which no descriptor reaches (offset <= 63, largest pattern + 6). */
+    /* nibbles x..x+7 of row y, spread into table entries x = 2j and 2j+1 (samples x..x+3, one per byte, times 16);
+       both share bytes j..j+4 of the row.  Entries near the end of a row run into the next row: those nibbles lie
+       beyond column 69, which no descriptor reaches (offset <= 63, largest pattern + 6). */
     const uint32_t *pw = stage;
-    for (int i = threadIdx.x; i < SYM_NEST_H * 32; i += kThreads)
+    for (int i = threadIdx.x; i < SYM_NEST_H * (RC_NEST_PITCH / 2); i += kThreads)
     {
-        const int y = i >> 5, j = i & 31;
+        const int y = i / (RC_NEST_PITCH / 2), j = i - y * (RC_NEST_PITCH / 2);
         const int b = y * SYM_NEST_ROW_BYTES + j, w = b >> 2, sh = (b & 3) * 8;
         const uint32_t w0 = pw[w], w1 = pw[w + 1], w2 = sh ? pw[w + 2] : 0u;
         const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
         const uint32_t odd = (lo >> 4) | (hi << 28);
-        s_nest_tab[y * 64 + 2 * j] = rc_nest_spread_step1(lo);
-        s_nest_tab[y * 64 + 2 * j + 1] = rc_nest_spread_step1(odd);
-        s_nest_tab[RC_NEST_STEP2_OFF + y * 64 + 2 * j] = rc_nest_spread_step2(lo);
-        s_nest_tab[RC_NEST_STEP2_OFF + y * 64 + 2 * j + 1] = rc_nest_spread_step2(odd);
+        s_nest_tab[y * RC_NEST_PITCH + 2 * j] = rc_nest_spread_step1(lo);
+        s_nest_tab[y * RC_NEST_PITCH + 2 * j + 1] = rc_nest_spread_step1(odd);
     }
 }
 
@@ -311,7 +309,7 @@ recon_map_kernel(const ReconJob *__restrict__ jobs, int units_per_pic, int ctas_
  * a scratch area used only while the nest table is being built
  * ------------------------------------------------------------------------------------------ */
 constexpr int kRecWarps = 8;
-constexpr int kRecSmem = RC_SMEM_TABLE_BYTES + SYM_NEST_H * 40 + 16;
+constexpr int kRecSmem = RC_SMEM_TABLE_BYTES + SYM_NEST_H * 40 + 32;
 
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kRecWarps * 32, kMinBlocks)

@@ -30,14 +30,22 @@
 
 #if defined(__CUDACC__)
 #define RC_HD __host__ __device__ __forceinline__
+#define RC_HDM __host__ __device__ __forceinline__   /* member functions */
 #else
 #define RC_HD static inline
+#define RC_HDM inline
 #endif
 
 #if defined(__CUDA_ARCH__)
+#if defined(RC_PLAIN_LOADS)   /* sweep.cu: symbol data and reference rows are staged in shared memory */
+#define RC_LD8(p) (*(const uint8_t *)(p))
+#define RC_LD32(p) (*(const uint32_t *)(p))
+#define RC_LD64(p) (*(const unsigned long long *)(p))
+#else
 #define RC_LD8(p) __ldg((const uint8_t *)(p))
 #define RC_LD32(p) __ldg((const uint32_t *)(p))
 #define RC_LD64(p) __ldg((const unsigned long long *)(p))
+#endif
 #define RC_PRMT(a, b, s) __byte_perm((a), (b), (s))
 #define RC_ADDMIN_U16X2(a, b, c) __viaddmin_u16x2((a), (b), (c))   /* VIADDMNMX.U16x2: per half min((a + b) mod 2^16, c) */
 #define RC_DP4A(a, b, c) __dp4a((uint32_t)(a), (uint32_t)(b), (uint32_t)(c))   /* IDP.4A.U8.U8: c + sum of byte products */
@@ -68,8 +76,8 @@ static inline uint32_t rc_dp4a_host(uint32_t a, uint32_t b, uint32_t c)
 #define RC_DP4A(a, b, c) rc_dp4a_host((a), (b), (c))
 #endif
 
-#define RC_NEST_TABLE_WORDS (2 * SYM_NEST_H * 64)   /* step-1 entries, then step-2 entries */
-#define RC_NEST_STEP2_OFF (SYM_NEST_H * 64)
+#define RC_NEST_PITCH 68                              /* entries per nest row: start columns 0..67 */
+#define RC_NEST_TABLE_WORDS (SYM_NEST_H * RC_NEST_PITCH)
 
 /* The three lookup tables live at fixed offsets at the start of dynamic shared memory on the
    GPU (no pointer registers); on the CPU they are reached through the view. */
@@ -131,19 +139,20 @@ RC_HD void rc_make_view(ReconView &v, const uint8_t *blob, const SymHeader &h, c
     v.off_nest = h.off_nest; v.n_chunks = h.n_chunks; v.n_chunks_nest = h.n_chunks_nest;
 }
 
-/* Nest lookup tables.  rc_nest_table_entry: the nibbles x..x+7 of packed nest row y (zero past
-   column 69) as one word; the two tables the kernels read are derived from it: entry (y, x) of
-   the step-1 table = samples x, x+1, x+2, x+3 and of the step-2 table = samples x, x+2, x+4, x+6,
-   one per byte and ALREADY MULTIPLIED BY 16 (the sample sits in the high nibble, exactly like a
-   reference pixel masked with 0xF0), so that a basis row is one load and intra and inter bases
-   share the arithmetic below. */
+/* Nest lookup table.  rc_nest_table_entry: the nibbles x..x+7 of packed nest row y (zero past
+   column 69) as one word; the table the kernels read is derived from it: entry (y, x), x = 0..67,
+   = samples x, x+1, x+2, x+3, one per byte and ALREADY MULTIPLIED BY 16 (the sample sits in the
+   high nibble, exactly like a reference pixel masked with 0xF0), so that intra and inter bases
+   share the arithmetic below.  A step-1 basis row is one load; a step-2 row (samples x, x+2, x+4,
+   x+6) is bytes 0 and 2 of entries x and x + 4.  (Until round 2 there was a second, pre-permuted
+   step-2 table: 19 KB instead of 10 KB of shared memory per CTA, which the sweep kernel needs for
+   its reference windows.) */
 RC_HD uint32_t rc_nest_spread_step1(uint32_t nibbles8)
 {
     uint32_t x = nibbles8 & 0xFFFFu;                   /* nibbles 0,1,2,3 -> one per byte */
     x = (x | x << 8) & 0x00FF00FFu;
     return ((x | x << 4) & 0x0F0F0F0Fu) << 4;
 }
-RC_HD uint32_t rc_nest_spread_step2(uint32_t nibbles8) { return (nibbles8 & 0x0F0F0F0Fu) << 4; }   /* nibbles 0,2,4,6 */
 
 RC_HD uint32_t rc_nest_table_entry(const uint8_t *packed, int y, int x)
 {
@@ -210,6 +219,30 @@ RC_HD void rc_weighted(uint32_t rows[4], int V, int T, int B, int L, int R)
  * ALU pipe, IMAD and IDP.4A at half rate on the FMA pipe, and the two pipes run side by side.  The
  * byte extracts are therefore split: IDP.4A with a one-hot weight (FMA pipe) and PRMT (ALU pipe). */
 
+/* Where reference pixels are read from.  The block functions see a patch as ROWS of aligned 32-bit words:
+ * rows.ld(r, k) = aligned word k of row r (r, k compile-time after unrolling).  RcLinearRows / RcLinearWindow
+ * address a frame surface in global memory (map, record and band kernels, and the CPU emulation);
+ * sweep_core.h adds the same two for the shared-memory ring of the sweep kernel. */
+struct RcLinearRows
+{
+    const uint8_t *base;   /* first byte of row 0, aligned down to 4 */
+    int pitch;             /* bytes between the patch's rows */
+    RC_HDM uint32_t ld(int r, int k) const { return RC_LD32(base + r * pitch + 4 * k); }
+};
+/* the 70x38 luma window of a macroblock's reference position (h4m:1864-1868) */
+struct RcLinearWindow
+{
+    const uint8_t *origin;
+    int width;
+    /* rows oy, oy + ys, ... starting at column ox; a = misalignment of the first byte */
+    RC_HDM RcLinearRows rows(int ox, int oy, int ys, uint32_t &a) const
+    {
+        const uint8_t *p = origin + oy * width + ox;
+        a = (uint32_t)((uintptr_t)p & 3);
+        return RcLinearRows{p - a, ys * width};
+    }
+};
+
 /* bytes a .. a+7 of the aligned words w0, w1, w2 (a = 0..3), then samples at step 1 or 2, masked to the high nibbles */
 RC_HD uint32_t rc_row_window(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t sel_align, uint32_t sel_step)
 {
@@ -243,8 +276,9 @@ RC_HD void rc_accumulate(const ReconView &v, uint32_t word, const uint32_t R[4],
     for (int i = 0; i < 16; ++i) acc[i] = (int32_t)((uint32_t)acc[i] + factor * b[i]);   /* mod 2^32 */
 }
 
-/* window == nullptr: intra (nest tables); else inter (reference luma window, stride = luma width) */
-RC_HD void rc_add_basis(const ReconView &v, uint32_t word, const uint8_t *window, int32_t &scale_sum, int32_t acc[16])
+/* window == nullptr: intra (nest table); else inter (reference luma window) */
+template <class Win>
+RC_HD void rc_add_basis(const ReconView &v, uint32_t word, const Win *window, int32_t &scale_sum, int32_t acc[16])
 {
     const int ox = word & 0x3F, oy = (word >> 6) & 0x1F;
     const uint32_t xs2 = (word >> 11) & 1;
@@ -252,33 +286,35 @@ RC_HD void rc_add_basis(const ReconView &v, uint32_t word, const uint8_t *window
     uint32_t R[4];
     if (window)
     {
-        /* sample = (pixel >> 4) & 0xF (h4m:756-761): rows are fetched as three aligned words */
-        const uint8_t *p = window + oy * v.width + ox;
-        const uint32_t a = (uint32_t)((uintptr_t)p & 3);
-        const uint8_t *base = p - a;
+        /* sample = (pixel >> 4) & 0xF (h4m:756-761): rows are fetched as up to three aligned words */
+        uint32_t a;
+        const auto rows = window->rows(ox, oy, ys, a);
         const uint32_t sel_align = 0x3210u + 0x1111u * a, sel_step = xs2 ? 0x6420u : 0x3210u;
-        const int pitch = ys * v.width;
         const bool need1 = xs2 || a >= 1, need2 = xs2 && a >= 2;
 #pragma unroll
         for (int y = 0; y < 4; ++y)
         {
-            const uint8_t *q = base + y * pitch;
             /* the samples end at byte a + 3 (step 1) or a + 6 (step 2): only the words they reach are fetched */
-            const uint32_t w0 = RC_LD32(q), w1 = need1 ? RC_LD32(q + 4) : 0u, w2 = need2 ? RC_LD32(q + 8) : 0u;
+            const uint32_t w0 = rows.ld(y, 0), w1 = need1 ? rows.ld(y, 1) : 0u, w2 = need2 ? rows.ld(y, 2) : 0u;
             R[y] = rc_row_window(w0, w1, w2, sel_align, sel_step);
         }
         rc_accumulate<4>(v, word, R, scale_sum, acc);
     }
     else
     {
-        const uint32_t *tab = RC_NEST_TAB(v) + (xs2 ? RC_NEST_STEP2_OFF : 0) + oy * 64 + ox;
+        const uint32_t *tab = RC_NEST_TAB(v) + oy * RC_NEST_PITCH + ox;
 #pragma unroll
-        for (int y = 0; y < 4; ++y) R[y] = tab[y * ys * 64];
+        for (int y = 0; y < 4; ++y)
+        {
+            const uint32_t e0 = tab[y * ys * RC_NEST_PITCH];
+            R[y] = xs2 ? RC_PRMT(e0, tab[y * ys * RC_NEST_PITCH + 4], 0x6420) : e0;
+        }
         rc_accumulate<2>(v, word, R, scale_sum, acc);
     }
 }
 
-RC_HD int32_t rc_aot_sum(const ReconView &v, const uint32_t *side, int n, const uint8_t *window, int32_t acc[16])
+template <class Win>
+RC_HD int32_t rc_aot_sum(const ReconView &v, const uint32_t *side, int n, const Win *window, int32_t acc[16])
 {
     int32_t scale_sum = 0;
 #pragma unroll
@@ -301,7 +337,7 @@ RC_HD int32_t rc_aot_sum(const ReconView &v, const uint32_t *side, int n, const 
 RC_HD void rc_intra_aot(const ReconView &v, uint32_t rows[4], const uint32_t *side, int n, int V)
 {
     int32_t acc[16];
-    const int32_t mean = rc_aot_sum(v, side, n, nullptr, acc);
+    const int32_t mean = rc_aot_sum<RcLinearWindow>(v, side, n, nullptr, acc);
     /* modulo 2^32 like the reference's int32 on its targets (damaged scale symbols overflow it) */
     const uint32_t delta = ((uint32_t)V << v.unk_shift) - (uint32_t)mean;
 #pragma unroll
@@ -323,26 +359,33 @@ RC_HD void rc_intra_aot(const ReconView &v, uint32_t rows[4], const uint32_t *si
  *                                   a phase bit is 0 ((4a+2)>>2 = a, (2a+2b+2)>>2 = (a+b+1)>>1). */
 RC_HD uint32_t rc_avg4(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) & 0xFEFEFEFEu) >> 1); }
 
-/* rows W[2r], W[2r+1] = the two aligned words that cover the 5 bytes of reference row r */
+/* rows W[2r], W[2r+1] = the two aligned words that cover the 5 bytes of reference row r; a = misalignment of
+   the patch's first byte */
 /* kSkipSecond: an aligned row without a horizontal half step ends in its first word, the second is then not
    requested (dense content, band kernel: +0.4 %; the ALU-bound map kernel on sparse content loses 0.6 % to the
    predicate, so it keeps the unconditional pair) */
-template <bool kSkipSecond>
-RC_HD void rc_predict_load(uint32_t W[10], const uint8_t *src, int stride, int hx, int hy)
+template <bool kSkipSecond, class Rows>
+RC_HD void rc_predict_load_rows(uint32_t W[10], const Rows &rows, uint32_t a, int hx, int hy)
 {
-    const uint8_t *base = src - ((uintptr_t)src & 3);
-    const bool second = !kSkipSecond || ((uintptr_t)src & 3) != 0 || hx;
+    const bool second = !kSkipSecond || a != 0 || hx;
 #pragma unroll
     for (int r = 0; r < 5; ++r)
     {
         if (r < 4 || hy)
         {
-            W[2 * r] = RC_LD32(base + r * stride);
-            W[2 * r + 1] = second ? RC_LD32(base + r * stride + 4) : 0u;
+            W[2 * r] = rows.ld(r, 0);
+            W[2 * r + 1] = second ? rows.ld(r, 1) : 0u;
         }
         else
             W[2 * r] = W[2 * r + 1] = 0;
     }
+}
+
+template <bool kSkipSecond>
+RC_HD void rc_predict_load(uint32_t W[10], const uint8_t *src, int stride, int hx, int hy)
+{
+    const uint32_t a = (uint32_t)((uintptr_t)src & 3);
+    rc_predict_load_rows<kSkipSecond>(W, RcLinearRows{src - a, stride}, a, hx, hy);
 }
 
 /* a = src & 3.  Alignment is a byte permute (A = bytes a..a+3, B = bytes a+1..a+4 of a row).
@@ -411,7 +454,8 @@ RC_HD uint32_t rc_sum4(uint32_t packed, uint32_t acc)
 #endif
 }
 
-RC_HD void rc_predicted_aot(const ReconView &v, uint32_t rows[4], const uint32_t *side, int nibble, const uint8_t *window)
+template <class Win>
+RC_HD void rc_predicted_aot(const ReconView &v, uint32_t rows[4], const uint32_t *side, int nibble, const Win *window)
 {
     int32_t acc[16];
     const uint32_t aot_mean = (uint32_t)rc_aot_sum(v, side, nibble - 1, window, acc);
@@ -535,6 +579,21 @@ RC_HD void rc_mc_packed2(const ReconView &v, int plane0, uint32_t mp0, uint32_t 
     else rows1[0] = rows1[1] = rows1[2] = rows1[3] = 0x80808080u;
 }
 
+/* tmap / dmap point at the block's own cell of the bordered type and DC maps (row pitch bstride) */
+RC_HD void rc_weighted_at(const uint8_t *tmap, const uint8_t *dmap, int bstride, int is_ipic, uint32_t rows[4])
+{
+    const int V = RC_LD8(dmap);
+    /* neighbour DC only if (type & 0x77) == 0, else own DC; borders carry type 0xFF.
+       In I pictures the left neighbour is tracked as "type 0 or 8" (h4m:1441-1454). */
+    const uint32_t tT = RC_LD8(tmap - bstride), tB = RC_LD8(tmap + bstride), tL = RC_LD8(tmap - 1), tR = RC_LD8(tmap + 1);
+    const int T = (tT & 0x77) ? V : RC_LD8(dmap - bstride);
+    const int B = (tB & 0x77) ? V : RC_LD8(dmap + bstride);
+    const int R = (tR & 0x77) ? V : RC_LD8(dmap + 1);
+    const bool left_ok = is_ipic ? (tL == 0 || tL == 8) : !(tL & 0x77);
+    const int L = left_ok ? RC_LD8(dmap - 1) : V;
+    rc_weighted(rows, V, T, B, L, R);
+}
+
 RC_HD void rc_weighted_block(const ReconView &v, int plane, int bx, int by, uint32_t rows[4])
 {
     const int bstride = ((v.width >> (plane ? 1 : 0)) >> 2) + 2;
@@ -634,7 +693,8 @@ RC_HD void rc_record_block_pre(const ReconView &v, int cls, uint32_t len, const 
     {
         const uint8_t *window = rc_motion_window(v, hdr & 0xFF, extra);
         if (!window) return;                          /* the map work painted it grey */
-        rc_predicted_aot(v, rows, rec + 1, (int)len - 1, window);
+        const RcLinearWindow win = {window, v.width};
+        rc_predicted_aot(v, rows, rec + 1, (int)len - 1, &win);
     }
 }
 
@@ -658,7 +718,8 @@ RC_HD void rc_record_block(const ReconView &v, int cls, uint32_t len, const uint
     {
         const uint8_t *window = rc_motion_window(v, t, rc_mv_word(v, plane, bx, by));
         if (!window) return;                          /* the map work painted it grey */
-        rc_predicted_aot(v, rows, rec + 1, (int)len - 1, window);
+        const RcLinearWindow win = {window, v.width};
+        rc_predicted_aot(v, rows, rec + 1, (int)len - 1, &win);
     }
 }
 

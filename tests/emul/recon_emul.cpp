@@ -32,12 +32,8 @@ int emul_recon_picture(const uint8_t *blob, uint8_t *present, const uint8_t *pas
     static uint32_t nest_tab[RC_NEST_TABLE_WORDS];
     if (h.has_nest)
         for (int y = 0; y < SYM_NEST_H; ++y)
-            for (int x = 0; x < 64; ++x)
-            {
-                const uint32_t nibbles8 = rc_nest_table_entry(blob + h.off_nest, y, x);
-                nest_tab[y * 64 + x] = rc_nest_spread_step1(nibbles8);
-                nest_tab[RC_NEST_STEP2_OFF + y * 64 + x] = rc_nest_spread_step2(nibbles8);
-            }
+            for (int x = 0; x < RC_NEST_PITCH; ++x)
+                nest_tab[y * RC_NEST_PITCH + x] = rc_nest_spread_step1(rc_nest_table_entry(blob + h.off_nest, y, x));
     ReconView v;
     rc_make_view(v, blob, h, nest_tab, g_div, g_mcdiv, past, future);
     uint8_t *planes[3] = {present, present + h.width * h.height, present + h.width * h.height * 5 / 4};
