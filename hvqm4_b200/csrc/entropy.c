@@ -864,8 +864,8 @@ H4E_FN void open_bytes(H4Seq *s, ByteSec *b, const uint8_t *data, size_t len, ui
 /* ------------------------------------------------------------------ record groups */
 
 /* block rows per band, as shifts */
-#define SYM_BAND_SHIFT_CHROMA 3
-#define SYM_BAND_SHIFT_LUMA 4
+#define SYM_BAND_SHIFT_CHROMA 0
+#define SYM_BAND_SHIFT_LUMA 1
 H4E_STATIC_ASSERT((1 << SYM_BAND_SHIFT_CHROMA) == SYM_BAND_MCB_ROWS, "band shift must match SYM_BAND_MCB_ROWS");
 
 H4E_INL int len_bucket(uint32_t len) { return len < SYM_LEN_BUCKETS ? (int)len - 1 : SYM_LEN_BUCKETS - 1; }
@@ -876,7 +876,7 @@ H4E_INL int group_of(const H4Seq *s, int cls, int band, uint32_t len)
 
 /* Called wherever a block's final type byte is written (ipic_types, pb_pass1): counts the
    record the block will own in its (class, band, length) group.  band_shift: log2 of block rows
-   per band (luma 4, chroma 3 for SYM_BAND_MCB_ROWS = 8). */
+   per band (luma 1, chroma 0 for SYM_BAND_MCB_ROWS = 1). */
 H4E_INL void count_record(H4Seq *s, uint32_t t, int is_ipic, int by, int band_shift)
 {
     const uint32_t lut = rec_lut(is_ipic, t);
@@ -888,12 +888,39 @@ H4E_INL void count_record(H4Seq *s, uint32_t t, int is_ipic, int by, int band_sh
     if (len >= SYM_LEN_BUCKETS) H4E_FETCH_ADD(&s->grp_base[g], len);   /* long-bucket word total, see plan_records */
 }
 
+/* warp-collective on the GPU */
 H4E_FN void reset_record_counts(H4Seq *s)
 {
-    memset(s->grp_count, 0, (size_t)s->ngroups * sizeof(uint32_t));
-    memset(s->grp_next, 0, (size_t)s->ngroups * sizeof(uint32_t));
-    memset(s->grp_base, 0, (size_t)s->ngroups * sizeof(uint32_t));
-    s->n_records = 0;
+    for (int g = H4E_LANE; g < s->ngroups; g += H4E_LANES) s->grp_count[g] = s->grp_next[g] = s->grp_base[g] = 0;
+    if (H4E_LANE == 0) s->n_records = 0;
+}
+
+/* exclusive prefix sum of `v` over the lanes (total in *sum); the identity on a host thread */
+H4E_INL uint32_t lane_scan(uint32_t v, uint32_t *sum)
+{
+#if defined(H4E_DEVICE)
+    uint32_t inc = v;
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (H4E_LANE >= d) inc += o;
+    }
+    *sum = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    return inc - v;
+#else
+    *sum = v;
+    return 0;
+#endif
+}
+
+/* number of lanes whose predicate holds */
+H4E_INL uint32_t lane_count(int pred)
+{
+#if defined(H4E_DEVICE)
+    return (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, pred));
+#else
+    return pred ? 1u : 0u;
+#endif
 }
 
 /*
@@ -902,54 +929,87 @@ H4E_FN void reset_record_counts(H4Seq *s)
  * Records of the last bucket ("long", >= SYM_LEN_BUCKETS words: only I-picture luma types
  * > 16, which no encoder emits) have individual lengths; they are packed in emission order
  * and get one chunk each.
+ *
+ * The layout order is the group index itself ((class * nbands + band) * SYM_LEN_BUCKETS + bucket),
+ * so the plan is an exclusive prefix sum over the groups: every lane sums a contiguous slice,
+ * the slice totals are scanned across the lanes, and a second walk writes the plan (a host thread
+ * is one lane and one slice).  With one record band per macroblock row a 640x480 picture has
+ * 3 240 groups; a single lane walking them spent 0.7 ms per picture on the GPU.
  */
+typedef struct { uint32_t words, chunks, ord; } GroupSize;
+
+H4E_INL GroupSize group_size(const H4Seq *s, int g)
+{
+    GroupSize z;
+    const uint32_t n = s->grp_count[g];
+    const int lb = g % SYM_LEN_BUCKETS;
+    z.ord = n;
+    if (lb < SYM_LEN_BUCKETS - 1)
+    {
+        z.words = n * ((uint32_t)lb + 1);
+        z.chunks = (n + SYM_CHUNK - 1) / SYM_CHUNK;
+    }
+    else
+    {   /* one chunk per long record; count_record() totalled their words in grp_base */
+        z.words = s->grp_base[g];
+        z.chunks = n;
+    }
+    return z;
+}
+
+/* warp-collective on the GPU */
 H4E_FN void plan_records(H4Seq *s, int is_ipic)
 {
-    int need_nest = 0;
-    uint32_t word = 0, chunk = 0, ord = 0;
-    s->n_chunks_nest = 0;
-    for (int cls = 0; cls < SYM_REC_CLASSES; ++cls)
+    const int per = (s->ngroups + H4E_LANES - 1) / H4E_LANES;
+    const int g0 = H4E_LANE * per < s->ngroups ? H4E_LANE * per : s->ngroups;
+    const int g1 = g0 + per < s->ngroups ? g0 + per : s->ngroups;
+    const int per_class = s->nbands * SYM_LEN_BUCKETS;
+    uint32_t words = 0, chunks = 0, ords = 0;
+    int nest = 0;
+    for (int g = g0; g < g1; ++g)
     {
-        for (int band = 0; band < s->nbands; ++band)
-        {
-            s->band_first[cls * (s->nbands + 1) + band] = chunk;
-            for (int lb = 0; lb < SYM_LEN_BUCKETS; ++lb)
-            {
-                const int g = (cls * s->nbands + band) * SYM_LEN_BUCKETS + lb;
-                const uint32_t n = s->grp_count[g];
-                const uint32_t long_words = s->grp_base[g];
-                s->grp_base[g] = word;
-                s->grp_chunk[g] = chunk;
-                s->grp_ord[g] = ord;
-                ord += n;
-                if (!n) continue;
-                need_nest |= cls == SYM_REC_INTRA;
-                if (lb < SYM_LEN_BUCKETS - 1)
-                {
-                    const uint32_t len = (uint32_t)lb + 1;
-                    for (uint32_t i = 0; i < n; i += SYM_CHUNK)
-                    {
-                        const uint32_t cnt = n - i < SYM_CHUNK ? n - i : SYM_CHUNK;
-                        s->chunks[2 * chunk] = word + i * len;
-                        s->chunks[2 * chunk + 1] = cnt | (len - 1) << 8 | (uint32_t)cls << 16;
-                        ++chunk;
-                    }
-                    word += n * len;
-                }
-                else
-                {   /* one chunk per long record, filled in when the record is placed */
-                    chunk += n;
-                    word += long_words;
-                }
-            }
-        }
-        s->band_first[cls * (s->nbands + 1) + s->nbands] = chunk;
-        if (cls == SYM_REC_INTRA) s->n_chunks_nest = chunk;
+        const GroupSize z = group_size(s, g);
+        words += z.words;
+        chunks += z.chunks;
+        ords += z.ord;
+        nest |= z.ord != 0 && g / per_class == SYM_REC_INTRA;
     }
-    s->n_rec_words = word;
-    s->n_records = ord;
-    s->n_chunks = chunk;
-    s->need_nest = is_ipic ? 1 : need_nest;
+    uint32_t n_words, n_chunks, n_ords;
+    uint32_t word = lane_scan(words, &n_words), chunk = lane_scan(chunks, &n_chunks), ord = lane_scan(ords, &n_ords);
+    const int need_nest = lane_count(nest) != 0;
+    for (int g = g0; g < g1; ++g)
+    {
+        const int cls = g / per_class, lb = g % SYM_LEN_BUCKETS;
+        if (lb == 0) s->band_first[cls * (s->nbands + 1) + (g - cls * per_class) / SYM_LEN_BUCKETS] = chunk;
+        const GroupSize z = group_size(s, g);
+        s->grp_base[g] = word;
+        s->grp_chunk[g] = chunk;
+        s->grp_ord[g] = ord;
+        if (lb < SYM_LEN_BUCKETS - 1)
+        {
+            const uint32_t len = (uint32_t)lb + 1;
+            for (uint32_t i = 0; i < z.ord; i += SYM_CHUNK)
+            {
+                const uint32_t cnt = z.ord - i < SYM_CHUNK ? z.ord - i : SYM_CHUNK;
+                s->chunks[2 * (chunk + i / SYM_CHUNK)] = word + i * len;
+                s->chunks[2 * (chunk + i / SYM_CHUNK) + 1] = cnt | (len - 1) << 8 | (uint32_t)cls << 16;
+            }
+        }   /* else: one chunk per long record, filled in when the record is placed */
+        word += z.words;
+        chunk += z.chunks;
+        ord += z.ord;
+        /* first chunk past the class = chunk count after its last group */
+        if (g + 1 - cls * per_class == per_class) s->band_first[cls * (s->nbands + 1) + s->nbands] = chunk;
+    }
+    H4E_SYNC();
+    if (H4E_LANE == 0)
+    {
+        s->n_chunks_nest = s->band_first[SYM_REC_INTRA * (s->nbands + 1) + s->nbands];
+        s->n_rec_words = n_words;
+        s->n_records = n_ords;
+        s->n_chunks = n_chunks;
+        s->need_nest = is_ipic ? 1 : need_nest;
+    }
 }
 
 /*
@@ -1027,34 +1087,6 @@ H4E_INL void schedule_record(H4Seq *s, Work *work, Cursors *c, uint32_t t, int i
     w->cls = (uint8_t)cls;
     w->plane = (uint8_t)p;
     cursors_advance(c, p, lut);
-}
-
-/* exclusive prefix sum of `v` over the lanes (total in *sum); the identity on a host thread */
-H4E_INL uint32_t lane_scan(uint32_t v, uint32_t *sum)
-{
-#if defined(H4E_DEVICE)
-    uint32_t inc = v;
-    for (int d = 1; d < 32; d <<= 1)
-    {
-        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-        if (H4E_LANE >= d) inc += o;
-    }
-    *sum = __shfl_sync(0xFFFFFFFFu, inc, 31);
-    return inc - v;
-#else
-    *sum = v;
-    return 0;
-#endif
-}
-
-/* number of lanes whose predicate holds */
-H4E_INL uint32_t lane_count(int pred)
-{
-#if defined(H4E_DEVICE)
-    return (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, pred));
-#else
-    return pred ? 1u : 0u;
-#endif
 }
 
 /* Records of one row in bitstream order: one macroblock row of a P/B picture (all three planes,
@@ -2269,7 +2301,7 @@ H4E_FN void begin_flat(H4Seq *s, int is_i)
 H4E_FN void begin_maps(H4Seq *s, int is_i)
 {
     PROF_T0();
-    if (H4E_LANE == 0) reset_record_counts(s);
+    reset_record_counts(s);
     H4E_SYNC();
 #if defined(H4E_DEVICE)
     const int split = 1;
@@ -2296,11 +2328,9 @@ H4E_FN void begin_maps(H4Seq *s, int is_i)
         pb_pass1(s);
     H4E_SYNC();
     PROF_ADD(1);
-    if (H4E_LANE == 0)
-    {
-        plan_records(s, is_i);
-        plan_blob(s);
-    }
+    plan_records(s, is_i);
+    H4E_SYNC();
+    if (H4E_LANE == 0) plan_blob(s);
     H4E_SYNC();
     PROF_ADD(2);
 }

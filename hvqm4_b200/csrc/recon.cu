@@ -425,6 +425,8 @@ recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs, uint32_t cta_
 #endif
 constexpr int kBandWarps = HVQM4_BAND_WARPS;
 constexpr int kTileMcbs = 128;
+constexpr int kBandRows = 8;   /* macroblock rows per CTA of the band kernel = kBandRows record bands of symbuf.h */
+static_assert(SYM_BAND_MCB_ROWS == 1, "the band kernel takes kBandRows record bands per CTA");
 
 /* queue capacity of one warp in entries: its four block rows (two luma, one U, one V) of one column tile */
 static inline int band_queue_entries(int mcb_w)
@@ -561,15 +563,16 @@ recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap)
     if (v.has_nest) nest_stage_begin<kBandWarps * 32>(v, rc_smem + RC_SMEM_TABLE_BYTES);   /* lands during the map phase */
 
     /* map phase */
-    const int row0 = band * SYM_BAND_MCB_ROWS, row1 = min(row0 + SYM_BAND_MCB_ROWS, v.mcb_h);
+    const int row0 = band * kBandRows, row1 = min(row0 + kBandRows, v.mcb_h);
 #pragma unroll 1
     for (int mx0 = 0; mx0 < v.mcb_w; mx0 += kTileMcbs)
         band_map_tile(v, row0, row1, mx0, min(mx0 + kTileMcbs, v.mcb_w), queue, queue_cap);
     /* record phase */
     const uint32_t nb1 = v.n_bands + 1;
-    const uint32_t raw0 = __ldg(v.bands + band), raw1 = __ldg(v.bands + band + 1);
-    const uint32_t intra0 = __ldg(v.bands + nb1 + band), intra1 = __ldg(v.bands + nb1 + band + 1);
-    const uint32_t inter0 = __ldg(v.bands + 2 * nb1 + band), inter1 = __ldg(v.bands + 2 * nb1 + band + 1);
+    /* the chunks of a class are ordered by record band (= macroblock row), so rows row0..row1 are one range */
+    const uint32_t raw0 = __ldg(v.bands + row0), raw1 = __ldg(v.bands + row1);
+    const uint32_t intra0 = __ldg(v.bands + nb1 + row0), intra1 = __ldg(v.bands + nb1 + row1);
+    const uint32_t inter0 = __ldg(v.bands + 2 * nb1 + row0), inter1 = __ldg(v.bands + 2 * nb1 + row1);
     if (intra1 > intra0)
     {
         nest_stage_wait();
@@ -687,7 +690,7 @@ extern "C" void hvqm4_recon_set_mode(int band_mode) { g_band_mode = band_mode; }
 extern "C" int hvqm4_recon_launch_band(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, cudaStream_t stream)
 {
     if (n_jobs <= 0) return 0;
-    const int n_bands = (mcb_h + SYM_BAND_MCB_ROWS - 1) / SYM_BAND_MCB_ROWS;
+    const int n_bands = (mcb_h + kBandRows - 1) / kBandRows;
     const int rc = launch_band<4>(d_jobs, n_jobs, n_bands, mcb_w, stream);
     if (rc == 0) ++g_band_launches;
     return rc;
@@ -703,7 +706,7 @@ extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w,
     /* HVQM4_MAP_CFG / HVQM4_REC_CFG / HVQM4_SUBBATCH pin a configuration (tuning experiments) */
     static const int map_cfg = env_int("HVQM4_MAP_CFG"), rec_cfg = env_int("HVQM4_REC_CFG"), sub_env = env_int("HVQM4_SUBBATCH");
     static const int band_env = env_int("HVQM4_BAND");   /* 1..4: force the band kernel (min blocks), -1: never */
-    const int n_bands = (mcb_h + SYM_BAND_MCB_ROWS - 1) / SYM_BAND_MCB_ROWS;
+    const int n_bands = (mcb_h + kBandRows - 1) / kBandRows;
     const int band_mode = g_band_mode != 0 ? g_band_mode : band_env;
     /* auto: the fused band kernel pays off when the pictures are record-heavy and there are enough bands
        (measured on dense 640x480 content: 16 pictures = 128 bands 444 k vs 424 k frames/s, 64 pictures 862 k vs
