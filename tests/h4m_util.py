@@ -31,8 +31,11 @@ def demux(data: bytes):
     return version, w, h, recs
 
 
-def emul_decode(lib, data: bytes):
-    """Host stage (entropy.c) + CPU emulation of the kernel work order; yields (type, yuv bytes, err)."""
+def emul_decode(lib, data: bytes, sweep=None, stats=None):
+    """Host stage (entropy.c) + CPU emulation of the kernel work order; yields (type, yuv bytes, err).
+    sweep = (band rows, shared-memory bytes, look-ahead bands): emulate the sweep kernel's plan and work order
+    (tests/emul/sweep_emul.cpp); pictures its plan does not serve go the band kernel's way, as in the product,
+    and are counted in stats["fallback"]."""
     version, w, h, recs = demux(data)
     seq = lib.h4e_seq_create(w, h, 2, 2, int(version == 15))
     assert seq
@@ -49,7 +52,14 @@ def emul_decode(lib, data: bytes):
             blob = np.zeros(n, np.uint8)
             err = lib.h4e_parse_finish(seq, blob.ctypes.data)
             fut = bufs[present] if ty == P_FRAME else bufs[future]
-            rc = lib.emul_recon_picture(blob.ctypes.data, bufs[present].ctypes.data, bufs[past].ctypes.data, fut.ctypes.data)
+            rc = 1
+            if sweep is not None:
+                rc = lib.emul_sweep_picture(blob.ctypes.data, bufs[present].ctypes.data, bufs[past].ctypes.data, fut.ctypes.data, *sweep)
+                assert rc in (0, 1), f"sweep emulation failed ({rc})"
+                if stats is not None:
+                    stats["sweep" if rc == 0 else "fallback"] = stats.get("sweep" if rc == 0 else "fallback", 0) + 1
+            if rc == 1:
+                rc = lib.emul_recon_picture(blob.ctypes.data, bufs[present].ctypes.data, bufs[past].ctypes.data, fut.ctypes.data)
             assert rc == 0, f"segment table / prefix sum disagree ({rc})"
             yield ty, bufs[present][:fb].tobytes(), err
             if ty != B_FRAME:
