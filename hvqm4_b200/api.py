@@ -93,6 +93,8 @@ SIGNATURES = {
     "HVQM4BatchReplay": (c_float, [c_void_p, c_int]),
     "HVQM4BatchStats": (None, [c_void_p, POINTER(c_uint64)]),
     "HVQM4KernelLaunches": (ctypes.c_longlong, []),
+    "HVQM4SweepLaunches": (ctypes.c_longlong, []),
+    "HVQM4SweepErrors": (ctypes.c_int, []),
     "HVQM4SetReconMode": (None, [c_int]),
     "HVQM4HostAlloc": (c_void_p, [c_size_t]),
     "HVQM4HostFree": (None, [c_void_p]),
@@ -418,8 +420,16 @@ class Batch:
 
 
 def set_recon_mode(mode: int) -> None:
-    """0 auto, >0 fused band kernel, <0 map + record kernels (see include/hvqm4.h)."""
+    """0 auto, 1..4 fused band kernel, 5 sweep kernel, <0 map + record kernels (see include/hvqm4.h)."""
     lib().HVQM4SetReconMode(mode)
+
+
+def sweep_launches() -> int:
+    return lib().HVQM4SweepLaunches()
+
+
+def sweep_errors() -> int:
+    return lib().HVQM4SweepErrors()
 
 
 def kernel_launches() -> int:

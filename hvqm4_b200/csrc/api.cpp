@@ -1346,6 +1346,11 @@ H4_API long long HVQM4KernelLaunches(void) { return g_launches.load(); }
 
 H4_API void HVQM4SetReconMode(int mode) { hvqm4_recon_set_mode(mode); }
 
+extern "C" int hvqm4_sweep_errors(void);
+extern "C" long long hvqm4_recon_sweep_launches(void);
+H4_API int HVQM4SweepErrors(void) { return hvqm4_sweep_errors(); }
+H4_API long long HVQM4SweepLaunches(void) { return hvqm4_recon_sweep_launches(); }
+
 /* ====================================================================== container walker */
 
 static inline uint32_t be32(const uint8_t *p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }

@@ -37,6 +37,7 @@
 
 #include "recon.h"
 #include "recon_core.h"
+#include "recon_dev.cuh"
 
 namespace {
 
@@ -47,27 +48,6 @@ namespace {
    a kernel's completion implies the completion of everything in front of it. */
 __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
-/* ------------------------------------------------------------------------------------------
- * picture parameters: one ReconView per CTA in shared memory (constant-offset LDS, no live
- * registers across the block functions)
- * ------------------------------------------------------------------------------------------ */
-__device__ __forceinline__ void load_view(ReconView &vw, const ReconJob &J)
-{
-    if (!J.blob)
-    {   /* the GPU entropy stage rejected this picture: nothing to reconstruct */
-        vw.blob = nullptr;
-        vw.mcb_h = 0; vw.mcb_w = 0; vw.nseg = 1; vw.n_bands = 0; vw.n_chunks = 0; vw.n_chunks_nest = 0; vw.has_nest = 0;
-        return;
-    }
-    SymHeader h;
-    const uint4 *src = reinterpret_cast<const uint4 *>(J.blob);
-    uint4 *dst = reinterpret_cast<uint4 *>(&h);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) dst[i] = __ldg(src + i);     /* header fields end at byte 88 */
-    rc_make_view(vw, J.blob, h, nullptr, nullptr, nullptr, J.past, J.future);
-    vw.present = J.present;
-}
 
 /* ------------------------------------------------------------------------------------------
  * building blocks shared by the kernels
@@ -215,52 +195,6 @@ __device__ __forceinline__ void record_chunk_pre(const ReconView &v, uint2 cd, i
     rc_record_block_pre(v, cls, len, rec, hdr, extra, rows);
 #pragma unroll
     for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];
-}
-
-/* h4m:262-273 into shared memory */
-template <int kThreads>
-__device__ __forceinline__ void build_div_tables()
-{
-    int32_t *s_mcdiv = reinterpret_cast<int32_t *>(rc_smem + RC_SMEM_MCDIV_OFF);
-    int32_t *s_div = reinterpret_cast<int32_t *>(rc_smem + RC_SMEM_DIV_OFF);
-    for (int i = threadIdx.x; i < 256; i += kThreads) s_mcdiv[i] = i ? 0x1000 / i : 0;
-    if (threadIdx.x < 16) s_div[threadIdx.x] = threadIdx.x ? 0x1000 / (threadIdx.x * 16) : 0;   /* divTable / 16 (recon_core.h) */
-}
-
-/* The packed nest of the CTA's picture (35-byte pitch, 16-byte aligned in the blob) is staged in shared memory
-   by asynchronous copies -- no registers, nothing waits for it -- and expanded into the lookup tables later:
-   nest_stage_begin() ... (other work) ... nest_stage_wait(); __syncthreads(); nest_spread(); __syncthreads().
-   The caller provides 38 * 40 bytes of scratch. */
-template <int kThreads>
-__device__ __forceinline__ void nest_stage_begin(const ReconView &v, uint8_t *packed)
-{
-    const uint8_t *src = v.blob + v.off_nest;
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(packed);
-    for (int i = threadIdx.x; i < (SYM_NEST_BYTES + 15) / 16; i += kThreads)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16 * i) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void nest_stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-template <int kThreads>
-__device__ __forceinline__ void nest_spread(uint8_t *packed)
-{
-    uint32_t *s_nest_tab = reinterpret_cast<uint32_t *>(rc_smem + RC_SMEM_NEST_OFF);
-    uint32_t *stage = reinterpret_cast<uint32_t *>(packed);
-    /* nibbles x..x+7 of row y, spread into table entries x = 2j and 2j+1 (samples x..x+3, one per byte, times 16);
-       both share bytes j..j+4 of the row.  Entries near the end of a row run into the next row: those nibbles lie
-       beyond column 69, which no descriptor reaches (offset <= 63, largest pattern + 6). */
-    const uint32_t *pw = stage;
-    for (int i = threadIdx.x; i < SYM_NEST_H * (RC_NEST_PITCH / 2); i += kThreads)
-    {
-        const int y = i / (RC_NEST_PITCH / 2), j = i - y * (RC_NEST_PITCH / 2);
-        const int b = y * SYM_NEST_ROW_BYTES + j, w = b >> 2, sh = (b & 3) * 8;
-        const uint32_t w0 = pw[w], w1 = pw[w + 1], w2 = sh ? pw[w + 2] : 0u;
-        const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-        const uint32_t odd = (lo >> 4) | (hi << 28);
-        s_nest_tab[y * RC_NEST_PITCH + 2 * j] = rc_nest_spread_step1(lo);
-        s_nest_tab[y * RC_NEST_PITCH + 2 * j + 1] = rc_nest_spread_step1(odd);
-    }
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -545,47 +479,56 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, int row0, int 
     __syncwarp();
 }
 
+/* n_items = pictures x bands.  A launch normally has one CTA per item; the fallback launch behind the sweep kernel
+   (skip_handled: pictures whose job says pad[0] = 1 are already reconstructed) has a few CTAs per SM walking all
+   items, because nearly all of them are skipped. */
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kBandWarps * 32, kMinBlocks)
-recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap)
+recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap, int n_items, int skip_handled)
 {
     ReconView &vw = *reinterpret_cast<ReconView *>(rc_smem + RC_SMEM_VIEW_OFF);
     /* dynamic shared memory: [tables + view | nest staging scratch | queue counters | queue] */
     uint32_t *queue = reinterpret_cast<uint32_t *>(rc_smem + kRecSmem) + (threadIdx.x >> 5) * queue_cap;   /* the warp's own */
-    const int job = blockIdx.x / n_bands;
-    const int band = blockIdx.x - job * n_bands;
-    if (threadIdx.x == 0) load_view(vw, jobs[job]);
     build_div_tables<kBandWarps * 32>();
-    __syncthreads();
-    const ReconView &v = vw;
-    if (!v.blob) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (v.has_nest) nest_stage_begin<kBandWarps * 32>(v, rc_smem + RC_SMEM_TABLE_BYTES);   /* lands during the map phase */
-
-    /* map phase */
-    const int row0 = band * kBandRows, row1 = min(row0 + kBandRows, v.mcb_h);
 #pragma unroll 1
-    for (int mx0 = 0; mx0 < v.mcb_w; mx0 += kTileMcbs)
-        band_map_tile(v, row0, row1, mx0, min(mx0 + kTileMcbs, v.mcb_w), queue, queue_cap);
-    /* record phase */
-    const uint32_t nb1 = v.n_bands + 1;
-    /* the chunks of a class are ordered by record band (= macroblock row), so rows row0..row1 are one range */
-    const uint32_t raw0 = __ldg(v.bands + row0), raw1 = __ldg(v.bands + row1);
-    const uint32_t intra0 = __ldg(v.bands + nb1 + row0), intra1 = __ldg(v.bands + nb1 + row1);
-    const uint32_t inter0 = __ldg(v.bands + 2 * nb1 + row0), inter1 = __ldg(v.bands + 2 * nb1 + row1);
-    if (intra1 > intra0)
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x)
     {
-        nest_stage_wait();
+        const int job = item / n_bands;
+        const int band = item - job * n_bands;
+        if (skip_handled && __ldg(&jobs[job].pad[0])) continue;
+        __syncthreads();     /* the previous item is finished (view, tables, queues) */
+        if (threadIdx.x == 0) load_view(vw, jobs[job]);
         __syncthreads();
-        nest_spread<kBandWarps * 32>(rc_smem + RC_SMEM_TABLE_BYTES);
+        const ReconView &v = vw;
+        if (!v.blob) continue;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (v.has_nest) nest_stage_begin<kBandWarps * 32>(v, rc_smem + RC_SMEM_TABLE_BYTES);   /* lands during the map phase */
+
+        /* map phase */
+        const int row0 = band * kBandRows, row1 = min(row0 + kBandRows, v.mcb_h);
+#pragma unroll 1
+        for (int mx0 = 0; mx0 < v.mcb_w; mx0 += kTileMcbs)
+            band_map_tile(v, row0, row1, mx0, min(mx0 + kTileMcbs, v.mcb_w), queue, queue_cap);
+        /* record phase */
+        const uint32_t nb1 = v.n_bands + 1;
+        /* the chunks of a class are ordered by record band (= macroblock row), so rows row0..row1 are one range */
+        const uint32_t raw0 = __ldg(v.bands + row0), raw1 = __ldg(v.bands + row1);
+        const uint32_t intra0 = __ldg(v.bands + nb1 + row0), intra1 = __ldg(v.bands + nb1 + row1);
+        const uint32_t inter0 = __ldg(v.bands + 2 * nb1 + row0), inter1 = __ldg(v.bands + 2 * nb1 + row1);
+        if (v.has_nest) nest_stage_wait();
+        if (intra1 > intra0)
+        {
+            __syncthreads();
+            nest_spread<kBandWarps * 32>(rc_smem + RC_SMEM_TABLE_BYTES);
+        }
+        __syncthreads();     /* map stores of the band visible to the whole CTA; nest table complete */
+#pragma unroll 1
+        for (uint32_t c = raw0 + warp; c < raw1; c += kBandWarps) record_chunk(v, c, lane);
+#pragma unroll 1
+        for (uint32_t c = intra0 + warp; c < intra1; c += kBandWarps) record_chunk(v, c, lane);
+#pragma unroll 1
+        for (uint32_t c = inter0 + warp; c < inter1; c += kBandWarps) record_chunk(v, c, lane);
     }
-    __syncthreads();     /* map stores of the band visible to the whole CTA; nest table complete */
-#pragma unroll 1
-    for (uint32_t c = raw0 + warp; c < raw1; c += kBandWarps) record_chunk(v, c, lane);
-#pragma unroll 1
-    for (uint32_t c = intra0 + warp; c < intra1; c += kBandWarps) record_chunk(v, c, lane);
-#pragma unroll 1
-    for (uint32_t c = inter0 + warp; c < inter1; c += kBandWarps) record_chunk(v, c, lane);
 }
 
 template <typename... KArgs, typename... Args>
@@ -630,10 +573,11 @@ int env_int(const char *name)
 }  // namespace
 
 template <int kMinBlocks>
-int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, int mcb_w, cudaStream_t stream)
+int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, int mcb_w, cudaStream_t stream, bool skip_handled = false)
 {
-    const long long grid = (long long)n_jobs * n_bands;
-    if (grid > 0x7FFFFFFFll) return (int)cudaErrorInvalidConfiguration;
+    const long long items = (long long)n_jobs * n_bands;
+    if (items > 0x7FFFFFFFll) return (int)cudaErrorInvalidConfiguration;
+    const long long grid = skip_handled && items > 148 * kMinBlocks ? 148 * kMinBlocks : items;
     const int cap = band_queue_entries(mcb_w);
     const int smem = kRecSmem + kBandWarps * cap * 4;
     if (smem > 48 * 1024)
@@ -641,12 +585,30 @@ int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, int mcb_w, cuda
         const cudaError_t e = cudaFuncSetAttribute(recon_band_kernel<kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
     }
-    recon_band_kernel<kMinBlocks><<<(unsigned)grid, kBandWarps * 32, smem, stream>>>(d_jobs, n_bands, cap);
+    recon_band_kernel<kMinBlocks><<<(unsigned)grid, kBandWarps * 32, smem, stream>>>(d_jobs, n_bands, cap, (int)items, skip_handled ? 1 : 0);
     return (int)cudaGetLastError();
 }
 
+extern "C" int hvqm4_sweep_supported(int mcb_w, int mcb_h);
+extern "C" int hvqm4_sweep_launch(ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, cudaStream_t stream);
+long long g_sweep_launches = 0;
+
+/* The sweep kernel (sweep.cu) reconstructs the pictures its plan serves and marks the others; the band kernel
+   behind it takes the marked ones (normally none: a few CTAs per SM walk the job list and leave). */
+static int launch_sweep_then_band(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, cudaStream_t stream, int *launches);
+
+/* 0 auto, 5 forced: does this step go to the sweep kernel?  One CTA per SM takes whole pictures, so it needs about
+   as many pictures as SMs to fill the GPU. */
+static bool use_sweep(int mode, int n_jobs, int mcb_w, int mcb_h)
+{
+    static const int env = getenv("HVQM4_SWEEP") ? atoi(getenv("HVQM4_SWEEP")) : -1;   /* 0: never in auto mode, 1: always */
+    if (mode == 5 || (mode == 0 && env == 1)) return hvqm4_sweep_supported(mcb_w, mcb_h) != 0;
+    if (mode != 0 || env == 0) return false;
+    return n_jobs >= 96 && hvqm4_sweep_supported(mcb_w, mcb_h) != 0;
+}
+
 int g_band_mode = 0;
-long long g_band_launches = 0;   /* steps issued as one fused band kernel (diagnostics) */   /* set by hvqm4_recon_set_mode: 0 auto, >0 force band kernel, <0 force map+record kernels */
+long long g_band_launches = 0;   /* steps issued as one fused band kernel (diagnostics) */   /* set by hvqm4_recon_set_mode: 0 auto, 1..4 force the band kernel, 5 force the sweep kernel, <0 force map+record kernels */
 
 static int launch_map_cfg(int cfg, const ReconJob *d_jobs, int n_jobs, int units, bool record_heavy, cudaStream_t stream)
 {
@@ -690,17 +652,31 @@ extern "C" void hvqm4_recon_set_mode(int band_mode) { g_band_mode = band_mode; }
 extern "C" int hvqm4_recon_launch_band(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, cudaStream_t stream)
 {
     if (n_jobs <= 0) return 0;
+    if (use_sweep(g_band_mode, n_jobs, mcb_w, mcb_h)) return launch_sweep_then_band(d_jobs, n_jobs, mcb_w, mcb_h, stream, nullptr);
     const int n_bands = (mcb_h + kBandRows - 1) / kBandRows;
     const int rc = launch_band<4>(d_jobs, n_jobs, n_bands, mcb_w, stream);
     if (rc == 0) ++g_band_launches;
     return rc;
 }
 extern "C" long long hvqm4_recon_band_launches(void) { return g_band_launches; }
+extern "C" long long hvqm4_recon_sweep_launches(void) { return g_sweep_launches; }
+
+static int launch_sweep_then_band(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, cudaStream_t stream, int *launches)
+{
+    int rc = hvqm4_sweep_launch(const_cast<ReconJob *>(d_jobs), n_jobs, mcb_w, mcb_h, stream);
+    if (rc != 0) return rc;
+    ++g_sweep_launches;
+    const int n_bands = (mcb_h + kBandRows - 1) / kBandRows;
+    rc = launch_band<3>(d_jobs, n_jobs, n_bands, mcb_w, stream, true);
+    if (rc == 0 && launches) *launches += 2;
+    return rc;
+}
 
 extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const uint32_t *h_rec_prefix,
                                   cudaStream_t stream, int *launches)
 {
     if (n_jobs <= 0) return 0;
+    if (use_sweep(g_band_mode, n_jobs, mcb_w, mcb_h)) return launch_sweep_then_band(d_jobs, n_jobs, mcb_w, mcb_h, stream, launches);
     const int nseg = (mcb_w + SYM_SEG_MCBS - 1) / SYM_SEG_MCBS;
     const int units = nseg * mcb_h;
     /* HVQM4_MAP_CFG / HVQM4_REC_CFG / HVQM4_SUBBATCH pin a configuration (tuning experiments) */

@@ -207,11 +207,18 @@ void HVQM4BatchStats(HVQM4Batch *b, uint64_t out[8]);
    SDK-mode decodes); used by benchmarks to report how much work really ran on the GPU. */
 long long HVQM4KernelLaunches(void);
 
-/* Reconstruction schedule: 0 = chosen by batch size (default); > 0 = always the fused per-band
+/* Reconstruction schedule: 0 = chosen by batch size (default); 1..4 = always the fused per-band
    kernel (one launch per step; 2, 3 or 4 also pins its CTAs per SM, 1 leaves that to the grid
-   size); < 0 = always the map kernel + record kernel pair.  All give identical pictures; the
-   switch exists for tests and measurements.  Process-wide. */
+   size); 5 = always the sweep kernel (one persistent CTA per SM walks a picture out of shared
+   memory, reference rows and symbol slices staged by TMA bulk copies; pictures its plan does not
+   serve and picture sizes it does not serve fall to the band kernel); < 0 = always the map
+   kernel + record kernel pair.  All give identical pictures; the switch exists for tests and
+   measurements.  Process-wide. */
 void HVQM4SetReconMode(int mode);
+/* Diagnostics of the sweep kernel: launches so far; nonzero if one of its CTAs ever gave up waiting on its
+   copy pipeline (never on a healthy device; synchronises the device). */
+long long HVQM4SweepLaunches(void);
+int HVQM4SweepErrors(void);
 
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA toolchain. */
 void *HVQM4HostAlloc(size_t bytes);

@@ -12,10 +12,10 @@ from tests.h4m_util import md5
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["two_kernels", "band_kernel"])
+@pytest.fixture(params=["two_kernels", "band_kernel", "sweep_kernel"])
 def recon_mode(request, native_lib):
-    """Every parity test runs under both reconstruction schedules (include/hvqm4.h HVQM4SetReconMode)."""
-    native_lib.set_recon_mode(-1 if request.param == "two_kernels" else 4)
+    """Every parity test runs under all three reconstruction schedules (include/hvqm4.h HVQM4SetReconMode)."""
+    native_lib.set_recon_mode({"two_kernels": -1, "band_kernel": 4, "sweep_kernel": 5}[request.param])
     yield request.param
     native_lib.set_recon_mode(0)
 
@@ -93,6 +93,26 @@ def test_batch_runtime_many_streams_vs_oracle(native_lib, oracle, recon_mode):
     for step, frames in enumerate(native_lib.decode_streams(files)):
         for i, (_, _, yuv) in enumerate(frames):
             assert yuv == want[i][step], (i, step)
+
+
+@pytest.mark.parametrize("profile", [0, 1])
+def test_sweep_kernel_full_size_vs_oracle(native_lib, oracle, profile):
+    """The sweep kernel at BASELINE.json's size, where the reference windows fill shared memory (dense content: vectors
+    of +-64 rows, B pictures swept twice): 12 streams of 640x480 against the oracle, frame by frame; the kernel must
+    actually have run and none of its CTAs may have given up on its copy pipeline."""
+    n = 12
+    files = [synth.generate(640, 480, 15, "IPBBPBB", 1, seed=7100 + i, profile=profile) for i in range(n)]
+    want = [[yuv for _, _, _, yuv in oracle.PortDecoder(f).frames()] for f in files]
+    native_lib.set_recon_mode(5)
+    try:
+        before = native_lib.sweep_launches()
+        for step, frames in enumerate(native_lib.decode_streams(files)):
+            for i, (_, _, yuv) in enumerate(frames):
+                assert yuv == want[i][step], (i, step)
+        assert native_lib.sweep_launches() - before == 7
+        assert native_lib.sweep_errors() == 0
+    finally:
+        native_lib.set_recon_mode(0)
 
 
 def test_record_replay_is_idempotent_and_counts_launches(native_lib, golden):
