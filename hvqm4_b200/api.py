@@ -95,6 +95,8 @@ SIGNATURES = {
     "HVQM4KernelLaunches": (ctypes.c_longlong, []),
     "HVQM4SweepLaunches": (ctypes.c_longlong, []),
     "HVQM4SweepErrors": (ctypes.c_int, []),
+    "HVQM4RowLaunches": (ctypes.c_longlong, []),
+    "HVQM4RowErrors": (ctypes.c_int, []),
     "HVQM4SetReconMode": (None, [c_int]),
     "HVQM4HostAlloc": (c_void_p, [c_size_t]),
     "HVQM4HostFree": (None, [c_void_p]),
@@ -420,7 +422,7 @@ class Batch:
 
 
 def set_recon_mode(mode: int) -> None:
-    """0 auto, 1..4 fused band kernel, 5 sweep kernel, <0 map + record kernels (see include/hvqm4.h)."""
+    """0 auto, 1..4 fused band kernel, 5 sweep kernel, 6 row kernel, <0 map + record kernels (see include/hvqm4.h)."""
     lib().HVQM4SetReconMode(mode)
 
 
@@ -430,6 +432,14 @@ def sweep_launches() -> int:
 
 def sweep_errors() -> int:
     return lib().HVQM4SweepErrors()
+
+
+def row_launches() -> int:
+    return lib().HVQM4RowLaunches()
+
+
+def row_errors() -> int:
+    return lib().HVQM4RowErrors()
 
 
 def kernel_launches() -> int:

@@ -7,8 +7,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libhvqm4_b200.so")
-SOURCES = ["recon.cu", "sweep.cu", "rgb.cu", "audio.cu", "entropy_dev.cu", "api.cpp", "player.cpp", "entropy.c"]
-HEADERS = ["recon.h", "recon_core.h", "recon_dev.cuh", "sweep_core.h", "symbuf.h", "entropy.h", "entropy_dev.h", os.path.join("..", "..", "include", "hvqm4.h")]
+SOURCES = ["recon.cu", "sweep.cu", "row.cu", "rgb.cu", "audio.cu", "entropy_dev.cu", "api.cpp", "player.cpp", "entropy.c"]
+HEADERS = ["recon.h", "recon_core.h", "recon_dev.cuh", "sweep_core.h", "row_core.h", "symbuf.h", "entropy.h", "entropy_dev.h", os.path.join("..", "..", "include", "hvqm4.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

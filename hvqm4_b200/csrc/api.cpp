@@ -207,6 +207,7 @@ struct HVQM4Batch
     int mcb_w = 0, mcb_h = 0;
     size_t frame_bytes = 0, surf_stride = 0;
     uint8_t *d_surfaces = nullptr;
+    bool slab_ok = false;      /* the surface slab is registered with the row kernel (tensor maps exist) */
     std::vector<StreamState> st;
     Arena arena[kArenas];
     int cur = 0;
@@ -455,6 +456,8 @@ H4_API HVQM4Batch *HVQM4BatchCreate(int device, int n_streams, int width, int he
             HVQM4BatchDestroy(b);
             return nullptr;
         }
+    /* tensor maps over the slab for the row kernel's reference patches (ragged widths: no maps, other kernels) */
+    b->slab_ok = hvqm4_row_register_slab(b->d_surfaces, b->surf_stride, kSurfaces * n_streams, width, height) == 0;
     if (host_threads <= 0)
     {
         host_threads = (int)std::thread::hardware_concurrency();
@@ -486,6 +489,7 @@ H4_API void HVQM4BatchDestroy(HVQM4Batch *b)
         if (a.d) cudaFree(a.d);
         if (a.consumed) cudaEventDestroy(a.consumed);
     }
+    if (b->slab_ok) hvqm4_row_unregister_slab(b->d_surfaces);
     if (b->d_surfaces) cudaFree(b->d_surfaces);
     if (b->d_rgb) cudaFree(b->d_rgb);
     for (int i = 0; i < 2; ++i)
@@ -650,7 +654,7 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
     {
         ++g_launches;
         b->stats[1] += 1;
-        rc = hvqm4_recon_launch_band(d_jobs, n, b->mcb_w, b->mcb_h, b->s_comp);
+        rc = hvqm4_recon_launch_band(d_jobs, n, b->mcb_w, b->mcb_h, b->slab_ok ? b->d_surfaces : nullptr, b->s_comp);
         if (rc == 0)
         {
             ++g_launches;
@@ -800,7 +804,7 @@ H4_API int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, con
     cudaStreamWaitEvent(b->s_comp, b->ev_h2d, 0);
     batch_wait_readbacks(b);
     int launched = 0;
-    int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(d_base), n, b->mcb_w, b->mcb_h, b->rec_prefix.data(), b->s_comp, &launched);
+    int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(d_base), n, b->mcb_w, b->mcb_h, b->rec_prefix.data(), b->slab_ok ? b->d_surfaces : nullptr, b->s_comp, &launched);
     g_launches += launched;
     b->stats[1] += (uint64_t)launched;
     if (rc != 0)
@@ -976,7 +980,7 @@ H4_API float HVQM4BatchReplay(HVQM4Batch *b, int repeats)
         for (auto &st : b->recorded)
         {
             int launched = 0;
-            int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(st.d), st.n, b->mcb_w, b->mcb_h, st.rec_prefix.data(), b->s_comp, &launched);
+            int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(st.d), st.n, b->mcb_w, b->mcb_h, st.rec_prefix.data(), b->slab_ok ? b->d_surfaces : nullptr, b->s_comp, &launched);
             g_launches += launched;
             b->stats[1] += (uint64_t)launched;
             if (rc != 0)
@@ -1164,7 +1168,7 @@ void compat_decode(SeqObj *so, int type, const uint8_t *frame, void *present, vo
     {
         int launched = 0;
         const uint32_t prefix[2] = {0, hvqm4_rec_ctas(job->n_chunks)};
-        int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(c->d_blob), 1, c->mcb_w, c->mcb_h, prefix, c->stream, &launched);
+        int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(c->d_blob), 1, c->mcb_w, c->mcb_h, prefix, nullptr, c->stream, &launched);
         g_launches += launched;
         ok = rc == 0 || cuda_ok((cudaError_t)rc, "recon kernel launch");
     }
@@ -1348,6 +1352,10 @@ H4_API void HVQM4SetReconMode(int mode) { hvqm4_recon_set_mode(mode); }
 
 extern "C" int hvqm4_sweep_errors(void);
 extern "C" long long hvqm4_recon_sweep_launches(void);
+extern "C" long long hvqm4_recon_row_launches(void);
+extern "C" int hvqm4_row_errors(void);
+H4_API int HVQM4RowErrors(void) { return hvqm4_row_errors(); }
+H4_API long long HVQM4RowLaunches(void) { return hvqm4_recon_row_launches(); }
 H4_API int HVQM4SweepErrors(void) { return hvqm4_sweep_errors(); }
 H4_API long long HVQM4SweepLaunches(void) { return hvqm4_recon_sweep_launches(); }
 

@@ -480,8 +480,9 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, int row0, int 
 }
 
 /* n_items = pictures x bands.  A launch normally has one CTA per item; the fallback launch behind the sweep kernel
-   (skip_handled: pictures whose job says pad[0] = 1 are already reconstructed) has a few CTAs per SM walking all
-   items, because nearly all of them are skipped. */
+   (skip_handled = 1: pictures whose job says pad[0] = 1 are already reconstructed) or the row kernel (skip_handled = 2:
+   only pictures whose job says pad[1] = 1 are left) has a few CTAs per SM walking all items, because nearly all of
+   them are skipped. */
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kBandWarps * 32, kMinBlocks)
 recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap, int n_items, int skip_handled)
@@ -495,7 +496,8 @@ recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap,
     {
         const int job = item / n_bands;
         const int band = item - job * n_bands;
-        if (skip_handled && __ldg(&jobs[job].pad[0])) continue;
+        if (skip_handled == 1 && __ldg(&jobs[job].pad[0])) continue;
+        if (skip_handled == 2 && !__ldg(&jobs[job].pad[1])) continue;
         __syncthreads();     /* the previous item is finished (view, tables, queues) */
         if (threadIdx.x == 0) load_view(vw, jobs[job]);
         __syncthreads();
@@ -573,7 +575,7 @@ int env_int(const char *name)
 }  // namespace
 
 template <int kMinBlocks>
-int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, int mcb_w, cudaStream_t stream, bool skip_handled = false)
+int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, int mcb_w, cudaStream_t stream, int skip_handled = 0)
 {
     const long long items = (long long)n_jobs * n_bands;
     if (items > 0x7FFFFFFFll) return (int)cudaErrorInvalidConfiguration;
@@ -585,13 +587,15 @@ int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, int mcb_w, cuda
         const cudaError_t e = cudaFuncSetAttribute(recon_band_kernel<kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
     }
-    recon_band_kernel<kMinBlocks><<<(unsigned)grid, kBandWarps * 32, smem, stream>>>(d_jobs, n_bands, cap, (int)items, skip_handled ? 1 : 0);
+    recon_band_kernel<kMinBlocks><<<(unsigned)grid, kBandWarps * 32, smem, stream>>>(d_jobs, n_bands, cap, (int)items, skip_handled);
     return (int)cudaGetLastError();
 }
 
 extern "C" int hvqm4_sweep_supported(int mcb_w, int mcb_h);
 extern "C" int hvqm4_sweep_launch(ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, cudaStream_t stream);
-long long g_sweep_launches = 0;
+extern "C" int hvqm4_row_supported(int mcb_w, int mcb_h, const void *slab_base);
+extern "C" int hvqm4_row_launch(ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const void *slab_base, cudaStream_t stream);
+long long g_sweep_launches = 0, g_row_launches = 0;
 
 /* The sweep kernel (sweep.cu) reconstructs the pictures its plan serves and marks the others; the band kernel
    behind it takes the marked ones (normally none: a few CTAs per SM walk the job list and leave). */
@@ -603,12 +607,25 @@ static bool use_sweep(int mode, int n_jobs, int mcb_w, int mcb_h)
 {
     static const int env = getenv("HVQM4_SWEEP") ? atoi(getenv("HVQM4_SWEEP")) : -1;   /* 0: never in auto mode, 1: always */
     if (mode == 5 || (mode == 0 && env == 1)) return hvqm4_sweep_supported(mcb_w, mcb_h) != 0;
-    if (mode != 0 || env == 0) return false;
-    return n_jobs >= 96 && hvqm4_sweep_supported(mcb_w, mcb_h) != 0;
+    (void)n_jobs;     /* measured (profiles/r02_*): the sweep kernel loses to the band kernel on every content; it stays selectable */
+    return false;
+}
+
+/* The row kernel (row.cu) likewise, for pictures whose surfaces lie in a registered slab. */
+static int launch_row_then_band(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const void *slab, cudaStream_t stream, int *launches);
+
+/* 0 auto, 6 forced: does this step go to the row kernel?  One CTA per SM walks macroblock rows of many pictures. */
+static bool use_row(int mode, int n_jobs, int mcb_w, int mcb_h, const void *slab)
+{
+    static const int env = getenv("HVQM4_ROW") ? atoi(getenv("HVQM4_ROW")) : -1;   /* 0: never in auto mode, 1: always */
+    if (!slab) return false;
+    if (mode == 6 || (mode == 0 && env == 1)) return hvqm4_row_supported(mcb_w, mcb_h, slab) != 0;
+    (void)n_jobs;
+    return false;
 }
 
 int g_band_mode = 0;
-long long g_band_launches = 0;   /* steps issued as one fused band kernel (diagnostics) */   /* set by hvqm4_recon_set_mode: 0 auto, 1..4 force the band kernel, 5 force the sweep kernel, <0 force map+record kernels */
+long long g_band_launches = 0;   /* steps issued as one fused band kernel (diagnostics) */   /* set by hvqm4_recon_set_mode: 0 auto, 1..4 force the band kernel, 5 force the sweep kernel, 6 force the row kernel, <0 force map+record kernels */
 
 static int launch_map_cfg(int cfg, const ReconJob *d_jobs, int n_jobs, int units, bool record_heavy, cudaStream_t stream)
 {
@@ -649,9 +666,10 @@ extern "C" void hvqm4_recon_set_mode(int band_mode) { g_band_mode = band_mode; }
 
 /* the fused band kernel only (no host-side record prefix needed): used behind the GPU entropy stage, where it
    runs next to the parse kernels -- the smallest register footprint (end to end 96.4 k vs 94.4 k frames/s) */
-extern "C" int hvqm4_recon_launch_band(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, cudaStream_t stream)
+extern "C" int hvqm4_recon_launch_band(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const void *slab, cudaStream_t stream)
 {
     if (n_jobs <= 0) return 0;
+    if (use_row(g_band_mode, n_jobs, mcb_w, mcb_h, slab)) return launch_row_then_band(d_jobs, n_jobs, mcb_w, mcb_h, slab, stream, nullptr);
     if (use_sweep(g_band_mode, n_jobs, mcb_w, mcb_h)) return launch_sweep_then_band(d_jobs, n_jobs, mcb_w, mcb_h, stream, nullptr);
     const int n_bands = (mcb_h + kBandRows - 1) / kBandRows;
     const int rc = launch_band<4>(d_jobs, n_jobs, n_bands, mcb_w, stream);
@@ -660,6 +678,18 @@ extern "C" int hvqm4_recon_launch_band(const ReconJob *d_jobs, int n_jobs, int m
 }
 extern "C" long long hvqm4_recon_band_launches(void) { return g_band_launches; }
 extern "C" long long hvqm4_recon_sweep_launches(void) { return g_sweep_launches; }
+extern "C" long long hvqm4_recon_row_launches(void) { return g_row_launches; }
+
+static int launch_row_then_band(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const void *slab, cudaStream_t stream, int *launches)
+{
+    int rc = hvqm4_row_launch(const_cast<ReconJob *>(d_jobs), n_jobs, mcb_w, mcb_h, slab, stream);
+    if (rc != 0) return rc;
+    ++g_row_launches;
+    const int n_bands = (mcb_h + kBandRows - 1) / kBandRows;
+    rc = launch_band<3>(d_jobs, n_jobs, n_bands, mcb_w, stream, 2);
+    if (rc == 0 && launches) *launches += 2;
+    return rc;
+}
 
 static int launch_sweep_then_band(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, cudaStream_t stream, int *launches)
 {
@@ -667,15 +697,16 @@ static int launch_sweep_then_band(const ReconJob *d_jobs, int n_jobs, int mcb_w,
     if (rc != 0) return rc;
     ++g_sweep_launches;
     const int n_bands = (mcb_h + kBandRows - 1) / kBandRows;
-    rc = launch_band<3>(d_jobs, n_jobs, n_bands, mcb_w, stream, true);
+    rc = launch_band<3>(d_jobs, n_jobs, n_bands, mcb_w, stream, 1);
     if (rc == 0 && launches) *launches += 2;
     return rc;
 }
 
-extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const uint32_t *h_rec_prefix,
+extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const uint32_t *h_rec_prefix, const void *slab,
                                   cudaStream_t stream, int *launches)
 {
     if (n_jobs <= 0) return 0;
+    if (use_row(g_band_mode, n_jobs, mcb_w, mcb_h, slab)) return launch_row_then_band(d_jobs, n_jobs, mcb_w, mcb_h, slab, stream, launches);
     if (use_sweep(g_band_mode, n_jobs, mcb_w, mcb_h)) return launch_sweep_then_band(d_jobs, n_jobs, mcb_w, mcb_h, stream, launches);
     const int nseg = (mcb_w + SYM_SEG_MCBS - 1) / SYM_SEG_MCBS;
     const int units = nseg * mcb_h;

@@ -87,7 +87,7 @@ static inline uint32_t rc_dp4a_host(uint32_t a, uint32_t b, uint32_t c)
 #define RC_SMEM_VIEW_OFF (RC_SMEM_DIV_OFF + 16 * 4)
 #define RC_SMEM_TABLE_BYTES (RC_SMEM_VIEW_OFF + 256)   /* ReconView of the CTA's picture lives in shared memory too */
 #if defined(__CUDACC__)
-extern __shared__ __align__(16) uint8_t rc_smem[];
+extern __shared__ __align__(128) uint8_t rc_smem[];   /* 128: destinations of tensor copies (row.cu) */
 #endif
 #if defined(__CUDA_ARCH__)
 #define RC_NEST_TAB(v) (reinterpret_cast<const uint32_t *>(rc_smem + RC_SMEM_NEST_OFF))

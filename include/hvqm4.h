@@ -211,14 +211,20 @@ long long HVQM4KernelLaunches(void);
    kernel (one launch per step; 2, 3 or 4 also pins its CTAs per SM, 1 leaves that to the grid
    size); 5 = always the sweep kernel (one persistent CTA per SM walks a picture out of shared
    memory, reference rows and symbol slices staged by TMA bulk copies; pictures its plan does not
-   serve and picture sizes it does not serve fall to the band kernel); < 0 = always the map
-   kernel + record kernel pair.  All give identical pictures; the switch exists for tests and
+   serve and picture sizes it does not serve fall to the band kernel); 6 = always the row kernel
+   (batch mode only: one persistent CTA per SM walks macroblock rows through a shared-memory
+   pipeline, one reference patch per inter macroblock fetched by TMA tensor copies, output rows
+   assembled in shared memory and written by bulk stores; pictures with predictions that leave
+   their plane fall to the band kernel); < 0 = always the map kernel + record kernel pair.  All give identical pictures; the switch exists for tests and
    measurements.  Process-wide. */
 void HVQM4SetReconMode(int mode);
 /* Diagnostics of the sweep kernel: launches so far; nonzero if one of its CTAs ever gave up waiting on its
    copy pipeline (never on a healthy device; synchronises the device). */
 long long HVQM4SweepLaunches(void);
 int HVQM4SweepErrors(void);
+/* the same for the row kernel */
+long long HVQM4RowLaunches(void);
+int HVQM4RowErrors(void);
 
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA toolchain. */
 void *HVQM4HostAlloc(size_t bytes);

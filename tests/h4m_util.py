@@ -31,11 +31,12 @@ def demux(data: bytes):
     return version, w, h, recs
 
 
-def emul_decode(lib, data: bytes, sweep=None, stats=None):
+def emul_decode(lib, data: bytes, sweep=None, stats=None, row=None):
     """Host stage (entropy.c) + CPU emulation of the kernel work order; yields (type, yuv bytes, err).
     sweep = (band rows, shared-memory bytes, look-ahead bands): emulate the sweep kernel's plan and work order
     (tests/emul/sweep_emul.cpp); pictures its plan does not serve go the band kernel's way, as in the product,
-    and are counted in stats["fallback"]."""
+    and are counted in stats["fallback"].
+    row = (shared-memory bytes, look-ahead rows): the same for the row kernel (tests/emul/row_emul.cpp)."""
     version, w, h, recs = demux(data)
     seq = lib.h4e_seq_create(w, h, 2, 2, int(version == 15))
     assert seq
@@ -58,6 +59,11 @@ def emul_decode(lib, data: bytes, sweep=None, stats=None):
                 assert rc in (0, 1), f"sweep emulation failed ({rc})"
                 if stats is not None:
                     stats["sweep" if rc == 0 else "fallback"] = stats.get("sweep" if rc == 0 else "fallback", 0) + 1
+            if row is not None:
+                rc = lib.emul_row_picture(blob.ctypes.data, bufs[present].ctypes.data, bufs[past].ctypes.data, fut.ctypes.data, *row)
+                assert rc in (0, 1), f"row emulation failed ({rc})"
+                if stats is not None:
+                    stats["row" if rc == 0 else "fallback"] = stats.get("row" if rc == 0 else "fallback", 0) + 1
             if rc == 1:
                 rc = lib.emul_recon_picture(blob.ctypes.data, bufs[present].ctypes.data, bufs[past].ctypes.data, fut.ctypes.data)
             assert rc == 0, f"segment table / prefix sum disagree ({rc})"

@@ -12,10 +12,10 @@ from tests.h4m_util import md5
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["two_kernels", "band_kernel", "sweep_kernel"])
+@pytest.fixture(params=["two_kernels", "band_kernel", "sweep_kernel", "row_kernel"])
 def recon_mode(request, native_lib):
     """Every parity test runs under all three reconstruction schedules (include/hvqm4.h HVQM4SetReconMode)."""
-    native_lib.set_recon_mode({"two_kernels": -1, "band_kernel": 4, "sweep_kernel": 5}[request.param])
+    native_lib.set_recon_mode({"two_kernels": -1, "band_kernel": 4, "sweep_kernel": 5, "row_kernel": 6}[request.param])
     yield request.param
     native_lib.set_recon_mode(0)
 
@@ -111,6 +111,26 @@ def test_sweep_kernel_full_size_vs_oracle(native_lib, oracle, profile):
                 assert yuv == want[i][step], (i, step)
         assert native_lib.sweep_launches() - before == 7
         assert native_lib.sweep_errors() == 0
+    finally:
+        native_lib.set_recon_mode(0)
+
+
+@pytest.mark.parametrize("profile", [0, 1])
+def test_row_kernel_full_size_vs_oracle(native_lib, oracle, profile):
+    """The row kernel at BASELINE.json's size: 160 streams of 640x480 (more than one picture per CTA, pictures split
+    between CTAs) against the oracle, frame by frame; the kernel must actually have run and none of its CTAs may have
+    given up on its copy pipeline."""
+    distinct = 10
+    files = [synth.generate(640, 480, 15, "IPBBPBB", 1, seed=7200 + i, profile=profile) for i in range(distinct)]
+    want = [[yuv for _, _, _, yuv in oracle.PortDecoder(f).frames()] for f in files]
+    native_lib.set_recon_mode(6)
+    try:
+        before = native_lib.row_launches()
+        for step, frames in enumerate(native_lib.decode_streams([files[i % distinct] for i in range(160)])):
+            for i, (_, _, yuv) in enumerate(frames):
+                assert yuv == want[i % distinct][step], (i, step)
+        assert native_lib.row_launches() - before == 7
+        assert native_lib.row_errors() == 0
     finally:
         native_lib.set_recon_mode(0)
 

@@ -28,6 +28,22 @@ def test_emulated_pipeline_matches_port_on_fresh_seeds(emul_lib, oracle):
         assert got == want
 
 
+@pytest.mark.parametrize("name", ["cfg3_640x480_v15_IPB", "cfg4_320x240_v13_IPB", "cfg5_stream511", "realistic_640x480_v15_IPB",
+                                  "wide_1024x576_v13_IPB", "hd_1280x720_v15_IPB", "small_64x48_v13_IPB"])
+@pytest.mark.parametrize("kernel", ["sweep", "row"])
+def test_emulated_pipeline_kernels_match_golden(emul_lib, golden, name, kernel):
+    """The shared-memory pipeline kernels (sweep.cu, row.cu): plan, slots, rings, lists and tasks run serially on the CPU.
+    Three slots / rows of look-ahead and then one, so that both a full and an empty pipeline are walked."""
+    case = golden[name]
+    for look in (6, 1):
+        stats = {}
+        kw = dict(sweep=(1, 232448, look)) if kernel == "sweep" else dict(row=(232448, look))
+        got = list(emul_decode(emul_lib, synth.generate(**case["args"]), stats=stats, **kw))
+        assert [md5(yuv) for _, yuv, _ in got] == case["md5"], (kernel, look)
+        if kernel == "row" and case["args"]["width"] % 32 == 0 and case["args"]["width"] <= 1024:
+            assert stats.get("row", 0) == len(got), stats      # every picture of these streams is served by the row kernel
+
+
 @pytest.mark.parametrize("args", [
     dict(width=320, height=240, version=15, gop="IPBBPBB", n_gops=1, seed=811, profile=0),
     dict(width=640, height=480, version=13, gop="IPB", n_gops=1, seed=812, profile=1),
