@@ -479,57 +479,70 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, int row0, int 
     __syncwarp();
 }
 
-/* n_items = pictures x bands.  A launch normally has one CTA per item; the fallback launch behind the sweep kernel
-   (skip_handled = 1: pictures whose job says pad[0] = 1 are already reconstructed) or the row kernel (skip_handled = 2:
-   only pictures whose job says pad[1] = 1 are left) has a few CTAs per SM walking all items, because nearly all of
-   them are skipped. */
-template <int kMinBlocks>
-__global__ void __launch_bounds__(kBandWarps * 32, kMinBlocks)
-recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap, int n_items, int skip_handled)
+/* one band of one picture: the whole CTA */
+__device__ __forceinline__ void band_item(const ReconJob *__restrict__ jobs, int job, int band, uint32_t *queue, int queue_cap)
 {
     ReconView &vw = *reinterpret_cast<ReconView *>(rc_smem + RC_SMEM_VIEW_OFF);
+    if (threadIdx.x == 0) load_view(vw, jobs[job]);
+    __syncthreads();
+    const ReconView &v = vw;
+    if (!v.blob) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (v.has_nest) nest_stage_begin<kBandWarps * 32>(v, rc_smem + RC_SMEM_TABLE_BYTES);   /* lands during the map phase */
+
+    /* map phase */
+    const int row0 = band * kBandRows, row1 = min(row0 + kBandRows, v.mcb_h);
+    for (int mx0 = 0; mx0 < v.mcb_w; mx0 += kTileMcbs)
+        band_map_tile(v, row0, row1, mx0, min(mx0 + kTileMcbs, v.mcb_w), queue, queue_cap);
+    /* record phase */
+    const uint32_t nb1 = v.n_bands + 1;
+    /* the chunks of a class are ordered by record band (= macroblock row), so rows row0..row1 are one range */
+    const uint32_t raw0 = __ldg(v.bands + row0), raw1 = __ldg(v.bands + row1);
+    const uint32_t intra0 = __ldg(v.bands + nb1 + row0), intra1 = __ldg(v.bands + nb1 + row1);
+    const uint32_t inter0 = __ldg(v.bands + 2 * nb1 + row0), inter1 = __ldg(v.bands + 2 * nb1 + row1);
+    if (v.has_nest) nest_stage_wait();
+    if (intra1 > intra0)
+    {
+        __syncthreads();
+        nest_spread<kBandWarps * 32>(rc_smem + RC_SMEM_TABLE_BYTES);
+    }
+    __syncthreads();     /* map stores of the band visible to the whole CTA; nest table complete */
+#pragma unroll 1
+    for (uint32_t c = raw0 + warp; c < raw1; c += kBandWarps) record_chunk(v, c, lane);
+#pragma unroll 1
+    for (uint32_t c = intra0 + warp; c < intra1; c += kBandWarps) record_chunk(v, c, lane);
+#pragma unroll 1
+    for (uint32_t c = inter0 + warp; c < inter1; c += kBandWarps) record_chunk(v, c, lane);
+}
+
+/* one CTA per (picture, band) */
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kBandWarps * 32, kMinBlocks)
+recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap)
+{
     /* dynamic shared memory: [tables + view | nest staging scratch | queue counters | queue] */
     uint32_t *queue = reinterpret_cast<uint32_t *>(rc_smem + kRecSmem) + (threadIdx.x >> 5) * queue_cap;   /* the warp's own */
+    build_div_tables<kBandWarps * 32>();
+    const int job = blockIdx.x / n_bands;
+    band_item(jobs, job, blockIdx.x - job * n_bands, queue, queue_cap);
+}
+
+/* The fallback launch behind the sweep kernel (skip_handled = 1: pictures whose job says pad[0] = 1 are already
+   reconstructed) or the row kernel (skip_handled = 2: only pictures whose job says pad[1] = 1 are left): a few CTAs per
+   SM walk all items, because nearly all of them are skipped. */
+__global__ void __launch_bounds__(kBandWarps * 32, 2)
+recon_band_walk_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap, int n_items, int skip_handled)
+{
+    uint32_t *queue = reinterpret_cast<uint32_t *>(rc_smem + kRecSmem) + (threadIdx.x >> 5) * queue_cap;
     build_div_tables<kBandWarps * 32>();
 #pragma unroll 1
     for (int item = blockIdx.x; item < n_items; item += gridDim.x)
     {
         const int job = item / n_bands;
-        const int band = item - job * n_bands;
         if (skip_handled == 1 && __ldg(&jobs[job].pad[0])) continue;
         if (skip_handled == 2 && !__ldg(&jobs[job].pad[1])) continue;
         __syncthreads();     /* the previous item is finished (view, tables, queues) */
-        if (threadIdx.x == 0) load_view(vw, jobs[job]);
-        __syncthreads();
-        const ReconView &v = vw;
-        if (!v.blob) continue;
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        if (v.has_nest) nest_stage_begin<kBandWarps * 32>(v, rc_smem + RC_SMEM_TABLE_BYTES);   /* lands during the map phase */
-
-        /* map phase */
-        const int row0 = band * kBandRows, row1 = min(row0 + kBandRows, v.mcb_h);
-#pragma unroll 1
-        for (int mx0 = 0; mx0 < v.mcb_w; mx0 += kTileMcbs)
-            band_map_tile(v, row0, row1, mx0, min(mx0 + kTileMcbs, v.mcb_w), queue, queue_cap);
-        /* record phase */
-        const uint32_t nb1 = v.n_bands + 1;
-        /* the chunks of a class are ordered by record band (= macroblock row), so rows row0..row1 are one range */
-        const uint32_t raw0 = __ldg(v.bands + row0), raw1 = __ldg(v.bands + row1);
-        const uint32_t intra0 = __ldg(v.bands + nb1 + row0), intra1 = __ldg(v.bands + nb1 + row1);
-        const uint32_t inter0 = __ldg(v.bands + 2 * nb1 + row0), inter1 = __ldg(v.bands + 2 * nb1 + row1);
-        if (v.has_nest) nest_stage_wait();
-        if (intra1 > intra0)
-        {
-            __syncthreads();
-            nest_spread<kBandWarps * 32>(rc_smem + RC_SMEM_TABLE_BYTES);
-        }
-        __syncthreads();     /* map stores of the band visible to the whole CTA; nest table complete */
-#pragma unroll 1
-        for (uint32_t c = raw0 + warp; c < raw1; c += kBandWarps) record_chunk(v, c, lane);
-#pragma unroll 1
-        for (uint32_t c = intra0 + warp; c < intra1; c += kBandWarps) record_chunk(v, c, lane);
-#pragma unroll 1
-        for (uint32_t c = inter0 + warp; c < inter1; c += kBandWarps) record_chunk(v, c, lane);
+        band_item(jobs, job, item - job * n_bands, queue, queue_cap);
     }
 }
 
@@ -579,15 +592,25 @@ int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, int mcb_w, cuda
 {
     const long long items = (long long)n_jobs * n_bands;
     if (items > 0x7FFFFFFFll) return (int)cudaErrorInvalidConfiguration;
-    const long long grid = skip_handled && items > 148 * kMinBlocks ? 148 * kMinBlocks : items;
     const int cap = band_queue_entries(mcb_w);
     const int smem = kRecSmem + kBandWarps * cap * 4;
+    if (skip_handled)
+    {
+        const long long grid = items > 148 * 2 ? 148 * 2 : items;
+        if (smem > 48 * 1024)
+        {
+            const cudaError_t e = cudaFuncSetAttribute(recon_band_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return (int)e;
+        }
+        recon_band_walk_kernel<<<(unsigned)grid, kBandWarps * 32, smem, stream>>>(d_jobs, n_bands, cap, (int)items, skip_handled);
+        return (int)cudaGetLastError();
+    }
     if (smem > 48 * 1024)
     {   /* wide pictures: opt in (per device, so not cached) */
         const cudaError_t e = cudaFuncSetAttribute(recon_band_kernel<kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
     }
-    recon_band_kernel<kMinBlocks><<<(unsigned)grid, kBandWarps * 32, smem, stream>>>(d_jobs, n_bands, cap, (int)items, skip_handled);
+    recon_band_kernel<kMinBlocks><<<(unsigned)items, kBandWarps * 32, smem, stream>>>(d_jobs, n_bands, cap);
     return (int)cudaGetLastError();
 }
 

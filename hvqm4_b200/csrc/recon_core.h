@@ -276,19 +276,22 @@ RC_HD void rc_accumulate(const ReconView &v, uint32_t word, const uint32_t R[4],
     for (int i = 0; i < 16; ++i) acc[i] = (int32_t)((uint32_t)acc[i] + factor * b[i]);   /* mod 2^32 */
 }
 
-/* window == nullptr: intra (nest table); else inter (reference luma window) */
-template <class Win>
-RC_HD void rc_add_basis(const ReconView &v, uint32_t word, const Win *window, int32_t &scale_sum, int32_t acc[16])
+/* kInter = false: intra (nest table, the window is not looked at); true: inter (reference luma window).  The window
+   policy is passed by value: a pointer to a local policy object put it on the stack (56 bytes of frame, 180 bytes of
+   spills in the band kernel at 80 registers). */
+struct RcNoWindow { };
+template <bool kInter, class Win>
+RC_HD void rc_add_basis(const ReconView &v, uint32_t word, const Win window, int32_t &scale_sum, int32_t acc[16])
 {
     const int ox = word & 0x3F, oy = (word >> 6) & 0x1F;
     const uint32_t xs2 = (word >> 11) & 1;
     const int ys = 1 + ((word >> 12) & 1);
     uint32_t R[4];
-    if (window)
+    if constexpr (kInter)
     {
         /* sample = (pixel >> 4) & 0xF (h4m:756-761): rows are fetched as up to three aligned words */
         uint32_t a;
-        const auto rows = window->rows(ox, oy, ys, a);
+        const auto rows = window.rows(ox, oy, ys, a);
         const uint32_t sel_align = 0x3210u + 0x1111u * a, sel_step = xs2 ? 0x6420u : 0x3210u;
         const bool need1 = xs2 || a >= 1, need2 = xs2 && a >= 2;
 #pragma unroll
@@ -313,8 +316,8 @@ RC_HD void rc_add_basis(const ReconView &v, uint32_t word, const Win *window, in
     }
 }
 
-template <class Win>
-RC_HD int32_t rc_aot_sum(const ReconView &v, const uint32_t *side, int n, const Win *window, int32_t acc[16])
+template <bool kInter, class Win>
+RC_HD int32_t rc_aot_sum(const ReconView &v, const uint32_t *side, int n, const Win window, int32_t acc[16])
 {
     int32_t scale_sum = 0;
 #pragma unroll
@@ -325,8 +328,8 @@ RC_HD int32_t rc_aot_sum(const ReconView &v, const uint32_t *side, int n, const 
     for (int k = 0; k < 4; ++k) w[k] = k < n ? RC_LD32(side + k) : 0u;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-        if (k < n) rc_add_basis(v, w[k], window, scale_sum, acc);
-    for (int k = 4; k < n; ++k) rc_add_basis(v, RC_LD32(side + k), window, scale_sum, acc);
+        if (k < n) rc_add_basis<kInter>(v, w[k], window, scale_sum, acc);
+    for (int k = 4; k < n; ++k) rc_add_basis<kInter>(v, RC_LD32(side + k), window, scale_sum, acc);
     uint32_t total = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) total += (uint32_t)acc[i];
@@ -337,7 +340,7 @@ RC_HD int32_t rc_aot_sum(const ReconView &v, const uint32_t *side, int n, const 
 RC_HD void rc_intra_aot(const ReconView &v, uint32_t rows[4], const uint32_t *side, int n, int V)
 {
     int32_t acc[16];
-    const int32_t mean = rc_aot_sum<RcLinearWindow>(v, side, n, nullptr, acc);
+    const int32_t mean = rc_aot_sum<false>(v, side, n, RcNoWindow{}, acc);
     /* modulo 2^32 like the reference's int32 on its targets (damaged scale symbols overflow it) */
     const uint32_t delta = ((uint32_t)V << v.unk_shift) - (uint32_t)mean;
 #pragma unroll
@@ -455,10 +458,10 @@ RC_HD uint32_t rc_sum4(uint32_t packed, uint32_t acc)
 }
 
 template <class Win>
-RC_HD void rc_predicted_aot(const ReconView &v, uint32_t rows[4], const uint32_t *side, int nibble, const Win *window)
+RC_HD void rc_predicted_aot(const ReconView &v, uint32_t rows[4], const uint32_t *side, int nibble, const Win window)
 {
     int32_t acc[16];
-    const uint32_t aot_mean = (uint32_t)rc_aot_sum(v, side, nibble - 1, window, acc);
+    const uint32_t aot_mean = (uint32_t)rc_aot_sum<true>(v, side, nibble - 1, window, acc);
     const uint32_t pair = RC_LD32(side + nibble - 1);
     const int32_t mean = (int32_t)(rc_sum4(rows[3], rc_sum4(rows[2], rc_sum4(rows[1], rc_sum4(rows[0], 8u)))) >> 4);
     int32_t lo = 255, hi = 0;
@@ -693,8 +696,7 @@ RC_HD void rc_record_block_pre(const ReconView &v, int cls, uint32_t len, const 
     {
         const uint8_t *window = rc_motion_window(v, hdr & 0xFF, extra);
         if (!window) return;                          /* the map work painted it grey */
-        const RcLinearWindow win = {window, v.width};
-        rc_predicted_aot(v, rows, rec + 1, (int)len - 1, &win);
+        rc_predicted_aot(v, rows, rec + 1, (int)len - 1, RcLinearWindow{window, v.width});
     }
 }
 
@@ -718,8 +720,7 @@ RC_HD void rc_record_block(const ReconView &v, int cls, uint32_t len, const uint
     {
         const uint8_t *window = rc_motion_window(v, t, rc_mv_word(v, plane, bx, by));
         if (!window) return;                          /* the map work painted it grey */
-        const RcLinearWindow win = {window, v.width};
-        rc_predicted_aot(v, rows, rec + 1, (int)len - 1, &win);
+        rc_predicted_aot(v, rows, rec + 1, (int)len - 1, RcLinearWindow{window, v.width});
     }
 }
 

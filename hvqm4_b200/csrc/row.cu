@@ -3,18 +3,21 @@
  * step's macroblock rows through a shared-memory pipeline (row_core.h has the design and all of the logic; this
  * file is the machinery around it: mbarriers, bulk copies, tensor copies, roles).
  *
- * Roles inside the CTA (1 + kFetchWarps + kWorkWarps warps):
- *   sequencer   per row: bulk asynchronous copies (cp.async.bulk) of the row's symbol slices, completing on `sym`;
- *               when they have landed, which macroblocks need a reference patch, ring space for them, `go`;
- *               when the work warps are done with a row, the bulk stores of its tile (shared memory -> picture)
- *               and the release of its ring space.
- *   fetch       rows in turn: wait for `go`, sort the row's blocks into class lists, set the task boundaries,
- *               announce the patch bytes on `ready` and issue two tensor copies (cp.async.bulk.tensor, luma box
- *               32 x 9 and chroma box 32 x 5 x 2) per inter macroblock; `ready` completes when they have landed.
- *   work        per row: wait for `ready`, take tasks from the row's ticket counter until none is left (32 list
- *               entries or 32 records of one class), make the tile writes visible to the asynchronous proxy and
- *               arrive on `done`.  No CTA-wide barrier inside a picture: a warp that runs out of tasks in one row
- *               starts on the next.
+ * Roles inside the CTA (2 + kWorkWarps warps):
+ *   request   per row: bulk asynchronous copies (cp.async.bulk) of the row's symbol slices, completing on `sym`;
+ *             when they have landed, ring space for the patches of its inter macroblocks, `go`.  Runs as far
+ *             ahead as slots and ring allow.
+ *   retire    per row: when the work warps are done with it (`done`), the bulk stores of its tile (shared memory
+ *             -> picture); once the tile has left shared memory the slot and the ring space are free again.
+ *   work      everything that grows with the row's content, as tasks from two ticket counters per row:
+ *             FETCH tasks (one per 32 macroblocks, for this row and the rows ahead whose `go` has been given):
+ *             sort the group's blocks into the row's class lists, give its inter macroblocks a patch place,
+ *             announce the patch bytes on `ready` and issue two tensor copies (cp.async.bulk.tensor, luma box
+ *             32 x 9 and chroma box 32 x 5 x 2) per inter macroblock -- `ready` completes when every fetch task
+ *             has arrived and all patches have landed; then the row's WORK tasks (32 list entries or 32 records
+ *             of one class) until none is left, the tile writes made visible to the asynchronous proxy, `done`.
+ *             No CTA-wide barrier inside a picture: a warp that runs out of tasks in one row starts on the next,
+ *             and a warp that waits for a row to become ready fetches for the rows ahead meanwhile.
  *
  * A picture the kernel cannot serve is marked in its job (pad[1] = 1) and reconstructed by the band kernel, which
  * the host launches behind this one (recon.cu).
@@ -24,24 +27,22 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "recon.h"
 #include "row_core.h"
 #include "recon_dev.cuh"
 
 #ifndef HVQM4_ROW_WORK_WARPS
-#define HVQM4_ROW_WORK_WARPS 20
-#endif
-#ifndef HVQM4_ROW_FETCH_WARPS
-#define HVQM4_ROW_FETCH_WARPS 3
+#define HVQM4_ROW_WORK_WARPS 22
 #endif
 
 namespace {
 
 constexpr int kWorkWarps = HVQM4_ROW_WORK_WARPS;
-constexpr int kFetchWarps = HVQM4_ROW_FETCH_WARPS;
-constexpr int kThreads = (1 + kFetchWarps + kWorkWarps) * 32;
+constexpr int kThreads = (2 + kWorkWarps) * 32;
 constexpr long long kTimeoutCycles = 4000000000ll;    /* ~2 s: a wait that long is a bug; everybody leaves */
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -72,6 +73,14 @@ __device__ __forceinline__ bool mbar_try(unsigned long long *bar, uint32_t parit
                  : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+/* suspends the warp (no issue slots) until the phase completes or about `ns` nanoseconds have passed */
+__device__ __forceinline__ bool mbar_try_for(unsigned long long *bar, uint32_t parity, uint32_t ns)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
 /* false: the CTA is aborting (some wait timed out) */
 __device__ __forceinline__ bool mbar_wait(RowCtl &ctl, unsigned long long *bar, uint32_t parity)
 {
@@ -100,19 +109,7 @@ __device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-/* at most n of the most recent store groups may still be reading shared memory */
-__device__ __forceinline__ void bulk_wait_read(int n)
-{
-    switch (n)
-    {
-    case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
-    case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
-    case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
-    case 3: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
-    case 4: asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory"); break;
-    default: asm volatile("cp.async.bulk.wait_group.read 5;" ::: "memory"); break;
-    }
-}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 /* tensor copies: the box starts at a multiple of 16 bytes in x (any other x is an illegal instruction on B200) */
@@ -126,6 +123,21 @@ __device__ __forceinline__ void tma_box_4d(uint32_t dst, const CUtensorMap *map,
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(dst), "l"(map), "r"(smem_addr(bar)), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
+
+/* HVQM4_ROW_TRACE (compile-time, tuning builds only): cycles every role of CTA 0 spends waiting and working,
+   summed per role into a global array that hvqm4_row_trace_dump() prints */
+#ifdef HVQM4_ROW_TRACE
+enum { TR_SEQ_LOOP, TR_SEQ_IDLE, TR_SEQ_RETIRE, TR_SEQ_RELEASE, TR_SEQ_REQUEST, TR_SEQ_RING_FULL, TR_FE_WAIT, TR_FE_CLASSIFY, TR_FE_ISSUE, TR_WK_WAIT, TR_WK_TASKS, TR_WK_TICKETS,
+       TR_WK_NTASKS, TR_SETUP, TR_ROWS, TR_N };
+__device__ unsigned long long g_trace[TR_N];
+#define TR_T0() const long long tr_t0 = clock64()
+#define TR_ADD(k) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd(&g_trace[k], (unsigned long long)(clock64() - tr_t0)); } while (0)
+#define TR_COUNT(k, n) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd(&g_trace[k], (unsigned long long)(n)); } while (0)
+#else
+#define TR_T0() do { } while (0)
+#define TR_ADD(k) do { } while (0)
+#define TR_COUNT(k, n) do { } while (0)
+#endif
 
 struct RowArgs
 {
@@ -141,84 +153,35 @@ __device__ __forceinline__ RowSlotMeta &meta_of(const RowGeom &g, uint32_t slot)
     return *reinterpret_cast<RowSlotMeta *>(rc_smem + g.off_slot0 + slot * g.slot_bytes + g.s_meta);
 }
 
-/* ---- sequencer warp ---------------------------------------------------------------------------- */
-__device__ bool sequencer(const RowGeom &g, const ReconView &v, RowCtl &ctl, const RowArgs &a)
+/* ---- request warp: symbol slices, ring space, `go` ------------------------------------------------- */
+__device__ bool requester(const RowGeom &g, const ReconView &v, RowCtl &ctl, const RowArgs &a)
 {
     const int lane = threadIdx.x & 31;
     const int n = a.n;
-    int ki = 0, kc = 0, ks = 0;            /* next row to request, to release to the fetch warps, to retire */
-    RwRing ring = {0, 0, 0};
-    bool planned = false;
-    uint32_t n_patch = 0;
+    int ki = 0, kc = 0;                    /* next row to request, to release to the fetch tasks */
+    RwRing ring = {0};
+    uint32_t tail = 0, freed = 0;          /* ring offset up to which patches are free again: the first `freed` rows are done */
+    uint32_t *ring_ends = ctl.ring_ends;
+    bool counted = false;
+    uint32_t n_inter = 0;
     long long idle_since = 0;
-    while (ks < n)
+    TR_T0();
+    while (kc < n)
     {
         bool progressed = false;
-        /* retire: store the tile of the oldest row once every work warp is done with it */
-        if (ks < kc)
+        const uint32_t retired = ctl.retired;
+        /* patch space is free as soon as the work warps are done with a row (its tile may still be on its way out) */
+        while ((int)freed < kc)
         {
-            const uint32_t seq = a.seq0 + (uint32_t)ks, slot = slot_of(g, seq);
-            if (mbar_test(&ctl.bar_done[slot], parity_of(g, seq)))
-            {
-                const uint32_t slot_off = g.off_slot0 + slot * g.slot_bytes;
-                const RowSlotMeta &m = meta_of(g, slot);
-                if (lane == 0)
-                {
-                    const uint32_t tile = smem_addr(rc_smem + slot_off + g.s_tile);
-                    const uint32_t wy = (uint32_t)g.width, wc = wy / 2;
-                    const int row = a.r0 + ks;
-                    uint8_t *py = a.present + (size_t)row * g.tile_y_bytes;
-                    uint8_t *pu = a.present + (size_t)wy * g.height + (size_t)row * g.tile_c_bytes;
-                    uint8_t *pv = pu + (size_t)wc * (g.height / 2);
-                    bulk_store(py, tile, g.tile_y_bytes);
-                    bulk_store(pu, tile + g.tile_y_bytes, g.tile_c_bytes);
-                    bulk_store(pv, tile + g.tile_y_bytes + g.tile_c_bytes, g.tile_c_bytes);
-                    bulk_commit();
-                }
-                rw_ring_retire(ring, m.ring_end);
-                ++ks;
-                progressed = true;
-            }
+            const uint32_t dseq = a.seq0 + freed, dslot = slot_of(g, dseq);
+            if (!mbar_test(&ctl.bar_done[dslot], parity_of(g, dseq))) break;
+            tail = ring_ends[dslot];
+            ++freed;
         }
-        /* release: the oldest requested row whose symbol slices have landed gets its patch plan and ring space */
-        if (kc < ki)
+        /* request: the next row's symbol slices, as soon as the row that used the slot before has been stored */
+        if (ki < n && ki < (int)retired + g.n_slots)
         {
-            const uint32_t seq = a.seq0 + (uint32_t)kc, slot = slot_of(g, seq);
-            if (planned || mbar_test(&ctl.bar_sym[slot], parity_of(g, seq)))
-            {
-                const uint32_t slot_off = g.off_slot0 + slot * g.slot_bytes;
-                RowSlotMeta &m = meta_of(g, slot);
-                if (!planned)
-                {
-                    int bad = 0;
-                    n_patch = rw_plan_patches(g, v, ctl, slot_off, m, lane, &bad);
-                    if (bad && lane == 0) ctl.unsupported = 1;
-                    planned = true;
-                }
-                const uint32_t pos = rw_ring_alloc(ring, g.ring_bytes, n_patch * RW_PATCH_BYTES);
-                if (pos != 0xFFFFFFFFu)
-                {
-                    if (lane == 0)
-                    {
-                        m.patch_base = g.off_ring + pos;
-                        m.n_patch = n_patch;
-                        m.ring_end = ring.head;
-                        /* the tile of the row that used this slot before must have left shared memory: its store is
-                           followed by those of the rows retired since */
-                        if (seq >= (uint32_t)g.n_slots) bulk_wait_read(ks - 1 - kc + g.n_slots);
-                    }
-                    __syncwarp();
-                    __threadfence_block();
-                    if (lane == 0) mbar_arrive(&ctl.bar_go[slot]);
-                    planned = false;
-                    ++kc;
-                    progressed = true;
-                }
-            }
-        }
-        /* request: the next row's symbol slices */
-        if (ki < n && ki < ks + g.n_slots)
-        {
+            TR_T0();
             const uint32_t seq = a.seq0 + (uint32_t)ki, slot = slot_of(g, seq);
             const uint32_t slot_off = g.off_slot0 + slot * g.slot_bytes;
             RowSlotMeta &m = meta_of(g, slot);
@@ -232,6 +195,45 @@ __device__ bool sequencer(const RowGeom &g, const ReconView &v, RowCtl &ctl, con
             if (k.bytes) bulk_load(smem_addr(rc_smem + k.dst_off), v.blob + k.src_off, k.bytes, &ctl.bar_sym[slot]);
             ++ki;
             progressed = true;
+            TR_ADD(TR_SEQ_REQUEST);
+        }
+        /* release: the oldest requested row whose symbol slices have landed gets ring space for its patches */
+        if (kc < ki)
+        {
+            TR_T0();
+            const uint32_t seq = a.seq0 + (uint32_t)kc, slot = slot_of(g, seq);
+            if (counted || mbar_test(&ctl.bar_sym[slot], parity_of(g, seq)))
+            {
+                RowSlotMeta &m = meta_of(g, slot);
+                if (!counted)
+                {
+                    n_inter = rw_count_inter(g, v, m, lane);
+                    counted = true;
+                }
+                const uint32_t live = (uint32_t)kc - freed;
+                if (!live) ring.head = tail = 0;
+                const uint32_t pos = rw_ring_alloc(ring, g.ring_bytes, n_inter * RW_PATCH_BYTES, live, tail);
+                if (pos != 0xFFFFFFFFu)
+                {
+                    if (lane == 0)
+                    {
+                        m.patch_base = g.off_ring + pos;
+                        m.n_patch = n_inter;
+                        m.ring_end = ring.head;
+                        ring_ends[slot] = ring.head;
+                        m.ticket = m.fticket = m.patch_count = 0;
+                        m.n_list[0] = m.n_list[1] = m.n_list[2] = 0;
+                    }
+                    __syncwarp();
+                    __threadfence_block();
+                    if (lane == 0) mbar_arrive(&ctl.bar_go[slot]);
+                    counted = false;
+                    ++kc;
+                    progressed = true;
+                }
+                else TR_COUNT(TR_SEQ_RING_FULL, 1);
+            }
+            TR_ADD(TR_SEQ_RELEASE);
         }
         if (progressed) idle_since = 0;
         else
@@ -244,68 +246,140 @@ __device__ bool sequencer(const RowGeom &g, const ReconView &v, RowCtl &ctl, con
                 *reinterpret_cast<volatile uint32_t *>(&ctl.abort_flag) = 1;
                 return false;
             }
-            __nanosleep(20);
-        }
-    }
-    return true;
-}
-
-/* ---- fetch warps ------------------------------------------------------------------------------- */
-__device__ bool fetcher(const RowGeom &g, const ReconView &v, RowCtl &ctl, const RowArgs &a, int f, const CUtensorMap *map_y, const CUtensorMap *map_c)
-{
-    const int lane = threadIdx.x & 31;
-    for (int k = 0; k < a.n; ++k)
-    {
-        const uint32_t seq = a.seq0 + (uint32_t)k;
-        if ((int)(seq % (uint32_t)kFetchWarps) != f) continue;
-        const uint32_t slot = slot_of(g, seq), slot_off = g.off_slot0 + slot * g.slot_bytes;
-        if (!mbar_wait(ctl, &ctl.bar_go[slot], parity_of(g, seq))) return false;
-        RowSlotMeta &m = meta_of(g, slot);
-        rw_classify_row(g, v, ctl, a.r0 + k, slot_off, m, lane);
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_expect_tx(&ctl.bar_ready[slot], m.n_patch * RW_PATCH_TX);
-        __syncwarp();
-        if (m.n_patch)
-        {
-            const uint16_t *poff = reinterpret_cast<const uint16_t *>(rc_smem + slot_off + g.s_poff);
-            const uint32_t *mv = reinterpret_cast<const uint32_t *>(rc_smem + m.p_mv);
-            const uint8_t *tags = rc_smem + m.p_type[0] + g.stride[0] + 1;
-            for (int mx = lane; mx < g.mcb_w; mx += 32)
             {
-                const uint32_t po = poff[mx];
-                if (po == RW_NO_PATCH) continue;
-                int ref, xl, yl, xc, yc, bad;
-                rw_patch_box(v, tags[2 * mx], mv[mx], ref, xl, yl, xc, yc, bad);
-                const uint32_t dst = smem_addr(rc_smem + m.patch_base + po * RW_BOX_W);
-                const int z = ctl.z[ref == 2 ? 1 : 0];
-                tma_box_3d(dst, map_y, &ctl.bar_ready[slot], xl, yl, z);
-                tma_box_4d(dst + RW_PATCH_C_OFF, map_c, &ctl.bar_ready[slot], xc, yc, 0, z);
+                TR_T0();
+                __nanosleep(200);
+                TR_ADD(TR_SEQ_IDLE);
             }
         }
     }
+    TR_ADD(TR_SEQ_LOOP);
+    TR_COUNT(TR_ROWS, n);
     return true;
 }
 
-/* ---- work warps -------------------------------------------------------------------------------- */
-__device__ bool worker(const RowGeom &g, const ReconView &v, RowCtl &ctl, const RowArgs &a)
+/* ---- retire warp: finished tiles leave with three bulk stores of whole picture rows ------------------ */
+__device__ bool retirer(const RowGeom &g, RowCtl &ctl, const RowArgs &a)
 {
     const int lane = threadIdx.x & 31;
+    for (int ks = 0; ks < a.n; ++ks)
+    {
+        const uint32_t seq = a.seq0 + (uint32_t)ks, slot = slot_of(g, seq);
+        if (!mbar_wait(ctl, &ctl.bar_done[slot], parity_of(g, seq))) return false;
+        TR_T0();
+        if (lane == 0)
+        {
+            const uint32_t tile = smem_addr(rc_smem + g.off_slot0 + slot * g.slot_bytes + g.s_tile);
+            const uint32_t wy = (uint32_t)g.width, wc = wy / 2;
+            const int row = a.r0 + ks;
+            uint8_t *py = a.present + (size_t)row * g.tile_y_bytes;
+            uint8_t *pu = a.present + (size_t)wy * g.height + (size_t)row * g.tile_c_bytes;
+            uint8_t *pv = pu + (size_t)wc * (g.height / 2);
+            bulk_store(py, tile, g.tile_y_bytes);
+            bulk_store(pu, tile + g.tile_y_bytes, g.tile_c_bytes);
+            bulk_store(pv, tile + g.tile_y_bytes + g.tile_c_bytes, g.tile_c_bytes);
+            bulk_commit();
+            bulk_wait_read();                 /* the tile has left shared memory: the slot may be used again */
+            __threadfence_block();
+            ctl.retired = (uint32_t)ks + 1u;
+        }
+        __syncwarp();
+        TR_ADD(TR_SEQ_RETIRE);
+    }
+    return true;
+}
+
+/* ---- work warps: fetch tasks of the rows ahead, then the row's own tasks --------------------------------- */
+__device__ __forceinline__ void fetch_task(const RowGeom &g, const ReconView &v, RowCtl &ctl, int row, int grp, uint32_t slot, const CUtensorMap *map_y,
+                                           const CUtensorMap *map_c)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t slot_off = g.off_slot0 + slot * g.slot_bytes;
+    RowSlotMeta &m = meta_of(g, slot);
+    RwBox box;
+    uint32_t n;
+    {
+        TR_T0();
+        n = rw_fetch_group(g, v, ctl, row, grp, slot_off, m, lane, box);
+        __threadfence_block();
+        __syncwarp();
+        TR_ADD(TR_FE_CLASSIFY);
+    }
+    TR_T0();
+    if (lane == 0) mbar_arrive_expect_tx(&ctl.bar_ready[slot], n * RW_PATCH_TX);
+    __syncwarp();
+    if (box.dst)
+    {
+        const uint32_t dst = smem_addr(rc_smem + box.dst);
+        if (!box.chroma) tma_box_3d(dst, map_y, &ctl.bar_ready[slot], box.x, box.y, box.z);
+        else tma_box_4d(dst, map_c, &ctl.bar_ready[slot], box.x, box.y, 0, box.z);
+    }
+    __syncwarp();
+    TR_ADD(TR_FE_ISSUE);
+}
+
+__device__ bool worker(const RowGeom &g, const ReconView &v, RowCtl &ctl, const RowArgs &a, const CUtensorMap *map_y, const CUtensorMap *map_c)
+{
+    const int lane = threadIdx.x & 31;
+    int f = 0;        /* first row that may still have fetch tasks to hand out */
     for (int k = 0; k < a.n; ++k)
     {
         const uint32_t seq = a.seq0 + (uint32_t)k, slot = slot_of(g, seq), slot_off = g.off_slot0 + slot * g.slot_bytes;
-        if (!mbar_wait(ctl, &ctl.bar_ready[slot], parity_of(g, seq))) return false;
         RowSlotMeta &m = meta_of(g, slot);
+        if (f < k) f = k;
+        const int f_end = k + g.n_slots < a.n ? k + g.n_slots : a.n;
+        /* Fetch tasks come first, whenever a warp looks for work: they are the head of the latency chain of a row
+           (sort, tensor copies in flight, then its work tasks).  Rows [k, k + n_slots) can have been given `go`. */
+        auto fetch_ahead = [&]() {
+            while (f < f_end)
+            {
+                const uint32_t fseq = a.seq0 + (uint32_t)f, fslot = slot_of(g, fseq);
+                if (!mbar_test(&ctl.bar_go[fslot], parity_of(g, fseq))) break;
+                uint32_t t = 0;
+                if (lane == 0) t = atomicAdd(&meta_of(g, fslot).fticket, 1u);
+                t = __shfl_sync(0xFFFFFFFFu, t, 0);
+                if (t >= (uint32_t)g.n_groups) { ++f; continue; }
+                fetch_task(g, v, ctl, a.r0 + f, (int)t, fslot, map_y, map_c);
+            }
+        };
+        {
+            TR_T0();
+            const long long t_start = clock64();
+            for (;;)
+            {
+                fetch_ahead();
+                /* asleep until the row is ready, with a look at the rows ahead now and then: a warp that polls takes
+                   issue slots from the warps that work (22 polling warps: fetch tasks ran at 30 cycles per instruction) */
+                if (mbar_try_for(&ctl.bar_ready[slot], parity_of(g, seq), 2000u)) break;
+                if (*reinterpret_cast<volatile uint32_t *>(&ctl.abort_flag)) return false;
+                if (clock64() - t_start > kTimeoutCycles)
+                {
+                    *reinterpret_cast<volatile uint32_t *>(&ctl.abort_flag) = 1;
+                    return false;
+                }
+            }
+            TR_ADD(TR_WK_WAIT);
+        }
         const RowWork w = {&g, &v, &m, slot_off};
-        const uint32_t n_tasks = m.t_end[RW_TASK_CLASSES - 1];
+        uint32_t t_end[RW_TASK_CLASSES];
+        rw_task_ends(m, t_end);
+        const uint32_t n_tasks = t_end[RW_TASK_CLASSES - 1];
         for (;;)
         {
+            fetch_ahead();
             uint32_t t = 0;
-            if (lane == 0) t = atomicAdd(&m.ticket, 1u);
-            t = __shfl_sync(0xFFFFFFFFu, t, 0);
+            {
+                TR_T0();
+                if (lane == 0) t = atomicAdd(&m.ticket, 1u);
+                t = __shfl_sync(0xFFFFFFFFu, t, 0);
+                TR_ADD(TR_WK_TICKETS);
+            }
             if (t >= n_tasks) break;
-            rw_run_task(w, t, lane);
+            TR_T0();
+            rw_run_task(w, t_end, t, lane);
             __syncwarp();
+            TR_ADD(TR_WK_TASKS);
+            TR_COUNT(TR_WK_NTASKS, 1);
         }
         fence_async_smem();      /* this lane's tile writes -> visible to the bulk store */
         __syncwarp();
@@ -327,7 +401,7 @@ recon_row_kernel(ReconJob *__restrict__ jobs, int n_jobs, const __grid_constant_
         {
             mbar_init(&ctl.bar_sym[s], 1);
             mbar_init(&ctl.bar_go[s], 1);
-            mbar_init(&ctl.bar_ready[s], 1);
+            mbar_init(&ctl.bar_ready[s], (uint32_t)g.n_groups);      /* one arrival (with its patch bytes) per fetch task */
             mbar_init(&ctl.bar_done[s], kWorkWarps);
         }
         ctl.abort_flag = 0;
@@ -346,10 +420,12 @@ recon_row_kernel(ReconJob *__restrict__ jobs, int n_jobs, const __grid_constant_
         const int r1 = (int)((long long)g.mcb_h < r0 + (R1 - R) ? (long long)g.mcb_h : r0 + (R1 - R));
         R += r1 - r0;
         __syncthreads();        /* the previous segment is finished by every role */
+        TR_T0();
         if (tid == 0)
         {
             load_view(vw, jobs[job]);
             ctl.unsupported = 0;
+            ctl.retired = 0;
             ctl.pad = (int32_t)jobs[job].pad[1];        /* one read for the whole CTA: another CTA may be marking the picture */
         }
         __syncthreads();
@@ -368,6 +444,7 @@ recon_row_kernel(ReconJob *__restrict__ jobs, int n_jobs, const __grid_constant_
             ctl.bf[cls][r] = __ldg(v.bands + cls * nb1 + r);
         }
         if (v.has_nest) nest_stage_begin<kThreads>(v, rc_smem + g.off_ring);
+        if (tid >= 32 && tid < 32 + 7) rw_sym_table(g, v, ctl, tid - 32);
         if (tid == 0)
         {
             ctl.is_bpic = __ldg(v.blob + offsetof(SymHeader, pic_type)) == SYM_PIC_B;
@@ -394,18 +471,19 @@ recon_row_kernel(ReconJob *__restrict__ jobs, int n_jobs, const __grid_constant_
         for (int r = r0 + tid; r < r1; r += kThreads)
             if (!rw_row_fits(ctl, r)) ctl.unsupported = 1;
         __syncthreads();
+        if (tid == 0) TR_ADD(TR_SETUP);
         if (!ctl.unsupported)
         {
             const RowArgs a = {r0, r1 - r0, seq, v.present};
-            if (warp == 0) ok = sequencer(g, v, ctl, a);
-            else if (warp <= kFetchWarps) ok = fetcher(g, v, ctl, a, warp - 1, &map_y, &map_c);
-            else ok = worker(g, v, ctl, a);
+            if (warp == 0) ok = requester(g, v, ctl, a);
+            else if (warp == 1) ok = retirer(g, ctl, a);
+            else ok = worker(g, v, ctl, a, &map_y, &map_c);
             seq += (uint32_t)(r1 - r0);
             __syncthreads();
         }
         if (ctl.unsupported && tid == 0) jobs[job].pad[1] = 1;
     }
-    if (warp == 0 && lane == 0) bulk_wait_all();      /* the last tiles have reached the picture */
+    if (warp == 1 && lane == 0) bulk_wait_all();      /* the last tiles have reached the picture */
     if (!ok && lane == 0) atomicOr(err, 1u);
 }
 
@@ -523,6 +601,21 @@ extern "C" int hvqm4_row_launch(ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb
                                                                         s->count, g_err);
     return (int)cudaGetLastError();
 }
+
+#ifdef HVQM4_ROW_TRACE
+extern "C" __attribute__((visibility("default"))) void hvqm4_row_trace_dump(void)
+{
+    unsigned long long h[TR_N];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h, g_trace, sizeof h);
+    static const char *names[TR_N] = {"seq loop", "seq idle", "seq retire", "seq release", "seq request", "seq ring-full events", "fetch wait", "fetch classify", "fetch issue",
+                                      "work wait", "work tasks", "work tickets", "work n_tasks", "setup", "rows"};
+    const double rows = (double)(h[TR_ROWS] ? h[TR_ROWS] : 1);
+    for (int i = 0; i < TR_N; ++i) fprintf(stderr, "row trace: %-22s %14llu  %10.1f per row\n", names[i], h[i], (double)h[i] / rows);
+    memset(h, 0, sizeof h);
+    cudaMemcpyToSymbol(g_trace, h, sizeof h);
+}
+#endif
 
 /* nonzero if a CTA of the row kernel ever gave up waiting (diagnostics; synchronises the device) */
 extern "C" int hvqm4_row_errors(void)

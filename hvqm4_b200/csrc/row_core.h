@@ -24,8 +24,12 @@
  *   Only the window gathers of predicted-AOT bases (h4m:734-773) still read the reference luma with per-lane
  *   loads: a 70 x 38 window per macroblock is 30 x the bytes its bases touch (tools/ubench/tma_box.cu).
  *
- *   Roles (row.cu): a SEQUENCER warp requests symbol slices, allocates ring space and retires rows; FETCH warps
- *   classify a row and issue its patch copies; WORK warps take tasks from a row's ticket counter.
+ *   Roles (row.cu): a REQUEST warp asks for symbol slices and allocates ring space, a RETIRE warp stores finished
+ *   tiles; everything else is a task taken from a row's ticket counters by the WORK warps: FETCH tasks (one per 16
+ *   macroblocks of a row: sort their blocks into the lists, issue their patch copies) for the rows ahead, then the
+ *   row's work tasks.  A first version with one warp per role measured 13 000 cycles of SERIAL work per row (one
+ *   warp issues an instruction every 5-8 cycles; a tensor copy costs its issuing warp ~86 cycles): nothing that
+ *   grows with the row's content may sit in a single warp.
  *
  *   A macroblock whose prediction is not inside its plane (the reference addresses linearly, such vectors wrap
  *   around picture rows, h4m:1344,1897; a tensor copy would fill with zeros instead) marks the picture for the
@@ -57,6 +61,7 @@ struct RowGeom
     int width, height, mcb_w, mcb_h;
     int bw[3], stride[3];        /* blocks per block row, bordered map pitch (plane 0, 1, 2) */
     int n_slots;
+    int n_groups;                /* fetch tasks per row: groups of 16 macroblocks */
     uint32_t off_ctl, off_slot0, slot_bytes, off_ring, ring_bytes, smem_bytes;
     /* inside a slot */
     uint32_t s_meta, s_type[3], s_dc[3], s_mv, s_desc, s_poff, s_list[RW_LISTS], s_tile;
@@ -72,6 +77,9 @@ struct RowCtl
     int32_t unsupported;                    /* the picture is left to the band kernel */
     int32_t z[2];                           /* surface index of past / future inside the registered slab; -1 = not in it */
     int32_t is_bpic, pad;                   /* pad: the job was already marked when the segment started */
+    volatile uint32_t retired;              /* rows of the segment the retire warp has stored */
+    uint32_t ring_ends[RW_MAX_SLOTS];       /* ring head after the allocation of the row in slot s (request warp) */
+    uint32_t sym_base[7], sym_step[7], sym_span[7], sym_region[7];   /* symbol slices 0-6 of row r: blob bytes [base + r * step, + span) */
     uint32_t bf[SYM_REC_CLASSES][RW_MAX_ROWS + 1];        /* first chunk of (class, macroblock row) */
     uint32_t rec_off[SYM_REC_CLASSES][RW_MAX_ROWS + 1];   /* first record word of (class, macroblock row) */
 };
@@ -79,14 +87,15 @@ struct RowCtl
 /* what the pipeline publishes for a row (lives in the row's slot) */
 struct RowSlotMeta
 {
-    uint32_t ticket;                         /* next task (work warps fetch-and-add) */
-    uint32_t t_end[RW_TASK_CLASSES];         /* tasks [t_end[k-1], t_end[k]) belong to class k */
+    uint32_t ticket;                         /* next work task (work warps fetch-and-add) */
+    uint32_t fticket;                        /* next fetch task */
+    uint32_t patch_count;                    /* patches handed out so far (fetch tasks fetch-and-add) */
     uint32_t n_rec[SYM_REC_CLASSES], rec_lo[SYM_REC_CLASSES];
-    uint32_t n_list[RW_LISTS];
+    uint32_t n_list[RW_LISTS];               /* list lengths (fetch tasks fetch-and-add their share) */
     uint32_t p_type[3], p_dc[3];             /* shared-memory offset of the bordered map row above the row's first block row */
     uint32_t p_mv, p_desc[SYM_REC_CLASSES];
     uint32_t patch_base;                     /* shared-memory offset of the row's patches */
-    uint32_t n_patch;
+    uint32_t n_patch;                        /* ring space of the row in patches: its inter macroblocks */
     uint32_t ring_end;                       /* ring head after this row's allocation (the tail once it retires) */
     int32_t row;                             /* macroblock row inside the picture */
 };
@@ -95,6 +104,7 @@ RC_HD int rw_make_geom(RowGeom &g, int width, int height, uint32_t smem_limit)
 {
     if (width <= 0 || height <= 0 || (width & 31) || (height & 7) || width > 2048) return 0;
     g.width = width; g.height = height; g.mcb_w = width / 8; g.mcb_h = height / 8;
+    g.n_groups = (g.mcb_w + 15) / 16;
     if (g.mcb_h > RW_MAX_ROWS) return 0;
     for (int p = 0; p < 3; ++p)
     {
@@ -134,28 +144,42 @@ RC_HD int rw_make_geom(RowGeom &g, int width, int height, uint32_t smem_limit)
 /* ---- symbol slices of a row ------------------------------------------------------------------ */
 #define RW_N_SYM_COPIES 10
 
-/* copy `id` (0-2 type rows, 3-5 DC rows, 6 vectors, 7-9 chunk descriptors) of macroblock row `row`; also fills the
-   matching pointer of the slot's meta (lane id does both, the fields are disjoint) */
-RC_HD SwCopy rw_sym_copy(const RowGeom &g, const ReconView &v, const RowCtl &c, int row, int id, uint32_t slot_off, RowSlotMeta &m)
+/* per segment: where slices 0-6 (0-2 type rows, 3-5 DC rows, 6 vectors) of row r lie in the blob and in a slot */
+RC_HD void rw_sym_table(const RowGeom &g, const ReconView &v, RowCtl &c, int id)
 {
-    SwCopy k = {SW_SRC_BLOB, 0, 0, 0};
-    uint32_t lo = 0, hi = 0, region = 0;
+    uint32_t base = 0, step = 0, span = 0, region = 0;
     if (id < 6)
     {
         const int p = id % 3;
-        const int by0 = p ? row : 2 * row, nrows = (p ? 1 : 2) + 2;
-        lo = (id < 3 ? rc_pick3(v.off_type, p) : rc_pick3(v.off_dc, p)) + (uint32_t)(by0 * g.stride[p]);   /* bordered row by0 = block row by0 - 1 */
-        hi = lo + (uint32_t)(nrows * g.stride[p]);
+        /* bordered row by0 = block row by0 - 1: the rows of the macroblock row plus one above and one below */
+        base = id < 3 ? rc_pick3(v.off_type, p) : rc_pick3(v.off_dc, p);
+        step = (uint32_t)((p ? 1 : 2) * g.stride[p]);
+        span = (uint32_t)(((p ? 1 : 2) + 2) * g.stride[p]);
         region = id < 3 ? g.s_type[p] : g.s_dc[p];
     }
-    else if (id == 6)
+    else
     {
         region = g.s_mv;
         if (!v.is_ipic)
         {
-            lo = v.off_mv + (uint32_t)(row * g.mcb_w * 4);
-            hi = lo + (uint32_t)(g.mcb_w * 4);
+            base = v.off_mv;
+            step = span = (uint32_t)(g.mcb_w * 4);
         }
+    }
+    c.sym_base[id] = base; c.sym_step[id] = step; c.sym_span[id] = span; c.sym_region[id] = region;
+}
+
+/* copy `id` (0-6 as above, 7-9 chunk descriptors) of macroblock row `row`; also fills the matching pointer of the
+   slot's meta (lane id does both, the fields are disjoint) */
+RC_HD SwCopy rw_sym_copy(const RowGeom &g, const ReconView &v, const RowCtl &c, int row, int id, uint32_t slot_off, RowSlotMeta &m)
+{
+    SwCopy k = {SW_SRC_BLOB, 0, 0, 0};
+    uint32_t lo, hi, region;
+    if (id < 7)
+    {
+        lo = c.sym_base[id] + (uint32_t)row * c.sym_step[id];
+        hi = lo + c.sym_span[id];
+        region = c.sym_region[id];
     }
     else
     {
@@ -215,136 +239,214 @@ RC_HD void rw_patch_box(const ReconView &v, uint32_t tag, uint32_t mvw, int &ref
     if (bad) ref = 0;
 }
 
-/* Sequencer, once a row's symbol slice has landed: which macroblocks get a patch and where (offset in units of
-   RW_BOX_W bytes from the row's patch base, RW_NO_PATCH = none).  Warp-collective on the GPU.  Returns the number
-   of patches; *bad is set if some macroblock cannot be served. */
-RC_HD uint32_t rw_plan_patches(const RowGeom &g, const ReconView &v, const RowCtl &c, uint32_t slot_off, const RowSlotMeta &m, int lane, int *bad_any)
+/* the same with the rules of the picture applied: what a fetch task really asks for */
+RC_HD void rw_patch_of(const ReconView &v, const RowCtl &c, uint32_t tag, uint32_t mvw, int &ref, int &xl, int &yl, int &xc, int &yc, int &bad)
 {
-    uint16_t *poff = reinterpret_cast<uint16_t *>(SW_SMEM(slot_off + g.s_poff));
+    rw_patch_box(v, tag, mvw, ref, xl, yl, xc, yc, bad);
+    if (ref == 2 && !c.is_bpic) { bad = 1; ref = 0; }      /* P picture (h4m:2058-2061): `future` is the picture itself */
+    if (ref && c.z[ref - 1] < 0) { bad = 1; ref = 0; }     /* the reference is not a surface of the registered slab */
+}
+
+/* Request warp, once a row's symbol slice has landed: the ring space the row may need = its inter macroblocks (a
+   poisoned one wastes its place).  Warp-collective on the GPU. */
+RC_HD uint32_t rw_count_inter(const RowGeom &g, const ReconView &v, const RowSlotMeta &m, int lane)
+{
+    if (v.is_ipic) return 0;
+    const uint8_t *tags = SW_SMEM(m.p_type[0]) + g.stride[0] + 1;
     uint32_t n = 0;
-    int bad_acc = 0;
     for (int mx0 = 0; mx0 < g.mcb_w; mx0 += SW_LANES)
     {
         const int mx = mx0 + lane;
-        int ref = 0, xl, yl, xc, yc, bad = 0;
-        if (mx < g.mcb_w && !v.is_ipic)
-        {
-            const uint32_t tag = *(SW_SMEM(m.p_type[0]) + g.stride[0] + 2 * mx + 1);
-            const uint32_t mvw = reinterpret_cast<const uint32_t *>(SW_SMEM(m.p_mv))[mx];
-            rw_patch_box(v, tag, mvw, ref, xl, yl, xc, yc, bad);
-            if (ref == 2 && !c.is_bpic) { bad = 1; ref = 0; }      /* P picture (h4m:2058-2061): `future` is the picture itself */
-            if (ref && c.z[ref - 1] < 0) { bad = 1; ref = 0; }     /* the reference is not a surface of the registered slab */
-        }
-        bad_acc |= bad;
-        const uint32_t bal = sw_ballot(ref != 0);
-        if (mx < g.mcb_w) poff[mx] = ref ? (uint16_t)((n + (uint32_t)SW_POPC(bal & ((1u << lane) - 1u))) * (RW_PATCH_BYTES / RW_BOX_W)) : (uint16_t)RW_NO_PATCH;
-        n += (uint32_t)SW_POPC(bal);
+        n += (uint32_t)SW_POPC(sw_ballot(mx < g.mcb_w && (tags[2 * mx] & 0x60) != 0));
     }
-    *bad_any = (int)sw_ballot(bad_acc != 0);
     return n;
 }
 
-/* Ring allocation (sequencer registers): [tail, head) in ring order is in use; rows retire in order. */
+/* Ring allocation.  The request warp owns the head, the retire warp publishes the tail and the number of retired
+   rows; rows retire in order.  live = rows that hold an allocation, tail = offset up to which the ring is free. */
 struct RwRing
 {
-    uint32_t head, tail, live;    /* live: rows that hold an allocation */
+    uint32_t head;
 };
 
 /* returns the offset inside the ring, or 0xFFFFFFFF if the bytes are not free yet */
-RC_HD uint32_t rw_ring_alloc(RwRing &r, uint32_t cap, uint32_t bytes)
+RC_HD uint32_t rw_ring_alloc(RwRing &r, uint32_t cap, uint32_t bytes, uint32_t live, uint32_t tail)
 {
     bytes = (bytes + 127u) & ~127u;
-    if (!r.live) { r.head = r.tail = 0; }
     uint32_t pos;
-    if (r.head >= r.tail && r.live)
-    {   /* in use: [tail, head); free: [head, cap) and [0, tail) */
-        if (r.head + bytes <= cap) pos = r.head;
-        else if (bytes < r.tail) pos = 0;
-        else return 0xFFFFFFFFu;
-    }
-    else if (!r.live)
-    {
+    if (!live)
+    {   /* nothing in use: start over at the front */
         if (bytes > cap) return 0xFFFFFFFFu;
         pos = 0;
     }
+    else if (r.head >= tail)
+    {   /* in use: [tail, head); free: [head, cap) and [0, tail) */
+        if (r.head + bytes <= cap) pos = r.head;
+        else if (bytes < tail) pos = 0;
+        else return 0xFFFFFFFFu;
+    }
     else
     {   /* wrapped: free is [head, tail) */
-        if (r.head + bytes < r.tail) pos = r.head;
+        if (r.head + bytes < tail) pos = r.head;
         else return 0xFFFFFFFFu;
     }
     r.head = pos + bytes;
-    ++r.live;
     return pos;
 }
-RC_HD void rw_ring_retire(RwRing &r, uint32_t ring_end)
-{
-    r.tail = ring_end;
-    --r.live;
-}
 
-/* ---- classification of a row (fetch warp) ------------------------------------------------------ */
+/* ---- fetch task: one group of 32 macroblocks of a row ------------------------------------------------ */
 
 /* list entry: [8:0] block x, [9] local block row (luma), [11:10] plane */
 RC_HD uint32_t rw_entry(int p, int lrow, int bx) { return (uint32_t)bx | (uint32_t)lrow << 9 | (uint32_t)p << 10; }
 
-/* Builds the three block lists of the row, sums the record counts and sets the task boundaries.  Warp-collective. */
-RC_HD void rw_classify_row(const RowGeom &g, const ReconView &v, const RowCtl &c, int row, uint32_t slot_off, RowSlotMeta &m, int lane)
+/* which list a block with type byte t belongs to; -1: none (it has a record, or nothing to do) */
+RC_HD int rw_block_list(uint32_t t, bool ipic)
 {
-    uint32_t n_list[RW_LISTS] = {0, 0, 0};
+    const uint32_t nib = ipic ? t : (t & 0xF);
+    if (!ipic && (t & 0x60)) return ((t & 0x10) || nib == 0) ? RW_LIST_MC : -1;
+    return nib == 0 ? RW_LIST_W : nib == 8 ? RW_LIST_FLAT : -1;
+}
+
+/* what a lane of a fetch task asks the TMA unit for */
+struct RwBox
+{
+    uint32_t dst;         /* shared-memory offset (128-byte aligned), 0 = nothing to fetch */
+    int chroma;           /* 0: luma box 32 x 9 at (x, y, z); 1: chroma box 32 x 5 x 2 at (x, y, 0, z) */
+    int x, y, z;
+};
+
+#define RW_GROUP_MCBS 16     /* macroblocks per fetch task */
+
+/* Group `grp` (16 macroblocks) of row `row`: sorts the blocks of its macroblocks into the row's lists (ranges
+   reserved with one fetch-and-add per list), gives every macroblock that needs one a patch place (another
+   fetch-and-add), and returns in `box` what the calling lane must fetch: lanes 0-15 the luma box of macroblock
+   16 * grp + lane, lanes 16-31 the chroma box of macroblock 16 * grp + lane - 16.  Group 0 also sums the record
+   counts of the row.  Warp-collective on the GPU; on the CPU (tests/emul) the caller passes lane = 0..31 in turn
+   and the reservations are plain additions, which gives a different but equally valid order inside the lists.
+   Returns the number of patches of the group (GPU: the same in every lane; CPU: 1 or 0 for this lane). */
+RC_HD uint32_t rw_fetch_group(const RowGeom &g, const ReconView &v, RowCtl &c, int row, int grp, uint32_t slot_off, RowSlotMeta &m, int lane, RwBox &box)
+{
+    const bool ipic = v.is_ipic != 0;
     uint16_t *lists[RW_LISTS];
     for (int l = 0; l < RW_LISTS; ++l) lists[l] = reinterpret_cast<uint16_t *>(SW_SMEM(slot_off + g.s_list[l]));
-    const bool ipic = v.is_ipic != 0;
-    for (int br = 0; br < 4; ++br)
-    {   /* block rows: luma upper, luma lower, U, V */
-        const int p = br < 2 ? 0 : br - 1, lrow = br < 2 ? br : 0;
-        const uint8_t *trow = SW_SMEM(m.p_type[p]) + (lrow + 1) * g.stride[p] + 1;
-        for (int x0 = 0; x0 < g.bw[p]; x0 += SW_LANES)
-        {
-            const int bx = x0 + lane;
-            const uint32_t t = bx < g.bw[p] ? trow[bx] : 6u;       /* past the row end: a raw block is nothing to do here */
-            const uint32_t nib = ipic ? t : (t & 0xF);
-            const bool inter = !ipic && (t & 0x60);
-            int l = -1;
-            if (inter) { if ((t & 0x10) || nib == 0) l = RW_LIST_MC; }
-            else l = nib == 0 ? RW_LIST_W : nib == 8 ? RW_LIST_FLAT : -1;
-            const uint32_t e = rw_entry(p, lrow, bx);
+    /* the group's blocks as three rounds of 32: luma upper row, luma lower row, 16 U + 16 V */
+    uint32_t t3[3], e3[3];
+    int l3[3];
 #pragma unroll
-            for (int k = 0; k < RW_LISTS; ++k)
-            {
-                const uint32_t bal = sw_ballot(l == k);
-                if (l == k) lists[k][n_list[k] + (uint32_t)SW_POPC(bal & ((1u << lane) - 1u))] = (uint16_t)e;
-                n_list[k] += (uint32_t)SW_POPC(bal);
-            }
+    for (int r = 0; r < 3; ++r)
+    {
+        const int p = r < 2 ? 0 : 1 + (lane >> 4), lrow = r < 2 ? r : 0;
+        const int bx = p ? RW_GROUP_MCBS * grp + (lane & 15) : 2 * RW_GROUP_MCBS * grp + lane;
+        const bool in_row = bx < g.bw[p];
+        t3[r] = in_row ? *(SW_SMEM(rc_pick3(m.p_type, p)) + (lrow + 1) * g.stride[p] + 1 + bx) : 6u;   /* past the row end: nothing to do */
+        l3[r] = rw_block_list(t3[r], ipic);
+        e3[r] = rw_entry(p, lrow, bx);
+    }
+#if defined(__CUDA_ARCH__)
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t bal[RW_LISTS][3], cnt[RW_LISTS] = {0, 0, 0};
+#pragma unroll
+    for (int l = 0; l < RW_LISTS; ++l)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+        {
+            bal[l][r] = __ballot_sync(0xFFFFFFFFu, l3[r] == l);
+            cnt[l] += (uint32_t)__popc(bal[l][r]);
+        }
+    uint32_t base = 0;
+    if (lane < RW_LISTS) base = atomicAdd(&m.n_list[lane], lane == 0 ? cnt[0] : lane == 1 ? cnt[1] : cnt[2]);
+#pragma unroll
+    for (int l = 0; l < RW_LISTS; ++l)
+    {
+        uint32_t at = __shfl_sync(0xFFFFFFFFu, base, l);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+        {
+            if (l3[r] == l) lists[l][at + (uint32_t)__popc(bal[l][r] & lt)] = (uint16_t)e3[r];
+            at += (uint32_t)__popc(bal[l][r]);
         }
     }
-    uint32_t n_rec[SYM_REC_CLASSES];
-    for (int cls = 0; cls < SYM_REC_CLASSES; ++cls)
+#else
+    for (int r = 0; r < 3; ++r)
+        if (l3[r] >= 0) lists[l3[r]][m.n_list[l3[r]]++] = (uint16_t)e3[r];
+#endif
+    /* patches: both half warps look at the same 16 macroblocks */
+    const int mx = RW_GROUP_MCBS * grp + (lane & 15), half = lane >> 4;
+    int ref = 0, bad = 0, xl = 0, yl = 0, xc = 0, yc = 0;
+    box.dst = 0;
+    box.chroma = half;
+    box.x = box.y = box.z = 0;
+    if (mx < g.mcb_w && !ipic)
     {
-        const uint32_t nd = c.bf[cls][row + 1] - c.bf[cls][row];
-        const uint2 *d = reinterpret_cast<const uint2 *>(SW_SMEM(m.p_desc[cls]));
-        uint32_t sum = 0;
-        for (uint32_t j = (uint32_t)lane; j < nd; j += SW_LANES) sum += d[j].y & 0xFF;
-        n_rec[cls] = sw_lane_sum(sum);
+        const uint32_t tag = *(SW_SMEM(m.p_type[0]) + g.stride[0] + 1 + 2 * mx);
+        const uint32_t mvw = reinterpret_cast<const uint32_t *>(SW_SMEM(m.p_mv))[mx];
+        rw_patch_of(v, c, tag, mvw, ref, xl, yl, xc, yc, bad);
     }
-    if (lane == 0)
+    uint16_t *poff = reinterpret_cast<uint16_t *>(SW_SMEM(slot_off + g.s_poff));
+    uint32_t n, idx;
+#if defined(__CUDA_ARCH__)
+    const uint32_t balp = __ballot_sync(0xFFFFFFFFu, ref != 0) & 0xFFFFu;
+    const bool bad_any = __any_sync(0xFFFFFFFFu, bad != 0);
+    n = (uint32_t)__popc(balp);
+    idx = 0;
+    if (lane == 0 && n) idx = atomicAdd(&m.patch_count, n);
+    idx = __shfl_sync(0xFFFFFFFFu, idx, 0) + (uint32_t)__popc(balp & ((1u << (lane & 15)) - 1u));
+#else
+    const bool bad_any = bad != 0;
+    n = 0;
+    if (half == 0)
     {
+        n = ref != 0;
+        idx = m.patch_count;
+        m.patch_count += n;
+    }
+    else
+        idx = ref ? poff[mx] / (RW_PATCH_BYTES / RW_BOX_W) : 0u;      /* the place lane - 16 has just given it */
+#endif
+    if (mx < g.mcb_w && half == 0) poff[mx] = ref ? (uint16_t)(idx * (RW_PATCH_BYTES / RW_BOX_W)) : (uint16_t)RW_NO_PATCH;
+    if (ref)
+    {
+        box.dst = m.patch_base + idx * RW_PATCH_BYTES + (half ? (uint32_t)RW_PATCH_C_OFF : 0u);
+        box.x = half ? xc : xl;
+        box.y = half ? yc : yl;
+        box.z = c.z[ref - 1];
+    }
+    if (bad_any && lane == 0) c.unsupported = 1;
+    if (grp == 0)
+    {   /* record counts of the row: the chunk descriptors of a class hold them */
         for (int cls = 0; cls < SYM_REC_CLASSES; ++cls)
         {
-            m.n_rec[cls] = n_rec[cls];
-            m.rec_lo[cls] = c.rec_off[cls][row];
+            const uint32_t nd = c.bf[cls][row + 1] - c.bf[cls][row];
+            const uint2 *d = reinterpret_cast<const uint2 *>(SW_SMEM(m.p_desc[cls]));
+            uint32_t sum = 0;
+#if defined(__CUDA_ARCH__)
+            for (uint32_t j = (uint32_t)lane; j < nd; j += 32) sum += d[j].y & 0xFF;
+            sum = sw_lane_sum(sum);
+#else
+            if (lane == 0)
+                for (uint32_t j = 0; j < nd; ++j) sum += d[j].y & 0xFF;
+#endif
+            if (lane == 0)
+            {
+                m.n_rec[cls] = sum;
+                m.rec_lo[cls] = c.rec_off[cls][row];
+            }
         }
-        for (int l = 0; l < RW_LISTS; ++l) m.n_list[l] = n_list[l];
-        uint32_t t = 0;
-        t += (n_rec[SYM_REC_INTER] + 31u) / 32u; m.t_end[RW_T_INTER] = t;
-        t += (n_rec[SYM_REC_INTRA] + 31u) / 32u; m.t_end[RW_T_INTRA] = t;
-        t += (n_list[RW_LIST_MC] + 31u) / 32u;   m.t_end[RW_T_MC] = t;
-        t += (n_list[RW_LIST_W] + 31u) / 32u;    m.t_end[RW_T_W] = t;
-        t += (n_rec[SYM_REC_RAW] + 31u) / 32u;   m.t_end[RW_T_RAW] = t;
-        t += (n_list[RW_LIST_FLAT] + 31u) / 32u; m.t_end[RW_T_FLAT] = t;
-        m.ticket = 0;
-        m.row = row;
+        if (lane == 0) m.row = row;
     }
-    sw_lane_sync();
+    return n;
+}
+
+/* task boundaries of a row once all of its fetch tasks are done: tasks [t_end[k-1], t_end[k]) belong to class k */
+RC_HD void rw_task_ends(const RowSlotMeta &m, uint32_t t_end[RW_TASK_CLASSES])
+{
+    uint32_t t = 0;
+    t += (m.n_rec[SYM_REC_INTER] + 31u) / 32u; t_end[RW_T_INTER] = t;
+    t += (m.n_rec[SYM_REC_INTRA] + 31u) / 32u; t_end[RW_T_INTRA] = t;
+    t += (m.n_list[RW_LIST_MC] + 31u) / 32u;   t_end[RW_T_MC] = t;
+    t += (m.n_list[RW_LIST_W] + 31u) / 32u;    t_end[RW_T_W] = t;
+    t += (m.n_rec[SYM_REC_RAW] + 31u) / 32u;   t_end[RW_T_RAW] = t;
+    t += (m.n_list[RW_LIST_FLAT] + 31u) / 32u; t_end[RW_T_FLAT] = t;
 }
 
 /* ---- work: one list entry or one record per lane ------------------------------------------------ */
@@ -505,7 +607,7 @@ RC_HD void rw_record_lane(const RowWork &w, int cls, uint32_t idx)
         {   /* window origin, h4m:1864-1868; linear addressing like the reference */
             const uint8_t *ref = ((t >> 5) & 3) == 2 ? v.ref[1] : v.ref[0];
             const RwGlobalWindow win = {ref + rx / 2 + (ry / 2 - 16) * v.width - 32, v.width};
-            rc_predicted_aot(v, rows, rec + 1, (int)len - 1, &win);
+            rc_predicted_aot(v, rows, rec + 1, (int)len - 1, win);
         }
     }
     else
@@ -526,15 +628,14 @@ RC_HD void rw_record_lane(const RowWork &w, int cls, uint32_t idx)
 }
 
 /* task t of a row -> what to do */
-RC_HD void rw_run_task(const RowWork &w, uint32_t t, int lane)
+RC_HD void rw_run_task(const RowWork &w, const uint32_t t_end[RW_TASK_CLASSES], uint32_t t, int lane)
 {
-    const RowSlotMeta &m = *w.m;
-    if (t < m.t_end[RW_T_INTER]) rw_record_lane(w, SYM_REC_INTER, t * 32u + (uint32_t)lane);
-    else if (t < m.t_end[RW_T_INTRA]) rw_record_lane(w, SYM_REC_INTRA, (t - m.t_end[RW_T_INTER]) * 32u + (uint32_t)lane);
-    else if (t < m.t_end[RW_T_MC]) rw_list_lane(w, RW_LIST_MC, (t - m.t_end[RW_T_INTRA]) * 32u + (uint32_t)lane);
-    else if (t < m.t_end[RW_T_W]) rw_list_lane(w, RW_LIST_W, (t - m.t_end[RW_T_MC]) * 32u + (uint32_t)lane);
-    else if (t < m.t_end[RW_T_RAW]) rw_record_lane(w, SYM_REC_RAW, (t - m.t_end[RW_T_W]) * 32u + (uint32_t)lane);
-    else rw_list_lane(w, RW_LIST_FLAT, (t - m.t_end[RW_T_RAW]) * 32u + (uint32_t)lane);
+    if (t < t_end[RW_T_INTER]) rw_record_lane(w, SYM_REC_INTER, t * 32u + (uint32_t)lane);
+    else if (t < t_end[RW_T_INTRA]) rw_record_lane(w, SYM_REC_INTRA, (t - t_end[RW_T_INTER]) * 32u + (uint32_t)lane);
+    else if (t < t_end[RW_T_MC]) rw_list_lane(w, RW_LIST_MC, (t - t_end[RW_T_INTRA]) * 32u + (uint32_t)lane);
+    else if (t < t_end[RW_T_W]) rw_list_lane(w, RW_LIST_W, (t - t_end[RW_T_MC]) * 32u + (uint32_t)lane);
+    else if (t < t_end[RW_T_RAW]) rw_record_lane(w, SYM_REC_RAW, (t - t_end[RW_T_W]) * 32u + (uint32_t)lane);
+    else rw_list_lane(w, RW_LIST_FLAT, (t - t_end[RW_T_RAW]) * 32u + (uint32_t)lane);
 }
 
 #endif

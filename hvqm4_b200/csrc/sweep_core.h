@@ -614,7 +614,7 @@ RC_HD void sw_record_lane(const SweepBand &b, int cls, uint32_t idx)
         {   /* window origin, h4m:1864-1868 */
             const uint32_t o = sw_ring_at(b, 0, rx / 2 - 32, ry / 2 - 16);
             const RcRingWindow win = {b.c->ring_off[0], o, (uint32_t)v.width, b.c->ring_bytes[0]};
-            rc_predicted_aot(v, rows, rec + 1, (int)len - 1, &win);
+            rc_predicted_aot(v, rows, rec + 1, (int)len - 1, win);
         }
     }
     else

@@ -2,7 +2,7 @@
  * tests/emul/row_emul.cpp -- TEST INFRASTRUCTURE ONLY.
  *
  * Serial CPU driver for hvqm4_b200/csrc/row_core.h: the row kernel's slot layout, the symbol slices of a row,
- * the patch plan and ring allocation (rows requested as far ahead as slots and ring allow, so that a patch or a
+ * the ring allocation and the fetch tasks (rows requested as far ahead as slots and ring allow, so that a patch or a
  * slot overwritten too early shows up as wrong pixels), the class lists and every task of every row, lane by
  * lane, with memcpy in place of the bulk and tensor copies (boxes filled with zeros outside the plane, like the
  * TMA unit does).  row.cu adds only the copies and the mbarrier pipeline around the same functions.  Never built
@@ -66,16 +66,18 @@ int emul_row_picture(const uint8_t *blob, uint8_t *present, const uint8_t *past,
     c.is_bpic = hd.pic_type == SYM_PIC_B;
     c.z[0] = 0;
     c.z[1] = 1;
+    for (int id = 0; id < 7; ++id) rw_sym_table(g, v, c, id);
     for (int r = 0; r < g.mcb_h; ++r)
         if (!rw_row_fits(c, r)) return 1;
     const int n = g.mcb_h;
     const int pw[3] = {g.width, g.width / 2, g.width / 2}, ph[3] = {g.height, g.height / 2, g.height / 2};
     const size_t plane_off[3] = {0, (size_t)g.width * g.height, (size_t)g.width * g.height + (size_t)pw[1] * ph[1]};
-    int ki = 0, ks = 0, bad_any = 0;
-    RwRing ring = {0, 0, 0};
+    int ki = 0, ks = 0;
+    RwRing ring = {0};
+    uint32_t tail = 0;
     while (ks < n)
     {
-        /* sequencer + fetch warps: rows as far ahead as slots, ring and the look-ahead limit allow */
+        /* request warp + fetch tasks: rows as far ahead as slots, ring and the look-ahead limit allow */
         while (ki < n && ki < ks + g.n_slots && ki < ks + lookahead_limit)
         {
             const uint32_t slot_off = g.off_slot0 + (uint32_t)(ki % g.n_slots) * g.slot_bytes;
@@ -85,42 +87,44 @@ int emul_row_picture(const uint8_t *blob, uint8_t *present, const uint8_t *past,
                 const SwCopy k = rw_sym_copy(g, v, c, ki, id, slot_off, m);
                 if (k.bytes) memcpy(sw_host_smem + k.dst_off, blob + k.src_off, k.bytes);
             }
-            int bad = 0;
-            const uint32_t n_patch = rw_plan_patches(g, v, c, slot_off, m, 0, &bad);
-            bad_any |= bad;
+            const uint32_t n_inter = rw_count_inter(g, v, m, 0);
+            const uint32_t live = (uint32_t)(ki - ks);
             RwRing trial = ring;
-            const uint32_t pos = rw_ring_alloc(trial, g.ring_bytes, n_patch * RW_PATCH_BYTES);
+            uint32_t ttail = tail;
+            if (!live) trial.head = ttail = 0;
+            const uint32_t pos = rw_ring_alloc(trial, g.ring_bytes, n_inter * RW_PATCH_BYTES, live, ttail);
             if (pos == 0xFFFFFFFFu)
             {
                 if (ki == ks) return -22;     /* an empty ring must take any row */
                 break;
             }
             ring = trial;
+            tail = ttail;
             m.patch_base = g.off_ring + pos;
-            m.n_patch = n_patch;
+            m.n_patch = n_inter;
             m.ring_end = ring.head;
-            rw_classify_row(g, v, c, ki, slot_off, m, 0);
-            const uint16_t *poff = reinterpret_cast<const uint16_t *>(sw_host_smem + slot_off + g.s_poff);
-            const uint32_t *mv = reinterpret_cast<const uint32_t *>(sw_host_smem + m.p_mv);
-            const uint8_t *tags = sw_host_smem + m.p_type[0] + g.stride[0] + 1;
+            m.ticket = m.fticket = m.patch_count = 0;
+            m.n_list[0] = m.n_list[1] = m.n_list[2] = 0;
             uint32_t issued = 0;
-            for (int mx = 0; mx < g.mcb_w; ++mx)
-            {
-                if (poff[mx] == RW_NO_PATCH) continue;
-                int ref, xl, yl, xc, yc, bad2;
-                rw_patch_box(v, tags[2 * mx], mv[mx], ref, xl, yl, xc, yc, bad2);
-                if (!ref) return -23;
-                if ((xl & 15) || (xc & 15)) return -24;   /* the TMA unit faults on such a box */
-                if ((m.patch_base + (uint32_t)poff[mx] * RW_BOX_W) & 127u) return -28;   /* ... and on such a destination */
-                const uint8_t *surf = ref == 2 ? future : past;
-                uint8_t *dst = sw_host_smem + m.patch_base + (uint32_t)poff[mx] * RW_BOX_W;
-                if (dst + RW_PATCH_BYTES > sw_host_smem + g.smem_bytes) return -25;
-                box_copy(dst, surf + plane_off[0], pw[0], ph[0], xl, yl, RW_BOX_W, 9);
-                box_copy(dst + RW_PATCH_C_OFF, surf + plane_off[1], pw[1], ph[1], xc, yc, RW_BOX_W, 5);
-                box_copy(dst + RW_PATCH_C_OFF + RW_PATCH_C, surf + plane_off[2], pw[2], ph[2], xc, yc, RW_BOX_W, 5);
-                ++issued;
-            }
-            if (issued != n_patch) return -26;
+            for (int grp = g.n_groups - 1; grp >= 0; --grp)       /* any order of the fetch tasks is valid */
+                for (int lane = 0; lane < 32; ++lane)
+                {
+                    RwBox box;
+                    issued += rw_fetch_group(g, v, c, ki, grp, slot_off, m, lane, box);
+                    if (!box.dst) continue;
+                    if (box.x & 15) return -24;                        /* the TMA unit faults on such a box */
+                    if (box.dst & 127u) return -28;                    /* ... and on such a destination */
+                    if (box.dst < m.patch_base || box.dst + RW_PATCH_C_OFF > m.patch_base + m.n_patch * RW_PATCH_BYTES) return -25;
+                    const uint8_t *surf = box.z == 1 ? future : past;
+                    uint8_t *dst = sw_host_smem + box.dst;
+                    if (!box.chroma) box_copy(dst, surf + plane_off[0], pw[0], ph[0], box.x, box.y, RW_BOX_W, 9);
+                    else
+                    {
+                        box_copy(dst, surf + plane_off[1], pw[1], ph[1], box.x, box.y, RW_BOX_W, 5);
+                        box_copy(dst + RW_PATCH_C, surf + plane_off[2], pw[2], ph[2], box.x, box.y, RW_BOX_W, 5);
+                    }
+                }
+            if (issued != m.patch_count || issued > n_inter) return -26;
             ++ki;
         }
         if (ki == ks) return -27;
@@ -128,21 +132,22 @@ int emul_row_picture(const uint8_t *blob, uint8_t *present, const uint8_t *past,
         const uint32_t slot_off = g.off_slot0 + (uint32_t)(ks % g.n_slots) * g.slot_bytes;
         const RowSlotMeta &m = *reinterpret_cast<const RowSlotMeta *>(sw_host_smem + slot_off + g.s_meta);
         const RowWork w = {&g, &v, &m, slot_off};
-        for (uint32_t t = 0; t < m.t_end[RW_TASK_CLASSES - 1]; ++t)
-            for (int lane = 0; lane < 32; ++lane) rw_run_task(w, t, lane);
+        uint32_t t_end[RW_TASK_CLASSES];
+        rw_task_ends(m, t_end);
+        for (uint32_t t = 0; t < t_end[RW_TASK_CLASSES - 1]; ++t)
+            for (int lane = 0; lane < 32; ++lane) rw_run_task(w, t_end, t, lane);
         /* retire */
         const uint8_t *tile = sw_host_smem + slot_off + g.s_tile;
-        const size_t wy = (size_t)g.width, wc = wy / 2;
         memcpy(present + (size_t)ks * g.tile_y_bytes, tile, g.tile_y_bytes);
         memcpy(present + plane_off[1] + (size_t)ks * g.tile_c_bytes, tile + g.tile_y_bytes, g.tile_c_bytes);
         memcpy(present + plane_off[2] + (size_t)ks * g.tile_c_bytes, tile + g.tile_y_bytes + g.tile_c_bytes, g.tile_c_bytes);
-        (void)wc;
         /* poison what the row held so that stale data cannot go unnoticed */
         if (m.n_patch) memset(sw_host_smem + m.patch_base, 0xCD, m.n_patch * RW_PATCH_BYTES);
-        rw_ring_retire(ring, m.ring_end);
+        tail = m.ring_end;
         memset(sw_host_smem + slot_off, 0xCD, g.slot_bytes);
         ++ks;
     }
+    const int bad_any = c.unsupported;
     sw_host_smem = nullptr;
     return bad_any ? 1 : 0;
 }
