@@ -208,6 +208,7 @@ struct HVQM4Batch
     size_t frame_bytes = 0, surf_stride = 0;
     uint8_t *d_surfaces = nullptr;
     bool slab_ok = false;      /* the surface slab is registered with the row kernel (tensor maps exist) */
+    int band_rows = 8;         /* macroblock rows per record band of this batch's streams (symbuf.h) */
     std::vector<StreamState> st;
     Arena arena[kArenas];
     int cur = 0;
@@ -416,6 +417,8 @@ H4_API HVQM4Batch *HVQM4BatchCreate(int device, int n_streams, int width, int he
     b->height = height;
     b->version15 = version == 15;
     b->st.resize(n_streams);
+    b->band_rows = hvqm4_recon_band_rows();      /* by the reconstruction schedule selected at this moment */
+    h4e_set_band_rows(b->band_rows);
     for (int i = 0; i < n_streams; ++i)
     {
         b->st[i].seq = h4e_seq_create(width, height, 2, 2, b->version15);
@@ -699,6 +702,7 @@ H4_API int HVQM4BatchSetEntropyMode(HVQM4Batch *b, int gpu)
         /* 16 symbols per block of a section's plane: every type an encoder emits fits (a block has
            at most 15 bases); a pathological section beyond that is flagged HVQM4_ERR_TRUNCATED */
         const uint32_t sym_cap = 16, work_cap = blocks;
+        hvqm4_dev_entropy_set_band_rows(b->band_rows);
         b->eslot = hvqm4_dev_entropy_slot_bytes(b->width, b->height, sym_cap, work_cap);
         if (!b->eslot) return HVQM4_ERR_GEOMETRY;
         /* symbol buffers of one step: twice the frame size covers the densest records; the constant covers the
@@ -1214,6 +1218,7 @@ H4_API void HVQM4SetBuffer(SeqObj *seqobj, void *workbuff)
     w->impl = nullptr;
     w->version15 = 1;
     Compat *c = new Compat;
+    h4e_set_band_rows(hvqm4_recon_band_rows());
     c->seq = h4e_seq_create(seqobj->width, seqobj->height, seqobj->h_samp, seqobj->v_samp, 1);
     if (!c->seq)
     {

@@ -635,6 +635,7 @@ struct H4Seq
     uint8_t nest[SYM_NEST_BYTES];        /* packed nibbles of the last I picture's nest */
     HTab tree[6];
     int nbands, ngroups;                 /* record groups: [class][band][length bucket] */
+    int bshift;                          /* log2 of the macroblock rows per record band (0 or 3) */
     uint32_t *grp_count, *grp_base, *grp_next, *grp_chunk, *grp_ord;
     uint8_t *mcb_tag;                    /* P/B pass 1, split form: type/proc tag of every macroblock ... */
     uint32_t *mcb_list, n_list;          /* ... and the macroblocks that carry block types, in bitstream order */
@@ -698,6 +699,16 @@ H4E_FN int seq_geometry_ok(int width, int height, int h_samp, int v_samp)
     return width <= 8192 && height <= 8192;
 }
 
+/* Macroblock rows per record band of the streams created from now on: 8 (default: the band kernel's unit, few and
+   full chunks) or 1 (a kernel can then take any number of consecutive macroblock rows as its unit: sweep and row
+   kernels).  Process-wide; the device build keeps its own copy (entropy_dev.cu sets it before it creates streams). */
+#if defined(H4E_DEVICE)
+__device__ int g_h4e_band_shift = 3;
+#else
+static int g_h4e_band_shift = 3;
+void h4e_set_band_rows(int rows) { g_h4e_band_shift = rows <= 1 ? 0 : 3; }
+#endif
+
 H4E_FN void seq_set_dims(H4Seq *s, int width, int height, int version15)
 {
     s->width = width;
@@ -714,7 +725,8 @@ H4E_FN void seq_set_dims(H4Seq *s, int width, int height, int version15)
         s->stride[p] = s->bw[p] + 2;
         s->map_cells[p] = (size_t)s->stride[p] * (s->bh[p] + 2);
     }
-    s->nbands = (s->mbh + SYM_BAND_MCB_ROWS - 1) / SYM_BAND_MCB_ROWS;
+    s->bshift = g_h4e_band_shift;
+    s->nbands = (s->mbh + (1 << s->bshift) - 1) >> s->bshift;
     s->ngroups = SYM_REC_CLASSES * s->nbands * SYM_LEN_BUCKETS;
     /* upper bound on chunks: one per group plus one per 32 blocks, or one per block in the long bucket */
     s->chunks_cap = (uint32_t)s->ngroups + (uint32_t)(s->bw[0] * s->bh[0] + 2 * s->bw[1] * s->bh[1]);
@@ -864,9 +876,8 @@ H4E_FN void open_bytes(H4Seq *s, ByteSec *b, const uint8_t *data, size_t len, ui
 /* ------------------------------------------------------------------ record groups */
 
 /* block rows per band, as shifts */
-#define SYM_BAND_SHIFT_CHROMA 0
-#define SYM_BAND_SHIFT_LUMA 1
-H4E_STATIC_ASSERT((1 << SYM_BAND_SHIFT_CHROMA) == SYM_BAND_MCB_ROWS, "band shift must match SYM_BAND_MCB_ROWS");
+#define SYM_BAND_SHIFT_CHROMA (s->bshift)
+#define SYM_BAND_SHIFT_LUMA (s->bshift + 1)
 
 H4E_INL int len_bucket(uint32_t len) { return len < SYM_LEN_BUCKETS ? (int)len - 1 : SYM_LEN_BUCKETS - 1; }
 H4E_INL int group_of(const H4Seq *s, int cls, int band, uint32_t len)
@@ -876,7 +887,7 @@ H4E_INL int group_of(const H4Seq *s, int cls, int band, uint32_t len)
 
 /* Called wherever a block's final type byte is written (ipic_types, pb_pass1): counts the
    record the block will own in its (class, band, length) group.  band_shift: log2 of block rows
-   per band (luma 1, chroma 0 for SYM_BAND_MCB_ROWS = 1). */
+   per band (luma 1, chroma 0 for bands of one macroblock row). */
 H4E_INL void count_record(H4Seq *s, uint32_t t, int is_ipic, int by, int band_shift)
 {
     const uint32_t lut = rec_lut(is_ipic, t);

@@ -25,6 +25,8 @@ typedef struct H4Seq H4Seq;
    Huffman leaf tables (they persist across pictures in the reference, h4m:474). */
 H4Seq *h4e_seq_create(int width, int height, int h_samp, int v_samp, int version15);
 void h4e_seq_destroy(H4Seq *s);
+/* macroblock rows per record band (symbuf.h) of the streams created from now on: 8 (default) or 1; process-wide */
+void h4e_set_band_rows(int rows);
 void h4e_seq_set_version(H4Seq *s, int version15);
 uint32_t h4e_seq_errors(const H4Seq *s);   /* OR of SYM_ERR_* since creation */
 

@@ -164,6 +164,12 @@ extern "C" size_t hvqm4_dev_entropy_slot_bytes(int width, int height, uint32_t s
     return (size_t)((h + 255) & ~255ull);
 }
 
+extern "C" void hvqm4_dev_entropy_set_band_rows(int rows)
+{
+    const int shift = rows <= 1 ? 0 : 3;
+    cudaMemcpyToSymbol(g_h4e_band_shift, &shift, sizeof shift);
+}
+
 extern "C" int hvqm4_dev_entropy_init(uint8_t *arena, size_t slot_bytes, int n_streams, int width, int height, int version15,
                                       uint32_t sym_cap, uint32_t work_cap, cudaStream_t stream)
 {

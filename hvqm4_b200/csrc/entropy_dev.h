@@ -36,6 +36,8 @@ extern "C" {
 
 /* bytes of device memory ONE parser slot needs (0 on unsupported geometry); a stream owns
    H4_PARSE_SLOTS slots, used by consecutive steps in turn, so the arena is H4_PARSE_SLOTS * n_streams slots */
+/* macroblock rows per record band of the device streams created from now on (entropy.h: h4e_set_band_rows) */
+void hvqm4_dev_entropy_set_band_rows(int rows);
 size_t hvqm4_dev_entropy_slot_bytes(int width, int height, uint32_t sym_cap, uint32_t work_cap);
 int hvqm4_dev_entropy_init(uint8_t *arena, size_t slot_bytes, int n_streams, int width, int height, int version15,
                            uint32_t sym_cap, uint32_t work_cap, cudaStream_t stream);

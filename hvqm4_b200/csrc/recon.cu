@@ -360,7 +360,7 @@ recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs, uint32_t cta_
 constexpr int kBandWarps = HVQM4_BAND_WARPS;
 constexpr int kTileMcbs = 128;
 constexpr int kBandRows = 8;   /* macroblock rows per CTA of the band kernel = kBandRows record bands of symbuf.h */
-static_assert(SYM_BAND_MCB_ROWS == 1, "the band kernel takes kBandRows record bands per CTA");
+static_assert(SYM_BAND_MCB_ROWS == kBandRows, "a CTA of the band kernel takes one record band of 8 rows, or 8 bands of one row");
 
 /* queue capacity of one warp in entries: its four block rows (two luma, one U, one V) of one column tile */
 static inline int band_queue_entries(int mcb_w)
@@ -496,10 +496,13 @@ __device__ __forceinline__ void band_item(const ReconJob *__restrict__ jobs, int
         band_map_tile(v, row0, row1, mx0, min(mx0 + kTileMcbs, v.mcb_w), queue, queue_cap);
     /* record phase */
     const uint32_t nb1 = v.n_bands + 1;
-    /* the chunks of a class are ordered by record band (= macroblock row), so rows row0..row1 are one range */
-    const uint32_t raw0 = __ldg(v.bands + row0), raw1 = __ldg(v.bands + row1);
-    const uint32_t intra0 = __ldg(v.bands + nb1 + row0), intra1 = __ldg(v.bands + nb1 + row1);
-    const uint32_t inter0 = __ldg(v.bands + 2 * nb1 + row0), inter1 = __ldg(v.bands + 2 * nb1 + row1);
+    /* the chunks of a class are ordered by record band: one band of 8 macroblock rows, or (streams made for the sweep
+       and row kernels) bands of one row, of which rows row0..row1 are one range */
+    const bool row_bands = (int)v.n_bands == v.mcb_h && v.mcb_h > 1;
+    const int b0 = row_bands ? row0 : band, b1 = row_bands ? row1 : band + 1;
+    const uint32_t raw0 = __ldg(v.bands + b0), raw1 = __ldg(v.bands + b1);
+    const uint32_t intra0 = __ldg(v.bands + nb1 + b0), intra1 = __ldg(v.bands + nb1 + b1);
+    const uint32_t inter0 = __ldg(v.bands + 2 * nb1 + b0), inter1 = __ldg(v.bands + 2 * nb1 + b1);
     if (v.has_nest) nest_stage_wait();
     if (intra1 > intra0)
     {
@@ -686,6 +689,13 @@ static int launch_record_cfg(int cfg, const ReconJob *d_jobs, int n_jobs, uint32
  * in L2; by default the sub-batch is the whole step (see below).
  */
 extern "C" void hvqm4_recon_set_mode(int band_mode) { g_band_mode = band_mode; }
+/* macroblock rows per record band the streams of a new batch / decoder should be created with: the sweep and row
+   kernels need bands of one row, everything else is fastest with the band kernel's eight */
+extern "C" int hvqm4_recon_band_rows(void)
+{
+    static const int env_sweep = getenv("HVQM4_SWEEP") ? atoi(getenv("HVQM4_SWEEP")) : -1, env_row = getenv("HVQM4_ROW") ? atoi(getenv("HVQM4_ROW")) : -1;
+    return (g_band_mode == 5 || g_band_mode == 6 || env_sweep == 1 || env_row == 1) ? 1 : SYM_BAND_MCB_ROWS;
+}
 
 /* the fused band kernel only (no host-side record prefix needed): used behind the GPU entropy stage, where it
    runs next to the parse kernels -- the smallest register footprint (end to end 96.4 k vs 94.4 k frames/s) */

@@ -39,6 +39,7 @@ static inline uint32_t hvqm4_rec_ctas(uint32_t n_chunks)
    map + record kernel pair */
 void hvqm4_recon_set_mode(int band_mode);
 long long hvqm4_recon_band_launches(void);
+int hvqm4_recon_band_rows(void);
 
 /* rgb.cu: planar Y|U|V 4:2:0 surfaces -> interleaved RGB (the reference's dumpRGB, h4m:895-926) */
 int hvqm4_rgb_launch(const uint8_t *const *d_frames, int n, uint8_t *d_dst, size_t dst_stride, int width, int height, cudaStream_t stream);

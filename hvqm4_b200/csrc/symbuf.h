@@ -52,8 +52,9 @@
 
 #define SYM_MAGIC 0x42533448u /* "H4SB" */
 #define SYM_SEG_MCBS 16       /* macroblocks per segment of the map kernel (= 32 luma blocks = one warp) */
-#define SYM_BAND_MCB_ROWS 1   /* record groups are formed per band of this many macroblock rows: one, so that a kernel can
-                                 take any number of consecutive macroblock rows as its unit (sweep kernel 1..4, band kernel 8) */
+#define SYM_BAND_MCB_ROWS 8   /* record groups are formed per band of this many macroblock rows -- the band kernel's unit: few, full
+                                 chunks -- or, chosen per stream at creation (h4e_set_band_rows), of ONE row, so that a kernel can take
+                                 any consecutive macroblock rows as its unit (sweep and row kernels); SymHeader.n_bands says which */
 #define SYM_CHUNK 32          /* records per chunk (= one warp of the record kernel) */
 #define SYM_LEN_BUCKETS 18    /* record lengths 1..17 words get their own group; longer ones one chunk each */
 #define SYM_NEST_W 70

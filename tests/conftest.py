@@ -45,6 +45,7 @@ def emul_lib():
     lib.h4e_seq_errors.restype = ctypes.c_uint32
     lib.h4e_seq_errors.argtypes = [ctypes.c_void_p]
     lib.emul_recon_picture.argtypes = [ctypes.c_void_p] * 4
+    lib.h4e_set_band_rows.argtypes = [ctypes.c_int]
     lib.emul_sweep_picture.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 3
     lib.emul_row_picture.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 2
     lib.emul_weighted.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 5

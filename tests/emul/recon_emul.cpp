@@ -41,10 +41,12 @@ int emul_recon_picture(const uint8_t *blob, uint8_t *present, const uint8_t *pas
     /* band by band, like the fused CUDA kernel: the band's map blocks, then the records of the band
        (the chunks of every (class, band) pair are contiguous; the band table gives their start) */
     uint32_t seen = 0, chunks_seen = 0;
-    if (h.n_bands != (uint32_t)((h.mcb_h + SYM_BAND_MCB_ROWS - 1) / SYM_BAND_MCB_ROWS)) return -6;
+    /* bands of 8 macroblock rows, or of one (streams made for the sweep and row kernels) */
+    const int band_rows = (h.n_bands == h.mcb_h && h.mcb_h > 1) ? 1 : SYM_BAND_MCB_ROWS;
+    if (h.n_bands != (uint32_t)((h.mcb_h + band_rows - 1) / band_rows)) return -6;
     for (uint32_t band = 0; band < h.n_bands; ++band)
     {
-        const int my0 = (int)band * SYM_BAND_MCB_ROWS, my1 = my0 + SYM_BAND_MCB_ROWS < h.mcb_h ? my0 + SYM_BAND_MCB_ROWS : h.mcb_h;
+        const int my0 = (int)band * band_rows, my1 = my0 + band_rows < h.mcb_h ? my0 + band_rows : h.mcb_h;
         for (int plane = 0; plane < 3; ++plane)
         {
             const int pw = h.width >> (plane ? 1 : 0);
@@ -77,7 +79,7 @@ int emul_recon_picture(const uint8_t *blob, uint8_t *present, const uint8_t *pas
                     uint32_t t;
                     int plane, bx, by;
                     rc_record_coords(rec[0], t, plane, bx, by);
-                    if ((uint32_t)((plane ? by : by >> 1) / SYM_BAND_MCB_ROWS) != band) return -9;
+                    if ((uint32_t)((plane ? by : by >> 1) / band_rows) != band) return -9;
                     const int pw = h.width >> (plane ? 1 : 0);
                     uint8_t *dst = planes[plane] + (by * 4) * pw + bx * 4;
                     uint32_t rows[4];

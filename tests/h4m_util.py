@@ -38,7 +38,9 @@ def emul_decode(lib, data: bytes, sweep=None, stats=None, row=None):
     and are counted in stats["fallback"].
     row = (shared-memory bytes, look-ahead rows): the same for the row kernel (tests/emul/row_emul.cpp)."""
     version, w, h, recs = demux(data)
+    lib.h4e_set_band_rows(1 if (sweep is not None or row is not None) else 8)     # record bands of one macroblock row for those kernels
     seq = lib.h4e_seq_create(w, h, 2, 2, int(version == 15))
+    lib.h4e_set_band_rows(8)
     assert seq
     fb = w * h * 3 // 2
     bufs = [np.zeros(fb + 64, np.uint8) for _ in range(3)]
