@@ -422,7 +422,7 @@ class Batch:
 
 
 def set_recon_mode(mode: int) -> None:
-    """0 auto, 1..4 fused band kernel, 5 sweep kernel, 6 row kernel, <0 map + record kernels (see include/hvqm4.h)."""
+    """0 auto, 1..4 fused band kernel, 5 sweep kernel, 6 row kernel, 7 band kernel with a shared-memory tile, <0 map + record kernels (see include/hvqm4.h)."""
     lib().HVQM4SetReconMode(mode)
 
 

@@ -657,7 +657,7 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
     {
         ++g_launches;
         b->stats[1] += 1;
-        rc = hvqm4_recon_launch_band(d_jobs, n, b->mcb_w, b->mcb_h, b->slab_ok ? b->d_surfaces : nullptr, b->s_comp);
+        rc = hvqm4_recon_launch_band(d_jobs, n, b->mcb_w, b->mcb_h, b->slab_ok ? b->d_surfaces : nullptr, b->band_rows, b->s_comp);
         if (rc == 0)
         {
             ++g_launches;
@@ -808,7 +808,7 @@ H4_API int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, con
     cudaStreamWaitEvent(b->s_comp, b->ev_h2d, 0);
     batch_wait_readbacks(b);
     int launched = 0;
-    int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(d_base), n, b->mcb_w, b->mcb_h, b->rec_prefix.data(), b->slab_ok ? b->d_surfaces : nullptr, b->s_comp, &launched);
+    int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(d_base), n, b->mcb_w, b->mcb_h, b->rec_prefix.data(), b->slab_ok ? b->d_surfaces : nullptr, b->band_rows, b->s_comp, &launched);
     g_launches += launched;
     b->stats[1] += (uint64_t)launched;
     if (rc != 0)
@@ -984,7 +984,7 @@ H4_API float HVQM4BatchReplay(HVQM4Batch *b, int repeats)
         for (auto &st : b->recorded)
         {
             int launched = 0;
-            int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(st.d), st.n, b->mcb_w, b->mcb_h, st.rec_prefix.data(), b->slab_ok ? b->d_surfaces : nullptr, b->s_comp, &launched);
+            int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(st.d), st.n, b->mcb_w, b->mcb_h, st.rec_prefix.data(), b->slab_ok ? b->d_surfaces : nullptr, b->band_rows, b->s_comp, &launched);
             g_launches += launched;
             b->stats[1] += (uint64_t)launched;
             if (rc != 0)
@@ -1041,6 +1041,7 @@ struct Compat
     int width = 0, height = 0;
     size_t frame_bytes = 0, surf_bytes = 0;
     int mcb_w = 0, mcb_h = 0;
+    int band_rows = 8;                              /* macroblock rows per record band of the stream (symbuf.h) */
     uint8_t *h_blob = nullptr, *d_blob = nullptr;   /* job descriptor (256 B) + blob */
     uint8_t *d_rgb = nullptr;                       /* HVQM4ConvertRGB staging */
     size_t blob_cap = 0;
@@ -1172,7 +1173,7 @@ void compat_decode(SeqObj *so, int type, const uint8_t *frame, void *present, vo
     {
         int launched = 0;
         const uint32_t prefix[2] = {0, hvqm4_rec_ctas(job->n_chunks)};
-        int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(c->d_blob), 1, c->mcb_w, c->mcb_h, prefix, nullptr, c->stream, &launched);
+        int rc = hvqm4_recon_launch(reinterpret_cast<const ReconJob *>(c->d_blob), 1, c->mcb_w, c->mcb_h, prefix, nullptr, c->band_rows, c->stream, &launched);
         g_launches += launched;
         ok = rc == 0 || cuda_ok((cudaError_t)rc, "recon kernel launch");
     }
@@ -1218,7 +1219,8 @@ H4_API void HVQM4SetBuffer(SeqObj *seqobj, void *workbuff)
     w->impl = nullptr;
     w->version15 = 1;
     Compat *c = new Compat;
-    h4e_set_band_rows(hvqm4_recon_band_rows());
+    c->band_rows = hvqm4_recon_band_rows();
+    h4e_set_band_rows(c->band_rows);
     c->seq = h4e_seq_create(seqobj->width, seqobj->height, seqobj->h_samp, seqobj->v_samp, 1);
     if (!c->seq)
     {

@@ -706,7 +706,7 @@ H4E_FN int seq_geometry_ok(int width, int height, int h_samp, int v_samp)
 __device__ int g_h4e_band_shift = 3;
 #else
 static int g_h4e_band_shift = 3;
-void h4e_set_band_rows(int rows) { g_h4e_band_shift = rows <= 1 ? 0 : 3; }
+void h4e_set_band_rows(int rows) { g_h4e_band_shift = rows <= 1 ? 0 : rows <= 4 ? 2 : 3; }
 #endif
 
 H4E_FN void seq_set_dims(H4Seq *s, int width, int height, int version15)

@@ -166,7 +166,7 @@ extern "C" size_t hvqm4_dev_entropy_slot_bytes(int width, int height, uint32_t s
 
 extern "C" void hvqm4_dev_entropy_set_band_rows(int rows)
 {
-    const int shift = rows <= 1 ? 0 : 3;
+    const int shift = rows <= 1 ? 0 : rows <= 4 ? 2 : 3;
     cudaMemcpyToSymbol(g_h4e_band_shift, &shift, sizeof shift);
 }
 

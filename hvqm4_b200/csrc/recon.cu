@@ -148,8 +148,14 @@ __device__ __forceinline__ void map_segment(const ReconView &v, int row, int mx0
     }
 }
 
+struct BandOut;
+template <bool kTile> __device__ __forceinline__ uint32_t block_off(const ReconView &v, const BandOut &o, int plane, int bx, int by, int &pw);
+template <bool kTile> __device__ __forceinline__ void block_st(const ReconView &v, uint32_t off, uint32_t val);
+template <bool kTile> __device__ __forceinline__ uint32_t block_ld(const ReconView &v, uint32_t off);
+
 /* RECORD work of one chunk: one record per lane */
-__device__ __forceinline__ void record_chunk(const ReconView &v, uint32_t c, int lane)
+template <bool kTile>
+__device__ __forceinline__ void record_chunk(const ReconView &v, const BandOut &o, uint32_t c, int lane)
 {
     const uint2 cd = __ldg(reinterpret_cast<const uint2 *>(v.chunks) + c);
     const uint32_t count = cd.y & 0xFF, len = ((cd.y >> 8) & 0xFF) + 1;
@@ -159,18 +165,17 @@ __device__ __forceinline__ void record_chunk(const ReconView &v, uint32_t c, int
     uint32_t t;
     int plane, bx, by;
     rc_record_coords(__ldg(rec), t, plane, bx, by);
-    const int pw = plane ? v.width >> 1 : v.width;
-    const int plane_off = plane == 0 ? 0 : plane == 1 ? v.width * v.height : v.width * v.height + (v.width >> 1) * (v.height >> 1);
-    uint8_t *dst = v.present + plane_off + (by * 4) * pw + bx * 4;
+    int pw;
+    const uint32_t dst = block_off<kTile>(v, o, plane, bx, by, pw);
     uint32_t rows[4];
     if (cls == SYM_REC_INTER)
     {   /* the prediction left by the map work; L2-coherent loads (it may have been written by another warp) */
 #pragma unroll
-        for (int r = 0; r < 4; ++r) rows[r] = __ldcg(reinterpret_cast<const uint32_t *>(dst + r * pw));
+        for (int r = 0; r < 4; ++r) rows[r] = block_ld<kTile>(v, dst + r * pw);
     }
     rc_record_block(v, cls, len, rec, rows);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];
+    for (int r = 0; r < 4; ++r) block_st<kTile>(v, dst + r * pw, rows[r]);
 }
 
 /* the same with the chunk descriptor, the lane's header word and rc_record_extra() fetched by the caller ahead of time */
@@ -363,16 +368,49 @@ constexpr int kBandRows = 8;   /* macroblock rows per CTA of the band kernel = k
 static_assert(SYM_BAND_MCB_ROWS == kBandRows, "a CTA of the band kernel takes one record band of 8 rows, or 8 bands of one row");
 
 /* queue capacity of one warp in entries: its four block rows (two luma, one U, one V) of one column tile */
-static inline int band_queue_entries(int mcb_w)
+static inline int band_queue_entries(int mcb_w, int rows = 8)
 {
-    return (mcb_w < kTileMcbs ? mcb_w : kTileMcbs) * 6;
+    /* 8 rows per CTA: two luma and two chroma block rows per warp; 4 rows: one of each */
+    return (mcb_w < kTileMcbs ? mcb_w : kTileMcbs) * (rows > 4 ? 6 : 3);
 }
 
-__device__ __forceinline__ uint8_t *block_dst(const ReconView &v, int plane, int bx, int by, int &pw)
+/* Where the band kernel's blocks go.  kTile = false: straight into the picture (4-byte stores scattered over the
+   band: every 32-byte sector of a picture row is written 3-4 times, once per class, and the predictions of
+   predicted-AOT blocks make a round trip through L2).  kTile = true: the band is assembled in shared memory -- same
+   layout as its part of the picture: (row1 - row0) * 8 luma rows, then the U rows, then the V rows -- and leaves with
+   three bulk stores of whole picture rows when the CTA is done. */
+struct BandOut
+{
+    uint32_t tile_off;       /* shared-memory offset of the tile */
+    uint32_t ybytes, cbytes; /* luma bytes, bytes of one chroma plane of the band */
+    int row0;                /* first macroblock row of the band */
+};
+
+template <bool kTile>
+__device__ __forceinline__ uint32_t block_off(const ReconView &v, const BandOut &o, int plane, int bx, int by, int &pw)
 {
     pw = plane ? v.width >> 1 : v.width;
+    if (kTile)
+    {
+        const uint32_t plane_off = plane == 0 ? 0u : plane == 1 ? o.ybytes : o.ybytes + o.cbytes;
+        const int lby = by - (plane ? o.row0 : 2 * o.row0);
+        return o.tile_off + plane_off + (uint32_t)((lby * 4) * pw + bx * 4);
+    }
     const int plane_off = plane == 0 ? 0 : plane == 1 ? v.width * v.height : v.width * v.height + (v.width >> 1) * (v.height >> 1);
-    return v.present + (uint32_t)(plane_off + (by * 4) * pw + bx * 4);
+    return (uint32_t)(plane_off + (by * 4) * pw + bx * 4);
+}
+template <bool kTile>
+__device__ __forceinline__ void block_st(const ReconView &v, uint32_t off, uint32_t val)
+{
+    if (kTile) *reinterpret_cast<uint32_t *>(rc_smem + off) = val;
+    else *reinterpret_cast<uint32_t *>(v.present + off) = val;
+}
+/* the prediction the map phase left for a predicted-AOT block (another warp may have written it) */
+template <bool kTile>
+__device__ __forceinline__ uint32_t block_ld(const ReconView &v, uint32_t off)
+{
+    if (kTile) return *reinterpret_cast<const uint32_t *>(rc_smem + off);
+    return __ldcg(reinterpret_cast<const uint32_t *>(v.present + off));
 }
 
 /* map work of macroblock rows [row0, row1) x macroblock columns [mx0, mx1) of the CTA's picture.
@@ -382,7 +420,8 @@ __device__ __forceinline__ uint8_t *block_dst(const ReconView &v, int plane, int
    32 are classified); everything that costs instructions runs in the drains, where all lanes of
    a warp do the same thing, two queue entries per lane at a time so that twice as many
    reference rows are in flight. */
-__device__ __forceinline__ void band_map_tile(const ReconView &v, int row0, int row1, int mx0, int mx1, uint32_t *q, int cap)
+template <bool kTile>
+__device__ __forceinline__ void band_map_tile(const ReconView &v, const BandOut &o, int row0, int row1, int mx0, int mx1, uint32_t *q, int cap)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
@@ -401,7 +440,7 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, int row0, int 
         const uint8_t *trow = v.blob + (rc_pick3(v.off_type, plane) + (by + 1) * bstride + 1);
         const uint8_t *drow = v.blob + (rc_pick3(v.off_dc, plane) + (by + 1) * bstride + 1);
         int pw2;
-        uint8_t *dst_row = block_dst(v, plane, 0, by, pw2);
+        const uint32_t dst_row = block_off<kTile>(v, o, plane, 0, by, pw2);
         const uint32_t entry_row = sym_record_header(0, plane, 0, by);
         /* lanes past the row end get type 6 (raw: nothing to do here) */
         int bx = x0 + lane;
@@ -434,9 +473,9 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, int row0, int 
             if (!inter && nib == 8)
             {   /* flat fill, h4m:281 */
                 const uint32_t V = dc * 0x01010101u;
-                uint8_t *dst = dst_row + bx * 4;
+                const uint32_t dst = dst_row + bx * 4;
 #pragma unroll
-                for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = V;
+                for (int r = 0; r < 4; ++r) block_st<kTile>(v, dst + r * pw, V);
             }
             bx = bx_n; t = t_n; dc = dc_n;
         }
@@ -449,9 +488,9 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, int row0, int 
         int plane, bx, by, pw;
         rc_record_coords(q[i], t, plane, bx, by);
         rc_weighted_block(v, plane, bx, by, rows);
-        uint8_t *dst = block_dst(v, plane, bx, by, pw);
+        const uint32_t dst = block_off<kTile>(v, o, plane, bx, by, pw);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst + r * pw) = rows[r];
+        for (int r = 0; r < 4; ++r) block_st<kTile>(v, dst + r * pw, rows[r]);
     }
     /* motion compensation: two entries per lane and round */
     const uint32_t *q_mc = q + cap - 1;
@@ -466,21 +505,22 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, int row0, int 
         const uint32_t mv0 = rc_mv_word(v, plane0, bx0, by0), mv1 = rc_mv_word(v, plane1, bx1, by1);
         const uint32_t mp0 = rc_motion_pack(v, plane0, bx0, by0, t0, mv0), mp1 = rc_motion_pack(v, plane1, bx1, by1, t1, mv1);
         rc_mc_packed2(v, plane0, mp0, rows0, plane1, mp1, rows1);
-        uint8_t *dst0 = block_dst(v, plane0, bx0, by0, pw0);
+        const uint32_t dst0 = block_off<kTile>(v, o, plane0, bx0, by0, pw0);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst0 + r * pw0) = rows0[r];
+        for (int r = 0; r < 4; ++r) block_st<kTile>(v, dst0 + r * pw0, rows0[r]);
         if (two)
         {
-            uint8_t *dst1 = block_dst(v, plane1, bx1, by1, pw1);
+            const uint32_t dst1 = block_off<kTile>(v, o, plane1, bx1, by1, pw1);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t *>(dst1 + r * pw1) = rows1[r];
+            for (int r = 0; r < 4; ++r) block_st<kTile>(v, dst1 + r * pw1, rows1[r]);
         }
     }
     __syncwarp();
 }
 
-/* one band of one picture: the whole CTA */
-__device__ __forceinline__ void band_item(const ReconJob *__restrict__ jobs, int job, int band, uint32_t *queue, int queue_cap)
+/* one band of kRows macroblock rows of one picture: the whole CTA.  tile_off: shared-memory offset of the output tile (kTile) */
+template <bool kTile, int kRows>
+__device__ __forceinline__ void band_item(const ReconJob *__restrict__ jobs, int job, int band, uint32_t *queue, int queue_cap, uint32_t tile_off)
 {
     ReconView &vw = *reinterpret_cast<ReconView *>(rc_smem + RC_SMEM_VIEW_OFF);
     if (threadIdx.x == 0) load_view(vw, jobs[job]);
@@ -491,15 +531,17 @@ __device__ __forceinline__ void band_item(const ReconJob *__restrict__ jobs, int
     if (v.has_nest) nest_stage_begin<kBandWarps * 32>(v, rc_smem + RC_SMEM_TABLE_BYTES);   /* lands during the map phase */
 
     /* map phase */
-    const int row0 = band * kBandRows, row1 = min(row0 + kBandRows, v.mcb_h);
+    const int row0 = band * kRows, row1 = min(row0 + kRows, v.mcb_h);
+    const BandOut out = {tile_off, (uint32_t)((row1 - row0) * 8 * v.width), (uint32_t)((row1 - row0) * 4 * (v.width >> 1)), row0};
     for (int mx0 = 0; mx0 < v.mcb_w; mx0 += kTileMcbs)
-        band_map_tile(v, row0, row1, mx0, min(mx0 + kTileMcbs, v.mcb_w), queue, queue_cap);
+        band_map_tile<kTile>(v, out, row0, row1, mx0, min(mx0 + kTileMcbs, v.mcb_w), queue, queue_cap);
     /* record phase */
     const uint32_t nb1 = v.n_bands + 1;
-    /* the chunks of a class are ordered by record band: one band of 8 macroblock rows, or (streams made for the sweep
-       and row kernels) bands of one row, of which rows row0..row1 are one range */
-    const bool row_bands = (int)v.n_bands == v.mcb_h && v.mcb_h > 1;
-    const int b0 = row_bands ? row0 : band, b1 = row_bands ? row1 : band + 1;
+    /* the chunks of a class are ordered by record band: bands of 8, 4 or 1 macroblock rows (h4e_set_band_rows; kRows is
+       a multiple), of which rows row0..row1 are one range */
+    const int nb = (int)v.n_bands;
+    const int rpb = nb == v.mcb_h ? 1 : nb == (v.mcb_h + 3) / 4 ? 4 : 8;
+    const int b0 = row0 / rpb, b1 = min((row1 + rpb - 1) / rpb, nb);
     const uint32_t raw0 = __ldg(v.bands + b0), raw1 = __ldg(v.bands + b1);
     const uint32_t intra0 = __ldg(v.bands + nb1 + b0), intra1 = __ldg(v.bands + nb1 + b1);
     const uint32_t inter0 = __ldg(v.bands + 2 * nb1 + b0), inter1 = __ldg(v.bands + 2 * nb1 + b1);
@@ -511,23 +553,40 @@ __device__ __forceinline__ void band_item(const ReconJob *__restrict__ jobs, int
     }
     __syncthreads();     /* map stores of the band visible to the whole CTA; nest table complete */
 #pragma unroll 1
-    for (uint32_t c = raw0 + warp; c < raw1; c += kBandWarps) record_chunk(v, c, lane);
+    for (uint32_t c = raw0 + warp; c < raw1; c += kBandWarps) record_chunk<kTile>(v, out, c, lane);
 #pragma unroll 1
-    for (uint32_t c = intra0 + warp; c < intra1; c += kBandWarps) record_chunk(v, c, lane);
+    for (uint32_t c = intra0 + warp; c < intra1; c += kBandWarps) record_chunk<kTile>(v, out, c, lane);
 #pragma unroll 1
-    for (uint32_t c = inter0 + warp; c < inter1; c += kBandWarps) record_chunk(v, c, lane);
+    for (uint32_t c = inter0 + warp; c < inter1; c += kBandWarps) record_chunk<kTile>(v, out, c, lane);
+    if (kTile)
+    {   /* the band leaves as whole picture rows: three bulk stores (shared memory -> picture) */
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     /* this thread's tile writes -> visible to the copies */
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            const uint32_t tile = (uint32_t)__cvta_generic_to_shared(rc_smem + tile_off);
+            uint8_t *py = v.present + (size_t)row0 * 8 * v.width;
+            uint8_t *pu = v.present + (size_t)v.width * v.height + (size_t)row0 * 4 * (v.width >> 1);
+            uint8_t *pv = pu + (size_t)(v.width >> 1) * (v.height >> 1);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(py), "r"(tile), "r"(out.ybytes) : "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(pu), "r"(tile + out.ybytes), "r"(out.cbytes) : "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(pv), "r"(tile + out.ybytes + out.cbytes), "r"(out.cbytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    /* the CTA's shared memory is released when it exits */
+        }
+    }
 }
 
 /* one CTA per (picture, band) */
-template <int kMinBlocks>
+template <int kMinBlocks, bool kTile, int kRows>
 __global__ void __launch_bounds__(kBandWarps * 32, kMinBlocks)
 recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap)
 {
-    /* dynamic shared memory: [tables + view | nest staging scratch | queue counters | queue] */
+    /* dynamic shared memory: [tables + view | nest staging scratch | queues | output tile (kTile)] */
     uint32_t *queue = reinterpret_cast<uint32_t *>(rc_smem + kRecSmem) + (threadIdx.x >> 5) * queue_cap;   /* the warp's own */
     build_div_tables<kBandWarps * 32>();
     const int job = blockIdx.x / n_bands;
-    band_item(jobs, job, blockIdx.x - job * n_bands, queue, queue_cap);
+    band_item<kTile, kRows>(jobs, job, blockIdx.x - job * n_bands, queue, queue_cap, (uint32_t)((kRecSmem + kBandWarps * queue_cap * 4 + 127) & ~127));
 }
 
 /* The fallback launch behind the sweep kernel (skip_handled = 1: pictures whose job says pad[0] = 1 are already
@@ -545,7 +604,7 @@ recon_band_walk_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue
         if (skip_handled == 1 && __ldg(&jobs[job].pad[0])) continue;
         if (skip_handled == 2 && !__ldg(&jobs[job].pad[1])) continue;
         __syncthreads();     /* the previous item is finished (view, tables, queues) */
-        band_item(jobs, job, item - job * n_bands, queue, queue_cap);
+        band_item<false, kBandRows>(jobs, job, item - job * n_bands, queue, queue_cap, 0u);
     }
 }
 
@@ -590,10 +649,31 @@ int env_int(const char *name)
 
 }  // namespace
 
-template <int kMinBlocks>
-int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, int mcb_w, cudaStream_t stream, int skip_handled = 0)
+template <int kMinBlocks, bool kTile, int kRows>
+int launch_band_plain(const ReconJob *d_jobs, long long items, int n_bands, int cap, int smem, cudaStream_t stream)
 {
-    const long long items = (long long)n_jobs * n_bands;
+    if (smem > 48 * 1024)
+    {   /* opt in (per device, so not cached) */
+        const cudaError_t e = cudaFuncSetAttribute(recon_band_kernel<kMinBlocks, kTile, kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    recon_band_kernel<kMinBlocks, kTile, kRows><<<(unsigned)items, kBandWarps * 32, smem, stream>>>(d_jobs, n_bands, cap);
+    return (int)cudaGetLastError();
+}
+
+/* bytes of the output tile of one band: `rows` macroblock rows of all three planes */
+static inline int band_tile_bytes(int mcb_w, int rows) { return rows * 8 * (mcb_w * 8) * 3 / 2; }
+static inline int band_tile_smem(int mcb_w, int rows)
+{
+    return ((kRecSmem + kBandWarps * band_queue_entries(mcb_w, rows) * 4 + 127) & ~127) + band_tile_bytes(mcb_w, rows);
+}
+
+/* tile = 0: blocks go straight into the picture, one CTA per band of 8 macroblock rows (n_bands of them per picture);
+   tile = 8 / 4: the band (8 / 4 macroblock rows) is assembled in shared memory (two / four CTAs per SM) */
+template <int kMinBlocks>
+int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, int mcb_w, cudaStream_t stream, int skip_handled = 0, int tile = 0, int mcb_h = 0)
+{
+    long long items = (long long)n_jobs * n_bands;
     if (items > 0x7FFFFFFFll) return (int)cudaErrorInvalidConfiguration;
     const int cap = band_queue_entries(mcb_w);
     const int smem = kRecSmem + kBandWarps * cap * 4;
@@ -608,13 +688,19 @@ int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, int mcb_w, cuda
         recon_band_walk_kernel<<<(unsigned)grid, kBandWarps * 32, smem, stream>>>(d_jobs, n_bands, cap, (int)items, skip_handled);
         return (int)cudaGetLastError();
     }
-    if (smem > 48 * 1024)
-    {   /* wide pictures: opt in (per device, so not cached) */
-        const cudaError_t e = cudaFuncSetAttribute(recon_band_kernel<kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
+    if (tile == 8) return launch_band_plain<2, true, 8>(d_jobs, items, n_bands, cap, band_tile_smem(mcb_w, 8), stream);
+    if (tile == 4)
+    {
+        const int nb4 = (mcb_h + 3) / 4;
+        return launch_band_plain<4, true, 4>(d_jobs, (long long)n_jobs * nb4, nb4, band_queue_entries(mcb_w, 4), band_tile_smem(mcb_w, 4), stream);
     }
-    recon_band_kernel<kMinBlocks><<<(unsigned)items, kBandWarps * 32, smem, stream>>>(d_jobs, n_bands, cap);
-    return (int)cudaGetLastError();
+    return launch_band_plain<kMinBlocks, false, kBandRows>(d_jobs, items, n_bands, cap, smem, stream);
+}
+
+/* does the tile variant of the band kernel fit `ctas` times into an SM for pictures this wide? */
+static bool band_tile_fits(int mcb_w, int rows, int ctas)
+{
+    return band_tile_smem(mcb_w, rows) + 1024 <= 227 * 1024 / ctas;
 }
 
 extern "C" int hvqm4_sweep_supported(int mcb_w, int mcb_h);
@@ -694,13 +780,17 @@ extern "C" void hvqm4_recon_set_mode(int band_mode) { g_band_mode = band_mode; }
 extern "C" int hvqm4_recon_band_rows(void)
 {
     static const int env_sweep = getenv("HVQM4_SWEEP") ? atoi(getenv("HVQM4_SWEEP")) : -1, env_row = getenv("HVQM4_ROW") ? atoi(getenv("HVQM4_ROW")) : -1;
-    return (g_band_mode == 5 || g_band_mode == 6 || env_sweep == 1 || env_row == 1) ? 1 : SYM_BAND_MCB_ROWS;
+    static const int env_rows = getenv("HVQM4_BAND_ROWS") ? atoi(getenv("HVQM4_BAND_ROWS")) : 0;     /* 1, 4 or 8 pins it (experiments) */
+    if (g_band_mode == 5 || g_band_mode == 6 || env_sweep == 1 || env_row == 1) return 1;
+    if (env_rows == 1 || env_rows == 4 || env_rows == 8) return env_rows;
+    return SYM_BAND_MCB_ROWS;     /* also for mode 7: tiles of 8 rows at two CTAs per SM beat tiles of 4 rows at four (1.07 M vs 0.79 M frames/s dense) */
 }
 
 /* the fused band kernel only (no host-side record prefix needed): used behind the GPU entropy stage, where it
    runs next to the parse kernels -- the smallest register footprint (end to end 96.4 k vs 94.4 k frames/s) */
-extern "C" int hvqm4_recon_launch_band(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const void *slab, cudaStream_t stream)
+extern "C" int hvqm4_recon_launch_band(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const void *slab, int band_rows, cudaStream_t stream)
 {
+    (void)band_rows;
     if (n_jobs <= 0) return 0;
     if (use_row(g_band_mode, n_jobs, mcb_w, mcb_h, slab)) return launch_row_then_band(d_jobs, n_jobs, mcb_w, mcb_h, slab, stream, nullptr);
     if (use_sweep(g_band_mode, n_jobs, mcb_w, mcb_h)) return launch_sweep_then_band(d_jobs, n_jobs, mcb_w, mcb_h, stream, nullptr);
@@ -735,7 +825,7 @@ static int launch_sweep_then_band(const ReconJob *d_jobs, int n_jobs, int mcb_w,
     return rc;
 }
 
-extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const uint32_t *h_rec_prefix, const void *slab,
+extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const uint32_t *h_rec_prefix, const void *slab, int band_rows,
                                   cudaStream_t stream, int *launches)
 {
     if (n_jobs <= 0) return 0;
@@ -763,9 +853,17 @@ extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w,
         const long long grid = (long long)n_jobs * n_bands;
         const long long waves4 = (grid + 4 * 148 - 1) / (4 * 148), waves3 = (grid + 3 * 148 - 1) / (3 * 148);
         const int per_sm = band_mode >= 2 && band_mode <= 4 ? band_mode : 1000 * waves4 <= 724 * waves3 ? 4 : 3;
+        /* HVQM4_BAND_TILE: 1 = the band assembled in shared memory (2 CTAs per SM) whenever it fits and no CTA count is
+           pinned, 0 = never; mode 7 forces it */
+        static const int tile_env = getenv("HVQM4_BAND_TILE") ? atoi(getenv("HVQM4_BAND_TILE")) : 0;
+        const bool want_tile = band_mode == 7 || ((band_mode == 0 || band_mode == 1) && tile_env == 1);
+        /* a CTA's rows are a multiple of the streams' record band: 4-row tiles (four CTAs per SM) for streams with bands
+           of 4 or 1 rows, else 8-row tiles (two CTAs per SM) */
+        const int tile = !want_tile ? 0 : (band_rows <= 4 && band_tile_fits(mcb_w, 4, 4)) ? 4 : (band_tile_fits(mcb_w, 8, 2) ? 8 : 0);
         int rc;
-        switch (per_sm)
+        switch (tile ? 0 : per_sm)
         {
+        case 0: rc = launch_band<2>(d_jobs, n_jobs, n_bands, mcb_w, stream, 0, tile, mcb_h); break;
         case 2: rc = launch_band<2>(d_jobs, n_jobs, n_bands, mcb_w, stream); break;
         case 3: rc = launch_band<3>(d_jobs, n_jobs, n_bands, mcb_w, stream); break;
         default: rc = launch_band<4>(d_jobs, n_jobs, n_bands, mcb_w, stream); break;

@@ -46,8 +46,9 @@ int hvqm4_rgb_launch(const uint8_t *const *d_frames, int n, uint8_t *d_dst, size
 /* one launch of the fused band kernel; jobs whose blob is NULL are skipped */
 /* slab: base of the registered surface slab (hvqm4_row_register_slab) the pictures' surfaces lie in, or NULL: the row
    kernel reads reference patches through tensor maps of that slab and is not used without one */
-int hvqm4_recon_launch_band(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const void *slab, cudaStream_t stream);
-int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const uint32_t *h_rec_prefix, const void *slab,
+int hvqm4_recon_launch_band(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const void *slab, int band_rows, cudaStream_t stream);
+/* band_rows: macroblock rows per record band the pictures' streams were created with (hvqm4_recon_band_rows at that time) */
+int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const uint32_t *h_rec_prefix, const void *slab, int band_rows,
                        cudaStream_t stream, int *launches);
 int hvqm4_row_register_slab(const void *base, size_t stride, int count, int width, int height);
 void hvqm4_row_unregister_slab(const void *base);

@@ -215,7 +215,9 @@ long long HVQM4KernelLaunches(void);
    (batch mode only: one persistent CTA per SM walks macroblock rows through a shared-memory
    pipeline, one reference patch per inter macroblock fetched by TMA tensor copies, output rows
    assembled in shared memory and written by bulk stores; pictures with predictions that leave
-   their plane fall to the band kernel); < 0 = always the map kernel + record kernel pair.  All give identical pictures; the switch exists for tests and
+   their plane fall to the band kernel); 7 = the band kernel with the band assembled in shared
+   memory and written by bulk stores of whole picture rows (two CTAs per SM; pictures too wide for
+   that use the plain band kernel); < 0 = always the map kernel + record kernel pair.  All give identical pictures; the switch exists for tests and
    measurements.  Process-wide. */
 void HVQM4SetReconMode(int mode);
 /* Diagnostics of the sweep kernel: launches so far; nonzero if one of its CTAs ever gave up waiting on its

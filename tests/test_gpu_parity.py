@@ -12,10 +12,10 @@ from tests.h4m_util import md5
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["two_kernels", "band_kernel", "sweep_kernel", "row_kernel"])
+@pytest.fixture(params=["two_kernels", "band_kernel", "band_tile", "sweep_kernel", "row_kernel"])
 def recon_mode(request, native_lib):
     """Every parity test runs under all three reconstruction schedules (include/hvqm4.h HVQM4SetReconMode)."""
-    native_lib.set_recon_mode({"two_kernels": -1, "band_kernel": 4, "sweep_kernel": 5, "row_kernel": 6}[request.param])
+    native_lib.set_recon_mode({"two_kernels": -1, "band_kernel": 4, "band_tile": 7, "sweep_kernel": 5, "row_kernel": 6}[request.param])
     yield request.param
     native_lib.set_recon_mode(0)
 
