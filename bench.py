@@ -125,17 +125,34 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+KERNEL_SOURCES = ("recon.cu", "recon_core.h", "recon_dev.cuh", "symbuf.h", "entropy.c")
+
+
+def kernel_sources_sha() -> str:
+    """Hash of the sources the reconstruction kernels and the symbol buffer they read are built from: a committed ncu
+    capture is only quoted next to a bench number if it was taken from the same sources."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "hvqm4_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def measured_traffic(profile: int, streams: int):
-    """DRAM bytes per step (dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of
-    one step, averaged over a GOP) from the committed ncu capture of this workload, or None."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """(DRAM bytes per step, note): dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of one step,
+    averaged over a GOP, from the committed ncu capture of this workload (tools/ncu_traffic.py) -- None when there is
+    none for these kernel sources (the capture is stamped with kernel_sources_sha())."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         with open(path) as f:
             t = json.load(f)
+        if t.get("kernel_sources_sha") != kernel_sources_sha():
+            return None, "profiles/r02_traffic.json was captured from other kernel sources (%s)" % t.get("kernel_sources_sha")
         key = f"{'dense' if profile == 0 else 'realistic'}_{streams}"
-        return t["dram_bytes_per_step"].get(key)
+        return t["dram_bytes_per_step"].get(key), "ncu capture of these kernel sources (profiles/r02_traffic.json)"
     except (OSError, KeyError, ValueError):
-        return None
+        return None, "no ncu capture committed"
 
 
 def cpu_reference_run(streams, seconds_target: float, nproc: int):
@@ -150,18 +167,80 @@ def cpu_reference_run(streams, seconds_target: float, nproc: int):
     t1, n1 = dec.bench(streams[0], 1)                      # calibration: one GOP on one core
     per_gop = max(t1, 1e-3)
     reps = max(1, int(seconds_target / per_gop))
-    wall, cpu_s, frames = dec.bench_mp(streams[0], nproc, reps)
+    wall, cpu_s, frames = dec.bench_mp_streams(streams, nproc, reps)
     return {
         "value": frames / wall, "unit": UNIT, "cores": nproc, "kind": kind,
-        "sample": f"{nproc} processes x {reps} x one 16-picture 640x480 I/P/B GOP (stream seed {BASE_SEED}), decode calls only",
+        "sample": (f"{nproc} processes x {reps} GOPs of 16 pictures each, cycling the same {len(streams)} distinct 640x480 I/P/B bitstreams "
+                   f"as the GPU arm (seeds {BASE_SEED}+), wall clock around fork..exit"),
         "single_core_fps": n1 / t1, "wall_s": wall,
     }, reps
+
+
+def reference_last_frames(files, which):
+    """MD5 of the last decoded picture (decode order) of the bitstreams `which`, from the checker -- the unmodified
+    reference (oracle/_ref) when it was built, else the oracle port.  Used only AFTER the clock has stopped."""
+    import hashlib
+    from oracle import bindings
+    dec = bindings.RefDecoder if bindings.have_ref() else bindings.PortDecoder
+    out = {}
+    for k in which:
+        last = None
+        for _, _, _, yuv in dec(files[k]).frames():
+            last = yuv
+        out[k] = hashlib.md5(last).hexdigest()
+    return out, dec.__name__
+
+
+def pcie_ceiling(torch, frame_bytes, n_frames, h2d_bytes, barrier):
+    """What this box's PCIe link gives this rank while every rank does the same: one step's read-back (n_frames frames,
+    pinned host memory) next to one step's upload, on two streams, best of three; GB/s per direction."""
+    import hashlib  # noqa: F401
+    d2h_n = n_frames * frame_bytes
+    try:
+        d_src = torch.empty(d2h_n, dtype=torch.uint8, device="cuda")
+        h_dst = torch.empty(d2h_n, dtype=torch.uint8, pin_memory=True)
+        h_src = torch.empty(max(h2d_bytes, 1 << 20), dtype=torch.uint8, pin_memory=True)
+        d_dst = torch.empty_like(h_src, device="cuda")
+    except RuntimeError:
+        return None
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    best = None
+    for _ in range(3):
+        barrier()
+        e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        with torch.cuda.stream(s1):
+            e0.record()
+            h_dst.copy_(d_src, non_blocking=True)
+            e1.record()
+        with torch.cuda.stream(s2):
+            e2.record()
+            d_dst.copy_(h_src, non_blocking=True)
+            e3.record()
+        torch.cuda.synchronize()
+        r = (d2h_n / (e0.elapsed_time(e1) * 1e-3) / 1e9, h_src.numel() / (e2.elapsed_time(e3) * 1e-3) / 1e9)
+        best = r if best is None or r[0] > best[0] else best
+    return {"d2h_gbs_per_gpu": best[0], "h2d_gbs_per_gpu": best[1]}
+
+
+def make_config(args, world):
+    """The workload both arms are measured on (identical keys and values: the driver compares them)."""
+    S = streams_per_rank(args, world)
+    return {"workload": workload_name(args), "gop": GOP, "profile": "dense" if args.profile == 0 else "realistic",
+            "streams_per_gpu": S, "distinct_bitstreams": min(S, DISTINCT_STREAMS), "pictures_per_step": S * len(GOP),
+            "scaling": args.scaling}
+
+
+def streams_per_rank(args, world):
+    """weak: --streams-per-gpu on every rank; strong: that many streams in all, split over the ranks (BASELINE config 5 as
+    written: 1024 streams sharded across the GPUs)."""
+    return args.streams_per_gpu if args.scaling == "weak" else max(1, args.streams_per_gpu // world)
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    streams = gen_streams(0, 1, args.streams_per_gpu, 1, args.profile)
+    S = streams_per_rank(args, world)
+    streams = gen_streams(0, 1, S, min(S, DISTINCT_STREAMS), args.profile)
     nproc = os.cpu_count() or 1
     t0 = time.perf_counter()
     total_frames, total_wall, base = 0, 0.0, None
@@ -176,9 +255,9 @@ def run_reference_arm(args, rank, world):
     base["value"] = value
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total_wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_wall / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "gop": GOP, "profile": "dense" if args.profile == 0 else "realistic"},
+        "config": make_config(args, world),
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
@@ -187,8 +266,9 @@ def run_reference_arm(args, rank, world):
 
 
 def workload_name(args):
-    return (f"BASELINE config 5: {args.streams_per_gpu} independent synthetic 640x480 HVQM4 1.5 I/P/B streams per GPU "
-            f"(GOP {GOP}, seeds {BASE_SEED}+, {min(args.streams_per_gpu, DISTINCT_STREAMS)} distinct bitstreams), one picture per stream per step")
+    per = "per GPU" if args.scaling == "weak" else "in all, sharded across the GPUs"
+    return (f"BASELINE config 5: {args.streams_per_gpu} independent synthetic 640x480 HVQM4 1.5 I/P/B streams {per} "
+            f"(GOP {GOP}, seeds {BASE_SEED}+), one picture per stream per step")
 
 
 def main():
@@ -197,7 +277,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams-per-gpu", type=int, default=1024)
+    ap.add_argument("--streams-per-gpu", type=int, default=1024, help="streams per GPU (weak scaling) or in all (strong scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--profile", type=int, default=0, help="0 dense (headline), 1 realistic")
     ap.add_argument("--host-threads", type=int, default=0)
     ap.add_argument("--ref-seconds", type=float, default=12.0, help="CPU seconds per process for the reference sample")
@@ -240,7 +321,8 @@ def main():
         dist.barrier()
     from hvqm4_b200 import api
 
-    S = args.streams_per_gpu
+    from hvqm4_b200 import shard
+    S = streams_per_rank(args, world)
     distinct = min(S, DISTINCT_STREAMS)
     files = gen_streams(rank, world, S, distinct, args.profile)
     parsed = [api.parse_file(f) for f in files]
@@ -268,11 +350,7 @@ def main():
             torch.cuda.synchronize()
 
     def max_over_ranks(x: float) -> float:
-        if not dist:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return shard.max_over_ranks(x, dist, "cuda")
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -304,10 +382,47 @@ def main():
     fused = batch.stats()["band_launches"] - band0 == recon_launches
     kernel_name = "recon_band_kernel (map work + records fused per band)" if fused else "recon_map_kernel + recon_record_kernel"
     frames_per_step = S * n_pics
-    value = world * frames_per_step * args.steps / (ms * 1e-3)
+    value = shard.job_throughput(frames_per_step * args.steps, world, ms * 1e-3)
     launch_ms = ms / (args.steps * n_pics)
     achieved_gbs = alg_bytes_per_gop / n_pics / (launch_ms * 1e-3) / 1e9
+    # B_out + B_ref only (no symbol bytes): every output byte once + 96 reference bytes per inter macroblock
+    pixel_gbs = (stats0["pictures"] * frame_bytes + stats0["inter_mcbs"] * 96) / n_pics / (launch_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak_gbs()
+
+    # ---- the clock has stopped: what the timed replay left in the surfaces is checked against the reference decoder
+    import hashlib
+    check_ids = sorted({0, 1, S // 2, S - 1, (S // 3) | 1, distinct - 1} & set(range(S)))
+    want_md5, checker_name = reference_last_frames(files, sorted({i % distinct for i in check_ids})) if rank == 0 else ({}, "")
+    parity = {"checker": checker_name, "replay_frames": 0, "e2e_frames": 0}
+    if rank == 0:
+        for i in check_ids:
+            got = hashlib.md5(batch.read_frame(i)).hexdigest()
+            if got != want_md5[i % distinct]:
+                raise SystemExit(f"bench.py: stream {i}: the picture left by the timed replay differs from {checker_name}")
+            parity["replay_frames"] += 1
+
+    # ---- the other scaling curve, reconstruction only: BASELINE config 5 as written shards 1024 streams across the GPUs
+    # (strong scaling: 1024 / N streams per rank); the headline line keeps --streams-per-gpu on every rank (weak)
+    strong = None
+    if world > 1 and args.scaling == "weak":
+        S2 = max(1, args.streams_per_gpu // world)
+        b2 = api.Batch(S2, W, H, 15, device=local, host_threads=threads)
+        ids2 = list(range(S2))
+        b2.record(True)
+        for k in range(n_pics):
+            frs = [parsed[i % distinct][1][k] for i in range(S2)]
+            b2.decode(ids2, [f.frame_type for f in frs], [bases[i % distinct] + frs[i].offset for i in range(S2)], [f.bytes for f in frs])
+        b2.sync()
+        b2.record(False)
+        b2.replay(args.warmup)
+        barrier()
+        l0 = api.kernel_launches()
+        ms2 = max_over_ranks(b2.replay(args.steps))
+        recon_launches += api.kernel_launches() - l0
+        barrier()
+        strong = {"value": shard.job_throughput(S2 * n_pics * args.steps, world, ms2 * 1e-3), "unit": UNIT, "scaling": "strong",
+                  "streams_per_gpu": S2, "streams_total": S2 * world, "ms_per_step": ms2 / args.steps}
+        b2.close()
 
     # ---- end to end through the C ABI with host buffers, once per entropy-stage placement
     e2e = None
@@ -359,7 +474,21 @@ def main():
         e2e = measure_e2e(gb, 12.0, "gpu (one warp per picture)")
         e2e["note"] = ("wall clock around K GOPs: raw picture bytes H2D -> entropy stage on the GPU -> reconstruction kernels -> "
                        "D2H of every frame to pinned host memory; HVQM4BatchSetEntropyMode(1)")
+        if rank == 0:
+            # the pinned buffer holds the last picture of every stream, as read back inside the timed region
+            for i in check_ids:
+                got = hashlib.md5(ctypes.string_at(pinned + i * frame_bytes, frame_bytes)).hexdigest()
+                if got != want_md5[i % distinct]:
+                    raise SystemExit(f"bench.py: stream {i}: the frame read back by the timed end-to-end run differs from {checker_name}")
+                parity["e2e_frames"] += 1
         gb.close()
+        # the link's own ceiling on this box, with every rank copying at once
+        ceil = pcie_ceiling(torch, frame_bytes, S, e2e["h2d_bytes_per_step"] // n_pics, barrier)
+        if ceil:
+            ceil["frames_per_s_ceiling"] = world * ceil["d2h_gbs_per_gpu"] * 1e9 / frame_bytes
+            e2e["pcie_ceiling"] = ceil
+            e2e["frac_of_ceiling"] = e2e["value"] / ceil["frames_per_s_ceiling"]
+            e2e["d2h_gbs_per_gpu"] = e2e["value"] / world * frame_bytes / 1e9
     sampler.stop()
     clocks = sampler.summary(windows)
 
@@ -392,7 +521,7 @@ def main():
         r_gbs = rst["algorithmic_bytes"] / n_pics / (rms / (rsteps * n_pics) * 1e-3) / 1e9
         realistic = {"value": world * frames_per_step * rsteps / (rms * 1e-3), "unit": UNIT, "achieved": r_gbs, "frac": r_gbs / peak,
                      "inter_mcb_fraction": round(rst["inter_mcbs"] / max(1, rst["total_mcbs"]), 4),
-                     "traffic": measured_traffic(1, S), "steps": rsteps}
+                     "traffic": measured_traffic(1, S)[0], "steps": rsteps}
         recon_launches += realistic_launches
         rb.close()
         if not args.no_e2e:
@@ -455,23 +584,28 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base, _ = cpu_reference_run(files, args.ref_seconds, os.cpu_count() or 1)
 
+    traffic, traffic_note = measured_traffic(args.profile, S)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u8/int32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "gop": GOP, "profile": "dense" if args.profile == 0 else "realistic",
-                       "streams_per_gpu": S, "pictures_per_step": frames_per_step, "launches_per_step": int(recon_launches // max(1, args.steps)),
-                       "inter_mcb_fraction": round(inter_frac, 4),
-                       "l2": "inputs larger than L2: one step touches %.0f MB of symbols + %.0f MB of surfaces per GPU"
-                             % (sym_bytes_per_gop / 1e6, 4 * S * frame_bytes / 1e6)},
+            "config": make_config(args, world),
+            "details": {"launches_per_step": int(recon_launches // max(1, args.steps)), "inter_mcb_fraction": round(inter_frac, 4),
+                        "host_threads_per_gpu": threads, "symbol_bytes_per_picture": round(sym_bytes_per_gop / frames_per_step),
+                        "l2": "inputs larger than L2: one step touches %.0f MB of symbols + %.0f MB of surfaces per GPU"
+                              % (sym_bytes_per_gop / 1e6, 4 * S * frame_bytes / 1e6)},
+            "parity_checked": parity,
             "mpixel_per_s": value * W * H / 1e6,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peak, "unit": "GB/s", "frac": achieved_gbs / peak,
-                         "traffic": measured_traffic(args.profile, S), "peak_source": peak_src, "kernel": kernel_name, "launch": "one step = one picture of every stream",
+                         "frac_pixel_only": pixel_gbs / peak, "achieved_pixel_only": pixel_gbs,
+                         "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src, "kernel": kernel_name, "launch": "one step = one picture of every stream",
                          "algorithmic_bytes_per_launch": alg_bytes_per_gop / n_pics, "launch_ms": launch_ms,
                          "frac_of_nominal_8TBs": achieved_gbs / 8000.0},
             "e2e": e2e, "gpu_launches": int(recon_launches + e2e_launches), "clocks": clocks,
         }
+        if strong:
+            line["strong_scaling"] = strong
         if e2e_host:
             line["e2e_host_entropy"] = e2e_host
         if realistic:

@@ -344,7 +344,9 @@ class Batch:
             pass
 
     def decode(self, stream_ids, frame_types, frame_ptrs, frame_bytes):
-        """One step.  frame_ptrs: addresses (ints) of picture headers that stay valid during the call."""
+        """One step.  frame_ptrs: addresses (ints) of picture headers that stay valid during the call -- and, when the
+        pictures lie in memory registered with HVQM4HostRegister and the entropy stage runs on the GPU, unmodified until
+        sync() returns (the GPU fetches them after the call; include/hvqm4.h)."""
         n = len(stream_ids)
         ids = (c_int32 * n)(*stream_ids)
         tys = (c_int32 * n)(*frame_types)

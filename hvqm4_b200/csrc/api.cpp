@@ -340,6 +340,9 @@ H4_API int HVQM4HostRegister(void *ptr, size_t bytes)
 
 H4_API int HVQM4HostUnregister(void *ptr)
 {
+    /* gather kernels of steps that have been submitted may still be reading the range over PCIe: they are asynchronous to
+       HVQM4BatchDecode.  Nothing of this process may touch the pages once they are unpinned. */
+    cudaDeviceSynchronize();
     std::lock_guard<std::mutex> guard(g_ranges_lock);
     for (size_t i = 0; i < g_ranges.size(); ++i)
         if (g_ranges[i].begin == (uintptr_t)ptr)
@@ -686,9 +689,25 @@ H4_API void HVQM4DevEntropyProfile(uint64_t out[8])
     for (int i = 0; i < 8; ++i) out[i] = tmp[i];
 }
 
+/* the GPU entropy stage's buffers exist together or not at all */
+static void batch_free_entropy_state(HVQM4Batch *b)
+{
+    cudaGetLastError();
+    if (b->d_estate) cudaFree(b->d_estate);
+    if (b->d_blobs) cudaFree(b->d_blobs);
+    if (b->d_blob_used) cudaFree(b->d_blob_used);
+    if (b->d_eerrors) cudaFree(b->d_eerrors);
+    b->d_estate = nullptr; b->d_blobs = nullptr; b->d_blob_used = nullptr; b->d_eerrors = nullptr;
+    b->eslot = 0;
+    b->gpu_entropy = false;
+}
+
 H4_API int HVQM4BatchSetEntropyMode(HVQM4Batch *b, int gpu)
 {
     if (!b) return HVQM4_ERR_ARGUMENT;
+    /* the two stages keep separate per-stream state (maps, the last I picture's nest): a switch after the first
+       picture would decode the following P/B pictures against state the other stage never saw */
+    if (b->stats[0] > 0 && (gpu != 0) != b->gpu_entropy) return HVQM4_ERR_ARGUMENT;
     cudaSetDevice(b->device);
     if (!cuda_ok(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return HVQM4_ERR_CUDA;
     if (!gpu)
@@ -713,9 +732,16 @@ H4_API int HVQM4BatchSetEntropyMode(HVQM4Batch *b, int gpu)
             !cuda_ok(cudaMalloc((void **)&b->d_blob_used, H4_PARSE_SLOTS * sizeof(unsigned long long)), "cudaMalloc") ||
             !cuda_ok(cudaMalloc((void **)&b->d_eerrors, sizeof(uint32_t)), "cudaMalloc") ||
             !cuda_ok(cudaMemset(b->d_eerrors, 0, sizeof(uint32_t)), "cudaMemset"))
+        {
+            batch_free_entropy_state(b);      /* all or nothing: a later call starts over */
             return HVQM4_ERR_NOMEM;
+        }
         int rc = hvqm4_dev_entropy_init(b->d_estate, b->eslot, b->n_streams, b->width, b->height, b->version15, sym_cap, work_cap, b->s_comp);
-        if (rc != 0 || !cuda_ok(cudaStreamSynchronize(b->s_comp), "GPU entropy state init")) return HVQM4_ERR_CUDA;
+        if (rc != 0 || !cuda_ok(cudaStreamSynchronize(b->s_comp), "GPU entropy state init"))
+        {
+            batch_free_entropy_state(b);
+            return HVQM4_ERR_CUDA;
+        }
     }
     b->gpu_entropy = true;
     return HVQM4_OK;

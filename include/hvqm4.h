@@ -152,7 +152,10 @@ int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, const int3
  * (one warp per picture runs the same parser, compiled as device code; only raw picture bytes are
  * uploaded, symbol buffers never exist on the host).  Both give identical pictures.  The switch
  * must be made before the first HVQM4BatchDecode of the batch: the two stages keep separate
- * per-stream state.  Recording (HVQM4BatchRecord) needs the host stage.
+ * per-stream state, and a switch after the first picture is refused (HVQM4_ERR_ARGUMENT).  If the
+ * device buffers of the GPU stage cannot be allocated the call returns HVQM4_ERR_NOMEM / _CUDA,
+ * the batch stays on the host stage and the call may be repeated.  Recording (HVQM4BatchRecord)
+ * needs the host stage.
  */
 int HVQM4BatchSetEntropyMode(HVQM4Batch *b, int gpu);
 
@@ -238,8 +241,12 @@ void HVQM4HostFree(void *p);
    (separately allocated buffers): a page stays registered until its last range is unregistered.
    It frees host cores, it is not faster (measured on B200, 1 024 streams, frames read back: dense
    97.6 k vs 105 k frames/s with 16 host threads, 95 k vs 92 k with 2; realistic 122 k vs 121 k and
-   109 k vs 119 k), so nothing registers memory implicitly.  Unregister before the memory is freed.
-   Returns HVQM4_OK or error bits. */
+   109 k vs 119 k), so nothing registers memory implicitly.
+   LIFETIME: in this mode the GPU reads the picture bytes AFTER HVQM4BatchDecode has returned
+   (frames[i] is otherwise only read during the call): they must stay unmodified until
+   HVQM4BatchSync returns, or until the step four submissions later has been submitted (the ring of
+   staging arenas).  HVQM4HostUnregister waits for the device to go idle first; unregister before
+   the memory is freed.  Returns HVQM4_OK or error bits. */
 int HVQM4HostRegister(void *ptr, size_t bytes);
 int HVQM4HostUnregister(void *ptr);
 

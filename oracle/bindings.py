@@ -176,6 +176,24 @@ class _Decoder:
         return out[0], out[1], int(out[2])
 
 
+    @classmethod
+    def bench_mp_streams(cls, datas, nproc: int, reps: int):
+        """nproc forked workers cycle through `datas` (worker i: streams i, i + nproc, ...), `reps` GOP decodes each:
+        (wall seconds, sum of in-decode seconds, total frames)."""
+        n = len(datas)
+        bufs = [ctypes.create_string_buffer(d, len(d)) for d in datas]
+        ptrs = (ctypes.c_char_p * n)(*[ctypes.cast(b, ctypes.c_char_p) for b in bufs])
+        lens = (ctypes.c_size_t * n)(*[len(d) for d in datas])
+        out = (ctypes.c_double * 3)()
+        fn = getattr(cls._lib(), cls._prefix + "bench_mp_streams")
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+        rc = fn(ptrs, lens, n, nproc, reps, out)
+        if rc:
+            raise RuntimeError(f"bench_mp_streams failed {rc}")
+        return out[0], out[1], int(out[2])
+
+
 class RefDecoder(_Decoder):
     _prefix = "ref_"
     _path = REF_LIB

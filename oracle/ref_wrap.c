@@ -405,6 +405,55 @@ REF_API int ref_bench_mp(const uint8_t *data, size_t len, int nproc, int reps, d
     return rc;
 }
 
+/*
+ * The same over a SET of streams: worker i decodes streams i, i + nproc, i + 2 nproc, ... (cyclically) once each,
+ * `reps` GOP decodes in all -- the bounded CPU sample of bench.py cycles the same distinct bitstreams as the GPU arm.
+ */
+REF_API int ref_bench_mp_streams(const uint8_t *const *datas, const size_t *lens, int n_streams, int nproc, int reps, double out[3])
+{
+    int (*pipes)[2] = malloc(sizeof(int[2]) * nproc);
+    pid_t *pids = malloc(sizeof(pid_t) * nproc);
+    double t0 = now_s();
+    for (int i = 0; i < nproc; ++i)
+    {
+        if (pipe(pipes[i])) return -1;
+        pids[i] = fork();
+        if (pids[i] == 0)
+        {
+            close(pipes[i][0]);
+            double msg[2] = {0, 0};
+            for (int r = 0; r < reps; ++r)
+            {
+                const int k = (int)(((long)i + (long)r * nproc) % n_streams);
+                long f;
+                msg[0] += bench_once(datas[k], lens[k], 1, &f);
+                msg[1] += (double)f;
+            }
+            if (write(pipes[i][1], msg, sizeof msg) != sizeof msg) _exit(1);
+            _exit(0);
+        }
+        close(pipes[i][1]);
+    }
+    double tsum = 0, fsum = 0;
+    int rc = 0;
+    for (int i = 0; i < nproc; ++i)
+    {
+        double msg[2] = {0, 0};
+        if (read(pipes[i][0], msg, sizeof msg) != sizeof msg) rc = -2;
+        close(pipes[i][0]);
+        int st;
+        waitpid(pids[i], &st, 0);
+        tsum += msg[0];
+        fsum += msg[1];
+    }
+    out[0] = now_s() - t0;
+    out[1] = tsum;
+    out[2] = fsum;
+    free(pipes);
+    free(pids);
+    return rc;
+}
+
 /* ---- leaf operators, exported for per-operator unit tests ---- */
 
 REF_API void ref_WeightImBlock(uint8_t *dst, uint32_t stride, uint8_t v, uint8_t t, uint8_t b, uint8_t l, uint8_t r)

@@ -520,6 +520,51 @@ def test_staggered_streams_and_partial_steps_match_oracle(native_lib, oracle, gp
         native_lib.lib().HVQM4HostFree(pinned)
 
 
+def test_entropy_mode_switch_after_the_first_picture_is_refused(native_lib, golden):
+    """The host and the GPU entropy stage keep separate per-stream state: switching once pictures have been decoded
+    would reconstruct the next P/B pictures against the wrong nest.  Same mode again is fine."""
+    case = golden["cfg4_320x240_v13_IPB"]
+    data = synth.generate(**case["args"])
+    info, frames = native_lib.parse_file(data)
+    buf = ctypes.create_string_buffer(data, len(data) + 8)
+    lib = native_lib.lib()
+    batch = native_lib.Batch(1, info.width, info.height, info.version)
+    try:
+        fr = frames[0]
+        batch.decode([0], [fr.frame_type], [ctypes.addressof(buf) + fr.offset], [fr.bytes])
+        batch.sync()
+        assert lib.HVQM4BatchSetEntropyMode(batch._h, 1) != 0
+        assert lib.HVQM4BatchSetEntropyMode(batch._h, 0) == 0
+        for k, fr in enumerate(frames[1:], 1):
+            batch.decode([0], [fr.frame_type], [ctypes.addressof(buf) + fr.offset], [fr.bytes])
+            batch.sync()
+            assert md5(batch.read_frame(0)) == case["md5"][k]
+    finally:
+        batch.close()
+
+
+def test_unregister_waits_for_pictures_still_being_fetched(native_lib, oracle):
+    """In gather mode the GPU reads the registered picture bytes after HVQM4BatchDecode has returned; unregistering right
+    behind the call must wait for those reads (and the application may overwrite the bytes once sync() has returned)."""
+    n = 24
+    data = synth.generate(320, 240, 15, "I", 1, seed=8800, profile=0)
+    want = [md5(yuv) for _, _, _, yuv in oracle.PortDecoder(data).frames()][0]
+    fr = native_lib.parse_file(data)[1][0]
+    image = ctypes.create_string_buffer(data, len(data) + 64)
+    base = ctypes.addressof(image)
+    lib = native_lib.lib()
+    assert lib.HVQM4HostRegister(base, len(data)) == 0
+    batch = native_lib.Batch(n, 320, 240, 15, gpu_entropy=True)
+    try:
+        batch.decode(list(range(n)), [fr.frame_type] * n, [base + fr.offset] * n, [fr.bytes] * n)
+        assert lib.HVQM4HostUnregister(base) == 0          # no sync in between
+        ctypes.memset(base, 0xEE, len(data))               # the application reuses its buffer
+        batch.sync()
+        assert all(md5(batch.read_frame(i)) == want for i in range(n))
+    finally:
+        batch.close()
+
+
 def test_registered_host_memory_is_gathered_by_the_gpu(native_lib, oracle):
     """HVQM4HostRegister: with the bitstreams in page-locked, mapped application memory the GPU entropy mode
     fetches the pictures itself (dev_gather_kernel) -- same frames as the oracle, every source alignment
