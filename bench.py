@@ -314,6 +314,18 @@ def main():
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
 
+    # every rank keeps its host threads (bitstream copies, host entropy stage) and its pinned arenas on its own share of
+    # the cores: without this the ranks' threads wander over all cores of the box and share caches with each other
+    cores = sorted(os.sched_getaffinity(0))
+    if world > 1 and len(cores) >= world:
+        mine = cores[rank * len(cores) // world:(rank + 1) * len(cores) // world]
+        try:
+            os.sched_setaffinity(0, mine)
+        except OSError:
+            mine = cores
+    else:
+        mine = cores
+
     import __graft_entry__
     if rank == 0:
         __graft_entry__.build()
@@ -329,7 +341,7 @@ def main():
     bufs = [ctypes.create_string_buffer(f, len(f) + 8) for f in files]
     bases = [ctypes.addressof(b) for b in bufs]
     n_pics = len(parsed[0][1])
-    threads = args.host_threads or max(1, (os.cpu_count() or 1) // world)
+    threads = args.host_threads or max(1, len(mine))
     batch = api.Batch(S, W, H, 15, device=local, host_threads=threads)
     ids = list(range(S))
     steps = []
@@ -592,7 +604,7 @@ def main():
             "dtype": "u8/int32", "data": "synthetic",
             "config": make_config(args, world),
             "details": {"launches_per_step": int(recon_launches // max(1, args.steps)), "inter_mcb_fraction": round(inter_frac, 4),
-                        "host_threads_per_gpu": threads, "symbol_bytes_per_picture": round(sym_bytes_per_gop / frames_per_step),
+                        "host_threads_per_gpu": threads, "host_cores_of_rank0": f"{mine[0]}-{mine[-1]}", "symbol_bytes_per_picture": round(sym_bytes_per_gop / frames_per_step),
                         "l2": "inputs larger than L2: one step touches %.0f MB of symbols + %.0f MB of surfaces per GPU"
                               % (sym_bytes_per_gop / 1e6, 4 * S * frame_bytes / 1e6)},
             "parity_checked": parity,

@@ -45,6 +45,16 @@ CASES = {
     "small_64x48_v13_IPB": dict(width=64, height=48, version=13, gop="IPBBPB", n_gops=2, seed=208, profile=0),
     "mirror_h_200x152_v15_IPB": dict(width=200, height=152, version=15, gop="IPBB", n_gops=2, seed=209, profile=0),
     "mirror_v_320x104_v15_IPB": dict(width=320, height=104, version=15, gop="IPBB", n_gops=2, seed=210, profile=0),
+    # the generator's stress profile: what the reference accepts and an encoder rarely emits (block types 7 and 9..255 in
+    # I-picture luma = that many bases, nibbles 7 and 9..15 elsewhere -- up to 14 bases per predicted block --, scale
+    # symbols to 255, dc_shift 0..3, unk_shift 6..12, escape chains, run counts >= 255, rb 0..3; h4m:1358-1459, 654-677)
+    "stress_640x480_v15_IPB": dict(width=640, height=480, version=15, gop="I" + "PBB" * 3, n_gops=2, seed=301, profile=2),
+    "stress_320x240_v13_IPB": dict(width=320, height=240, version=13, gop="I" + "PBB" * 5, n_gops=2, seed=302, profile=2),
+    "stress_328x248_v15_IPB": dict(width=328, height=248, version=15, gop="IPBBPB", n_gops=2, seed=303, profile=2),
+    "stress_64x48_v15_IPB": dict(width=64, height=48, version=15, gop="IPBBPB", n_gops=3, seed=304, profile=2),
+    # every luma block of the I pictures carries 16 / 17 bases: at / beyond the symbol capacity of the GPU entropy stage
+    "cap16_320x240_v15_I": dict(width=320, height=240, version=15, gop="II", n_gops=1, seed=305, profile=3),
+    "cap17_320x240_v15_I": dict(width=320, height=240, version=15, gop="II", n_gops=1, seed=306, profile=4),
 }
 
 

@@ -23,7 +23,9 @@ SDK_CASES = ["cfg1_320x240_v15_I30", "cfg2_640x480_v15_IP15", "cfg3_640x480_v15_
              "realistic_640x480_v15_IPB", "realistic_320x240_v13_IPB", "min_280x152_v15_IPB",
              "ragged_328x248_v15_IPB", "wide_1024x576_v13_IPB", "hd_1280x720_v15_IPB",
              "tiny_16x16_v15_IPB", "small_64x48_v13_IPB", "mirror_h_200x152_v15_IPB", "mirror_v_320x104_v15_IPB",
-             "uhd_4096x2160_v15_IPB"]
+             "uhd_4096x2160_v15_IPB",
+             "stress_640x480_v15_IPB", "stress_320x240_v13_IPB", "stress_328x248_v15_IPB", "stress_64x48_v15_IPB",
+             "cap16_320x240_v15_I", "cap17_320x240_v15_I"]
 
 
 @pytest.mark.parametrize("name", SDK_CASES)
@@ -259,12 +261,59 @@ def test_gpu_entropy_stage_matches_golden(native_lib, golden):
 
 @pytest.mark.parametrize("name", ["cfg4_320x240_v13_IPB", "realistic_640x480_v15_IPB", "ragged_328x248_v15_IPB", "wide_1024x576_v13_IPB",
                                   "hd_1280x720_v15_IPB", "tiny_16x16_v15_IPB", "small_64x48_v13_IPB", "mirror_h_200x152_v15_IPB",
-                                  "uhd_4096x2160_v15_IPB"])
+                                  "uhd_4096x2160_v15_IPB", "stress_640x480_v15_IPB", "stress_320x240_v13_IPB", "stress_328x248_v15_IPB",
+                                  "stress_64x48_v15_IPB"])
 def test_gpu_entropy_stage_other_geometries(native_lib, golden, name):
     case = golden[name]
     data = synth.generate(**case["args"])
     got = [md5(frames[0][2]) for frames in native_lib.decode_streams([data, data], gpu_entropy=True)]
     assert got == case["md5"]
+
+
+@pytest.mark.parametrize("mode", [-1, 4, 6, 7])
+def test_batch_runtime_matches_golden_stress(native_lib, golden, mode):
+    """The generator's stress profile (long basis lists, wide shifts, escape chains, long runs) through the batch runtime
+    under every reconstruction schedule that serves batches."""
+    native_lib.set_recon_mode(mode)
+    try:
+        for name in ("stress_640x480_v15_IPB", "stress_320x240_v13_IPB"):
+            case = golden[name]
+            data = synth.generate(**case["args"])
+            got = [[md5(f[2]) for f in frames] for frames in native_lib.decode_streams([data] * 5)]
+            assert got == [[m] * 5 for m in case["md5"]], (name, mode)
+    finally:
+        native_lib.set_recon_mode(0)
+
+
+def test_gpu_entropy_stage_symbol_capacity(native_lib, golden):
+    """The GPU entropy stage holds 16 symbols per block of a section's plane (api.cpp).  I pictures whose every luma block
+    carries 16 bases sit exactly at that capacity and decode; with 17 bases per block the section no longer fits: the
+    picture is reported as truncated (error bit, no CUDA fault) -- the host stage decodes both.  The heavy stream shares
+    its step with light ones: the device symbol arena of a step is sized for twice the frame bytes per stream on average."""
+    light = synth.generate(320, 240, 15, "II", 1, seed=307, profile=1)
+    for name, fits in (("cap16_320x240_v15_I", True), ("cap17_320x240_v15_I", False)):
+        case = golden[name]
+        data = synth.generate(**case["args"])
+        assert [md5(frames[0][2]) for frames in native_lib.decode_streams([data, data])] == case["md5"]      # host stage
+        files = [data] + [light] * 5
+        parsed = [native_lib.parse_file(f) for f in files]
+        bufs = [ctypes.create_string_buffer(f, len(f) + 8) for f in files]
+        batch = native_lib.Batch(len(files), 320, 240, 15, gpu_entropy=True)
+        try:
+            errors = 0
+            for k in range(2):
+                frs = [p[1][k] for p in parsed]
+                batch.decode(list(range(len(files))), [f.frame_type for f in frs],
+                             [ctypes.addressof(bufs[i]) + frs[i].offset for i in range(len(files))], [f.bytes for f in frs])
+                try:
+                    batch.sync()
+                except native_lib.HVQM4Error as e:
+                    errors |= e.bits
+                if fits:
+                    assert md5(batch.read_frame(0)) == case["md5"][k]
+            assert (errors == 0) == fits, (name, hex(errors))
+        finally:
+            batch.close()
 
 
 def _decode_damaged(native_lib, files, gpu_entropy):

@@ -12,7 +12,9 @@ from tests.h4m_util import demux, emul_decode, md5
 @pytest.mark.parametrize("name", [
     "cfg1_320x240_v15_I30", "cfg3_640x480_v15_IPB", "cfg4_320x240_v13_IPB", "cfg5_stream511",
     "realistic_640x480_v15_IPB", "min_280x152_v15_IPB", "ragged_328x248_v15_IPB", "wide_1024x576_v13_IPB",
-    "hd_1280x720_v15_IPB", "tiny_16x16_v15_IPB", "small_64x48_v13_IPB", "mirror_h_200x152_v15_IPB", "mirror_v_320x104_v15_IPB"])
+    "hd_1280x720_v15_IPB", "tiny_16x16_v15_IPB", "small_64x48_v13_IPB", "mirror_h_200x152_v15_IPB", "mirror_v_320x104_v15_IPB",
+    "stress_640x480_v15_IPB", "stress_320x240_v13_IPB", "stress_328x248_v15_IPB", "stress_64x48_v15_IPB", "cap16_320x240_v15_I",
+    "cap17_320x240_v15_I"])
 def test_emulated_pipeline_matches_golden(emul_lib, golden, name):
     case = golden[name]
     got = list(emul_decode(emul_lib, synth.generate(**case["args"])))
@@ -29,7 +31,8 @@ def test_emulated_pipeline_matches_port_on_fresh_seeds(emul_lib, oracle):
 
 
 @pytest.mark.parametrize("name", ["cfg3_640x480_v15_IPB", "cfg4_320x240_v13_IPB", "cfg5_stream511", "realistic_640x480_v15_IPB",
-                                  "wide_1024x576_v13_IPB", "hd_1280x720_v15_IPB", "small_64x48_v13_IPB"])
+                                  "wide_1024x576_v13_IPB", "hd_1280x720_v15_IPB", "small_64x48_v13_IPB", "stress_640x480_v15_IPB",
+                                  "stress_320x240_v13_IPB"])
 @pytest.mark.parametrize("kernel", ["sweep", "row"])
 def test_emulated_pipeline_kernels_match_golden(emul_lib, golden, name, kernel):
     """The shared-memory pipeline kernels (sweep.cu, row.cu): plan, slots, rings, lists and tasks run serially on the CPU.
@@ -41,7 +44,10 @@ def test_emulated_pipeline_kernels_match_golden(emul_lib, golden, name, kernel):
         got = list(emul_decode(emul_lib, synth.generate(**case["args"]), stats=stats, **kw))
         assert [md5(yuv) for _, yuv, _ in got] == case["md5"], (kernel, look)
         if kernel == "row" and case["args"]["width"] % 32 == 0 and case["args"]["width"] <= 1024:
-            assert stats.get("row", 0) == len(got), stats      # every picture of these streams is served by the row kernel
+            if "stress" in name:      # a row with more chunk descriptors than a slot holds leaves the picture to the band kernel
+                assert stats.get("row", 0) >= len(got) // 2, stats
+            else:
+                assert stats.get("row", 0) == len(got), stats      # every picture of these streams is served by the row kernel
 
 
 @pytest.mark.parametrize("args", [

@@ -30,7 +30,7 @@ def test_port_matches_golden(oracle, golden, name):
 def test_reference_build_matches_golden(oracle, golden):
     if not oracle.have_ref():
         pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
-    for name in ("cfg1_320x240_v15_I30", "cfg4_320x240_v13_IPB", "cfg5_stream1"):
+    for name in ("cfg1_320x240_v15_I30", "cfg4_320x240_v13_IPB", "cfg5_stream1", "stress_320x240_v13_IPB", "cap17_320x240_v15_I"):
         case = golden[name]
         got = oracle.RefDecoder.md5s(synth.generate(**case["args"]))
         assert [m for _, _, m in got] == case["md5"], name
@@ -40,7 +40,8 @@ def test_port_matches_reference_maps_and_sections(oracle):
     """Beyond pixels: block maps, nest and per-section consumption agree picture by picture."""
     if not oracle.have_ref():
         pytest.skip("oracle/_ref not built")
-    for seed, (w, h, v, gop, prof) in enumerate([(320, 240, 15, "IPBBPBB", 0), (640, 480, 13, "IPBB", 0), (328, 248, 15, "IPB", 1)]):
+    for seed, (w, h, v, gop, prof) in enumerate([(320, 240, 15, "IPBBPBB", 0), (640, 480, 13, "IPBB", 0), (328, 248, 15, "IPB", 1),
+                                                 (320, 240, 15, "IPBBPBB", 2), (640, 480, 13, "IPBB", 2), (320, 240, 15, "I", 4)]):
         data = synth.generate(w, h, v, gop, 2, seed=900 + seed, profile=prof)
         a, b = oracle.RefDecoder(data), oracle.PortDecoder(data)
         for fa, fb in zip(a.frames(), b.frames()):

@@ -40,7 +40,11 @@ typedef struct
     int32_t width, height;   /* multiples of 8, >= 16; below 280x152 the nest is mirrored / zero-filled (h4m:1173-1203) */
     int32_t version;         /* 13 or 15 */
     int32_t n_gops;
-    int32_t profile;         /* 0 = dense (worst case), 1 = realistic (sparse, coherent motion) */
+    int32_t profile;         /* 0 = dense (worst case), 1 = realistic (sparse, coherent motion), 2 = stress: dense plus everything the
+                                reference accepts and an encoder rarely emits (block types 7 and 9..255 = that many bases in I-picture
+                                luma, nibbles 7 and 9..15 elsewhere, scale symbols to 255, dc_shift 0..3, unk_shift 6..12, escape
+                                chains, run lengths >= 255, rb 0..3), 3 / 4 = every luma block of an I picture carries 16 / 17 bases
+                                (at / beyond the symbol capacity of the GPU entropy stage) */
     int32_t usec_per_frame;
     uint64_t seed;
     const char *gop;         /* decode-order pattern, e.g. "IPPP" or "IPBBPBB"; must start with I */
@@ -251,9 +255,19 @@ typedef struct
 
 /* -- distributions -------------------------------------------------- */
 
-static int pick_intra_type(Gen *g)
+static int prof_dense(const Gen *g) { return g->prm->profile != 1; }
+static int prof_stress(const Gen *g) { return g->prm->profile >= 2; }
+
+/* luma_ipic: the block type is a whole byte there (h4m:1433-1459: type n = n bases), a nibble everywhere else */
+static int pick_intra_type_ex(Gen *g, int luma_ipic)
 {
-    if (g->prm->profile == 0)
+    if (g->prm->profile == 3 || g->prm->profile == 4) return luma_ipic ? 13 + g->prm->profile : 0;
+    if (prof_stress(g) && chance(&g->rng, 12))
+    {
+        if (luma_ipic) return chance(&g->rng, 8) ? rnd_range(&g->rng, 41, 255) : chance(&g->rng, 50) ? 7 : rnd_range(&g->rng, 9, 40);
+        return chance(&g->rng, 40) ? 7 : rnd_range(&g->rng, 9, 15);
+    }
+    if (prof_dense(g))
     {
         static const uint8_t t[11] = {0, 0, 0, 8, 8, 1, 2, 3, 4, 5, 6};
         return t[rnd(&g->rng, 11)];
@@ -261,13 +275,16 @@ static int pick_intra_type(Gen *g)
     uint32_t x = rnd(&g->rng, 100);
     return x < 70 ? 0 : x < 80 ? 8 : x < 90 ? 1 : x < 95 ? 2 : x < 98 ? 3 : 6;
 }
+static int pick_intra_type(Gen *g) { return pick_intra_type_ex(g, 0); }
 
 static int pick_inter_nibble(Gen *g, int window_ok)
 {
-    if (g->prm->profile == 0)
+    if (prof_dense(g))
     {
         if (window_ok)
         {
+            /* k = k - 1 bases (h4m:1383); 8 is not a flat block here but 7 bases */
+            if (prof_stress(g) && chance(&g->rng, 12)) return rnd_range(&g->rng, 7, 15);
             static const uint8_t t[10] = {0, 0, 0, 6, 1, 2, 3, 4, 5, 2};
             return t[rnd(&g->rng, 10)];
         }
@@ -280,13 +297,19 @@ static int pick_inter_nibble(Gen *g, int window_ok)
 
 static int pick_zero_run(Gen *g)
 {
-    if (g->prm->profile == 0) return chance(&g->rng, 30) ? rnd_range(&g->rng, 1, 5) : 0;
+    if (prof_stress(g) && chance(&g->rng, 3)) return rnd_range(&g->rng, 200, 255);      /* the run length is one symbol: at most 255 */
+    if (prof_dense(g)) return chance(&g->rng, 30) ? rnd_range(&g->rng, 1, 5) : 0;
     return chance(&g->rng, 60) ? rnd_range(&g->rng, 1, 24) : 0;
 }
 
 static int32_t pick_dc_delta(Gen *g)
 {
-    if (g->prm->profile == 0)
+    if (prof_stress(g) && chance(&g->rng, 3))
+    {   /* a chain of escapes (h4m:654-664), both signs, also ending exactly on a multiple of the escape value */
+        int32_t m = chance(&g->rng, 30) ? 127 * rnd_range(&g->rng, 1, 6) : rnd_range(&g->rng, 300, 1500);
+        return chance(&g->rng, 50) ? m : -m - 1;
+    }
+    if (prof_dense(g))
     {
         if (chance(&g->rng, 6))
         {   /* needs one or more escape symbols */
@@ -304,7 +327,8 @@ static void emit_bases(Gen *g, Pic *p, int plane, int n)
     for (int k = 0; k < n; ++k)
     {
         put16(&p->fix[plane], rnd(&g->rng, 0x10000));
-        op_sym(&p->ops[S_SC[plane]], g->prm->profile == 0 ? rnd(&g->rng, 6) : rnd(&g->rng, 4));
+        if (prof_stress(g) && chance(&g->rng, 10)) op_sym(&p->ops[S_SC[plane]], rnd(&g->rng, 256));   /* scale_sum wraps mod 2^32 in the products */
+        else op_sym(&p->ops[S_SC[plane]], prof_dense(g) ? rnd(&g->rng, 6) : rnd(&g->rng, 4));
     }
 }
 static void emit_raw(Gen *g, Pic *p, int plane)
@@ -317,8 +341,8 @@ static void emit_raw(Gen *g, Pic *p, int plane)
 static void gen_ipic(Gen *g, Pic *p, uint8_t hdr[8])
 {
     Rng *r = &g->rng;
-    int dc_shift = rnd(r, 2);
-    int unk_shift = g->prm->profile == 0 ? rnd_range(r, 8, 10) : 10;
+    int dc_shift = prof_stress(g) ? (int)rnd(r, 4) : (int)rnd(r, 2);
+    int unk_shift = prof_stress(g) ? rnd_range(r, 6, 12) : prof_dense(g) ? rnd_range(r, 8, 10) : 10;
     /* pictures narrower / lower than the nest take MakeNest's mirror + zero-fill path (h4m:1173-1203): origin 0 */
     int nest_x = g->bw[0] >= 70 ? (int)rnd(r, g->bw[0] - 70 + 1) : 0, nest_y = g->bh[0] >= 38 ? (int)rnd(r, g->bh[0] - 38 + 1) : 0;
     hdr[0] = dc_shift; hdr[1] = unk_shift; hdr[2] = 0; hdr[3] = 0;
@@ -332,7 +356,7 @@ static void gen_ipic(Gen *g, Pic *p, uint8_t hdr[8])
         for (int i = 0; i < g->bw[0] * g->bh[0]; ++i)
         {
             if (run) { type[0][i] = 0; --run; continue; }
-            int t = pick_intra_type(g);
+            int t = pick_intra_type_ex(g, 1);
             type[0][i] = t;
             op_sym(&p->ops[S_BN_Y], t);
             if (t == 0) { run = pick_zero_run(g); op_sym(&p->ops[S_BNR_Y], run); }
@@ -356,11 +380,11 @@ static void gen_ipic(Gen *g, Pic *p, uint8_t hdr[8])
         for (int i = 0; i < g->bw[pl] * g->bh[pl]; ++i)
         {
             if (run) { --run; continue; }
-            int32_t d = chance(r, g->prm->profile == 0 ? 30 : 50) ? 0 : pick_dc_delta(g);
+            int32_t d = chance(r, prof_dense(g) ? 30 : 50) ? 0 : pick_dc_delta(g);
             op_sovf(&p->ops[S_DC[pl]], d);
             if (d == 0)
             {
-                run = g->prm->profile == 0 ? rnd(r, 6) : rnd(r, 12);
+                run = prof_stress(g) && chance(r, 3) ? rnd_range(r, 200, 255) : prof_dense(g) ? rnd(r, 6) : rnd(r, 12);
                 op_sym(&p->ops[S_X0 + pl], run);
             }
         }
@@ -411,12 +435,12 @@ static void emit_mv(Ops *o, int *pred, int target, int rb)
 static void gen_pbpic(Gen *g, Pic *p, uint8_t hdr[8], int is_b)
 {
     Rng *r = &g->rng;
-    const int dense = g->prm->profile == 0;
-    int dc_shift = rnd(r, 2);
-    int unk_shift = dense ? rnd_range(r, 8, 10) : 10;
+    const int dense = prof_dense(g), stress = prof_stress(g);
+    int dc_shift = stress ? (int)rnd(r, 4) : (int)rnd(r, 2);
+    int unk_shift = stress ? rnd_range(r, 6, 12) : dense ? rnd_range(r, 8, 10) : 10;
     int rb[2][2];   /* [ref][h/v] */
     for (int f = 0; f < 2; ++f)
-        for (int a = 0; a < 2; ++a) rb[f][a] = rnd_range(r, 1, 2);
+        for (int a = 0; a < 2; ++a) rb[f][a] = stress ? rnd_range(r, 0, 3) : rnd_range(r, 1, 2);
     hdr[0] = dc_shift; hdr[1] = unk_shift;
     hdr[2] = rb[0][0]; hdr[3] = rb[0][1]; hdr[4] = rb[1][0]; hdr[5] = rb[1][1];
     hdr[6] = 0; hdr[7] = 0;
@@ -431,7 +455,9 @@ static void gen_pbpic(Gen *g, Pic *p, uint8_t hdr[8], int is_b)
     /* macroblock types: random walk; P pictures never use type 2 (h4m:2060) */
     {
         int t = dense ? (int)rnd(r, is_b ? 3 : 2) : 1;
-        int change = dense ? 15 : 4;
+        /* stress: some pictures change type / proc so rarely that the run counts need escapes (>= 255, h4m:667-677) */
+        const int long_runs = stress && chance(r, 40);
+        int change = long_runs ? 1 : dense ? 15 : 4;
         for (int i = 0; i < nmb; ++i)
         {
             if (i && chance(r, change))
@@ -446,7 +472,7 @@ static void gen_pbpic(Gen *g, Pic *p, uint8_t hdr[8], int is_b)
         for (int i = 0; i < nmb; ++i)
         {
             if (mtype[i] == 0) { mproc[i] = 0; continue; }
-            if (chance(r, dense ? 20 : 10)) pr ^= 1;
+            if (chance(r, long_runs ? 1 : dense ? 20 : 10)) pr ^= 1;
             if (!dense && pr == 0 && chance(r, 50)) pr = 1;
             mproc[i] = pr;
         }
@@ -575,6 +601,7 @@ static void gen_pbpic(Gen *g, Pic *p, uint8_t hdr[8], int is_b)
                     int32_t s1 = dense ? rnd_range(r, -40, 40) : rnd_range(r, -10, 10);
                     int32_t s2 = dense ? rnd_range(r, -48, 48) : rnd_range(r, -8, 8);
                     if (dense && chance(r, 4)) s1 = chance(r, 50) ? rnd_range(r, 127, 260) : -rnd_range(r, 128, 260);
+                    if (stress && chance(r, 4)) s2 = chance(r, 50) ? rnd_range(r, 127, 2000) : -rnd_range(r, 128, 2000);
                     op_sovf(&p->dc_pass2[pl], s1);
                     op_sovf(&p->dc_pass2[pl], s2);
                 }
@@ -752,7 +779,7 @@ int main(int argc, char **argv)
 {
     if (argc < 9)
     {
-        fprintf(stderr, "usage: %s out.h4m W H version(13|15) gop n_gops seed profile(0 dense|1 realistic)\n", argv[0]);
+        fprintf(stderr, "usage: %s out.h4m W H version(13|15) gop n_gops seed profile(0 dense|1 realistic|2 stress|3,4 capacity)\n", argv[0]);
         return 2;
     }
     H4MGenParams p = {atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[6]), atoi(argv[8]), 0,
