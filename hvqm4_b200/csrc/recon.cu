@@ -150,8 +150,8 @@ __device__ __forceinline__ void map_segment(const ReconView &v, int row, int mx0
 
 struct BandOut;
 template <bool kTile> __device__ __forceinline__ uint32_t block_off(const ReconView &v, const BandOut &o, int plane, int bx, int by, int &pw);
-template <bool kTile> __device__ __forceinline__ void block_st(const ReconView &v, uint32_t off, uint32_t val);
-template <bool kTile> __device__ __forceinline__ uint32_t block_ld(const ReconView &v, uint32_t off);
+template <bool kTile> __device__ __forceinline__ void block_st(uint8_t *base, uint32_t off, uint32_t val);
+template <bool kTile> __device__ __forceinline__ uint32_t block_ld(const uint8_t *base, uint32_t off);
 
 /* RECORD work of one chunk: one record per lane */
 template <bool kTile>
@@ -167,15 +167,16 @@ __device__ __forceinline__ void record_chunk(const ReconView &v, const BandOut &
     rc_record_coords(__ldg(rec), t, plane, bx, by);
     int pw;
     const uint32_t dst = block_off<kTile>(v, o, plane, bx, by, pw);
+    uint8_t *const pic = v.present;
     uint32_t rows[4];
     if (cls == SYM_REC_INTER)
     {   /* the prediction left by the map work; L2-coherent loads (it may have been written by another warp) */
 #pragma unroll
-        for (int r = 0; r < 4; ++r) rows[r] = block_ld<kTile>(v, dst + r * pw);
+        for (int r = 0; r < 4; ++r) rows[r] = block_ld<kTile>(pic, dst + r * pw);
     }
     rc_record_block(v, cls, len, rec, rows);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) block_st<kTile>(v, dst + r * pw, rows[r]);
+    for (int r = 0; r < 4; ++r) block_st<kTile>(pic, dst + r * pw, rows[r]);
 }
 
 /* the same with the chunk descriptor, the lane's header word and rc_record_extra() fetched by the caller ahead of time */
@@ -399,18 +400,20 @@ __device__ __forceinline__ uint32_t block_off(const ReconView &v, const BandOut 
     const int plane_off = plane == 0 ? 0 : plane == 1 ? v.width * v.height : v.width * v.height + (v.width >> 1) * (v.height >> 1);
     return (uint32_t)(plane_off + (by * 4) * pw + bx * 4);
 }
+/* base = the picture (read ONCE by the caller: behind a store through a generic pointer the compiler reloads the view's
+   `present` from shared memory for every row -- 6.6 % of the kernel's instructions); unused with kTile */
 template <bool kTile>
-__device__ __forceinline__ void block_st(const ReconView &v, uint32_t off, uint32_t val)
+__device__ __forceinline__ void block_st(uint8_t *base, uint32_t off, uint32_t val)
 {
     if (kTile) *reinterpret_cast<uint32_t *>(rc_smem + off) = val;
-    else *reinterpret_cast<uint32_t *>(v.present + off) = val;
+    else *reinterpret_cast<uint32_t *>(base + off) = val;
 }
 /* the prediction the map phase left for a predicted-AOT block (another warp may have written it) */
 template <bool kTile>
-__device__ __forceinline__ uint32_t block_ld(const ReconView &v, uint32_t off)
+__device__ __forceinline__ uint32_t block_ld(const uint8_t *base, uint32_t off)
 {
     if (kTile) return *reinterpret_cast<const uint32_t *>(rc_smem + off);
-    return __ldcg(reinterpret_cast<const uint32_t *>(v.present + off));
+    return __ldcg(reinterpret_cast<const uint32_t *>(base + off));
 }
 
 /* map work of macroblock rows [row0, row1) x macroblock columns [mx0, mx1) of the CTA's picture.
@@ -426,6 +429,7 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, const BandOut 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     const bool ipic = v.is_ipic != 0;
+    uint8_t *const pic = v.present;
     uint32_t n_w = 0, n_mc = 0;
     /* classify: row tasks = 2 luma block rows per macroblock row, then the U rows, then the V rows */
     const int mrows = row1 - row0, n_tasks = mrows * 4;
@@ -475,7 +479,7 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, const BandOut 
                 const uint32_t V = dc * 0x01010101u;
                 const uint32_t dst = dst_row + bx * 4;
 #pragma unroll
-                for (int r = 0; r < 4; ++r) block_st<kTile>(v, dst + r * pw, V);
+                for (int r = 0; r < 4; ++r) block_st<kTile>(pic, dst + r * pw, V);
             }
             bx = bx_n; t = t_n; dc = dc_n;
         }
@@ -490,7 +494,7 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, const BandOut 
         rc_weighted_block(v, plane, bx, by, rows);
         const uint32_t dst = block_off<kTile>(v, o, plane, bx, by, pw);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) block_st<kTile>(v, dst + r * pw, rows[r]);
+        for (int r = 0; r < 4; ++r) block_st<kTile>(pic, dst + r * pw, rows[r]);
     }
     /* motion compensation: two entries per lane and round */
     const uint32_t *q_mc = q + cap - 1;
@@ -507,12 +511,12 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, const BandOut 
         rc_mc_packed2(v, plane0, mp0, rows0, plane1, mp1, rows1);
         const uint32_t dst0 = block_off<kTile>(v, o, plane0, bx0, by0, pw0);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) block_st<kTile>(v, dst0 + r * pw0, rows0[r]);
+        for (int r = 0; r < 4; ++r) block_st<kTile>(pic, dst0 + r * pw0, rows0[r]);
         if (two)
         {
             const uint32_t dst1 = block_off<kTile>(v, o, plane1, bx1, by1, pw1);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) block_st<kTile>(v, dst1 + r * pw1, rows1[r]);
+            for (int r = 0; r < 4; ++r) block_st<kTile>(pic, dst1 + r * pw1, rows1[r]);
         }
     }
     __syncwarp();
