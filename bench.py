@@ -279,6 +279,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams-per-gpu", type=int, default=1024, help="streams per GPU (weak scaling) or in all (strong scaling)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--gather", default="auto", choices=["auto", "on", "off"],
+                    help="end to end: bitstreams fetched by the GPU from registered host memory (auto: from 4 ranks per box on)")
     ap.add_argument("--profile", type=int, default=0, help="0 dense (headline), 1 realistic")
     ap.add_argument("--host-threads", type=int, default=0)
     ap.add_argument("--ref-seconds", type=float, default=12.0, help="CPU seconds per process for the reference sample")
@@ -340,6 +342,14 @@ def main():
     parsed = [api.parse_file(f) for f in files]
     bufs = [ctypes.create_string_buffer(f, len(f) + 8) for f in files]
     bases = [ctypes.addressof(b) for b in bufs]
+    # --gather: the bitstreams are page-locked and mapped (HVQM4HostRegister), the GPU entropy stage fetches the pictures
+    # itself instead of the host threads copying them into the pinned staging arena (include/hvqm4.h)
+    gather = args.gather == "on" or (args.gather == "auto" and world >= 4)
+    if gather:
+        for b, f in zip(bufs, files):
+            if api.lib().HVQM4HostRegister(ctypes.addressof(b), len(f)) != 0:
+                gather = False
+                break
     n_pics = len(parsed[0][1])
     threads = args.host_threads or max(1, len(mine))
     batch = api.Batch(S, W, H, 15, device=local, host_threads=threads)
@@ -604,7 +614,7 @@ def main():
             "dtype": "u8/int32", "data": "synthetic",
             "config": make_config(args, world),
             "details": {"launches_per_step": int(recon_launches // max(1, args.steps)), "inter_mcb_fraction": round(inter_frac, 4),
-                        "host_threads_per_gpu": threads, "host_cores_of_rank0": f"{mine[0]}-{mine[-1]}", "symbol_bytes_per_picture": round(sym_bytes_per_gop / frames_per_step),
+                        "bitstreams_fetched_by_gpu": gather, "host_threads_per_gpu": threads, "host_cores_of_rank0": f"{mine[0]}-{mine[-1]}", "symbol_bytes_per_picture": round(sym_bytes_per_gop / frames_per_step),
                         "l2": "inputs larger than L2: one step touches %.0f MB of symbols + %.0f MB of surfaces per GPU"
                               % (sym_bytes_per_gop / 1e6, 4 * S * frame_bytes / 1e6)},
             "parity_checked": parity,
