@@ -691,11 +691,12 @@ static void init_rec_lut(void)
 H4E_INL uint32_t rec_lut(int is_ipic, uint32_t t) { return g_rec_lut[is_ipic][t & 0xFF]; }
 #endif
 
-/* geometry checks shared by both builds; 4:2:0 landscape only: the only layout HVQM4 content uses
-   (h4m:872,896; README:23) */
+/* geometry checks shared by both builds; 4:2:0 only: the only sampling HVQM4 content uses (h4m:872,896).  Portrait
+   pictures (width < height: the nest is 38 x 70 and the axes of the basis descriptors swap, h4m:700-711, 743-754,
+   965-975, 1865-1868) are decoded like the reference does; upstream calls that orientation untested (README:23). */
 H4E_FN int seq_geometry_ok(int width, int height, int h_samp, int v_samp)
 {
-    if (width <= 0 || height <= 0 || (width & 7) || (height & 7) || h_samp != 2 || v_samp != 2 || width < height) return 0;
+    if (width <= 0 || height <= 0 || (width & 7) || (height & 7) || h_samp != 2 || v_samp != 2) return 0;
     return width <= 8192 && height <= 8192;
 }
 
@@ -1236,6 +1237,7 @@ H4E_FN void plan_blob(H4Seq *s)
     h->dc_shift = (uint8_t)s->dc_shift;
     h->unk_shift = (uint8_t)s->unk_shift;
     h->has_nest = (uint8_t)s->need_nest;
+    h->portrait = (uint8_t)(s->width < s->height);
     h->mcb_w = (uint16_t)s->mbw;
     h->mcb_h = (uint16_t)s->mbh;
     h->nseg = (uint16_t)s->nseg;
@@ -1359,14 +1361,16 @@ H4E_FN void ipic_dcs(H4Seq *s)
     }
 }
 
-/* MakeNest, h4m:1166-1239 (including the mirror / zero-fill path), packed to nibbles */
+/* MakeNest, h4m:1166-1239 (including the mirror / zero-fill path), packed to nibbles.  The nest is 70 x 38 in landscape
+   and 38 x 70 in portrait pictures (h4m:965-975); packed rows are NW / 2 bytes either way (35 or 19), 1 330 bytes in all */
 H4E_FN void make_nest(H4Seq *s, int nx, int ny)
 {
-    uint8_t full[SYM_NEST_H][SYM_NEST_W];
+    uint8_t full[SYM_NEST_H * SYM_NEST_W];
+    const int NW = s->width < s->height ? SYM_NEST_H : SYM_NEST_W, NH = s->width < s->height ? SYM_NEST_W : SYM_NEST_H;
     int bw = s->bw[0], bh = s->bh[0];
-    int cols = bw < SYM_NEST_W ? bw : SYM_NEST_W, rows = bh < SYM_NEST_H ? bh : SYM_NEST_H;
-    int mcols = bw < SYM_NEST_W ? (SYM_NEST_W - bw < bw ? SYM_NEST_W - bw : bw) : 0;
-    int mrows = bh < SYM_NEST_H ? (SYM_NEST_H - bh < bh ? SYM_NEST_H - bh : bh) : 0;
+    int cols = bw < NW ? bw : NW, rows = bh < NH ? bh : NH;
+    int mcols = bw < NW ? (NW - bw < bw ? NW - bw : bw) : 0;
+    int mrows = bh < NH ? (NH - bh < bh ? NH - bh : bh) : 0;
     /* keep the window inside the map even for a hostile header */
     if (nx < 0 || nx + cols > bw) { nx = 0; s->err |= SYM_ERR_MV_RANGE; }
     if (ny < 0 || ny + rows > bh) { ny = 0; s->err |= SYM_ERR_MV_RANGE; }
@@ -1374,13 +1378,13 @@ H4E_FN void make_nest(H4Seq *s, int nx, int ny)
     for (int i = 0; i < rows; ++i)
     {
         const uint8_t *src = s->dc[0] + cell_at(s, 0, nx, ny + i);
-        for (int j = 0; j < cols; ++j) full[i][j] = (src[j] >> 4) & 0xF;
-        for (int j = 0; j < mcols; ++j) full[i][cols + j] = (src[cols - 1 - j] >> 4) & 0xF;
+        for (int j = 0; j < cols; ++j) full[i * NW + j] = (src[j] >> 4) & 0xF;
+        for (int j = 0; j < mcols; ++j) full[i * NW + cols + j] = (src[cols - 1 - j] >> 4) & 0xF;
     }
-    for (int i = 0; i < mrows; ++i) memcpy(full[rows + i], full[rows - 1 - i], SYM_NEST_W);
-    for (int i = 0; i < SYM_NEST_H; ++i)
-        for (int j = 0; j < SYM_NEST_ROW_BYTES; ++j)
-            s->nest[i * SYM_NEST_ROW_BYTES + j] = (uint8_t)(full[i][2 * j] | full[i][2 * j + 1] << 4);
+    for (int i = 0; i < mrows; ++i) memcpy(full + (rows + i) * NW, full + (rows - 1 - i) * NW, (size_t)NW);
+    for (int i = 0; i < NH; ++i)
+        for (int j = 0; j < NW / 2; ++j)
+            s->nest[i * (NW / 2) + j] = (uint8_t)(full[i * NW + 2 * j] | full[i * NW + 2 * j + 1] << 4);
 }
 
 /* ------------------------------------------------------------------ P/B picture, pass 1 */
@@ -1998,8 +2002,11 @@ H4E_FN int mcb_refs_in_surface(const H4Seq *s, int32_t rx, int32_t ry, int needs
     }
     if (needs_window)
     {
-        int64_t org = (int64_t)(rx / 2) + (int64_t)(ry / 2 - 16) * s->width - 32;
-        if (org < 0 || org + (int64_t)(SYM_NEST_H - 1) * s->width + SYM_NEST_W - 1 >= total) return 0;
+        /* window origin and size, h4m:1864-1868: 70 x 38 at (-32, -16) in landscape, 38 x 70 at (-16, -32) in portrait */
+        const int portrait = s->width < s->height;
+        const int NW = portrait ? SYM_NEST_H : SYM_NEST_W, NH = portrait ? SYM_NEST_W : SYM_NEST_H;
+        int64_t org = (int64_t)(rx / 2) + (int64_t)(ry / 2 - (portrait ? 32 : 16)) * s->width - (portrait ? 16 : 32);
+        if (org < 0 || org + (int64_t)(NH - 1) * s->width + NW - 1 >= total) return 0;
     }
     return 1;
 }

@@ -324,7 +324,7 @@ recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs, uint32_t cta_
     {
         nest_stage_wait();
         __syncthreads();
-        nest_spread<kRecWarps * 32>(rc_smem + RC_SMEM_TABLE_BYTES);
+        nest_spread<kRecWarps * 32>(rc_smem + RC_SMEM_TABLE_BYTES, v.portrait != 0);
         __syncthreads();
     }
     pdl_wait();                                           /* the map kernel's predictions, and the surfaces at all */
@@ -553,7 +553,7 @@ __device__ __forceinline__ void band_item(const ReconJob *__restrict__ jobs, int
     if (intra1 > intra0)
     {
         __syncthreads();
-        nest_spread<kBandWarps * 32>(rc_smem + RC_SMEM_TABLE_BYTES);
+        nest_spread<kBandWarps * 32>(rc_smem + RC_SMEM_TABLE_BYTES, v.portrait != 0);
     }
     __syncthreads();     /* map stores of the band visible to the whole CTA; nest table complete */
 #pragma unroll 1

@@ -77,6 +77,7 @@ static inline uint32_t rc_dp4a_host(uint32_t a, uint32_t b, uint32_t c)
 #endif
 
 #define RC_NEST_PITCH 68                              /* entries per nest row: start columns 0..67 */
+#define RC_NEST_PITCH_PORTRAIT 36                     /* portrait nest (38 wide, 70 rows): start columns 0..35; 70 * 36 <= 38 * 68 words */
 #define RC_NEST_TABLE_WORDS (SYM_NEST_H * RC_NEST_PITCH)
 
 /* The three lookup tables live at fixed offsets at the start of dynamic shared memory on the
@@ -116,6 +117,7 @@ struct ReconView
     uint8_t *present;
     const uint32_t *rec, *chunks, *bands;
     int nseg, mcb_h, has_nest;
+    int portrait;              /* width < height: nest 38 x 70, basis descriptor axes swapped (h4m:700-711, 743-754) */
     uint32_t off_nest, n_chunks, n_chunks_nest, n_bands;
 };
 
@@ -136,6 +138,7 @@ RC_HD void rc_make_view(ReconView &v, const uint8_t *blob, const SymHeader &h, c
     v.bands = reinterpret_cast<const uint32_t *>(blob + h.off_bands);
     v.n_bands = h.n_bands;
     v.nseg = h.nseg; v.mcb_h = h.mcb_h; v.has_nest = h.has_nest;
+    v.portrait = h.portrait;
     v.off_nest = h.off_nest; v.n_chunks = h.n_chunks; v.n_chunks_nest = h.n_chunks_nest;
 }
 
@@ -154,14 +157,14 @@ RC_HD uint32_t rc_nest_spread_step1(uint32_t nibbles8)
     return ((x | x << 4) & 0x0F0F0F0Fu) << 4;
 }
 
-RC_HD uint32_t rc_nest_table_entry(const uint8_t *packed, int y, int x)
+RC_HD uint32_t rc_nest_table_entry(const uint8_t *packed, int y, int x, int row_bytes = SYM_NEST_ROW_BYTES)
 {
-    const uint8_t *row = packed + y * SYM_NEST_ROW_BYTES;
+    const uint8_t *row = packed + y * row_bytes;
     uint64_t bits = 0;
     const int b0 = x >> 1;
 #pragma unroll
     for (int i = 0; i < 5; ++i)
-        if (b0 + i < SYM_NEST_ROW_BYTES) bits |= (uint64_t)row[b0 + i] << (8 * i);
+        if (b0 + i < row_bytes) bits |= (uint64_t)row[b0 + i] << (8 * i);
     return (uint32_t)(bits >> ((x & 1) * 4));
 }
 
@@ -283,9 +286,14 @@ struct RcNoWindow { };
 template <bool kInter, class Win>
 RC_HD void rc_add_basis(const ReconView &v, uint32_t word, const Win window, int32_t &scale_sum, int32_t acc[16])
 {
-    const int ox = word & 0x3F, oy = (word >> 6) & 0x1F;
-    const uint32_t xs2 = (word >> 11) & 1;
-    const int ys = 1 + ((word >> 12) & 1);
+    /* landscape: [5:0] column, [10:6] row, [11] column step 2, [12] row step 2; portrait: the other way round
+       (h4m:700-711, 743-754) */
+    const int f6 = word & 0x3F, f5 = (word >> 6) & 0x1F;
+    const uint32_t s11 = (word >> 11) & 1, s12 = (word >> 12) & 1;
+    const bool portrait = v.portrait != 0;
+    const int ox = portrait ? f5 : f6, oy = portrait ? f6 : f5;
+    const uint32_t xs2 = portrait ? s12 : s11;
+    const int ys = 1 + (int)(portrait ? s11 : s12);
     uint32_t R[4];
     if constexpr (kInter)
     {
@@ -305,12 +313,13 @@ RC_HD void rc_add_basis(const ReconView &v, uint32_t word, const Win window, int
     }
     else
     {
-        const uint32_t *tab = RC_NEST_TAB(v) + oy * RC_NEST_PITCH + ox;
+        const int pitch = portrait ? RC_NEST_PITCH_PORTRAIT : RC_NEST_PITCH;
+        const uint32_t *tab = RC_NEST_TAB(v) + oy * pitch + ox;
 #pragma unroll
         for (int y = 0; y < 4; ++y)
         {
-            const uint32_t e0 = tab[y * ys * RC_NEST_PITCH];
-            R[y] = xs2 ? RC_PRMT(e0, tab[y * ys * RC_NEST_PITCH + 4], 0x6420) : e0;
+            const uint32_t e0 = tab[y * ys * pitch];
+            R[y] = xs2 ? RC_PRMT(e0, tab[y * ys * pitch + 4], 0x6420) : e0;
         }
         rc_accumulate<2>(v, word, R, scale_sum, acc);
     }
@@ -552,7 +561,8 @@ RC_HD const uint8_t *rc_motion_window(const ReconView &v, uint32_t t, uint32_t m
     const int rx = (int16_t)(mvw & 0xFFFF), ry = (int16_t)(mvw >> 16);
     if (rx == -32768) return nullptr;
     const uint8_t *ref = ((t >> 5) & 3) == 2 ? v.ref[1] : v.ref[0];
-    return ref + rx / 2 + (ry / 2 - 16) * v.width - 32;
+    /* 70 x 38 at (-32, -16) in landscape, 38 x 70 at (-16, -32) in portrait pictures */
+    return v.portrait ? ref + rx / 2 + (ry / 2 - 32) * v.width - 16 : ref + rx / 2 + (ry / 2 - 16) * v.width - 32;
 }
 
 RC_HD void rc_mc_packed(const ReconView &v, int plane, uint32_t mp, uint32_t rows[4])

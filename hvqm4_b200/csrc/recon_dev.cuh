@@ -59,23 +59,26 @@ __device__ __forceinline__ void nest_stage_begin(const ReconView &v, uint8_t *pa
 __device__ __forceinline__ void nest_stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int kThreads>
-__device__ __forceinline__ void nest_spread(uint8_t *packed)
+__device__ __forceinline__ void nest_spread(uint8_t *packed, bool portrait = false)
 {
+    /* landscape: 38 rows of 35 packed bytes -> 68 entries per row; portrait: 70 rows of 19 bytes -> 36 entries per row */
+    const int rows = portrait ? SYM_NEST_W : SYM_NEST_H, row_bytes = portrait ? SYM_NEST_H / 2 : SYM_NEST_ROW_BYTES;
+    const int half = portrait ? RC_NEST_PITCH_PORTRAIT / 2 : RC_NEST_PITCH / 2, pitch = 2 * half;
     uint32_t *s_nest_tab = reinterpret_cast<uint32_t *>(rc_smem + RC_SMEM_NEST_OFF);
     uint32_t *stage = reinterpret_cast<uint32_t *>(packed);
     /* nibbles x..x+7 of row y, spread into table entries x = 2j and 2j+1 (samples x..x+3, one per byte, times 16);
        both share bytes j..j+4 of the row.  Entries near the end of a row run into the next row: those nibbles lie
        beyond column 69, which no descriptor reaches (offset <= 63, largest pattern + 6). */
     const uint32_t *pw = stage;
-    for (int i = threadIdx.x; i < SYM_NEST_H * (RC_NEST_PITCH / 2); i += kThreads)
+    for (int i = threadIdx.x; i < rows * half; i += kThreads)
     {
-        const int y = i / (RC_NEST_PITCH / 2), j = i - y * (RC_NEST_PITCH / 2);
-        const int b = y * SYM_NEST_ROW_BYTES + j, w = b >> 2, sh = (b & 3) * 8;
+        const int y = i / half, j = i - y * half;
+        const int b = y * row_bytes + j, w = b >> 2, sh = (b & 3) * 8;
         const uint32_t w0 = pw[w], w1 = pw[w + 1], w2 = sh ? pw[w + 2] : 0u;
         const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
         const uint32_t odd = (lo >> 4) | (hi << 28);
-        s_nest_tab[y * RC_NEST_PITCH + 2 * j] = rc_nest_spread_step1(lo);
-        s_nest_tab[y * RC_NEST_PITCH + 2 * j + 1] = rc_nest_spread_step1(odd);
+        s_nest_tab[y * pitch + 2 * j] = rc_nest_spread_step1(lo);
+        s_nest_tab[y * pitch + 2 * j + 1] = rc_nest_spread_step1(odd);
     }
 }
 

@@ -103,6 +103,7 @@ struct RowSlotMeta
 RC_HD int rw_make_geom(RowGeom &g, int width, int height, uint32_t smem_limit)
 {
     if (width <= 0 || height <= 0 || (width & 31) || (height & 7) || width > 2048) return 0;
+    if (width < height) return 0;      /* portrait pictures (38 x 70 nest, swapped window origin): the other kernels */
     g.width = width; g.height = height; g.mcb_w = width / 8; g.mcb_h = height / 8;
     g.n_groups = (g.mcb_w + 15) / 16;
     if (g.mcb_h > RW_MAX_ROWS) return 0;

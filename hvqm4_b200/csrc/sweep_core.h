@@ -118,6 +118,7 @@ RC_HD int sw_band_rows(const SweepGeom &g, int band)
 RC_HD int sw_make_geom(SweepGeom &g, int width, int height, int h, uint32_t smem_limit)
 {
     if (width <= 0 || height <= 0 || (width & 31) || (height & 7) || width > 2048 || h < 1 || h > 4) return 0;
+    if (width < height) return 0;      /* portrait pictures (38 x 70 nest, swapped window origin): the other kernels */
     g.width = width; g.height = height; g.mcb_w = width / 8; g.mcb_h = height / 8;
     g.h = h;
     g.n_bands = (g.mcb_h + h - 1) / h;

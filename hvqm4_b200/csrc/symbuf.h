@@ -19,8 +19,8 @@
  *                  (ref_x, ref_y of h4m:1954-1955) as int16 x 2; predictor chain,
  *                  wrap-around and reference switches (h4m:1846-1860,1943-1949) are
  *                  already resolved by the host.
- *   nest           the 70x38 4-bit nest of the last I picture (h4m:1166-1239), packed two
- *                  samples per byte (even x in the low nibble); present in every I picture
+ *   nest           the 70x38 (portrait pictures: 38x70) 4-bit nest of the last I picture (h4m:1166-1239),
+ *                  packed two samples per byte (even x in the low nibble); present in every I picture
  *                  and in P/B pictures that contain intra AOT blocks.
  *   records        one variable-length record per block that carries side data, i.e. raw
  *                  blocks (h4m:543-549) and blocks with an AOT basis loop (h4m:1358-1420):
@@ -87,7 +87,9 @@ typedef struct SymHeader
     uint8_t  dc_shift;         /* P/B only (h4m:2021) */
     uint8_t  unk_shift;        /* h4m:1974, 2022 */
     uint8_t  has_nest;
-    uint8_t  pad0[3];
+    uint8_t  portrait;         /* width < height: the nest is 38 x 70 (19 packed bytes per row) and the axes of the basis
+                                  descriptors swap (h4m:700-711, 743-754, 965-975) */
+    uint8_t  pad0[2];
     uint32_t errors;           /* SYM_ERR_* */
     uint16_t mcb_w, mcb_h;     /* macroblocks */
     uint16_t nseg;             /* segments per macroblock row = ceil(mcb_w / 16) */

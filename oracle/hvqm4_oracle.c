@@ -19,7 +19,8 @@
  * Every function cites the reference lines it restates ("h4m:N" =
  * /root/reference/h4m_audio_decode.c line N).
  *
- * Scope: landscape 4:2:0 (h_samp = v_samp = 2) like every known stream; other
+ * Scope: 4:2:0 (h_samp = v_samp = 2) like every known stream, landscape and portrait (h4m:700-711, 743-754, 965-975,
+ * 1865-1868; upstream calls portrait untested, README:23: pinned here against the reference build like everything else); other
  * sampling factors are rejected at open().
  */
 #define _GNU_SOURCE
@@ -245,9 +246,12 @@ static void aot_add_basis(Dec *d, int plane, const uint8_t *src, int src_stride,
     Section *fx = &d->fix[plane];
     uint32_t desc = be16(fx->base + fx->byte);
     fx->byte += 2;
-    const uint8_t *org = src + src_stride * ((desc >> 6) & 0x1F) + (desc & 0x3F);
-    int xs = 1 << ((desc >> 11) & 1);
-    int ys = src_stride << ((desc >> 12) & 1);
+    /* portrait pictures swap the axes: the 6-bit field is the row, the 5-bit field the column (h4m:700-711, 743-754) */
+    const int portrait = d->width < d->height;
+    const uint32_t f6 = desc & 0x3F, f5 = (desc >> 6) & 0x1F, s11 = (desc >> 11) & 1, s12 = (desc >> 12) & 1;
+    const uint8_t *org = portrait ? src + src_stride * f6 + f5 : src + src_stride * f5 + f6;
+    int xs = 1 << (portrait ? s12 : s11);
+    int ys = src_stride << (portrait ? s11 : s12);
     uint8_t b[16];
     int lo = 255, hi = 0;
     for (int y = 0; y < 4; ++y)
@@ -282,7 +286,7 @@ static void fill_intra_aot(Dec *d, int plane, uint8_t *dst, int stride, int dc, 
 {
     if (type == 6) { fill_raw(d, plane, dst, stride); return; }
     int32_t acc[16];
-    int32_t mean = aot_sum(d, plane, type, d->nest, NEST_W, 0, acc);
+    int32_t mean = aot_sum(d, plane, type, d->nest, d->width < d->height ? NEST_H : NEST_W, 0, acc);   /* nest 38 wide in portrait, h4m:965-975 */
     int32_t delta = (int32_t)((uint32_t)dc << d->unk_shift) - mean;
     for (int i = 0; i < 16; ++i)
         dst[(i >> 2) * stride + (i & 3)] = clamp255((acc[i] + delta) >> d->unk_shift);
@@ -399,18 +403,20 @@ static void ipic_dcs(Dec *d)
 static void make_nest(Dec *d, int nx, int ny)
 {
     Plane *y = &d->pl[0];
-    int cols = y->bw < NEST_W ? y->bw : NEST_W, rows = y->bh < NEST_H ? y->bh : NEST_H;
-    int mcols = y->bw < NEST_W ? (NEST_W - y->bw < y->bw ? NEST_W - y->bw : y->bw) : 0;
-    int mrows = y->bh < NEST_H ? (NEST_H - y->bh < y->bh ? NEST_H - y->bh : y->bh) : 0;
+    /* 70 x 38 in landscape, 38 x 70 in portrait pictures (h4m:965-975) */
+    const int NW = d->width < d->height ? NEST_H : NEST_W, NH = d->width < d->height ? NEST_W : NEST_H;
+    int cols = y->bw < NW ? y->bw : NW, rows = y->bh < NH ? y->bh : NH;
+    int mcols = y->bw < NW ? (NW - y->bw < y->bw ? NW - y->bw : y->bw) : 0;
+    int mrows = y->bh < NH ? (NH - y->bh < y->bh ? NH - y->bh : y->bh) : 0;
     memset(d->nest, 0, sizeof d->nest);
     for (int i = 0; i < rows; ++i)
     {
-        uint8_t *row = d->nest + i * NEST_W;
+        uint8_t *row = d->nest + i * NW;
         for (int j = 0; j < cols; ++j) row[j] = (cell(y, nx + j, ny + i)->dc >> 4) & 0xF;
         for (int j = 0; j < mcols; ++j) row[cols + j] = (cell(y, nx + cols - 1 - j, ny + i)->dc >> 4) & 0xF;
     }
     for (int i = 0; i < mrows; ++i)
-        memcpy(d->nest + (rows + i) * NEST_W, d->nest + (rows - 1 - i) * NEST_W, NEST_W);
+        memcpy(d->nest + (rows + i) * NW, d->nest + (rows - 1 - i) * NW, (size_t)NW);
 }
 
 /* h4m:1433-1518.  Top/bottom/right follow the 0x77 rule (the first/last line and the
@@ -622,7 +628,8 @@ static void pb_pass2(Dec *d, uint8_t *present, const uint8_t *past, const uint8_
             int32_t rx = mx * 16 + mvx, ry = my * 16 + mvy;      /* half-sample luma coordinates */
             int whole = (tag >> 4) & 1;
             /* 70x38 luma window of the reference frame used as the nest of this MCB (h4m:1864-1868) */
-            const uint8_t *window = refs[ref][0] + rx / 2 + (ry / 2 - 16) * d->pl[0].w - 32;
+            const uint8_t *window = d->width < d->height ? refs[ref][0] + rx / 2 + (ry / 2 - 32) * d->pl[0].w - 16
+                                                         : refs[ref][0] + rx / 2 + (ry / 2 - 16) * d->pl[0].w - 32;
             int hx = rx & 1, hy = ry & 1;                            /* 1.3: luma phase for every plane */
             for (int p = 0; p < 3; ++p)
             {
@@ -710,7 +717,6 @@ static int parse_header(const uint8_t *h, size_t len, int out[7])
     out[0] = (int)be16(h + 0x34);
     out[1] = (int)be16(h + 0x36);
     if (h[0x38] != 2 || h[0x39] != 2) return -2;
-    if (out[0] < out[1]) return -3;   /* portrait: untested upstream (README:23), not restated */
     return 0;
 }
 

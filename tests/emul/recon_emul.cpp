@@ -31,9 +31,13 @@ int emul_recon_picture(const uint8_t *blob, uint8_t *present, const uint8_t *pas
     if (h.magic != SYM_MAGIC) return -1;
     static uint32_t nest_tab[RC_NEST_TABLE_WORDS];
     if (h.has_nest)
-        for (int y = 0; y < SYM_NEST_H; ++y)
-            for (int x = 0; x < RC_NEST_PITCH; ++x)
-                nest_tab[y * RC_NEST_PITCH + x] = rc_nest_spread_step1(rc_nest_table_entry(blob + h.off_nest, y, x));
+    {   /* landscape: 38 rows of 35 packed bytes, 68 entries per row; portrait: 70 rows of 19 bytes, 36 entries per row */
+        const int rows = h.portrait ? SYM_NEST_W : SYM_NEST_H, row_bytes = h.portrait ? SYM_NEST_H / 2 : SYM_NEST_ROW_BYTES;
+        const int pitch = h.portrait ? RC_NEST_PITCH_PORTRAIT : RC_NEST_PITCH;
+        for (int y = 0; y < rows; ++y)
+            for (int x = 0; x < pitch; ++x)
+                nest_tab[y * pitch + x] = rc_nest_spread_step1(rc_nest_table_entry(blob + h.off_nest, y, x, row_bytes));
+    }
     ReconView v;
     rc_make_view(v, blob, h, nest_tab, g_div, g_mcdiv, past, future);
     uint8_t *planes[3] = {present, present + h.width * h.height, present + h.width * h.height * 5 / 4};

@@ -55,6 +55,13 @@ CASES = {
     # every luma block of the I pictures carries 16 / 17 bases: at / beyond the symbol capacity of the GPU entropy stage
     "cap16_320x240_v15_I": dict(width=320, height=240, version=15, gop="II", n_gops=1, seed=305, profile=3),
     "cap17_320x240_v15_I": dict(width=320, height=240, version=15, gop="II", n_gops=1, seed=306, profile=4),
+    # portrait pictures: the nest is 38 x 70, the axes of the basis descriptors swap and the window of predicted-AOT
+    # macroblocks sits at (-16, -32) (h4m:700-711, 743-754, 965-975, 1865-1868); upstream calls the orientation untested
+    # (README:23): what counts here is what the reference build does
+    "portrait_240x320_v15_IPB": dict(width=240, height=320, version=15, gop="I" + "PBB" * 3, n_gops=2, seed=401, profile=0),
+    "portrait_480x640_v13_IPB": dict(width=480, height=640, version=13, gop="IPBBPBB", n_gops=1, seed=402, profile=0),
+    "portrait_stress_240x320_v15_IPB": dict(width=240, height=320, version=15, gop="IPBBPB", n_gops=2, seed=403, profile=2),
+    "portrait_small_64x96_v15_IPB": dict(width=64, height=96, version=15, gop="IPBBPB", n_gops=2, seed=404, profile=0),
 }
 
 

@@ -25,7 +25,8 @@ SDK_CASES = ["cfg1_320x240_v15_I30", "cfg2_640x480_v15_IP15", "cfg3_640x480_v15_
              "tiny_16x16_v15_IPB", "small_64x48_v13_IPB", "mirror_h_200x152_v15_IPB", "mirror_v_320x104_v15_IPB",
              "uhd_4096x2160_v15_IPB",
              "stress_640x480_v15_IPB", "stress_320x240_v13_IPB", "stress_328x248_v15_IPB", "stress_64x48_v15_IPB",
-             "cap16_320x240_v15_I", "cap17_320x240_v15_I"]
+             "cap16_320x240_v15_I", "cap17_320x240_v15_I",
+             "portrait_240x320_v15_IPB", "portrait_480x640_v13_IPB", "portrait_stress_240x320_v15_IPB", "portrait_small_64x96_v15_IPB"]
 
 
 @pytest.mark.parametrize("name", SDK_CASES)
@@ -262,7 +263,8 @@ def test_gpu_entropy_stage_matches_golden(native_lib, golden):
 @pytest.mark.parametrize("name", ["cfg4_320x240_v13_IPB", "realistic_640x480_v15_IPB", "ragged_328x248_v15_IPB", "wide_1024x576_v13_IPB",
                                   "hd_1280x720_v15_IPB", "tiny_16x16_v15_IPB", "small_64x48_v13_IPB", "mirror_h_200x152_v15_IPB",
                                   "uhd_4096x2160_v15_IPB", "stress_640x480_v15_IPB", "stress_320x240_v13_IPB", "stress_328x248_v15_IPB",
-                                  "stress_64x48_v15_IPB"])
+                                  "stress_64x48_v15_IPB", "portrait_240x320_v15_IPB", "portrait_480x640_v13_IPB",
+                                  "portrait_stress_240x320_v15_IPB", "portrait_small_64x96_v15_IPB"])
 def test_gpu_entropy_stage_other_geometries(native_lib, golden, name):
     case = golden[name]
     data = synth.generate(**case["args"])
@@ -276,7 +278,7 @@ def test_batch_runtime_matches_golden_stress(native_lib, golden, mode):
     under every reconstruction schedule that serves batches."""
     native_lib.set_recon_mode(mode)
     try:
-        for name in ("stress_640x480_v15_IPB", "stress_320x240_v13_IPB"):
+        for name in ("stress_640x480_v15_IPB", "stress_320x240_v13_IPB", "portrait_240x320_v15_IPB"):
             case = golden[name]
             data = synth.generate(**case["args"])
             got = [[md5(f[2]) for f in frames] for frames in native_lib.decode_streams([data] * 5)]

@@ -14,7 +14,8 @@ from tests.h4m_util import demux, emul_decode, md5
     "realistic_640x480_v15_IPB", "min_280x152_v15_IPB", "ragged_328x248_v15_IPB", "wide_1024x576_v13_IPB",
     "hd_1280x720_v15_IPB", "tiny_16x16_v15_IPB", "small_64x48_v13_IPB", "mirror_h_200x152_v15_IPB", "mirror_v_320x104_v15_IPB",
     "stress_640x480_v15_IPB", "stress_320x240_v13_IPB", "stress_328x248_v15_IPB", "stress_64x48_v15_IPB", "cap16_320x240_v15_I",
-    "cap17_320x240_v15_I"])
+    "cap17_320x240_v15_I", "portrait_240x320_v15_IPB", "portrait_480x640_v13_IPB", "portrait_stress_240x320_v15_IPB",
+    "portrait_small_64x96_v15_IPB"])
 def test_emulated_pipeline_matches_golden(emul_lib, golden, name):
     case = golden[name]
     got = list(emul_decode(emul_lib, synth.generate(**case["args"])))
@@ -135,7 +136,9 @@ def test_truncated_and_corrupt_pictures_raise_error_bits_not_crashes(emul_lib):
 def test_unsupported_geometry_is_rejected(emul_lib):
     assert not emul_lib.h4e_seq_create(322, 240, 2, 2, 1)     # not a multiple of 8
     assert not emul_lib.h4e_seq_create(320, 240, 1, 1, 1)     # 4:4:4
-    assert not emul_lib.h4e_seq_create(240, 320, 2, 2, 1)     # portrait (untested upstream, README:23)
+    seq = emul_lib.h4e_seq_create(240, 320, 2, 2, 1)          # portrait: decoded like the reference does (38 x 70 nest)
+    assert seq
+    emul_lib.h4e_seq_destroy(seq)
 
 
 def test_kernel_leaf_arithmetic_equals_reference_leaves(emul_lib, oracle):

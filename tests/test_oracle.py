@@ -41,7 +41,8 @@ def test_port_matches_reference_maps_and_sections(oracle):
     if not oracle.have_ref():
         pytest.skip("oracle/_ref not built")
     for seed, (w, h, v, gop, prof) in enumerate([(320, 240, 15, "IPBBPBB", 0), (640, 480, 13, "IPBB", 0), (328, 248, 15, "IPB", 1),
-                                                 (320, 240, 15, "IPBBPBB", 2), (640, 480, 13, "IPBB", 2), (320, 240, 15, "I", 4)]):
+                                                 (320, 240, 15, "IPBBPBB", 2), (640, 480, 13, "IPBB", 2), (320, 240, 15, "I", 4),
+                                                 (240, 320, 15, "IPBBPBB", 0), (96, 160, 13, "IPB", 2)]):
         data = synth.generate(w, h, v, gop, 2, seed=900 + seed, profile=prof)
         a, b = oracle.RefDecoder(data), oracle.PortDecoder(data)
         for fa, fb in zip(a.frames(), b.frames()):

@@ -344,7 +344,9 @@ static void gen_ipic(Gen *g, Pic *p, uint8_t hdr[8])
     int dc_shift = prof_stress(g) ? (int)rnd(r, 4) : (int)rnd(r, 2);
     int unk_shift = prof_stress(g) ? rnd_range(r, 6, 12) : prof_dense(g) ? rnd_range(r, 8, 10) : 10;
     /* pictures narrower / lower than the nest take MakeNest's mirror + zero-fill path (h4m:1173-1203): origin 0 */
-    int nest_x = g->bw[0] >= 70 ? (int)rnd(r, g->bw[0] - 70 + 1) : 0, nest_y = g->bh[0] >= 38 ? (int)rnd(r, g->bh[0] - 38 + 1) : 0;
+    /* the nest is 70 x 38 blocks, 38 x 70 in portrait pictures (h4m:965-975) */
+    const int nw = g->w < g->h ? 38 : 70, nh = g->w < g->h ? 70 : 38;
+    int nest_x = g->bw[0] >= nw ? (int)rnd(r, g->bw[0] - nw + 1) : 0, nest_y = g->bh[0] >= nh ? (int)rnd(r, g->bh[0] - nh + 1) : 0;
     hdr[0] = dc_shift; hdr[1] = unk_shift; hdr[2] = 0; hdr[3] = 0;
     hdr[4] = nest_x >> 8; hdr[5] = nest_x; hdr[6] = nest_y >> 8; hdr[7] = nest_y;
 
@@ -489,7 +491,10 @@ static void gen_pbpic(Gen *g, Pic *p, uint8_t hdr[8], int is_b)
                 int f = mtype[i] - 1;
                 int Mh = 1 << (rb[f][0] + 5), Mv = 1 << (rb[f][1] + 5);
                 Span sh = mv_span(mx * 8, g->w, Mh, 0, 0), sv = mv_span(my * 8, g->h, Mv, 0, 0);
-                Span wh = mv_span(mx * 8, g->w, Mh, 32, 38), wv = mv_span(my * 8, g->h, Mv, 16, 22);
+                /* window of predicted-AOT macroblocks: 70 x 38 at (-32, -16), in portrait 38 x 70 at (-16, -32), h4m:1864-1868 */
+                const int portrait = g->w < g->h;
+                Span wh = portrait ? mv_span(mx * 8, g->w, Mh, 16, 22) : mv_span(mx * 8, g->w, Mh, 32, 38);
+                Span wv = portrait ? mv_span(my * 8, g->h, Mv, 32, 38) : mv_span(my * 8, g->h, Mv, 16, 22);
                 int can_win = wh.lo <= wh.hi && wv.lo <= wv.hi;
                 int want_win = mproc[i] == 0 && can_win && chance(r, dense ? 60 : 90);
                 Span uh = want_win ? wh : sh, uv = want_win ? wv : sv;
@@ -507,7 +512,8 @@ static void gen_pbpic(Gen *g, Pic *p, uint8_t hdr[8], int is_b)
                 }
                 mv[i][0] = th; mv[i][1] = tv;
                 int rx = (2 * mx * 8 + th) >> 1, ry = (2 * my * 8 + tv) >> 1;
-                winok[i] = rx >= 32 && rx + 38 <= g->w && ry >= 16 && ry + 22 <= g->h;
+                winok[i] = portrait ? rx >= 16 && rx + 22 <= g->w && ry >= 32 && ry + 38 <= g->h
+                                    : rx >= 32 && rx + 38 <= g->w && ry >= 16 && ry + 22 <= g->h;
             }
     }
 
@@ -692,7 +698,6 @@ GEN_API int h4mgen_generate(const H4MGenParams *prm, uint8_t **out_data, uint64_
 {
     if (!prm || !prm->gop || prm->gop[0] != 'I') return -1;
     if (prm->width % 8 || prm->height % 8 || prm->width < 16 || prm->height < 16) return -2;
-    if (prm->width < prm->height) return -3;   /* portrait is untested upstream (README:23) */
     if (prm->version != 13 && prm->version != 15) return -4;
     Gen g;
     memset(&g, 0, sizeof g);
