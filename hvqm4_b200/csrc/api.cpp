@@ -1059,7 +1059,27 @@ struct Twin
     const void *host = nullptr;
     uint8_t *dev = nullptr;
     uint64_t stamp = 0;
+    uint64_t print = 0;       /* fingerprint of the host frame when the twin last equalled it (twin_print) */
+    bool printed = false;
 };
+
+/* 64 words spread over a host frame, folded: cheap enough for every decode call, and an application that writes into
+   a frame buffer behind the library's back (clears it on a seek, draws into it) changes it with near certainty, so
+   the stale device twin is uploaded again instead of being used as a reference.  HVQM4InvalidateFrame stays for the
+   writes this cannot see. */
+static uint64_t twin_print(const void *host, size_t bytes)
+{
+    const uint8_t *p = static_cast<const uint8_t *>(host);
+    const size_t words = bytes / 8, step = words / 64 ? words / 64 : 1;
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (size_t i = 0; i < words; i += step)
+    {
+        uint64_t w;
+        memcpy(&w, p + 8 * i, 8);
+        h = (h ^ w) * 0x100000001B3ull + (h >> 29);
+    }
+    return h;
+}
 
 struct Compat
 {
@@ -1127,9 +1147,18 @@ uint8_t *resolve(Compat *c, void *p, bool is_reference)
         fresh = true;
     }
     slot->stamp = ++c->clock;
-    if (fresh && is_reference &&
-        !cuda_ok(cudaMemcpyAsync(slot->dev, p, c->frame_bytes, cudaMemcpyHostToDevice, c->stream), "upload reference frame"))
-        return nullptr;
+    if (is_reference)
+    {
+        const uint64_t print = twin_print(p, c->frame_bytes);
+        if (fresh || !slot->printed || slot->print != print)
+        {   /* unknown, or the application has written into the frame since the library last saw it */
+            if (!cuda_ok(cudaMemcpyAsync(slot->dev, p, c->frame_bytes, cudaMemcpyHostToDevice, c->stream), "upload reference frame")) return nullptr;
+            slot->print = print;
+            slot->printed = true;
+        }
+    }
+    else
+        slot->printed = false;      /* about to be overwritten by this picture: fingerprinted after the read-back */
     return slot->dev;
 }
 
@@ -1146,7 +1175,11 @@ void compat_decode(SeqObj *so, int type, const uint8_t *frame, void *present, vo
         c->errors |= HVQM4_ERR_NO_DEVICE;
         return;
     }
-    const size_t len = c->next_frame_bytes ? c->next_frame_bytes : (size_t)1 << 30;
+    /* The SDK protocol has no picture length (the reference trusts the record, h4m:1061-1071).  Without
+       HVQM4SetFrameBytes the readable length is bounded by what a picture of this geometry can possibly need -- every
+       block at the format's maximum of side data -- so that a damaged section table is reported as truncated instead
+       of sending the parser gigabytes away; applications that feed untrusted input call HVQM4SetFrameBytes. */
+    const size_t len = c->next_frame_bytes ? c->next_frame_bytes : (size_t)64 * c->frame_bytes + 65536;
     c->next_frame_bytes = 0;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
@@ -1208,6 +1241,13 @@ void compat_decode(SeqObj *so, int type, const uint8_t *frame, void *present, vo
     const auto t3 = now();
     ok = ok && cuda_ok(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
     if (!ok) c->errors |= HVQM4_ERR_CUDA;
+    if (ok && !is_device_ptr(present))
+        for (auto &t : c->twin)
+            if (t.host == present)
+            {   /* the host frame and its twin are equal now */
+                t.print = twin_print(present, c->frame_bytes);
+                t.printed = true;
+            }
     if (c->trace)
     {
         c->t_phase[0] += secs(t0, t1);

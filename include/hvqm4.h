@@ -102,7 +102,9 @@ enum
 int HVQM4SetVersion(SeqObj *seqobj, int version);
 
 /* Optional: readable bytes behind the `frame` pointer of the NEXT decode call (record size
-   minus 4).  Without it sections are bounded by their own declared sizes only. */
+   minus 4).  The SDK protocol carries no length: without this call the sections are bounded by
+   their own declared sizes and by what a picture of this geometry can need at most (64 frames'
+   worth), so feed untrusted input with it. */
 void HVQM4SetFrameBytes(SeqObj *seqobj, uint32_t bytes);
 
 /* OR of all error bits since the last call; clears them.  The SDK entry points return void. */
@@ -113,7 +115,10 @@ int HVQM4GetLastCudaError(void);
 void HVQM4ReleaseBuffer(SeqObj *seqobj);
 
 /* Drop-in mode caches a device copy of every host frame buffer it has written, keyed by
-   the host address.  Call this if the application modified such a buffer itself. */
+   the host address.  A reference frame is fingerprinted (64 words spread over the buffer)
+   before every use and uploaded again when the application has written into it; call this
+   after a modification that such a sample may miss.  Device frame pointers (zero-copy mode)
+   must be followed by 64 readable bytes: the half-sample filter reads whole aligned words. */
 void HVQM4InvalidateFrame(SeqObj *seqobj, void *host_frame);
 
 /* dumpRGB (h4m:895-926) of one frame through the GPU: `frame` is a planar picture of

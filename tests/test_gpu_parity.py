@@ -571,6 +571,44 @@ def test_staggered_streams_and_partial_steps_match_oracle(native_lib, oracle, gp
         native_lib.lib().HVQM4HostFree(pinned)
 
 
+def test_sdk_mode_notices_a_reference_frame_the_application_wrote_into(native_lib, oracle):
+    """Drop-in mode keeps device twins of the host frame buffers.  An application that writes into a reference frame
+    between two decode calls must get pictures predicted from what it wrote -- the same as after an explicit
+    HVQM4InvalidateFrame -- and a frame it scribbled over and restored must still predict the reference's picture."""
+    data = synth.generate(320, 240, 15, "IPPP", 1, seed=8900, profile=0)
+    info, frames = native_lib.parse_file(data)
+    fb = info.width * info.height * 3 // 2
+    pics = [data[f.offset:f.offset + f.bytes] for f in frames]
+    want = [yuv for _, _, _, yuv in oracle.PortDecoder(data).frames()]
+    lib = native_lib.lib()
+
+    def run(invalidate):
+        dec = native_lib.SeqDecoder(info.width, info.height, info.version)
+        try:
+            a, b = (ctypes.c_uint8 * (fb + 64))(), (ctypes.c_uint8 * (fb + 64))()
+            dec.decode(frames[0].frame_type, pics[0], a)
+            assert bytes(a)[:fb] == want[0]
+            dec.decode(frames[1].frame_type, pics[1], b, a)
+            assert bytes(b)[:fb] == want[1]
+            ctypes.memset(b, 0x33, fb)                 # scribbled over ...
+            ctypes.memmove(b, want[1], fb)             # ... and restored
+            if invalidate:
+                lib.HVQM4InvalidateFrame(ctypes.byref(dec.seq), b)
+            dec.decode(frames[2].frame_type, pics[2], a, b)
+            assert bytes(a)[:fb] == want[2]
+            ctypes.memset(a, 0x80, fb)                 # really changed: the next picture is predicted from grey
+            if invalidate:
+                lib.HVQM4InvalidateFrame(ctypes.byref(dec.seq), a)
+            dec.decode(frames[3].frame_type, pics[3], b, a)
+            return bytes(b)[:fb]
+        finally:
+            dec.close()
+
+    from_grey = run(True)
+    assert from_grey != want[3]
+    assert run(False) == from_grey                     # noticed without being told
+
+
 def test_entropy_mode_switch_after_the_first_picture_is_refused(native_lib, golden):
     """The host and the GPU entropy stage keep separate per-stream state: switching once pictures have been decoded
     would reconstruct the next P/B pictures against the wrong nest.  Same mode again is fine."""
