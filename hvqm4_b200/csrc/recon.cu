@@ -153,18 +153,37 @@ template <bool kTile> __device__ __forceinline__ uint32_t block_off(const ReconV
 template <bool kTile> __device__ __forceinline__ void block_st(uint8_t *base, uint32_t off, uint32_t val);
 template <bool kTile> __device__ __forceinline__ uint32_t block_ld(const uint8_t *base, uint32_t off);
 
-/* RECORD work of one chunk: one record per lane */
-template <bool kTile>
-__device__ __forceinline__ void record_chunk(const ReconView &v, const BandOut &o, uint32_t c, int lane)
+/* What the band kernel stages in shared memory for the record phase of a band (cp.async.bulk, issued before the map phase,
+   landed long before the record phase starts): the chunk descriptors and the records of the band's three classes and
+   the band's rows of the vector table.  In the profile of the kernel that read them from global memory a third of all
+   stall samples sat on the heads of the record phase's load chain (descriptor -> header -> vector word -> window rows,
+   each a trip to L2 or HBM); staged, only the window rows are left.  A class whose records do not fit stays where it is:
+   the pointers below are generic and point into shared or global memory. */
+struct BandStage
 {
-    const uint2 cd = __ldg(reinterpret_cast<const uint2 *>(v.chunks) + c);
+    unsigned long long bar;
+    uint32_t pad0[2];
+    const uint2 *desc[SYM_REC_CLASSES];       /* descriptor of chunk c of class k: desc[k][c - c0[k]] */
+    const uint32_t *rec[SYM_REC_CLASSES];     /* record word w (counted from the picture's first record word): rec[k][w] */
+    const uint32_t *mv;                       /* vector word of macroblock (mx, my): mv[my * mcb_w + mx] */
+    uint32_t c0[SYM_REC_CLASSES], c1[SYM_REC_CLASSES];
+};
+
+/* RECORD work of one chunk of class cls: one record per lane */
+template <bool kTile>
+__device__ __forceinline__ void record_chunk(const ReconView &v, const BandOut &o, const BandStage &st, int cls, uint32_t c, int lane)
+{
+    const uint2 cd = st.desc[cls][c - st.c0[cls]];
     const uint32_t count = cd.y & 0xFF, len = ((cd.y >> 8) & 0xFF) + 1;
-    const int cls = (int)((cd.y >> 16) & 0xFF);
     if ((uint32_t)lane >= count) return;
-    const uint32_t *rec = v.rec + cd.x + lane * len;
+    const uint32_t *rec = st.rec[cls] + cd.x + lane * len;
+    const uint32_t hdr = *rec;
     uint32_t t;
     int plane, bx, by;
-    rc_record_coords(__ldg(rec), t, plane, bx, by);
+    rc_record_coords(hdr, t, plane, bx, by);
+    uint32_t extra = 0;
+    if (cls == SYM_REC_INTER) extra = st.mv[(plane ? by : by >> 1) * v.mcb_w + (plane ? bx : bx >> 1)];
+    else if (cls == SYM_REC_INTRA) extra = rc_record_extra(v, cls, hdr);
     int pw;
     const uint32_t dst = block_off<kTile>(v, o, plane, bx, by, pw);
     uint8_t *const pic = v.present;
@@ -174,7 +193,7 @@ __device__ __forceinline__ void record_chunk(const ReconView &v, const BandOut &
 #pragma unroll
         for (int r = 0; r < 4; ++r) rows[r] = block_ld<kTile>(pic, dst + r * pw);
     }
-    rc_record_block(v, cls, len, rec, rows);
+    rc_record_block_pre<true>(v, cls, len, rec, hdr, extra, rows);
 #pragma unroll
     for (int r = 0; r < 4; ++r) block_st<kTile>(pic, dst + r * pw, rows[r]);
 }
@@ -250,6 +269,9 @@ recon_map_kernel(const ReconJob *__restrict__ jobs, int units_per_pic, int ctas_
  * ------------------------------------------------------------------------------------------ */
 constexpr int kRecWarps = 8;
 constexpr int kRecSmem = RC_SMEM_TABLE_BYTES + SYM_NEST_H * 40 + 32;
+/* band kernels: [tables + view | nest staging scratch | BandStage | queues | staged record data | output tile (kTile)] */
+constexpr int kBandStageOff = (kRecSmem + 15) & ~15;
+constexpr int kBandQueueOff = kBandStageOff + 128;
 
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kRecWarps * 32, kMinBlocks)
@@ -523,45 +545,117 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, const BandOut 
 }
 
 /* one band of kRows macroblock rows of one picture: the whole CTA.  tile_off: shared-memory offset of the output tile (kTile) */
+/* stage_off / stage_cap: shared-memory area for the band's record data (0 bytes: nothing is staged); stage_phase: how often
+   the CTA has used the staging barrier before (the walk kernel reuses it) */
 template <bool kTile, int kRows>
-__device__ __forceinline__ void band_item(const ReconJob *__restrict__ jobs, int job, int band, uint32_t *queue, int queue_cap, uint32_t tile_off)
+__device__ __forceinline__ bool band_item(const ReconJob *__restrict__ jobs, int job, int band, uint32_t *queue, int queue_cap, uint32_t tile_off,
+                                          uint32_t stage_off, uint32_t stage_cap, uint32_t stage_phase)
 {
     ReconView &vw = *reinterpret_cast<ReconView *>(rc_smem + RC_SMEM_VIEW_OFF);
-    if (threadIdx.x == 0) load_view(vw, jobs[job]);
+    BandStage &st = *reinterpret_cast<BandStage *>(rc_smem + kBandStageOff);
+    if (threadIdx.x == 0)
+    {
+        load_view(vw, jobs[job]);
+        if (stage_phase == 0)
+        {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&st.bar)) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
     __syncthreads();
     const ReconView &v = vw;
-    if (!v.blob) return;
+    if (!v.blob) return false;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (v.has_nest) nest_stage_begin<kBandWarps * 32>(v, rc_smem + RC_SMEM_TABLE_BYTES);   /* lands during the map phase */
 
-    /* map phase */
     const int row0 = band * kRows, row1 = min(row0 + kRows, v.mcb_h);
-    const BandOut out = {tile_off, (uint32_t)((row1 - row0) * 8 * v.width), (uint32_t)((row1 - row0) * 4 * (v.width >> 1)), row0};
-    for (int mx0 = 0; mx0 < v.mcb_w; mx0 += kTileMcbs)
-        band_map_tile<kTile>(v, out, row0, row1, mx0, min(mx0 + kTileMcbs, v.mcb_w), queue, queue_cap);
-    /* record phase */
-    const uint32_t nb1 = v.n_bands + 1;
     /* the chunks of a class are ordered by record band: bands of 8, 4 or 1 macroblock rows (h4e_set_band_rows; kRows is
        a multiple), of which rows row0..row1 are one range */
     const int nb = (int)v.n_bands;
     const int rpb = nb == v.mcb_h ? 1 : nb == (v.mcb_h + 3) / 4 ? 4 : 8;
     const int b0 = row0 / rpb, b1 = min((row1 + rpb - 1) / rpb, nb);
-    const uint32_t raw0 = __ldg(v.bands + b0), raw1 = __ldg(v.bands + b1);
-    const uint32_t intra0 = __ldg(v.bands + nb1 + b0), intra1 = __ldg(v.bands + nb1 + b1);
-    const uint32_t inter0 = __ldg(v.bands + 2 * nb1 + b0), inter1 = __ldg(v.bands + 2 * nb1 + b1);
+    if (warp == kBandWarps - 1)
+    {   /* the last warp (it has the fewest block rows of the map phase when they do not divide) requests the band's record
+           data: lane k < 3 looks up class k's chunk and record range (two dependent loads), lane 3 the vector rows */
+        const uint32_t nb1 = v.n_bands + 1;
+        uint32_t src = 0, bytes = 0, head = 0;         /* source offset in the blob, bytes to copy (16-byte units), misalignment */
+        uint32_t c0 = 0, c1 = 0, r0 = 0, r1 = 0;
+        if (lane < SYM_REC_CLASSES)
+        {
+            c0 = __ldg(v.bands + lane * nb1 + b0);
+            c1 = __ldg(v.bands + lane * nb1 + b1);
+            const uint32_t n_words = __ldg(reinterpret_cast<const uint32_t *>(v.blob + offsetof(SymHeader, n_rec_words)));
+            r0 = c0 < v.n_chunks ? __ldg(v.chunks + 2 * c0) : n_words;
+            r1 = c1 < v.n_chunks ? __ldg(v.chunks + 2 * c1) : n_words;
+        }
+        /* seven ranges of the blob: descriptors per class (lanes 0-2), vectors (lane 3), records per class (lanes 4-6: predicted
+           AOT first -- its chain is the longest --, then intra AOT, then raw: what does not fit is the cheapest to leave) */
+        const int k = lane < 4 ? lane & 3 : 6 - lane;
+        const uint32_t kc0 = __shfl_sync(0xFFFFFFFFu, c0, k), kc1 = __shfl_sync(0xFFFFFFFFu, c1, k);
+        const uint32_t kr0 = __shfl_sync(0xFFFFFFFFu, r0, k), kr1 = __shfl_sync(0xFFFFFFFFu, r1, k);
+        uint32_t lo = 0, hi = 0;
+        if (lane < 3) { lo = (uint32_t)((const uint8_t *)v.chunks - v.blob) + kc0 * 8u; hi = lo + (kc1 - kc0) * 8u; }
+        else if (lane == 3 && !v.is_ipic) { lo = v.off_mv + (uint32_t)(row0 * v.mcb_w * 4); hi = lo + (uint32_t)((row1 - row0) * v.mcb_w * 4); }
+        else if (lane >= 4 && lane < 7) { lo = (uint32_t)((const uint8_t *)v.rec - v.blob) + kr0 * 4u; hi = (uint32_t)((const uint8_t *)v.rec - v.blob) + kr1 * 4u; }
+        if (hi > lo) { src = lo & ~15u; head = lo - src; bytes = ((hi + 15u) & ~15u) - src; }
+        /* places in the staging area by prefix sum; a range that does not fit (and everything behind it) stays in global memory */
+        uint32_t at = bytes;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1)
+        {
+            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, at, d);
+            if ((lane & 7) >= d) at += up;
+        }
+        const bool fits = stage_cap != 0 && at <= stage_cap;
+        const uint32_t dst = stage_off + at - bytes;
+        const uint8_t *base = fits ? rc_smem + dst + head : v.blob + lo;      /* where byte `lo` of the blob is read from */
+        if (lane < 3)
+        {
+            st.desc[lane] = reinterpret_cast<const uint2 *>(base);
+            st.c0[lane] = kc0;
+            st.c1[lane] = kc1;
+        }
+        else if (lane == 3) st.mv = reinterpret_cast<const uint32_t *>(base) - row0 * v.mcb_w;
+        else if (lane < 7) st.rec[k] = reinterpret_cast<const uint32_t *>(base) - kr0;
+        uint32_t tx = fits && lane < 7 ? bytes : 0u;
+#pragma unroll
+        for (int d = 4; d; d >>= 1) tx += __shfl_xor_sync(0xFFFFFFFFu, tx, d);
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&st.bar);
+        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+        __syncwarp();
+        if (fits && lane < 7 && bytes)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(rc_smem + dst)), "l"(v.blob + src), "r"(bytes), "r"(bar) : "memory");
+    }
+
+    /* map phase */
+    const BandOut out = {tile_off, (uint32_t)((row1 - row0) * 8 * v.width), (uint32_t)((row1 - row0) * 4 * (v.width >> 1)), row0};
+    for (int mx0 = 0; mx0 < v.mcb_w; mx0 += kTileMcbs)
+        band_map_tile<kTile>(v, out, row0, row1, mx0, min(mx0 + kTileMcbs, v.mcb_w), queue, queue_cap);
+    /* record phase */
     if (v.has_nest) nest_stage_wait();
+    __syncthreads();     /* map stores of the band and the staging pointers visible to the whole CTA */
+    {   /* the band's record data has landed (it was requested before the map phase) */
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&st.bar);
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(bar), "r"(stage_phase & 1u) : "memory");
+    }
+    const uint32_t raw0 = st.c0[SYM_REC_RAW], raw1 = st.c1[SYM_REC_RAW];
+    const uint32_t intra0 = st.c0[SYM_REC_INTRA], intra1 = st.c1[SYM_REC_INTRA];
+    const uint32_t inter0 = st.c0[SYM_REC_INTER], inter1 = st.c1[SYM_REC_INTER];
     if (intra1 > intra0)
     {
-        __syncthreads();
         nest_spread<kBandWarps * 32>(rc_smem + RC_SMEM_TABLE_BYTES, v.portrait != 0);
+        __syncthreads();     /* nest table complete */
     }
-    __syncthreads();     /* map stores of the band visible to the whole CTA; nest table complete */
 #pragma unroll 1
-    for (uint32_t c = raw0 + warp; c < raw1; c += kBandWarps) record_chunk<kTile>(v, out, c, lane);
+    for (uint32_t c = raw0 + warp; c < raw1; c += kBandWarps) record_chunk<kTile>(v, out, st, SYM_REC_RAW, c, lane);
 #pragma unroll 1
-    for (uint32_t c = intra0 + warp; c < intra1; c += kBandWarps) record_chunk<kTile>(v, out, c, lane);
+    for (uint32_t c = intra0 + warp; c < intra1; c += kBandWarps) record_chunk<kTile>(v, out, st, SYM_REC_INTRA, c, lane);
 #pragma unroll 1
-    for (uint32_t c = inter0 + warp; c < inter1; c += kBandWarps) record_chunk<kTile>(v, out, c, lane);
+    for (uint32_t c = inter0 + warp; c < inter1; c += kBandWarps) record_chunk<kTile>(v, out, st, SYM_REC_INTER, c, lane);
     if (kTile)
     {   /* the band leaves as whole picture rows: three bulk stores (shared memory -> picture) */
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     /* this thread's tile writes -> visible to the copies */
@@ -579,18 +673,19 @@ __device__ __forceinline__ void band_item(const ReconJob *__restrict__ jobs, int
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    /* the CTA's shared memory is released when it exits */
         }
     }
+    return true;
 }
 
 /* one CTA per (picture, band) */
 template <int kMinBlocks, bool kTile, int kRows>
 __global__ void __launch_bounds__(kBandWarps * 32, kMinBlocks)
-recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap)
+recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap, int stage_cap)
 {
-    /* dynamic shared memory: [tables + view | nest staging scratch | queues | output tile (kTile)] */
-    uint32_t *queue = reinterpret_cast<uint32_t *>(rc_smem + kRecSmem) + (threadIdx.x >> 5) * queue_cap;   /* the warp's own */
+    uint32_t *queue = reinterpret_cast<uint32_t *>(rc_smem + kBandQueueOff) + (threadIdx.x >> 5) * queue_cap;   /* the warp's own */
     build_div_tables<kBandWarps * 32>();
     const int job = blockIdx.x / n_bands;
-    band_item<kTile, kRows>(jobs, job, blockIdx.x - job * n_bands, queue, queue_cap, (uint32_t)((kRecSmem + kBandWarps * queue_cap * 4 + 127) & ~127));
+    const uint32_t stage_off = (uint32_t)((kBandQueueOff + kBandWarps * queue_cap * 4 + 127) & ~127);
+    band_item<kTile, kRows>(jobs, job, blockIdx.x - job * n_bands, queue, queue_cap, stage_off + (uint32_t)stage_cap, stage_off, (uint32_t)stage_cap, 0u);
 }
 
 /* The fallback launch behind the sweep kernel (skip_handled = 1: pictures whose job says pad[0] = 1 are already
@@ -599,8 +694,9 @@ recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap)
 __global__ void __launch_bounds__(kBandWarps * 32, 2)
 recon_band_walk_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap, int n_items, int skip_handled)
 {
-    uint32_t *queue = reinterpret_cast<uint32_t *>(rc_smem + kRecSmem) + (threadIdx.x >> 5) * queue_cap;
+    uint32_t *queue = reinterpret_cast<uint32_t *>(rc_smem + kBandQueueOff) + (threadIdx.x >> 5) * queue_cap;
     build_div_tables<kBandWarps * 32>();
+    uint32_t phase = 0;      /* uses of the staging barrier so far (nothing is staged here: the record data is read in place) */
 #pragma unroll 1
     for (int item = blockIdx.x; item < n_items; item += gridDim.x)
     {
@@ -608,7 +704,7 @@ recon_band_walk_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue
         if (skip_handled == 1 && __ldg(&jobs[job].pad[0])) continue;
         if (skip_handled == 2 && !__ldg(&jobs[job].pad[1])) continue;
         __syncthreads();     /* the previous item is finished (view, tables, queues) */
-        band_item<false, kBandRows>(jobs, job, item - job * n_bands, queue, queue_cap, 0u);
+        phase += band_item<false, kBandRows>(jobs, job, item - job * n_bands, queue, queue_cap, 0u, 0u, 0u, phase) ? 1u : 0u;
     }
 }
 
@@ -654,23 +750,39 @@ int env_int(const char *name)
 }  // namespace
 
 template <int kMinBlocks, bool kTile, int kRows>
-int launch_band_plain(const ReconJob *d_jobs, long long items, int n_bands, int cap, int smem, cudaStream_t stream)
+int launch_band_plain(const ReconJob *d_jobs, long long items, int n_bands, int cap, int stage, int smem, cudaStream_t stream)
 {
     if (smem > 48 * 1024)
     {   /* opt in (per device, so not cached) */
         const cudaError_t e = cudaFuncSetAttribute(recon_band_kernel<kMinBlocks, kTile, kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
     }
-    recon_band_kernel<kMinBlocks, kTile, kRows><<<(unsigned)items, kBandWarps * 32, smem, stream>>>(d_jobs, n_bands, cap);
+    recon_band_kernel<kMinBlocks, kTile, kRows><<<(unsigned)items, kBandWarps * 32, smem, stream>>>(d_jobs, n_bands, cap, stage);
     return (int)cudaGetLastError();
+}
+
+/* Bytes of shared memory for a band's staged record data (descriptors, vector rows, records; what does not fit is read in
+   place).  Measured on B200, 1 024 streams (profiles/r02_band_stage_ab.txt): dense content 1.203 M frames/s with nothing
+   staged, 1.154 M with 4 KB (descriptors + vectors), 1.171 M with 12 KB, 1.128 M with 20 KB, 1.017 M with 30 KB (everything):
+   every staged kilobyte is taken from the L1 cache that the reference gathers live in (three CTAs per SM), and a chain that
+   starts earlier only queues earlier on the same memory system; sparse content gains 5 % (2.07 -> 2.18 M) but runs the
+   map + record kernels anyway (3.15 M).  So nothing is staged by default; HVQM4_BAND_STAGE=<bytes> (1 = eight bytes per
+   block) turns it on for experiments. */
+static inline int band_stage_bytes(int mcb_w, int rows)
+{
+    static const int env = getenv("HVQM4_BAND_STAGE") ? atoi(getenv("HVQM4_BAND_STAGE")) : 0;
+    if (env <= 0) return 0;
+    const int want = env > 1 ? env : rows * mcb_w * 6 * 8;
+    return (want < 48 * 1024 ? want : 48 * 1024) & ~127;
 }
 
 /* bytes of the output tile of one band: `rows` macroblock rows of all three planes */
 static inline int band_tile_bytes(int mcb_w, int rows) { return rows * 8 * (mcb_w * 8) * 3 / 2; }
-static inline int band_tile_smem(int mcb_w, int rows)
+static inline int band_plain_smem(int mcb_w, int rows)
 {
-    return ((kRecSmem + kBandWarps * band_queue_entries(mcb_w, rows) * 4 + 127) & ~127) + band_tile_bytes(mcb_w, rows);
+    return ((kBandQueueOff + kBandWarps * band_queue_entries(mcb_w, rows) * 4 + 127) & ~127) + band_stage_bytes(mcb_w, rows);
 }
+static inline int band_tile_smem(int mcb_w, int rows) { return band_plain_smem(mcb_w, rows) + band_tile_bytes(mcb_w, rows); }
 
 /* tile = 0: blocks go straight into the picture, one CTA per band of 8 macroblock rows (n_bands of them per picture);
    tile = 8 / 4: the band (8 / 4 macroblock rows) is assembled in shared memory (two / four CTAs per SM) */
@@ -680,7 +792,7 @@ int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, int mcb_w, cuda
     long long items = (long long)n_jobs * n_bands;
     if (items > 0x7FFFFFFFll) return (int)cudaErrorInvalidConfiguration;
     const int cap = band_queue_entries(mcb_w);
-    const int smem = kRecSmem + kBandWarps * cap * 4;
+    const int smem = kBandQueueOff + kBandWarps * cap * 4;
     if (skip_handled)
     {
         const long long grid = items > 148 * 2 ? 148 * 2 : items;
@@ -692,13 +804,14 @@ int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, int mcb_w, cuda
         recon_band_walk_kernel<<<(unsigned)grid, kBandWarps * 32, smem, stream>>>(d_jobs, n_bands, cap, (int)items, skip_handled);
         return (int)cudaGetLastError();
     }
-    if (tile == 8) return launch_band_plain<2, true, 8>(d_jobs, items, n_bands, cap, band_tile_smem(mcb_w, 8), stream);
+    if (tile == 8) return launch_band_plain<2, true, 8>(d_jobs, items, n_bands, cap, band_stage_bytes(mcb_w, 8), band_tile_smem(mcb_w, 8), stream);
     if (tile == 4)
     {
         const int nb4 = (mcb_h + 3) / 4;
-        return launch_band_plain<4, true, 4>(d_jobs, (long long)n_jobs * nb4, nb4, band_queue_entries(mcb_w, 4), band_tile_smem(mcb_w, 4), stream);
+        return launch_band_plain<4, true, 4>(d_jobs, (long long)n_jobs * nb4, nb4, band_queue_entries(mcb_w, 4), band_stage_bytes(mcb_w, 4),
+                                             band_tile_smem(mcb_w, 4), stream);
     }
-    return launch_band_plain<kMinBlocks, false, kBandRows>(d_jobs, items, n_bands, cap, smem, stream);
+    return launch_band_plain<kMinBlocks, false, kBandRows>(d_jobs, items, n_bands, cap, band_stage_bytes(mcb_w, kBandRows), band_plain_smem(mcb_w, kBandRows), stream);
 }
 
 /* does the tile variant of the band kernel fit `ctas` times into an SM for pictures this wide? */

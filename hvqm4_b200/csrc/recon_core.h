@@ -325,7 +325,16 @@ RC_HD void rc_add_basis(const ReconView &v, uint32_t word, const Win window, int
     }
 }
 
-template <bool kInter, class Win>
+/* kGen: the side words are read with plain (generic) loads -- the band kernel stages a band's records in shared memory
+   when they fit and leaves them in global memory when they do not, one code path for both */
+template <bool kGen>
+RC_HD uint32_t rc_ld_side(const uint32_t *p)
+{
+    if (kGen) return *p;
+    return RC_LD32(p);
+}
+
+template <bool kInter, bool kGen = false, class Win>
 RC_HD int32_t rc_aot_sum(const ReconView &v, const uint32_t *side, int n, const Win window, int32_t acc[16])
 {
     int32_t scale_sum = 0;
@@ -334,11 +343,11 @@ RC_HD int32_t rc_aot_sum(const ReconView &v, const uint32_t *side, int n, const 
     /* the first four basis words are fetched together (one memory latency instead of one per basis) */
     uint32_t w[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) w[k] = k < n ? RC_LD32(side + k) : 0u;
+    for (int k = 0; k < 4; ++k) w[k] = k < n ? rc_ld_side<kGen>(side + k) : 0u;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         if (k < n) rc_add_basis<kInter>(v, w[k], window, scale_sum, acc);
-    for (int k = 4; k < n; ++k) rc_add_basis<kInter>(v, RC_LD32(side + k), window, scale_sum, acc);
+    for (int k = 4; k < n; ++k) rc_add_basis<kInter>(v, rc_ld_side<kGen>(side + k), window, scale_sum, acc);
     uint32_t total = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) total += (uint32_t)acc[i];
@@ -346,10 +355,11 @@ RC_HD int32_t rc_aot_sum(const ReconView &v, const uint32_t *side, int n, const 
 }
 
 /* IntraAotBlock, h4m:1358-1377 */
+template <bool kGen = false>
 RC_HD void rc_intra_aot(const ReconView &v, uint32_t rows[4], const uint32_t *side, int n, int V)
 {
     int32_t acc[16];
-    const int32_t mean = rc_aot_sum<false>(v, side, n, RcNoWindow{}, acc);
+    const int32_t mean = rc_aot_sum<false, kGen>(v, side, n, RcNoWindow{}, acc);
     /* modulo 2^32 like the reference's int32 on its targets (damaged scale symbols overflow it) */
     const uint32_t delta = ((uint32_t)V << v.unk_shift) - (uint32_t)mean;
 #pragma unroll
@@ -466,12 +476,12 @@ RC_HD uint32_t rc_sum4(uint32_t packed, uint32_t acc)
 #endif
 }
 
-template <class Win>
+template <bool kGen = false, class Win>
 RC_HD void rc_predicted_aot(const ReconView &v, uint32_t rows[4], const uint32_t *side, int nibble, const Win window)
 {
     int32_t acc[16];
-    const uint32_t aot_mean = (uint32_t)rc_aot_sum<true>(v, side, nibble - 1, window, acc);
-    const uint32_t pair = RC_LD32(side + nibble - 1);
+    const uint32_t aot_mean = (uint32_t)rc_aot_sum<true, kGen>(v, side, nibble - 1, window, acc);
+    const uint32_t pair = rc_ld_side<kGen>(side + nibble - 1);
     const int32_t mean = (int32_t)(rc_sum4(rows[3], rc_sum4(rows[2], rc_sum4(rows[1], rc_sum4(rows[0], 8u)))) >> 4);
     int32_t lo = 255, hi = 0;
 #pragma unroll
@@ -693,20 +703,21 @@ RC_HD uint32_t rc_record_extra(const ReconView &v, int cls, uint32_t hdr)
 }
 
 /* hdr = rec[0], extra = rc_record_extra(v, cls, hdr) */
+template <bool kGen = false>
 RC_HD void rc_record_block_pre(const ReconView &v, int cls, uint32_t len, const uint32_t *rec, uint32_t hdr, uint32_t extra, uint32_t rows[4])
 {
     if (cls == SYM_REC_RAW)
     {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) rows[r] = RC_LD32(rec + 1 + r);
+        for (int r = 0; r < 4; ++r) rows[r] = rc_ld_side<kGen>(rec + 1 + r);
     }
     else if (cls == SYM_REC_INTRA)
-        rc_intra_aot(v, rows, rec + 1, (int)len - 1, (int)extra);
+        rc_intra_aot<kGen>(v, rows, rec + 1, (int)len - 1, (int)extra);
     else
     {
         const uint8_t *window = rc_motion_window(v, hdr & 0xFF, extra);
         if (!window) return;                          /* the map work painted it grey */
-        rc_predicted_aot(v, rows, rec + 1, (int)len - 1, RcLinearWindow{window, v.width});
+        rc_predicted_aot<kGen>(v, rows, rec + 1, (int)len - 1, RcLinearWindow{window, v.width});
     }
 }
 
