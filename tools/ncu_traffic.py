@@ -1,6 +1,7 @@
 """Sums dram__bytes_read.sum + dram__bytes_write.sum and gpu__time_duration.sum per step from an
 `ncu --csv --metrics ...` log of tools/profile_recon.py and prints / merges the result into
-profiles/r01_traffic.json.
+profiles/r02_traffic.json, stamped with the hash of the kernel sources it was captured from (bench.py only quotes a capture
+of the sources it runs).
     python tools/ncu_traffic.py log.csv key launches_per_step first_launch n_steps"""
 import csv
 import json
@@ -30,13 +31,19 @@ for i in ids:
 print(f"{key}: {len(ids)} launches = {n_steps} steps; DRAM {tot_b / n_steps / 1e6:.1f} MB/step, {tot_t / n_steps * 1e6:.1f} us/step (ncu, cold cache, serialised)")
 for k, e in by_kernel.items():
     print(f"   {k}: {e[0]} launches, {100 * e[1] / tot_t:.1f}% of time, {e[2] / e[0] / 1e6:.1f} MB DRAM per launch")
-out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r01_traffic.json")
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, root)
+import bench  # noqa: E402  (kernel_sources_sha)
+out = os.path.join(root, "profiles", "r02_traffic.json")
 try:
     t = json.load(open(out))
+    if t.get("kernel_sources_sha") != bench.kernel_sources_sha():
+        raise ValueError("stale capture")
 except (OSError, ValueError):
     t = {"how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none on tools/profile_recon.py; "
                 "bytes summed over the launches of one step (one picture per stream), averaged over the 16 steps of a GOP replay",
          "dram_bytes_per_step": {}, "ncu_us_per_step": {}}
 t["dram_bytes_per_step"][key] = tot_b / n_steps
 t["ncu_us_per_step"][key] = tot_t / n_steps * 1e6
+t["kernel_sources_sha"] = bench.kernel_sources_sha()
 json.dump(t, open(out, "w"), indent=1)
