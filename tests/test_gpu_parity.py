@@ -369,6 +369,42 @@ def test_gpu_entropy_stage_equals_host_stage_on_damaged_streams(native_lib, prof
     assert native_lib.lib().HVQM4GetLastCudaError() == 0
 
 
+@pytest.mark.parametrize("recon", [0, 6])
+def test_damaged_headers_and_section_tables_host_equals_gpu_stage(native_lib, recon):
+    """The part of a picture the other fuzz test leaves alone: the 8-byte header (dc_shift, unk_shift, nest origin /
+    residual-bit counts) and the section table, of I, P and B pictures.  Hostile shifts are clamped, a nest origin outside
+    the map is pulled back, sections that point outside the record read as empty -- whatever the host stage makes of it,
+    the GPU build makes the same frames and error bits, no kernel faults (also not the row kernel with its tensor copies,
+    which leaves pictures with poisoned or out-of-plane vectors to the band kernel)."""
+    import numpy as np
+    rng = np.random.default_rng(4242)
+    files = []
+    for i in range(8):
+        data = bytearray(synth.generate(320, 240, 15, "IPBBPB", 1, seed=950 + i, profile=i % 3))
+        _, recs = native_lib.parse_file(bytes(data))
+        for k, fr in enumerate(recs):
+            if i == 0:
+                continue                                    # one intact stream
+            if (i + k) % 2:
+                continue                                    # every other picture of a stream
+            if i % 2:                                       # header bytes: any value
+                data[fr.offset + int(rng.integers(0, 8))] = int(rng.integers(0, 256))
+            else:                                           # section table: flip bits of an offset word
+                at = fr.offset + 8 + int(rng.integers(0, 68))
+                data[at] ^= 1 << int(rng.integers(0, 8))
+        files.append(bytes(data))
+    native_lib.set_recon_mode(recon)
+    try:
+        host, host_bits = _decode_damaged(native_lib, files, False)
+        dev, dev_bits = _decode_damaged(native_lib, files, True)
+    finally:
+        native_lib.set_recon_mode(0)
+    assert host == dev
+    assert host_bits == dev_bits and host_bits != 0
+    assert native_lib.lib().HVQM4GetLastCudaError() == 0
+    assert native_lib.row_errors() == 0
+
+
 def test_gpu_entropy_stage_matches_oracle_on_fresh_seeds(native_lib, oracle):
     files = [synth.generate(320, 240, 15 if seed % 2 else 13, "IPBBPBB", 1, seed=7100 + seed, profile=(seed // 2) % 2)
              for seed in range(2)]
