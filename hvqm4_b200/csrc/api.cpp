@@ -555,6 +555,9 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
         b->offs[i] = total + (gather ? (size_t)((uintptr_t)b->gather_src[i] & 15u) : 0);
         total += align_up((size_t)frame_bytes[i] + 16, 16) + (gather ? 16 : 0);
     }
+    /* everything that can refuse the step comes before anything of the batch changes (surface rotation, parser turn,
+       I-picture fences): an error return leaves the batch where it was */
+    if (total > 0xFFFFFFFFull) return HVQM4_ERR_OVERFLOW;
     Arena &a = b->arena[b->cur];
     const auto t_w0 = std::chrono::steady_clock::now();
     if (a.in_flight)
@@ -635,7 +638,9 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
         cudaStreamWaitEvent(sp, b->ev_parse[b->ipic_slot], 0);
         --b->ipic_fence_left;
     }
-    if (total > 0xFFFFFFFFull) return HVQM4_ERR_OVERFLOW;
+    /* from here on work is queued on the arena: it counts as in flight whatever happens next */
+    a.in_flight = true;
+    cudaEventRecord(a.consumed, sp);
     if (!cuda_ok(cudaMemcpyAsync(a.d, a.h, gather ? head_bytes : total, cudaMemcpyHostToDevice, sp), "cudaMemcpyAsync(H2D)")) return HVQM4_ERR_CUDA;
     if (gather)
     {
