@@ -283,6 +283,9 @@ def main():
                     help="end to end: bitstreams fetched by the GPU from registered host memory (auto: from 4 ranks per box on)")
     ap.add_argument("--profile", type=int, default=0, help="0 dense (headline), 1 realistic")
     ap.add_argument("--host-threads", type=int, default=0)
+    ap.add_argument("--host-share", type=int, default=-1,
+                    help="end to end, GPU entropy stage: streams per GPU whose pictures the host threads parse next to the parse kernel "
+                         "(HVQM4BatchSetHostShare); -1 = one stream in eight per 16 host threads at one or two ranks, none beyond")
     ap.add_argument("--ref-seconds", type=float, default=12.0, help="CPU seconds per process for the reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -492,10 +495,17 @@ def main():
         e2e_host["note"] = ("wall clock around K GOPs: host entropy threads -> pinned symbol arena -> H2D -> kernels -> "
                             "D2H of every frame to pinned host memory")
         # (b) the same C source compiled as device code (entropy_dev.cu): raw pictures up, frames down
-        gb = api.Batch(S, W, H, 15, device=local, host_threads=threads, gpu_entropy=True)
-        e2e = measure_e2e(gb, 12.0, "gpu (one warp per picture)")
+        # the host cores are idle in this mode: they parse a share of the streams next to the parse kernel (measured on one
+        # B200 + 16 cores, profiles/r02_host_share_ab.txt: 106 k frames/s with no share, 110-111 k with 64..160 of 1 024 streams,
+        # 104 k with 192, 87 k with 256).  With four ranks or more the node's PCIe, not the parser, is the limit: no share.
+        share = args.host_share if args.host_share >= 0 else (S * threads // 128 if world <= 2 else 0)
+        share = max(0, min(S, share))
+        gb = api.Batch(S, W, H, 15, device=local, host_threads=threads, gpu_entropy=True, host_share=share)
+        e2e = measure_e2e(gb, 12.0, "gpu (one warp per picture)" + (f" + host threads for {share} of {S} streams" if share else ""))
+        e2e["host_share_streams"] = share
         e2e["note"] = ("wall clock around K GOPs: raw picture bytes H2D -> entropy stage on the GPU -> reconstruction kernels -> "
-                       "D2H of every frame to pinned host memory; HVQM4BatchSetEntropyMode(1)")
+                       "D2H of every frame to pinned host memory; HVQM4BatchSetEntropyMode(1)" +
+                       (f", HVQM4BatchSetHostShare({share})" if share else ""))
         if rank == 0:
             # the pinned buffer holds the last picture of every stream, as read back inside the timed region
             for i in check_ids:

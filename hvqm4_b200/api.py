@@ -82,6 +82,7 @@ SIGNATURES = {
     "HVQM4BatchDestroy": (None, [c_void_p]),
     "HVQM4BatchDecode": (c_int, [c_void_p, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_void_p), POINTER(c_uint32)]),
     "HVQM4BatchSetEntropyMode": (c_int, [c_void_p, c_int]),
+    "HVQM4BatchSetHostShare": (c_int, [c_void_p, c_int]),
     "HVQM4DevEntropyProfile": (None, [POINTER(c_uint64)]),
     "HVQM4BatchSync": (c_int, [c_void_p]),
     "HVQM4BatchReadFrame": (c_int, [c_void_p, c_int, c_void_p]),
@@ -319,7 +320,7 @@ class Batch:
     """n_streams independent streams of one geometry on one GPU (HVQM4Batch*)."""
 
     def __init__(self, n_streams: int, width: int, height: int, version: int = 15, device: int = -1, host_threads: int = 0,
-                 gpu_entropy: bool = False):
+                 gpu_entropy: bool = False, host_share: int = 0):
         self._h = lib().HVQM4BatchCreate(device, n_streams, width, height, version, host_threads)
         if not self._h:
             raise HVQM4Error(ERR_NO_DEVICE, "HVQM4BatchCreate failed (no CUDA device, or unsupported geometry)")
@@ -327,6 +328,10 @@ class Batch:
             rc = lib().HVQM4BatchSetEntropyMode(self._h, 1)
             if rc:
                 raise HVQM4Error(rc, "HVQM4BatchSetEntropyMode")
+            if host_share:      # streams [0, host_share) go through the host stage, next to the parse kernel
+                rc = lib().HVQM4BatchSetHostShare(self._h, host_share)
+                if rc:
+                    raise HVQM4Error(rc, "HVQM4BatchSetHostShare")
         self.n_streams = n_streams
         self.width, self.height = width, height
         self.frame_bytes = width * height * 3 // 2

@@ -236,6 +236,7 @@ struct HVQM4Batch
 
     /* GPU entropy stage (HVQM4BatchSetEntropyMode): per-stream parser state, blob arena, counters */
     bool gpu_entropy = false;
+    int host_share = 0;        /* GPU entropy mode: streams [0, host_share) are parsed by the host threads (HVQM4BatchSetHostShare) */
     uint8_t *d_estate = nullptr;
     size_t eslot = 0;
     uint8_t *d_blobs = nullptr;
@@ -548,9 +549,28 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
         }
     }
     const size_t head_bytes = pics_bytes + jobs_bytes + (gather ? gather_bytes : 0);
-    size_t total = head_bytes;
+    /* Pictures of the host's share of the streams (HVQM4BatchSetHostShare) go through the host stage of entropy.c on the
+       thread pool: their symbol buffers are built in the pinned arena, right behind the tables, and the parse kernel skips
+       them.  Phase A (sizes) comes first, like in the host-entropy step. */
+    const int share = b->host_share;
+    int n_host = 0;
+    for (int i = 0; i < n; ++i) n_host += stream_ids[i] < share;
+    if (n_host)
+        b->pool->parallel_for(n, [&](int i) {
+            if (stream_ids[i] < share) b->sizes[i] = h4e_parse_begin(b->st[stream_ids[i]].seq, frame_types[i], frames[i], frame_bytes[i]);
+        });
+    size_t total = align_up(head_bytes, 128);
     for (int i = 0; i < n; ++i)
     {
+        if (stream_ids[i] >= share) continue;
+        if (b->sizes[i] == 0) return HVQM4_ERR_GEOMETRY;
+        b->offs[i] = total;
+        total += align_up(b->sizes[i], 128);
+    }
+    const size_t upload_bytes = total;      /* what the host always uploads: tables + the host share's symbol buffers */
+    for (int i = 0; i < n; ++i)
+    {
+        if (stream_ids[i] < share) continue;
         /* the device copy keeps the source's alignment modulo 16 when the GPU gathers it */
         b->offs[i] = total + (gather ? (size_t)((uintptr_t)b->gather_src[i] & 15u) : 0);
         total += align_up((size_t)frame_bytes[i] + 16, 16) + (gather ? 16 : 0);
@@ -570,35 +590,43 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
     H4DevPicture *pics = reinterpret_cast<H4DevPicture *>(a.h);
     ReconJob *jobs = reinterpret_cast<ReconJob *>(a.h + pics_bytes);
     H4Gather *gd = reinterpret_cast<H4Gather *>(a.h + pics_bytes + jobs_bytes);
-    if (!gather)
+    std::atomic<uint32_t> host_err{0};
+    if (!gather || n_host)
         b->pool->parallel_for(n, [&](int i) {
             uint8_t *dst = a.h + b->offs[i];
-            memcpy(dst, frames[i], frame_bytes[i]);
-            memset(dst + frame_bytes[i], 0, 16);
+            if (stream_ids[i] < share)
+                host_err |= h4e_parse_finish(b->st[stream_ids[i]].seq, dst);      /* phase B: the symbol buffer itself */
+            else if (!gather)
+            {
+                memcpy(dst, frames[i], frame_bytes[i]);
+                memset(dst + frame_bytes[i], 0, 16);
+            }
         });
+    b->errors |= host_err.load();
     const auto t_w2 = std::chrono::steady_clock::now();
     for (int i = 0; i < n; ++i)
     {
+        const bool on_host = stream_ids[i] < share;
         if (gather)
-        {
+        {   /* a picture of the host's share: nothing to fetch */
             gd[i].src = b->gather_src[i];
             gd[i].dst_off = (uint32_t)b->offs[i];
-            gd[i].bytes = frame_bytes[i];
+            gd[i].bytes = on_host ? 0u : frame_bytes[i];
         }
         StreamState &s = b->st[stream_ids[i]];
         const int t = frame_types[i];
         pics[i].data = a.d + b->offs[i];
         pics[i].bytes = frame_bytes[i];
-        pics[i].pic_type = t;
+        pics[i].pic_type = on_host ? 0 : t;      /* 0: the parse kernel leaves the picture and its job alone */
         pics[i].stream = stream_ids[i];
         pics[i].pad = 0;
         if (t != SYM_PIC_B) std::swap(s.past, s.future);
-        jobs[i].blob = nullptr;
+        jobs[i].blob = on_host ? a.d + b->offs[i] : nullptr;
         jobs[i].present = b->surface(stream_ids[i], s.present);
         jobs[i].past = b->surface(stream_ids[i], s.past);
         jobs[i].future = b->surface(stream_ids[i], t == SYM_PIC_P ? s.present : s.future);
         jobs[i].rec_cta_begin = 0;
-        jobs[i].n_chunks = 0;
+        jobs[i].n_chunks = on_host ? h4e_last_chunks(s.seq) : 0;
         jobs[i].pad[0] = jobs[i].pad[1] = 0;
         s.last = s.present;
         if (t != SYM_PIC_B) std::swap(s.present, s.future);
@@ -641,7 +669,7 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
     /* from here on work is queued on the arena: it counts as in flight whatever happens next */
     a.in_flight = true;
     cudaEventRecord(a.consumed, sp);
-    if (!cuda_ok(cudaMemcpyAsync(a.d, a.h, gather ? head_bytes : total, cudaMemcpyHostToDevice, sp), "cudaMemcpyAsync(H2D)")) return HVQM4_ERR_CUDA;
+    if (!cuda_ok(cudaMemcpyAsync(a.d, a.h, gather ? upload_bytes : total, cudaMemcpyHostToDevice, sp), "cudaMemcpyAsync(H2D)")) return HVQM4_ERR_CUDA;
     if (gather)
     {
         const int grc = hvqm4_dev_gather(reinterpret_cast<const H4Gather *>(a.d + pics_bytes + jobs_bytes), n, a.d, sp);
@@ -749,6 +777,17 @@ H4_API int HVQM4BatchSetEntropyMode(HVQM4Batch *b, int gpu)
         }
     }
     b->gpu_entropy = true;
+    return HVQM4_OK;
+}
+
+/* GPU entropy mode: the pictures of streams [0, n_streams) are parsed by the host threads instead (the host stage of
+   entropy.c writes their symbol buffers into the step's pinned arena), next to the parse kernel that takes the rest */
+H4_API int HVQM4BatchSetHostShare(HVQM4Batch *b, int n_streams)
+{
+    if (!b || n_streams < 0 || n_streams > b->n_streams) return HVQM4_ERR_ARGUMENT;
+    /* a stream's maps and nest live with the stage that parsed its earlier pictures */
+    if (b->stats[0] > 0 && n_streams != b->host_share) return HVQM4_ERR_ARGUMENT;
+    b->host_share = n_streams;
     return HVQM4_OK;
 }
 

@@ -72,6 +72,7 @@ dev_parse_kernel(uint8_t *arena, size_t slot_bytes, const H4DevPicture *pics, in
     if (i >= n_pics) return;
     const int lane = threadIdx.x;
     const H4DevPicture pic = pics[i];
+    if (pic.pic_type == 0) return;     /* a picture of the host's share (api.cpp): its job is already complete */
     H4Seq *s = slot_seq(arena, slot_bytes, pic.stream * H4_PARSE_SLOTS + parity);
     const size_t bytes = h4e_parse_begin(s, pic.pic_type, pic.data, pic.bytes);
     uint32_t err = 0;
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(128)
 dev_gather_kernel(const H4Gather *__restrict__ descs, uint8_t *__restrict__ base)
 {
     const H4Gather d = descs[blockIdx.x];
+    if (d.bytes == 0) return;          /* nothing to fetch (a picture parsed by the host) */
     const uint8_t *src = d.src;
     uint8_t *dst = base + d.dst_off;
     const uint32_t head = min((16u - (uint32_t)((uintptr_t)src & 15u)) & 15u, d.bytes);

@@ -385,7 +385,13 @@ recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs, uint32_t cta_
 #ifndef HVQM4_BAND_WARPS
 #define HVQM4_BAND_WARPS 8
 #endif
-constexpr int kBandWarps = HVQM4_BAND_WARPS;
+constexpr int kBandWarps = HVQM4_BAND_WARPS;     /* plain band kernel: three or four CTAs of this many warps per SM */
+#ifndef HVQM4_BAND_TILE_WARPS
+#define HVQM4_BAND_TILE_WARPS 12
+#endif
+/* tile variant: two CTAs per SM (90 KB of shared memory each), so twelve warps per CTA give the SM the 24 warps the plain
+   kernel has (measured dense: 8 warps 1.09 M, 10 warps 1.16 M, 12 warps 1.23 M frames/s; plain kernel 1.20 M) */
+constexpr int kBandTileWarps = HVQM4_BAND_TILE_WARPS;
 constexpr int kTileMcbs = 128;
 constexpr int kBandRows = 8;   /* macroblock rows per CTA of the band kernel = kBandRows record bands of symbuf.h */
 static_assert(SYM_BAND_MCB_ROWS == kBandRows, "a CTA of the band kernel takes one record band of 8 rows, or 8 bands of one row");
@@ -445,7 +451,7 @@ __device__ __forceinline__ uint32_t block_ld(const uint8_t *base, uint32_t off)
    32 are classified); everything that costs instructions runs in the drains, where all lanes of
    a warp do the same thing, two queue entries per lane at a time so that twice as many
    reference rows are in flight. */
-template <bool kTile>
+template <bool kTile, int kWarps>
 __device__ __forceinline__ void band_map_tile(const ReconView &v, const BandOut &o, int row0, int row1, int mx0, int mx1, uint32_t *q, int cap)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -456,7 +462,7 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, const BandOut 
     /* classify: row tasks = 2 luma block rows per macroblock row, then the U rows, then the V rows */
     const int mrows = row1 - row0, n_tasks = mrows * 4;
 #pragma unroll 1
-    for (int task = warp; task < n_tasks; task += kBandWarps)
+    for (int task = warp; task < n_tasks; task += kWarps)
     {
         const int plane = task < 2 * mrows ? 0 : task < 3 * mrows ? 1 : 2;
         const int by = plane == 0 ? row0 * 2 + task : row0 + (task - (plane + 1) * mrows);
@@ -547,7 +553,7 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, const BandOut 
 /* one band of kRows macroblock rows of one picture: the whole CTA.  tile_off: shared-memory offset of the output tile (kTile) */
 /* stage_off / stage_cap: shared-memory area for the band's record data (0 bytes: nothing is staged); stage_phase: how often
    the CTA has used the staging barrier before (the walk kernel reuses it) */
-template <bool kTile, int kRows>
+template <bool kTile, int kRows, int kWarps>
 __device__ __forceinline__ bool band_item(const ReconJob *__restrict__ jobs, int job, int band, uint32_t *queue, int queue_cap, uint32_t tile_off,
                                           uint32_t stage_off, uint32_t stage_cap, uint32_t stage_phase)
 {
@@ -566,7 +572,7 @@ __device__ __forceinline__ bool band_item(const ReconJob *__restrict__ jobs, int
     const ReconView &v = vw;
     if (!v.blob) return false;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (v.has_nest) nest_stage_begin<kBandWarps * 32>(v, rc_smem + RC_SMEM_TABLE_BYTES);   /* lands during the map phase */
+    if (v.has_nest) nest_stage_begin<kWarps * 32>(v, rc_smem + RC_SMEM_TABLE_BYTES);   /* lands during the map phase */
 
     const int row0 = band * kRows, row1 = min(row0 + kRows, v.mcb_h);
     /* the chunks of a class are ordered by record band: bands of 8, 4 or 1 macroblock rows (h4e_set_band_rows; kRows is
@@ -574,7 +580,7 @@ __device__ __forceinline__ bool band_item(const ReconJob *__restrict__ jobs, int
     const int nb = (int)v.n_bands;
     const int rpb = nb == v.mcb_h ? 1 : nb == (v.mcb_h + 3) / 4 ? 4 : 8;
     const int b0 = row0 / rpb, b1 = min((row1 + rpb - 1) / rpb, nb);
-    if (warp == kBandWarps - 1)
+    if (warp == kWarps - 1)
     {   /* the last warp (it has the fewest block rows of the map phase when they do not divide) requests the band's record
            data: lane k < 3 looks up class k's chunk and record range (two dependent loads), lane 3 the vector rows */
         const uint32_t nb1 = v.n_bands + 1;
@@ -631,7 +637,7 @@ __device__ __forceinline__ bool band_item(const ReconJob *__restrict__ jobs, int
     /* map phase */
     const BandOut out = {tile_off, (uint32_t)((row1 - row0) * 8 * v.width), (uint32_t)((row1 - row0) * 4 * (v.width >> 1)), row0};
     for (int mx0 = 0; mx0 < v.mcb_w; mx0 += kTileMcbs)
-        band_map_tile<kTile>(v, out, row0, row1, mx0, min(mx0 + kTileMcbs, v.mcb_w), queue, queue_cap);
+        band_map_tile<kTile, kWarps>(v, out, row0, row1, mx0, min(mx0 + kTileMcbs, v.mcb_w), queue, queue_cap);
     /* record phase */
     if (v.has_nest) nest_stage_wait();
     __syncthreads();     /* map stores of the band and the staging pointers visible to the whole CTA */
@@ -647,15 +653,15 @@ __device__ __forceinline__ bool band_item(const ReconJob *__restrict__ jobs, int
     const uint32_t inter0 = st.c0[SYM_REC_INTER], inter1 = st.c1[SYM_REC_INTER];
     if (intra1 > intra0)
     {
-        nest_spread<kBandWarps * 32>(rc_smem + RC_SMEM_TABLE_BYTES, v.portrait != 0);
+        nest_spread<kWarps * 32>(rc_smem + RC_SMEM_TABLE_BYTES, v.portrait != 0);
         __syncthreads();     /* nest table complete */
     }
 #pragma unroll 1
-    for (uint32_t c = raw0 + warp; c < raw1; c += kBandWarps) record_chunk<kTile>(v, out, st, SYM_REC_RAW, c, lane);
+    for (uint32_t c = raw0 + warp; c < raw1; c += kWarps) record_chunk<kTile>(v, out, st, SYM_REC_RAW, c, lane);
 #pragma unroll 1
-    for (uint32_t c = intra0 + warp; c < intra1; c += kBandWarps) record_chunk<kTile>(v, out, st, SYM_REC_INTRA, c, lane);
+    for (uint32_t c = intra0 + warp; c < intra1; c += kWarps) record_chunk<kTile>(v, out, st, SYM_REC_INTRA, c, lane);
 #pragma unroll 1
-    for (uint32_t c = inter0 + warp; c < inter1; c += kBandWarps) record_chunk<kTile>(v, out, st, SYM_REC_INTER, c, lane);
+    for (uint32_t c = inter0 + warp; c < inter1; c += kWarps) record_chunk<kTile>(v, out, st, SYM_REC_INTER, c, lane);
     if (kTile)
     {   /* the band leaves as whole picture rows: three bulk stores (shared memory -> picture) */
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     /* this thread's tile writes -> visible to the copies */
@@ -670,7 +676,9 @@ __device__ __forceinline__ bool band_item(const ReconJob *__restrict__ jobs, int
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(pu), "r"(tile + out.ybytes), "r"(out.cbytes) : "memory");
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(pv), "r"(tile + out.ybytes + out.cbytes), "r"(out.cbytes) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    /* the CTA's shared memory is released when it exits */
+            /* the CTA's shared memory is released when it exits: the copies must have READ it by then (their writes to the
+               picture complete by the end of the kernel like any store) */
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
     }
     return true;
@@ -678,14 +686,15 @@ __device__ __forceinline__ bool band_item(const ReconJob *__restrict__ jobs, int
 
 /* one CTA per (picture, band) */
 template <int kMinBlocks, bool kTile, int kRows>
-__global__ void __launch_bounds__(kBandWarps * 32, kMinBlocks)
+__global__ void __launch_bounds__((kTile ? kBandTileWarps : kBandWarps) * 32, kMinBlocks)
 recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap, int stage_cap)
 {
+    constexpr int kWarps = kTile ? kBandTileWarps : kBandWarps;
     uint32_t *queue = reinterpret_cast<uint32_t *>(rc_smem + kBandQueueOff) + (threadIdx.x >> 5) * queue_cap;   /* the warp's own */
-    build_div_tables<kBandWarps * 32>();
+    build_div_tables<kWarps * 32>();
     const int job = blockIdx.x / n_bands;
-    const uint32_t stage_off = (uint32_t)((kBandQueueOff + kBandWarps * queue_cap * 4 + 127) & ~127);
-    band_item<kTile, kRows>(jobs, job, blockIdx.x - job * n_bands, queue, queue_cap, stage_off + (uint32_t)stage_cap, stage_off, (uint32_t)stage_cap, 0u);
+    const uint32_t stage_off = (uint32_t)((kBandQueueOff + kWarps * queue_cap * 4 + 127) & ~127);
+    band_item<kTile, kRows, kWarps>(jobs, job, blockIdx.x - job * n_bands, queue, queue_cap, stage_off + (uint32_t)stage_cap, stage_off, (uint32_t)stage_cap, 0u);
 }
 
 /* The fallback launch behind the sweep kernel (skip_handled = 1: pictures whose job says pad[0] = 1 are already
@@ -704,7 +713,7 @@ recon_band_walk_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue
         if (skip_handled == 1 && __ldg(&jobs[job].pad[0])) continue;
         if (skip_handled == 2 && !__ldg(&jobs[job].pad[1])) continue;
         __syncthreads();     /* the previous item is finished (view, tables, queues) */
-        phase += band_item<false, kBandRows>(jobs, job, item - job * n_bands, queue, queue_cap, 0u, 0u, 0u, phase) ? 1u : 0u;
+        phase += band_item<false, kBandRows, kBandWarps>(jobs, job, item - job * n_bands, queue, queue_cap, 0u, 0u, 0u, phase) ? 1u : 0u;
     }
 }
 
@@ -757,7 +766,7 @@ int launch_band_plain(const ReconJob *d_jobs, long long items, int n_bands, int 
         const cudaError_t e = cudaFuncSetAttribute(recon_band_kernel<kMinBlocks, kTile, kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
     }
-    recon_band_kernel<kMinBlocks, kTile, kRows><<<(unsigned)items, kBandWarps * 32, smem, stream>>>(d_jobs, n_bands, cap, stage);
+    recon_band_kernel<kMinBlocks, kTile, kRows><<<(unsigned)items, (kTile ? kBandTileWarps : kBandWarps) * 32, smem, stream>>>(d_jobs, n_bands, cap, stage);
     return (int)cudaGetLastError();
 }
 
@@ -778,11 +787,11 @@ static inline int band_stage_bytes(int mcb_w, int rows)
 
 /* bytes of the output tile of one band: `rows` macroblock rows of all three planes */
 static inline int band_tile_bytes(int mcb_w, int rows) { return rows * 8 * (mcb_w * 8) * 3 / 2; }
-static inline int band_plain_smem(int mcb_w, int rows)
+static inline int band_plain_smem(int mcb_w, int rows, int warps = kBandWarps)
 {
-    return ((kBandQueueOff + kBandWarps * band_queue_entries(mcb_w, rows) * 4 + 127) & ~127) + band_stage_bytes(mcb_w, rows);
+    return ((kBandQueueOff + warps * band_queue_entries(mcb_w, rows) * 4 + 127) & ~127) + band_stage_bytes(mcb_w, rows);
 }
-static inline int band_tile_smem(int mcb_w, int rows) { return band_plain_smem(mcb_w, rows) + band_tile_bytes(mcb_w, rows); }
+static inline int band_tile_smem(int mcb_w, int rows) { return band_plain_smem(mcb_w, rows, kBandTileWarps) + band_tile_bytes(mcb_w, rows); }
 
 /* tile = 0: blocks go straight into the picture, one CTA per band of 8 macroblock rows (n_bands of them per picture);
    tile = 8 / 4: the band (8 / 4 macroblock rows) is assembled in shared memory (two / four CTAs per SM) */
@@ -907,12 +916,14 @@ extern "C" int hvqm4_recon_band_rows(void)
    runs next to the parse kernels -- the smallest register footprint (end to end 96.4 k vs 94.4 k frames/s) */
 extern "C" int hvqm4_recon_launch_band(const ReconJob *d_jobs, int n_jobs, int mcb_w, int mcb_h, const void *slab, int band_rows, cudaStream_t stream)
 {
-    (void)band_rows;
     if (n_jobs <= 0) return 0;
     if (use_row(g_band_mode, n_jobs, mcb_w, mcb_h, slab)) return launch_row_then_band(d_jobs, n_jobs, mcb_w, mcb_h, slab, stream, nullptr);
     if (use_sweep(g_band_mode, n_jobs, mcb_w, mcb_h)) return launch_sweep_then_band(d_jobs, n_jobs, mcb_w, mcb_h, stream, nullptr);
     const int n_bands = (mcb_h + kBandRows - 1) / kBandRows;
-    const int rc = launch_band<4>(d_jobs, n_jobs, n_bands, mcb_w, stream);
+    /* HVQM4_BAND_BEHIND_PARSER=7: the tile variant here too (experiments; its CTAs hold 30 k registers each) */
+    static const int behind_env = getenv("HVQM4_BAND_BEHIND_PARSER") ? atoi(getenv("HVQM4_BAND_BEHIND_PARSER")) : 0;
+    const bool tile = (behind_env == 7 || g_band_mode == 7) && band_rows > 4 && band_tile_fits(mcb_w, 8, 2);
+    const int rc = tile ? launch_band<2>(d_jobs, n_jobs, n_bands, mcb_w, stream, 0, 8, mcb_h) : launch_band<4>(d_jobs, n_jobs, n_bands, mcb_w, stream);
     if (rc == 0) ++g_band_launches;
     return rc;
 }
@@ -970,10 +981,13 @@ extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w,
         const long long grid = (long long)n_jobs * n_bands;
         const long long waves4 = (grid + 4 * 148 - 1) / (4 * 148), waves3 = (grid + 3 * 148 - 1) / (3 * 148);
         const int per_sm = band_mode >= 2 && band_mode <= 4 ? band_mode : 1000 * waves4 <= 724 * waves3 ? 4 : 3;
-        /* HVQM4_BAND_TILE: 1 = the band assembled in shared memory (2 CTAs per SM) whenever it fits and no CTA count is
-           pinned, 0 = never; mode 7 forces it */
-        static const int tile_env = getenv("HVQM4_BAND_TILE") ? atoi(getenv("HVQM4_BAND_TILE")) : 0;
-        const bool want_tile = band_mode == 7 || ((band_mode == 0 || band_mode == 1) && tile_env == 1);
+        /* The band assembled in shared memory and written by bulk stores (two CTAs of twelve warps per SM) whenever it fits
+           and no CTA count is pinned: no global store requests, DRAM bytes -29 %, and faster than the plain kernel at every
+           grid size (profiles/r02_tile_grid_ab.txt, dense: 16 pictures 589 k vs 485 k frames/s, 32: 891 k vs 769 k,
+           256: 1.15 M vs 1.08 M, 1 024: 1.235 M vs 1.204 M).  HVQM4_BAND_TILE=0: never; mode 7 forces it, modes 2..4 pin
+           the plain kernel with that many CTAs per SM. */
+        static const int tile_env = getenv("HVQM4_BAND_TILE") ? atoi(getenv("HVQM4_BAND_TILE")) : 1;
+        const bool want_tile = band_mode == 7 || ((band_mode == 0 || band_mode == 1) && tile_env != 0);
         /* a CTA's rows are a multiple of the streams' record band: 4-row tiles (four CTAs per SM) for streams with bands
            of 4 or 1 rows, else 8-row tiles (two CTAs per SM) */
         const int tile = !want_tile ? 0 : (band_rows <= 4 && band_tile_fits(mcb_w, 4, 4)) ? 4 : (band_tile_fits(mcb_w, 8, 2) ? 8 : 0);

@@ -164,6 +164,17 @@ int HVQM4BatchDecode(HVQM4Batch *b, int n, const int32_t *stream_ids, const int3
  */
 int HVQM4BatchSetEntropyMode(HVQM4Batch *b, int gpu);
 
+/*
+ * Extension of the mode above (it has no effect on the host stage): the pictures of streams 0 .. n_streams - 1 are parsed
+ * by the batch's host threads -- the host stage of the same parser, writing their symbol buffers into the step's pinned
+ * staging arena -- while the parse kernel takes the other streams of the step.  Both stages then feed ONE reconstruction
+ * launch.  The GPU stage is the slower of the two stages of a dense end-to-end step and the host
+ * cores are otherwise idle in this mode: a share of about one picture in eight per 16 host threads moves the step to the
+ * PCIe bound.  Like the mode itself the share is fixed with the first picture (a stream's maps and nest live with the
+ * stage that parsed its earlier pictures): a different value afterwards returns HVQM4_ERR_ARGUMENT.  Default 0.
+ */
+int HVQM4BatchSetHostShare(HVQM4Batch *b, int n_streams);
+
 /* Diagnostics: SM cycles the GPU bitstream stage spent per phase since the last call, summed over
    pictures: header+trees, pass 1 (maps), record planning, pass 2 (scheduling), map copies, flat
    section decode, record fill, unused. */

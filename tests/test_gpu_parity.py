@@ -456,13 +456,15 @@ def test_rgb_of_decoded_frames_sdk_and_batch(native_lib, oracle):
             batch.close()
 
 
-@pytest.mark.parametrize("gpu_entropy", [False, True])
-def test_pipelined_steps_with_async_readback_match_oracle(native_lib, oracle, gpu_entropy):
+@pytest.mark.parametrize("gpu_entropy,host_share", [(False, 0), (True, 0), (True, 20)])
+def test_pipelined_steps_with_async_readback_match_oracle(native_lib, oracle, gpu_entropy, host_share):
     """The way bench.py's end-to-end arm drives the batch runtime: every step of a GOP submitted
     back to back, each followed by an asynchronous read-back of all frames into its own pinned
     buffer, one sync at the end.  Uploads, entropy stage, reconstruction and read-backs of
     neighbouring steps overlap (staging ring, alternating parser slots, spare B surface), so every
-    frame of every step is compared with the oracle: a missing dependency shows up as a torn frame."""
+    frame of every step is compared with the oracle: a missing dependency shows up as a torn frame.
+    host_share: the first streams of the batch are parsed by the host threads next to the parse kernel
+    (HVQM4BatchSetHostShare), both stages feed the same reconstruction launch."""
     S, distinct, gop = 96, 3, "IPBBPBBPBB"
     files = [synth.generate(640, 480, 15, gop, 1, seed=8300 + i, profile=i & 1) for i in range(distinct)]
     want = [[md5(yuv) for _, _, _, yuv in oracle.PortDecoder(f).frames()] for f in files]
@@ -470,7 +472,7 @@ def test_pipelined_steps_with_async_readback_match_oracle(native_lib, oracle, gp
     bufs = [ctypes.create_string_buffer(f, len(f) + 8) for f in files]
     bases = [ctypes.addressof(b) for b in bufs]
     n_steps = len(parsed[0][1])
-    batch = native_lib.Batch(S, 640, 480, 15, gpu_entropy=gpu_entropy)
+    batch = native_lib.Batch(S, 640, 480, 15, gpu_entropy=gpu_entropy, host_share=host_share)
     fb = batch.frame_bytes
     pinned = native_lib.lib().HVQM4HostAlloc(n_steps * S * fb)
     assert pinned
@@ -563,8 +565,8 @@ def test_file_player_matches_the_reference_program(native_lib, oracle):
         player.close()
 
 
-@pytest.mark.parametrize("gpu_entropy", [False, True])
-def test_staggered_streams_and_partial_steps_match_oracle(native_lib, oracle, gpu_entropy):
+@pytest.mark.parametrize("gpu_entropy,host_share", [(False, 0), (True, 0), (True, 7), (True, 24)])
+def test_staggered_streams_and_partial_steps_match_oracle(native_lib, oracle, gpu_entropy, host_share):
     """Streams that are out of phase with each other (stream i joins at step i % 4 and sits out every
     step where (step + i) % 5 == 0): every step mixes I, P and B pictures and addresses a different
     subset of the batch, read-backs are asynchronous, nothing is synchronised until the end.  The
@@ -576,7 +578,7 @@ def test_staggered_streams_and_partial_steps_match_oracle(native_lib, oracle, gp
     parsed = [native_lib.parse_file(f)[1] for f in files]
     bufs = [ctypes.create_string_buffer(f, len(f) + 8) for f in files]
     bases = [ctypes.addressof(b) for b in bufs]
-    batch = native_lib.Batch(n, 320, 240, 15, gpu_entropy=gpu_entropy)
+    batch = native_lib.Batch(n, 320, 240, 15, gpu_entropy=gpu_entropy, host_share=host_share)
     fb = batch.frame_bytes
     total_frames = sum(len(p) for p in parsed)
     pinned = native_lib.lib().HVQM4HostAlloc(total_frames * fb)
@@ -660,6 +662,9 @@ def test_entropy_mode_switch_after_the_first_picture_is_refused(native_lib, gold
         batch.sync()
         assert lib.HVQM4BatchSetEntropyMode(batch._h, 1) != 0
         assert lib.HVQM4BatchSetEntropyMode(batch._h, 0) == 0
+        assert lib.HVQM4BatchSetHostShare(batch._h, 1) != 0       # the share is fixed with the first picture as well
+        assert lib.HVQM4BatchSetHostShare(batch._h, 0) == 0
+        assert lib.HVQM4BatchSetHostShare(batch._h, 2) != 0       # more streams than the batch has
         for k, fr in enumerate(frames[1:], 1):
             batch.decode([0], [fr.frame_type], [ctypes.addressof(buf) + fr.offset], [fr.bytes])
             batch.sync()
@@ -690,7 +695,8 @@ def test_unregister_waits_for_pictures_still_being_fetched(native_lib, oracle):
         batch.close()
 
 
-def test_registered_host_memory_is_gathered_by_the_gpu(native_lib, oracle):
+@pytest.mark.parametrize("host_share", [0, 5])
+def test_registered_host_memory_is_gathered_by_the_gpu(native_lib, oracle, host_share):
     """HVQM4HostRegister: with the bitstreams in page-locked, mapped application memory the GPU entropy mode
     fetches the pictures itself (dev_gather_kernel) -- same frames as the oracle, every source alignment
     modulo 16 occurs (the pictures sit at arbitrary offsets inside the file images), and a step that mixes
@@ -713,7 +719,7 @@ def test_registered_host_memory_is_gathered_by_the_gpu(native_lib, oracle):
     lib = native_lib.lib()
     for i, f in enumerate(files):
         assert lib.HVQM4HostRegister(base + offs[i], len(f)) == 0
-    batch = native_lib.Batch(n, 320, 240, 15, gpu_entropy=True)
+    batch = native_lib.Batch(n, 320, 240, 15, gpu_entropy=True, host_share=host_share)
     try:
         assert {(base + offs[i] + parsed[i][k].offset) & 15 for i in range(n) for k in range(len(gop))} == set(range(16))
         launches0 = native_lib.kernel_launches()

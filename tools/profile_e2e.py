@@ -1,5 +1,5 @@
 """End-to-end timing experiments: entropy stage (host or GPU) + H2D + kernels (+ optional D2H).
-    python tools/profile_e2e.py [S] [threads] [d2h 0|1] [profile] [gops] [gpu_entropy 0|1]"""
+    python tools/profile_e2e.py [S] [threads] [d2h 0|1] [profile] [gops] [gpu_entropy 0|1] [host_share streams]"""
 import ctypes
 import os
 import sys
@@ -15,6 +15,7 @@ D2H = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 PROFILE = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 GOPS = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 GPU_ENTROPY = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+SHARE = int(sys.argv[7]) if len(sys.argv) > 7 else 0
 GOP = "I" + "PBB" * 5
 distinct = min(S, 64)
 files = [synth.generate(640, 480, 15, GOP, 1, seed=5000 + i, profile=PROFILE) for i in range(distinct)]
@@ -24,7 +25,7 @@ bases = [ctypes.addressof(b) for b in bufs]
 if os.environ.get('E2E_REGISTER'):
     for b in bufs:
         assert api.lib().HVQM4HostRegister(ctypes.addressof(b), len(b)) == 0
-batch = api.Batch(S, 640, 480, 15, host_threads=T, gpu_entropy=bool(GPU_ENTROPY))
+batch = api.Batch(S, 640, 480, 15, host_threads=T, gpu_entropy=bool(GPU_ENTROPY), host_share=SHARE)
 ids = list(range(S))
 steps = []
 for k in range(len(parsed[0][1])):
@@ -51,7 +52,7 @@ batch.sync()
 t1 = time.perf_counter()
 h1 = batch.stats()["host_ns"]
 n = S * 16 * GOPS
-print(f"gpu_entropy={GPU_ENTROPY} S={S} threads={T or os.cpu_count()} d2h={D2H} profile={PROFILE}: {n / (t1 - t0):.0f} fps e2e; "
+print(f"gpu_entropy={GPU_ENTROPY} share={SHARE} S={S} threads={T or os.cpu_count()} d2h={D2H} profile={PROFILE}: {n / (t1 - t0):.0f} fps e2e; "
       f"host stage alone {(h1 - h0) / 1e9:.3f} s of {t1 - t0:.3f} s wall -> {n / ((h1 - h0) / 1e9):.0f} fps if host-only")
 if GPU_ENTROPY:
     prof = (ctypes.c_uint64 * 8)()
