@@ -280,15 +280,16 @@ def main():
     ap.add_argument("--streams-per-gpu", type=int, default=1024, help="streams per GPU (weak scaling) or in all (strong scaling)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--gather", default="auto", choices=["auto", "on", "off"],
-                    help="end to end: bitstreams fetched by the GPU from registered host memory (auto: from 4 ranks per box on)")
+                    help="end to end: bitstreams fetched by the GPU from registered host memory (auto: from 2 ranks per box on)")
     ap.add_argument("--profile", type=int, default=0, help="0 dense (headline), 1 realistic")
     ap.add_argument("--host-threads", type=int, default=0)
     ap.add_argument("--host-share", type=int, default=-1,
                     help="end to end, GPU entropy stage: streams per GPU whose pictures the host threads parse next to the parse kernel "
-                         "(HVQM4BatchSetHostShare); -1 = one stream in eight per 16 host threads at one or two ranks, none beyond")
+                         "(HVQM4BatchSetHostShare); -1 = one stream in eight per 16 host threads at one rank, none beyond")
     ap.add_argument("--ref-seconds", type=float, default=12.0, help="CPU seconds per process for the reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-host", action="store_true", help="skip the host-entropy end-to-end leg (experiments)")
     ap.add_argument("--no-realistic", action="store_true", help="skip the secondary realistic-profile measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -347,7 +348,9 @@ def main():
     bases = [ctypes.addressof(b) for b in bufs]
     # --gather: the bitstreams are page-locked and mapped (HVQM4HostRegister), the GPU entropy stage fetches the pictures
     # itself instead of the host threads copying them into the pinned staging arena (include/hvqm4.h)
-    gather = args.gather == "on" or (args.gather == "auto" and world >= 4)
+    # measured (profiles/r02_n2_ab.txt, r02_share_gather_ab.txt): one rank with 16 cores 105 k frames/s with host copies, 98-102 k
+    # with the gather; two ranks with 12 cores each 180 k vs 198 k; eight ranks with 4 cores each 151 k vs 185 k
+    gather = args.gather == "on" or (args.gather == "auto" and world >= 2)
     if gather:
         for b, f in zip(bufs, files):
             if api.lib().HVQM4HostRegister(ctypes.addressof(b), len(f)) != 0:
@@ -490,15 +493,17 @@ def main():
                     "ms_per_step": 1e3 * sec / k, "steps": k, "entropy_stage": what}
 
         # (a) the layout BASELINE.json's north_star describes: entropy stage on host threads
-        e2e_host = measure_e2e(batch, 12.0, "host threads")
-        e2e_host["host_threads_per_gpu"] = threads
-        e2e_host["note"] = ("wall clock around K GOPs: host entropy threads -> pinned symbol arena -> H2D -> kernels -> "
-                            "D2H of every frame to pinned host memory")
+        if not args.no_e2e_host:
+            e2e_host = measure_e2e(batch, 12.0, "host threads")
+            e2e_host["host_threads_per_gpu"] = threads
+            e2e_host["note"] = ("wall clock around K GOPs: host entropy threads -> pinned symbol arena -> H2D -> kernels -> "
+                                "D2H of every frame to pinned host memory")
         # (b) the same C source compiled as device code (entropy_dev.cu): raw pictures up, frames down
         # the host cores are idle in this mode: they parse a share of the streams next to the parse kernel (measured on one
         # B200 + 16 cores, profiles/r02_host_share_ab.txt: 106 k frames/s with no share, 110-111 k with 64..160 of 1 024 streams,
-        # 104 k with 192, 87 k with 256).  With four ranks or more the node's PCIe, not the parser, is the limit: no share.
-        share = args.host_share if args.host_share >= 0 else (S * threads // 128 if world <= 2 else 0)
+        # 104 k with 192, 87 k with 256).  With several ranks per box the host cores are fewer per GPU and the bitstreams are
+        # fetched by the GPU (--gather): two ranks with 12 cores each 198 k with no share, 197 k with 96 streams: no share.
+        share = args.host_share if args.host_share >= 0 else (S * threads // 128 if world == 1 else 0)
         share = max(0, min(S, share))
         gb = api.Batch(S, W, H, 15, device=local, host_threads=threads, gpu_entropy=True, host_share=share)
         e2e = measure_e2e(gb, 12.0, "gpu (one warp per picture)" + (f" + host threads for {share} of {S} streams" if share else ""))

@@ -269,9 +269,27 @@ recon_map_kernel(const ReconJob *__restrict__ jobs, int units_per_pic, int ctas_
  * ------------------------------------------------------------------------------------------ */
 constexpr int kRecWarps = 8;
 constexpr int kRecSmem = RC_SMEM_TABLE_BYTES + SYM_NEST_H * 40 + 32;
-/* band kernels: [tables + view | nest staging scratch | BandStage | queues | staged record data | output tile (kTile)] */
+/* band kernels: [tables + view | nest staging scratch | BandStage | queues that do not fit over the nest table | staged record
+   data | output tile (kTile)] */
 constexpr int kBandStageOff = (kRecSmem + 15) & ~15;
 constexpr int kBandQueueOff = kBandStageOff + 128;
+/* The warps' queues (16-bit entries, band_map_tile) live where the NEST TABLE will be: the table is spread only after the map
+   phase, when the queues are dead (band_item); the warps whose queues do not fit there follow the BandStage.  Shared memory
+   is L1 the gathers do not get: with 32-bit entries behind the tables the tile variant needed 96 KB per CTA -- two CTAs =
+   the 196 KB carve-out, 60 KB of L1 -- now 75 KB, the 164 KB carve-out and 92 KB of L1 (profiles/r02_carve_ab.txt: the
+   plain kernel loses 3 % from 124 to 92 KB of L1, 11 % more from 92 to 60 KB, 40 % more from 60 to 28 KB). */
+constexpr int kBandQueueAlias = RC_SMEM_MCDIV_OFF - RC_SMEM_NEST_OFF;
+__device__ __forceinline__ uint16_t *band_queue(int warp, int cap)
+{
+    const int per = cap * 2, n_alias = kBandQueueAlias / per;
+    return reinterpret_cast<uint16_t *>(rc_smem + (warp < n_alias ? RC_SMEM_NEST_OFF + warp * per : kBandQueueOff + (warp - n_alias) * per));
+}
+/* bytes behind kBandQueueOff for the queues of `warps` warps of `cap` entries */
+__host__ __device__ constexpr int band_queue_extra_dev(int warps, int cap)
+{
+    return warps > kBandQueueAlias / (cap * 2) ? (warps - kBandQueueAlias / (cap * 2)) * cap * 2 : 0;
+}
+static inline int band_queue_extra(int warps, int cap) { return band_queue_extra_dev(warps, cap); }
 
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kRecWarps * 32, kMinBlocks)
@@ -392,6 +410,8 @@ constexpr int kBandWarps = HVQM4_BAND_WARPS;     /* plain band kernel: three or 
 /* tile variant: two CTAs per SM (90 KB of shared memory each), so twelve warps per CTA give the SM the 24 warps the plain
    kernel has (measured dense: 8 warps 1.09 M, 10 warps 1.16 M, 12 warps 1.23 M frames/s; plain kernel 1.20 M) */
 constexpr int kBandTileWarps = HVQM4_BAND_TILE_WARPS;
+/* warps per CTA of a band kernel instantiation: twelve for the 8-row tile variant (two CTAs per SM), eight otherwise */
+__host__ __device__ constexpr int band_warps(bool tile, int rows) { return tile && rows == 8 ? kBandTileWarps : kBandWarps; }
 constexpr int kTileMcbs = 128;
 constexpr int kBandRows = 8;   /* macroblock rows per CTA of the band kernel = kBandRows record bands of symbuf.h */
 static_assert(SYM_BAND_MCB_ROWS == kBandRows, "a CTA of the band kernel takes one record band of 8 rows, or 8 bands of one row");
@@ -452,17 +472,20 @@ __device__ __forceinline__ uint32_t block_ld(const uint8_t *base, uint32_t off)
    a warp do the same thing, two queue entries per lane at a time so that twice as many
    reference rows are in flight. */
 template <bool kTile, int kWarps>
-__device__ __forceinline__ void band_map_tile(const ReconView &v, const BandOut &o, int row0, int row1, int mx0, int mx1, uint32_t *q, int cap)
+__device__ __forceinline__ void band_map_tile(const ReconView &v, const BandOut &o, int row0, int row1, int mx0, int mx1, uint16_t *q, int cap)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     const bool ipic = v.is_ipic != 0;
     uint8_t *const pic = v.present;
     uint32_t n_w = 0, n_mc = 0;
-    /* classify: row tasks = 2 luma block rows per macroblock row, then the U rows, then the V rows */
+    /* classify: row tasks = 2 luma block rows per macroblock row, then the U rows, then the V rows.
+       Queue entry (16 bits): [7:0] block x inside the column tile, [9:8] which of the warp's tasks, [10] the reference is
+       the future picture -- everything else a drain needs follows from the task */
     const int mrows = row1 - row0, n_tasks = mrows * 4;
+    uint32_t slot = 0;
 #pragma unroll 1
-    for (int task = warp; task < n_tasks; task += kWarps)
+    for (int task = warp; task < n_tasks; task += kWarps, slot += 1u << 8)
     {
         const int plane = task < 2 * mrows ? 0 : task < 3 * mrows ? 1 : 2;
         const int by = plane == 0 ? row0 * 2 + task : row0 + (task - (plane + 1) * mrows);
@@ -473,7 +496,6 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, const BandOut 
         const uint8_t *drow = v.blob + (rc_pick3(v.off_dc, plane) + (by + 1) * bstride + 1);
         int pw2;
         const uint32_t dst_row = block_off<kTile>(v, o, plane, 0, by, pw2);
-        const uint32_t entry_row = sym_record_header(0, plane, 0, by);
         /* lanes past the row end get type 6 (raw: nothing to do here) */
         int bx = x0 + lane;
         uint32_t t = 6u, dc = 0u;
@@ -496,10 +518,10 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, const BandOut 
             const uint32_t nib = ipic ? t : (t & 0xF);
             const bool is_w = !inter && nib == 0;
             const bool is_mc = inter && ((t & 0x10) || nib != 6);
-            const uint32_t entry = entry_row + ((uint32_t)bx << 10) + t;
+            const uint32_t entry = slot + (uint32_t)(bx - x0) + ((t & 0x40) << 4);
             const uint32_t m_w = __ballot_sync(0xFFFFFFFFu, is_w), m_mc = __ballot_sync(0xFFFFFFFFu, is_mc);
-            if (is_w) q[n_w + __popc(m_w & lt)] = entry;
-            if (is_mc) q[cap - 1 - (int)(n_mc + __popc(m_mc & lt))] = entry;
+            if (is_w) q[n_w + __popc(m_w & lt)] = (uint16_t)entry;
+            if (is_mc) q[cap - 1 - (int)(n_mc + __popc(m_mc & lt))] = (uint16_t)entry;
             n_w += __popc(m_w);
             n_mc += __popc(m_mc);
             if (!inter && nib == 8)
@@ -513,27 +535,35 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, const BandOut 
         }
     }
     __syncwarp();
+    /* entry -> plane, block coordinates, and the one type bit motion compensation looks at (past / future) */
+    auto coords = [&](uint32_t e, uint32_t &t, int &plane, int &bx, int &by) {
+        const int task = warp + (int)((e >> 8) & 3u) * kWarps;
+        plane = task < 2 * mrows ? 0 : task < 3 * mrows ? 1 : 2;
+        by = plane == 0 ? row0 * 2 + task : row0 + (task - (plane + 1) * mrows);
+        bx = (int)(e & 0xFFu) + (plane ? mx0 : mx0 << 1);
+        t = (e & 0x400u) ? 0x40u : 0x20u;
+    };
 #pragma unroll 1
     for (uint32_t i = lane; i < n_w; i += 32)
     {
         uint32_t t, rows[4];
         int plane, bx, by, pw;
-        rc_record_coords(q[i], t, plane, bx, by);
+        coords(q[i], t, plane, bx, by);
         rc_weighted_block(v, plane, bx, by, rows);
         const uint32_t dst = block_off<kTile>(v, o, plane, bx, by, pw);
 #pragma unroll
         for (int r = 0; r < 4; ++r) block_st<kTile>(pic, dst + r * pw, rows[r]);
     }
     /* motion compensation: two entries per lane and round */
-    const uint32_t *q_mc = q + cap - 1;
+    const uint16_t *q_mc = q + cap - 1;
 #pragma unroll 1
     for (uint32_t i = lane; i < n_mc; i += 64)
     {
         const bool two = i + 32 < n_mc;
         uint32_t t0, t1, rows0[4], rows1[4];
         int plane0, bx0, by0, plane1, bx1, by1, pw0, pw1;
-        rc_record_coords(q_mc[-(int)i], t0, plane0, bx0, by0);
-        rc_record_coords(q_mc[-(int)(two ? i + 32 : i)], t1, plane1, bx1, by1);
+        coords(q_mc[-(int)i], t0, plane0, bx0, by0);
+        coords(q_mc[-(int)(two ? i + 32 : i)], t1, plane1, bx1, by1);
         const uint32_t mv0 = rc_mv_word(v, plane0, bx0, by0), mv1 = rc_mv_word(v, plane1, bx1, by1);
         const uint32_t mp0 = rc_motion_pack(v, plane0, bx0, by0, t0, mv0), mp1 = rc_motion_pack(v, plane1, bx1, by1, t1, mv1);
         rc_mc_packed2(v, plane0, mp0, rows0, plane1, mp1, rows1);
@@ -554,7 +584,7 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, const BandOut 
 /* stage_off / stage_cap: shared-memory area for the band's record data (0 bytes: nothing is staged); stage_phase: how often
    the CTA has used the staging barrier before (the walk kernel reuses it) */
 template <bool kTile, int kRows, int kWarps>
-__device__ __forceinline__ bool band_item(const ReconJob *__restrict__ jobs, int job, int band, uint32_t *queue, int queue_cap, uint32_t tile_off,
+__device__ __forceinline__ bool band_item(const ReconJob *__restrict__ jobs, int job, int band, uint16_t *queue, int queue_cap, uint32_t tile_off,
                                           uint32_t stage_off, uint32_t stage_cap, uint32_t stage_phase)
 {
     ReconView &vw = *reinterpret_cast<ReconView *>(rc_smem + RC_SMEM_VIEW_OFF);
@@ -686,14 +716,14 @@ __device__ __forceinline__ bool band_item(const ReconJob *__restrict__ jobs, int
 
 /* one CTA per (picture, band) */
 template <int kMinBlocks, bool kTile, int kRows>
-__global__ void __launch_bounds__((kTile ? kBandTileWarps : kBandWarps) * 32, kMinBlocks)
+__global__ void __launch_bounds__(band_warps(kTile, kRows) * 32, kMinBlocks)
 recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap, int stage_cap)
 {
-    constexpr int kWarps = kTile ? kBandTileWarps : kBandWarps;
-    uint32_t *queue = reinterpret_cast<uint32_t *>(rc_smem + kBandQueueOff) + (threadIdx.x >> 5) * queue_cap;   /* the warp's own */
+    constexpr int kWarps = band_warps(kTile, kRows);
+    uint16_t *queue = band_queue(threadIdx.x >> 5, queue_cap);   /* the warp's own */
     build_div_tables<kWarps * 32>();
     const int job = blockIdx.x / n_bands;
-    const uint32_t stage_off = (uint32_t)((kBandQueueOff + kWarps * queue_cap * 4 + 127) & ~127);
+    const uint32_t stage_off = (uint32_t)((kBandQueueOff + band_queue_extra_dev(kWarps, queue_cap) + 127) & ~127);
     band_item<kTile, kRows, kWarps>(jobs, job, blockIdx.x - job * n_bands, queue, queue_cap, stage_off + (uint32_t)stage_cap, stage_off, (uint32_t)stage_cap, 0u);
 }
 
@@ -703,7 +733,7 @@ recon_band_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap,
 __global__ void __launch_bounds__(kBandWarps * 32, 2)
 recon_band_walk_kernel(const ReconJob *__restrict__ jobs, int n_bands, int queue_cap, int n_items, int skip_handled)
 {
-    uint32_t *queue = reinterpret_cast<uint32_t *>(rc_smem + kBandQueueOff) + (threadIdx.x >> 5) * queue_cap;
+    uint16_t *queue = band_queue(threadIdx.x >> 5, queue_cap);
     build_div_tables<kBandWarps * 32>();
     uint32_t phase = 0;      /* uses of the staging barrier so far (nothing is staged here: the record data is read in place) */
 #pragma unroll 1
@@ -766,7 +796,11 @@ int launch_band_plain(const ReconJob *d_jobs, long long items, int n_bands, int 
         const cudaError_t e = cudaFuncSetAttribute(recon_band_kernel<kMinBlocks, kTile, kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
     }
-    recon_band_kernel<kMinBlocks, kTile, kRows><<<(unsigned)items, (kTile ? kBandTileWarps : kBandWarps) * 32, smem, stream>>>(d_jobs, n_bands, cap, stage);
+    {   /* HVQM4_BAND_CARVEOUT=<percent of the SM's shared memory>: pins the L1 / shared memory split (experiments) */
+        static const int carve = getenv("HVQM4_BAND_CARVEOUT") ? atoi(getenv("HVQM4_BAND_CARVEOUT")) : -1;
+        if (carve >= 0) cudaFuncSetAttribute(recon_band_kernel<kMinBlocks, kTile, kRows>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    }
+    recon_band_kernel<kMinBlocks, kTile, kRows><<<(unsigned)items, band_warps(kTile, kRows) * 32, smem, stream>>>(d_jobs, n_bands, cap, stage);
     return (int)cudaGetLastError();
 }
 
@@ -789,9 +823,9 @@ static inline int band_stage_bytes(int mcb_w, int rows)
 static inline int band_tile_bytes(int mcb_w, int rows) { return rows * 8 * (mcb_w * 8) * 3 / 2; }
 static inline int band_plain_smem(int mcb_w, int rows, int warps = kBandWarps)
 {
-    return ((kBandQueueOff + warps * band_queue_entries(mcb_w, rows) * 4 + 127) & ~127) + band_stage_bytes(mcb_w, rows);
+    return ((kBandQueueOff + band_queue_extra(warps, band_queue_entries(mcb_w, rows)) + 127) & ~127) + band_stage_bytes(mcb_w, rows);
 }
-static inline int band_tile_smem(int mcb_w, int rows) { return band_plain_smem(mcb_w, rows, kBandTileWarps) + band_tile_bytes(mcb_w, rows); }
+static inline int band_tile_smem(int mcb_w, int rows) { return band_plain_smem(mcb_w, rows, band_warps(true, rows)) + band_tile_bytes(mcb_w, rows); }
 
 /* tile = 0: blocks go straight into the picture, one CTA per band of 8 macroblock rows (n_bands of them per picture);
    tile = 8 / 4: the band (8 / 4 macroblock rows) is assembled in shared memory (two / four CTAs per SM) */
@@ -801,7 +835,7 @@ int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, int mcb_w, cuda
     long long items = (long long)n_jobs * n_bands;
     if (items > 0x7FFFFFFFll) return (int)cudaErrorInvalidConfiguration;
     const int cap = band_queue_entries(mcb_w);
-    const int smem = kBandQueueOff + kBandWarps * cap * 4;
+    const int smem = kBandQueueOff + band_queue_extra(kBandWarps, cap);
     if (skip_handled)
     {
         const long long grid = items > 148 * 2 ? 148 * 2 : items;
@@ -988,9 +1022,9 @@ extern "C" int hvqm4_recon_launch(const ReconJob *d_jobs, int n_jobs, int mcb_w,
            the plain kernel with that many CTAs per SM. */
         static const int tile_env = getenv("HVQM4_BAND_TILE") ? atoi(getenv("HVQM4_BAND_TILE")) : 1;
         const bool want_tile = band_mode == 7 || ((band_mode == 0 || band_mode == 1) && tile_env != 0);
-        /* a CTA's rows are a multiple of the streams' record band: 4-row tiles (four CTAs per SM) for streams with bands
-           of 4 or 1 rows, else 8-row tiles (two CTAs per SM) */
-        const int tile = !want_tile ? 0 : (band_rows <= 4 && band_tile_fits(mcb_w, 4, 4)) ? 4 : (band_tile_fits(mcb_w, 8, 2) ? 8 : 0);
+        /* a CTA's rows are a multiple of the streams' record band: 8-row tiles (two CTAs per SM); mode 7 on streams with
+           bands of 4 or 1 rows takes 4-row tiles (four CTAs per SM: measured slower, kept as a tested alternative) */
+        const int tile = !want_tile ? 0 : (band_mode == 7 && band_rows <= 4 && band_tile_fits(mcb_w, 4, 4)) ? 4 : (band_tile_fits(mcb_w, 8, 2) ? 8 : 0);
         int rc;
         switch (tile ? 0 : per_sm)
         {
