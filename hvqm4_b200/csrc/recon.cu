@@ -405,10 +405,13 @@ recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs, uint32_t cta_
 #endif
 constexpr int kBandWarps = HVQM4_BAND_WARPS;     /* plain band kernel: three or four CTAs of this many warps per SM */
 #ifndef HVQM4_BAND_TILE_WARPS
-#define HVQM4_BAND_TILE_WARPS 12
+#define HVQM4_BAND_TILE_WARPS 16
 #endif
-/* tile variant: two CTAs per SM (90 KB of shared memory each), so twelve warps per CTA give the SM the 24 warps the plain
-   kernel has (measured dense: 8 warps 1.09 M, 10 warps 1.16 M, 12 warps 1.23 M frames/s; plain kernel 1.20 M) */
+/* tile variant: two CTAs per SM by shared memory (75 KB + queues each), so sixteen warps per CTA at 64 registers (no spills)
+   give the SM 32 warps where the plain kernel has 24, and the 32 row tasks of a band are two per warp.  Measured dense
+   (profiles/r02_tile_warps2_ab.txt, after the queues moved over the nest table): 12 warps 1.307 M, 13 1.298 M, 14 1.305 M,
+   16 warps 1.360 M frames/s (128 pictures: 1.08 -> 1.14 M); before that, at 96+ KB per CTA: 8 warps 1.09 M, 10 1.16 M,
+   12 1.23 M, 14 and 16 one CTA per SM.  Plain kernel 1.20-1.22 M. */
 constexpr int kBandTileWarps = HVQM4_BAND_TILE_WARPS;
 /* warps per CTA of a band kernel instantiation: twelve for the 8-row tile variant (two CTAs per SM), eight otherwise */
 __host__ __device__ constexpr int band_warps(bool tile, int rows) { return tile && rows == 8 ? kBandTileWarps : kBandWarps; }
