@@ -162,7 +162,8 @@ template <bool kTile> __device__ __forceinline__ uint32_t block_ld(const uint8_t
 struct BandStage
 {
     unsigned long long bar;
-    uint32_t pad0[2];
+    int next;                                 /* record phase: chunks of the band not yet taken by a warp (counts down) */
+    uint32_t pad0;
     const uint2 *desc[SYM_REC_CLASSES];       /* descriptor of chunk c of class k: desc[k][c - c0[k]] */
     const uint32_t *rec[SYM_REC_CLASSES];     /* record word w (counted from the picture's first record word): rec[k][w] */
     const uint32_t *mv;                       /* vector word of macroblock (mx, my): mv[my * mcb_w + mx] */
@@ -656,6 +657,11 @@ __device__ __forceinline__ bool band_item(const ReconJob *__restrict__ jobs, int
         }
         else if (lane == 3) st.mv = reinterpret_cast<const uint32_t *>(base) - row0 * v.mcb_w;
         else if (lane < 7) st.rec[k] = reinterpret_cast<const uint32_t *>(base) - kr0;
+        {   /* chunks of all three classes (lanes 0..2 hold one class each: k == lane there) */
+            const uint32_t n = kc1 - kc0;
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, n, 0) + __shfl_sync(0xFFFFFFFFu, n, 1) + __shfl_sync(0xFFFFFFFFu, n, 2);
+            if (lane == 0) st.next = (int)total;
+        }
         uint32_t tx = fits && lane < 7 ? bytes : 0u;
 #pragma unroll
         for (int d = 4; d; d >>= 1) tx += __shfl_xor_sync(0xFFFFFFFFu, tx, d);
@@ -683,18 +689,28 @@ __device__ __forceinline__ bool band_item(const ReconJob *__restrict__ jobs, int
     }
     const uint32_t raw0 = st.c0[SYM_REC_RAW], raw1 = st.c1[SYM_REC_RAW];
     const uint32_t intra0 = st.c0[SYM_REC_INTRA], intra1 = st.c1[SYM_REC_INTRA];
-    const uint32_t inter0 = st.c0[SYM_REC_INTER], inter1 = st.c1[SYM_REC_INTER];
+    const uint32_t inter0 = st.c0[SYM_REC_INTER];
     if (intra1 > intra0)
     {
         nest_spread<kWarps * 32>(rc_smem + RC_SMEM_TABLE_BYTES, v.portrait != 0);
         __syncthreads();     /* nest table complete */
     }
+    /* The band's chunks are TAKEN by the warps one at a time from a shared counter, the expensive ones first (it counts
+       down: predicted AOT, then intra AOT, then raw; inside a class the chunks are sorted by record length, longest last).
+       Dealt out statically -- warp, warp + kWarps, ... per class -- a band's ~100 chunks of 1 to 6 words per record left the
+       warps up to three chunks apart and 9 % of all warp samples sat at the barrier behind this loop. */
+    const int n_raw = (int)(raw1 - raw0), n_intra = (int)(intra1 - intra0);
 #pragma unroll 1
-    for (uint32_t c = raw0 + warp; c < raw1; c += kWarps) record_chunk<kTile>(v, out, st, SYM_REC_RAW, c, lane);
-#pragma unroll 1
-    for (uint32_t c = intra0 + warp; c < intra1; c += kWarps) record_chunk<kTile>(v, out, st, SYM_REC_INTRA, c, lane);
-#pragma unroll 1
-    for (uint32_t c = inter0 + warp; c < inter1; c += kWarps) record_chunk<kTile>(v, out, st, SYM_REC_INTER, c, lane);
+    for (;;)
+    {
+        int u = 0;
+        if (lane == 0) u = atomicSub(&st.next, 1) - 1;
+        u = __shfl_sync(0xFFFFFFFFu, u, 0);
+        if (u < 0) break;
+        if (u >= n_raw + n_intra) record_chunk<kTile>(v, out, st, SYM_REC_INTER, inter0 + (uint32_t)(u - n_raw - n_intra), lane);
+        else if (u >= n_raw) record_chunk<kTile>(v, out, st, SYM_REC_INTRA, intra0 + (uint32_t)(u - n_raw), lane);
+        else record_chunk<kTile>(v, out, st, SYM_REC_RAW, raw0 + (uint32_t)u, lane);
+    }
     if (kTile)
     {   /* the band leaves as whole picture rows: three bulk stores (shared memory -> picture) */
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     /* this thread's tile writes -> visible to the copies */
