@@ -558,11 +558,26 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, const BandOut 
 #pragma unroll
         for (int r = 0; r < 4; ++r) block_st<kTile>(pic, dst + r * pw, rows[r]);
     }
-    /* motion compensation: two entries per lane and round */
+    /* motion compensation: two entries per lane and round; a last round of at most 32 entries (with sixteen warps per CTA a
+       warp holds ~96: every second round) takes one entry per lane instead of computing the same block twice */
     const uint16_t *q_mc = q + cap - 1;
 #pragma unroll 1
-    for (uint32_t i = lane; i < n_mc; i += 64)
+    for (uint32_t i = lane; i - lane < n_mc; i += 64)
     {
+        if (n_mc - (i - lane) <= 32u)
+        {
+            if (i < n_mc)
+            {
+                uint32_t t0, rows0[4];
+                int plane0, bx0, by0, pw0;
+                coords(q_mc[-(int)i], t0, plane0, bx0, by0);
+                rc_mc_packed(v, plane0, rc_motion_pack(v, plane0, bx0, by0, t0, rc_mv_word(v, plane0, bx0, by0)), rows0);
+                const uint32_t dst0 = block_off<kTile>(v, o, plane0, bx0, by0, pw0);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) block_st<kTile>(pic, dst0 + r * pw0, rows0[r]);
+            }
+            break;
+        }
         const bool two = i + 32 < n_mc;
         uint32_t t0, t1, rows0[4], rows1[4];
         int plane0, bx0, by0, plane1, bx1, by1, pw0, pw1;
