@@ -222,6 +222,11 @@ struct HVQM4Batch
     /* HVQM4_BATCH_TRACE=1: where the submitting thread spends a GPU-entropy step (printed by HVQM4BatchDestroy) */
     double t_trace[4] = {0, 0, 0, 0};               /* waiting for a staging arena, copying pictures, descriptors, enqueueing */
     unsigned n_trace = 0, steps_seen = 0;
+    /* HVQM4_BATCH_TIMELINE=1: device-side timeline of the last GPU-entropy steps -- events on the streams around the upload,
+       the parse kernel, the reconstruction and the read-back of every step (printed by HVQM4BatchDestroy) */
+    struct StepMarks { cudaEvent_t e[7]; };         /* upload begin, upload end, parse end, recon begin, recon end, d2h begin, d2h end */
+    std::vector<StepMarks> marks;
+    long long mark_step = -1;                       /* step whose read-back comes next */
     bool d2h_pending = false;
     cudaEvent_t ev_d2h_mark[2] = {nullptr, nullptr};   /* read-backs issued before step n, n - 1 (batch_wait_readbacks) */
     unsigned step_no = 0;
@@ -393,6 +398,45 @@ static void batch_wait_readbacks(HVQM4Batch *b)
     b->d2h_pending = false;
 }
 
+constexpr int kTimelineSteps = 96;
+static bool timeline_on()
+{
+    static const bool on = getenv("HVQM4_BATCH_TIMELINE") != nullptr;
+    return on;
+}
+/* event k of the step in flight (nullptr: timeline off) */
+static cudaEvent_t timeline_mark(HVQM4Batch *b, long long step, int k, cudaStream_t stream)
+{
+    if (!timeline_on() || step < 0) return nullptr;
+    if (b->marks.empty())
+    {
+        b->marks.resize(kTimelineSteps);
+        for (auto &m : b->marks)
+            for (auto &e : m.e) cudaEventCreate(&e);
+    }
+    cudaEvent_t e = b->marks[(size_t)(step % kTimelineSteps)].e[k];
+    cudaEventRecord(e, stream);
+    return e;
+}
+static void timeline_print(HVQM4Batch *b)
+{
+    if (b->marks.empty() || b->steps_seen < 8) return;
+    cudaDeviceSynchronize();
+    const long long last = (long long)b->steps_seen - 1, first = last - 39 > 0 ? last - 39 : 0;
+    if (last - first >= kTimelineSteps) return;
+    cudaEvent_t t0 = b->marks[(size_t)(first % kTimelineSteps)].e[0];
+    fprintf(stderr, "hvqm4_b200: device timeline of GPU-entropy steps %lld..%lld, ms since the first upload began\n"
+                    "  step   upload          parse end   recon            read-back\n", first, last);
+    for (long long s = first; s <= last; ++s)
+    {
+        float t[7];
+        bool ok = true;
+        for (int k = 0; k < 7; ++k) ok = ok && cudaEventElapsedTime(&t[k], t0, b->marks[(size_t)(s % kTimelineSteps)].e[k]) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); continue; }
+        fprintf(stderr, "  %4lld   %7.2f-%7.2f   %7.2f   %7.2f-%7.2f   %7.2f-%7.2f\n", s, t[0], t[1], t[2], t[3], t[4], t[5], t[6]);
+    }
+}
+
 static bool arena_reserve(HVQM4Batch *b, Arena &a, size_t need)
 {
     if (need <= a.cap) return true;
@@ -484,6 +528,9 @@ H4_API void HVQM4BatchDestroy(HVQM4Batch *b)
     if (!b) return;
     cudaSetDevice(b->device);
     cudaDeviceSynchronize();
+    timeline_print(b);
+    for (auto &m : b->marks)
+        for (auto &e : m.e) cudaEventDestroy(e);
     if (b->n_trace && getenv("HVQM4_BATCH_TRACE"))
         fprintf(stderr, "hvqm4_b200: %u GPU-entropy steps, submitting thread per step: arena wait %.2f ms, picture copies %.2f ms, descriptors %.2f ms, enqueue %.2f ms\n",
                 b->n_trace, 1e3 * b->t_trace[0] / b->n_trace, 1e3 * b->t_trace[1] / b->n_trace, 1e3 * b->t_trace[2] / b->n_trace, 1e3 * b->t_trace[3] / b->n_trace);
@@ -669,7 +716,10 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
     /* from here on work is queued on the arena: it counts as in flight whatever happens next */
     a.in_flight = true;
     cudaEventRecord(a.consumed, sp);
+    const long long tl_step = (long long)b->steps_seen - 1;
+    timeline_mark(b, tl_step, 0, sp);
     if (!cuda_ok(cudaMemcpyAsync(a.d, a.h, gather ? upload_bytes : total, cudaMemcpyHostToDevice, sp), "cudaMemcpyAsync(H2D)")) return HVQM4_ERR_CUDA;
+    timeline_mark(b, tl_step, 1, sp);
     if (gather)
     {
         const int grc = hvqm4_dev_gather(reinterpret_cast<const H4Gather *>(a.d + pics_bytes + jobs_bytes), n, a.d, sp);
@@ -687,8 +737,11 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
                                      b->d_blobs + (size_t)b->cur * b->blobs_cap, b->d_blob_used + par, (unsigned long long)b->blobs_cap,
                                      d_jobs, b->d_eerrors, sp);
     cudaEventRecord(b->ev_parse[par], sp);
+    timeline_mark(b, tl_step, 2, sp);
     cudaStreamWaitEvent(b->s_comp, b->ev_parse[par], 0);
     batch_wait_readbacks(b);
+    timeline_mark(b, tl_step, 3, b->s_comp);
+    b->mark_step = tl_step;
     if (rc == 0)
     {
         ++g_launches;
@@ -707,6 +760,7 @@ static int batch_decode_gpu_entropy(HVQM4Batch *b, int n, const int32_t *stream_
     }
     cudaEventRecord(a.consumed, b->s_comp);
     cudaEventRecord(b->ev_kernel, b->s_comp);
+    timeline_mark(b, tl_step, 4, b->s_comp);
     a.in_flight = true;
     b->cur = (b->cur + 1) % kArenas;
     b->stats[0] += n;
@@ -958,10 +1012,12 @@ H4_API int HVQM4BatchReadFramesAsync(HVQM4Batch *b, int n, const int32_t *stream
     {
         cudaSetDevice(b->device);
         if (!b->d2h_pending) cudaStreamWaitEvent(b->s_d2h, b->ev_kernel, 0);
+        timeline_mark(b, b->mark_step, 5, b->s_d2h);
         if (!cuda_ok(cudaMemcpy2DAsync(host_base, host_stride, b->surface(stream_ids[0], b->st[stream_ids[0]].last), kSurfaces * b->surf_stride,
                                        b->frame_bytes, (size_t)n, cudaMemcpyDeviceToHost, b->s_d2h), "cudaMemcpy2DAsync(D2H)"))
             return HVQM4_ERR_CUDA;
         cudaEventRecord(b->ev_d2h, b->s_d2h);
+        timeline_mark(b, b->mark_step, 6, b->s_d2h);
         b->d2h_pending = true;
         return HVQM4_OK;
     }
