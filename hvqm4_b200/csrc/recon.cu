@@ -400,6 +400,12 @@ recon_record_kernel(const ReconJob *__restrict__ jobs, int n_jobs, uint32_t cta_
  * from the back, positions from a ballot -- and then drains 32 entries of ONE class at a time.
  * Wide pictures are walked in column tiles of kTileMcbs macroblocks so that the queue has a
  * fixed upper size.
+ *
+ * Two variants (template parameter kTile).  Plain: finished blocks are stored straight into the picture.  Tile (the
+ * default wherever two CTAs of it fit an SM): the band is assembled in shared memory -- same layout as its part of the
+ * picture -- and leaves through three bulk stores; sixteen warps per CTA, 16-bit queue entries in the space of the nest
+ * table, record chunks taken from a shared counter.  What the gathers of both phases get as L1 decides the speed
+ * (last table), so every byte of shared memory here is accounted for.
  * ------------------------------------------------------------------------------------------ */
 #ifndef HVQM4_BAND_WARPS
 #define HVQM4_BAND_WARPS 8
@@ -414,7 +420,7 @@ constexpr int kBandWarps = HVQM4_BAND_WARPS;     /* plain band kernel: three or 
    16 warps 1.360 M frames/s (128 pictures: 1.08 -> 1.14 M); before that, at 96+ KB per CTA: 8 warps 1.09 M, 10 1.16 M,
    12 1.23 M, 14 and 16 one CTA per SM.  Plain kernel 1.20-1.22 M. */
 constexpr int kBandTileWarps = HVQM4_BAND_TILE_WARPS;
-/* warps per CTA of a band kernel instantiation: twelve for the 8-row tile variant (two CTAs per SM), eight otherwise */
+/* warps per CTA of a band kernel instantiation: kBandTileWarps for the 8-row tile variant (two CTAs per SM), eight otherwise */
 __host__ __device__ constexpr int band_warps(bool tile, int rows) { return tile && rows == 8 ? kBandTileWarps : kBandWarps; }
 constexpr int kTileMcbs = 128;
 constexpr int kBandRows = 8;   /* macroblock rows per CTA of the band kernel = kBandRows record bands of symbuf.h */
