@@ -285,7 +285,7 @@ def main():
     ap.add_argument("--host-threads", type=int, default=0)
     ap.add_argument("--host-share", type=int, default=-1,
                     help="end to end, GPU entropy stage: streams per GPU whose pictures the host threads parse next to the parse kernel "
-                         "(HVQM4BatchSetHostShare); -1 = one stream in eight per 16 host threads at one rank, none beyond")
+                         "(HVQM4BatchSetHostShare); -1 = one stream in eight per 16 host threads (at most one in eight) at one rank, none beyond")
     ap.add_argument("--ref-seconds", type=float, default=12.0, help="CPU seconds per process for the reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -503,7 +503,7 @@ def main():
         # B200 + 16 cores, profiles/r02_host_share_ab.txt: 106 k frames/s with no share, 110-111 k with 64..160 of 1 024 streams,
         # 104 k with 192, 87 k with 256).  With several ranks per box the host cores are fewer per GPU and the bitstreams are
         # fetched by the GPU (--gather): two ranks with 12 cores each 198 k with no share, 197 k with 96 streams: no share.
-        share = args.host_share if args.host_share >= 0 else (S * threads // 128 if world == 1 else 0)
+        share = args.host_share if args.host_share >= 0 else (min(S * threads // 128, S // 8) if world == 1 else 0)
         share = max(0, min(S, share))
         gb = api.Batch(S, W, H, 15, device=local, host_threads=threads, gpu_entropy=True, host_share=share)
         e2e = measure_e2e(gb, 12.0, "gpu (one warp per picture)" + (f" + host threads for {share} of {S} streams" if share else ""))
