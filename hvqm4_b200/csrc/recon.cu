@@ -897,10 +897,12 @@ int launch_band(const ReconJob *d_jobs, int n_jobs, int n_bands, int mcb_w, cuda
     return launch_band_plain<kMinBlocks, false, kBandRows>(d_jobs, items, n_bands, cap, band_stage_bytes(mcb_w, kBandRows), band_plain_smem(mcb_w, kBandRows), stream);
 }
 
-/* does the tile variant of the band kernel fit `ctas` times into an SM for pictures this wide? */
+/* does the tile variant of the band kernel fit `ctas` times into an SM for pictures this wide -- and leave the gathers an L1
+   worth having?  Up to the 196 KB carve-out (60 KB of L1) it is at least as fast as the plain kernel; in the 228 KB one
+   (28 KB of L1) it loses a third (profiles/r02_queue16_ab.txt).  640-wide pictures: 2 x 80 KB, the 164 KB carve-out. */
 static bool band_tile_fits(int mcb_w, int rows, int ctas)
 {
-    return band_tile_smem(mcb_w, rows) + 1024 <= 227 * 1024 / ctas;
+    return (band_tile_smem(mcb_w, rows) + 1024) * ctas <= 196 * 1024;
 }
 
 extern "C" int hvqm4_sweep_supported(int mcb_w, int mcb_h);
