@@ -492,7 +492,8 @@ __device__ __forceinline__ void band_map_tile(const ReconView &v, const BandOut 
     /* classify: row tasks = 2 luma block rows per macroblock row, then the U rows, then the V rows.
        Queue entry (16 bits): [7:0] block x inside the column tile, [9:8] which of the warp's tasks, [10] the reference is
        the future picture -- everything else a drain needs follows from the task */
-    const int mrows = row1 - row0, n_tasks = mrows * 4;
+    static_assert(kTileMcbs * 2 <= 256, "a queue entry holds the block x inside the column tile in 8 bits");
+    const int mrows = row1 - row0, n_tasks = mrows * 4;      /* at most 4 per warp: band_item asserts it */
     uint32_t slot = 0;
 #pragma unroll 1
     for (int task = warp; task < n_tasks; task += kWarps, slot += 1u << 8)
@@ -612,6 +613,7 @@ template <bool kTile, int kRows, int kWarps>
 __device__ __forceinline__ bool band_item(const ReconJob *__restrict__ jobs, int job, int band, uint16_t *queue, int queue_cap, uint32_t tile_off,
                                           uint32_t stage_off, uint32_t stage_cap, uint32_t stage_phase)
 {
+    static_assert(kRows * 4 <= 4 * kWarps, "a queue entry names one of at most four row tasks of its warp (band_map_tile)");
     ReconView &vw = *reinterpret_cast<ReconView *>(rc_smem + RC_SMEM_VIEW_OFF);
     BandStage &st = *reinterpret_cast<BandStage *>(rc_smem + kBandStageOff);
     if (threadIdx.x == 0)
