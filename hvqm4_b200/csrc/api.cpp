@@ -162,6 +162,52 @@ private:
 
 }  // namespace
 
+/* Device -> host copy of one frame that also works when the destination STRADDLES page-locked and pageable memory: a heap
+   block next to a range registered with HVQM4HostRegister shares the range's first or last page (registration is by
+   page), and cudaMemcpyAsync refuses such a destination with cudaErrorInvalidValue.  Then the frame takes the detour over
+   a page-locked bounce buffer of the library (synchronous: the case is rare and only costs time). */
+struct Bounce
+{
+    uint8_t *h = nullptr;
+    size_t cap = 0;
+    bool reserve(size_t bytes)
+    {
+        if (bytes <= cap) return true;
+        if (h) cudaFreeHost(h);
+        h = nullptr;
+        cap = 0;
+        if (!cuda_ok(cudaHostAlloc((void **)&h, bytes, cudaHostAllocDefault), "cudaHostAlloc(bounce)")) return false;
+        cap = bytes;
+        return true;
+    }
+    void release() { if (h) cudaFreeHost(h); h = nullptr; cap = 0; }
+};
+static bool copy_frame_to_host(void *dst, const void *src, size_t bytes, cudaStream_t stream, Bounce *bounce, const char *what)
+{
+    const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) return true;
+    if (e != cudaErrorInvalidValue) return cuda_ok(e, what);
+    cudaGetLastError();
+    if (!cuda_ok(cudaStreamSynchronize(stream), what) || !bounce->reserve(bytes)) return false;
+    if (!cuda_ok(cudaMemcpyAsync(bounce->h, src, bytes, cudaMemcpyDeviceToHost, stream), what) ||
+        !cuda_ok(cudaStreamSynchronize(stream), what))
+        return false;
+    memcpy(dst, bounce->h, bytes);
+    return true;
+}
+
+/* the same for an application frame on its way to the device (reference frames of the SDK entry points, RGB conversion) */
+static bool copy_frame_to_device(void *dst, const void *src, size_t bytes, cudaStream_t stream, Bounce *bounce, const char *what)
+{
+    const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) return true;
+    if (e != cudaErrorInvalidValue) return cuda_ok(e, what);
+    cudaGetLastError();
+    if (!cuda_ok(cudaStreamSynchronize(stream), what) || !bounce->reserve(bytes)) return false;      /* nothing reads the buffer any more */
+    memcpy(bounce->h, src, bytes);
+    return cuda_ok(cudaMemcpyAsync(dst, bounce->h, bytes, cudaMemcpyHostToDevice, stream), what) && cuda_ok(cudaStreamSynchronize(stream), what);
+}
+
 /* ====================================================================== batch runtime */
 
 struct StreamState
@@ -240,6 +286,7 @@ struct HVQM4Batch
     std::vector<uint8_t> seen;
 
     /* GPU entropy stage (HVQM4BatchSetEntropyMode): per-stream parser state, blob arena, counters */
+    Bounce bounce;                 /* copy_frame_to_host */
     bool gpu_entropy = false;
     int host_share = 0;        /* GPU entropy mode: streams [0, host_share) are parsed by the host threads (HVQM4BatchSetHostShare) */
     uint8_t *d_estate = nullptr;
@@ -528,6 +575,7 @@ H4_API void HVQM4BatchDestroy(HVQM4Batch *b)
     if (!b) return;
     cudaSetDevice(b->device);
     cudaDeviceSynchronize();
+    b->bounce.release();
     timeline_print(b);
     for (auto &m : b->marks)
         for (auto &e : m.e) cudaEventDestroy(e);
@@ -991,7 +1039,7 @@ H4_API int HVQM4BatchReadFrameAsync(HVQM4Batch *b, int stream_id, void *host_dst
     if (!src || !host_dst) return HVQM4_ERR_ARGUMENT;
     cudaSetDevice(b->device);
     if (!b->d2h_pending) cudaStreamWaitEvent(b->s_d2h, b->ev_kernel, 0);
-    if (!cuda_ok(cudaMemcpyAsync(host_dst, src, b->frame_bytes, cudaMemcpyDeviceToHost, b->s_d2h), "cudaMemcpyAsync(D2H)")) return HVQM4_ERR_CUDA;
+    if (!copy_frame_to_host(host_dst, src, b->frame_bytes, b->s_d2h, &b->bounce, "cudaMemcpyAsync(D2H)")) return HVQM4_ERR_CUDA;
     cudaEventRecord(b->ev_d2h, b->s_d2h);
     b->d2h_pending = true;
     return HVQM4_OK;
@@ -1013,8 +1061,17 @@ H4_API int HVQM4BatchReadFramesAsync(HVQM4Batch *b, int n, const int32_t *stream
         cudaSetDevice(b->device);
         if (!b->d2h_pending) cudaStreamWaitEvent(b->s_d2h, b->ev_kernel, 0);
         timeline_mark(b, b->mark_step, 5, b->s_d2h);
-        if (!cuda_ok(cudaMemcpy2DAsync(host_base, host_stride, b->surface(stream_ids[0], b->st[stream_ids[0]].last), kSurfaces * b->surf_stride,
-                                       b->frame_bytes, (size_t)n, cudaMemcpyDeviceToHost, b->s_d2h), "cudaMemcpy2DAsync(D2H)"))
+        const cudaError_t e2 = cudaMemcpy2DAsync(host_base, host_stride, b->surface(stream_ids[0], b->st[stream_ids[0]].last), kSurfaces * b->surf_stride,
+                                                 b->frame_bytes, (size_t)n, cudaMemcpyDeviceToHost, b->s_d2h);
+        if (e2 == cudaErrorInvalidValue)
+        {   /* a destination that straddles page-locked and pageable memory (copy_frame_to_host): frame by frame */
+            cudaGetLastError();
+            for (int i = 0; i < n; ++i)
+                if (!copy_frame_to_host(static_cast<uint8_t *>(host_base) + (size_t)i * host_stride, b->surface(stream_ids[i], b->st[stream_ids[i]].last),
+                                        b->frame_bytes, b->s_d2h, &b->bounce, "cudaMemcpyAsync(D2H)"))
+                    return HVQM4_ERR_CUDA;
+        }
+        else if (!cuda_ok(e2, "cudaMemcpy2DAsync(D2H)"))
             return HVQM4_ERR_CUDA;
         cudaEventRecord(b->ev_d2h, b->s_d2h);
         timeline_mark(b, b->mark_step, 6, b->s_d2h);
@@ -1078,8 +1135,16 @@ H4_API int HVQM4BatchReadFramesRGBAsync(HVQM4Batch *b, int n, const int32_t *str
     cudaEventRecord(b->ev_rgb, b->s_comp);
     cudaEventRecord(b->ev_kernel, b->s_comp);
     cudaStreamWaitEvent(b->s_d2h, b->ev_rgb, 0);
-    if (!cuda_ok(cudaMemcpy2DAsync(host_base, host_stride, b->d_rgb, rgb_bytes, rgb_bytes, (size_t)n, cudaMemcpyDeviceToHost, b->s_d2h),
-                 "cudaMemcpy2DAsync(D2H rgb)"))
+    const cudaError_t e2 = cudaMemcpy2DAsync(host_base, host_stride, b->d_rgb, rgb_bytes, rgb_bytes, (size_t)n, cudaMemcpyDeviceToHost, b->s_d2h);
+    if (e2 == cudaErrorInvalidValue)
+    {   /* destination straddling page-locked and pageable memory (copy_frame_to_host) */
+        cudaGetLastError();
+        for (int i = 0; i < n; ++i)
+            if (!copy_frame_to_host(static_cast<uint8_t *>(host_base) + (size_t)i * host_stride, b->d_rgb + (size_t)i * rgb_bytes, rgb_bytes, b->s_d2h,
+                                    &b->bounce, "cudaMemcpyAsync(D2H rgb)"))
+                return HVQM4_ERR_CUDA;
+    }
+    else if (!cuda_ok(e2, "cudaMemcpy2DAsync(D2H rgb)"))
         return HVQM4_ERR_CUDA;
     cudaEventRecord(b->ev_d2h, b->s_d2h);
     b->d2h_pending = true;
@@ -1189,6 +1254,7 @@ struct Compat
     int mcb_w = 0, mcb_h = 0;
     int band_rows = 8;                              /* macroblock rows per record band of the stream (symbuf.h) */
     uint8_t *h_blob = nullptr, *d_blob = nullptr;   /* job descriptor (256 B) + blob */
+    Bounce bounce;                                  /* copy_frame_to_host / copy_frame_to_device */
     uint8_t *d_rgb = nullptr;                       /* HVQM4ConvertRGB staging */
     size_t blob_cap = 0;
     Twin twin[kTwins];
@@ -1252,7 +1318,7 @@ uint8_t *resolve(Compat *c, void *p, bool is_reference)
         const uint64_t print = twin_print(p, c->frame_bytes);
         if (fresh || !slot->printed || slot->print != print)
         {   /* unknown, or the application has written into the frame since the library last saw it */
-            if (!cuda_ok(cudaMemcpyAsync(slot->dev, p, c->frame_bytes, cudaMemcpyHostToDevice, c->stream), "upload reference frame")) return nullptr;
+            if (!copy_frame_to_device(slot->dev, p, c->frame_bytes, c->stream, &c->bounce, "upload reference frame")) return nullptr;
             slot->print = print;
             slot->printed = true;
         }
@@ -1337,7 +1403,7 @@ void compat_decode(SeqObj *so, int type, const uint8_t *frame, void *present, vo
         ok = rc == 0 || cuda_ok((cudaError_t)rc, "recon kernel launch");
     }
     if (ok && !is_device_ptr(present))
-        ok = cuda_ok(cudaMemcpyAsync(present, d_present, c->frame_bytes, cudaMemcpyDeviceToHost, c->stream), "download frame");
+        ok = copy_frame_to_host(present, d_present, c->frame_bytes, c->stream, &c->bounce, "download frame");
     const auto t3 = now();
     ok = ok && cuda_ok(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
     if (!ok) c->errors |= HVQM4_ERR_CUDA;
@@ -1425,6 +1491,7 @@ H4_API void HVQM4ReleaseBuffer(SeqObj *seqobj)
     for (auto &t : c->twin)
         if (t.dev) cudaFree(t.dev);
     if (c->h_blob) cudaFreeHost(c->h_blob);
+    c->bounce.release();
     if (c->d_blob) cudaFree(c->d_blob);
     if (c->d_rgb) cudaFree(c->d_rgb);
     h4e_seq_destroy(c->seq);
@@ -1488,7 +1555,7 @@ H4_API int HVQM4ConvertRGB(SeqObj *seqobj, const void *frame, void *rgb)
     if (!is_device_ptr(frame))
     {
         src = c->d_rgb + in_off;
-        ok = cuda_ok(cudaMemcpyAsync(c->d_rgb + in_off, frame, c->frame_bytes, cudaMemcpyHostToDevice, c->stream), "upload frame");
+        ok = copy_frame_to_device(c->d_rgb + in_off, frame, c->frame_bytes, c->stream, &c->bounce, "upload frame");
     }
     const uint8_t **d_ptr = reinterpret_cast<const uint8_t **>(c->d_rgb + ptr_off);
     ok = ok && cuda_ok(cudaMemcpyAsync((void *)d_ptr, &src, sizeof src, cudaMemcpyHostToDevice, c->stream), "cudaMemcpyAsync");
@@ -1499,7 +1566,7 @@ H4_API int HVQM4ConvertRGB(SeqObj *seqobj, const void *frame, void *rgb)
         ok = rc == 0 || cuda_ok((cudaError_t)rc, "yuv2rgb kernel launch");
         if (rc == 0) ++g_launches;
     }
-    ok = ok && cuda_ok(cudaMemcpyAsync(rgb, c->d_rgb, rgb_bytes, cudaMemcpyDeviceToHost, c->stream), "download rgb");
+    ok = ok && copy_frame_to_host(rgb, c->d_rgb, rgb_bytes, c->stream, &c->bounce, "download rgb");
     ok = ok && cuda_ok(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
     return ok ? HVQM4_OK : HVQM4_ERR_CUDA;
 }

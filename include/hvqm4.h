@@ -262,7 +262,12 @@ void HVQM4HostFree(void *p);
    (frames[i] is otherwise only read during the call): they must stay unmodified until
    HVQM4BatchSync returns, or until the step four submissions later has been submitted (the ring of
    staging arenas).  HVQM4HostUnregister waits for the device to go idle first; unregister before
-   the memory is freed.  Returns HVQM4_OK or error bits. */
+   the memory is freed.  Returns HVQM4_OK or error bits.
+   PAGES: registration is by page, so other heap blocks of the application may share the first or last page of a
+   range and thereby become partly page-locked.  CUDA refuses a copy whose host side straddles page-locked and pageable
+   memory; the library's own read-backs and uploads (HVQM4BatchReadFrame*, the SDK entry points with host frames,
+   HVQM4ConvertRGB) take such a frame over an internal page-locked bounce buffer instead of failing.  Page-aligned,
+   page-padded ranges avoid the detour. */
 int HVQM4HostRegister(void *ptr, size_t bytes);
 int HVQM4HostUnregister(void *ptr);
 

@@ -741,3 +741,37 @@ def test_registered_host_memory_is_gathered_by_the_gpu(native_lib, oracle, host_
         # every page was released with its last user: the whole image can be registered again
         assert lib.HVQM4HostRegister(base, len(blob)) == 0
         assert lib.HVQM4HostUnregister(base) == 0
+
+
+def test_read_back_into_memory_that_shares_a_page_with_a_registered_range(native_lib, oracle):
+    """HVQM4HostRegister pins whole pages, so a heap block next to a registered range shares the range's last page, and
+    cudaMemcpyAsync refuses a destination that straddles page-locked and pageable memory (seen as a 1-in-17 failure of
+    the test above, whenever Python happened to put a read-back buffer there).  The library then takes the frame over
+    its own page-locked bounce buffer: single-frame and pitched multi-frame read-backs into exactly such a destination."""
+    n = 6
+    data = synth.generate(320, 240, 15, "I", 1, seed=8801, profile=0)
+    want = [md5(yuv) for _, _, _, yuv in oracle.PortDecoder(data).frames()][0]
+    fr = native_lib.parse_file(data)[1][0]
+    fb = 320 * 240 * 3 // 2
+    arena = ctypes.create_string_buffer(len(data) + (n + 2) * fb + 4 * 4096)
+    base = (ctypes.addressof(arena) + 4095) & ~4095
+    length = ((len(data) + 4095) & ~4095) + 100              # the range ends 100 bytes into its last page
+    ctypes.memmove(base, data, len(data))
+    lib = native_lib.lib()
+    assert lib.HVQM4HostRegister(base, length) == 0
+    dst = base + ((length + 4095) & ~4095) - 2000            # begins in that page, ends n frames further on in pageable memory
+    assert dst >= base + length
+    batch = native_lib.Batch(n, 320, 240, 15, gpu_entropy=True)
+    try:
+        batch.decode(list(range(n)), [fr.frame_type] * n, [base + fr.offset] * n, [fr.bytes] * n)
+        batch.sync()
+        assert lib.HVQM4BatchReadFrame(batch._h, 0, ctypes.c_void_p(dst)) == 0
+        assert md5(ctypes.string_at(dst, fb)) == want
+        ctypes.memset(dst, 0, n * fb)
+        ids = (ctypes.c_int32 * n)(*range(n))
+        batch.read_frames_async(ids, n, dst, fb)
+        batch.sync()
+        assert all(md5(ctypes.string_at(dst + i * fb, fb)) == want for i in range(n))
+    finally:
+        batch.close()
+        assert lib.HVQM4HostUnregister(base) == 0
